@@ -1,0 +1,234 @@
+/*
+ * b200rl.h -- C ABI of libb200rl.so: the PPO data path of rl-algo-impls as hand-written
+ * sm_100a CUDA kernels.
+ *
+ * The reference (rl-algo-impls) is pure Python and has no FFI of its own; each entry point
+ * below replaces one eager numpy / torch op sequence of the reference, cited as file:line
+ * relative to the reference root.  The reference-side binding (a ctypes stub) is shown in
+ * INTEGRATION.md; this repo's own binding is rl_algo_impls_b200/_lib.py.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on the current device unless the name ends in _host;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *    synchronises the device and never allocates or frees memory: scratch space is a caller
+ *    buffer sized by the matching *_workspace_bytes();
+ *  - returns 0 on success, B200RL_EINVAL (-1) for a bad argument, B200RL_EUNSUPPORTED (-2)
+ *    for a shape/dtype this build has no kernel for, B200RL_ECUDA (-3) for a CUDA launch
+ *    error; b200rl_last_error() returns the thread-local message;
+ *  - there is no CPU path: without a CUDA device every compute call fails with B200RL_ECUDA.
+ *  - layouts are the reference's flattened rollout layouts: time-major [T, N, ...] for the
+ *    rollout buffer (flat sample = t*N + n, rollout/rollout.py:120-121) and row-major
+ *    [B, ...] for minibatches.
+ */
+#ifndef B200RL_H
+#define B200RL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RL_VERSION 100 /* major*100 + minor */
+
+#define B200RL_OK 0
+#define B200RL_EINVAL (-1)
+#define B200RL_EUNSUPPORTED (-2)
+#define B200RL_ECUDA (-3)
+
+#define B200RL_MAX_HEADS 16       /* action planes per cell (A) */
+#define B200RL_MAX_VALUE_HEADS 32 /* value / reward heads (V) */
+#define B200RL_MAX_GATHER 16      /* tensors per gather call */
+
+/* element types of the tensors whose dtype the reference lets vary */
+#define B200RL_F32 0
+#define B200RL_BF16 1
+#define B200RL_U8 2
+#define B200RL_I32 3
+#define B200RL_I64 4
+
+typedef void* b200rl_stream_t; /* cudaStream_t */
+
+int b200rl_version(void);
+const char* b200rl_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  GAE(lambda) reverse-time scan + returns.
+ * Replaces shared/gae.py:97-124 (compute_advantages) and rollout/vec_rollout.py:88 (returns).
+ *   rewards, values, advantages, returns : [T, N, V] f32     (V == 1: [T, N])
+ *   episode_starts                       : [T, N] u8 (bool)
+ *   next_episode_starts                  : [N] u8,  next_values : [N, V] f32
+ *   gamma_host, gae_lambda_host          : HOST arrays of V doubles
+ *   gamma_is_scalar: non-zero when the reference was given a Python-float gamma (a weak
+ *     scalar: gamma*next_value is rounded to f32, gae.py:121); zero for a per-head ndarray
+ *     gamma (product in f64).  Either way the carry is f64 and the store f32, like numpy.
+ * Bit-exact with the reference.  `returns` may be NULL.
+ */
+int b200rl_gae_scan_f32(const float* rewards, const float* values, const uint8_t* episode_starts,
+                        const uint8_t* next_episode_starts, const float* next_values,
+                        const double* gamma_host, const double* gae_lambda_host, int gamma_is_scalar,
+                        float* advantages, float* returns, int64_t T, int64_t N, int64_t V,
+                        b200rl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  per-minibatch advantage moments and normalisation.  Replaces ppo/ppo.py:307-318.
+ * adv_mode:
+ *   0 none;  1 (A - mean(0)) / (std(0) + 1e-8) per head (unbiased std);  2 A / (std(0) + 1e-8);
+ *   3 contract with weights first, then scalar (A - mean) / (std + 1e-8)
+ *     (normalize_advantages_after_scaling).
+ * In modes 0-2 the [V] result is contracted with `weights_host` when it is non-NULL
+ * (multi_reward_weights, ppo.py:317-318); V > 1 without weights is only legal when the
+ * consumer wants [B, V] back (b200rl_adv_normalize_f32 with out_v == V).
+ *
+ * b200rl_adv_moments_f64: moments[0..Vm) = sum, moments[Vm..2Vm) = sum of squares, moments[2Vm] = B,
+ *   over rows idx[0..B) of adv[., V] (idx NULL: rows 0..B); Vm = 1 in mode 3 else V.  f64
+ *   accumulation, deterministic reduction order.  The caller may all-reduce `moments`
+ *   across ranks before normalising (exact global-minibatch statistics).
+ */
+size_t b200rl_adv_moments_workspace_bytes(int64_t B, int64_t V);
+int b200rl_adv_moments_f64(const float* adv, const int64_t* idx, int64_t B, int64_t V, int adv_mode,
+                           const float* weights_host, double* moments, void* workspace,
+                           size_t workspace_bytes, b200rl_stream_t stream);
+int b200rl_adv_normalize_f32(const float* adv, const int64_t* idx, int64_t B, int64_t V, int adv_mode,
+                             const float* weights_host, const double* moments, float* out, int64_t out_v,
+                             b200rl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  minibatch row gather.  Replaces rollout/rollout.py:56-69 (Batch.__getitem__) and
+ * shared/tensor_utils.py:66-72: dst[t][b, :] = src[t][idx[b], :] for n_tensors tensors in one
+ * launch.  src_host / dst_host / row_bytes_host are HOST arrays of device pointers / sizes.
+ * Rows whose size and base addresses are 16-byte multiples move through shared memory with
+ * bulk async copies; other rows take a scalar path.  idx is int64 [B] on the device.
+ */
+int b200rl_gather_rows(const void* const* src_host, void* const* dst_host, const int64_t* row_bytes_host,
+                       int n_tensors, const int64_t* idx, int64_t B, int64_t n_src_rows,
+                       b200rl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * PPO per-sample loss terms, shared by every K4 variant.  Replaces ppo/ppo.py:326-361,373-374
+ * and the stats of :379-409.
+ *   old_logp [B]; adv [B, adv_v] raw advantages; moments from K2 (NULL when adv_mode == 0);
+ *   adv_weights_host [adv_v] or NULL; old_values, returns, new_values, dvalues: [B, V] f32.
+ *   clip_range_vf < 0 disables value clipping.  vf_coef_host [V].  loss_scale multiplies the
+ *   total loss and every gradient (1 / num_minibatches under gradient accumulation).
+ *   kl_cutoff < 0 disables the cut-off; pi_coef_state is a device float (1 or 0) that the
+ *   scalar kernel reads, zeroes when approx_kl > kl_cutoff and leaves sticky (ppo.py:279,354).
+ * stats_out (device, f32): [0] loss [1] pi_loss [2] entropy_loss [3] approx_kl [4] clipped_frac
+ *   [5 .. 5+V) v_loss per head (after halving) [5+V .. 5+2V) val_clipped_frac.
+ */
+typedef struct b200rl_ppo_args {
+  const float* old_logp;
+  const float* adv;
+  const double* moments;
+  const float* adv_weights_host;
+  int64_t adv_v;
+  int adv_mode;
+  const float* old_values;
+  const float* returns;
+  const float* new_values;
+  float* dvalues;
+  int64_t V;
+  double clip_range;    /* Python float: 1 - clip_range is formed in double, then rounded to f32 */
+  double clip_range_vf; /* < 0: value clipping off */
+  const float* vf_coef_host;
+  float ent_coef;
+  float pi_coef;
+  int vf_halving;
+  float loss_scale;
+  float* stats_out;
+} b200rl_ppo_args;
+
+#define B200RL_PPO_NSTATS(V) (5 + 2 * (V))
+
+/* Per-sample stage alone (distribution-level path): given new_logp [B] and entropy
+ * [B, ent_d] produced by any differentiable head, writes dlogp [B], dentropy [B, ent_d],
+ * dvalues and stats.  Honours kl_cutoff without a host sync (two-phase inside one launch). */
+size_t b200rl_ppo_workspace_bytes(int64_t B, int64_t V);
+int b200rl_ppo_scalar_loss_f32(const float* new_logp, const float* entropy, int64_t ent_d, int64_t B,
+                               const b200rl_ppo_args* args, float kl_cutoff, float* pi_coef_state,
+                               float* dlogp, float* dentropy, void* workspace, size_t workspace_bytes,
+                               b200rl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4a  (Masked)Categorical over the last dim.  Replaces shared/actor/categorical.py:12-54 and
+ * torch.distributions.Categorical log_prob / entropy and their autograd backward.
+ *   logits [R, n] f32; mask [R, n] u8 or NULL; actions [R] (act_dtype U8/I32/I64).
+ * fwd: logp [R], entropy [R].   bwd: dlogits [R, n] from dlogp [R], dentropy [R].
+ * fused: PPO loss forward + backward in one launch (R == B): dlogits, dvalues, stats.
+ */
+int b200rl_categorical_fwd_f32(const float* logits, const uint8_t* mask, const void* actions, int act_dtype,
+                               int64_t R, int64_t n, float* logp, float* entropy, b200rl_stream_t stream);
+int b200rl_categorical_bwd_f32(const float* logits, const uint8_t* mask, const void* actions, int act_dtype,
+                               int64_t R, int64_t n, const float* dlogp, const float* dentropy,
+                               float* dlogits, b200rl_stream_t stream);
+int b200rl_ppo_categorical_loss_f32(const float* logits, const uint8_t* mask, const void* actions,
+                                    int act_dtype, int64_t B, int64_t n, const b200rl_ppo_args* args,
+                                    float* dlogits, void* workspace, size_t workspace_bytes,
+                                    b200rl_stream_t stream);
+
+/* K4b  diagonal Gaussian.  Replaces shared/actor/gaussian.py:11-16,42-45 (+ torch Normal).
+ *   mu [B, D], log_std [D], actions [B, D] f32.  logp summed over D; entropy [B, D] (not
+ *   summed, as the reference), so entropy_loss averages over B*D.
+ * fused: dmu [B, D], dlog_std [D], dvalues, stats. */
+int b200rl_gaussian_fwd_f32(const float* mu, const float* log_std, const float* actions, int64_t B, int64_t D,
+                            float* logp, float* entropy, b200rl_stream_t stream);
+int b200rl_ppo_gaussian_loss_f32(const float* mu, const float* log_std, const float* actions, int64_t B,
+                                 int64_t D, const b200rl_ppo_args* args, float* dmu, float* dlog_std,
+                                 void* workspace, size_t workspace_bytes, b200rl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4c  GridNet per-cell MultiDiscrete heads (+ pick_position categoricals over the cells).
+ * Replaces shared/actor/gridnet.py:38-193 over shared/actor/categorical.py:12-54.
+ *   logits  [B, HW, S + n_pick]  f32 or bf16 (logits_dtype); S = sum(nvec)
+ *   mask    [B, HW, S] u8;  pick_mask [B, n_pick, HW] u8 (NULL when n_pick == 0)
+ *   actions [B, HW, A] (act_dtype U8/I32/I64); pick_actions [B, n_pick] (pick_dtype I32/I64)
+ *   nvec_host [A]; gate_ref_host / gate_val_host [A]: head h only counts where
+ *     actions[.., gate_ref[h]] == gate_val[h] (gate_ref[h] < 0: ungated)  (gridnet.py:119-127)
+ * Mask semantics are the reference's, bit for bit: masked logits become finfo.min; a row
+ * with no valid entry has log-prob 0, entropy -0 and zero gradient.
+ */
+typedef struct b200rl_gridnet_desc {
+  int64_t B;
+  int64_t HW;
+  int A;
+  int n_pick;
+  int logits_dtype;
+  int act_dtype;
+  int pick_dtype;
+  const int32_t* nvec_host;
+  const int32_t* gate_ref_host;
+  const int32_t* gate_val_host;
+} b200rl_gridnet_desc;
+
+int b200rl_gridnet_fwd(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
+                       const uint8_t* pick_mask, const void* actions, const void* pick_actions, float* logp,
+                       float* entropy, b200rl_stream_t stream);
+int b200rl_gridnet_bwd(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
+                       const uint8_t* pick_mask, const void* actions, const void* pick_actions,
+                       const float* dlogp, const float* dentropy, void* dlogits, b200rl_stream_t stream);
+/* One launch: masked logsumexp / log-prob / entropy forward, PPO ratio / clip / value-clip /
+ * entropy loss, and the backward into dlogits and dvalues; logits read once, dlogits written once. */
+int b200rl_ppo_gridnet_loss(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
+                            const uint8_t* pick_mask, const void* actions, const void* pick_actions,
+                            const b200rl_ppo_args* args, void* dlogits, float* logp_out /*nullable*/,
+                            float* entropy_out /*nullable*/, void* workspace, size_t workspace_bytes,
+                            b200rl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K5  rollout-time sampling: one action per head per cell (+ pick) from the masked logits and
+ * its log-prob, in one launch.  Replaces shared/actor/gridnet.py:195-207 (sample) +
+ * log_prob at shared/policy/actor_critic.py:311-314.  Gumbel-max over a counter-based RNG
+ * (Philox4x32-10 keyed by seed, counter = (offset, sample, cell, head)): the distribution is
+ * the reference's, the random stream is not torch.multinomial's.
+ */
+int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
+                          const uint8_t* pick_mask, uint64_t seed, uint64_t offset, void* actions_out,
+                          void* pick_actions_out, float* logp, b200rl_stream_t stream);
+int b200rl_categorical_sample_f32(const float* logits, const uint8_t* mask, int64_t R, int64_t n, uint64_t seed,
+                                  uint64_t offset, int64_t* actions_out, float* logp, b200rl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H */

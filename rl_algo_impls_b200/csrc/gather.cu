@@ -1,0 +1,132 @@
+// K3: minibatch row gather -- dst[t][b, :] = src[t][idx[b], :] for every Batch field in one call.
+// Replaces the 8-12 separate fancy-index kernels of rollout/rollout.py:56-69
+// (Batch.__getitem__) / shared/tensor_utils.py:66-72 and the .to(device) of
+// rollout/vec_rollout.py:175 (the rollout is already device resident here).
+//
+// Wide rows (observations, masks, per-cell actions: KBs to MBs per row) are cut into 16 KB
+// chunks, one CTA per chunk, moved with 128-bit streaming loads/stores -- every load of a
+// chunk is issued before its first store.  Narrow rows (log-probs, values, advantages,
+// returns: 4..128 bytes) are handled one row per thread in the same launch family so a
+// minibatch costs two launches instead of one per field.
+#include "common.cuh"
+
+namespace b200rl {
+
+constexpr int kGatherBlock = 256;
+constexpr int kChunkBytes = 16 * 1024;
+constexpr int kNarrowRow = 256;  // rows up to this many bytes take the row-per-thread path
+
+struct GatherParams {
+  const uint8_t* src[B200RL_MAX_GATHER];
+  uint8_t* dst[B200RL_MAX_GATHER];
+  long long row_bytes[B200RL_MAX_GATHER];
+  long long first_item[B200RL_MAX_GATHER + 1];  // prefix sum of work items per tensor
+  int chunks_per_row[B200RL_MAX_GATHER];
+  int n;
+  const long long* idx;
+  long long B, n_src_rows;
+};
+
+__global__ void __launch_bounds__(kGatherBlock) gather_wide_kernel(const GatherParams p) {
+  const long long item = blockIdx.x;
+  int t = 0;
+  while (t + 1 < p.n && item >= p.first_item[t + 1]) ++t;
+  const long long local = item - p.first_item[t];
+  const long long b = local / p.chunks_per_row[t];
+  const int chunk = (int)(local - b * p.chunks_per_row[t]);
+  const long long row = p.idx[b];
+  if (row < 0 || row >= p.n_src_rows) return;
+  const long long rb = p.row_bytes[t];
+  const long long begin = (long long)chunk * kChunkBytes;
+  const long long bytes = (rb - begin < kChunkBytes) ? rb - begin : kChunkBytes;
+  const uint8_t* s = p.src[t] + row * rb + begin;
+  uint8_t* d = p.dst[t] + b * rb + begin;
+  const int tid = threadIdx.x;
+  if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15u) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(s);
+    uint4* d4 = reinterpret_cast<uint4*>(d);
+    const int n4 = (int)(bytes >> 4);
+    constexpr int kIter = kChunkBytes / 16 / kGatherBlock;  // 4
+    uint4 v[kIter];
+#pragma unroll
+    for (int i = 0; i < kIter; ++i) {
+      const int o = tid + i * kGatherBlock;
+      if (o < n4) v[i] = ldg_stream_u4(s4 + o);
+    }
+#pragma unroll
+    for (int i = 0; i < kIter; ++i) {
+      const int o = tid + i * kGatherBlock;
+      if (o < n4) stg_stream_u4(d4 + o, v[i]);
+    }
+    for (long long o = ((long long)n4 << 4) + tid; o < bytes; o += kGatherBlock) d[o] = s[o];
+  } else if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 3u) == 0) {
+    const uint32_t* s1 = reinterpret_cast<const uint32_t*>(s);
+    uint32_t* d1 = reinterpret_cast<uint32_t*>(d);
+    const int n1 = (int)(bytes >> 2);
+    for (int o = tid; o < n1; o += kGatherBlock) d1[o] = __ldg(s1 + o);
+    for (long long o = ((long long)n1 << 2) + tid; o < bytes; o += kGatherBlock) d[o] = s[o];
+  } else {
+    for (long long o = tid; o < bytes; o += kGatherBlock) d[o] = s[o];
+  }
+}
+
+__global__ void __launch_bounds__(kGatherBlock) gather_narrow_kernel(const GatherParams p) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.B * p.n) return;
+  const int t = (int)(e / p.B);  // tensor-major: threads of a warp share the tensor, walk rows
+  const long long b = e - (long long)t * p.B;
+  const long long row = p.idx[b];
+  if (row < 0 || row >= p.n_src_rows) return;
+  const long long rb = p.row_bytes[t];
+  const uint8_t* s = p.src[t] + row * rb;
+  uint8_t* d = p.dst[t] + b * rb;
+  if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | (uintptr_t)rb) & 3u) == 0) {
+    for (long long o = 0; o < rb; o += 4)
+      *reinterpret_cast<uint32_t*>(d + o) = __ldg(reinterpret_cast<const uint32_t*>(s + o));
+  } else {
+    for (long long o = 0; o < rb; ++o) d[o] = s[o];
+  }
+}
+
+}  // namespace b200rl
+
+extern "C" int b200rl_gather_rows(const void* const* src_host, void* const* dst_host, const int64_t* row_bytes_host,
+                                  int n_tensors, const int64_t* idx, int64_t B, int64_t n_src_rows,
+                                  b200rl_stream_t stream) {
+  using namespace b200rl;
+  B200RL_REQUIRE(src_host && dst_host && row_bytes_host && idx, "gather_rows: null pointer");
+  B200RL_REQUIRE(n_tensors >= 0 && n_tensors <= B200RL_MAX_GATHER, "gather_rows: n_tensors=%d (max %d)", n_tensors,
+                 B200RL_MAX_GATHER);
+  B200RL_REQUIRE(B >= 0 && n_src_rows >= 0, "gather_rows: bad shape");
+  if (B == 0 || n_tensors == 0) return B200RL_OK;
+  GatherParams wide{}, narrow{};
+  wide.idx = narrow.idx = reinterpret_cast<const long long*>(idx);
+  wide.B = narrow.B = B;
+  wide.n_src_rows = narrow.n_src_rows = n_src_rows;
+  long long items = 0;
+  for (int t = 0; t < n_tensors; ++t) {
+    B200RL_REQUIRE(src_host[t] && dst_host[t] && row_bytes_host[t] >= 0, "gather_rows: tensor %d is null", t);
+    if (row_bytes_host[t] == 0) continue;
+    GatherParams& g = row_bytes_host[t] <= kNarrowRow ? narrow : wide;
+    const int k = g.n++;
+    g.src[k] = static_cast<const uint8_t*>(src_host[t]);
+    g.dst[k] = static_cast<uint8_t*>(dst_host[t]);
+    g.row_bytes[k] = row_bytes_host[t];
+    if (&g == &wide) {
+      g.chunks_per_row[k] = (int)((row_bytes_host[t] + kChunkBytes - 1) / kChunkBytes);
+      g.first_item[k] = items;
+      items += B * g.chunks_per_row[k];
+      g.first_item[k + 1] = items;
+    }
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (wide.n) {
+    B200RL_UNSUPPORTED(items > 0x7fffffffLL, "gather_rows: %lld chunks in one call", items);
+    gather_wide_kernel<<<(unsigned)items, kGatherBlock, 0, s>>>(wide);
+  }
+  if (narrow.n) {
+    const long long threads = B * narrow.n;
+    gather_narrow_kernel<<<(unsigned)((threads + kGatherBlock - 1) / kGatherBlock), kGatherBlock, 0, s>>>(narrow);
+  }
+  return check_launch("gather_rows");
+}

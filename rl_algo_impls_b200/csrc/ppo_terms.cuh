@@ -1,0 +1,145 @@
+// Per-sample PPO loss terms shared by every fused-loss kernel (device side).
+//
+// Replaces the eager torch sequence of ppo/ppo.py:307-318 (advantage normalisation),
+// :326-361 (ratio, clipped surrogate, clipped value loss, entropy loss, approx-KL, total),
+// :373-374 (loss / num_minibatches) and the autograd backward of all of it, plus the stats
+// of :379-409.  Gradients are the analytic derivatives torch autograd produces, including
+// its tie rules: torch.min / torch.max split the gradient evenly on ties and clamp passes
+// the gradient on its closed interval.
+#pragma once
+#include "common.cuh"
+
+namespace b200rl {
+
+constexpr int kPolicyStats = 4;  // surrogate sum, entropy sum, kl sum, clipped count
+
+struct PpoDev {
+  const float* old_logp;
+  const float* adv;
+  const double* moments;
+  int adv_v;
+  int adv_mode;
+  int has_w;
+  float w[B200RL_MAX_VALUE_HEADS];
+  const float* old_values;
+  const float* returns;
+  const float* new_values;
+  float* dvalues;
+  int V;
+  float clip;      // (float)clip_range, for the clipped-fraction comparison
+  float ratio_lo;  // (float)(1.0 - clip_range), computed in double like Python does
+  float ratio_hi;
+  float vclip;  // < 0: value clipping off
+  float vf_coef[B200RL_MAX_VALUE_HEADS];
+  float ent_coef;
+  float pi_coef;
+  const float* pi_coef_dev;  // when non-null, overrides pi_coef (KL cut-off state on the device)
+  int halving;
+  float loss_scale;
+  long long B;
+  double* partials;  // [rows][4 + 2V]
+  float* stats_out;
+};
+
+__host__ __device__ inline int ppo_nstat(int V) { return kPolicyStats + 2 * V; }
+
+// (A - mean) / (std + 1e-8) etc. for one sample, then the reward-weight contraction.
+__device__ __forceinline__ float ppo_sample_advantage(const PpoDev& P, long long i) {
+  const float* row = P.adv + i * P.adv_v;
+  if (P.adv_mode == 3) {
+    float a = row[0];
+    if (P.has_w) {
+      a = 0.f;
+      for (int v = 0; v < P.adv_v; ++v) a = fmaf(row[v], P.w[v], a);
+    }
+    const double n = P.moments[2], mean = P.moments[0] / n;
+    const double var = fmax(0.0, (P.moments[1] - P.moments[0] * mean) / (n - 1.0));
+    return (a - (float)mean) / ((float)sqrt(var) + 1e-8f);
+  }
+  float acc = 0.f;
+  for (int v = 0; v < P.adv_v; ++v) {
+    float a = row[v];
+    if (P.adv_mode != 0) {
+      const double n = P.moments[2 * P.adv_v], mean = P.moments[v] / n;
+      const double var = fmax(0.0, (P.moments[P.adv_v + v] - P.moments[v] * mean) / (n - 1.0));
+      const float denom = (float)sqrt(var) + 1e-8f;
+      a = (P.adv_mode == 1) ? (a - (float)mean) / denom : a / denom;
+    }
+    if (!P.has_w) return a;  // adv_v == 1 (checked on the host)
+    acc = fmaf(a, P.w[v], acc);
+  }
+  return acc;
+}
+
+struct PolicyTerms {
+  float dlogp;      // d loss / d new_logp[i]
+  float surrogate;  // min(ratio*A, clamp(ratio)*A)
+  float kl;         // (ratio - 1) - logratio
+  float clipped;    // |ratio - 1| > clip
+};
+
+__device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long long i, float new_logp) {
+  const float A = ppo_sample_advantage(P, i);
+  const float logratio = new_logp - P.old_logp[i];
+  const float ratio = expf(logratio);
+  const float cr = fminf(fmaxf(ratio, P.ratio_lo), P.ratio_hi);
+  const float s1 = ratio * A, s2 = cr * A;
+  const bool in_range = ratio >= P.ratio_lo && ratio <= P.ratio_hi;
+  float dsurr;
+  if (in_range) {
+    dsurr = A;  // both branches of the tie carry grad/2 and clamp is transparent
+  } else if (s1 < s2) {
+    dsurr = A;
+  } else if (s1 == s2) {
+    dsurr = 0.5f * A;  // tie outside the clip range: only the unclipped half reaches ratio
+  } else {
+    dsurr = 0.f;
+  }
+  const float pi_coef = P.pi_coef_dev ? *P.pi_coef_dev : P.pi_coef;
+  PolicyTerms t;
+  t.surrogate = fminf(s1, s2);
+  t.dlogp = -(pi_coef * P.loss_scale / (float)P.B) * dsurr * ratio;
+  t.kl = (ratio - 1.f) - logratio;
+  t.clipped = fabsf(ratio - 1.f) > P.clip ? 1.f : 0.f;
+  return t;
+}
+
+// d loss / d entropy element (entropy_loss = -mean over B * ent_d elements)
+__device__ __forceinline__ float ppo_dentropy(const PpoDev& P, int ent_d) {
+  return -(P.ent_coef * P.loss_scale) / ((float)P.B * (float)ent_d);
+}
+
+// value head v of sample i: writes dvalues[i, v]; returns (loss element, clipped indicator)
+__device__ __forceinline__ float2 ppo_value_terms(const PpoDev& P, long long i, int v) {
+  const long long o = i * P.V + v;
+  const float nv = P.new_values[o], ov = P.old_values[o], rt = P.returns[o];
+  const float eu = nv - rt;
+  const float u = eu * eu;
+  float vl = u, g = 2.f * eu, clipped = 0.f;
+  if (P.vclip >= 0.f) {
+    const float d = nv - ov;
+    const float c = ov + fminf(fmaxf(d, -P.vclip), P.vclip);
+    const float ec = c - rt;
+    const float cl = ec * ec;
+    const float gc = (d >= -P.vclip && d <= P.vclip) ? 2.f * ec : 0.f;
+    if (u > cl) {
+      vl = u;
+    } else if (u < cl) {
+      vl = cl, g = gc;
+    } else {
+      vl = u, g = 0.5f * g + 0.5f * gc;
+    }
+    clipped = fabsf(d) > P.vclip ? 1.f : 0.f;
+  }
+  const float half = P.halving ? 0.5f : 1.f;
+  if (P.dvalues) P.dvalues[o] = P.vf_coef[v] * half * P.loss_scale / (float)P.B * g;
+  return make_float2(vl, clipped);
+}
+
+// partials [rows][4 + 2V] -> stats_out (see b200rl.h).  One block; fixed order => deterministic.
+int ppo_launch_finalize(const PpoDev& P, long long rows, int ent_d, cudaStream_t stream);
+
+// host: b200rl_ppo_args -> PpoDev.  Returns 0 or an error code (message set).
+int ppo_make_dev(const b200rl_ppo_args* a, long long B, void* workspace, size_t workspace_bytes, PpoDev* out);
+
+}  // namespace b200rl
