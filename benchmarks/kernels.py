@@ -1,0 +1,149 @@
+"""Kernel-level roofline measurements (CUDA events on torch's current stream, inputs > L2 or L2
+flushed between iterations).  Usage: python benchmarks/kernels.py [gae|loss|gather|all] [--json out]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from rl_algo_impls_b200 import ops  # noqa: E402
+from tests.synth import LUX_GATES, LUX_NVEC, MICRORTS_GATES, MICRORTS_NVEC  # noqa: E402
+
+
+def peak_gbs() -> float:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"])
+    return 6650.0
+
+
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    _flush.zero_()
+
+
+def time_kernel(fn, iters=20, warmup=3, flush=True):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        if flush:
+            flush_l2()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        times.append(s.elapsed_time(e))
+    return float(np.median(times)), float(np.min(times))
+
+
+def bench_gae(T, N, V):
+    dev = "cuda"
+    shape = (T, N) if V == 1 else (T, N, V)
+    r, v = torch.randn(shape, device=dev), torch.randn(shape, device=dev)
+    es = torch.rand((T, N), device=dev) < 0.005
+    nes = torch.rand((N,), device=dev) < 0.005
+    nv = torch.randn(shape[1:], device=dev)
+    adv, ret = torch.empty_like(r), torch.empty_like(r)
+    gamma = 0.99 if V == 1 else np.full(V, 1.0)
+    lam = 0.95 if V == 1 else np.full(V, 0.95)
+    fn = lambda: ops.gae_scan(r, v, es, nes, nv, gamma, lam, adv, ret)
+    med, best = time_kernel(fn)
+    nbytes = T * N * (16 * V + 1) + N * (4 * V + 1)
+    return dict(kernel="gae_scan", T=T, N=N, V=V, ms_median=med, ms_best=best, bytes=nbytes,
+                gbs=nbytes / med / 1e6, frac=nbytes / med / 1e6 / peak_gbs())
+
+
+def gridnet_tensors(B, HW, nvec, n_pick, unit_p, dtype=torch.float32, act_dtype=torch.uint8):
+    dev = "cuda"
+    S, A = sum(nvec), len(nvec)
+    g = torch.Generator(device=dev).manual_seed(0)
+    logits = torch.randn((B, HW, S + n_pick), device=dev, generator=g).to(dtype)
+    has_unit = torch.rand((B, HW, 1), device=dev, generator=g) < unit_p
+    mask = (torch.rand((B, HW, S), device=dev, generator=g) < 0.5) & has_unit
+    actions = torch.stack([torch.randint(0, n, (B, HW), device=dev, generator=g) for n in nvec], -1).to(act_dtype)
+    pick_mask = pick = None
+    if n_pick:
+        pick_mask = torch.rand((B, n_pick, HW), device=dev, generator=g) < 0.05
+        pick = torch.randint(0, HW, (B, n_pick), device=dev, generator=g)
+    return logits, mask, pick_mask, actions, pick
+
+
+def bench_loss(B, HW, nvec, gates, n_pick, V, unit_p, dtype=torch.float32):
+    dev = "cuda"
+    logits, mask, pick_mask, actions, pick = gridnet_tensors(B, HW, nvec, n_pick, unit_p, dtype)
+    spec = ops.GridnetSpec.from_subaction_mask(nvec, gates, n_pick)
+    vs = (B,) if V == 1 else (B, V)
+    old_logp = torch.randn(B, device=dev) * 0.1 - 20
+    adv = torch.randn(vs, device=dev)
+    ov, rt, nv = torch.randn(vs, device=dev), torch.randn(vs, device=dev), torch.randn(vs, device=dev)
+    w = [1.0 / V] * V if V > 1 else None
+    h = ops.PpoHyper(clip_range=0.1, clip_range_vf=0.1, ent_coef=0.01, vf_coef=[0.5] * V, adv_weights=w)
+    moments = ops.adv_moments(adv.view(B, V), None, ops.ADV_NORMALIZE, w)
+    fn = lambda: ops.ppo_gridnet_loss(h, spec, logits, mask, pick_mask, actions, pick, old_logp, adv, ov, rt, nv,
+                                      moments=moments)
+    med, best = time_kernel(fn)
+    S, A, es = sum(nvec), len(nvec), logits.element_size()
+    nbytes = B * (2 * es * HW * (S + n_pick) + HW * S + n_pick * HW + HW * A + 2 * n_pick + 4 * (2 + 5 * V))
+    return dict(kernel="ppo_gridnet_loss", B=B, HW=HW, S=S + n_pick, V=V, dtype=str(dtype), ms_median=med,
+                ms_best=best, bytes=nbytes, gbs=nbytes / med / 1e6, frac=nbytes / med / 1e6 / peak_gbs())
+
+
+def bench_gather(M, B, row_shapes):
+    dev = "cuda"
+    srcs = [torch.empty((M,) + tuple(s), dtype=dt, device=dev) for s, dt in row_shapes]
+    for s in srcs:
+        s.view(torch.uint8).random_(0, 255) if s.dtype != torch.bool else None
+    idx = torch.randperm(M, device=dev)[:B]
+    fn = lambda: ops.gather_rows(srcs, idx)
+    med, best = time_kernel(fn)
+    nbytes = 2 * B * sum(int(np.prod(s.shape[1:])) * s.element_size() for s in srcs)
+    return dict(kernel="gather_rows", M=M, B=B, ms_median=med, ms_best=best, bytes=nbytes, gbs=nbytes / med / 1e6,
+                frac=nbytes / med / 1e6 / peak_gbs())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="?", default="all")
+    ap.add_argument("--json", default=None)
+    a = ap.parse_args()
+    rows = []
+    if a.what in ("gae", "all"):
+        for T, N, V in [(32, 8, 1), (128, 8, 1), (64, 4096, 1), (512, 24, 1), (32, 1024, 13), (128, 1 << 20, 1),
+                        (32, 131072, 13)]:
+            rows.append(bench_gae(T, N, V))
+            print(json.dumps(rows[-1]), flush=True)
+    if a.what in ("loss", "all"):
+        for B in (256, 3072):
+            rows.append(bench_loss(B, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 0.06))
+            print(json.dumps(rows[-1]), flush=True)
+        for B in (128, 512):
+            rows.append(bench_loss(B, 4096, LUX_NVEC, LUX_GATES, 1, 13, 0.02))
+            print(json.dumps(rows[-1]), flush=True)
+        rows.append(bench_loss(3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 0.06, torch.bfloat16))
+        print(json.dumps(rows[-1]), flush=True)
+    if a.what in ("gather", "all"):
+        rows.append(bench_gather(12288, 3072, [((74, 16, 16), torch.float32), ((256, 78), torch.uint8),
+                                               ((256, 7), torch.uint8), ((), torch.float32), ((), torch.float32),
+                                               ((), torch.float32), ((), torch.float32)]))
+        print(json.dumps(rows[-1]), flush=True)
+        rows.append(bench_gather(8192, 2048, [((4, 84, 84), torch.uint8), ((), torch.float32), ((), torch.int64)]))
+        print(json.dumps(rows[-1]), flush=True)
+    if a.json:
+        json.dump(rows, open(a.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

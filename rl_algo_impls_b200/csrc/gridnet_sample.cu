@@ -1,0 +1,207 @@
+// K5: rollout-time GridNet sampling -- one action per head per cell (+ pick_position) and the
+// joint log-prob of the draw, in one launch.
+//
+// Replaces GridnetDistribution.sample (shared/actor/gridnet.py:195-207: one torch.multinomial
+// per head) followed by log_prob (gridnet.py:104-176) at shared/policy/actor_critic.py:311-314.
+// Gumbel-max: argmax_k (x_k + g_k) over the valid entries is an exact draw from the masked
+// softmax; g_k comes from Philox4x32-10 keyed by `seed` with counter
+// (sample*HW + cell, offset, head, k/4), so the stream is reproducible and independent of the
+// launch geometry.  A row with no valid entry draws uniformly over all entries and contributes
+// log-prob 0, as the reference (probs = 1/n, normalised logits = 0).
+// One CTA per sample: rollouts have few samples (n_envs) and the pick categorical needs a
+// sample-wide argmax.
+#include "categorical.cuh"
+#include "philox.cuh"
+
+namespace b200rl {
+
+constexpr int kSampleBlock = 256;
+
+struct SampleDev {
+  const void* logits;
+  int logits_dtype;
+  const uint8_t* mask;
+  const uint8_t* pick_mask;
+  long long B, HW;
+  int A, S, Sp, n_pick;
+  int nvec[B200RL_MAX_HEADS], off[B200RL_MAX_HEADS], gate_ref[B200RL_MAX_HEADS], gate_val[B200RL_MAX_HEADS];
+  uint64_t seed, offset;
+  void* actions_out;
+  int act_dtype;
+  void* pick_out;
+  int pick_dtype;
+  float* logp;
+};
+
+__device__ __forceinline__ float logit_at(const SampleDev& G, long long i) {
+  return G.logits_dtype == B200RL_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(G.logits)[i])
+                                       : static_cast<const float*>(G.logits)[i];
+}
+__device__ __forceinline__ void put_index(void* base, int dtype, long long i, long long v) {
+  switch (dtype) {
+    case B200RL_U8: static_cast<uint8_t*>(base)[i] = (uint8_t)v; break;
+    case B200RL_I32: static_cast<int32_t*>(base)[i] = (int32_t)v; break;
+    default: static_cast<long long*>(base)[i] = v; break;
+  }
+}
+__device__ __forceinline__ float gumbel(uint32_t bits) { return -logf(-logf(u01(bits))); }
+__device__ __forceinline__ uint64_t stream_id(uint64_t offset, int head, int kblock) {
+  return (offset << 24) ^ ((uint64_t)head << 16) ^ (uint64_t)kblock;
+}
+
+__global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const SampleDev G) {
+  __shared__ float s_red[32];
+  __shared__ float s_best[32];
+  __shared__ long long s_arg[32];
+  __shared__ float s_scalar[2];
+  const long long b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float logp_acc = 0.f;
+
+  for (long long c = tid; c < G.HW; c += kSampleBlock) {
+    const long long cell = b * G.HW + c;
+    const long long xbase = cell * G.Sp;
+    const uint8_t* m = G.mask + cell * G.S;
+    int chosen[B200RL_MAX_HEADS];
+    float lp[B200RL_MAX_HEADS];
+    for (int h = 0; h < G.A; ++h) {
+      const int off = G.off[h], n = G.nvec[h];
+      bool any = false;
+      for (int k = 0; k < n; ++k) any |= (m[off + k] != 0);
+      int best = 0;
+      float best_score = -INFINITY;
+      for (int k0 = 0; k0 < n; k0 += 4) {
+        const Philox4 r = philox4x32_10(G.seed, (uint64_t)cell, stream_id(G.offset, h, k0 >> 2));
+        const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+        for (int j = 0; j < 4 && k0 + j < n; ++j) {
+          const int k = k0 + j;
+          if (any && !m[off + k]) continue;
+          const float score = (any ? logit_at(G, xbase + off + k) : 0.f) + gumbel(bits[j]);
+          if (score > best_score) best_score = score, best = k;
+        }
+      }
+      chosen[h] = best;
+      lp[h] = 0.f;
+      if (any) {
+        CatRow row = cat_forward([&](int k) { return logit_at(G, xbase + off + k); },
+                                 [&](int k) { return m[off + k] != 0; }, n, best);
+        lp[h] = row.logp;
+      }
+      put_index(G.actions_out, G.act_dtype, cell * G.A + h, best);
+    }
+    for (int h = 0; h < G.A; ++h) {
+      const int gr = G.gate_ref[h];
+      if (gr < 0 || chosen[gr] == G.gate_val[h]) logp_acc += lp[h];
+    }
+  }
+
+  // pick_position: Gumbel arg-max over the cells of the sample, then its log-prob
+  for (int kp = 0; kp < G.n_pick; ++kp) {
+    const uint8_t* pm = G.pick_mask + (b * G.n_pick + kp) * G.HW;
+    // does any cell qualify?
+    float anyf = 0.f;
+    for (long long c = tid; c < G.HW; c += kSampleBlock) anyf = fmaxf(anyf, pm[c] ? 1.f : 0.f);
+    anyf = warp_max(anyf);
+    if (lane == 0) s_red[warp] = anyf;
+    __syncthreads();
+    if (warp == 0) {
+      float x = lane < kSampleBlock / 32 ? s_red[lane] : 0.f;
+      x = warp_max(x);
+      if (lane == 0) s_scalar[0] = x;
+    }
+    __syncthreads();
+    const bool any = s_scalar[0] > 0.f;
+    float best_score = -INFINITY, mx = -INFINITY;
+    long long best = 0x7fffffffffffLL;
+    for (long long c = tid; c < G.HW; c += kSampleBlock) {
+      if (any && !pm[c]) continue;
+      const Philox4 r = philox4x32_10(G.seed, (uint64_t)(b * G.HW + c), stream_id(G.offset, G.A + kp, 0));
+      const float x = any ? logit_at(G, (b * G.HW + c) * G.Sp + G.S + kp) : 0.f;
+      const float score = x + gumbel(r.x);
+      if (score > best_score) best_score = score, best = c;
+      mx = fmaxf(mx, x);
+    }
+    // block arg-max (ties -> lowest cell index, so the result does not depend on warp order)
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, best_score, o);
+      const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+      if (os > best_score || (os == best_score && ob < best)) best_score = os, best = ob;
+    }
+    mx = warp_max(mx);
+    __syncthreads();
+    if (lane == 0) s_best[warp] = best_score, s_arg[warp] = best, s_red[warp] = mx;
+    __syncthreads();
+    if (warp == 0) {
+      float bs = lane < kSampleBlock / 32 ? s_best[lane] : -INFINITY;
+      long long ba = lane < kSampleBlock / 32 ? s_arg[lane] : 0x7fffffffffffLL;
+      float m2 = lane < kSampleBlock / 32 ? s_red[lane] : -INFINITY;
+      for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const long long ob = __shfl_xor_sync(0xffffffffu, ba, o);
+        if (os > bs || (os == bs && ob < ba)) bs = os, ba = ob;
+      }
+      m2 = warp_max(m2);
+      if (lane == 0) s_arg[0] = ba, s_scalar[1] = m2;
+    }
+    __syncthreads();
+    const long long pick = s_arg[0];
+    mx = s_scalar[1];
+    float se = 0.f;
+    if (any)
+      for (long long c = tid; c < G.HW; c += kSampleBlock)
+        if (pm[c]) se += expf(logit_at(G, (b * G.HW + c) * G.Sp + G.S + kp) - mx);
+    se = warp_sum(se);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = se;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < kSampleBlock / 32; ++w) tot += s_red[w];
+      put_index(G.pick_out, G.pick_dtype, b * G.n_pick + kp, pick);
+      if (any) logp_acc += logit_at(G, (b * G.HW + pick) * G.Sp + G.S + kp) - (mx + logf(tot));
+    }
+    __syncthreads();
+  }
+
+  logp_acc = warp_sum(logp_acc);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = logp_acc;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < kSampleBlock / 32; ++w) tot += s_red[w];
+    G.logp[b] = tot;
+  }
+}
+
+}  // namespace b200rl
+
+extern "C" int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
+                                     const uint8_t* pick_mask, uint64_t seed, uint64_t offset, void* actions_out,
+                                     void* pick_actions_out, float* logp, b200rl_stream_t stream) {
+  using namespace b200rl;
+  B200RL_REQUIRE(d && logits && mask && actions_out && logp, "gridnet_sample: null pointer");
+  B200RL_REQUIRE(d->B >= 0 && d->HW >= 1 && d->A >= 1 && d->A <= B200RL_MAX_HEADS && d->n_pick >= 0,
+                 "gridnet_sample: bad shape");
+  B200RL_REQUIRE(d->n_pick == 0 || (pick_mask && pick_actions_out), "gridnet_sample: pick tensors are null");
+  B200RL_UNSUPPORTED(d->logits_dtype != B200RL_F32 && d->logits_dtype != B200RL_BF16, "gridnet_sample: logits dtype");
+  if (d->B == 0) return B200RL_OK;
+  SampleDev G{};
+  G.logits = logits, G.logits_dtype = d->logits_dtype, G.mask = mask, G.pick_mask = pick_mask;
+  G.B = d->B, G.HW = d->HW, G.A = d->A, G.n_pick = d->n_pick;
+  int S = 0;
+  for (int h = 0; h < d->A; ++h) {
+    G.nvec[h] = d->nvec_host[h], G.off[h] = S;
+    S += d->nvec_host[h];
+    const int gr = d->gate_ref_host ? d->gate_ref_host[h] : -1;
+    B200RL_REQUIRE(gr < d->A, "gridnet_sample: gate_ref[%d] out of range", h);
+    G.gate_ref[h] = gr;
+    G.gate_val[h] = (gr >= 0 && d->gate_val_host) ? d->gate_val_host[h] : 0;
+  }
+  G.S = S, G.Sp = S + d->n_pick;
+  G.seed = seed, G.offset = offset;
+  G.actions_out = actions_out, G.act_dtype = d->act_dtype, G.pick_out = pick_actions_out, G.pick_dtype = d->pick_dtype;
+  G.logp = logp;
+  gridnet_sample_kernel<<<(unsigned)d->B, kSampleBlock, 0, (cudaStream_t)stream>>>(G);
+  return check_launch("gridnet_sample");
+}

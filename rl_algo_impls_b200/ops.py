@@ -1,0 +1,584 @@
+"""Tensor-level entry points over the C ABI (include/b200rl.h).
+
+Every function takes CUDA tensors, checks dtype / contiguity, and launches on torch's current
+stream.  Nothing here computes on the host and nothing falls back to eager PyTorch: a missing
+library or a CPU tensor raises.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GridnetDesc, PpoArgs, check
+
+NumOrArray = Union[float, int, np.ndarray, Sequence[float]]
+
+ADV_NONE, ADV_NORMALIZE, ADV_STANDARDIZE, ADV_AFTER_SCALING = 0, 1, 2, 3
+
+_INDEX_DTYPES = {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.int64: _lib.I64}
+_LOGIT_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _cuda(t: torch.Tensor, dtype: Optional[torch.dtype], name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.B200RLError(f"{name}: expected a CUDA tensor (rl_algo_impls_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    return t
+
+
+def _as_u8(mask: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if mask is None:
+        return None
+    if not mask.is_cuda:
+        raise _lib.B200RLError(f"{name}: expected a CUDA tensor")
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)  # same bytes, no copy
+    if mask.dtype != torch.uint8:
+        raise TypeError(f"{name}: expected bool or uint8, got {mask.dtype}")
+    return mask.contiguous()
+
+
+def _f32_array(values: Sequence[float]):
+    arr = (C.c_float * len(values))(*[float(v) for v in values])
+    return arr
+
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Per (device, stream) scratch buffer.  Calls on one stream are ordered, so reuse is safe."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------------
+# K1
+def gae_scan(
+    rewards: torch.Tensor,
+    values: torch.Tensor,
+    episode_starts: torch.Tensor,
+    next_episode_starts: torch.Tensor,
+    next_values: torch.Tensor,
+    gamma: NumOrArray,
+    gae_lambda: NumOrArray,
+    out_advantages: Optional[torch.Tensor] = None,
+    out_returns: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """advantages, returns over a time-major [T, N(, V)] rollout (shared/gae.py:97-124, vec_rollout.py:88)."""
+    _cuda(rewards, torch.float32, "rewards")
+    _cuda(values, torch.float32, "values")
+    _cuda(next_values, torch.float32, "next_values")
+    es, nes = _as_u8(episode_starts, "episode_starts"), _as_u8(next_episode_starts, "next_episode_starts")
+    if rewards.shape != values.shape or rewards.dim() not in (2, 3):
+        raise ValueError(f"rewards {tuple(rewards.shape)} / values {tuple(values.shape)} must be [T, N] or [T, N, V]")
+    T, N = rewards.shape[:2]
+    V = rewards.shape[2] if rewards.dim() == 3 else 1
+    if es.shape != (T, N) or nes.shape != (N,) or next_values.numel() != N * V:
+        raise ValueError("episode_starts / next_episode_starts / next_values shapes do not match rewards")
+    gamma_is_scalar = not isinstance(gamma, (np.ndarray, list, tuple))
+
+    def per_head(x: NumOrArray, name: str):
+        a = np.asarray(x, dtype=np.float64).reshape(-1)
+        if a.size == 1:
+            a = np.repeat(a, V)
+        if a.size != V:
+            raise ValueError(f"{name} has {a.size} entries for {V} value heads")
+        return (C.c_double * V)(*a.tolist())
+
+    g, lam = per_head(gamma, "gamma"), per_head(gae_lambda, "gae_lambda")
+    adv = out_advantages if out_advantages is not None else torch.empty_like(rewards)
+    ret = out_returns if out_returns is not None else torch.empty_like(rewards)
+    _cuda(adv, torch.float32, "out_advantages"), _cuda(ret, torch.float32, "out_returns")
+    rc = _lib.lib().b200rl_gae_scan_f32(
+        rewards.data_ptr(), values.data_ptr(), es.data_ptr(), nes.data_ptr(), next_values.data_ptr(),
+        g, lam, int(gamma_is_scalar), adv.data_ptr(), ret.data_ptr(), T, N, V, _stream(),
+    )  # fmt: skip
+    check(rc, "b200rl_gae_scan_f32")
+    return adv, ret
+
+
+# ------------------------------------------------------------------------------------------------
+# K2
+def adv_moments(
+    adv: torch.Tensor, idx: Optional[torch.Tensor], mode: int, weights: Optional[Sequence[float]] = None
+) -> torch.Tensor:
+    """(sum[Vm], sumsq[Vm], count) in f64 over rows ``idx`` of adv [M, V] (ppo.py:307-318 statistics)."""
+    _cuda(adv, torch.float32, "adv")
+    V = adv.shape[1] if adv.dim() == 2 else 1
+    B = adv.shape[0] if idx is None else idx.numel()
+    if idx is not None:
+        _cuda(idx, torch.int64, "idx")
+    vm = 1 if mode == ADV_AFTER_SCALING else V
+    moments = torch.empty(2 * vm + 1, dtype=torch.float64, device=adv.device)
+    L = _lib.lib()
+    nbytes = L.b200rl_adv_moments_workspace_bytes(B, V)
+    ws = _workspace(nbytes, adv.device)
+    w = _f32_array(weights) if weights is not None else None
+    rc = L.b200rl_adv_moments_f64(
+        adv.data_ptr(), _ptr(idx), B, V, mode, w, moments.data_ptr(), ws.data_ptr(), ws.numel(), _stream()
+    )
+    check(rc, "b200rl_adv_moments_f64")
+    return moments
+
+
+def adv_normalize(
+    adv: torch.Tensor,
+    idx: Optional[torch.Tensor],
+    mode: int,
+    weights: Optional[Sequence[float]] = None,
+    moments: Optional[torch.Tensor] = None,
+    contract: bool = True,
+) -> torch.Tensor:
+    """Normalised (and, with ``contract``, reward-weight contracted) advantages of a minibatch."""
+    _cuda(adv, torch.float32, "adv")
+    V = adv.shape[1] if adv.dim() == 2 else 1
+    B = adv.shape[0] if idx is None else idx.numel()
+    if mode != ADV_NONE and moments is None:
+        moments = adv_moments(adv, idx, mode, weights)
+    out_v = 1 if (contract and (weights is not None or V == 1)) or mode == ADV_AFTER_SCALING else V
+    out = torch.empty((B,) if out_v == 1 else (B, V), dtype=torch.float32, device=adv.device)
+    w = _f32_array(weights) if weights is not None else None
+    rc = _lib.lib().b200rl_adv_normalize_f32(
+        adv.data_ptr(), _ptr(idx), B, V, mode, w, _ptr(moments), out.data_ptr(), out_v, _stream()
+    )
+    check(rc, "b200rl_adv_normalize_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K3
+def gather_rows(sources: Sequence[torch.Tensor], idx: torch.Tensor) -> List[torch.Tensor]:
+    """[src[idx] for src in sources] in (at most) two launches (rollout.py:56-69)."""
+    _cuda(idx, torch.int64, "idx")
+    B = idx.numel()
+    if not sources:
+        return []
+    n_rows = sources[0].shape[0]
+    outs: List[torch.Tensor] = []
+    for start in range(0, len(sources), _lib.MAX_GATHER):
+        group = sources[start : start + _lib.MAX_GATHER]
+        n = len(group)
+        src_arr, dst_arr, rb_arr = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_int64 * n)()
+        for k, s in enumerate(group):
+            _cuda(s, None, f"sources[{start + k}]")
+            if s.shape[0] != n_rows:
+                raise ValueError("every gathered tensor must have the same number of rows")
+            d = torch.empty((B,) + tuple(s.shape[1:]), dtype=s.dtype, device=s.device)
+            outs.append(d)
+            src_arr[k], dst_arr[k] = s.data_ptr(), d.data_ptr()
+            rb_arr[k] = (s.numel() // max(n_rows, 1)) * s.element_size()
+        rc = _lib.lib().b200rl_gather_rows(src_arr, dst_arr, rb_arr, n, idx.data_ptr(), B, n_rows, _stream())
+        check(rc, "b200rl_gather_rows")
+    return outs
+
+
+# ------------------------------------------------------------------------------------------------
+# PPO arguments shared by the fused-loss entry points
+@dataclass
+class PpoHyper:
+    """Host-side scalars of ppo/ppo.py:307-375 for one minibatch."""
+
+    clip_range: float
+    clip_range_vf: Optional[float]
+    ent_coef: float
+    vf_coef: Sequence[float]  # one per value head
+    vf_halving: bool = False
+    pi_coef: float = 1.0
+    loss_scale: float = 1.0
+    adv_mode: int = ADV_NORMALIZE
+    adv_weights: Optional[Sequence[float]] = None
+
+
+class PpoCall:
+    """Builds a b200rl_ppo_args and keeps every buffer it points at alive until the call returns."""
+
+    def __init__(
+        self,
+        h: PpoHyper,
+        old_logp: torch.Tensor,
+        adv: torch.Tensor,
+        old_values: torch.Tensor,
+        returns: torch.Tensor,
+        new_values: torch.Tensor,
+        moments: Optional[torch.Tensor] = None,
+        need_dvalues: bool = True,
+    ):
+        B = old_logp.numel()
+        dev = old_logp.device
+        for name, t in (("old_logp", old_logp), ("adv", adv), ("old_values", old_values), ("returns", returns),
+                        ("new_values", new_values)):  # fmt: skip
+            _cuda(t, torch.float32, name)
+        V = new_values.numel() // B
+        adv_v = adv.numel() // B
+        if old_values.numel() != B * V or returns.numel() != B * V:
+            raise ValueError("old_values / returns / new_values shapes differ")
+        if len(h.vf_coef) != V:
+            raise ValueError(f"vf_coef has {len(h.vf_coef)} entries for {V} value heads")
+        if adv_v > 1 and h.adv_weights is None:
+            raise ValueError("multi-head advantages need multi_reward_weights")
+        if h.adv_mode != ADV_NONE and moments is None:
+            moments = adv_moments(adv.view(B, adv_v), None, h.adv_mode, h.adv_weights)
+        self.B, self.V = B, V
+        self.moments = moments
+        self.dvalues = torch.empty_like(new_values) if need_dvalues else None
+        self.stats = torch.empty(5 + 2 * V, dtype=torch.float32, device=dev)
+        self._w = _f32_array(h.adv_weights) if h.adv_weights is not None else None
+        self._vf = _f32_array(h.vf_coef)
+        L = _lib.lib()
+        self.workspace = _workspace(L.b200rl_ppo_workspace_bytes(B, V), dev)
+        a = PpoArgs()
+        a.old_logp, a.adv, a.moments = old_logp.data_ptr(), adv.data_ptr(), _ptr(moments)
+        a.adv_weights_host = self._w
+        a.adv_v, a.adv_mode = adv_v, h.adv_mode
+        a.old_values, a.returns, a.new_values = old_values.data_ptr(), returns.data_ptr(), new_values.data_ptr()
+        a.dvalues = _ptr(self.dvalues)
+        a.V = V
+        a.clip_range = float(h.clip_range)
+        a.clip_range_vf = -1.0 if h.clip_range_vf is None else float(h.clip_range_vf)
+        a.vf_coef_host = self._vf
+        a.ent_coef, a.pi_coef = float(h.ent_coef), float(h.pi_coef)
+        a.vf_halving, a.loss_scale = int(bool(h.vf_halving)), float(h.loss_scale)
+        a.stats_out = self.stats.data_ptr()
+        self.args = a
+        self._keep = (old_logp, adv, old_values, returns, new_values, moments)
+
+
+@dataclass
+class LossOut:
+    """Device-side results of one fused loss launch.  ``stats`` layout: see include/b200rl.h."""
+
+    stats: torch.Tensor
+    dvalues: torch.Tensor
+    grads: Tuple[torch.Tensor, ...]
+    logp: Optional[torch.Tensor] = None
+    entropy: Optional[torch.Tensor] = None
+
+
+def ppo_scalar_loss(
+    h: PpoHyper,
+    new_logp: torch.Tensor,
+    entropy: torch.Tensor,
+    old_logp: torch.Tensor,
+    adv: torch.Tensor,
+    old_values: torch.Tensor,
+    returns: torch.Tensor,
+    new_values: torch.Tensor,
+    moments: Optional[torch.Tensor] = None,
+    kl_cutoff: Optional[float] = None,
+    pi_coef_state: Optional[torch.Tensor] = None,
+) -> LossOut:
+    """Per-sample stage for heads that produced (new_logp [B], entropy [B] or [B, D]) elsewhere."""
+    _cuda(new_logp, torch.float32, "new_logp"), _cuda(entropy, torch.float32, "entropy")
+    B = new_logp.numel()
+    ent_d = entropy.numel() // B
+    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments)
+    dlogp, dent = torch.empty_like(new_logp), torch.empty_like(entropy)
+    if kl_cutoff is not None and pi_coef_state is None:
+        raise ValueError("kl_cutoff needs a device pi_coef_state tensor")
+    rc = _lib.lib().b200rl_ppo_scalar_loss_f32(
+        new_logp.data_ptr(), entropy.data_ptr(), ent_d, B, C.byref(call.args),
+        -1.0 if kl_cutoff is None else float(kl_cutoff), _ptr(pi_coef_state),
+        dlogp.data_ptr(), dent.data_ptr(), call.workspace.data_ptr(), call.workspace.numel(), _stream(),
+    )  # fmt: skip
+    check(rc, "b200rl_ppo_scalar_loss_f32")
+    return LossOut(call.stats, call.dvalues, (dlogp, dent))
+
+
+def ppo_categorical_loss(
+    h: PpoHyper,
+    logits: torch.Tensor,
+    mask: Optional[torch.Tensor],
+    actions: torch.Tensor,
+    old_logp: torch.Tensor,
+    adv: torch.Tensor,
+    old_values: torch.Tensor,
+    returns: torch.Tensor,
+    new_values: torch.Tensor,
+    moments: Optional[torch.Tensor] = None,
+) -> LossOut:
+    _cuda(logits, torch.float32, "logits")
+    B, n = logits.shape
+    m = _as_u8(mask, "mask")
+    _cuda(actions, None, "actions")
+    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments)
+    dlogits = torch.empty_like(logits)
+    rc = _lib.lib().b200rl_ppo_categorical_loss_f32(
+        logits.data_ptr(), _ptr(m), actions.data_ptr(), _INDEX_DTYPES[actions.dtype], B, n, C.byref(call.args),
+        dlogits.data_ptr(), call.workspace.data_ptr(), call.workspace.numel(), _stream(),
+    )  # fmt: skip
+    check(rc, "b200rl_ppo_categorical_loss_f32")
+    return LossOut(call.stats, call.dvalues, (dlogits,))
+
+
+def ppo_gaussian_loss(
+    h: PpoHyper,
+    mu: torch.Tensor,
+    log_std: torch.Tensor,
+    actions: torch.Tensor,
+    old_logp: torch.Tensor,
+    adv: torch.Tensor,
+    old_values: torch.Tensor,
+    returns: torch.Tensor,
+    new_values: torch.Tensor,
+    moments: Optional[torch.Tensor] = None,
+) -> LossOut:
+    for name, t in (("mu", mu), ("log_std", log_std), ("actions", actions)):
+        _cuda(t, torch.float32, name)
+    B, D = mu.shape
+    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments)
+    dmu, dls = torch.empty_like(mu), torch.empty_like(log_std)
+    rc = _lib.lib().b200rl_ppo_gaussian_loss_f32(
+        mu.data_ptr(), log_std.data_ptr(), actions.data_ptr(), B, D, C.byref(call.args), dmu.data_ptr(),
+        dls.data_ptr(), call.workspace.data_ptr(), call.workspace.numel(), _stream(),
+    )  # fmt: skip
+    check(rc, "b200rl_ppo_gaussian_loss_f32")
+    return LossOut(call.stats, call.dvalues, (dmu, dls))
+
+
+def gaussian_logp_entropy(mu: torch.Tensor, log_std: torch.Tensor, actions: torch.Tensor):
+    for name, t in (("mu", mu), ("log_std", log_std), ("actions", actions)):
+        _cuda(t, torch.float32, name)
+    B, D = mu.shape
+    logp = torch.empty(B, dtype=torch.float32, device=mu.device)
+    ent = torch.empty(B, D, dtype=torch.float32, device=mu.device)
+    rc = _lib.lib().b200rl_gaussian_fwd_f32(
+        mu.data_ptr(), log_std.data_ptr(), actions.data_ptr(), B, D, logp.data_ptr(), ent.data_ptr(), _stream()
+    )
+    check(rc, "b200rl_gaussian_fwd_f32")
+    return logp, ent
+
+
+# ------------------------------------------------------------------------------------------------
+# categorical distribution-level ops
+def categorical_fwd(logits: torch.Tensor, mask: Optional[torch.Tensor], actions: torch.Tensor):
+    _cuda(logits, torch.float32, "logits")
+    R, n = logits.shape
+    m = _as_u8(mask, "mask")
+    _cuda(actions, None, "actions")
+    logp = torch.empty(R, dtype=torch.float32, device=logits.device)
+    ent = torch.empty(R, dtype=torch.float32, device=logits.device)
+    rc = _lib.lib().b200rl_categorical_fwd_f32(
+        logits.data_ptr(), _ptr(m), actions.data_ptr(), _INDEX_DTYPES[actions.dtype], R, n, logp.data_ptr(),
+        ent.data_ptr(), _stream(),
+    )  # fmt: skip
+    check(rc, "b200rl_categorical_fwd_f32")
+    return logp, ent
+
+
+def categorical_bwd(logits, mask, actions, dlogp, dent):
+    R, n = logits.shape
+    m = _as_u8(mask, "mask")
+    dlogits = torch.empty_like(logits)
+    rc = _lib.lib().b200rl_categorical_bwd_f32(
+        logits.data_ptr(), _ptr(m), actions.data_ptr(), _INDEX_DTYPES[actions.dtype], R, n,
+        _cuda(dlogp.contiguous(), torch.float32, "dlogp").data_ptr(),
+        _cuda(dent.contiguous(), torch.float32, "dentropy").data_ptr(), dlogits.data_ptr(), _stream(),
+    )  # fmt: skip
+    check(rc, "b200rl_categorical_bwd_f32")
+    return dlogits
+
+
+class _CategoricalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, mask, actions):
+        logits = logits.contiguous()
+        logp, ent = categorical_fwd(logits, mask, actions)
+        ctx.save_for_backward(logits, actions)
+        ctx.mask = mask
+        return logp, ent
+
+    @staticmethod
+    def backward(ctx, dlogp, dent):
+        logits, actions = ctx.saved_tensors
+        return categorical_bwd(logits, ctx.mask, actions, dlogp, dent), None, None
+
+
+def categorical_logp_entropy(logits, mask, actions):
+    """Differentiable (log_prob [R], entropy [R]) of a masked categorical (categorical.py:12-54)."""
+    return _CategoricalFn.apply(logits, mask, actions)
+
+
+def categorical_sample(logits: torch.Tensor, mask: Optional[torch.Tensor], seed: int, offset: int):
+    _cuda(logits, torch.float32, "logits")
+    R, n = logits.shape
+    m = _as_u8(mask, "mask")
+    actions = torch.empty(R, dtype=torch.int64, device=logits.device)
+    logp = torch.empty(R, dtype=torch.float32, device=logits.device)
+    rc = _lib.lib().b200rl_categorical_sample_f32(
+        logits.data_ptr(), _ptr(m), R, n, seed, offset, actions.data_ptr(), logp.data_ptr(), _stream()
+    )
+    check(rc, "b200rl_categorical_sample_f32")
+    return actions, logp
+
+
+# ------------------------------------------------------------------------------------------------
+# GridNet
+@dataclass(frozen=True)
+class GridnetSpec:
+    """Static description of a per-cell MultiDiscrete head (gridnet.py:39-66)."""
+
+    nvec: Tuple[int, ...]
+    gates: Tuple[Tuple[int, int, int], ...] = ()  # (head, reference head, required value)
+    n_pick: int = 0
+
+    @staticmethod
+    def from_subaction_mask(nvec, subaction_mask=None, n_pick: int = 0) -> "GridnetSpec":
+        gates = []
+        for ref, per_head in (subaction_mask or {}).items():
+            if hasattr(per_head, "reference_index"):  # already {head: ValueDependentMask}
+                gates.append((int(ref), int(per_head.reference_index), int(per_head.value)))
+            else:
+                for head, value in per_head.items():
+                    gates.append((int(head), int(ref), int(value)))
+        return GridnetSpec(tuple(int(n) for n in nvec), tuple(sorted(gates)), int(n_pick))
+
+
+class _GridCall:
+    def __init__(self, spec: GridnetSpec, logits, mask, pick_mask, actions, pick_actions):
+        if logits.dtype not in _LOGIT_DTYPES:
+            raise TypeError(f"logits: expected float32 or bfloat16, got {logits.dtype}")
+        _cuda(logits, None, "logits")
+        A, S = len(spec.nvec), sum(spec.nvec)
+        Sp = S + spec.n_pick
+        if logits.shape[-1] != Sp:
+            raise ValueError(f"logits last dim {logits.shape[-1]} != sum(nvec) + n_pick = {Sp}")
+        B = logits.shape[0]
+        HW = logits.numel() // (B * Sp) if B else 0
+        self.B, self.HW, self.A, self.S, self.Sp = B, HW, A, S, Sp
+        self.mask = _as_u8(mask, "mask")
+        if self.mask.numel() != B * HW * S:
+            raise ValueError(f"mask has {self.mask.numel()} elements, expected {B * HW * S}")
+        self.pick_mask = _as_u8(pick_mask, "pick_mask") if spec.n_pick else None
+        if spec.n_pick and (self.pick_mask is None or self.pick_mask.numel() != B * spec.n_pick * HW):
+            raise ValueError("pick_mask must be [B, n_pick, HW]")
+        self.actions, self.pick_actions = actions, pick_actions
+        if actions is not None:
+            _cuda(actions, None, "actions")
+            if actions.numel() != B * HW * A:
+                raise ValueError(f"actions has {actions.numel()} elements, expected {B * HW * A}")
+        if spec.n_pick and pick_actions is not None:
+            _cuda(pick_actions, None, "pick_actions")
+        self._nvec = (C.c_int32 * A)(*spec.nvec)
+        gate_ref, gate_val = [-1] * A, [0] * A
+        for head, ref, value in spec.gates:
+            gate_ref[head], gate_val[head] = ref, value
+        self._gref, self._gval = (C.c_int32 * A)(*gate_ref), (C.c_int32 * A)(*gate_val)
+        d = GridnetDesc()
+        d.B, d.HW, d.A, d.n_pick = B, HW, A, spec.n_pick
+        d.logits_dtype = _LOGIT_DTYPES[logits.dtype]
+        d.act_dtype = _INDEX_DTYPES[actions.dtype] if actions is not None else _lib.U8
+        d.pick_dtype = _INDEX_DTYPES[pick_actions.dtype] if pick_actions is not None else _lib.I64
+        d.nvec_host, d.gate_ref_host, d.gate_val_host = self._nvec, self._gref, self._gval
+        self.desc = d
+
+
+def gridnet_fwd(spec, logits, mask, pick_mask, actions, pick_actions):
+    g = _GridCall(spec, logits, mask, pick_mask, actions, pick_actions)
+    logp = torch.empty(g.B, dtype=torch.float32, device=logits.device)
+    ent = torch.empty(g.B, dtype=torch.float32, device=logits.device)
+    rc = _lib.lib().b200rl_gridnet_fwd(
+        C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), actions.data_ptr(),
+        _ptr(pick_actions), logp.data_ptr(), ent.data_ptr(), _stream(),
+    )  # fmt: skip
+    check(rc, "b200rl_gridnet_fwd")
+    return logp, ent
+
+
+def gridnet_bwd(spec, logits, mask, pick_mask, actions, pick_actions, dlogp, dent):
+    g = _GridCall(spec, logits, mask, pick_mask, actions, pick_actions)
+    dlogits = torch.empty_like(logits)
+    dlogp = _cuda(dlogp.contiguous(), torch.float32, "dlogp")
+    dent = _cuda(dent.contiguous(), torch.float32, "dentropy")
+    rc = _lib.lib().b200rl_gridnet_bwd(
+        C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), actions.data_ptr(),
+        _ptr(pick_actions), dlogp.data_ptr(), dent.data_ptr(), dlogits.data_ptr(), _stream(),
+    )  # fmt: skip
+    check(rc, "b200rl_gridnet_bwd")
+    return dlogits
+
+
+class _GridnetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, spec, mask, pick_mask, actions, pick_actions):
+        logits = logits.contiguous()
+        logp, ent = gridnet_fwd(spec, logits, mask, pick_mask, actions, pick_actions)
+        ctx.save_for_backward(logits)
+        ctx.rest = (spec, mask, pick_mask, actions, pick_actions)
+        return logp, ent
+
+    @staticmethod
+    def backward(ctx, dlogp, dent):
+        (logits,) = ctx.saved_tensors
+        spec, mask, pick_mask, actions, pick_actions = ctx.rest
+        return gridnet_bwd(spec, logits, mask, pick_mask, actions, pick_actions, dlogp, dent), None, None, None, None, None
+
+
+def gridnet_logp_entropy(spec, logits, mask, pick_mask, actions, pick_actions):
+    """Differentiable (log_prob [B], entropy [B]) of the GridNet distribution (gridnet.py:104-193)."""
+    return _GridnetFn.apply(logits, spec, mask, pick_mask, actions, pick_actions)
+
+
+def ppo_gridnet_loss(
+    h: PpoHyper,
+    spec: GridnetSpec,
+    logits: torch.Tensor,
+    mask: torch.Tensor,
+    pick_mask: Optional[torch.Tensor],
+    actions: torch.Tensor,
+    pick_actions: Optional[torch.Tensor],
+    old_logp: torch.Tensor,
+    adv: torch.Tensor,
+    old_values: torch.Tensor,
+    returns: torch.Tensor,
+    new_values: torch.Tensor,
+    moments: Optional[torch.Tensor] = None,
+    want_logp: bool = False,
+) -> LossOut:
+    """One launch: masked log-prob/entropy forward, PPO loss, backward into dlogits / dvalues."""
+    g = _GridCall(spec, logits, mask, pick_mask, actions, pick_actions)
+    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments)
+    dlogits = torch.empty_like(logits)
+    logp = torch.empty(g.B, dtype=torch.float32, device=logits.device) if want_logp else None
+    ent = torch.empty(g.B, dtype=torch.float32, device=logits.device) if want_logp else None
+    rc = _lib.lib().b200rl_ppo_gridnet_loss(
+        C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), actions.data_ptr(),
+        _ptr(pick_actions), C.byref(call.args), dlogits.data_ptr(), _ptr(logp), _ptr(ent),
+        call.workspace.data_ptr(), call.workspace.numel(), _stream(),
+    )  # fmt: skip
+    check(rc, "b200rl_ppo_gridnet_loss")
+    return LossOut(call.stats, call.dvalues, (dlogits,), logp, ent)
+
+
+def gridnet_sample(spec: GridnetSpec, logits, mask, pick_mask, seed: int, offset: int, act_dtype=torch.uint8):
+    """Sample per-cell actions (+ pick) and their joint log-prob in one launch (gridnet.py:195-207)."""
+    g = _GridCall(spec, logits, mask, pick_mask, None, None)
+    actions = torch.empty((g.B, g.HW, g.A), dtype=act_dtype, device=logits.device)
+    pick = torch.empty((g.B, spec.n_pick), dtype=torch.int64, device=logits.device) if spec.n_pick else None
+    logp = torch.empty(g.B, dtype=torch.float32, device=logits.device)
+    g.desc.act_dtype = _INDEX_DTYPES[act_dtype]
+    g.desc.pick_dtype = _lib.I64
+    rc = _lib.lib().b200rl_gridnet_sample(
+        C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), seed, offset,
+        actions.data_ptr(), _ptr(pick), logp.data_ptr(), _stream(),
+    )  # fmt: skip
+    check(rc, "b200rl_gridnet_sample")
+    return actions, pick, logp

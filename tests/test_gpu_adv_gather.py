@@ -1,0 +1,87 @@
+"""K2 / K3 parity: advantage moments + normalisation (ppo.py:307-318) and the minibatch row gather
+(rollout.py:56-69), plus the VecRollout index stream (vec_rollout.py:166-175; bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.ppo_loss import normalize_advantages
+from oracle.rollout import minibatch_index_stream
+from tests.test_gpu_gridnet import close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,V,B", [(1024, 1, 256), (12288, 1, 3072), (4096, 13, 128), (500, 3, 500), (64, 2, 2)])
+@pytest.mark.parametrize("mode", ["normalize", "standardize", "after_scaling", "none"])
+def test_adv_normalize(cuda, M, V, B, mode):
+    from rl_algo_impls_b200 import ops
+
+    g = torch.Generator().manual_seed(M + V)
+    adv = (torch.randn(M, V, generator=g) * 3 + 1) if V > 1 else (torch.randn(M, generator=g) * 3 + 1)
+    idx = torch.randperm(M, generator=g)[:B]
+    w = torch.linspace(0.2, 1.0, V) if V > 1 else None
+    kw = dict(normalize_advantage=mode == "normalize", standardize_advantage=mode == "standardize",
+              normalize_advantages_after_scaling=mode == "after_scaling")
+    want = normalize_advantages(adv[idx], multi_reward_weights=w, **kw)
+    m = {"normalize": ops.ADV_NORMALIZE, "standardize": ops.ADV_STANDARDIZE, "after_scaling": ops.ADV_AFTER_SCALING,
+         "none": ops.ADV_NONE}[mode]
+    adv_d = adv.to(cuda).reshape(M, V)
+    got = ops.adv_normalize(adv_d, idx.to(cuda), m, w.tolist() if w is not None else None)
+    close(got, want.reshape(got.shape), rtol=2e-5, what="normalised advantages")
+
+
+def test_gather_rows_bit_exact(cuda):
+    from rl_algo_impls_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    M, B = 700, 300
+    srcs = [
+        torch.randint(0, 255, (M, 4, 84, 84), dtype=torch.uint8, generator=g),  # Atari obs (28,224 B rows)
+        torch.randn(M, generator=g),  # logprobs
+        torch.randint(0, 6, (M, 256, 7), generator=g),  # int64 per-cell actions
+        torch.rand(M, 256, 78, generator=g) < 0.5,  # bool masks (19,968 B rows)
+        torch.randn(M, 13, generator=g),  # multi-head values (52 B rows)
+        torch.randn(M, 17, generator=g).double(),  # f64 obs
+        torch.randint(0, 255, (M, 3, 5), dtype=torch.uint8, generator=g),  # 15 B rows: unaligned scalar path
+        torch.randn(M, 75, 9, generator=g),  # 2,700 B rows: 4-byte aligned only
+    ]
+    idx = torch.randperm(M, generator=g)[:B]
+    outs = ops.gather_rows([s.to(cuda) for s in srcs], idx.to(cuda))
+    for s, o in zip(srcs, outs):
+        assert o.dtype == s.dtype and o.shape == (B,) + s.shape[1:]
+        assert torch.equal(o.cpu(), s[idx])
+
+
+def test_vec_rollout_index_stream_and_batches(cuda):
+    """Same seed -> the same randperm stream as the reference's VecRollout.minibatches, and every
+    minibatch field equals the flat rollout indexed by it (short last minibatch kept)."""
+    from rl_algo_impls_b200.rollout import VecRollout
+    from oracle.gae import gae_advantages
+    from tests.synth import gae_inputs
+
+    T, N, bs = 16, 10, 48  # 160 steps -> 3 full minibatches + one of 16
+    inp = gae_inputs(3, T, N, 1, 0.05)
+    rng = np.random.default_rng(0)
+    obs = rng.standard_normal((T, N, 4), dtype=np.float32)
+    actions = rng.integers(0, 2, size=(T, N))
+    logprobs = rng.standard_normal((T, N), dtype=np.float32)
+    r = VecRollout(cuda, inp["next_episode_starts"], inp["next_values"], obs, actions, inp["rewards"],
+                   inp["episode_starts"], inp["values"], logprobs, None, gamma=0.99, gae_lambda=0.95)
+    adv = gae_advantages(gamma=0.99, gae_lambda=0.95, **inp)
+    assert r.total_steps == T * N and r.num_minibatches(bs) == 4
+    np.testing.assert_array_equal(r.y_true, (adv + inp["values"]).reshape(-1))
+    np.testing.assert_array_equal(r.y_pred, inp["values"].reshape(-1))
+    torch.manual_seed(77)
+    want_stream = minibatch_index_stream(T * N, bs, shuffle=True)
+    torch.manual_seed(77)
+    got = list(r.minibatches(bs, shuffle=True))
+    assert [len(b) for b in got] == [48, 48, 48, 16]
+    for mb, idx in zip(got, want_stream):
+        i = idx.numpy()
+        np.testing.assert_array_equal(mb.obs.cpu().numpy(), obs.reshape(-1, 4)[i])
+        np.testing.assert_array_equal(mb.actions.cpu().numpy(), actions.reshape(-1)[i])
+        np.testing.assert_array_equal(mb.logprobs.cpu().numpy(), logprobs.reshape(-1)[i])
+        np.testing.assert_array_equal(mb.advantages.cpu().numpy(), adv.reshape(-1)[i])
+        np.testing.assert_array_equal(mb.values.cpu().numpy(), inp["values"].reshape(-1)[i])
+    got2 = list(r.minibatches(bs, shuffle=False))
+    np.testing.assert_array_equal(got2[0].logprobs.cpu().numpy(), logprobs.reshape(-1)[:48])
