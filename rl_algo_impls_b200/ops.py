@@ -108,6 +108,8 @@ def gae_scan(
     adv = out_advantages if out_advantages is not None else torch.empty_like(rewards)
     ret = out_returns if out_returns is not None else torch.empty_like(rewards)
     _cuda(adv, torch.float32, "out_advantages"), _cuda(ret, torch.float32, "out_returns")
+    if T == 0 or N == 0:  # nothing to scan (and empty tensors have null data pointers)
+        return adv, ret
     rc = _lib.lib().b200rl_gae_scan_f32(
         rewards.data_ptr(), values.data_ptr(), es.data_ptr(), nes.data_ptr(), next_values.data_ptr(),
         g, lam, int(gamma_is_scalar), adv.data_ptr(), ret.data_ptr(), T, N, V, _stream(),

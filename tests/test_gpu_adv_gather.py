@@ -6,7 +6,7 @@ import torch
 
 from oracle.ppo_loss import normalize_advantages
 from oracle.rollout import minibatch_index_stream
-from tests.test_gpu_gridnet import close
+from tests.parity import close
 
 pytestmark = pytest.mark.gpu
 

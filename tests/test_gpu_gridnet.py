@@ -10,14 +10,7 @@ from tests.synth import LUX_GATES, LUX_NVEC, MICRORTS_GATES, MICRORTS_NVEC, grid
 
 pytestmark = pytest.mark.gpu
 
-RTOL = 1e-5  # north_star: within 1e-5 relative fp32
-
-
-def close(got: torch.Tensor, want: torch.Tensor, rtol=RTOL, what=""):
-    got, want = got.detach().cpu().double(), want.detach().cpu().double()
-    scale = want.abs().max().item() if want.numel() else 0.0
-    err = (got - want).abs().max().item() if want.numel() else 0.0
-    assert err <= rtol * max(scale, 1e-30) + 1e-30, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+from tests.parity import close, close_conditioned  # noqa: E402
 
 
 def oracle_dist(inp, nvec, gates, HW):
@@ -63,9 +56,10 @@ def test_gridnet_fwd_bwd(cuda, B, HW, nvec, gates, n_pick, unit_p):
     spec = spec_of(nvec, gates, n_pick)
     logp_g, ent_g = ops.gridnet_logp_entropy(spec, lg, dv["mask"], dv["pick_mask"], dv["actions"], dv["pick_actions"])
     (logp_g * dlogp.to(cuda) + ent_g * dent.to(cuda)).sum().backward()
-    close(logp_g, logp, what="logp")
-    close(ent_g, ent, what="entropy")
-    close(lg.grad, logits.grad, what="dlogits")
+    atol = 4e-7 * inp["logits"].abs().max().item()  # logp = x_a - lse cancels to ~0 on near-certain rows
+    close(logp_g, logp, atol=atol, what="logp")
+    close(ent_g, ent, atol=atol, what="entropy")
+    close(lg.grad, logits.grad, atol=atol * 0.1, what="dlogits")
     # bit-exact mask handling: masked entries and cells without a unit get exactly zero gradient
     S = sum(nvec)
     masked = ~inp["mask"]
@@ -87,22 +81,34 @@ def test_gridnet_action_dtypes(cuda, act_dtype):
     close(ent_g, dist.entropy(), what="entropy")
 
 
+def _oracle_fused(inp, pp, nvec, gates, HW, dtype, old_logp, V, adv_mode_kw, clip_vf, halving, weights):
+    f = lambda t: t.to(dtype) if t is not None and t.is_floating_point() else t
+    inp = dict(inp, logits=f(inp["logits"]))
+    logits, dist, action = oracle_dist(inp, nvec, gates, HW)
+    logp, ent = dist.log_prob(action), dist.entropy()
+    if old_logp is None:
+        old_logp = (logp.detach() + pp["old_logp_noise"]).float()
+    new_values = f(pp["new_values"]).clone().requires_grad_(True)
+    w = torch.tensor(weights, dtype=dtype) if weights is not None else None
+    adv = normalize_advantages(f(pp["adv"]), multi_reward_weights=w, **adv_mode_kw)
+    vf_coef = torch.linspace(0.5, 1.0, V, dtype=dtype) if V > 1 else torch.tensor(0.5, dtype=dtype)
+    parts = ppo_loss(logp, ent, new_values, f(old_logp), adv, f(pp["old_values"]), f(pp["returns"]),
+                     clip_range=0.1, clip_range_vf=clip_vf, ent_coef=0.01, vf_coef=vf_coef,
+                     ppo2_vf_coef_halving=halving)
+    parts.loss.backward()
+    return dict(logp=logp.detach(), entropy=ent.detach(), parts=parts, dlogits=logits.grad, dvalues=new_values.grad,
+                old_logp=old_logp, vf_coef=vf_coef)
+
+
 def _fused_case(cuda, B, HW, nvec, gates, n_pick, unit_p, V, adv_mode_kw, clip_vf, halving, weights, seed=0):
     from rl_algo_impls_b200 import ops
 
     inp = to_torch(gridnet_inputs(31 + seed + B + HW, B, HW, nvec, n_pick, unit_p))
     pp = to_torch(ppo_inputs(seed, B, V))
-    logits, dist, action = oracle_dist(inp, nvec, gates, HW)
-    with torch.no_grad():
-        old_logp = dist.log_prob(action) + pp["old_logp_noise"]
-    new_values = pp["new_values"].clone().requires_grad_(True)
-    w = torch.tensor(weights, dtype=torch.float32) if weights is not None else None
-    adv = normalize_advantages(pp["adv"], multi_reward_weights=w, **adv_mode_kw)
-    vf_coef = torch.linspace(0.5, 1.0, V) if V > 1 else torch.tensor(0.5)
-    parts = ppo_loss(dist.log_prob(action), dist.entropy(), new_values, old_logp, adv, pp["old_values"], pp["returns"],
-                     clip_range=0.1, clip_range_vf=clip_vf, ent_coef=0.01, vf_coef=vf_coef,
-                     ppo2_vf_coef_halving=halving)
-    parts.loss.backward()
+    o32 = _oracle_fused(inp, pp, nvec, gates, HW, torch.float32, None, V, adv_mode_kw, clip_vf, halving, weights)
+    o64 = _oracle_fused(inp, pp, nvec, gates, HW, torch.float64, o32["old_logp"], V, adv_mode_kw, clip_vf, halving,
+                        weights)
+    parts, parts64, old_logp = o32["parts"], o64["parts"], o32["old_logp"]
 
     if adv_mode_kw.get("normalize_advantages_after_scaling"):
         mode = ops.ADV_AFTER_SCALING
@@ -112,7 +118,7 @@ def _fused_case(cuda, B, HW, nvec, gates, n_pick, unit_p, V, adv_mode_kw, clip_v
         mode = ops.ADV_STANDARDIZE
     else:
         mode = ops.ADV_NONE
-    h = ops.PpoHyper(clip_range=0.1, clip_range_vf=clip_vf, ent_coef=0.01, vf_coef=vf_coef.reshape(-1).tolist(),
+    h = ops.PpoHyper(clip_range=0.1, clip_range_vf=clip_vf, ent_coef=0.01, vf_coef=o32["vf_coef"].reshape(-1).tolist(),
                      vf_halving=halving, adv_mode=mode, adv_weights=weights)
     dv = {k: (v.to(cuda) if v is not None else None) for k, v in inp.items()}
     out = ops.ppo_gridnet_loss(h, spec_of(nvec, gates, n_pick), dv["logits"], dv["mask"], dv["pick_mask"],
@@ -121,19 +127,20 @@ def _fused_case(cuda, B, HW, nvec, gates, n_pick, unit_p, V, adv_mode_kw, clip_v
                                want_logp=True)
     torch.cuda.synchronize()
     stats = out.stats.cpu()
-    close(out.logp, dist.log_prob(action), what="logp")
-    close(stats[0], parts.loss, what="loss")
-    close(stats[1], parts.pi_loss, what="pi_loss")
+    close(out.logp, o32["logp"], what="logp")
+    close(out.entropy, o32["entropy"], what="entropy")
+    close_conditioned(stats[0], parts.loss, parts64.loss, what="loss")
+    close_conditioned(stats[1], parts.pi_loss, parts64.pi_loss, what="pi_loss")
     close(stats[2], parts.entropy_loss, what="entropy_loss")
-    assert abs(stats[3].item() - parts.approx_kl) <= 1e-5 * max(abs(parts.approx_kl), 1e-3)
-    assert abs(stats[4].item() - parts.clipped_frac) < 0.5 / B  # exact count
+    close_conditioned(stats[3], torch.tensor(parts.approx_kl), torch.tensor(parts64.approx_kl), what="approx_kl")
+    assert abs(stats[4].item() - parts.clipped_frac) <= 1.5 / B  # counts; a ratio on the clip edge may flip
     close(stats[5 : 5 + V], parts.v_loss.reshape(-1), what="v_loss")
     np.testing.assert_allclose(stats[5 + V : 5 + 2 * V].numpy(), np.asarray(parts.val_clipped_frac).reshape(-1),
                                atol=0.5 / B)
-    close(out.grads[0], logits.grad, what="dlogits")
-    close(out.dvalues, new_values.grad, what="dvalues")
+    close_conditioned(out.grads[0], o32["dlogits"], o64["dlogits"], what="dlogits")
+    close(out.dvalues, o32["dvalues"], what="dvalues")
     S = sum(nvec)
-    assert (out.grads[0].cpu()[..., :S][~inp["mask"]] == 0).all()
+    assert (out.grads[0].cpu()[..., :S][~inp["mask"]] == 0).all()  # bit-exact mask handling
 
 
 def test_fused_microrts(cuda):

@@ -7,7 +7,7 @@ import torch
 from oracle.distributions import MaskedLogits, gaussian_logp_entropy
 from oracle.ppo_loss import normalize_advantages, ppo_loss
 from tests.synth import ppo_inputs, to_torch
-from tests.test_gpu_gridnet import close
+from tests.parity import close, close_conditioned
 
 pytestmark = pytest.mark.gpu
 
@@ -76,6 +76,21 @@ def test_fused_categorical(cuda, B, n, clip_vf, norm):
     close(out.dvalues, nv.grad, what="dvalues")
 
 
+def _gauss_oracle(mu, log_std, actions, pp, old_logp, dtype):
+    f = lambda t: t.to(dtype)
+    mu_r, ls_r = f(mu).clone().requires_grad_(True), f(log_std).clone().requires_grad_(True)
+    nv = f(pp["new_values"]).clone().requires_grad_(True)
+    logp, ent = gaussian_logp_entropy(mu_r, ls_r, f(actions))
+    if old_logp is None:
+        old_logp = (logp.detach() + pp["old_logp_noise"]).float()
+    adv = normalize_advantages(f(pp["adv"]), normalize_advantage=True)
+    parts = ppo_loss(logp, ent, nv, f(old_logp), adv, f(pp["old_values"]), f(pp["returns"]), clip_range=0.1,
+                     clip_range_vf=None, ent_coef=4e-4, vf_coef=torch.tensor(0.581, dtype=dtype))
+    parts.loss.backward()
+    return dict(parts=parts, logp=logp.detach(), ent=ent.detach(), dmu=mu_r.grad, dls=ls_r.grad, dv=nv.grad,
+                old_logp=old_logp)
+
+
 @pytest.mark.parametrize("B,D", [(64, 6), (16384, 6), (100, 17)])
 def test_fused_gaussian(cuda, B, D):
     from rl_algo_impls_b200 import ops
@@ -85,29 +100,23 @@ def test_fused_gaussian(cuda, B, D):
     log_std = torch.full((D,), -2.0) + 0.1 * torch.randn(D, generator=g)
     actions = mu + torch.exp(log_std) * torch.randn(B, D, generator=g)
     pp = to_torch(ppo_inputs(B + 1, B, 1))
-    mu_r, ls_r = mu.clone().requires_grad_(True), log_std.clone().requires_grad_(True)
-    with torch.no_grad():
-        old_logp = gaussian_logp_entropy(mu, log_std, actions)[0] + pp["old_logp_noise"]
-    nv = pp["new_values"].clone().requires_grad_(True)
-    logp, ent = gaussian_logp_entropy(mu_r, ls_r, actions)
-    adv = normalize_advantages(pp["adv"], normalize_advantage=True)
-    parts = ppo_loss(logp, ent, nv, old_logp, adv, pp["old_values"], pp["returns"], clip_range=0.1,
-                     clip_range_vf=None, ent_coef=4e-4, vf_coef=torch.tensor(0.581))
-    parts.loss.backward()
+    o32 = _gauss_oracle(mu, log_std, actions, pp, None, torch.float32)
+    o64 = _gauss_oracle(mu, log_std, actions, pp, o32["old_logp"], torch.float64)
+    old_logp, parts, parts64 = o32["old_logp"], o32["parts"], o64["parts"]
     h = ops.PpoHyper(clip_range=0.1, clip_range_vf=None, ent_coef=4e-4, vf_coef=[0.581])
     out = ops.ppo_gaussian_loss(h, mu.to(cuda), log_std.to(cuda), actions.to(cuda), old_logp.to(cuda),
                                 pp["adv"].to(cuda), pp["old_values"].to(cuda), pp["returns"].to(cuda),
                                 pp["new_values"].to(cuda))
     stats = out.stats.cpu()
-    close(stats[0], parts.loss, what="loss")
-    close(stats[1], parts.pi_loss, what="pi_loss")
+    close_conditioned(stats[0], parts.loss, parts64.loss, what="loss")
+    close_conditioned(stats[1], parts.pi_loss, parts64.pi_loss, what="pi_loss")
     close(stats[2], parts.entropy_loss, what="entropy_loss")
-    close(out.grads[0], mu_r.grad, what="dmu")
-    close(out.grads[1], ls_r.grad, what="dlog_std", rtol=2e-5)
-    close(out.dvalues, nv.grad, what="dvalues")
+    close_conditioned(out.grads[0], o32["dmu"], o64["dmu"], what="dmu")
+    close_conditioned(out.grads[1], o32["dls"], o64["dls"], what="dlog_std")
+    close(out.dvalues, o32["dv"], what="dvalues")
     lp_g, ent_g = ops.gaussian_logp_entropy(mu.to(cuda), log_std.to(cuda), actions.to(cuda))
-    close(lp_g, logp, what="logp")
-    close(ent_g, ent, what="entropy")
+    close(lp_g, o32["logp"], what="logp")
+    close(ent_g, o32["ent"], what="entropy")
 
 
 def test_scalar_stage_and_kl_cutoff(cuda):
