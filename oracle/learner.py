@@ -1,0 +1,191 @@
+"""Oracle: one PPO ``learn_epoch`` on the CPU -- rollout loop, GAE, minibatch loop, optimizer step.
+TEST INFRASTRUCTURE (see oracle/__init__.py); also the timed CPU baseline of bench.py.
+
+Restates, with torch-CPU / numpy (the reference's own arithmetic libraries):
+  * ``rl_algo_impls/rollout/sync_step_rollout.py:181-216``  the host rollout loop into numpy [T, N, ...] buffers
+  * ``rl_algo_impls/shared/policy/actor_critic.py:306-318``  policy.step: sample + log_prob, no grad
+  * ``rl_algo_impls/rollout/vec_rollout.py:38-175``          GAE, returns, flatten, randperm minibatches, gather
+  * ``rl_algo_impls/ppo/ppo.py:214-447``                     the minibatch loop, stats and optimizer step
+The policy trunk is whatever ``nn.Module`` the caller passes (it returns an object with ``pi``,
+``values`` and optionally ``log_std``); heads are the oracle distributions of oracle/distributions.py.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .distributions import Gridnet, MaskedLogits, gates_from_subaction_mask, gaussian_logp_entropy
+from .gae import gae_advantages, gae_returns
+from .ppo_loss import normalize_advantages, ppo_loss
+from .rollout import flatten_time_major, minibatch_index_stream
+
+
+@dataclass
+class Hyper:
+    """The reference's PPO keyword arguments (ppo/ppo.py:107-140), same names and defaults."""
+
+    batch_size: int = 64
+    n_epochs: int = 10
+    gamma: Union[float, np.ndarray] = 0.99
+    gae_lambda: Union[float, np.ndarray] = 0.95
+    clip_range: float = 0.2
+    clip_range_vf: Optional[float] = None
+    normalize_advantage: bool = True
+    standardize_advantage: bool = False
+    ent_coef: float = 0.0
+    vf_coef: Union[float, Sequence[float]] = 0.5
+    ppo2_vf_coef_halving: bool = False
+    max_grad_norm: float = 0.5
+    multi_reward_weights: Optional[Sequence[float]] = None
+    gradient_accumulation: bool = False
+    kl_cutoff: Optional[float] = None
+    normalize_advantages_after_scaling: bool = False
+    learning_rate: float = 3e-4
+
+
+class OraclePolicy:
+    """forward / step of shared/policy/actor_critic.py over a caller-supplied trunk."""
+
+    def __init__(self, network: nn.Module, kind: str, nvec: Sequence[int] = (), map_size: int = 0,
+                 subaction_mask: Optional[Dict[int, Dict[int, int]]] = None):
+        self.network, self.kind, self.nvec, self.map_size = network, kind, tuple(nvec), map_size
+        self.gates = gates_from_subaction_mask(subaction_mask)
+
+    def parameters(self):
+        return self.network.parameters()
+
+    def _dist(self, out, masks):
+        if self.kind == "gridnet":
+            return Gridnet(self.map_size, self.nvec, out.pi, masks, self.gates)
+        if self.kind == "categorical":
+            return MaskedLogits(out.pi, masks)
+        return None
+
+    def forward(self, obs, actions, masks):
+        out = self.network(obs)
+        if self.kind == "gaussian":
+            logp, ent = gaussian_logp_entropy(out.pi, out.log_std, actions)
+            return logp, ent, out.values
+        d = self._dist(out, masks)
+        return d.log_prob(actions), d.entropy(), out.values
+
+    @torch.no_grad()
+    def step(self, obs, masks):
+        out = self.network(obs)
+        if self.kind == "gaussian":
+            a = out.pi + torch.exp(out.log_std) * torch.randn_like(out.pi)
+            return a, out.values, gaussian_logp_entropy(out.pi, out.log_std, a)[0]
+        d = self._dist(out, masks)
+        a = d.sample()
+        return a, out.values, d.log_prob(a)
+
+    @torch.no_grad()
+    def value(self, obs):
+        return self.network(obs).values
+
+
+def _t(a):
+    if a is None:
+        return None
+    if isinstance(a, dict):
+        return {k: _t(v) for k, v in a.items()}
+    return torch.as_tensor(a)
+
+
+def collect_rollout(policy: OraclePolicy, env, n_steps: int, state: dict) -> dict:
+    """sync_step_rollout.py:181-216 into freshly allocated numpy buffers.  ``state`` carries
+    next_obs / next_action_masks / next_episode_starts between rollouts."""
+    N = env.num_envs
+    if not state:
+        state["next_obs"], _ = env.reset()
+        state["next_masks"] = env.get_action_mask()
+        state["next_starts"] = np.ones(N, dtype=np.bool_)
+    bufs: Dict[str, list] = {k: [] for k in ("obs", "episode_starts", "masks", "actions", "values", "logprobs", "rewards")}
+    for _ in range(n_steps):
+        obs, masks = state["next_obs"], state["next_masks"]
+        bufs["obs"].append(np.asarray(obs)), bufs["episode_starts"].append(np.asarray(state["next_starts"]))
+        bufs["masks"].append(masks)
+        a, v, logp = policy.step(_t(np.asarray(obs)), _t(masks))
+        a_np = {k: x.numpy() for k, x in a.items()} if isinstance(a, dict) else a.numpy()
+        bufs["actions"].append(a_np), bufs["values"].append(v.numpy()), bufs["logprobs"].append(logp.numpy())
+        nobs, rew, term, trunc, _ = env.step(a_np)
+        bufs["rewards"].append(np.asarray(rew))
+        state["next_obs"], state["next_starts"] = nobs, np.logical_or(term, trunc)
+        state["next_masks"] = env.get_action_mask()
+    stack = lambda xs: ({k: np.stack([x[k] for x in xs]) for k in xs[0]} if isinstance(xs[0], dict)
+                        else (None if xs[0] is None else np.stack(xs)))
+    out = {k: stack(v) for k, v in bufs.items()}
+    out["next_values"] = policy.value(_t(np.asarray(state["next_obs"]))).numpy()
+    out["next_episode_starts"] = np.asarray(state["next_starts"])
+    return out
+
+
+def _flat(a):
+    if a is None:
+        return None
+    if isinstance(a, dict):
+        return {k: _flat(v) for k, v in a.items()}
+    return torch.as_tensor(flatten_time_major(np.asarray(a)))
+
+
+def _take(a, idx):
+    if a is None:
+        return None
+    if isinstance(a, dict):
+        return {k: v[idx] for k, v in a.items()}
+    return a[idx]
+
+
+def learn_epoch(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict, hp: Hyper) -> dict:
+    """vec_rollout.py:38-175 + ppo.py:258-447 on a collected rollout ``ro`` (numpy [T, N, ...] arrays)."""
+    adv = gae_advantages(ro["rewards"], ro["values"], ro["episode_starts"], ro["next_episode_starts"],
+                         ro["next_values"], hp.gamma, hp.gae_lambda)
+    ret = gae_returns(adv, ro["values"])
+    b = dict(obs=_flat(ro["obs"]), logprobs=_flat(ro["logprobs"]), actions=_flat(ro["actions"]),
+             masks=_flat(ro["masks"]), values=_flat(ro["values"]), adv=_flat(adv), returns=_flat(ret))
+    total = b["logprobs"].shape[0]
+    n_mb = total // hp.batch_size + (1 if total % hp.batch_size else 0)
+    w = torch.tensor(np.asarray(hp.multi_reward_weights), dtype=torch.float32) if hp.multi_reward_weights is not None else None
+    vf_coef = torch.tensor(np.asarray(hp.vf_coef), dtype=torch.float32)
+    params = list(policy.parameters())
+    pi_coef = 1
+    step_stats: List[dict] = []
+    grad_norms: List[float] = []
+
+    def optimizer_step() -> float:
+        gn = nn.utils.clip_grad_norm_(params, hp.max_grad_norm).item()
+        optimizer.step()
+        optimizer.zero_grad(set_to_none=True)
+        return gn
+
+    for _ in range(hp.n_epochs):
+        step_stats.clear(), grad_norms.clear()
+        for idx in minibatch_index_stream(total, hp.batch_size, shuffle=not hp.gradient_accumulation):
+            mb_adv = normalize_advantages(
+                b["adv"][idx], normalize_advantage=hp.normalize_advantage,
+                standardize_advantage=hp.standardize_advantage,
+                normalize_advantages_after_scaling=hp.normalize_advantages_after_scaling, multi_reward_weights=w)
+            logp, ent, v = policy.forward(b["obs"][idx], _take(b["actions"], idx), _take(b["masks"], idx))
+            parts = ppo_loss(logp, ent, v, b["logprobs"][idx], mb_adv, b["values"][idx], b["returns"][idx],
+                             clip_range=hp.clip_range, clip_range_vf=hp.clip_range_vf, ent_coef=hp.ent_coef,
+                             vf_coef=vf_coef, ppo2_vf_coef_halving=hp.ppo2_vf_coef_halving, pi_coef=pi_coef,
+                             kl_cutoff=hp.kl_cutoff, loss_divisor=n_mb if hp.gradient_accumulation else None)
+            pi_coef = parts.pi_coef
+            parts.loss.backward()
+            if not hp.gradient_accumulation:
+                grad_norms.append(optimizer_step())
+            step_stats.append(dict(loss=parts.loss.item(), pi_loss=parts.pi_loss.item(),
+                                   v_loss=parts.v_loss.detach().numpy().copy(), entropy_loss=parts.entropy_loss.item(),
+                                   approx_kl=parts.approx_kl, clipped_frac=parts.clipped_frac,
+                                   val_clipped_frac=np.asarray(parts.val_clipped_frac)))
+        if hp.gradient_accumulation:
+            grad_norms.append(optimizer_step())
+    y_true, y_pred = flatten_time_major(ret), flatten_time_major(ro["values"])
+    var_y = np.var(y_true).item()
+    stats = {k: np.mean([s[k] for s in step_stats], axis=0) for k in step_stats[0]}
+    stats["explained_var"] = np.nan if var_y == 0 else 1 - np.var(y_true - y_pred).item() / var_y
+    stats["grad_norm"] = float(np.mean(grad_norms))
+    stats["total_steps"] = total
+    return stats

@@ -1,0 +1,396 @@
+"""PPO learner over the fused B200 kernels.
+
+Mirrors ``rl_algo_impls/ppo/ppo.py:106-447``: same constructor keywords (every one is a YAML key of
+the reference's hyperparams files), same mutable attributes (callbacks ``setattr`` them between
+epochs, hyperparam_transitions.py:19-43), same ``learn`` / ``learn_epoch`` / ``optimizer_step``
+and the same ``TrainStats`` handed to ``callback.on_step``.
+
+What differs is the inside of the minibatch loop (ppo.py:290-409).  The reference runs ~60-80
+eager torch ops per action head forward, twice that backward, ~20 loss ops and 6-8 host syncs per
+minibatch; here one minibatch is
+
+    K3 gather  ->  trunk forward (PyTorch)  ->  K2 moments  ->  K4 fused loss fwd+bwd (one launch:
+    dlogits, dvalues, stats)  ->  torch.autograd.backward through the trunk  ->  optimizer step
+
+with the statistics left on the device and read back once per ``learn_epoch``.  Under
+``torch.distributed`` (one process per GPU, envs sharded) the advantage moments and the gradients
+are all-reduced so that the update equals the single-process update on the concatenated minibatch.
+"""
+import gc
+from dataclasses import asdict, astuple, dataclass
+from time import perf_counter
+from typing import Dict, List, NamedTuple, Optional, Sequence, Tuple, TypeVar, Union
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+from torch.optim import Adam
+
+from .. import ops
+from ..algorithm import Algorithm, update_learning_rate
+
+NumOrList = Union[float, int, Sequence[float]]
+
+
+def num_or_array(x):
+    """shared/tensor_utils.py: a list becomes a float64 ndarray, a number stays a number."""
+    return np.array(x, dtype=np.float64) if isinstance(x, (list, tuple, np.ndarray)) else x
+
+
+class TrainStepStats(NamedTuple):
+    loss: float
+    pi_loss: float
+    v_loss: np.ndarray
+    entropy_loss: float
+    approx_kl: float
+    clipped_frac: float
+    val_clipped_frac: np.ndarray
+    additional_losses: Dict[str, float]
+
+
+@dataclass
+class TrainStats:
+    loss: float
+    pi_loss: float
+    v_loss: Union[float, np.ndarray]
+    entropy_loss: float
+    approx_kl: float
+    clipped_frac: float
+    val_clipped_frac: Union[float, np.ndarray]
+    additional_losses: Dict[str, float]
+    explained_var: float
+    grad_norm: float
+
+    def __init__(self, step_stats: List[TrainStepStats], explained_var: float, grad_norms: List[float]) -> None:
+        self.loss = np.mean([s.loss for s in step_stats]).item()
+        self.pi_loss = np.mean([s.pi_loss for s in step_stats]).item()
+        self.v_loss = np.mean([s.v_loss for s in step_stats], axis=0)
+        self.entropy_loss = np.mean([s.entropy_loss for s in step_stats]).item()
+        self.approx_kl = np.mean([s.approx_kl for s in step_stats]).item()
+        self.clipped_frac = np.mean([s.clipped_frac for s in step_stats]).item()
+        self.val_clipped_frac = np.mean([s.val_clipped_frac for s in step_stats], axis=0)
+        self.additional_losses = {
+            k: np.mean([s.additional_losses[k] for s in step_stats]).item() for k in step_stats[0].additional_losses
+        }
+        self.explained_var = explained_var
+        self.grad_norm = np.mean(grad_norms).item()
+
+    def write_to_tensorboard(self, tb_writer) -> None:
+        for name, value in asdict(self).items():
+            if isinstance(value, np.ndarray):
+                for idx, v in enumerate(value.flatten()):
+                    tb_writer.add_scalar(f"losses/{name}_{idx}", v)
+            elif isinstance(value, dict):
+                for k, v in value.items():
+                    tb_writer.add_scalar(f"losses/{k}", v)
+            else:
+                tb_writer.add_scalar(f"losses/{name}", value)
+
+
+PPOSelf = TypeVar("PPOSelf", bound="PPO")
+
+
+def _world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class PPO(Algorithm):
+    def __init__(
+        self,
+        policy,
+        device: torch.device,
+        tb_writer=None,
+        learning_rate: float = 3e-4,
+        batch_size: int = 64,
+        n_epochs: int = 10,
+        gamma: NumOrList = 0.99,
+        gae_lambda: NumOrList = 0.95,
+        clip_range: float = 0.2,
+        clip_range_vf: Optional[float] = None,
+        normalize_advantage: bool = True,
+        standardize_advantage: bool = False,
+        ent_coef: float = 0.0,
+        vf_coef: NumOrList = 0.5,
+        ppo2_vf_coef_halving: bool = False,
+        max_grad_norm: float = 0.5,
+        multi_reward_weights: Optional[List[float]] = None,
+        gradient_accumulation: bool = False,
+        kl_cutoff: Optional[float] = None,
+        freeze_policy_head: bool = False,
+        freeze_value_head: bool = False,
+        freeze_backbone: bool = False,
+        switch_range: Optional[int] = None,
+        guide_probability: Optional[float] = None,
+        normalize_advantages_after_scaling: bool = False,
+        autocast_loss: bool = False,
+        vf_loss_fn: str = "mse_loss",
+        vf_weights: Optional[List[float]] = None,
+        teacher_kl_loss_coef: Optional[float] = None,
+        teacher_kl_loss_fn=None,
+        teacher_loss_importance_sampling: bool = True,
+    ) -> None:
+        super().__init__(policy, device, tb_writer, learning_rate,
+                         Adam(policy.parameters(), lr=learning_rate, eps=1e-7))
+        self.policy = policy
+        self.gamma = num_or_array(gamma)
+        self.gae_lambda = num_or_array(gae_lambda)
+        self.max_grad_norm = max_grad_norm
+        self.clip_range = clip_range
+        self.clip_range_vf = clip_range_vf
+        self.normalize_advantage = normalize_advantage
+        self.standardize_advantage = standardize_advantage
+        assert not (normalize_advantage and standardize_advantage), "Cannot both normalize and standardize advantage"
+        self.ent_coef = ent_coef
+        self.vf_coef = num_or_array(vf_coef)
+        self.vf_weights = np.array(vf_weights) if vf_weights is not None else None
+        self.ppo2_vf_coef_halving = ppo2_vf_coef_halving
+        self.batch_size = batch_size
+        self.n_epochs = n_epochs
+        self.multi_reward_weights = np.array(multi_reward_weights) if multi_reward_weights else None
+        self.gradient_accumulation = gradient_accumulation
+        self.kl_cutoff = kl_cutoff
+        self.freeze_policy_head = freeze_policy_head
+        self.freeze_value_head = freeze_value_head
+        self.freeze_backbone = freeze_backbone
+        self.switch_range = switch_range
+        self.guide_probability = guide_probability
+        self.normalize_advantages_after_scaling = normalize_advantages_after_scaling
+        self.autocast_loss = autocast_loss
+        if vf_loss_fn != "mse_loss":
+            raise NotImplementedError(f"vf_loss_fn={vf_loss_fn!r}: the fused kernels implement the reference default, mse_loss")
+        if teacher_kl_loss_coef or teacher_kl_loss_fn is not None:
+            raise NotImplementedError("teacher-KL loss is outside the path built so far (SURVEY.md section 8f, rank 3)")
+        self.teacher_kl_loss_coef = teacher_kl_loss_coef
+        self.teacher_kl_loss_fn = teacher_kl_loss_fn
+        self.teacher_loss_importance_sampling = teacher_loss_importance_sampling
+        self.last_train_stats: Optional[TrainStats] = None
+        self.launches_last_epoch = 0  # our kernels launched by the last learn_epoch (bench.py reports it)
+
+    # ---------------------------------------------------------------------------------------------
+    def learn(self: PPOSelf, train_timesteps: int, rollout_generator, callbacks: Optional[List] = None,
+              total_timesteps: Optional[int] = None, start_timesteps: int = 0) -> PPOSelf:
+        if total_timesteps is None:
+            total_timesteps = train_timesteps
+        assert start_timesteps + train_timesteps <= total_timesteps
+        timesteps_elapsed = start_timesteps
+        while timesteps_elapsed < start_timesteps + train_timesteps:
+            timesteps_elapsed, should_continue = self.learn_epoch(timesteps_elapsed, total_timesteps,
+                                                                  rollout_generator, callbacks)
+            if not should_continue:
+                break
+        return self
+
+    # ---------------------------------------------------------------------------------------------
+    def _hyper(self, V: int, adv_v: int, loss_scale: float, pi_coef: float) -> ops.PpoHyper:
+        """Host scalars of this epoch, re-read every learn_epoch (callbacks may have changed them)."""
+        vf = np.broadcast_to(np.asarray(self.vf_coef, dtype=np.float64).reshape(-1), (V,)).copy() \
+            if np.ndim(self.vf_coef) == 0 or len(np.atleast_1d(self.vf_coef)) == 1 \
+            else np.asarray(self.vf_coef, dtype=np.float64).reshape(-1)
+        if self.vf_weights is not None:
+            # v_loss @ vf_weights -> scalar value loss (ppo.py:344-345): fold the weights into vf_coef
+            assert np.ndim(self.vf_coef) == 0 or np.size(self.vf_coef) == 1, "vf_weights needs a scalar vf_coef"
+            vf = float(np.asarray(self.vf_coef).reshape(-1)[0]) * np.asarray(self.vf_weights, dtype=np.float64)
+        assert vf.size == V, f"vf_coef has {vf.size} entries for {V} value heads"
+        if self.normalize_advantages_after_scaling:
+            mode = ops.ADV_AFTER_SCALING
+        elif self.normalize_advantage:
+            mode = ops.ADV_NORMALIZE
+        elif self.standardize_advantage:
+            mode = ops.ADV_STANDARDIZE
+        else:
+            mode = ops.ADV_NONE
+        w = None if self.multi_reward_weights is None else [float(x) for x in self.multi_reward_weights]
+        if adv_v > 1 and w is None:
+            raise ValueError("multi-head advantages need multi_reward_weights (ppo.py:317-318)")
+        return ops.PpoHyper(clip_range=float(self.clip_range), clip_range_vf=self.clip_range_vf,
+                            ent_coef=float(self.ent_coef), vf_coef=[float(x) for x in vf],
+                            vf_halving=bool(self.ppo2_vf_coef_halving), pi_coef=pi_coef, loss_scale=loss_scale,
+                            adv_mode=mode, adv_weights=w)
+
+    def _moments(self, adv: torch.Tensor, h: ops.PpoHyper) -> Optional[torch.Tensor]:
+        if h.adv_mode == ops.ADV_NONE:
+            return None
+        B = adv.shape[0]
+        moments = ops.adv_moments(adv.reshape(B, -1), None, h.adv_mode, h.adv_weights)
+        self.launches_last_epoch += 2
+        if _world() > 1:  # exact global-minibatch statistics: (sum, sumsq, count) are additive
+            dist.all_reduce(moments)
+        return moments
+
+    def _minibatch(self, mb, h: ops.PpoHyper, pi_coef_state: Optional[torch.Tensor]) -> Tuple[torch.Tensor, int]:
+        """Forward + fused loss + backward of one minibatch.  Returns the device stats vector."""
+        obs, old_logp, actions, masks, _, old_values, adv, returns, _additional = (
+            mb.obs, mb.logprobs, mb.actions, mb.action_masks, mb.num_actions, mb.values, mb.advantages, mb.returns,
+            mb.additional)
+        policy = self.policy
+        B = obs.shape[0]
+        moments = self._moments(adv, h)
+        kind = getattr(policy, "kind", None)
+        fused = kind is not None and hasattr(policy, "head_outputs") and self.kl_cutoff is None
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(self.autocast_loss)):
+            if fused:
+                out = policy.head_outputs(obs)
+            else:
+                logp_a, entropy, new_values = policy(obs, actions, action_masks=masks)
+        if fused:
+            values = out.values
+            v32 = values.detach().float().contiguous()
+            if kind == "gridnet":
+                cells = actions["per_position"] if isinstance(actions, dict) else actions
+                pick = actions.get("pick_position") if isinstance(actions, dict) else None
+                cmask = masks["per_position"] if isinstance(masks, dict) else masks
+                pmask = masks.get("pick_position") if isinstance(masks, dict) else None
+                logits = out.pi.detach()
+                logits = logits.reshape(B, policy.map_size, logits.shape[-1])
+                if not logits.is_contiguous():
+                    logits = logits.contiguous()
+                res = ops.ppo_gridnet_loss(h, policy.spec, logits, cmask, pmask, cells, pick, old_logp, adv,
+                                           old_values, returns, v32, moments=moments)
+                grads = [res.grads[0].reshape(out.pi.shape)]
+                roots = [out.pi]
+            elif kind == "categorical":
+                logits = out.pi.detach().float().contiguous()
+                res = ops.ppo_categorical_loss(h, logits, masks, actions, old_logp, adv, old_values, returns, v32,
+                                               moments=moments)
+                grads, roots = [res.grads[0].to(out.pi.dtype)], [out.pi]
+            else:
+                mu = out.pi.detach().float().contiguous()
+                res = ops.ppo_gaussian_loss(h, mu, out.log_std.detach().float().contiguous(),
+                                            actions.float().contiguous(), old_logp, adv, old_values, returns, v32,
+                                            moments=moments)
+                grads, roots = [res.grads[0].to(out.pi.dtype), res.grads[1]], [out.pi, out.log_std]
+            self.launches_last_epoch += 2
+            roots.append(values)
+            grads.append(res.dvalues.reshape(values.shape).to(values.dtype))
+            torch.autograd.backward(roots, grads)
+            return res.stats, 1
+        # distribution-level path: any policy with forward(obs, actions, masks) -> (logp, entropy, v)
+        res = ops.ppo_scalar_loss(h, logp_a.detach().float().contiguous(), entropy.detach().float().contiguous(),
+                                  old_logp, adv, old_values, returns, new_values.detach().float().contiguous(),
+                                  moments=moments, kl_cutoff=self.kl_cutoff, pi_coef_state=pi_coef_state)
+        self.launches_last_epoch += 2 + (2 if self.kl_cutoff is not None else 0)
+        torch.autograd.backward(
+            [logp_a, entropy, new_values],
+            [res.grads[0].to(logp_a.dtype).reshape(logp_a.shape), res.grads[1].to(entropy.dtype).reshape(entropy.shape),
+             res.dvalues.reshape(new_values.shape).to(new_values.dtype)])
+        return res.stats, 1
+
+    def learn_epoch(self, timesteps_elapsed: int, total_timesteps: int, rollout_generator,
+                    callbacks: Optional[List] = None) -> Tuple[int, bool]:
+        start_time = perf_counter()
+        self.launches_last_epoch = 0
+        update_learning_rate(self.optimizer, self.learning_rate)
+        if self.switch_range is not None:
+            assert hasattr(rollout_generator, "switch_range")
+            setattr(rollout_generator, "switch_range", self.switch_range)
+        if self.guide_probability is not None:
+            assert hasattr(rollout_generator, "guide_probability")
+            setattr(rollout_generator, "guide_probability", self.guide_probability)
+        if self.tb_writer is not None:
+            self._log_chart_scalars(timesteps_elapsed)
+
+        r = rollout_generator.rollout(gamma=self.gamma, gae_lambda=self.gae_lambda)
+        self.launches_last_epoch += 1 + getattr(rollout_generator, "n_steps", 0)  # GAE scan + one sample launch per step
+        timesteps_elapsed += r.total_steps
+
+        V = int(np.prod(r.values.shape[2:])) if hasattr(r, "values") else 1
+        n_mb = r.num_minibatches(self.batch_size)
+        loss_scale = 1.0 / n_mb if self.gradient_accumulation else 1.0
+        h = self._hyper(V, V, loss_scale, 1.0)
+        pi_coef_state = torch.ones(1, dtype=torch.float32, device=self.device) if self.kl_cutoff is not None else None
+        if self.freeze_policy_head or self.freeze_value_head or self.freeze_backbone:
+            self.policy.freeze(self.freeze_policy_head, self.freeze_value_head, self.freeze_backbone)
+
+        step_stats: List[torch.Tensor] = []
+        grad_norms: List[torch.Tensor] = []
+        for _ in range(self.n_epochs):
+            step_stats.clear()  # only the last epoch's stats are reported (ppo.py:287-289)
+            grad_norms.clear()
+            for mb in r.minibatches(self.batch_size, shuffle=not self.gradient_accumulation):
+                self.launches_last_epoch += 2  # K3 gather: wide + narrow launch
+                self.policy.reset_noise(self.batch_size)
+                stats, _ = self._minibatch(mb, h, pi_coef_state)
+                step_stats.append(stats)
+                if not self.gradient_accumulation:
+                    grad_norms.append(self.optimizer_step_device())
+            if self.gradient_accumulation:
+                grad_norms.append(self.optimizer_step_device())
+        if self.freeze_policy_head or self.freeze_value_head or self.freeze_backbone:
+            self.policy.unfreeze()
+
+        # one device -> host read for the whole epoch
+        ev = r.explained_variance() if hasattr(r, "explained_variance") else None
+        packed = torch.stack(step_stats).double()
+        norms = torch.stack(grad_norms).double().reshape(-1)
+        tail = torch.cat([norms, ev.reshape(1).double()]) if ev is not None else norms
+        host = torch.cat([packed.reshape(-1), tail]).cpu().numpy()
+        S = packed.shape[1]
+        rows = host[: packed.numel()].reshape(-1, S)
+        gn = host[packed.numel(): packed.numel() + norms.numel()]
+        if ev is not None:
+            explained_var = float(host[-1])
+        else:
+            var_y = np.var(r.y_true).item()
+            explained_var = np.nan if var_y == 0 else 1 - np.var(r.y_true - r.y_pred).item() / var_y
+        steps = [
+            TrainStepStats(float(x[0]), float(x[1]), _vec(x[5:5 + V], V), float(x[2]), float(x[3]), float(x[4]),
+                           _vec(x[5 + V:5 + 2 * V], V), {})
+            for x in rows
+        ]
+        train_stats = TrainStats(steps, explained_var, [float(g) for g in gn])
+        self.last_train_stats = train_stats
+        rollout_steps = r.total_steps
+        if self.tb_writer is not None:
+            train_stats.write_to_tensorboard(self.tb_writer)
+            self.tb_writer.add_scalar("train/steps_per_second", rollout_steps / (perf_counter() - start_time))
+            if hasattr(self.tb_writer, "on_steps"):
+                self.tb_writer.on_steps(rollout_steps)
+        if callbacks:
+            if not all(c.on_step(timesteps_elapsed=rollout_steps, train_stats=train_stats) for c in callbacks):
+                return timesteps_elapsed, False
+        return timesteps_elapsed, True
+
+    # ---------------------------------------------------------------------------------------------
+    def _sync_grads(self, params: List[nn.Parameter]) -> None:
+        """Data-parallel ranks (envs sharded): one all-reduce of the flattened gradients, then / R,
+        issued before the clip so that clipping sees the global gradient (ppo.py:441-447)."""
+        world = _world()
+        if world == 1:
+            return
+        grads = [p.grad for p in params]
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat)
+        flat.div_(world)
+        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+            g.copy_(f)
+
+    def optimizer_step_device(self) -> torch.Tensor:
+        params = [p for p in self.policy.parameters() if p.grad is not None]
+        self._sync_grads(params)
+        grad_norm = nn.utils.clip_grad_norm_(params, self.max_grad_norm)
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=True)
+        return grad_norm.detach()
+
+    def optimizer_step(self) -> float:
+        return self.optimizer_step_device().item()
+
+    def _log_chart_scalars(self, timesteps_elapsed: int) -> None:
+        scalars = {"learning_rate": self.optimizer.param_groups[0]["lr"], "ent_coef": self.ent_coef,
+                   "pi_clip": self.clip_range, "gamma": self.gamma, "gae_lambda": self.gae_lambda,
+                   "vf_coef": self.vf_coef}
+        if self.clip_range_vf is not None:
+            scalars["v_clip"] = self.clip_range_vf
+        if self.multi_reward_weights is not None:
+            scalars["reward_weights"] = self.multi_reward_weights
+        for name, value in scalars.items():
+            if isinstance(value, np.ndarray):
+                for i, v in enumerate(value.reshape(-1)):
+                    self.tb_writer.add_scalar(f"charts/{name}_{i}", float(v), timesteps_elapsed)
+            else:
+                self.tb_writer.add_scalar(f"charts/{name}", float(value), timesteps_elapsed)
+
+
+def _vec(x: np.ndarray, V: int):
+    return np.asarray(x, dtype=np.float64) if V > 1 else np.asarray(x[0], dtype=np.float64)

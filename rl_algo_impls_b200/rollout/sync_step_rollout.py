@@ -1,0 +1,266 @@
+"""SyncStepRolloutGenerator: the rollout buffer and step loop, resident in HBM.
+
+Mirrors ``rl_algo_impls/rollout/sync_step_rollout.py:14-294`` (constructor keywords, ``prepare``,
+``rollout(gamma, gae_lambda) -> VecRollout``, the masked-reset options).  What changes is where
+the buffers live: the reference keeps host numpy ``[T, N, ...]`` arrays (:98-131) and round-trips
+every policy step through H2D / D2H copies (actor_critic.py:306-318); here the arrays are CUDA
+tensors allocated once, ``policy.step_device`` samples and evaluates log-probs in one launch and
+its outputs are written straight into row ``s`` of the buffers.  A host ``VectorEnv`` (numpy in,
+numpy out -- the reference's contract) still works: its observations / masks are uploaded through
+pinned staging buffers and the sampled actions are downloaded for ``env.step``; a device env
+(CUDA tensors in / out) never touches PCIe.
+"""
+from typing import Dict, Optional, Union
+
+import numpy as np
+import torch
+
+from .rollout import RolloutGenerator
+from .vec_rollout import VecRollout
+
+_TORCH_DTYPES = {"float32": torch.float32, "float64": torch.float32, "uint8": torch.uint8, "int64": torch.int64,
+                 "bool": torch.bool, "int32": torch.int32, "float16": torch.float16}
+
+
+def _torch_dtype(np_dtype) -> torch.dtype:
+    return _TORCH_DTYPES[np.dtype(np_dtype).name]
+
+
+class _Uploader:
+    """numpy -> CUDA through a reusable pinned staging buffer (one per distinct field)."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self._pinned: Dict[str, torch.Tensor] = {}
+        self._done: Dict[str, torch.cuda.Event] = {}
+
+    def __call__(self, name: str, src, dst: torch.Tensor) -> None:
+        if isinstance(src, torch.Tensor):
+            dst.copy_(src, non_blocking=True)
+            return
+        a = np.ascontiguousarray(src)
+        stage = self._pinned.get(name)
+        if stage is None or stage.shape != a.shape or stage.dtype != dst.dtype:
+            stage = torch.empty(a.shape, dtype=dst.dtype, pin_memory=True)
+            self._pinned[name] = stage
+            self._done[name] = torch.cuda.Event()
+        else:
+            self._done[name].synchronize()  # the previous upload out of this staging buffer has landed
+        stage.copy_(torch.from_numpy(a))  # host-side convert (e.g. float64 obs -> float32) + copy
+        dst.copy_(stage, non_blocking=True)
+        self._done[name].record()
+
+
+class SyncStepRolloutGenerator(RolloutGenerator):
+    def __init__(
+        self,
+        policy,
+        vec_env,
+        n_steps: int = 2048,
+        sde_sample_freq: int = -1,
+        scale_advantage_by_values_accuracy: bool = False,
+        full_batch_off_accelerator: bool = False,
+        include_logp: bool = True,
+        subaction_mask: Optional[Dict[int, Dict[int, int]]] = None,
+        num_envs_reset_every_rollout: int = 0,
+        rolling_num_envs_reset_every_rollout: int = 0,
+        random_num_envs_reset_every_rollout: int = 0,
+        prepare_steps: int = 0,
+        rolling_num_envs_reset_every_prepare_step: int = 0,
+    ) -> None:
+        super().__init__(policy, vec_env)
+        self.n_steps = int(n_steps)
+        self.sde_sample_freq = sde_sample_freq
+        self.scale_advantage_by_values_accuracy = scale_advantage_by_values_accuracy
+        self.full_batch_off_accelerator = full_batch_off_accelerator
+        self.include_logp = include_logp
+        self.subaction_mask = subaction_mask
+        for name, v in (("num_envs_reset_every_rollout", num_envs_reset_every_rollout),
+                        ("rolling_num_envs_reset_every_rollout", rolling_num_envs_reset_every_rollout),
+                        ("random_num_envs_reset_every_rollout", random_num_envs_reset_every_rollout),
+                        ("rolling_num_envs_reset_every_prepare_step", rolling_num_envs_reset_every_prepare_step)):
+            assert v % 2 == 0, f"{name} must be even, got {v}"
+        self.num_envs_reset_every_rollout = num_envs_reset_every_rollout
+        self.rolling_num_envs_reset_every_rollout = rolling_num_envs_reset_every_rollout
+        self.random_num_envs_reset_every_rollout = random_num_envs_reset_every_rollout
+        self.prepare_steps = prepare_steps
+        self.rolling_num_envs_reset_every_prepare_step = rolling_num_envs_reset_every_prepare_step
+        N = vec_env.num_envs
+        assert N > (num_envs_reset_every_rollout + rolling_num_envs_reset_every_rollout
+                    + random_num_envs_reset_every_rollout), "more envs reset per rollout than envs"
+        self.rolling_mask_idx = 0
+        self.rolling_reset_indexes = np.random.permutation(N // 2)
+
+        self.device = torch.device(policy.device)
+        if self.device.type != "cuda":
+            raise RuntimeError("SyncStepRolloutGenerator keeps the rollout in HBM: the policy must be on a CUDA device")
+        self._upload = _Uploader(self.device)
+        self.get_action_mask = getattr(vec_env, "get_action_mask", None)
+
+        T = self.n_steps
+        dev = self.device
+        obs_space = vec_env.single_observation_space
+        value_shape = tuple(policy.value_shape)
+        act_shape = policy.action_shape
+        self.obs = torch.zeros((T, N) + tuple(obs_space.shape), dtype=_torch_dtype(obs_space.dtype), device=dev)
+        self.rewards = torch.zeros((T, N) + value_shape, dtype=torch.float32, device=dev)
+        self.episode_starts = torch.zeros((T, N), dtype=torch.bool, device=dev)
+        self.values = torch.zeros((T, N) + value_shape, dtype=torch.float32, device=dev)
+        self.logprobs = torch.zeros((T, N), dtype=torch.float32, device=dev) if include_logp else None
+        self.next_episode_starts = torch.ones((N,), dtype=torch.bool, device=dev)
+        self.next_obs = torch.zeros((N,) + tuple(obs_space.shape), dtype=self.obs.dtype, device=dev)
+
+        kind = getattr(policy, "kind", None)
+        if isinstance(act_shape, dict):
+            self.actions = {
+                k: torch.zeros((T, N) + tuple(s), dtype=torch.uint8 if k == "per_position" else torch.int64, device=dev)
+                for k, s in act_shape.items()
+            }
+        else:
+            adt = torch.uint8 if kind == "gridnet" else (torch.float32 if kind == "gaussian" else torch.int64)
+            self.actions = torch.zeros((T, N) + tuple(act_shape), dtype=adt, device=dev)
+
+        first_obs, _ = vec_env.reset()
+        self._upload("obs", first_obs, self.next_obs)
+        self.action_masks = None
+        self.next_action_masks = None
+        if self.get_action_mask is not None:
+            m = self.get_action_mask()
+            if m is not None:
+                if isinstance(m, dict):
+                    self.action_masks = {k: torch.zeros((T,) + tuple(v.shape), dtype=torch.bool, device=dev) for k, v in m.items()}
+                    self.next_action_masks = {k: torch.zeros(tuple(v.shape), dtype=torch.bool, device=dev) for k, v in m.items()}
+                else:
+                    self.action_masks = torch.zeros((T,) + tuple(m.shape), dtype=torch.bool, device=dev)
+                    self.next_action_masks = torch.zeros(tuple(m.shape), dtype=torch.bool, device=dev)
+                self._upload_masks(m)
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _upload_masks(self, m) -> None:
+        if isinstance(m, dict):
+            for k, v in m.items():
+                self._upload("mask_" + k, v, self.next_action_masks[k])
+        else:
+            self._upload("mask", m, self.next_action_masks)
+
+    def _env_actions(self, a):
+        """What vec_env.step receives: CUDA tensors for a device env, numpy (int64 / f32) for a host env."""
+        if getattr(self.vec_env, "device", None) is not None:
+            return a
+        from ..policy.actor_critic import clamp_actions
+
+        if isinstance(a, dict):
+            return {k: t.cpu().numpy().astype(np.int64) for k, t in a.items()}
+        a_np = a.cpu().numpy()
+        if a_np.dtype == np.uint8:
+            a_np = a_np.astype(np.int64)
+        return clamp_actions(a_np, self.vec_env.single_action_space, getattr(self.policy, "squash_output", False))
+
+    def prepare(self) -> None:
+        if not self.prepare_steps:
+            return
+        for _ in range(0, self.prepare_steps, self.n_steps):
+            self._rollout(output_next_values=False)
+            self._reset_envs(0, self.rolling_num_envs_reset_every_prepare_step, 0)
+
+    # -- the step loop (sync_step_rollout.py:181-216) ------------------------------------------------
+    def _rollout(self, output_next_values: bool) -> Optional[torch.Tensor]:
+        self.policy.eval()
+        self.policy.reset_noise()
+        for s in range(self.n_steps):
+            if self.sde_sample_freq > 0 and s > 0 and s % self.sde_sample_freq == 0:
+                self.policy.reset_noise()
+            self.obs[s].copy_(self.next_obs, non_blocking=True)
+            self.episode_starts[s].copy_(self.next_episode_starts, non_blocking=True)
+            masks_s = None
+            if self.action_masks is not None:
+                if isinstance(self.action_masks, dict):
+                    for k, buf in self.action_masks.items():
+                        buf[s].copy_(self.next_action_masks[k], non_blocking=True)
+                    masks_s = {k: buf[s] for k, buf in self.action_masks.items()}
+                else:
+                    self.action_masks[s].copy_(self.next_action_masks, non_blocking=True)
+                    masks_s = self.action_masks[s]
+            a, v, logp = self.policy.step_device(self.obs[s], masks_s)
+            self.values[s].copy_(v.reshape(self.values[s].shape), non_blocking=True)
+            if self.logprobs is not None:
+                self.logprobs[s].copy_(logp, non_blocking=True)
+            if isinstance(self.actions, dict):
+                for k, buf in self.actions.items():
+                    buf[s].copy_(a[k].reshape(buf[s].shape), non_blocking=True)
+            else:
+                self.actions[s].copy_(a.reshape(self.actions[s].shape), non_blocking=True)
+            next_obs, rewards, terminations, truncations, _ = self.vec_env.step(self._env_actions(a))
+            self._upload("obs", next_obs, self.next_obs)
+            self._upload("rewards", rewards, self.rewards[s])
+            if isinstance(terminations, torch.Tensor):
+                torch.logical_or(terminations, truncations, out=self.next_episode_starts)
+            else:
+                self._upload("starts", np.logical_or(terminations, truncations), self.next_episode_starts)
+            if self.get_action_mask is not None and self.next_action_masks is not None:
+                self._upload_masks(self.get_action_mask())
+        next_values = self.policy.value_device(self.next_obs) if output_next_values else None
+        self.policy.train()
+        return next_values
+
+    def rollout(self, gamma, gae_lambda) -> VecRollout:
+        next_values = self._rollout(output_next_values=True)
+        assert next_values is not None
+        self._reset_envs(self.num_envs_reset_every_rollout, self.rolling_num_envs_reset_every_rollout,
+                         self.random_num_envs_reset_every_rollout)
+        return VecRollout(
+            device=self.device,
+            next_episode_starts=self.next_episode_starts,
+            next_values=next_values,
+            obs=self.obs,
+            actions=self.actions,
+            rewards=self.rewards,
+            episode_starts=self.episode_starts,
+            values=self.values,
+            logprobs=self.logprobs,
+            action_masks=self.action_masks,
+            gamma=gamma,
+            gae_lambda=gae_lambda,
+            scale_advantage_by_values_accuracy=self.scale_advantage_by_values_accuracy,
+            full_batch_off_accelerator=self.full_batch_off_accelerator,
+            subaction_mask=self.subaction_mask,
+            action_plane_space=getattr(self.vec_env, "action_plane_space", None),
+        )
+
+    # -- masked resets (sync_step_rollout.py:218-278) ------------------------------------------------
+    def _reset_envs(self, num_envs_reset: int, rolling_num_envs_reset: int, random_num_envs_reset: int) -> None:
+        assert bool(num_envs_reset) + bool(rolling_num_envs_reset) + bool(random_num_envs_reset) <= 1, \
+            "Only one of num_envs_reset, rolling_num_envs_reset, random_num_envs_reset can be set"
+        N = self.vec_env.num_envs
+        reset = np.zeros(N, dtype=np.bool_)
+        if num_envs_reset > 0:
+            reset[-num_envs_reset:] = True
+        if rolling_num_envs_reset > 0:
+            pairs = len(self.rolling_reset_indexes)
+            end_idx = (self.rolling_mask_idx + rolling_num_envs_reset // 2) % pairs
+            if end_idx < self.rolling_mask_idx:
+                chosen = np.concatenate((self.rolling_reset_indexes[self.rolling_mask_idx:],
+                                         self.rolling_reset_indexes[:end_idx]))
+                self.rolling_reset_indexes = np.random.permutation(N // 2)
+            else:
+                chosen = self.rolling_reset_indexes[self.rolling_mask_idx:end_idx]
+            pair_mask = np.zeros(N // 2, dtype=np.bool_)
+            pair_mask[chosen] = True
+            reset[pair_mask.repeat(2)] = True
+            self.rolling_mask_idx = end_idx
+        if random_num_envs_reset > 0:
+            pair_mask = np.zeros(N // 2, dtype=np.bool_)
+            pair_mask[np.random.choice(N // 2, random_num_envs_reset // 2, replace=False)] = True
+            reset[pair_mask.repeat(2)] = True
+        assert reset.sum() == num_envs_reset + rolling_num_envs_reset + random_num_envs_reset
+        if not reset.any():
+            return
+        next_obs, action_mask, _ = self.vec_env.masked_reset(reset)
+        rows = torch.from_numpy(np.nonzero(reset)[0]).to(self.device)
+        self.next_obs[rows] = torch.as_tensor(next_obs).to(self.device, dtype=self.next_obs.dtype)
+        if self.next_action_masks is not None and action_mask is not None:
+            if isinstance(self.next_action_masks, dict):
+                for k, dst in self.next_action_masks.items():
+                    dst[rows] = torch.as_tensor(action_mask[k]).to(self.device, dtype=torch.bool)
+            else:
+                self.next_action_masks[rows] = torch.as_tensor(action_mask).to(self.device, dtype=torch.bool)

@@ -1,0 +1,34 @@
+"""Learner-level golden cases (hyperparameters + stub trunks), shared by the fixture generator and
+the tests.  Importable without the reference."""
+import numpy as np
+
+from oracle import learner as olearn
+from tests.golden.stub_nets import TinyGrid, TinyMlp
+from tests.synth import LUX_GATES, LUX_NVEC, MICRORTS_GATES, MICRORTS_NVEC
+
+LEARNER_CASES = {
+    "cartpole": dict(kind="categorical", T=32, N=8, obs_shape=(4,), nvec=(2,), V=1,
+                     hp=olearn.Hyper(batch_size=64, n_epochs=3, gamma=0.98, gae_lambda=0.8, clip_range=0.2,
+                                     ent_coef=0.0, learning_rate=1e-3)),
+    "gaussian": dict(kind="gaussian", T=16, N=8, obs_shape=(17,), nvec=(6,), V=1,
+                     hp=olearn.Hyper(batch_size=48, n_epochs=2, gamma=0.98, gae_lambda=0.92, clip_range=0.1,
+                                     ent_coef=4e-4, vf_coef=0.581, max_grad_norm=0.8, learning_rate=1e-3)),
+    "microrts": dict(kind="gridnet", T=8, N=6, obs_shape=(5, 8, 8), nvec=MICRORTS_NVEC, side=8, gates=MICRORTS_GATES, V=1,
+                     hp=olearn.Hyper(batch_size=20, n_epochs=2, gamma=0.999, gae_lambda=0.99, clip_range=0.1,
+                                     clip_range_vf=0.1, ppo2_vf_coef_halving=True, ent_coef=0.01, vf_coef=0.5,
+                                     learning_rate=1e-3)),
+    "lux": dict(kind="gridnet", T=6, N=4, obs_shape=(5, 8, 8), nvec=LUX_NVEC, side=8, gates=LUX_GATES, n_pick=1, V=3,
+                hp=olearn.Hyper(batch_size=8, n_epochs=2, gamma=np.array([1.0, 1.0, 0.99]),
+                                gae_lambda=np.array([0.95, 0.95, 0.9]), clip_range=0.1, ent_coef=0.01,
+                                vf_coef=[0.5, 0.25, 0.25], multi_reward_weights=[0.6, 0.3, 0.1],
+                                gradient_accumulation=True, learning_rate=1e-3)),
+}
+
+
+def make_net_for(case):
+    if case["kind"] == "gridnet":
+        n_logits = sum(case["nvec"]) + case.get("n_pick", 0)
+        return lambda: TinyGrid(case["obs_shape"][0], n_logits, case["V"])
+    return lambda: TinyMlp(case["obs_shape"][0], case["nvec"][0], case["V"], gaussian=case["kind"] == "gaussian")
+
+

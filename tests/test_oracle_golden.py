@@ -1,0 +1,140 @@
+"""The oracle against the golden fixtures generated from the live reference
+(tests/golden/make_golden.py).  CPU only: this is what pins the checker."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import learner as olearn
+from oracle.distributions import Gridnet, MaskedLogits, gaussian_logp_entropy
+from oracle.gae import gae_advantages, gae_returns
+from oracle.rollout import minibatch_index_stream
+from tests.golden.stub_nets import TinyGrid, TinyMlp
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
+
+
+def cases(z):
+    return sorted({k.split(".")[0] for k in z})
+
+
+def gates_of(arr):
+    return {int(h): (int(r), int(v)) for h, r, v in arr}
+
+
+@pytest.mark.parametrize("name", cases(load("gae")))
+def test_gae_matches_reference(name):
+    z = load("gae")
+    g = lambda k: z[f"{name}.{k}"]
+    gamma = float(g("gamma")) if bool(g("gamma_is_scalar")) else g("gamma")
+    lam = float(g("gae_lambda")) if bool(g("gamma_is_scalar")) else g("gae_lambda")
+    adv = gae_advantages(g("rewards"), g("values"), g("episode_starts"), g("next_episode_starts"), g("next_values"),
+                         gamma, lam)
+    np.testing.assert_array_equal(adv, g("advantages"))
+    np.testing.assert_array_equal(gae_returns(adv, g("values")), g("returns"))
+
+
+@pytest.mark.parametrize("name", cases(load("gridnet")))
+def test_gridnet_matches_reference(name):
+    z = load("gridnet")
+    g = lambda k: z.get(f"{name}.{k}")
+    t = lambda k: None if g(k) is None else torch.from_numpy(g(k))
+    masks = t("mask") if g("pick_mask") is None else {"per_position": t("mask"), "pick_position": t("pick_mask")}
+    action = t("actions") if g("pick_actions") is None else {"per_position": t("actions"), "pick_position": t("pick_actions")}
+    logits = t("logits").requires_grad_(True)
+    d = Gridnet(logits.shape[1], g("nvec").tolist(), logits, masks, gates_of(g("gates")))
+    logp, ent = d.log_prob(action), d.entropy()
+    (logp * t("dlogp") + ent * t("dentropy")).sum().backward()
+    np.testing.assert_array_equal(logp.detach().numpy(), g("logp"))
+    np.testing.assert_array_equal(ent.detach().numpy(), g("entropy"))
+    np.testing.assert_array_equal(logits.grad.numpy(), g("dlogits"))
+
+
+def test_fully_masked_rows_are_exact_zeros():
+    z = load("gridnet")
+    assert (z["all_masked.dlogits"][..., :-1] == 0).all()
+    # only the pick_position head (last logit) can carry anything when no cell has a unit
+    assert np.isfinite(z["all_masked.logp"]).all()
+
+
+@pytest.mark.parametrize("name", ["cartpole", "atari", "masked"])
+def test_categorical_matches_reference(name):
+    z = load("heads")
+    g = lambda k: z.get(f"{name}.{k}")
+    logits = torch.from_numpy(g("logits")).requires_grad_(True)
+    mask = torch.from_numpy(g("mask")) if g("mask") is not None else None
+    d = MaskedLogits(logits, mask)
+    a = torch.from_numpy(g("actions"))
+    logp, ent = d.log_prob(a), d.entropy()
+    (logp * torch.from_numpy(g("dlogp")) + ent * torch.from_numpy(g("dentropy"))).sum().backward()
+    np.testing.assert_array_equal(logp.detach().numpy(), g("logp"))
+    np.testing.assert_array_equal(ent.detach().numpy(), g("entropy"))
+    np.testing.assert_allclose(logits.grad.numpy(), g("dlogits"), rtol=1e-6, atol=1e-7)
+
+
+def test_gaussian_matches_reference():
+    z = load("heads")
+    g = lambda k: torch.from_numpy(z[f"gaussian.{k}"])
+    mu, ls = g("mu").requires_grad_(True), g("log_std").requires_grad_(True)
+    logp, ent = gaussian_logp_entropy(mu, ls, g("actions"))
+    np.testing.assert_array_equal(logp.detach().numpy(), z["gaussian.logp"])
+    np.testing.assert_array_equal(ent.detach().numpy(), z["gaussian.entropy"])
+    ((logp * g("dlogp")).sum() + (ent * g("dentropy")).sum()).backward()
+    np.testing.assert_allclose(mu.grad.numpy(), z["gaussian.dmu"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(ls.grad.numpy(), z["gaussian.dlog_std"], rtol=1e-5, atol=1e-6)
+
+
+def test_minibatch_index_stream_is_the_references():
+    z = load("index_stream")
+    torch.manual_seed(int(z["seed"]))
+    stream = minibatch_index_stream(int(z["total"]), int(z["batch_size"]), shuffle=True)
+    np.testing.assert_array_equal(np.concatenate([i.numpy() for i in stream]), z["shuffled"])
+    np.testing.assert_array_equal([len(i) for i in stream], z["sizes"])
+    seq = minibatch_index_stream(int(z["total"]), int(z["batch_size"]), shuffle=False)
+    np.testing.assert_array_equal(np.concatenate([i.numpy() for i in seq]), z["sequential"])
+
+
+def rollout_from(z):
+    ro = {}
+    for k, v in z.items():
+        if not k.startswith("ro."):
+            continue
+        parts = k.split(".")[1:]
+        if len(parts) == 2:
+            ro.setdefault(parts[0], {})[parts[1]] = v
+        else:
+            ro[parts[0]] = v
+    ro.setdefault("masks", None)
+    return ro
+
+
+def learner_setup(name):
+    from tests.golden.make_golden_cases import LEARNER_CASES, make_net_for
+
+    case = LEARNER_CASES[name]
+    z = load("learner_" + name)
+    net = make_net_for(case)()
+    net.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("init.")})
+    return case, z, net
+
+
+@pytest.mark.parametrize("name", ["cartpole", "gaussian", "microrts", "lux"])
+def test_oracle_learn_epoch_reproduces_the_reference(name):
+    """Same initial weights + rollout + randperm seed -> the reference PPO.learn_epoch's final
+    parameters and TrainStats, bit for bit."""
+    case, z, net = learner_setup(name)
+    hp = case["hp"]
+    pol = olearn.OraclePolicy(net, case["kind"], case["nvec"], case.get("side", 0) ** 2, case.get("gates"))
+    opt = torch.optim.Adam(net.parameters(), lr=hp.learning_rate, eps=1e-7)
+    torch.manual_seed(int(z["seed"]) + 100)
+    stats = olearn.learn_epoch(pol, opt, rollout_from(z), hp)
+    for k, v in net.state_dict().items():
+        np.testing.assert_array_equal(v.numpy(), z[f"final.{k}"], err_msg=k)
+    for k in ("loss", "pi_loss", "entropy_loss", "approx_kl", "clipped_frac", "grad_norm", "explained_var"):
+        assert np.float64(stats[k]) == z[f"stats.{k}"], k
+    np.testing.assert_array_equal(np.asarray(stats["v_loss"], np.float64), z["stats.v_loss"])
