@@ -26,6 +26,42 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelTimer:
+    """CUDA-event timing of individual C-ABI calls on torch's current stream (bench.py's roofline
+    leg).  Events are recorded on the stream the kernel is launched on; read with ``summary()``."""
+
+    def __init__(self, names: Optional[Sequence[str]] = None):
+        self.names = set(names) if names else None
+        self.events: Dict[str, List[Tuple[torch.cuda.Event, torch.cuda.Event]]] = {}
+
+    def summary(self) -> Dict[str, Tuple[int, float]]:
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(s.elapsed_time(e) for s, e in v) / len(v)) for k, v in self.events.items() if v}
+
+
+LAUNCHES = 0  # kernels of libb200rl.so launched since import (bench.py reports the delta)
+_timer: Optional[KernelTimer] = None
+
+
+def set_kernel_timer(timer: Optional[KernelTimer]) -> None:
+    global _timer
+    _timer = timer
+
+
+def _call(name: str, n_kernels: int, fn, *args) -> int:
+    global LAUNCHES
+    LAUNCHES += n_kernels
+    t = _timer
+    if t is None or (t.names is not None and name not in t.names):
+        return fn(*args)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn(*args)
+    e.record()
+    t.events.setdefault(name, []).append((s, e))
+    return rc
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -110,7 +146,7 @@ def gae_scan(
     _cuda(adv, torch.float32, "out_advantages"), _cuda(ret, torch.float32, "out_returns")
     if T == 0 or N == 0:  # nothing to scan (and empty tensors have null data pointers)
         return adv, ret
-    rc = _lib.lib().b200rl_gae_scan_f32(
+    rc = _call("b200rl_gae_scan_f32", 1, _lib.lib().b200rl_gae_scan_f32,
         rewards.data_ptr(), values.data_ptr(), es.data_ptr(), nes.data_ptr(), next_values.data_ptr(),
         g, lam, int(gamma_is_scalar), adv.data_ptr(), ret.data_ptr(), T, N, V, _stream(),
     )  # fmt: skip
@@ -135,7 +171,7 @@ def adv_moments(
     nbytes = L.b200rl_adv_moments_workspace_bytes(B, V)
     ws = _workspace(nbytes, adv.device)
     w = _f32_array(weights) if weights is not None else None
-    rc = L.b200rl_adv_moments_f64(
+    rc = _call("b200rl_adv_moments_f64", 2, L.b200rl_adv_moments_f64,
         adv.data_ptr(), _ptr(idx), B, V, mode, w, moments.data_ptr(), ws.data_ptr(), ws.numel(), _stream()
     )
     check(rc, "b200rl_adv_moments_f64")
@@ -159,7 +195,7 @@ def adv_normalize(
     out_v = 1 if (contract and (weights is not None or V == 1)) or mode == ADV_AFTER_SCALING else V
     out = torch.empty((B,) if out_v == 1 else (B, V), dtype=torch.float32, device=adv.device)
     w = _f32_array(weights) if weights is not None else None
-    rc = _lib.lib().b200rl_adv_normalize_f32(
+    rc = _call("b200rl_adv_normalize_f32", 1, _lib.lib().b200rl_adv_normalize_f32,
         adv.data_ptr(), _ptr(idx), B, V, mode, w, _ptr(moments), out.data_ptr(), out_v, _stream()
     )
     check(rc, "b200rl_adv_normalize_f32")
@@ -188,7 +224,7 @@ def gather_rows(sources: Sequence[torch.Tensor], idx: torch.Tensor) -> List[torc
             outs.append(d)
             src_arr[k], dst_arr[k] = s.data_ptr(), d.data_ptr()
             rb_arr[k] = (s.numel() // max(n_rows, 1)) * s.element_size()
-        rc = _lib.lib().b200rl_gather_rows(src_arr, dst_arr, rb_arr, n, idx.data_ptr(), B, n_rows, _stream())
+        rc = _call("b200rl_gather_rows", 2, _lib.lib().b200rl_gather_rows,src_arr, dst_arr, rb_arr, n, idx.data_ptr(), B, n_rows, _stream())
         check(rc, "b200rl_gather_rows")
     return outs
 
@@ -296,7 +332,7 @@ def ppo_scalar_loss(
     dlogp, dent = torch.empty_like(new_logp), torch.empty_like(entropy)
     if kl_cutoff is not None and pi_coef_state is None:
         raise ValueError("kl_cutoff needs a device pi_coef_state tensor")
-    rc = _lib.lib().b200rl_ppo_scalar_loss_f32(
+    rc = _call("b200rl_ppo_scalar_loss_f32", 2, _lib.lib().b200rl_ppo_scalar_loss_f32,
         new_logp.data_ptr(), entropy.data_ptr(), ent_d, B, C.byref(call.args),
         -1.0 if kl_cutoff is None else float(kl_cutoff), _ptr(pi_coef_state),
         dlogp.data_ptr(), dent.data_ptr(), call.workspace.data_ptr(), call.workspace.numel(), _stream(),
@@ -323,7 +359,7 @@ def ppo_categorical_loss(
     _cuda(actions, None, "actions")
     call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments)
     dlogits = torch.empty_like(logits)
-    rc = _lib.lib().b200rl_ppo_categorical_loss_f32(
+    rc = _call("b200rl_ppo_categorical_loss_f32", 2, _lib.lib().b200rl_ppo_categorical_loss_f32,
         logits.data_ptr(), _ptr(m), actions.data_ptr(), _INDEX_DTYPES[actions.dtype], B, n, C.byref(call.args),
         dlogits.data_ptr(), call.workspace.data_ptr(), call.workspace.numel(), _stream(),
     )  # fmt: skip
@@ -348,7 +384,7 @@ def ppo_gaussian_loss(
     B, D = mu.shape
     call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments)
     dmu, dls = torch.empty_like(mu), torch.empty_like(log_std)
-    rc = _lib.lib().b200rl_ppo_gaussian_loss_f32(
+    rc = _call("b200rl_ppo_gaussian_loss_f32", 3, _lib.lib().b200rl_ppo_gaussian_loss_f32,
         mu.data_ptr(), log_std.data_ptr(), actions.data_ptr(), B, D, C.byref(call.args), dmu.data_ptr(),
         dls.data_ptr(), call.workspace.data_ptr(), call.workspace.numel(), _stream(),
     )  # fmt: skip
@@ -362,7 +398,7 @@ def gaussian_logp_entropy(mu: torch.Tensor, log_std: torch.Tensor, actions: torc
     B, D = mu.shape
     logp = torch.empty(B, dtype=torch.float32, device=mu.device)
     ent = torch.empty(B, D, dtype=torch.float32, device=mu.device)
-    rc = _lib.lib().b200rl_gaussian_fwd_f32(
+    rc = _call("b200rl_gaussian_fwd_f32", 1, _lib.lib().b200rl_gaussian_fwd_f32,
         mu.data_ptr(), log_std.data_ptr(), actions.data_ptr(), B, D, logp.data_ptr(), ent.data_ptr(), _stream()
     )
     check(rc, "b200rl_gaussian_fwd_f32")
@@ -378,7 +414,7 @@ def categorical_fwd(logits: torch.Tensor, mask: Optional[torch.Tensor], actions:
     _cuda(actions, None, "actions")
     logp = torch.empty(R, dtype=torch.float32, device=logits.device)
     ent = torch.empty(R, dtype=torch.float32, device=logits.device)
-    rc = _lib.lib().b200rl_categorical_fwd_f32(
+    rc = _call("b200rl_categorical_fwd_f32", 1, _lib.lib().b200rl_categorical_fwd_f32,
         logits.data_ptr(), _ptr(m), actions.data_ptr(), _INDEX_DTYPES[actions.dtype], R, n, logp.data_ptr(),
         ent.data_ptr(), _stream(),
     )  # fmt: skip
@@ -390,7 +426,7 @@ def categorical_bwd(logits, mask, actions, dlogp, dent):
     R, n = logits.shape
     m = _as_u8(mask, "mask")
     dlogits = torch.empty_like(logits)
-    rc = _lib.lib().b200rl_categorical_bwd_f32(
+    rc = _call("b200rl_categorical_bwd_f32", 1, _lib.lib().b200rl_categorical_bwd_f32,
         logits.data_ptr(), _ptr(m), actions.data_ptr(), _INDEX_DTYPES[actions.dtype], R, n,
         _cuda(dlogp.contiguous(), torch.float32, "dlogp").data_ptr(),
         _cuda(dent.contiguous(), torch.float32, "dentropy").data_ptr(), dlogits.data_ptr(), _stream(),
@@ -425,7 +461,7 @@ def categorical_sample(logits: torch.Tensor, mask: Optional[torch.Tensor], seed:
     m = _as_u8(mask, "mask")
     actions = torch.empty(R, dtype=torch.int64, device=logits.device)
     logp = torch.empty(R, dtype=torch.float32, device=logits.device)
-    rc = _lib.lib().b200rl_categorical_sample_f32(
+    rc = _call("b200rl_categorical_sample_f32", 1, _lib.lib().b200rl_categorical_sample_f32,
         logits.data_ptr(), _ptr(m), R, n, seed, offset, actions.data_ptr(), logp.data_ptr(), _stream()
     )
     check(rc, "b200rl_categorical_sample_f32")
@@ -497,7 +533,7 @@ def gridnet_fwd(spec, logits, mask, pick_mask, actions, pick_actions):
     g = _GridCall(spec, logits, mask, pick_mask, actions, pick_actions)
     logp = torch.empty(g.B, dtype=torch.float32, device=logits.device)
     ent = torch.empty(g.B, dtype=torch.float32, device=logits.device)
-    rc = _lib.lib().b200rl_gridnet_fwd(
+    rc = _call("b200rl_gridnet_fwd", 1, _lib.lib().b200rl_gridnet_fwd,
         C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), actions.data_ptr(),
         _ptr(pick_actions), logp.data_ptr(), ent.data_ptr(), _stream(),
     )  # fmt: skip
@@ -510,7 +546,7 @@ def gridnet_bwd(spec, logits, mask, pick_mask, actions, pick_actions, dlogp, den
     dlogits = torch.empty_like(logits)
     dlogp = _cuda(dlogp.contiguous(), torch.float32, "dlogp")
     dent = _cuda(dent.contiguous(), torch.float32, "dentropy")
-    rc = _lib.lib().b200rl_gridnet_bwd(
+    rc = _call("b200rl_gridnet_bwd", 1, _lib.lib().b200rl_gridnet_bwd,
         C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), actions.data_ptr(),
         _ptr(pick_actions), dlogp.data_ptr(), dent.data_ptr(), dlogits.data_ptr(), _stream(),
     )  # fmt: skip
@@ -561,7 +597,7 @@ def ppo_gridnet_loss(
     dlogits = torch.empty_like(logits)
     logp = torch.empty(g.B, dtype=torch.float32, device=logits.device) if want_logp else None
     ent = torch.empty(g.B, dtype=torch.float32, device=logits.device) if want_logp else None
-    rc = _lib.lib().b200rl_ppo_gridnet_loss(
+    rc = _call("b200rl_ppo_gridnet_loss", 2, _lib.lib().b200rl_ppo_gridnet_loss,
         C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), actions.data_ptr(),
         _ptr(pick_actions), C.byref(call.args), dlogits.data_ptr(), _ptr(logp), _ptr(ent),
         call.workspace.data_ptr(), call.workspace.numel(), _stream(),
@@ -578,7 +614,7 @@ def gridnet_sample(spec: GridnetSpec, logits, mask, pick_mask, seed: int, offset
     logp = torch.empty(g.B, dtype=torch.float32, device=logits.device)
     g.desc.act_dtype = _INDEX_DTYPES[act_dtype]
     g.desc.pick_dtype = _lib.I64
-    rc = _lib.lib().b200rl_gridnet_sample(
+    rc = _call("b200rl_gridnet_sample", 1, _lib.lib().b200rl_gridnet_sample,
         C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), seed, offset,
         actions.data_ptr(), _ptr(pick), logp.data_ptr(), _stream(),
     )  # fmt: skip

@@ -165,7 +165,8 @@ class PPO(Algorithm):
         self.teacher_kl_loss_fn = teacher_kl_loss_fn
         self.teacher_loss_importance_sampling = teacher_loss_importance_sampling
         self.last_train_stats: Optional[TrainStats] = None
-        self.launches_last_epoch = 0  # our kernels launched by the last learn_epoch (bench.py reports it)
+        self.launches_last_epoch = 0  # libb200rl kernels launched by the last learn_epoch (bench.py reports it)
+        self.d2h_bytes_last_epoch = 0
 
     # ---------------------------------------------------------------------------------------------
     def learn(self: PPOSelf, train_timesteps: int, rollout_generator, callbacks: Optional[List] = None,
@@ -213,7 +214,6 @@ class PPO(Algorithm):
             return None
         B = adv.shape[0]
         moments = ops.adv_moments(adv.reshape(B, -1), None, h.adv_mode, h.adv_weights)
-        self.launches_last_epoch += 2
         if _world() > 1:  # exact global-minibatch statistics: (sum, sumsq, count) are additive
             dist.all_reduce(moments)
         return moments
@@ -260,7 +260,6 @@ class PPO(Algorithm):
                                             actions.float().contiguous(), old_logp, adv, old_values, returns, v32,
                                             moments=moments)
                 grads, roots = [res.grads[0].to(out.pi.dtype), res.grads[1]], [out.pi, out.log_std]
-            self.launches_last_epoch += 2
             roots.append(values)
             grads.append(res.dvalues.reshape(values.shape).to(values.dtype))
             torch.autograd.backward(roots, grads)
@@ -269,7 +268,6 @@ class PPO(Algorithm):
         res = ops.ppo_scalar_loss(h, logp_a.detach().float().contiguous(), entropy.detach().float().contiguous(),
                                   old_logp, adv, old_values, returns, new_values.detach().float().contiguous(),
                                   moments=moments, kl_cutoff=self.kl_cutoff, pi_coef_state=pi_coef_state)
-        self.launches_last_epoch += 2 + (2 if self.kl_cutoff is not None else 0)
         torch.autograd.backward(
             [logp_a, entropy, new_values],
             [res.grads[0].to(logp_a.dtype).reshape(logp_a.shape), res.grads[1].to(entropy.dtype).reshape(entropy.shape),
@@ -279,7 +277,7 @@ class PPO(Algorithm):
     def learn_epoch(self, timesteps_elapsed: int, total_timesteps: int, rollout_generator,
                     callbacks: Optional[List] = None) -> Tuple[int, bool]:
         start_time = perf_counter()
-        self.launches_last_epoch = 0
+        launches0 = ops.LAUNCHES
         update_learning_rate(self.optimizer, self.learning_rate)
         if self.switch_range is not None:
             assert hasattr(rollout_generator, "switch_range")
@@ -291,7 +289,6 @@ class PPO(Algorithm):
             self._log_chart_scalars(timesteps_elapsed)
 
         r = rollout_generator.rollout(gamma=self.gamma, gae_lambda=self.gae_lambda)
-        self.launches_last_epoch += 1 + getattr(rollout_generator, "n_steps", 0)  # GAE scan + one sample launch per step
         timesteps_elapsed += r.total_steps
 
         V = int(np.prod(r.values.shape[2:])) if hasattr(r, "values") else 1
@@ -308,7 +305,6 @@ class PPO(Algorithm):
             step_stats.clear()  # only the last epoch's stats are reported (ppo.py:287-289)
             grad_norms.clear()
             for mb in r.minibatches(self.batch_size, shuffle=not self.gradient_accumulation):
-                self.launches_last_epoch += 2  # K3 gather: wide + narrow launch
                 self.policy.reset_noise(self.batch_size)
                 stats, _ = self._minibatch(mb, h, pi_coef_state)
                 step_stats.append(stats)
@@ -325,6 +321,8 @@ class PPO(Algorithm):
         norms = torch.stack(grad_norms).double().reshape(-1)
         tail = torch.cat([norms, ev.reshape(1).double()]) if ev is not None else norms
         host = torch.cat([packed.reshape(-1), tail]).cpu().numpy()
+        self.d2h_bytes_last_epoch = host.nbytes
+        self.launches_last_epoch = ops.LAUNCHES - launches0
         S = packed.shape[1]
         rows = host[: packed.numel()].reshape(-1, S)
         gn = host[packed.numel(): packed.numel() + norms.numel()]

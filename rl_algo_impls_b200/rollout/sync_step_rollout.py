@@ -33,6 +33,7 @@ class _Uploader:
         self.device = device
         self._pinned: Dict[str, torch.Tensor] = {}
         self._done: Dict[str, torch.cuda.Event] = {}
+        self.bytes = 0  # host -> device bytes moved so far
 
     def __call__(self, name: str, src, dst: torch.Tensor) -> None:
         if isinstance(src, torch.Tensor):
@@ -46,6 +47,7 @@ class _Uploader:
             self._done[name] = torch.cuda.Event()
         else:
             self._done[name].synchronize()  # the previous upload out of this staging buffer has landed
+        self.bytes += stage.numel() * stage.element_size()
         stage.copy_(torch.from_numpy(a))  # host-side convert (e.g. float64 obs -> float32) + copy
         dst.copy_(stage, non_blocking=True)
         self._done[name].record()
@@ -95,6 +97,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         if self.device.type != "cuda":
             raise RuntimeError("SyncStepRolloutGenerator keeps the rollout in HBM: the policy must be on a CUDA device")
         self._upload = _Uploader(self.device)
+        self.d2h_bytes = 0  # device -> host bytes (sampled actions handed to a host env)
         self.get_action_mask = getattr(vec_env, "get_action_mask", None)
 
         T = self.n_steps
@@ -150,7 +153,9 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         from ..policy.actor_critic import clamp_actions
 
         if isinstance(a, dict):
+            self.d2h_bytes += sum(t.numel() * t.element_size() for t in a.values())
             return {k: t.cpu().numpy().astype(np.int64) for k, t in a.items()}
+        self.d2h_bytes += a.numel() * a.element_size()
         a_np = a.cpu().numpy()
         if a_np.dtype == np.uint8:
             a_np = a_np.astype(np.int64)

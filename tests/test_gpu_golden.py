@@ -1,0 +1,158 @@
+"""The CUDA path against the golden fixtures generated from the live reference
+(tests/golden/*.npz): GAE bit-exact; GridNet / categorical / Gaussian log-prob, entropy and
+gradients within 1e-5; and a whole PPO.learn_epoch (same initial weights, same rollout arrays,
+same randperm seed) landing on the reference's final parameters and TrainStats."""
+import numpy as np
+import pytest
+import torch
+
+from tests.parity import close
+from tests.test_oracle_golden import cases, gates_of, learner_setup, load, rollout_from
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", cases(load("gae")))
+def test_gae_vs_reference_fixture(cuda, name):
+    from rl_algo_impls_b200 import ops
+
+    z = load("gae")
+    g = lambda k: z[f"{name}.{k}"]
+    t = lambda k: torch.from_numpy(g(k)).to(cuda)
+    scalar = bool(g("gamma_is_scalar"))
+    gamma = float(g("gamma")) if scalar else g("gamma")
+    lam = float(g("gae_lambda")) if scalar else g("gae_lambda")
+    adv, ret = ops.gae_scan(t("rewards"), t("values"), t("episode_starts"), t("next_episode_starts"), t("next_values"),
+                            gamma, lam)
+    np.testing.assert_array_equal(adv.cpu().numpy(), g("advantages"))
+    np.testing.assert_array_equal(ret.cpu().numpy(), g("returns"))
+
+
+@pytest.mark.parametrize("name", cases(load("gridnet")))
+def test_gridnet_vs_reference_fixture(cuda, name):
+    from rl_algo_impls_b200 import ops
+
+    z = load("gridnet")
+    g = lambda k: z.get(f"{name}.{k}")
+    t = lambda k: None if g(k) is None else torch.from_numpy(g(k)).to(cuda)
+    gates = {}
+    for h, (r, v) in gates_of(g("gates")).items():
+        gates.setdefault(r, {})[h] = v
+    n_pick = 0 if g("pick_mask") is None else g("pick_mask").shape[1]
+    spec = ops.GridnetSpec.from_subaction_mask(g("nvec").tolist(), gates, n_pick)
+    logits = t("logits").requires_grad_(True)
+    logp, ent = ops.gridnet_logp_entropy(spec, logits, t("mask"), t("pick_mask"), t("actions"), t("pick_actions"))
+    (logp * t("dlogp") + ent * t("dentropy")).sum().backward()
+    atol = 4e-7 * float(np.abs(g("logits")).max())
+    close(logp, g("logp"), atol=atol, what="logp")
+    close(ent, g("entropy"), atol=atol, what="entropy")
+    close(logits.grad, g("dlogits"), atol=atol * 0.1, what="dlogits")
+    S = int(g("nvec").sum())
+    assert (logits.grad.cpu().numpy()[..., :S][~g("mask")] == 0).all()
+
+
+@pytest.mark.parametrize("name", ["cartpole", "atari", "masked"])
+def test_categorical_vs_reference_fixture(cuda, name):
+    from rl_algo_impls_b200 import ops
+
+    z = load("heads")
+    g = lambda k: z.get(f"{name}.{k}")
+    t = lambda k: None if g(k) is None else torch.from_numpy(g(k)).to(cuda)
+    logits = t("logits").requires_grad_(True)
+    logp, ent = ops.categorical_logp_entropy(logits, t("mask"), t("actions"))
+    (logp * t("dlogp") + ent * t("dentropy")).sum().backward()
+    close(logp, g("logp"), atol=1e-6, what="logp")
+    close(ent, g("entropy"), atol=1e-6, what="entropy")
+    close(logits.grad, g("dlogits"), atol=1e-6, what="dlogits")
+
+
+def test_gaussian_vs_reference_fixture(cuda):
+    from rl_algo_impls_b200 import ops
+
+    z = load("heads")
+    t = lambda k: torch.from_numpy(z[f"gaussian.{k}"]).to(cuda)
+    logp, ent = ops.gaussian_logp_entropy(t("mu"), t("log_std"), t("actions"))
+    close(logp, z["gaussian.logp"], what="logp")
+    close(ent, z["gaussian.entropy"], what="entropy")
+
+
+def _device_policy(case, net, cuda):
+    """An ActorCritic over the stub trunk, on the GPU."""
+    from rl_algo_impls_b200 import spaces
+    from rl_algo_impls_b200.policy import ActorCritic
+
+    class Env:
+        num_envs = case["N"]
+        single_observation_space = spaces.Box(-np.inf, np.inf, case["obs_shape"], np.float32)
+
+    env = Env()
+    if case["kind"] == "categorical":
+        env.single_action_space = spaces.Discrete(case["nvec"][0])
+    elif case["kind"] == "gaussian":
+        env.single_action_space = spaces.Box(-1, 1, (case["nvec"][0],), np.float32)
+    else:
+        hw = case["side"] ** 2
+        env.action_plane_space = spaces.MultiDiscrete(case["nvec"])
+        per_pos = spaces.MultiDiscrete(np.tile(np.asarray(case["nvec"]), hw))
+        env.single_action_space = per_pos if not case.get("n_pick") else spaces.Dict(
+            {"per_position": per_pos, "pick_position": spaces.MultiDiscrete([hw] * case["n_pick"])})
+    net.n_values = case["V"]
+    return ActorCritic(env, network=net, subaction_mask=case.get("gates")).to(cuda)
+
+
+@pytest.mark.parametrize("name", ["cartpole", "gaussian", "microrts", "lux"])
+def test_learn_epoch_vs_reference_fixture(cuda, name):
+    from rl_algo_impls_b200.ppo import PPO
+    from rl_algo_impls_b200.rollout import VecRollout
+
+    case, z, net = learner_setup(name)
+    hp = case["hp"]
+    torch.backends.cudnn.allow_tf32 = False  # the trunk is PyTorch's; keep its convs in fp32 like the CPU reference
+    torch.backends.cuda.matmul.allow_tf32 = False
+    policy = _device_policy(case, net, cuda)
+    ro = rollout_from(z)
+
+    class Gen:
+        n_steps = case["T"]
+
+        def rollout(self, gamma, gae_lambda):
+            return VecRollout(cuda, ro["next_episode_starts"], ro["next_values"], ro["obs"], ro["actions"], ro["rewards"],
+                              ro["episode_starts"], ro["values"], ro["logprobs"], ro["masks"], gamma, gae_lambda,
+                              subaction_mask=case.get("gates"))
+
+    kw = {k: getattr(hp, k) for k in ("batch_size", "n_epochs", "gamma", "gae_lambda", "clip_range", "clip_range_vf",
+                                      "normalize_advantage", "standardize_advantage", "ent_coef", "vf_coef",
+                                      "ppo2_vf_coef_halving", "max_grad_norm", "multi_reward_weights",
+                                      "gradient_accumulation", "kl_cutoff", "normalize_advantages_after_scaling",
+                                      "learning_rate")}
+    algo = PPO(policy, cuda, None, **kw)
+    box = {}
+
+    class CB:
+        def on_step(self, timesteps_elapsed, train_stats):
+            box["s"] = train_stats
+            return True
+
+    torch.manual_seed(int(z["seed"]) + 100)  # same randperm stream as the reference run
+    steps, cont = algo.learn_epoch(0, case["T"] * case["N"], Gen(), [CB()])
+    assert steps == case["T"] * case["N"] and cont
+    s = box["s"]
+    # parameters after n_epochs x minibatches of Adam steps: each step is lr * a unit-scale update, so
+    # compare against the parameter *change* (final - init), not the parameter magnitude
+    # Adam divides by sqrt(v): an element whose gradient is ~0 takes a +-lr step on rounding noise
+    # alone, so the bound is two-sided -- RMS error small against the RMS update, and no element
+    # further off than the steps Adam could have taken.
+    n_updates = hp.n_epochs * (1 if hp.gradient_accumulation else -(-case["T"] * case["N"] // hp.batch_size))
+    for k, v in policy.network.state_dict().items():
+        want, init = z[f"final.{k}"].astype(np.float64), z[f"init.{k}"].astype(np.float64)
+        got = v.cpu().numpy().astype(np.float64)
+        rms_update = np.sqrt(np.mean((want - init) ** 2))
+        rms_err = np.sqrt(np.mean((got - want) ** 2))
+        assert rms_err <= 5e-3 * rms_update + 1e-8, f"{name} param {k}: rms err {rms_err:.3e} vs rms update {rms_update:.3e}"
+        assert np.abs(got - want).max() <= 2 * hp.learning_rate * n_updates
+    for k, tol in (("loss", 1e-4), ("pi_loss", 2e-3), ("entropy_loss", 1e-5), ("approx_kl", 2e-3), ("grad_norm", 1e-3),
+                   ("explained_var", 1e-5)):
+        got, want = getattr(s, k), float(z[f"stats.{k}"])
+        assert abs(got - want) <= tol * max(abs(want), 1e-2), f"{name} {k}: {got} vs {want}"
+    np.testing.assert_allclose(np.asarray(s.v_loss, np.float64), z["stats.v_loss"], rtol=1e-4)
+    assert abs(s.clipped_frac - float(z["stats.clipped_frac"])) <= 2.0 / hp.batch_size
