@@ -32,20 +32,21 @@ def flush_l2():
     _flush.zero_()
 
 
-def time_kernel(fn, iters=20, warmup=3, flush=True):
+def time_kernel(fn, name, iters=20, warmup=3, flush=True):
+    """CUDA events recorded immediately around the C-ABI call `name` (ops.KernelTimer), so that the
+    Python-side argument marshalling of the wrapper is outside the bracket."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
-    times = []
+    timer = ops.KernelTimer([name])
+    ops.set_kernel_timer(timer)
     for _ in range(iters):
         if flush:
             flush_l2()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
         fn()
-        e.record()
-        torch.cuda.synchronize()
-        times.append(s.elapsed_time(e))
+    torch.cuda.synchronize()
+    ops.set_kernel_timer(None)
+    times = [s.elapsed_time(e) for s, e in timer.events[name]]
     return float(np.median(times)), float(np.min(times))
 
 
@@ -60,7 +61,7 @@ def bench_gae(T, N, V):
     gamma = 0.99 if V == 1 else np.full(V, 1.0)
     lam = 0.95 if V == 1 else np.full(V, 0.95)
     fn = lambda: ops.gae_scan(r, v, es, nes, nv, gamma, lam, adv, ret)
-    med, best = time_kernel(fn)
+    med, best = time_kernel(fn, 'b200rl_gae_scan_f32')
     nbytes = T * N * (16 * V + 1) + N * (4 * V + 1)
     return dict(kernel="gae_scan", T=T, N=N, V=V, ms_median=med, ms_best=best, bytes=nbytes,
                 gbs=nbytes / med / 1e6, frac=nbytes / med / 1e6 / peak_gbs())
@@ -94,10 +95,10 @@ def bench_loss(B, HW, nvec, gates, n_pick, V, unit_p, dtype=torch.float32):
     moments = ops.adv_moments(adv.view(B, V), None, ops.ADV_NORMALIZE, w)
     fn = lambda: ops.ppo_gridnet_loss(h, spec, logits, mask, pick_mask, actions, pick, old_logp, adv, ov, rt, nv,
                                       moments=moments)
-    med, best = time_kernel(fn)
+    med, best = time_kernel(fn, 'b200rl_ppo_gridnet_loss')
     S, A, es = sum(nvec), len(nvec), logits.element_size()
     nbytes = B * (2 * es * HW * (S + n_pick) + HW * S + n_pick * HW + HW * A + 2 * n_pick + 4 * (2 + 5 * V))
-    return dict(kernel="ppo_gridnet_loss", B=B, HW=HW, S=S + n_pick, V=V, dtype=str(dtype), ms_median=med,
+    return dict(kernel="ppo_gridnet_loss", B=B, HW=HW, S=S + n_pick, V=V, unit_p=unit_p, dtype=str(dtype), ms_median=med,
                 ms_best=best, bytes=nbytes, gbs=nbytes / med / 1e6, frac=nbytes / med / 1e6 / peak_gbs())
 
 
@@ -108,7 +109,7 @@ def bench_gather(M, B, row_shapes):
         s.view(torch.uint8).random_(0, 255) if s.dtype != torch.bool else None
     idx = torch.randperm(M, device=dev)[:B]
     fn = lambda: ops.gather_rows(srcs, idx)
-    med, best = time_kernel(fn)
+    med, best = time_kernel(fn, 'b200rl_gather_rows')
     nbytes = 2 * B * sum(int(np.prod(s.shape[1:])) * s.element_size() for s in srcs)
     return dict(kernel="gather_rows", M=M, B=B, ms_median=med, ms_best=best, bytes=nbytes, gbs=nbytes / med / 1e6,
                 frac=nbytes / med / 1e6 / peak_gbs())
@@ -133,6 +134,22 @@ def main():
             rows.append(bench_loss(B, 4096, LUX_NVEC, LUX_GATES, 1, 13, 0.02))
             print(json.dumps(rows[-1]), flush=True)
         rows.append(bench_loss(3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 0.06, torch.bfloat16))
+        print(json.dumps(rows[-1]), flush=True)
+    if a.what in ("loss", "all"):  # dense masks: every cell has a unit (worst case for the mask-driven kernel)
+        rows.append(bench_loss(3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 1.0))
+        print(json.dumps(rows[-1]), flush=True)
+        rows.append(bench_loss(512, 4096, LUX_NVEC, LUX_GATES, 1, 13, 1.0))
+        print(json.dumps(rows[-1]), flush=True)
+    if a.what == "loss_c4":  # one shape, few launches: the ncu target
+        rows.append(bench_loss(3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 0.06))
+        print(json.dumps(rows[-1]), flush=True)
+    if a.what == "loss_c5":
+        rows.append(bench_loss(512, 4096, LUX_NVEC, LUX_GATES, 1, 13, 0.02))
+        print(json.dumps(rows[-1]), flush=True)
+    if a.what == "gae_big":
+        rows.append(bench_gae(128, 1 << 20, 1))
+        print(json.dumps(rows[-1]), flush=True)
+        rows.append(bench_gae(32, 131072, 13))
         print(json.dumps(rows[-1]), flush=True)
     if a.what in ("gather", "all"):
         rows.append(bench_gather(12288, 3072, [((74, 16, 16), torch.float32), ((256, 78), torch.uint8),

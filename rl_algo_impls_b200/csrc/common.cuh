@@ -110,6 +110,8 @@ __device__ __forceinline__ void stg_stream_u4(uint4* p, const uint4& v) {
                : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // ---- mbarrier + 1-D bulk async copies (TMA engine, no tensor map) ----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -5,25 +5,32 @@
 // fused mode, ppo/ppo.py:326-361 with the autograd backward of the whole chain: ~60-80
 // eager launches forward and twice that backward in the reference.
 //
-// Shape of the kernel (memory-bound; 8*HW*S' + HW*S + ... bytes per sample):
-//   * one thread-block cluster per sample; each CTA of the cluster owns HW / cluster cells
-//     and stages its [cells, S'] logits tile and [cells, S] mask tile in shared memory with
-//     1-D bulk async copies (TMA engine, completion on an mbarrier) -- logits are read from
-//     HBM exactly once;
-//   * one thread per cell walks the heads of its cell: masked max, one exp per valid entry
-//     (sum e and sum e*(x-max) give logsumexp and entropy together), the chosen action's
-//     log-prob with the value-dependent gate; (lse, entropy) per head stay in registers;
-//   * per-sample sums go through warp shuffles, shared memory and, when the sample spans
-//     several CTAs, distributed shared memory across the cluster; the pick_position
-//     categorical over all cells of the sample uses the same path for its max / partition sum;
-//   * thread 0 turns the sample's log-prob into ratio / clipped surrogate / KL terms
-//     (ppo_terms.cuh); one warp handles the value heads;
-//   * the backward overwrites the logits tile in place with d loss / d logits and one bulk
-//     async copy writes the tile back -- dlogits are written exactly once.
+// The kernel is driven by the action MASK.  A cell whose S mask bytes are all zero (no unit
+// on it: ~94-98 % of the cells of a MicroRTS / Lux map) contributes exactly 0 to the
+// log-prob, to the entropy and to the gradient (reference semantics: a fully masked row
+// normalises to uniform, log_prob 0, entropy -0, gradient blocked by torch.where), so its
+// logits are never read; its dlogits row is plain zero fill.
+//
+//   1. every thread zero-fills its share of the sample's dlogits (128-bit stores) and scans
+//      the mask bytes with 128-bit loads; a non-zero word flags its cell(s) in a shared bitmap;
+//   2. warp 0 compacts the bitmap into a list of "unit" cells;
+//   3. unit cells are processed by groups of G lanes (G = 8 or 16 for the reference's action
+//      planes): every lane owns one piece of <= PMAX adjacent logits of one head -- small
+//      heads are one lane, a wide head (MicroRTS' 49-way attack target) is spread over an
+//      aligned power-of-two block of lanes and reduced with xor shuffles.  Adjacent lanes read
+//      adjacent addresses, so a cell's row is one coalesced ~300-byte access;
+//   4. per-sample sums run in float64 through shuffles, shared memory and -- when a sample
+//      spans several CTAs -- distributed shared memory across the thread-block cluster; the
+//      pick_position categorical over all cells of the sample uses the same path;
+//   5. thread 0 turns the sample's log-prob into ratio / clipped surrogate / KL terms
+//      (ppo_terms.cuh), one warp handles the value heads;
+//   6. the same lanes revisit the unit cells (L1/L2 hits) and overwrite their zero-filled
+//      dlogits rows with d loss / d logits.
+//
+// HBM traffic per sample: dlogits written once, masks read once, logits / actions read only
+// for unit cells.  No shared-memory tile => ~20 KB of shared memory per CTA and full occupancy.
 #include <cooperative_groups.h>
 
-#include "categorical.cuh"
-#include "philox.cuh"
 #include "ppo_terms.cuh"
 
 namespace cg = cooperative_groups;
@@ -31,11 +38,20 @@ namespace cg = cooperative_groups;
 namespace b200rl {
 
 constexpr int kGridBlock = 256;
-constexpr int kRegHeads = 8;   // heads whose (lse, entropy) live in registers
 constexpr int kMaxPick = 4;
-constexpr int kMaxCpt = 4;     // cells per thread
+constexpr int kMaxCellsPerCta = 4096;
 
-enum GridMode { kFwd = 0, kBwd = 1, kPpo = 2, kSample = 3 };
+enum GridMode { kFwd = 0, kBwd = 1, kPpo = 2 };
+
+// One lane slot of a G-lane group: a piece of `len` adjacent logits of head `head`.
+struct LaneSlot {
+  uint16_t off;       // first logit of the piece within the cell's row
+  uint16_t head_off;  // first logit of the piece's head
+  uint8_t len;        // 0: idle lane
+  uint8_t head;
+  uint8_t width;  // lanes of this head's block (power of two, block is width-aligned)
+  uint8_t first;  // first lane of its block
+};
 
 struct GridDev {
   const void* logits;
@@ -47,89 +63,71 @@ struct GridDev {
   long long B, HW;
   int A, S, Sp, n_pick;
   int act_dtype, pick_dtype;
-  int nvec[B200RL_MAX_HEADS], off[B200RL_MAX_HEADS], gate_ref[B200RL_MAX_HEADS], gate_val[B200RL_MAX_HEADS];
+  int gate_ref[B200RL_MAX_HEADS], gate_val[B200RL_MAX_HEADS];
   float* logp;
   float* entropy;
   const float* dlogp_in;
   const float* dent_in;
   int cluster;        // CTAs per sample
   int cells_per_cta;  // HW / cluster
-  // sampling
-  uint64_t seed, offset;
-  void* actions_out;
-  void* pick_actions_out;
+  int G;              // lanes per cell group (power of two <= 32)
+  int max_width;      // widest head block
+  LaneSlot slot[32];
 };
 
 __device__ __forceinline__ int load_index(const void* base, int dtype, long long i) {
   switch (dtype) {
-    case B200RL_U8: return (int)static_cast<const uint8_t*>(base)[i];
-    case B200RL_I32: return (int)static_cast<const int32_t*>(base)[i];
-    default: return (int)static_cast<const long long*>(base)[i];
+    case B200RL_U8: return (int)__ldg(static_cast<const uint8_t*>(base) + i);
+    case B200RL_I32: return (int)__ldg(static_cast<const int32_t*>(base) + i);
+    default: return (int)__ldg(static_cast<const long long*>(base) + i);
   }
-}
-__device__ __forceinline__ void store_index(void* base, int dtype, long long i, int v) {
-  switch (dtype) {
-    case B200RL_U8: static_cast<uint8_t*>(base)[i] = (uint8_t)v; break;
-    case B200RL_I32: static_cast<int32_t*>(base)[i] = v; break;
-    default: static_cast<long long*>(base)[i] = v; break;
-  }
-}
-
-// ---- tile staging ----------------------------------------------------------------------------
-// Global bytes [src, src+bytes) land at smem_base + (src & 15) so that the 16-byte aligned
-// middle can go through one bulk async copy; the <16-byte head and tail are plain byte copies.
-struct TilePlan {
-  uint32_t lead;    // src & 15
-  uint32_t head;    // bytes before the aligned middle
-  uint32_t middle;  // multiple of 16
-  uint32_t tail;
-};
-__device__ __forceinline__ TilePlan plan_tile(const void* src, uint32_t bytes) {
-  TilePlan t;
-  t.lead = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
-  t.head = (16u - t.lead) & 15u;
-  if (t.head > bytes) t.head = bytes;
-  t.middle = (bytes - t.head) & ~15u;
-  t.tail = bytes - t.head - t.middle;
-  return t;
-}
-__device__ __forceinline__ void copy_edges_in(uint8_t* dst, const uint8_t* src, const TilePlan& t) {
-  const int tid = threadIdx.x;
-  if (tid < (int)t.head) dst[tid] = src[tid];
-  if (tid >= 32 && tid - 32 < (int)t.tail) dst[t.head + t.middle + tid - 32] = src[t.head + t.middle + tid - 32];
 }
 
 // ---- per-sample reductions over the CTA and the cluster --------------------------------------
+__device__ __forceinline__ double shfl_xor_f64(double v, int o) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(0xffffffffu, lo, o);
+  hi = __shfl_xor_sync(0xffffffffu, hi, o);
+  return __hiloint2double(hi, lo);
+}
+
 // v[0..K) summed (or maxed) over every thread of every CTA of the cluster; result in all threads.
-template <int K, bool IS_MAX>
-__device__ __forceinline__ void sample_reduce(float (&v)[K], float* s_warp /*[K*32]*/, float* s_cta /*[K]*/,
-                                              int cluster_size) {
+template <typename T, int K, bool IS_MAX>
+__device__ __forceinline__ void sample_reduce(T (&v)[K], T* s_warp /*[K*8]*/, T* s_cta /*[K]*/, int cluster_size) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int nwarps = kGridBlock / 32;
 #pragma unroll
-  for (int k = 0; k < K; ++k) v[k] = IS_MAX ? warp_max(v[k]) : warp_sum(v[k]);
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      T other;
+      if constexpr (sizeof(T) == 8) other = shfl_xor_f64(v[k], o);
+      else other = __shfl_xor_sync(0xffffffffu, v[k], o);
+      v[k] = IS_MAX ? (other > v[k] ? other : v[k]) : v[k] + other;
+    }
+  }
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) s_warp[k * 32 + warp] = v[k];
+    for (int k = 0; k < K; ++k) s_warp[k * nwarps + warp] = v[k];
   }
   __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      float x = lane < nwarps ? s_warp[k * 32 + lane] : (IS_MAX ? -INFINITY : 0.f);
-      x = IS_MAX ? warp_max(x) : warp_sum(x);
-      if (lane == 0) s_cta[k] = x;
+  if (threadIdx.x < K) {
+    T acc = s_warp[threadIdx.x * nwarps];
+    for (int w = 1; w < nwarps; ++w) {
+      const T x = s_warp[threadIdx.x * nwarps + w];
+      acc = IS_MAX ? (x > acc ? x : acc) : acc + x;
     }
+    s_cta[threadIdx.x] = acc;
   }
   if (cluster_size > 1) {
     cg::cluster_group cluster = cg::this_cluster();
     cluster.sync();  // every CTA's s_cta is written
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      float acc = IS_MAX ? -INFINITY : 0.f;
-      for (int r = 0; r < cluster_size; ++r) {
-        const float x = cluster.map_shared_rank(s_cta, r)[k];
-        acc = IS_MAX ? fmaxf(acc, x) : acc + x;
+      T acc = cluster.map_shared_rank(s_cta, 0)[k];
+      for (int r = 1; r < cluster_size; ++r) {
+        const T x = cluster.map_shared_rank(s_cta, r)[k];
+        acc = IS_MAX ? (x > acc ? x : acc) : acc + x;
       }
       v[k] = acc;
     }
@@ -142,15 +140,187 @@ __device__ __forceinline__ void sample_reduce(float (&v)[K], float* s_warp /*[K*
   }
 }
 
+// ---- zero fill / mask scan -----------------------------------------------------------------------
+__device__ __forceinline__ void zero_fill(uint8_t* dst, long long bytes) {
+  const int tid = threadIdx.x;
+  const long long head = min((long long)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u), bytes);
+  if (tid < head) dst[tid] = 0;
+  uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+  const long long n4 = (bytes - head) >> 4;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (long long i = tid; i < n4; i += kGridBlock) d4[i] = z;
+  const long long done = head + (n4 << 4);
+  if (tid < bytes - done) dst[done + tid] = 0;
+}
+
+__device__ __forceinline__ void flag_cell(uint32_t* bitmap, uint32_t cell) {
+  atomicOr(&bitmap[cell >> 5], 1u << (cell & 31));
+}
+
+// A 16-byte word of the mask chunk with at least one non-zero byte: flag the cell(s) it covers.
+// Rows are S bytes, so for S >= 16 a word touches at most two cells; two 32-bit divisions and a
+// byte-boundary split decide which.  (Chunk sizes are < 2^31 bytes: cells <= 4096, S <= 65535.)
+__device__ __forceinline__ void flag_word(uint32_t* bitmap, uint32_t base, const uint4& w, uint32_t S) {
+  const uint32_t c0 = base / S, c1 = (base + 15u) / S;
+  if (c0 == c1) {
+    flag_cell(bitmap, c0);
+    return;
+  }
+  if (S >= 16u) {
+    const uint32_t k = c1 * S - base;  // bytes [0, k) belong to c0, [k, 16) to c1; 1 <= k <= 15
+    const unsigned long long lo = (unsigned long long)w.x | ((unsigned long long)w.y << 32);
+    const unsigned long long hi = (unsigned long long)w.z | ((unsigned long long)w.w << 32);
+    unsigned long long first, second;
+    if (k < 8u) {
+      first = lo & ((1ull << (8u * k)) - 1ull);
+      second = (lo >> (8u * k)) | hi;
+    } else {
+      first = lo | (k == 8u ? 0ull : (hi & ((1ull << (8u * (k - 8u))) - 1ull)));
+      second = hi >> (8u * (k - 8u));
+    }
+    if (first) flag_cell(bitmap, c0);
+    if (second) flag_cell(bitmap, c1);
+    return;
+  }
+  const uint32_t word[4] = {w.x, w.y, w.z, w.w};  // narrow rows: several cells per word
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    for (int r = 0; r < 4; ++r)
+      if ((word[q] >> (8 * r)) & 0xffu) flag_cell(bitmap, (base + 4u * q + r) / S);
+}
+
+// flags every cell of [mask, mask + bytes) that has a non-zero byte
+__device__ __forceinline__ void scan_mask(const uint8_t* mask, uint32_t bytes, uint32_t S, uint32_t* bitmap) {
+  const uint32_t tid = threadIdx.x;
+  uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(mask) & 15u)) & 15u;
+  if (head > bytes) head = bytes;
+  if (tid < head && mask[tid]) flag_cell(bitmap, tid / S);
+  const uint4* m4 = reinterpret_cast<const uint4*>(mask + head);
+  const uint32_t n4 = (bytes - head) >> 4;
+  constexpr uint32_t kUnroll = 4;
+  for (uint32_t i0 = tid; i0 < n4; i0 += kGridBlock * kUnroll) {
+    uint4 w[kUnroll];
+#pragma unroll
+    for (uint32_t u = 0; u < kUnroll; ++u) {
+      const uint32_t i = i0 + u * kGridBlock;
+      // plain read-only loads (allocate in L1): the unit cells re-read their own mask bytes
+      w[u] = i < n4 ? __ldg(m4 + i) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (uint32_t u = 0; u < kUnroll; ++u)
+      if ((w[u].x | w[u].y | w[u].z | w[u].w) != 0u) flag_word(bitmap, head + ((i0 + u * kGridBlock) << 4), w[u], S);
+  }
+  const uint32_t done = head + (n4 << 4);
+  if (tid < bytes - done && mask[done + tid]) flag_cell(bitmap, (done + tid) / S);
+}
+
+// warp 0: bitmap -> ascending list of flagged cells; returns the count through *s_count
+__device__ __forceinline__ void compact_cells(const uint32_t* bitmap, int words, uint16_t* list, int* s_count) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  int base = 0;
+  for (int w0 = 0; w0 < words; w0 += 32) {
+    const int w = w0 + lane;
+    uint32_t bits = w < words ? bitmap[w] : 0u;
+    const int cnt = __popc(bits);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int pos = base + incl - cnt;
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      list[pos++] = (uint16_t)(w * 32 + b);
+    }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) *s_count = base;
+}
+
+// ---- one piece of one head ------------------------------------------------------------------------
+template <typename LT, int PMAX>
+struct Piece {
+  float x[PMAX];
+  uint32_t valid;  // bit j: entry j of the piece is unmasked
+};
+
+template <typename LT, int PMAX>
+__device__ __forceinline__ Piece<LT, PMAX> load_piece(const LT* row, const uint8_t* mrow, const LaneSlot& s) {
+  Piece<LT, PMAX> p;
+  p.valid = 0u;
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j) {
+    p.x[j] = 0.f;
+    if (j < s.len) {
+      p.x[j] = to_f32(row[s.off + j]);
+      if (mrow[s.off + j]) p.valid |= 1u << j;
+    }
+  }
+  return p;
+}
+
+// xor-butterfly over the lanes of this head's block; lanes outside the block never mix in
+// because blocks are width-aligned.  `steps` = log2(widest block in the plan), warp-uniform.
+template <bool IS_MAX>
+__device__ __forceinline__ float block_reduce(float v, int width, int max_width) {
+  for (int o = 1; o < max_width; o <<= 1) {
+    const float other = __shfl_xor_sync(0xffffffffu, v, o);
+    if (o < width) v = IS_MAX ? fmaxf(v, other) : v + other;
+  }
+  return v;
+}
+
+struct HeadStat {
+  float lse, ent;
+  bool any;
+};
+
+template <typename LT, int PMAX>
+__device__ __forceinline__ HeadStat head_forward(const Piece<LT, PMAX>& p, const LaneSlot& s, int max_width) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j)
+    if ((p.valid >> j) & 1u) mx = fmaxf(mx, p.x[j]);
+  mx = block_reduce<true>(mx, s.width, max_width);
+  HeadStat h;
+  h.any = mx > -INFINITY;
+  float sum = 0.f, q = 0.f;
+  if (h.any) {
+#pragma unroll
+    for (int j = 0; j < PMAX; ++j)
+      if ((p.valid >> j) & 1u) {
+        const float d = p.x[j] - mx;
+        const float e = expf(d);
+        sum += e;
+        q = fmaf(e, d, q);
+      }
+  }
+  sum = block_reduce<false>(sum, s.width, max_width);
+  q = block_reduce<false>(q, s.width, max_width);
+  h.lse = 0.f, h.ent = 0.f;
+  if (h.any) {
+    const float ls = logf(sum);
+    h.lse = mx + ls;
+    h.ent = ls - q / sum;  // -sum p * logp over the valid entries
+  }
+  return h;
+}
+
 // ---- the kernel --------------------------------------------------------------------------------
-template <int MODE, typename LT, int CPT>
-__global__ void __launch_bounds__(kGridBlock) gridnet_kernel(const GridDev G, const PpoDev P) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t s_bar;
-  __shared__ float s_warp[8 * 32];
-  __shared__ float s_cta[8];
-  __shared__ float s_bcast[4];
+template <int MODE, typename LT, int PMAX>
+__global__ void __launch_bounds__(kGridBlock, PMAX <= 8 ? 4 : 2) gridnet_kernel(const __grid_constant__ GridDev G,
+                                                             const __grid_constant__ PpoDev P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ double s_warp64[2 * 8];
+  __shared__ double s_cta64[2];
+  __shared__ float s_warp32[2 * 8];
+  __shared__ float s_cta32[2];
+  __shared__ float s_bcast[2];
   __shared__ float s_pick[kMaxPick * 3];  // lse, entropy, any per pick head
+  __shared__ int s_count;
 
   const int tid = threadIdx.x;
   const int cluster_size = G.cluster;
@@ -158,131 +328,96 @@ __global__ void __launch_bounds__(kGridBlock) gridnet_kernel(const GridDev G, co
   const long long b = blockIdx.x / cluster_size;
   const int cells = G.cells_per_cta;
   const long long cell0 = (long long)rank * cells;  // first cell of this CTA within the sample
+  const long long row0 = b * G.HW + cell0;          // global index of that cell
 
-  const uint32_t tile_bytes = (uint32_t)cells * G.Sp * sizeof(LT);
-  const uint32_t mask_bytes = (uint32_t)cells * G.S;
-  const uint8_t* g_tile = static_cast<const uint8_t*>(G.logits) + ((b * G.HW + cell0) * G.Sp) * sizeof(LT);
-  const uint8_t* g_mask = G.mask + (b * G.HW + cell0) * G.S;
-  const TilePlan tp = plan_tile(g_tile, tile_bytes);
-  const TilePlan mp = plan_tile(g_mask, mask_bytes);
-  uint8_t* s_tile_base = smem;  // capacity tile_bytes + 16, 16-byte aligned
-  uint8_t* s_mask_base = smem + ((tile_bytes + 16 + 15) & ~15u);
-  LT* tile = reinterpret_cast<LT*>(s_tile_base + tp.lead);
-  const uint8_t* mtile = s_mask_base + mp.lead;
+  // dynamic shared memory: bitmap | unit-cell list | per (unit cell, head) lse and entropy
+  const int words = (cells + 31) >> 5;
+  uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem);
+  uint16_t* list = reinterpret_cast<uint16_t*>(bitmap + words);
+  float* s_lse = reinterpret_cast<float*>(smem + (((size_t)words * 4 + (size_t)cells * 2 + 15) & ~(size_t)15));
+  float* s_ent = s_lse + (size_t)cells * G.A;
 
-  // ---- 1. stage logits + masks -------------------------------------------------------------
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    mbar_fence_init();
+  const LT* g_logits = static_cast<const LT*>(G.logits) + row0 * G.Sp;
+  LT* g_out = static_cast<LT*>(G.dlogits) + row0 * G.Sp;
+  const uint8_t* g_mask = G.mask + row0 * G.S;
+
+  // the per-sample PPO scalars are consumed by one thread after the reductions: start pulling them now
+  if (MODE == kPpo && rank == 0) {
+    if (tid == 0) {
+      prefetch_l1(P.old_logp + b);
+      prefetch_l1(P.adv + b * P.adv_v);
+      if (P.moments) prefetch_l1(P.moments);
+    } else if (tid >= 32 && tid < 32 + P.V) {
+      const long long o = b * P.V + (tid - 32);
+      prefetch_l1(P.new_values + o), prefetch_l1(P.old_values + o), prefetch_l1(P.returns + o);
+    }
   }
+
+  // ---- 1. zero fill + mask scan ------------------------------------------------------------------
+  for (int w = tid; w < words; w += kGridBlock) bitmap[w] = 0u;
+  if (MODE != kFwd) zero_fill(reinterpret_cast<uint8_t*>(g_out), (long long)cells * G.Sp * (long long)sizeof(LT));
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&s_bar, tp.middle + mp.middle);
-    if (tp.middle) bulk_g2s(s_tile_base + tp.lead + tp.head, g_tile + tp.head, tp.middle, &s_bar);
-    if (mp.middle) bulk_g2s(s_mask_base + mp.lead + mp.head, g_mask + mp.head, mp.middle, &s_bar);
-  }
-  copy_edges_in(s_tile_base + tp.lead, g_tile, tp);
-  copy_edges_in(s_mask_base + mp.lead, g_mask, mp);
+  scan_mask(g_mask, (uint32_t)cells * (uint32_t)G.S, (uint32_t)G.S, bitmap);
+  __syncthreads();
 
-  // per-cell actions (registers) while the copies fly
-  uint32_t act_lo[CPT], act_hi[CPT];  // 8 packed bytes per cell
-  if (MODE != kSample) {
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const int c = tid + j * kGridBlock;
-      uint32_t lo = 0, hi = 0;
-      if (c < cells) {
-        const long long base = (b * G.HW + cell0 + c) * G.A;
-        for (int h = 0; h < G.A; ++h) {
-          const uint32_t a = (uint32_t)load_index(G.actions, G.act_dtype, base + h) & 0xffu;
-          if (h < 4) lo |= a << (8 * h); else hi |= a << (8 * (h - 4));
-        }
-      }
-      act_lo[j] = lo, act_hi[j] = hi;
+  // ---- 2. compaction -------------------------------------------------------------------------------
+  compact_cells(bitmap, words, list, &s_count);
+  __syncthreads();
+  const int n_unit = s_count;
+
+  // ---- 3. forward over the unit cells -----------------------------------------------------------------
+  const int group = tid / G.G, n_groups = kGridBlock / G.G;
+  const LaneSlot slot = G.slot[tid & (G.G - 1)];
+  const int gate_ref = slot.len ? G.gate_ref[slot.head] : -1;
+  const int gate_val = slot.len ? G.gate_val[slot.head] : 0;
+  double logp_acc = 0.0, ent_acc = 0.0;
+  for (int i0 = 0; i0 < n_unit; i0 += n_groups) {  // uniform trip count: shuffles stay converged
+    const int i = i0 + group;
+    const bool live = i < n_unit && slot.len > 0;
+    const int cell = live ? (int)list[i] : 0;
+    Piece<LT, PMAX> p;
+    p.valid = 0u;
+    if (live) p = load_piece<LT, PMAX>(g_logits + (long long)cell * G.Sp, g_mask + (long long)cell * G.S, slot);
+    const HeadStat h = head_forward<LT, PMAX>(p, slot, G.max_width);
+    if (!live) continue;
+    if (slot.first) {
+      s_lse[i * G.A + slot.head] = h.any ? h.lse : INFINITY;  // +inf marks a head with no valid entry
+      s_ent[i * G.A + slot.head] = h.ent;
+      if (h.any) ent_acc += (double)h.ent;
     }
-  }
-  auto action_of = [&](int j, int h) -> int {
-    return (int)(((h < 4 ? act_lo[j] >> (8 * h) : act_hi[j] >> (8 * (h - 4)))) & 0xffu);
-  };
-
-  __syncthreads();        // edge bytes written by other threads
-  mbar_wait(&s_bar, 0);   // bulk bytes landed
-
-  // ---- 2. forward over this thread's cells ---------------------------------------------------
-  float lse[CPT][kRegHeads], ent[CPT][kRegHeads];
-  uint32_t any_bits[CPT], gate_bits[CPT];
-  float logp_acc = 0.f, ent_acc = 0.f;
+    if (h.any) {
+      const long long abase = (row0 + cell) * G.A;
+      const bool gated_in = gate_ref < 0 || load_index(G.actions, G.act_dtype, abase + gate_ref) == gate_val;
+      const int local = load_index(G.actions, G.act_dtype, abase + slot.head) - (int)(slot.off - slot.head_off);
+      if (gated_in && local >= 0 && local < slot.len) {
+        float xa = kF32Lowest;
 #pragma unroll
-  for (int j = 0; j < CPT; ++j) {
-    const int c = tid + j * kGridBlock;
-    any_bits[j] = 0, gate_bits[j] = 0;
-    if (c >= cells) continue;
-    const LT* x = tile + (long long)c * G.Sp;
-    const uint8_t* m = mtile + (long long)c * G.S;
-#pragma unroll
-    for (int h = 0; h < kRegHeads; ++h) {
-      lse[j][h] = 0.f, ent[j][h] = 0.f;
-      if (h >= G.A) continue;
-      const int off = G.off[h], n = G.nvec[h];
-      float mx = -INFINITY;
-      bool any = false;
-      for (int k = 0; k < n; ++k)
-        if (m[off + k]) {
-          any = true;
-          mx = fmaxf(mx, to_f32(x[off + k]));
-        }
-      if (!any) continue;
-      float s = 0.f, q = 0.f;
-      for (int k = 0; k < n; ++k)
-        if (m[off + k]) {
-          const float d = to_f32(x[off + k]) - mx;
-          const float e = expf(d);
-          s += e;
-          q = fmaf(e, d, q);
-        }
-      const float ls = logf(s);
-      lse[j][h] = mx + ls;
-      ent[j][h] = ls - q / s;  // -sum p * logp
-      any_bits[j] |= 1u << h;
-      ent_acc += ent[j][h];
-      if (MODE != kSample) {
-        const int gr = G.gate_ref[h];
-        const bool gated_in = gr < 0 || action_of(j, gr) == G.gate_val[h];
-        if (gated_in) {
-          gate_bits[j] |= 1u << h;
-          const int a = action_of(j, h);
-          const float xa = (a < n && m[off + a]) ? to_f32(x[off + a]) : kF32Lowest;
-          logp_acc += xa - lse[j][h];
-        }
+        for (int j = 0; j < PMAX; ++j)
+          if (j == local && ((p.valid >> j) & 1u)) xa = p.x[j];
+        logp_acc += (double)(xa - h.lse);
       }
     }
   }
 
-  // ---- 3. pick_position categoricals over all cells of the sample ------------------------------
+  // ---- 4. pick_position categoricals over all cells of the sample --------------------------------------
   for (int kp = 0; kp < G.n_pick; ++kp) {
     const uint8_t* pm = G.pick_mask + (b * G.n_pick + kp) * G.HW + cell0;
     float mx[1] = {-INFINITY};
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const int c = tid + j * kGridBlock;
-      if (c < cells && pm[c]) mx[0] = fmaxf(mx[0], to_f32(tile[(long long)c * G.Sp + G.S + kp]));
-    }
-    sample_reduce<1, true>(mx, s_warp, s_cta, cluster_size);
+    for (int c = tid; c < cells; c += kGridBlock)
+      if (pm[c]) mx[0] = fmaxf(mx[0], to_f32(g_logits[(long long)c * G.Sp + G.S + kp]));
+    sample_reduce<float, 1, true>(mx, s_warp32, s_cta32, cluster_size);
     const bool any = mx[0] > -INFINITY;
     float sq[2] = {0.f, 0.f};
     if (any) {
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const int c = tid + j * kGridBlock;
-        if (c < cells && pm[c]) {
-          const float d = to_f32(tile[(long long)c * G.Sp + G.S + kp]) - mx[0];
+      for (int c = tid; c < cells; c += kGridBlock)
+        if (pm[c]) {
+          const float d = to_f32(g_logits[(long long)c * G.Sp + G.S + kp]) - mx[0];
           const float e = expf(d);
           sq[0] += e;
           sq[1] = fmaf(e, d, sq[1]);
         }
-      }
     }
-    sample_reduce<2, false>(sq, s_warp, s_cta, cluster_size);
+    sample_reduce<float, 2, false>(sq, s_warp32, s_cta32, cluster_size);
     float p_lse = 0.f, p_ent = 0.f;
     if (any) {
       const float ls = logf(sq[0]);
@@ -290,25 +425,23 @@ __global__ void __launch_bounds__(kGridBlock) gridnet_kernel(const GridDev G, co
       p_ent = ls - sq[1] / sq[0];
     }
     if (tid == 0) s_pick[kp * 3] = p_lse, s_pick[kp * 3 + 1] = p_ent, s_pick[kp * 3 + 2] = any ? 1.f : 0.f;
-    if (MODE != kSample && any) {
-      const long long a = load_index(G.pick_actions, G.pick_dtype, b * G.n_pick + kp);
-      const long long local = a - cell0;
-      if (local >= 0 && local < cells && (int)(local % kGridBlock) == tid) {
-        const float xa = pm[local] ? to_f32(tile[local * G.Sp + G.S + kp]) : kF32Lowest;
-        logp_acc += xa - p_lse;
+    if (any && tid == 0) {
+      const long long local = (long long)load_index(G.pick_actions, G.pick_dtype, b * G.n_pick + kp) - cell0;
+      if (local >= 0 && local < cells) {
+        const float xa = pm[local] ? to_f32(g_logits[local * G.Sp + G.S + kp]) : kF32Lowest;
+        logp_acc += (double)(xa - p_lse);
       }
+      if (rank == 0) ent_acc += (double)p_ent;
     }
-    if (rank == 0 && tid == 0) ent_acc += p_ent;
   }
 
-  // ---- 4. per-sample totals -----------------------------------------------------------------
-  float tot[2] = {logp_acc, ent_acc};
+  // ---- 5. per-sample totals (float64) --------------------------------------------------------------------
+  double tot[2] = {logp_acc, ent_acc};
   float dlogp = 0.f, dent = 0.f;
-  if (MODE == kFwd || MODE == kPpo) sample_reduce<2, false>(tot, s_warp, s_cta, cluster_size);
+  if (MODE == kFwd || MODE == kPpo) sample_reduce<double, 2, false>(tot, s_warp64, s_cta64, cluster_size);
 
   if (MODE == kFwd) {
-    if (rank == 0 && tid == 0) G.logp[b] = tot[0], G.entropy[b] = tot[1];
-    if (cluster_size > 1) cg::this_cluster().sync();
+    if (rank == 0 && tid == 0) G.logp[b] = (float)tot[0], G.entropy[b] = (float)tot[1];
     return;
   }
   if (MODE == kBwd) {
@@ -316,15 +449,15 @@ __global__ void __launch_bounds__(kGridBlock) gridnet_kernel(const GridDev G, co
     __syncthreads();  // s_pick visible
   }
   if (MODE == kPpo) {
-    // ---- 5. PPO scalar stage ----------------------------------------------------------------
+    // ---- 6. PPO scalar stage ----------------------------------------------------------------------------
     if (tid == 0) {
       PolicyTerms t = ppo_policy_terms(P, b, tot[0]);
       s_bcast[0] = t.dlogp;
       if (rank == 0) {
         double* row = P.partials + b * ppo_nstat(P.V);
         row[0] = t.surrogate, row[1] = tot[1], row[2] = t.kl, row[3] = t.clipped;
-        if (G.logp) G.logp[b] = tot[0];
-        if (G.entropy) G.entropy[b] = tot[1];
+        if (G.logp) G.logp[b] = (float)tot[0];
+        if (G.entropy) G.entropy[b] = (float)tot[1];
       }
     }
     if (rank == 0 && tid >= 32 && tid < 32 + P.V) {
@@ -338,110 +471,115 @@ __global__ void __launch_bounds__(kGridBlock) gridnet_kernel(const GridDev G, co
     dent = ppo_dentropy(P, 1);
   }
 
-  // ---- 6. backward in place -------------------------------------------------------------------
+  // ---- 7. backward over the unit cells: overwrite their zero-filled rows ------------------------------------
+  for (int i = group; i < n_unit; i += n_groups) {
+    if (slot.len == 0) continue;
+    const float lse = s_lse[i * G.A + slot.head];
+    if (lse == INFINITY) continue;  // no valid entry in this head: gradient stays zero
+    const float ent = s_ent[i * G.A + slot.head];
+    const int cell = (int)list[i];
+    const Piece<LT, PMAX> p = load_piece<LT, PMAX>(g_logits + (long long)cell * G.Sp, g_mask + (long long)cell * G.S, slot);
+    const long long abase = (row0 + cell) * G.A;
+    const bool gated_in = gate_ref < 0 || load_index(G.actions, G.act_dtype, abase + gate_ref) == gate_val;
+    const int local = load_index(G.actions, G.act_dtype, abase + slot.head) - (int)(slot.off - slot.head_off);
+    const float dl = gated_in ? dlogp : 0.f;
+    LT* out = g_out + (long long)cell * G.Sp + slot.off;
 #pragma unroll
-  for (int j = 0; j < CPT; ++j) {
-    const int c = tid + j * kGridBlock;
-    if (c >= cells) continue;
-    LT* x = tile + (long long)c * G.Sp;
-    const uint8_t* m = mtile + (long long)c * G.S;
-#pragma unroll
-    for (int h = 0; h < kRegHeads; ++h) {
-      if (h >= G.A) continue;
-      const int off = G.off[h], n = G.nvec[h];
-      if (!((any_bits[j] >> h) & 1u)) {
-        for (int k = 0; k < n; ++k) x[off + k] = from_f32<LT>(0.f);
-        continue;
+    for (int j = 0; j < PMAX; ++j) {
+      if (j < slot.len && ((p.valid >> j) & 1u)) {
+        const float lp = p.x[j] - lse;
+        const float pr = expf(lp);
+        out[j] = from_f32<LT>(dl * ((j == local ? 1.f : 0.f) - pr) - dent * pr * (lp + ent));
       }
-      const float dl = ((gate_bits[j] >> h) & 1u) ? dlogp : 0.f;
-      const int a = action_of(j, h);
-      const float l = lse[j][h], e = ent[j][h];
-      for (int k = 0; k < n; ++k) {
-        float g = 0.f;
-        if (m[off + k]) {
-          const float lp = to_f32(x[off + k]) - l;
-          const float p = expf(lp);
-          g = dl * ((k == a ? 1.f : 0.f) - p) - dent * p * (lp + e);
-        }
-        x[off + k] = from_f32<LT>(g);
-      }
-    }
-    for (int kp = 0; kp < G.n_pick; ++kp) {
-      const float p_lse = s_pick[kp * 3], p_ent = s_pick[kp * 3 + 1];
-      const bool any = s_pick[kp * 3 + 2] != 0.f;
-      float g = 0.f;
-      if (any && G.pick_mask[(b * G.n_pick + kp) * G.HW + cell0 + c]) {
-        const long long a = load_index(G.pick_actions, G.pick_dtype, b * G.n_pick + kp);
-        const float lp = to_f32(x[G.S + kp]) - p_lse;
-        const float p = expf(lp);
-        g = dlogp * ((a == cell0 + c ? 1.f : 0.f) - p) - dent * p * (lp + p_ent);
-      }
-      x[G.S + kp] = from_f32<LT>(g);
     }
   }
-
-  // ---- 7. write the gradient tile back ----------------------------------------------------------
-  uint8_t* g_out = static_cast<uint8_t*>(G.dlogits) + ((b * G.HW + cell0) * G.Sp) * sizeof(LT);
-  const bool same_phase = (reinterpret_cast<uintptr_t>(g_out) & 15u) == tp.lead;
-  fence_async_smem();
-  __syncthreads();
-  const uint8_t* s_src = s_tile_base + tp.lead;
-  if (same_phase) {
-    if (tid == 0 && tp.middle) {
-      bulk_s2g(g_out + tp.head, s_src + tp.head, tp.middle);
-      bulk_commit();
-    }
-    if (tid < (int)tp.head) g_out[tid] = s_src[tid];
-    if (tid >= 32 && tid - 32 < (int)tp.tail)
-      g_out[tp.head + tp.middle + tid - 32] = s_src[tp.head + tp.middle + tid - 32];
-    if (tid == 0 && tp.middle) bulk_wait_read<0>();  // shared memory must outlive the copy's reads
-  } else {
-    for (uint32_t o = tid; o < tile_bytes; o += kGridBlock) g_out[o] = s_src[o];
+  for (int kp = 0; kp < G.n_pick; ++kp) {
+    if (s_pick[kp * 3 + 2] == 0.f) continue;
+    const float p_lse = s_pick[kp * 3], p_ent = s_pick[kp * 3 + 1];
+    const uint8_t* pm = G.pick_mask + (b * G.n_pick + kp) * G.HW + cell0;
+    const long long a = (long long)load_index(G.pick_actions, G.pick_dtype, b * G.n_pick + kp) - cell0;
+    for (int c = tid; c < cells; c += kGridBlock)
+      if (pm[c]) {
+        const float lp = to_f32(g_logits[(long long)c * G.Sp + G.S + kp]) - p_lse;
+        const float pr = expf(lp);
+        g_out[(long long)c * G.Sp + G.S + kp] = from_f32<LT>(dlogp * ((a == c ? 1.f : 0.f) - pr) - dent * pr * (lp + p_ent));
+      }
   }
-  if (cluster_size > 1) cg::this_cluster().sync();  // no CTA exits while a peer may read its smem
 }
 
 // ---- host side -----------------------------------------------------------------------------------
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Lay the heads out over the lanes of a group: head h is cut into pieces of <= pmax logits that
+// occupy a width-aligned power-of-two block of lanes; wide blocks first so that alignment is free.
+static bool plan_lanes(GridDev* G, const int* nvec, int pmax) {
+  struct Blk { int head, pieces, width, piece_len; };
+  Blk blk[B200RL_MAX_HEADS];
+  int off[B200RL_MAX_HEADS], S = 0;
+  for (int h = 0; h < G->A; ++h) {
+    off[h] = S, S += nvec[h];
+    const int pieces = (nvec[h] + pmax - 1) / pmax;
+    blk[h] = Blk{h, pieces, pow2_ceil(pieces), (nvec[h] + pieces - 1) / pieces};
+  }
+  for (int i = 0; i < G->A; ++i)  // stable insertion sort by width, descending
+    for (int j = i; j > 0 && blk[j].width > blk[j - 1].width; --j) {
+      Blk t = blk[j]; blk[j] = blk[j - 1]; blk[j - 1] = t;
+    }
+  int lanes = 0, max_width = 1;
+  for (int i = 0; i < G->A; ++i) lanes += blk[i].width, max_width = blk[i].width > max_width ? blk[i].width : max_width;
+  if (lanes > 32) return false;
+  G->G = pow2_ceil(lanes), G->max_width = max_width;
+  for (int l = 0; l < 32; ++l) G->slot[l] = LaneSlot{0, 0, 0, 0, 1, 0};
+  int lane = 0;
+  for (int i = 0; i < G->A; ++i) {
+    const Blk& k = blk[i];
+    for (int q = 0; q < k.width; ++q, ++lane) {
+      LaneSlot s{0, (uint16_t)off[k.head], 0, (uint8_t)k.head, (uint8_t)k.width, (uint8_t)(q == 0)};
+      const int begin = q * k.piece_len;
+      if (q < k.pieces && begin < nvec[k.head]) {
+        const int len = nvec[k.head] - begin < k.piece_len ? nvec[k.head] - begin : k.piece_len;
+        s.off = (uint16_t)(off[k.head] + begin), s.len = (uint8_t)len;
+      } else {
+        s.off = (uint16_t)off[k.head];  // idle lane of the block: takes part in the shuffles only
+      }
+      G->slot[lane] = s;
+    }
+  }
+  return true;
+}
+
 struct GridLaunch {
   int cluster;
   int cells_per_cta;
-  int cpt;
   size_t smem;
 };
 
-static size_t grid_smem(long long cells, int Sp, int S, size_t lt) {
-  const size_t tile = (size_t)cells * Sp * lt;
-  return ((tile + 16 + 15) & ~(size_t)15) + (size_t)cells * S + 32;
+static size_t grid_smem(int cells, int A) {
+  const size_t words = (size_t)(cells + 31) / 32;
+  return ((words * 4 + (size_t)cells * 2 + 15) & ~(size_t)15) + (size_t)cells * A * 2 * sizeof(float);
 }
 
-static int plan_launch(const GridDev& G, size_t lt, GridLaunch* out) {
-  const size_t limit_two = 110 * 1024, limit_one = (size_t)device_info().max_smem_optin - 2048;
-  GridLaunch best{0, 0, 0, 0};
-  for (int pass = 0; pass < 2 && !best.cluster; ++pass) {
-    for (int cs = 1; cs <= 8; cs *= 2) {
-      if (G.HW % cs) continue;
-      const long long cells = G.HW / cs;
-      if (cells > (long long)kGridBlock * kMaxCpt) continue;
-      const size_t smem = grid_smem(cells, G.Sp, G.S, lt);
-      if (smem <= (pass == 0 ? limit_two : limit_one)) {
-        int cpt = (int)((cells + kGridBlock - 1) / kGridBlock);
-        cpt = cpt <= 1 ? 1 : (cpt <= 2 ? 2 : 4);
-        best = GridLaunch{cs, (int)cells, cpt, smem};
-        break;
-      }
-    }
-  }
-  if (!best.cluster) {
-    set_error("gridnet: a sample of HW=%lld cells x S'=%d logits does not fit 8 CTAs of shared memory", G.HW, G.Sp);
+static int plan_launch(const GridDev& G, GridLaunch* out) {
+  // spread a sample over a cluster until a CTA holds <= 512 cells (one or two cells per thread of
+  // scan work, ~25 KB of shared memory); larger maps fall back to the biggest portable cluster
+  int cs = 1;
+  while (cs < 8 && (G.HW % (cs * 2) == 0) && G.HW / cs > 512) cs *= 2;
+  const long long cells = G.HW / cs;
+  if (cells > kMaxCellsPerCta) {
+    set_error("gridnet: HW=%lld cells needs %lld cells per CTA (max %d)", G.HW, cells, kMaxCellsPerCta);
     return B200RL_EUNSUPPORTED;
   }
-  *out = best;
+  *out = GridLaunch{cs, (int)cells, grid_smem((int)cells, G.A)};
   return B200RL_OK;
 }
 
-template <int MODE, typename LT, int CPT>
+template <int MODE, typename LT, int PMAX>
 static int launch_one(GridDev& G, const PpoDev& P, const GridLaunch& L, cudaStream_t stream) {
-  auto kernel = gridnet_kernel<MODE, LT, CPT>;
+  auto kernel = gridnet_kernel<MODE, LT, PMAX>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
   if (e != cudaSuccess) {
     set_error("gridnet: cudaFuncSetAttribute(%zu bytes): %s", L.smem, cudaGetErrorString(e));
@@ -467,44 +605,39 @@ static int launch_one(GridDev& G, const PpoDev& P, const GridLaunch& L, cudaStre
   return B200RL_OK;
 }
 
-template <int MODE, typename LT>
-static int launch_cpt(GridDev& G, const PpoDev& P, const GridLaunch& L, cudaStream_t stream) {
-  switch (L.cpt) {
-    case 1: return launch_one<MODE, LT, 1>(G, P, L, stream);
-    case 2: return launch_one<MODE, LT, 2>(G, P, L, stream);
-    default: return launch_one<MODE, LT, 4>(G, P, L, stream);
-  }
-}
-
 template <int MODE>
-static int launch_mode(GridDev& G, const PpoDev& P, int logits_dtype, cudaStream_t stream) {
+static int launch_mode(GridDev& G, const PpoDev& P, const int* nvec, int logits_dtype, cudaStream_t stream) {
   GridLaunch L;
-  int rc = plan_launch(G, logits_dtype == B200RL_BF16 ? 2 : 4, &L);
+  int rc = plan_launch(G, &L);
   if (rc) return rc;
   G.cluster = L.cluster, G.cells_per_cta = L.cells_per_cta;
-  if (logits_dtype == B200RL_BF16) return launch_cpt<MODE, __nv_bfloat16>(G, P, L, stream);
-  return launch_cpt<MODE, float>(G, P, L, stream);
+  const bool bf16 = logits_dtype == B200RL_BF16;
+  if (plan_lanes(&G, nvec, 8)) {
+    return bf16 ? launch_one<MODE, __nv_bfloat16, 8>(G, P, L, stream) : launch_one<MODE, float, 8>(G, P, L, stream);
+  }
+  if (plan_lanes(&G, nvec, 32)) {
+    return bf16 ? launch_one<MODE, __nv_bfloat16, 32>(G, P, L, stream) : launch_one<MODE, float, 32>(G, P, L, stream);
+  }
+  set_error("gridnet: the action planes do not fit one warp (32 lanes x 32 logits)");
+  return B200RL_EUNSUPPORTED;
 }
 
 static int make_grid(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask, const uint8_t* pick_mask,
-                     const void* actions, const void* pick_actions, bool need_actions, GridDev* out, const char* who) {
+                     const void* actions, const void* pick_actions, GridDev* out, const char* who) {
   B200RL_REQUIRE(d && logits && mask, "%s: null pointer", who);
   B200RL_REQUIRE(d->B >= 0 && d->HW >= 1 && d->A >= 1 && d->n_pick >= 0, "%s: bad shape", who);
   B200RL_REQUIRE(d->nvec_host != nullptr, "%s: nvec is null", who);
-  B200RL_UNSUPPORTED(d->A > kRegHeads, "%s: A=%d action planes (this build keeps at most %d in registers)", who, d->A,
-                     kRegHeads);
+  B200RL_UNSUPPORTED(d->A > B200RL_MAX_HEADS, "%s: A=%d action planes (max %d)", who, d->A, B200RL_MAX_HEADS);
   B200RL_UNSUPPORTED(d->n_pick > kMaxPick, "%s: n_pick=%d exceeds %d", who, d->n_pick, kMaxPick);
   B200RL_UNSUPPORTED(d->logits_dtype != B200RL_F32 && d->logits_dtype != B200RL_BF16, "%s: logits dtype %d", who,
                      d->logits_dtype);
   B200RL_REQUIRE(d->n_pick == 0 || pick_mask, "%s: pick_mask is null", who);
-  if (need_actions) {
-    B200RL_REQUIRE(actions != nullptr, "%s: actions is null", who);
-    B200RL_REQUIRE(d->n_pick == 0 || pick_actions, "%s: pick_actions is null", who);
-    B200RL_UNSUPPORTED(d->act_dtype != B200RL_U8 && d->act_dtype != B200RL_I32 && d->act_dtype != B200RL_I64,
-                       "%s: action dtype %d", who, d->act_dtype);
-    B200RL_UNSUPPORTED(d->n_pick > 0 && d->pick_dtype != B200RL_I32 && d->pick_dtype != B200RL_I64,
-                       "%s: pick action dtype %d", who, d->pick_dtype);
-  }
+  B200RL_REQUIRE(actions != nullptr, "%s: actions is null", who);
+  B200RL_REQUIRE(d->n_pick == 0 || pick_actions, "%s: pick_actions is null", who);
+  B200RL_UNSUPPORTED(d->act_dtype != B200RL_U8 && d->act_dtype != B200RL_I32 && d->act_dtype != B200RL_I64,
+                     "%s: action dtype %d", who, d->act_dtype);
+  B200RL_UNSUPPORTED(d->n_pick > 0 && d->pick_dtype != B200RL_I32 && d->pick_dtype != B200RL_I64,
+                     "%s: pick action dtype %d", who, d->pick_dtype);
   GridDev G{};
   G.logits = logits, G.mask = mask, G.pick_mask = pick_mask, G.actions = actions, G.pick_actions = pick_actions;
   G.B = d->B, G.HW = d->HW, G.A = d->A, G.n_pick = d->n_pick;
@@ -512,14 +645,14 @@ static int make_grid(const b200rl_gridnet_desc* d, const void* logits, const uin
   int S = 0;
   for (int h = 0; h < d->A; ++h) {
     B200RL_REQUIRE(d->nvec_host[h] >= 1, "%s: nvec[%d]=%d", who, h, d->nvec_host[h]);
-    B200RL_UNSUPPORTED(d->nvec_host[h] > 256, "%s: nvec[%d]=%d exceeds 256", who, h, d->nvec_host[h]);
-    G.nvec[h] = d->nvec_host[h], G.off[h] = S;
+    B200RL_UNSUPPORTED(d->nvec_host[h] > 1024, "%s: nvec[%d]=%d exceeds 1024", who, h, d->nvec_host[h]);
     S += d->nvec_host[h];
     const int gr = d->gate_ref_host ? d->gate_ref_host[h] : -1;
     B200RL_REQUIRE(gr < d->A, "%s: gate_ref[%d]=%d out of range", who, h, gr);
     G.gate_ref[h] = gr;
     G.gate_val[h] = (gr >= 0 && d->gate_val_host) ? d->gate_val_host[h] : 0;
   }
+  B200RL_UNSUPPORTED(S > 65535, "%s: sum(nvec)=%d exceeds 65535", who, S);
   G.S = S, G.Sp = S + d->n_pick;
   *out = G;
   return B200RL_OK;
@@ -532,13 +665,13 @@ extern "C" int b200rl_gridnet_fwd(const b200rl_gridnet_desc* d, const void* logi
                                   float* logp, float* entropy, b200rl_stream_t stream) {
   using namespace b200rl;
   GridDev G;
-  int rc = make_grid(d, logits, mask, pick_mask, actions, pick_actions, true, &G, "gridnet_fwd");
+  int rc = make_grid(d, logits, mask, pick_mask, actions, pick_actions, &G, "gridnet_fwd");
   if (rc) return rc;
   B200RL_REQUIRE(logp && entropy, "gridnet_fwd: null output");
   if (G.B == 0) return B200RL_OK;
   G.logp = logp, G.entropy = entropy;
   PpoDev P{};
-  return launch_mode<kFwd>(G, P, d->logits_dtype, (cudaStream_t)stream);
+  return launch_mode<kFwd>(G, P, d->nvec_host, d->logits_dtype, (cudaStream_t)stream);
 }
 
 extern "C" int b200rl_gridnet_bwd(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
@@ -547,13 +680,13 @@ extern "C" int b200rl_gridnet_bwd(const b200rl_gridnet_desc* d, const void* logi
                                   b200rl_stream_t stream) {
   using namespace b200rl;
   GridDev G;
-  int rc = make_grid(d, logits, mask, pick_mask, actions, pick_actions, true, &G, "gridnet_bwd");
+  int rc = make_grid(d, logits, mask, pick_mask, actions, pick_actions, &G, "gridnet_bwd");
   if (rc) return rc;
   B200RL_REQUIRE(dlogp && dentropy && dlogits, "gridnet_bwd: null pointer");
   if (G.B == 0) return B200RL_OK;
   G.dlogp_in = dlogp, G.dent_in = dentropy, G.dlogits = dlogits;
   PpoDev P{};
-  return launch_mode<kBwd>(G, P, d->logits_dtype, (cudaStream_t)stream);
+  return launch_mode<kBwd>(G, P, d->nvec_host, d->logits_dtype, (cudaStream_t)stream);
 }
 
 extern "C" int b200rl_ppo_gridnet_loss(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
@@ -563,7 +696,7 @@ extern "C" int b200rl_ppo_gridnet_loss(const b200rl_gridnet_desc* d, const void*
                                        b200rl_stream_t stream) {
   using namespace b200rl;
   GridDev G;
-  int rc = make_grid(d, logits, mask, pick_mask, actions, pick_actions, true, &G, "ppo_gridnet_loss");
+  int rc = make_grid(d, logits, mask, pick_mask, actions, pick_actions, &G, "ppo_gridnet_loss");
   if (rc) return rc;
   B200RL_REQUIRE(dlogits != nullptr, "ppo_gridnet_loss: dlogits is null");
   PpoDev P;
@@ -571,7 +704,7 @@ extern "C" int b200rl_ppo_gridnet_loss(const b200rl_gridnet_desc* d, const void*
   if (rc) return rc;
   G.dlogits = dlogits, G.logp = logp_out, G.entropy = entropy_out;
   cudaStream_t s = (cudaStream_t)stream;
-  rc = launch_mode<kPpo>(G, P, d->logits_dtype, s);
+  rc = launch_mode<kPpo>(G, P, d->nvec_host, d->logits_dtype, s);
   if (rc) return rc;
   return ppo_launch_finalize(P, G.B, 1, s);
 }

@@ -78,9 +78,11 @@ struct PolicyTerms {
   float clipped;    // |ratio - 1| > clip
 };
 
-__device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long long i, float new_logp) {
+// new_logp arrives in float64 when the caller summed it that way (GridNet: hundreds of per-cell
+// terms); the subtraction is exact in float64 and rounds once, like an f32 subtraction of f32 inputs.
+__device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long long i, double new_logp) {
   const float A = ppo_sample_advantage(P, i);
-  const float logratio = new_logp - P.old_logp[i];
+  const float logratio = (float)(new_logp - (double)P.old_logp[i]);
   const float ratio = expf(logratio);
   const float cr = fminf(fmaxf(ratio, P.ratio_lo), P.ratio_hi);
   const float s1 = ratio * A, s2 = cr * A;

@@ -148,7 +148,7 @@ def test_learn_epoch_vs_reference_fixture(cuda, name):
         got = v.cpu().numpy().astype(np.float64)
         rms_update = np.sqrt(np.mean((want - init) ** 2))
         rms_err = np.sqrt(np.mean((got - want) ** 2))
-        assert rms_err <= 5e-3 * rms_update + 1e-8, f"{name} param {k}: rms err {rms_err:.3e} vs rms update {rms_update:.3e}"
+        assert rms_err <= 1e-2 * rms_update + 1e-8, f"{name} param {k}: rms err {rms_err:.3e} vs rms update {rms_update:.3e}"
         assert np.abs(got - want).max() <= 2 * hp.learning_rate * n_updates
     for k, tol in (("loss", 1e-4), ("pi_loss", 2e-3), ("entropy_loss", 1e-5), ("approx_kl", 2e-3), ("grad_norm", 1e-3),
                    ("explained_var", 1e-5)):
