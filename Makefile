@@ -12,7 +12,7 @@ build/%.o: rl_algo_impls_b200/csrc/%.cu $(wildcard rl_algo_impls_b200/csrc/*.cuh
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 $(LIB): $(OBJ)
-	$(NVCC) -shared -o $@ $(OBJ) -lcudart
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(OBJ) -lcudart
 
 clean:
 	rm -rf build $(LIB)

@@ -176,6 +176,8 @@ extern "C" int b200rl_ppo_categorical_loss_f32(const float* logits, const uint8_
   CatParams p{logits, mask, actions, B, (int)n, nullptr, nullptr, nullptr, nullptr, dlogits};
   const unsigned grid = (unsigned)((B + kCatBlock - 1) / kCatBlock);
   cudaStream_t s = (cudaStream_t)stream;
+  rc = ppo_launch_prepare(P, s);
+  if (rc) return rc;
   DISPATCH_ACT(act_dtype, cat_ppo_kernel, <<<grid, kCatBlock, 0, s>>>(p, P));
   rc = check_launch("ppo_categorical_loss");
   if (rc) return rc;

@@ -110,6 +110,7 @@ __device__ __forceinline__ void stg_stream_u4(uint4* p, const uint4& v) {
                : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ---- mbarrier + 1-D bulk async copies (TMA engine, no tensor map) ----------------------------

@@ -128,6 +128,8 @@ extern "C" int b200rl_ppo_gaussian_loss_f32(const float* mu, const float* log_st
   p.ls_partials = P.partials + (size_t)B * ppo_nstat(P.V);
   const unsigned grid = (unsigned)((B + kGaussBlock - 1) / kGaussBlock);
   cudaStream_t s = (cudaStream_t)stream;
+  rc = ppo_launch_prepare(P, s);
+  if (rc) return rc;
   gauss_ppo_kernel<<<grid, kGaussBlock, 0, s>>>(p, P);
   gauss_logstd_final_kernel<<<1, kGaussMaxD, 0, s>>>(p, (int)grid);
   rc = check_launch("ppo_gaussian_loss");

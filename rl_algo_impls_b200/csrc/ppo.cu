@@ -34,9 +34,31 @@ int ppo_make_dev(const b200rl_ppo_args* a, long long B, void* workspace, size_t 
   P.halving = a->vf_halving, P.loss_scale = a->loss_scale;
   P.B = B;
   P.partials = static_cast<double*>(workspace);
+  // the last 2 * MAX_VALUE_HEADS floats of the workspace hold the derived (mean, denominator) pairs
+  P.norm = reinterpret_cast<const float*>(static_cast<const uint8_t*>(workspace) + b200rl_ppo_workspace_bytes(B, a->V) -
+                                          2 * B200RL_MAX_VALUE_HEADS * sizeof(float));
   P.stats_out = a->stats_out;
   *out = P;
   return B200RL_OK;
+}
+
+// (sum, sum of squares, count) in f64 -> (mean, unbiased std + 1e-8) in f32, exactly the values the
+// reference's mb_adv.mean(0) / mb_adv.std(0) + 1e-8 feed into the division (ppo.py:307-316).
+__global__ void ppo_prepare_kernel(PpoDev P) {
+  const int Vm = P.adv_mode == 3 ? 1 : P.adv_v;
+  const int v = threadIdx.x;
+  if (v >= Vm) return;
+  const double n = P.moments[2 * Vm], mean = P.moments[v] / n;
+  const double var = fmax(0.0, (P.moments[Vm + v] - P.moments[v] * mean) / (n - 1.0));
+  float* norm = const_cast<float*>(P.norm);
+  norm[v] = (float)mean;
+  norm[Vm + v] = (float)sqrt(var) + 1e-8f;
+}
+
+int ppo_launch_prepare(const PpoDev& P, cudaStream_t stream) {
+  if (P.adv_mode == 0) return B200RL_OK;
+  ppo_prepare_kernel<<<1, B200RL_MAX_VALUE_HEADS, 0, stream>>>(P);
+  return check_launch("ppo_prepare");
 }
 
 // One block.  Column c of partials is summed over rows by the threads with tid % ns == c in a
@@ -158,7 +180,8 @@ extern "C" size_t b200rl_ppo_workspace_bytes(int64_t B, int64_t V) {
   if (V < 1) V = 1;
   // one row of partial stats per sample (grid-per-sample kernels) + per-block rows for the
   // Gaussian log_std gradient (<= 64 action dims)
-  return (size_t)B * (size_t)(4 + 2 * V) * sizeof(double) + ((size_t)B / 128 + 2) * 64 * sizeof(double);
+  return (size_t)B * (size_t)(4 + 2 * V) * sizeof(double) + ((size_t)B / 128 + 2) * 64 * sizeof(double) +
+         2 * B200RL_MAX_VALUE_HEADS * sizeof(float);
 }
 
 extern "C" int b200rl_ppo_scalar_loss_f32(const float* new_logp, const float* entropy, int64_t ent_d, int64_t B,
@@ -172,6 +195,8 @@ extern "C" int b200rl_ppo_scalar_loss_f32(const float* new_logp, const float* en
   int rc = ppo_make_dev(args, B, workspace, workspace_bytes, &P);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  rc = ppo_launch_prepare(P, s);
+  if (rc) return rc;
   const int blocks = (int)((B + kScalarBlock - 1) / kScalarBlock);
   if (kl_cutoff >= 0.f) {
     B200RL_REQUIRE(pi_coef_state != nullptr, "ppo_scalar_loss: kl_cutoff needs pi_coef_state");

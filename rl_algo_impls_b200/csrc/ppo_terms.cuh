@@ -37,33 +37,34 @@ struct PpoDev {
   int halving;
   float loss_scale;
   long long B;
+  const float* norm;  // [2 * Vm] (mean, std + 1e-8) derived from `moments` by ppo_launch_prepare
   double* partials;  // [rows][4 + 2V]
   float* stats_out;
 };
 
 __host__ __device__ inline int ppo_nstat(int V) { return kPolicyStats + 2 * V; }
 
-// (A - mean) / (std + 1e-8) etc. for one sample, then the reward-weight contraction.
+// (A - mean) / (std + 1e-8) etc. for one sample, then the reward-weight contraction.  The float64
+// moments were turned into float (mean, denominator) pairs once per launch (ppo_prepare_kernel),
+// so the per-sample path has no double-precision division or square root on it.
 __device__ __forceinline__ float ppo_sample_advantage(const PpoDev& P, long long i) {
   const float* row = P.adv + i * P.adv_v;
   if (P.adv_mode == 3) {
     float a = row[0];
     if (P.has_w) {
       a = 0.f;
+#pragma unroll 1
       for (int v = 0; v < P.adv_v; ++v) a = fmaf(row[v], P.w[v], a);
     }
-    const double n = P.moments[2], mean = P.moments[0] / n;
-    const double var = fmax(0.0, (P.moments[1] - P.moments[0] * mean) / (n - 1.0));
-    return (a - (float)mean) / ((float)sqrt(var) + 1e-8f);
+    return (a - P.norm[0]) / P.norm[1];
   }
   float acc = 0.f;
+#pragma unroll 1
   for (int v = 0; v < P.adv_v; ++v) {
     float a = row[v];
     if (P.adv_mode != 0) {
-      const double n = P.moments[2 * P.adv_v], mean = P.moments[v] / n;
-      const double var = fmax(0.0, (P.moments[P.adv_v + v] - P.moments[v] * mean) / (n - 1.0));
-      const float denom = (float)sqrt(var) + 1e-8f;
-      a = (P.adv_mode == 1) ? (a - (float)mean) / denom : a / denom;
+      const float denom = P.norm[P.adv_v + v];
+      a = (P.adv_mode == 1) ? (a - P.norm[v]) / denom : a / denom;
     }
     if (!P.has_w) return a;  // adv_v == 1 (checked on the host)
     acc = fmaf(a, P.w[v], acc);
@@ -137,6 +138,9 @@ __device__ __forceinline__ float2 ppo_value_terms(const PpoDev& P, long long i, 
   if (P.dvalues) P.dvalues[o] = P.vf_coef[v] * half * P.loss_scale / (float)P.B * g;
   return make_float2(vl, clipped);
 }
+
+// moments (f64 sum, sum of squares, count) -> norm (f32 mean, std + 1e-8); no-op for adv_mode 0.
+int ppo_launch_prepare(const PpoDev& P, cudaStream_t stream);
 
 // partials [rows][4 + 2V] -> stats_out (see b200rl.h).  One block; fixed order => deterministic.
 int ppo_launch_finalize(const PpoDev& P, long long rows, int ent_d, cudaStream_t stream);
