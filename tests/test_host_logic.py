@@ -1,0 +1,121 @@
+"""Host-side logic that needs no GPU: the Batch contract, spaces, synthetic envs, configs, the lane
+plan of the GridNet kernel's host mirror, TrainStats, and the loud failure without a CUDA device."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+from rl_algo_impls_b200 import ops, spaces
+from rl_algo_impls_b200.configs import CONFIGS
+from rl_algo_impls_b200.envs import SPECS, make_synthetic_env
+from rl_algo_impls_b200.policy import ActorCritic, clamp_actions
+from rl_algo_impls_b200.ppo.ppo import PPO, TrainStats, TrainStepStats, num_or_array
+from rl_algo_impls_b200.rollout import Batch, VecRollout
+from tests.test_oracle_golden import load
+
+
+def test_batch_field_order_is_the_references():
+    # consumers unpack with dataclasses.astuple (ppo/ppo.py:295-305): the order is part of the contract
+    names = [f.name for f in dataclasses.fields(Batch)]
+    assert names == ["obs", "logprobs", "actions", "action_masks", "num_actions", "values", "advantages", "returns",
+                     "additional"]
+
+
+def test_clamp_actions_is_the_references():
+    """The reference's one unit test (tests/shared/policy/test_actor_critic.py:8-17), against the
+    values the live reference produced (tests/golden/index_stream.npz)."""
+    z = load("index_stream")
+    got = clamp_actions(np.array([-1.5, 0, 1.5]), spaces.Box(-1, 1, (1,)), squash_output=False)
+    np.testing.assert_array_equal(got, z["clamp_noscale"])
+    np.testing.assert_array_equal(got, np.array([-1, 0, 1]))
+    got = clamp_actions(np.array([-1, 0, 1]), spaces.Box(-3, 2, (1,)), squash_output=True)
+    np.testing.assert_array_equal(got, z["clamp_squash"])
+    np.testing.assert_array_equal(got, np.array([-3, -0.5, 2]))
+
+
+def test_no_cpu_path():
+    with pytest.raises(RuntimeError, match="CUDA"):
+        VecRollout(torch.device("cpu"), np.zeros(2, bool), np.zeros(2, np.float32), np.zeros((3, 2, 4), np.float32),
+                   np.zeros((3, 2), np.int64), np.zeros((3, 2), np.float32), np.zeros((3, 2), bool),
+                   np.zeros((3, 2), np.float32), np.zeros((3, 2), np.float32), None, 0.99, 0.95)
+    with pytest.raises(Exception, match="CUDA"):
+        ops.gae_scan(torch.zeros(3, 2), torch.zeros(3, 2), torch.zeros(3, 2, dtype=torch.bool),
+                     torch.zeros(2, dtype=torch.bool), torch.zeros(2), 0.99, 0.95)
+
+
+def test_gridnet_spec_from_subaction_mask():
+    spec = ops.GridnetSpec.from_subaction_mask((6, 4, 4, 4, 4, 7, 49), {0: {1: 1, 2: 2, 3: 3, 4: 4, 5: 4, 6: 5}})
+    assert spec.nvec == (6, 4, 4, 4, 4, 7, 49) and spec.n_pick == 0
+    assert spec.gates == ((1, 0, 1), (2, 0, 2), (3, 0, 3), (4, 0, 4), (5, 0, 4), (6, 0, 5))
+    lux = ops.GridnetSpec.from_subaction_mask((4, 6, 4, 4, 5, 5), {1: {2: 0, 3: 1, 4: 1, 5: 2}}, n_pick=1)
+    assert lux.gates == ((2, 1, 0), (3, 1, 1), (4, 1, 1), (5, 1, 2)) and lux.n_pick == 1
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_synthetic_env_contract(name):
+    env = make_synthetic_env(name, 4, seed=3, pool=2)
+    obs, info = env.reset()
+    assert obs.shape == (4,) + SPECS[name].obs_shape and isinstance(info, dict)
+    nobs, rew, term, trunc, _ = env.step(None)
+    V = SPECS[name].n_values
+    assert rew.shape == ((4,) if V == 1 else (4, V)) and rew.dtype == np.float32
+    assert term.dtype == np.bool_ and trunc.dtype == np.bool_ and term.shape == (4,)
+    mask = env.get_action_mask()
+    if SPECS[name].kind == "gridnet":
+        cells = mask["per_position"] if isinstance(mask, dict) else mask
+        hw = SPECS[name].map_hw[0] * SPECS[name].map_hw[1]
+        assert cells.shape == (4, hw, sum(SPECS[name].nvec)) and cells.dtype == np.bool_
+        # a cell is either empty or has at least one valid entry in every head
+        start = 0
+        any_cell = cells.any(-1)
+        for n in SPECS[name].nvec:
+            assert (cells[..., start:start + n].any(-1) == any_cell).all()
+            start += n
+    else:
+        assert mask is None
+    # same seed -> same data
+    env2 = make_synthetic_env(name, 4, seed=3, pool=2)
+    np.testing.assert_array_equal(env2.reset()[0], obs)
+
+
+@pytest.mark.parametrize("key", list(CONFIGS))
+def test_policies_match_the_reference_parameter_counts(key):
+    """Trunks are ours, but built to the reference architectures: the parameter counts of the
+    instantiated reference models are the check."""
+    cfg = CONFIGS[key]
+    env = make_synthetic_env(cfg.env, 2, pool=1)
+    policy = ActorCritic(env, **cfg.policy)
+    n = sum(p.numel() for p in policy.parameters())
+    want = {"C1": 9155, "C2": 1686693, "C3": 142605, "C4": 851727}.get(key)
+    if want is not None:
+        assert n == want, (key, n)
+    assert policy.value_shape == (() if SPECS[cfg.env].n_values == 1 else (SPECS[cfg.env].n_values,))
+    if key == "C5":
+        assert policy.action_shape == {"per_position": (4096, 6), "pick_position": (1,)}
+    if key == "C4":
+        assert policy.action_shape == (256, 7)
+
+
+def test_train_stats_aggregation_matches_the_reference_rules():
+    steps = [TrainStepStats(1.0, 0.5, np.array([1.0, 2.0]), -0.1, 0.01, 0.2, np.array([0.0, 0.5]), {}),
+             TrainStepStats(3.0, 1.5, np.array([3.0, 4.0]), -0.3, 0.03, 0.4, np.array([1.0, 0.5]), {})]
+    s = TrainStats(steps, explained_var=0.25, grad_norms=[1.0, 3.0])
+    assert s.loss == 2.0 and s.pi_loss == 1.0 and s.approx_kl == pytest.approx(0.02) and s.grad_norm == 2.0
+    np.testing.assert_allclose(s.v_loss, [2.0, 3.0])
+    np.testing.assert_allclose(s.val_clipped_frac, [0.5, 0.5])
+
+
+def test_ppo_constructor_keeps_the_reference_attribute_names():
+    env = make_synthetic_env("CartPole-v1", 2, pool=1)
+    algo = PPO(ActorCritic(env), torch.device("cpu"), None, gamma=[1.0, 0.99], gae_lambda=0.9, vf_coef=[0.5, 0.25])
+    # callbacks setattr these between epochs (hyperparam_transitions.py:19-43)
+    for name in ("learning_rate", "clip_range", "clip_range_vf", "ent_coef", "gamma", "gae_lambda", "vf_coef",
+                 "multi_reward_weights", "switch_range", "guide_probability", "teacher_kl_loss_coef",
+                 "freeze_policy_head", "freeze_value_head", "freeze_backbone", "batch_size", "n_epochs", "max_grad_norm"):
+        assert hasattr(algo, name), name
+    assert isinstance(algo.gamma, np.ndarray) and algo.gamma.dtype == np.float64 and algo.gae_lambda == 0.9
+    assert num_or_array(0.5) == 0.5
+    assert algo.optimizer.defaults["eps"] == 1e-7  # ppo.py:146
+    with pytest.raises(AssertionError):
+        PPO(ActorCritic(env), torch.device("cpu"), None, normalize_advantage=True, standardize_advantage=True)
