@@ -214,6 +214,10 @@ def main():
             dist.broadcast(p.data, 0)
     for _ in range(max(3, args.warmup)):
         algo.learn_epoch(0, 1 << 40, gen, None)
+    algo.profile_stages = True
+    algo.learn_epoch(0, 1 << 40, gen, None)
+    algo.profile_stages = False
+    stages = algo.stage_ms
     timer = ops.KernelTimer(["b200rl_ppo_gridnet_loss", "b200rl_gae_scan_f32", "b200rl_gather_rows",
                              "b200rl_ppo_categorical_loss_f32", "b200rl_ppo_gaussian_loss_f32"])
     ops.set_kernel_timer(timer)
@@ -279,7 +283,7 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if not cfg.algo.get("autocast_loss") else "bf16 trunk / f32 loss math",
             "data": "synthetic", "config": workload, "clocks": clock_info, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+            "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "stages_ms": stages,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

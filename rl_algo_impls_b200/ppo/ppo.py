@@ -167,6 +167,8 @@ class PPO(Algorithm):
         self.last_train_stats: Optional[TrainStats] = None
         self.launches_last_epoch = 0  # libb200rl kernels launched by the last learn_epoch (bench.py reports it)
         self.d2h_bytes_last_epoch = 0
+        self.profile_stages = False  # bench.py: CUDA events around rollout / update of the next learn_epoch
+        self.stage_ms: Optional[Dict[str, float]] = None
 
     # ---------------------------------------------------------------------------------------------
     def learn(self: PPOSelf, train_timesteps: int, rollout_generator, callbacks: Optional[List] = None,
@@ -288,7 +290,12 @@ class PPO(Algorithm):
         if self.tb_writer is not None:
             self._log_chart_scalars(timesteps_elapsed)
 
+        if self.profile_stages:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         r = rollout_generator.rollout(gamma=self.gamma, gae_lambda=self.gae_lambda)
+        if self.profile_stages:
+            ev[1].record()
         timesteps_elapsed += r.total_steps
 
         V = int(np.prod(r.values.shape[2:])) if hasattr(r, "values") else 1
@@ -315,18 +322,22 @@ class PPO(Algorithm):
         if self.freeze_policy_head or self.freeze_value_head or self.freeze_backbone:
             self.policy.unfreeze()
 
+        if self.profile_stages:
+            ev[2].record()
+            torch.cuda.synchronize()
+            self.stage_ms = {"rollout_and_gae": ev[0].elapsed_time(ev[1]), "update": ev[1].elapsed_time(ev[2])}
         # one device -> host read for the whole epoch
-        ev = r.explained_variance() if hasattr(r, "explained_variance") else None
+        exv = r.explained_variance() if hasattr(r, "explained_variance") else None
         packed = torch.stack(step_stats).double()
         norms = torch.stack(grad_norms).double().reshape(-1)
-        tail = torch.cat([norms, ev.reshape(1).double()]) if ev is not None else norms
+        tail = torch.cat([norms, exv.reshape(1).double()]) if exv is not None else norms
         host = torch.cat([packed.reshape(-1), tail]).cpu().numpy()
         self.d2h_bytes_last_epoch = host.nbytes
         self.launches_last_epoch = ops.LAUNCHES - launches0
         S = packed.shape[1]
         rows = host[: packed.numel()].reshape(-1, S)
         gn = host[packed.numel(): packed.numel() + norms.numel()]
-        if ev is not None:
+        if exv is not None:
             explained_var = float(host[-1])
         else:
             var_y = np.var(r.y_true).item()
