@@ -220,13 +220,28 @@ int b200rl_ppo_gridnet_loss(const b200rl_gridnet_desc* d, const void* logits, co
  * its log-prob, in one launch.  Replaces shared/actor/gridnet.py:195-207 (sample) +
  * log_prob at shared/policy/actor_critic.py:311-314.  Gumbel-max over a counter-based RNG
  * (Philox4x32-10 keyed by seed, counter = (offset, sample, cell, head)): the distribution is
- * the reference's, the random stream is not torch.multinomial's.
+ * the reference's, the random stream is not torch.multinomial's.  The effective offset is
+ * `offset + *offset_dev` when offset_dev is non-NULL (a device-side step counter: one captured
+ * launch draws fresh numbers on every graph replay).  A head with no valid entry returns action 0
+ * (the reference draws uniformly there; such a head has log-prob 0 and no effect on training).
  */
 int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
-                          const uint8_t* pick_mask, uint64_t seed, uint64_t offset, void* actions_out,
-                          void* pick_actions_out, float* logp, b200rl_stream_t stream);
+                          const uint8_t* pick_mask, uint64_t seed, uint64_t offset, const int64_t* offset_dev,
+                          void* actions_out, void* pick_actions_out, float* logp, b200rl_stream_t stream);
 int b200rl_categorical_sample_f32(const float* logits, const uint8_t* mask, int64_t R, int64_t n, uint64_t seed,
-                                  uint64_t offset, int64_t* actions_out, float* logp, b200rl_stream_t stream);
+                                  uint64_t offset, const int64_t* offset_dev, int64_t* actions_out, float* logp,
+                                  b200rl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K0  rollout-buffer step write.  Replaces the per-step numpy slice assignments of
+ * rollout/sync_step_rollout.py:188-201 (obs[s] = ..., episode_starts[s] = ..., fold_in(...)).
+ * For each of n_tensors fields, copies step_bytes[t] bytes from src[t] (this step's [N, ...] slice)
+ * to dst[t] + (*step_dev % T) * step_bytes[t] (row s of the [T, N, ...] buffer).  The step index
+ * lives on the device so that the whole env step -- policy forward, sampling, buffer write -- can
+ * be captured once in a CUDA graph and replayed T times.
+ */
+int b200rl_rollout_store_step(const void* const* src_host, void* const* dst_host, const int64_t* step_bytes_host,
+                              int n_tensors, const int64_t* step_dev, int64_t T, b200rl_stream_t stream);
 
 #ifdef __cplusplus
 }

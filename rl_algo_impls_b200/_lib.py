@@ -95,8 +95,9 @@ PROTOTYPES = {
         _int,
         [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, C.POINTER(PpoArgs), _vp, _vp, _vp, _vp, _sz, _vp],
     ),
-    "b200rl_gridnet_sample": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
-    "b200rl_categorical_sample_f32": (_int, [_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp]),
+    "b200rl_gridnet_sample": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "b200rl_categorical_sample_f32": (_int, [_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
+    "b200rl_rollout_store_step": (_int, [C.POINTER(_vp), C.POINTER(_vp), c_i64p, _int, _vp, _i64, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -25,3 +25,9 @@ def next_sample_stream() -> Tuple[int, int]:
         reseed()
     _offset += 1
     return _seed, _offset
+
+
+def current_seed() -> int:
+    if _seed is None:
+        reseed()
+    return _seed

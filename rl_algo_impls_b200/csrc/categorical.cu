@@ -89,9 +89,11 @@ __global__ void __launch_bounds__(kCatBlock) cat_ppo_kernel(const CatParams p, c
 
 // Gumbel-max: argmax_k (x_k + g_k) over the valid entries is a draw from softmax(x | valid).
 __global__ void __launch_bounds__(kCatBlock)
-    cat_sample_kernel(const CatParams p, uint64_t seed, uint64_t offset, long long* actions_out) {
+    cat_sample_kernel(const CatParams p, uint64_t seed, uint64_t offset0, const long long* offset_dev,
+                      long long* actions_out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.R) return;
+  const uint64_t offset = offset0 + (offset_dev ? (uint64_t)*offset_dev : 0ull);
   const float* x = p.logits + i * p.n;
   const uint8_t* m = p.mask ? p.mask + i * p.n : nullptr;
   bool any = false;
@@ -185,15 +187,15 @@ extern "C" int b200rl_ppo_categorical_loss_f32(const float* logits, const uint8_
 }
 
 extern "C" int b200rl_categorical_sample_f32(const float* logits, const uint8_t* mask, int64_t R, int64_t n,
-                                             uint64_t seed, uint64_t offset, int64_t* actions_out, float* logp,
-                                             b200rl_stream_t stream) {
+                                             uint64_t seed, uint64_t offset, const int64_t* offset_dev,
+                                             int64_t* actions_out, float* logp, b200rl_stream_t stream) {
   using namespace b200rl;
   B200RL_REQUIRE(logits && actions_out, "categorical_sample: null pointer");
   B200RL_REQUIRE(R >= 0 && n >= 1, "categorical_sample: bad shape");
   if (R == 0) return B200RL_OK;
   CatParams p{logits, mask, nullptr, R, (int)n, logp, nullptr, nullptr, nullptr, nullptr};
   const unsigned grid = (unsigned)((R + kCatBlock - 1) / kCatBlock);
-  cat_sample_kernel<<<grid, kCatBlock, 0, (cudaStream_t)stream>>>(p, seed, offset,
-                                                                 reinterpret_cast<long long*>(actions_out));
+  cat_sample_kernel<<<grid, kCatBlock, 0, (cudaStream_t)stream>>>(
+      p, seed, offset, reinterpret_cast<const long long*>(offset_dev), reinterpret_cast<long long*>(actions_out));
   return check_launch("categorical_sample");
 }

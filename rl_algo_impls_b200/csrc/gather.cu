@@ -88,7 +88,78 @@ __global__ void __launch_bounds__(kGatherBlock) gather_narrow_kernel(const Gathe
   }
 }
 
+// K0: one env step's [N, ...] slices -> row (*step % T) of the [T, N, ...] rollout buffers.
+struct StoreParams {
+  const uint8_t* src[B200RL_MAX_GATHER];
+  uint8_t* dst[B200RL_MAX_GATHER];
+  long long step_bytes[B200RL_MAX_GATHER];
+  long long first_chunk[B200RL_MAX_GATHER + 1];
+  int n;
+  const long long* step_dev;
+  long long T;
+};
+
+__global__ void __launch_bounds__(kGatherBlock) store_step_kernel(const StoreParams p) {
+  const long long item = blockIdx.x;
+  int t = 0;
+  while (t + 1 < p.n && item >= p.first_chunk[t + 1]) ++t;
+  const long long begin = (item - p.first_chunk[t]) * kChunkBytes;
+  const long long sb = p.step_bytes[t];
+  const long long bytes = sb - begin < kChunkBytes ? sb - begin : kChunkBytes;
+  const long long step = *p.step_dev % p.T;
+  const uint8_t* s = p.src[t] + begin;
+  uint8_t* d = p.dst[t] + step * sb + begin;
+  const int tid = threadIdx.x;
+  if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15u) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(s);
+    uint4* d4 = reinterpret_cast<uint4*>(d);
+    const int n4 = (int)(bytes >> 4);
+    constexpr int kIter = kChunkBytes / 16 / kGatherBlock;
+    uint4 v[kIter];
+#pragma unroll
+    for (int i = 0; i < kIter; ++i) {
+      const int o = tid + i * kGatherBlock;
+      if (o < n4) v[i] = ldg_stream_u4(s4 + o);
+    }
+#pragma unroll
+    for (int i = 0; i < kIter; ++i) {
+      const int o = tid + i * kGatherBlock;
+      if (o < n4) stg_stream_u4(d4 + o, v[i]);
+    }
+    for (long long o = ((long long)n4 << 4) + tid; o < bytes; o += kGatherBlock) d[o] = s[o];
+  } else {
+    for (long long o = tid; o < bytes; o += kGatherBlock) d[o] = s[o];
+  }
+}
+
 }  // namespace b200rl
+
+extern "C" int b200rl_rollout_store_step(const void* const* src_host, void* const* dst_host,
+                                         const int64_t* step_bytes_host, int n_tensors, const int64_t* step_dev,
+                                         int64_t T, b200rl_stream_t stream) {
+  using namespace b200rl;
+  B200RL_REQUIRE(src_host && dst_host && step_bytes_host && step_dev, "rollout_store_step: null pointer");
+  B200RL_REQUIRE(n_tensors >= 0 && n_tensors <= B200RL_MAX_GATHER, "rollout_store_step: n_tensors=%d (max %d)",
+                 n_tensors, B200RL_MAX_GATHER);
+  B200RL_REQUIRE(T >= 1, "rollout_store_step: T=%lld", (long long)T);
+  StoreParams p{};
+  p.step_dev = reinterpret_cast<const long long*>(step_dev), p.T = T;
+  long long chunks = 0;
+  for (int t = 0; t < n_tensors; ++t) {
+    B200RL_REQUIRE(src_host[t] && dst_host[t] && step_bytes_host[t] >= 0, "rollout_store_step: tensor %d is null", t);
+    if (step_bytes_host[t] == 0) continue;
+    const int k = p.n++;
+    p.src[k] = static_cast<const uint8_t*>(src_host[t]), p.dst[k] = static_cast<uint8_t*>(dst_host[t]);
+    p.step_bytes[k] = step_bytes_host[t];
+    p.first_chunk[k] = chunks;
+    chunks += (step_bytes_host[t] + kChunkBytes - 1) / kChunkBytes;
+    p.first_chunk[k + 1] = chunks;
+  }
+  if (chunks == 0) return B200RL_OK;
+  B200RL_UNSUPPORTED(chunks > 0x7fffffffLL, "rollout_store_step: %lld chunks", chunks);
+  store_step_kernel<<<(unsigned)chunks, kGatherBlock, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("rollout_store_step");
+}
 
 extern "C" int b200rl_gather_rows(const void* const* src_host, void* const* dst_host, const int64_t* row_bytes_host,
                                   int n_tensors, const int64_t* idx, int64_t B, int64_t n_src_rows,

@@ -26,6 +26,7 @@ struct SampleDev {
   int A, S, Sp, n_pick;
   int nvec[B200RL_MAX_HEADS], off[B200RL_MAX_HEADS], gate_ref[B200RL_MAX_HEADS], gate_val[B200RL_MAX_HEADS];
   uint64_t seed, offset;
+  const long long* offset_dev;
   void* actions_out;
   int act_dtype;
   void* pick_out;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
   __shared__ float s_scalar[2];
   const long long b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t offset = G.offset + (G.offset_dev ? (uint64_t)*G.offset_dev : 0ull);
   float logp_acc = 0.f;
 
   for (long long c = tid; c < G.HW; c += kSampleBlock) {
@@ -68,10 +70,15 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
       const int off = G.off[h], n = G.nvec[h];
       bool any = false;
       for (int k = 0; k < n; ++k) any |= (m[off + k] != 0);
+      if (!any) {  // no unit / nothing to choose: action 0, log-prob 0, no random numbers spent
+        chosen[h] = 0, lp[h] = 0.f;
+        put_index(G.actions_out, G.act_dtype, cell * G.A + h, 0);
+        continue;
+      }
       int best = 0;
       float best_score = -INFINITY;
       for (int k0 = 0; k0 < n; k0 += 4) {
-        const Philox4 r = philox4x32_10(G.seed, (uint64_t)cell, stream_id(G.offset, h, k0 >> 2));
+        const Philox4 r = philox4x32_10(G.seed, (uint64_t)cell, stream_id(offset, h, k0 >> 2));
         const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
         for (int j = 0; j < 4 && k0 + j < n; ++j) {
           const int k = k0 + j;
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
     long long best = 0x7fffffffffffLL;
     for (long long c = tid; c < G.HW; c += kSampleBlock) {
       if (any && !pm[c]) continue;
-      const Philox4 r = philox4x32_10(G.seed, (uint64_t)(b * G.HW + c), stream_id(G.offset, G.A + kp, 0));
+      const Philox4 r = philox4x32_10(G.seed, (uint64_t)(b * G.HW + c), stream_id(offset, G.A + kp, 0));
       const float x = any ? logit_at(G, (b * G.HW + c) * G.Sp + G.S + kp) : 0.f;
       const float score = x + gumbel(r.x);
       if (score > best_score) best_score = score, best = c;
@@ -177,8 +184,9 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
 }  // namespace b200rl
 
 extern "C" int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
-                                     const uint8_t* pick_mask, uint64_t seed, uint64_t offset, void* actions_out,
-                                     void* pick_actions_out, float* logp, b200rl_stream_t stream) {
+                                     const uint8_t* pick_mask, uint64_t seed, uint64_t offset,
+                                     const int64_t* offset_dev, void* actions_out, void* pick_actions_out,
+                                     float* logp, b200rl_stream_t stream) {
   using namespace b200rl;
   B200RL_REQUIRE(d && logits && mask && actions_out && logp, "gridnet_sample: null pointer");
   B200RL_REQUIRE(d->B >= 0 && d->HW >= 1 && d->A >= 1 && d->A <= B200RL_MAX_HEADS && d->n_pick >= 0,
@@ -199,7 +207,7 @@ extern "C" int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* l
     G.gate_val[h] = (gr >= 0 && d->gate_val_host) ? d->gate_val_host[h] : 0;
   }
   G.S = S, G.Sp = S + d->n_pick;
-  G.seed = seed, G.offset = offset;
+  G.seed = seed, G.offset = offset, G.offset_dev = reinterpret_cast<const long long*>(offset_dev);
   G.actions_out = actions_out, G.act_dtype = d->act_dtype, G.pick_out = pick_actions_out, G.pick_dtype = d->pick_dtype;
   G.logp = logp;
   gridnet_sample_kernel<<<(unsigned)d->B, kSampleBlock, 0, (cudaStream_t)stream>>>(G);

@@ -102,11 +102,20 @@ class SyntheticVecEnv:
                 masks = cells
         self._obs, self._rewards, self._dones, self._masks = obs, rewards, dones, masks
         if device is not None:
+            # Device env: the pool lives in HBM, the slot counter is a device scalar and every output is
+            # a fixed tensor refreshed in place (index_select with out=), so a step is a short, sync-free
+            # kernel sequence with static addresses -- capturable in a CUDA graph like a Jux-style env.
             to = lambda a: torch.from_numpy(a).to(device)
             self._obs, self._rewards, self._dones = to(obs), to(rewards), to(dones)
             if masks is not None:
                 self._masks = {k: to(v) for k, v in masks.items()} if isinstance(masks, dict) else to(masks)
             self._no_trunc = torch.zeros(N, dtype=torch.bool, device=device)
+            self._slot_dev = torch.zeros(1, dtype=torch.int64, device=device)
+            one = lambda a: torch.empty((1,) + tuple(a.shape[1:]), dtype=a.dtype, device=device)
+            self._out_obs, self._out_rew, self._out_done = one(self._obs), one(self._rewards), one(self._dones)
+            if masks is not None:
+                self._out_masks = ({k: one(v) for k, v in self._masks.items()} if isinstance(self._masks, dict)
+                                   else one(self._masks))
         else:
             self._no_trunc = np.zeros(N, dtype=np.bool_)
         self._t = 0
@@ -118,12 +127,31 @@ class SyntheticVecEnv:
     def _slot(self) -> int:
         return self._t % self.pool
 
+    def _refresh_device_outputs(self) -> None:
+        torch.index_select(self._obs, 0, self._slot_dev, out=self._out_obs)
+        if self._masks is not None:
+            if isinstance(self._masks, dict):
+                for n, m in self._masks.items():
+                    torch.index_select(m, 0, self._slot_dev, out=self._out_masks[n])
+            else:
+                torch.index_select(self._masks, 0, self._slot_dev, out=self._out_masks)
+
     def reset(self, **_kwargs):
         self._t = 0
+        if self.device is not None:
+            self._slot_dev.zero_()
+            self._refresh_device_outputs()
+            return self._out_obs[0], {}
         return self._obs[0], {}
 
     def step(self, actions):
         """-> (next_obs, rewards, terminations, truncations, infos); actions are accepted and ignored."""
+        if self.device is not None:
+            torch.index_select(self._rewards, 0, self._slot_dev, out=self._out_rew)
+            torch.index_select(self._dones, 0, self._slot_dev, out=self._out_done)
+            self._slot_dev.add_(1).remainder_(self.pool)
+            self._refresh_device_outputs()
+            return self._out_obs[0], self._out_rew[0], self._out_done[0], self._no_trunc, {}
         k = self._slot()
         self._t += 1
         return self._obs[self._slot()], self._rewards[k], self._dones[k], self._no_trunc, {}
@@ -131,6 +159,9 @@ class SyntheticVecEnv:
     def get_action_mask(self):
         if self._masks is None:
             return None
+        if self.device is not None:
+            return ({n: m[0] for n, m in self._out_masks.items()} if isinstance(self._out_masks, dict)
+                    else self._out_masks[0])
         k = self._slot()
         return {n: m[k] for n, m in self._masks.items()} if isinstance(self._masks, dict) else self._masks[k]
 

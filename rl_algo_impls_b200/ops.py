@@ -230,6 +230,29 @@ def gather_rows(sources: Sequence[torch.Tensor], idx: torch.Tensor) -> List[torc
 
 
 # ------------------------------------------------------------------------------------------------
+# K0
+def rollout_store_step(step_tensors: Sequence[torch.Tensor], buffers: Sequence[torch.Tensor], step_dev: torch.Tensor) -> None:
+    """buffers[t][*step_dev % T] = step_tensors[t] for every rollout field in one launch
+    (sync_step_rollout.py:188-201); the step index is read on the device (CUDA-graph friendly)."""
+    _cuda(step_dev, torch.int64, "step_dev")
+    n = len(step_tensors)
+    if n == 0:
+        return
+    if n > _lib.MAX_GATHER:
+        raise ValueError(f"at most {_lib.MAX_GATHER} fields per call")
+    T = buffers[0].shape[0]
+    src_arr, dst_arr, sb_arr = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_int64 * n)()
+    for k, (s, d) in enumerate(zip(step_tensors, buffers)):
+        _cuda(s, None, f"step_tensors[{k}]"), _cuda(d, None, f"buffers[{k}]")
+        if d.shape[0] != T or s.dtype != d.dtype or s.numel() * T != d.numel():
+            raise ValueError(f"field {k}: step slice {tuple(s.shape)} {s.dtype} does not fit buffer {tuple(d.shape)} {d.dtype}")
+        src_arr[k], dst_arr[k], sb_arr[k] = s.data_ptr(), d.data_ptr(), s.numel() * s.element_size()
+    rc = _call("b200rl_rollout_store_step", 1, _lib.lib().b200rl_rollout_store_step, src_arr, dst_arr, sb_arr, n,
+               step_dev.data_ptr(), T, _stream())
+    check(rc, "b200rl_rollout_store_step")
+
+
+# ------------------------------------------------------------------------------------------------
 # PPO arguments shared by the fused-loss entry points
 @dataclass
 class PpoHyper:
@@ -455,14 +478,15 @@ def categorical_logp_entropy(logits, mask, actions):
     return _CategoricalFn.apply(logits, mask, actions)
 
 
-def categorical_sample(logits: torch.Tensor, mask: Optional[torch.Tensor], seed: int, offset: int):
+def categorical_sample(logits: torch.Tensor, mask: Optional[torch.Tensor], seed: int, offset: int,
+                       offset_dev: Optional[torch.Tensor] = None):
     _cuda(logits, torch.float32, "logits")
     R, n = logits.shape
     m = _as_u8(mask, "mask")
     actions = torch.empty(R, dtype=torch.int64, device=logits.device)
     logp = torch.empty(R, dtype=torch.float32, device=logits.device)
     rc = _call("b200rl_categorical_sample_f32", 1, _lib.lib().b200rl_categorical_sample_f32,
-        logits.data_ptr(), _ptr(m), R, n, seed, offset, actions.data_ptr(), logp.data_ptr(), _stream()
+        logits.data_ptr(), _ptr(m), R, n, seed, offset, _ptr(offset_dev), actions.data_ptr(), logp.data_ptr(), _stream()
     )
     check(rc, "b200rl_categorical_sample_f32")
     return actions, logp
@@ -606,7 +630,8 @@ def ppo_gridnet_loss(
     return LossOut(call.stats, call.dvalues, (dlogits,), logp, ent)
 
 
-def gridnet_sample(spec: GridnetSpec, logits, mask, pick_mask, seed: int, offset: int, act_dtype=torch.uint8):
+def gridnet_sample(spec: GridnetSpec, logits, mask, pick_mask, seed: int, offset: int, act_dtype=torch.uint8,
+                   offset_dev: Optional[torch.Tensor] = None):
     """Sample per-cell actions (+ pick) and their joint log-prob in one launch (gridnet.py:195-207)."""
     g = _GridCall(spec, logits, mask, pick_mask, None, None)
     actions = torch.empty((g.B, g.HW, g.A), dtype=act_dtype, device=logits.device)
@@ -615,7 +640,7 @@ def gridnet_sample(spec: GridnetSpec, logits, mask, pick_mask, seed: int, offset
     g.desc.act_dtype = _INDEX_DTYPES[act_dtype]
     g.desc.pick_dtype = _lib.I64
     rc = _call("b200rl_gridnet_sample", 1, _lib.lib().b200rl_gridnet_sample,
-        C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), seed, offset,
+        C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), seed, offset, _ptr(offset_dev),
         actions.data_ptr(), _ptr(pick), logp.data_ptr(), _stream(),
     )  # fmt: skip
     check(rc, "b200rl_gridnet_sample")

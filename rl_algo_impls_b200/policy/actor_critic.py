@@ -19,7 +19,7 @@ import torch.nn as nn
 from .. import ops, spaces
 from ..actor.categorical import MaskedCategorical
 from ..actor.gridnet import GridnetDistribution, ValueDependentMask
-from ..actor.rng import next_sample_stream
+from ..actor.rng import current_seed, next_sample_stream
 from .networks import (GridEncoderDecoderActorCritic, HeadOutputs, MlpActorCritic, NatureCnnActorCritic,
                        UShapedActorCritic)
 
@@ -130,19 +130,26 @@ class ActorCritic(nn.Module):
         return ACForward(logp, ent, out.values)
 
     @torch.no_grad()
-    def step_device(self, obs: torch.Tensor, action_masks: Optional[TensorOrDict] = None):
-        """(actions, values, logp) on the device; per-cell actions are uint8, pick / discrete int64."""
+    def step_device(self, obs: torch.Tensor, action_masks: Optional[TensorOrDict] = None,
+                    offset_dev: Optional[torch.Tensor] = None):
+        """(actions, values, logp) on the device; per-cell actions are uint8, pick / discrete int64.
+        ``offset_dev`` (int64 device scalar) is added to the RNG offset on the device, so a launch
+        captured in a CUDA graph draws fresh numbers on every replay."""
         out = self.head_outputs(obs)
-        seed, offset = next_sample_stream()
+        if offset_dev is None:
+            seed, offset = next_sample_stream()
+        else:  # the device counter alone advances the stream: eager calls and graph replays draw alike
+            seed, offset = current_seed(), 0
         if self.kind == "gridnet":
             cells_mask = action_masks["per_position"] if isinstance(action_masks, dict) else action_masks
             pick_mask = action_masks.get("pick_position") if isinstance(action_masks, dict) else None
             logits = self._grid_logits(out).contiguous()
-            cells, pick, logp = ops.gridnet_sample(self.spec, logits, cells_mask, pick_mask, seed, offset, torch.uint8)
+            cells, pick, logp = ops.gridnet_sample(self.spec, logits, cells_mask, pick_mask, seed, offset, torch.uint8,
+                                                   offset_dev)
             a: TensorOrDict = {"per_position": cells, "pick_position": pick} if self.n_pick else cells
             return a, out.values, logp
         if self.kind == "categorical":
-            a, logp = ops.categorical_sample(out.pi.float().contiguous(), action_masks, seed, offset)
+            a, logp = ops.categorical_sample(out.pi.float().contiguous(), action_masks, seed, offset, offset_dev)
             return a, out.values, logp
         std = torch.exp(out.log_std)
         a = out.pi + std * torch.randn_like(out.pi)

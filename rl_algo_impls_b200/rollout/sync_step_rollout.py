@@ -69,8 +69,10 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         random_num_envs_reset_every_rollout: int = 0,
         prepare_steps: int = 0,
         rolling_num_envs_reset_every_prepare_step: int = 0,
+        cuda_graph: bool = True,
     ) -> None:
         super().__init__(policy, vec_env)
+        self.cuda_graph = cuda_graph
         self.n_steps = int(n_steps)
         self.sde_sample_freq = sde_sample_freq
         self.scale_advantage_by_values_accuracy = scale_advantage_by_values_accuracy
@@ -97,6 +99,13 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         if self.device.type != "cuda":
             raise RuntimeError("SyncStepRolloutGenerator keeps the rollout in HBM: the policy must be on a CUDA device")
         self._upload = _Uploader(self.device)
+        # env steps taken so far, on the device: row index of the buffer write (mod n_steps) and RNG
+        # offset of the sampling kernel, both read inside captured launches
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._rollouts_done = 0
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_outputs = None
+        self._kernels_per_replay = 0
         self.d2h_bytes = 0  # device -> host bytes (sampled actions handed to a host env)
         self.get_action_mask = getattr(vec_env, "get_action_mask", None)
 
@@ -169,39 +178,117 @@ class SyncStepRolloutGenerator(RolloutGenerator):
             self._reset_envs(0, self.rolling_num_envs_reset_every_prepare_step, 0)
 
     # -- the step loop (sync_step_rollout.py:181-216) ------------------------------------------------
+    def _fields(self, a, v, logp, rewards=None):
+        """(this step's slices, their [T, ...] buffers) in one list pair for the K0 store."""
+        src, dst = [self.next_obs, self.next_episode_starts], [self.obs, self.episode_starts]
+        if self.action_masks is not None:
+            if isinstance(self.action_masks, dict):
+                for k, buf in self.action_masks.items():
+                    src.append(self.next_action_masks[k]), dst.append(buf)
+            else:
+                src.append(self.next_action_masks), dst.append(self.action_masks)
+        if isinstance(self.actions, dict):
+            for k, buf in self.actions.items():
+                src.append(a[k].contiguous()), dst.append(buf)
+        else:
+            src.append(a.contiguous()), dst.append(self.actions)
+        src.append(v.contiguous()), dst.append(self.values)
+        if self.logprobs is not None:
+            src.append(logp.contiguous()), dst.append(self.logprobs)
+        if rewards is not None:
+            src.append(rewards.contiguous()), dst.append(self.rewards)
+        return src, dst
+
+    def _policy_step(self):
+        """Sample + evaluate on the current next_obs / masks and write the pre-env fields of this
+        step into row (step_count % T) of the buffers.  Static addresses only: graph-capturable."""
+        from .. import ops
+
+        a, v, logp = self.policy.step_device(self.next_obs, self.next_action_masks, offset_dev=self.step_count)
+        src, dst = self._fields(a, v, logp)
+        ops.rollout_store_step(src, dst, self.step_count)
+        return a
+
+    def _device_env_step(self):
+        """One whole env step with a device env: policy, env, buffer write, carry-over.  No host
+        synchronisation and no host-dependent address: one CUDA-graph replay per env step."""
+        from .. import ops
+
+        a, v, logp = self.policy.step_device(self.next_obs, self.next_action_masks, offset_dev=self.step_count)
+        next_obs, rewards, terminations, truncations, _ = self.vec_env.step(a)
+        src, dst = self._fields(a, v, logp, rewards.reshape(self.rewards.shape[1:]))
+        ops.rollout_store_step(src, dst, self.step_count)  # before next_obs / masks are overwritten
+        self.next_obs.copy_(next_obs)
+        torch.logical_or(terminations, truncations, out=self.next_episode_starts)
+        if self.next_action_masks is not None:
+            m = self.get_action_mask()
+            if isinstance(m, dict):
+                for k, dst_m in self.next_action_masks.items():
+                    dst_m.copy_(m[k])
+            else:
+                self.next_action_masks.copy_(m)
+        self.step_count.add_(1)
+
+    def _capture(self, fn):
+        """Warm up on a side stream, then capture `fn` once (torch.cuda.graph)."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                out = fn()
+        torch.cuda.current_stream().wait_stream(side)
+        from .. import ops
+
+        graph = torch.cuda.CUDAGraph()
+        before = ops.LAUNCHES
+        with torch.cuda.graph(graph):
+            out = fn()
+        self._kernels_per_replay = ops.LAUNCHES - before  # libb200rl kernels inside one replay
+        return graph, out
+
     def _rollout(self, output_next_values: bool) -> Optional[torch.Tensor]:
+        from .. import ops
+
         self.policy.eval()
         self.policy.reset_noise()
-        for s in range(self.n_steps):
+        device_env = getattr(self.vec_env, "device", None) is not None
+        T = self.n_steps
+        if self.cuda_graph and self._graph is None:
+            with torch.no_grad():
+                if device_env:
+                    self._graph, _ = self._capture(self._device_env_step)
+                else:
+                    def policy_part():
+                        a = self._policy_step()
+                        self.step_count.add_(1)
+                        return a
+                    self._graph, self._graph_outputs = self._capture(policy_part)
+        self.step_count.fill_(self._rollouts_done * T)  # row 0 of the buffer, fresh RNG offsets
+        self._rollouts_done += 1
+        for s in range(T):
             if self.sde_sample_freq > 0 and s > 0 and s % self.sde_sample_freq == 0:
                 self.policy.reset_noise()
-            self.obs[s].copy_(self.next_obs, non_blocking=True)
-            self.episode_starts[s].copy_(self.next_episode_starts, non_blocking=True)
-            masks_s = None
-            if self.action_masks is not None:
-                if isinstance(self.action_masks, dict):
-                    for k, buf in self.action_masks.items():
-                        buf[s].copy_(self.next_action_masks[k], non_blocking=True)
-                    masks_s = {k: buf[s] for k, buf in self.action_masks.items()}
+            if device_env:
+                if self._graph is not None:
+                    self._graph.replay()
+                    ops.LAUNCHES += self._kernels_per_replay
                 else:
-                    self.action_masks[s].copy_(self.next_action_masks, non_blocking=True)
-                    masks_s = self.action_masks[s]
-            a, v, logp = self.policy.step_device(self.obs[s], masks_s)
-            self.values[s].copy_(v.reshape(self.values[s].shape), non_blocking=True)
-            if self.logprobs is not None:
-                self.logprobs[s].copy_(logp, non_blocking=True)
-            if isinstance(self.actions, dict):
-                for k, buf in self.actions.items():
-                    buf[s].copy_(a[k].reshape(buf[s].shape), non_blocking=True)
+                    with torch.no_grad():
+                        self._device_env_step()
+                continue
+            # host env: the policy half runs on the device (captured), the env half on the host
+            if self._graph is not None:
+                self._graph.replay()
+                ops.LAUNCHES += self._kernels_per_replay
+                a = self._graph_outputs
             else:
-                self.actions[s].copy_(a.reshape(self.actions[s].shape), non_blocking=True)
+                with torch.no_grad():
+                    a = self._policy_step()
+                    self.step_count.add_(1)
             next_obs, rewards, terminations, truncations, _ = self.vec_env.step(self._env_actions(a))
             self._upload("obs", next_obs, self.next_obs)
             self._upload("rewards", rewards, self.rewards[s])
-            if isinstance(terminations, torch.Tensor):
-                torch.logical_or(terminations, truncations, out=self.next_episode_starts)
-            else:
-                self._upload("starts", np.logical_or(terminations, truncations), self.next_episode_starts)
+            self._upload("starts", np.logical_or(terminations, truncations), self.next_episode_starts)
             if self.get_action_mask is not None and self.next_action_masks is not None:
                 self._upload_masks(self.get_action_mask())
         next_values = self.policy.value_device(self.next_obs) if output_next_values else None
