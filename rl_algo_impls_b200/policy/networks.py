@@ -76,9 +76,10 @@ class NatureCnnActorCritic(nn.Module):
         self.fc = nn.Sequential(ortho_(nn.Linear(n, flatten_dim)), nn.ReLU())
         self.pi = ortho_(nn.Linear(flatten_dim, n_actions), 0.01)
         self.v = ortho_(nn.Linear(flatten_dim, 1), 1.0)
+        self.to(memory_format=torch.channels_last)
 
     def forward(self, obs: torch.Tensor) -> HeadOutputs:
-        x = self.fc(self.cnn(obs.float() / 255.0))
+        x = self.fc(self.cnn((obs.float() / 255.0).contiguous(memory_format=torch.channels_last)))
         return HeadOutputs(self.pi(x), self.v(x).squeeze(-1))
 
 
@@ -106,9 +107,13 @@ class GridEncoderDecoderActorCritic(nn.Module):
             feat = self.encoder(torch.zeros(1, in_channels, *map_hw))
         self.critic = nn.Sequential(nn.Flatten(), mlp([int(np.prod(feat.shape[1:])), *v_hidden, n_values], "relu", 1.0))
         self.n_values = n_values
+        # NHWC in memory: cuDNN's native layout on sm_100 (no nchw<->nhwc transposes around every conv),
+        # and the decoder output is then physically [B, H, W, S] -- the layout the fused loss kernel
+        # reads and writes -- so permute(0, 2, 3, 1) is a free view instead of a 245 MB copy per minibatch.
+        self.to(memory_format=torch.channels_last)
 
     def forward(self, obs: torch.Tensor) -> HeadOutputs:
-        z = self.encoder(obs.float())
+        z = self.encoder(obs.float().contiguous(memory_format=torch.channels_last))
         logits = self.decoder(z).permute(0, 2, 3, 1)  # [B, H, W, S]
         v = self.critic(z)
         return HeadOutputs(logits, v.squeeze(-1) if self.n_values == 1 else v)
@@ -144,9 +149,10 @@ class UShapedActorCritic(nn.Module):
         self.critic_conv = nn.Sequential(nn.Conv2d(channels[0], critic_channels, 3, stride=2, padding=1), nn.GELU())
         self.critic_out = ortho_(nn.Linear(critic_channels, n_values), 1.0)
         self.n_values = n_values
+        self.to(memory_format=torch.channels_last)  # see GridEncoderDecoderActorCritic
 
     def forward(self, obs: torch.Tensor) -> HeadOutputs:
-        x = self.stem(obs.float())
+        x = self.stem(obs.float().contiguous(memory_format=torch.channels_last))
         skips = []
         for i, enc in enumerate(self.enc):
             x = enc(x)
