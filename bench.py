@@ -91,6 +91,15 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def measured_traffic(cfg_key: str, batch: int):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    entry = json.load(open(p)).get(cfg_key)
+    return int(entry["traffic_bytes_per_sample"] * batch) if entry else None
+
+
 def loss_kernel_bytes(policy, batch: int, V: int, logits_bytes: int) -> int:
     """Algorithmic bytes of one fused-loss launch: logits read + dlogits written,
     1 B per mask element, 1 B per per-cell action, 2 B per pick index, 4*(2+5V) per-sample scalars."""
@@ -241,8 +250,10 @@ def main():
         achieved = nbytes / (mean_ms * 1e-3) / 1e9
         roofline = {"kernel": "gridnet_kernel<kPpo> via b200rl_ppo_gridnet_loss (+ its 1-block stats finaliser)",
                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "bytes_per_launch": nbytes, "ms_per_launch": mean_ms, "launches_timed": n,
-                    "peak_source": peak_src}
+                    "traffic": measured_traffic(cfg.key, cfg.algo["batch_size"]), "bytes_per_launch": nbytes,
+                    "ms_per_launch": mean_ms, "launches_timed": n, "peak_source": peak_src,
+                    "note": "mask-driven kernel: logits are read only for cells with a valid action, so DRAM "
+                            "traffic is below the algorithmic bytes (DESIGN.md 4.1)"}
     elif "b200rl_gae_scan_f32" in kernel_ms:
         n, mean_ms = kernel_ms["b200rl_gae_scan_f32"]
         nbytes = cfg.rollout_steps * (16 * V + 1)
