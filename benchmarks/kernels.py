@@ -162,5 +162,19 @@ def main():
         json.dump(rows, open(a.json, "w"), indent=1)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "sample"):
     main()
+
+
+def bench_sample(N, HW, nvec, gates, n_pick, unit_p):
+    logits, mask, pick_mask, _, _ = gridnet_tensors(N, HW, nvec, n_pick, unit_p)
+    spec = ops.GridnetSpec.from_subaction_mask(nvec, gates, n_pick)
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    fn = lambda: ops.gridnet_sample(spec, logits, mask, pick_mask, 1, 0, torch.uint8, counter)
+    med, best = time_kernel(fn, "b200rl_gridnet_sample", flush=False)
+    return dict(kernel="gridnet_sample", N=N, HW=HW, unit_p=unit_p, ms_median=med, ms_best=best)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sample":
+    print(json.dumps(bench_sample(24, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 0.06)))
+    print(json.dumps(bench_sample(128, 4096, LUX_NVEC, LUX_GATES, 1, 0.02)))

@@ -41,4 +41,7 @@ class Algorithm(ABC):
 def update_learning_rate(optimizer: Optimizer, learning_rate: float) -> None:
     """shared/schedule.py:64-66"""
     for group in optimizer.param_groups:
-        group["lr"] = learning_rate
+        if isinstance(group["lr"], torch.Tensor):  # capturable optimizer: the value lives on the device
+            group["lr"].fill_(float(learning_rate))
+        else:
+            group["lr"] = learning_rate

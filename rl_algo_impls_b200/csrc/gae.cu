@@ -57,10 +57,18 @@ __device__ __forceinline__ void store_lanes(float* p, const Lanes<VEC>& r) {
 }
 
 // episode_starts flags of the VEC lanes at one time row.  V == 1 && VEC == 4: one 32-bit load.
+// V > 1 && VEC == 4: four adjacent lanes (lane0 a multiple of 4) belong to at most two envs, the
+// first lane's and the last lane's, so two byte loads cover them.
 template <int VEC, bool V1>
 __device__ __forceinline__ uint32_t load_starts(const uint8_t* row, const long long (&env)[VEC]) {
   if constexpr (V1 && VEC == 4) {
     return __ldg(reinterpret_cast<const unsigned int*>(row + env[0]));
+  } else if constexpr (VEC == 4) {
+    const uint32_t lo = __ldg(row + env[0]) != 0, hi = __ldg(row + env[3]) != 0;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) packed |= (env[i] == env[0] ? lo : hi) << (8 * i);
+    return packed;
   } else {
     uint32_t packed = 0;
 #pragma unroll

@@ -95,6 +95,133 @@ def _world() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+
+class _GraphedUpdate:
+    """One minibatch update -- K3 gather, K2 moments, trunk forward, K4 fused loss, trunk backward and
+    (unless gradients accumulate) clip + Adam -- captured once per (batch size, hyperparameters, buffer
+    addresses) and replayed per minibatch.  Collectives stay outside the captured segments: at world
+    size R > 1 the update is three segments with the moments all-reduce and the gradient all-reduce
+    between them; at R == 1 it is a single graph."""
+
+    def __init__(self, algo: "PPO", batch, B: int, h: ops.PpoHyper, accumulate: bool):
+        self.algo, self.B, self.accumulate = algo, B, accumulate
+        self.world = _world()
+        dev = algo.device
+        self.idx = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.params = [p for p in algo.policy.parameters() if p.requires_grad]
+        self.pool = torch.cuda.graph_pool_handle()
+        self.graphs: List[torch.cuda.CUDAGraph] = []
+        self.kernels_per_replay = 0
+        self.stats: Optional[torch.Tensor] = None
+        self.grad_norm: Optional[torch.Tensor] = None
+        self._mb = self._moments = self._flat = None
+
+        def seg_a():
+            self._mb = batch[self.idx]
+            self._moments = algo._moments_local(self._mb.advantages, h)
+
+        def seg_b():
+            self.stats, _ = algo._minibatch(self._mb, h, None, moments=self._moments)
+            if self.world > 1:
+                self._flat = torch._utils._flatten_dense_tensors([p.grad for p in self.params])
+
+        def seg_c():
+            if self.world > 1:
+                for p, f in zip(self.params, torch._utils._unflatten_dense_tensors(self._flat, [p.grad for p in self.params])):
+                    p.grad.copy_(f)
+            self.grad_norm = nn.utils.clip_grad_norm_(self.params, algo.max_grad_norm).detach()
+            algo.optimizer.step()
+
+        self.segments = [seg_a, seg_b] + ([] if accumulate else [seg_c])
+        self._capture()
+
+    def _between(self, k: int) -> None:
+        """Collectives between segment k and k + 1 (eager, on the same stream)."""
+        if self.world == 1:
+            return
+        if k == 0 and self._moments is not None:
+            dist.all_reduce(self._moments)
+        if k == 1:
+            dist.all_reduce(self._flat)
+            self._flat.div_(self.world)
+
+    def _run_eager(self) -> None:
+        for k, seg in enumerate(self.segments):
+            seg()
+            self._between(k)
+
+    def _capture(self) -> None:
+        algo, opt = self.algo, self.algo.optimizer
+        # the warm-up runs really execute (and, without accumulation, really step the optimizer):
+        # snapshot parameters and Adam state, restore them in place afterwards
+        saved_p = [p.detach().clone() for p in self.params]
+        had_state = {id(p): (p in opt.state and len(opt.state[p]) > 0) for p in self.params}
+        saved_s = {id(p): {k: v.detach().clone() for k, v in opt.state[p].items() if torch.is_tensor(v)}
+                   for p in self.params if had_state[id(p)]}
+        if self.accumulate:
+            for p in self.params:  # backward must ACCUMULATE into fixed buffers
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+        else:
+            opt.zero_grad(set_to_none=True)  # backward must ASSIGN fresh (graph-pool) gradients
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._run_eager()
+                if not self.accumulate:
+                    opt.zero_grad(set_to_none=True)
+        torch.cuda.current_stream().wait_stream(side)
+        before = ops.LAUNCHES
+        merged = self.world == 1
+        if merged:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.pool):
+                for seg in self.segments:
+                    seg()
+            self.graphs = [g]
+        else:
+            for k, seg in enumerate(self.segments):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self.pool):
+                    seg()
+                self.graphs.append(g)
+        self.kernels_per_replay = ops.LAUNCHES - before
+        with torch.no_grad():
+            for p, sp in zip(self.params, saved_p):
+                p.copy_(sp)
+                st = opt.state.get(p, {})
+                if had_state[id(p)]:
+                    for k, v in saved_s[id(p)].items():
+                        st[k].copy_(v)
+                else:
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            if self.accumulate:
+                for p in self.params:
+                    p.grad.zero_()
+        self.grad_buffers = [p.grad for p in self.params] if self.accumulate else None
+
+    def attach(self) -> None:
+        """Accumulating graphs add into fixed gradient buffers: make sure they are the parameters' .grad."""
+        if self.accumulate:
+            for p, g in zip(self.params, self.grad_buffers):
+                if p.grad is not g:
+                    p.grad = g
+
+    def run(self, idx: torch.Tensor):
+        self.idx.copy_(idx, non_blocking=True)
+        if len(self.graphs) == 1:
+            self.graphs[0].replay()
+        else:
+            for k, g in enumerate(self.graphs):
+                g.replay()
+                self._between(k)
+        ops.LAUNCHES += self.kernels_per_replay
+        return self.stats.clone(), (None if self.accumulate else self.grad_norm.clone())
+
+
 class PPO(Algorithm):
     def __init__(
         self,
@@ -130,8 +257,16 @@ class PPO(Algorithm):
         teacher_kl_loss_fn=None,
         teacher_loss_importance_sampling: bool = True,
     ) -> None:
+        on_cuda = torch.device(device).type == "cuda"
+        # Adam(eps=1e-7) as ppo.py:146.  On CUDA the step counter and the learning rate live on the device
+        # (capturable=True, tensor lr) so that the whole update can be replayed from a CUDA graph while
+        # callbacks keep changing the learning rate between epochs.
+        lr = torch.tensor(float(learning_rate), dtype=torch.float32, device=device) if on_cuda else learning_rate
         super().__init__(policy, device, tb_writer, learning_rate,
-                         Adam(policy.parameters(), lr=learning_rate, eps=1e-7))
+                         Adam(policy.parameters(), lr=lr, eps=1e-7, capturable=on_cuda))
+        self.cuda_graph_update = on_cuda  # replay the minibatch update from CUDA graphs when possible
+        self._update_graphs: Dict[tuple, "_GraphedUpdate"] = {}
+        self._captures_in_a_row = 0
         self.policy = policy
         self.gamma = num_or_array(gamma)
         self.gae_lambda = num_or_array(gae_lambda)
@@ -211,23 +346,28 @@ class PPO(Algorithm):
                             vf_halving=bool(self.ppo2_vf_coef_halving), pi_coef=pi_coef, loss_scale=loss_scale,
                             adv_mode=mode, adv_weights=w)
 
-    def _moments(self, adv: torch.Tensor, h: ops.PpoHyper) -> Optional[torch.Tensor]:
+    def _moments_local(self, adv: torch.Tensor, h: ops.PpoHyper) -> Optional[torch.Tensor]:
         if h.adv_mode == ops.ADV_NONE:
             return None
-        B = adv.shape[0]
-        moments = ops.adv_moments(adv.reshape(B, -1), None, h.adv_mode, h.adv_weights)
-        if _world() > 1:  # exact global-minibatch statistics: (sum, sumsq, count) are additive
+        return ops.adv_moments(adv.reshape(adv.shape[0], -1), None, h.adv_mode, h.adv_weights)
+
+    def _moments(self, adv: torch.Tensor, h: ops.PpoHyper) -> Optional[torch.Tensor]:
+        moments = self._moments_local(adv, h)
+        if moments is not None and _world() > 1:  # exact global-minibatch statistics: (sum, sumsq, count) are additive
             dist.all_reduce(moments)
         return moments
 
-    def _minibatch(self, mb, h: ops.PpoHyper, pi_coef_state: Optional[torch.Tensor]) -> Tuple[torch.Tensor, int]:
+    _UNSET = object()
+
+    def _minibatch(self, mb, h: ops.PpoHyper, pi_coef_state: Optional[torch.Tensor], moments=_UNSET) -> Tuple[torch.Tensor, int]:
         """Forward + fused loss + backward of one minibatch.  Returns the device stats vector."""
         obs, old_logp, actions, masks, _, old_values, adv, returns, _additional = (
             mb.obs, mb.logprobs, mb.actions, mb.action_masks, mb.num_actions, mb.values, mb.advantages, mb.returns,
             mb.additional)
         policy = self.policy
         B = obs.shape[0]
-        moments = self._moments(adv, h)
+        if moments is PPO._UNSET:
+            moments = self._moments(adv, h)
         kind = getattr(policy, "kind", None)
         fused = kind is not None and hasattr(policy, "head_outputs") and self.kl_cutoff is None
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(self.autocast_loss)):
@@ -276,6 +416,36 @@ class PPO(Algorithm):
              res.dvalues.reshape(new_values.shape).to(new_values.dtype)])
         return res.stats, 1
 
+    def _graphed_update(self, r, h: ops.PpoHyper) -> Optional["_GraphedUpdate"]:
+        """The captured update for this rollout, or None when the eager path must run: a policy without
+        raw head outputs, the device-side KL cut-off (a data-dependent branch between forward and
+        backward), a ragged last minibatch, or buffers / hyperparameters that change on every epoch
+        (then re-capturing would cost more than it saves)."""
+        if not self.cuda_graph_update or not hasattr(r, "minibatch_indices") or not hasattr(r, "batch"):
+            return None
+        kind = getattr(self.policy, "kind", None)
+        if kind is None or not hasattr(self.policy, "head_outputs") or self.kl_cutoff is not None:
+            return None
+        if r.total_steps % self.batch_size != 0:
+            return None
+        batch = r.batch()
+        _, tensors = batch._flat()
+        key = (self.batch_size, bool(self.gradient_accumulation), bool(self.autocast_loss), float(self.max_grad_norm),
+               h.clip_range, h.clip_range_vf, h.ent_coef, tuple(h.vf_coef), h.vf_halving, h.loss_scale, h.adv_mode,
+               tuple(h.adv_weights) if h.adv_weights is not None else None, tuple(t.data_ptr() for t in tensors))
+        g = self._update_graphs.get(key)
+        if g is not None:
+            self._captures_in_a_row = 0
+            return g
+        if self._captures_in_a_row >= 3:  # the key keeps changing (fresh buffers / scheduled hyperparameters)
+            return None
+        self._captures_in_a_row += 1
+        if len(self._update_graphs) >= 4:
+            self._update_graphs.pop(next(iter(self._update_graphs)))
+        g = _GraphedUpdate(self, batch, self.batch_size, h, bool(self.gradient_accumulation))
+        self._update_graphs[key] = g
+        return g
+
     def learn_epoch(self, timesteps_elapsed: int, total_timesteps: int, rollout_generator,
                     callbacks: Optional[List] = None) -> Tuple[int, bool]:
         start_time = perf_counter()
@@ -308,9 +478,26 @@ class PPO(Algorithm):
 
         step_stats: List[torch.Tensor] = []
         grad_norms: List[torch.Tensor] = []
+        graphed = self._graphed_update(r, h)
+        if graphed is None:
+            self.optimizer.zero_grad(set_to_none=True)  # a captured update may have left its gradient buffers attached
+        else:
+            graphed.attach()
         for _ in range(self.n_epochs):
             step_stats.clear()  # only the last epoch's stats are reported (ppo.py:287-289)
             grad_norms.clear()
+            if graphed is not None:
+                if self.gradient_accumulation:
+                    for p in graphed.params:
+                        p.grad.zero_()
+                for idx in r.minibatch_indices(self.batch_size, shuffle=not self.gradient_accumulation):
+                    stats, gn = graphed.run(idx)
+                    step_stats.append(stats)
+                    if gn is not None:
+                        grad_norms.append(gn)
+                if self.gradient_accumulation:
+                    grad_norms.append(self.optimizer_step_device(keep_grad_buffers=True))
+                continue
             for mb in r.minibatches(self.batch_size, shuffle=not self.gradient_accumulation):
                 self.policy.reset_noise(self.batch_size)
                 stats, _ = self._minibatch(mb, h, pi_coef_state)
@@ -374,12 +561,13 @@ class PPO(Algorithm):
         for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
             g.copy_(f)
 
-    def optimizer_step_device(self) -> torch.Tensor:
+    def optimizer_step_device(self, keep_grad_buffers: bool = False) -> torch.Tensor:
         params = [p for p in self.policy.parameters() if p.grad is not None]
         self._sync_grads(params)
         grad_norm = nn.utils.clip_grad_norm_(params, self.max_grad_norm)
         self.optimizer.step()
-        self.optimizer.zero_grad(set_to_none=True)
+        if not keep_grad_buffers:  # the captured accumulate-backward writes into fixed gradient buffers
+            self.optimizer.zero_grad(set_to_none=True)
         return grad_norm.detach()
 
     def optimizer_step(self) -> float:

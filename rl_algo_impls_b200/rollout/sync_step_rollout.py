@@ -119,6 +119,9 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         self.episode_starts = torch.zeros((T, N), dtype=torch.bool, device=dev)
         self.values = torch.zeros((T, N) + value_shape, dtype=torch.float32, device=dev)
         self.logprobs = torch.zeros((T, N), dtype=torch.float32, device=dev) if include_logp else None
+        # GAE outputs live in fixed buffers too: a captured update graph gathers from the same addresses every rollout
+        self.advantages = torch.zeros((T, N) + value_shape, dtype=torch.float32, device=dev)
+        self.returns = torch.zeros((T, N) + value_shape, dtype=torch.float32, device=dev)
         self.next_episode_starts = torch.ones((N,), dtype=torch.bool, device=dev)
         self.next_obs = torch.zeros((N,) + tuple(obs_space.shape), dtype=self.obs.dtype, device=dev)
 
@@ -317,6 +320,8 @@ class SyncStepRolloutGenerator(RolloutGenerator):
             full_batch_off_accelerator=self.full_batch_off_accelerator,
             subaction_mask=self.subaction_mask,
             action_plane_space=getattr(self.vec_env, "action_plane_space", None),
+            out_advantages=self.advantages,
+            out_returns=self.returns,
         )
 
     # -- masked resets (sync_step_rollout.py:218-278) ------------------------------------------------

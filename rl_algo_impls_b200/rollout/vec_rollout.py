@@ -62,6 +62,8 @@ class VecRollout(Rollout):
         subaction_mask: Optional[Dict[int, Dict[int, int]]] = None,
         action_plane_space=None,
         include_num_actions: bool = False,
+        out_advantages: Optional[torch.Tensor] = None,
+        out_returns: Optional[torch.Tensor] = None,
     ) -> None:
         super().__init__()
         self.device = torch.device(device)
@@ -91,6 +93,8 @@ class VecRollout(Rollout):
             next_values.contiguous(),
             gamma,
             gae_lambda,
+            out_advantages,
+            out_returns,
         )
         if scale_advantage_by_values_accuracy:  # vec_rollout.py:91-94
             spread = self.returns.max() - self.returns.min()
