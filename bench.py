@@ -174,7 +174,20 @@ def run_cpu_learner(cfg_key: str, steps: int, warmup: int, threads: int):
     return n_envs * n_steps * steps / dt, dt / steps * 1e3, sample
 
 
+def emit(line: dict) -> None:
+    """The ONE JSON line, on the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    # Libraries chat on stdout (NCCL prints its version there): keep fd 1 for the JSON line alone.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -200,13 +213,13 @@ def main():
         if rank != 0:
             return
         value, ms, sample = run_cpu_learner(args.config, max(1, args.steps), max(1, min(args.warmup, 2)), threads)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }), flush=True)
+        })
         return
 
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (there is no CPU path)"
@@ -302,7 +315,7 @@ def main():
             "data": "synthetic", "config": workload, "clocks": clock_info, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "stages_ms": stages,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
