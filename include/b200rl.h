@@ -201,14 +201,23 @@ typedef struct b200rl_gridnet_desc {
   const int32_t* gate_val_host;
 } b200rl_gridnet_desc;
 
+/* Scratch for the two-launch scheme (streaming pre-pass writes per-sample lists of the cells that
+ * have a valid action; the fused compute launch reads them).  The PPO entry point needs
+ * b200rl_ppo_gridnet_workspace_bytes(): PPO partials first, GridNet lists after. */
+size_t b200rl_gridnet_workspace_bytes(int64_t B, int64_t HW, int n_pick);
+size_t b200rl_ppo_gridnet_workspace_bytes(int64_t B, int64_t HW, int n_pick, int64_t V);
+
 int b200rl_gridnet_fwd(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
                        const uint8_t* pick_mask, const void* actions, const void* pick_actions, float* logp,
-                       float* entropy, b200rl_stream_t stream);
+                       float* entropy, void* workspace, size_t workspace_bytes, b200rl_stream_t stream);
 int b200rl_gridnet_bwd(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
                        const uint8_t* pick_mask, const void* actions, const void* pick_actions,
-                       const float* dlogp, const float* dentropy, void* dlogits, b200rl_stream_t stream);
-/* One launch: masked logsumexp / log-prob / entropy forward, PPO ratio / clip / value-clip /
- * entropy loss, and the backward into dlogits and dvalues; logits read once, dlogits written once. */
+                       const float* dlogp, const float* dentropy, void* dlogits, void* workspace,
+                       size_t workspace_bytes, b200rl_stream_t stream);
+/* Streaming pre-pass (zero fill of dlogits + mask compaction) followed by ONE fused launch: masked
+ * logsumexp / log-prob / entropy forward, PPO ratio / clip / value-clip / entropy loss, and the
+ * backward into dlogits and dvalues; logits are read only for cells with a valid action, dlogits
+ * written once. */
 int b200rl_ppo_gridnet_loss(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
                             const uint8_t* pick_mask, const void* actions, const void* pick_actions,
                             const b200rl_ppo_args* args, void* dlogits, float* logp_out /*nullable*/,

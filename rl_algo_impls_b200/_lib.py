@@ -89,8 +89,10 @@ PROTOTYPES = {
     ),
     "b200rl_gaussian_fwd_f32": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "b200rl_ppo_gaussian_loss_f32": (_int, [_vp, _vp, _vp, _i64, _i64, C.POINTER(PpoArgs), _vp, _vp, _vp, _sz, _vp]),
-    "b200rl_gridnet_fwd": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "b200rl_gridnet_bwd": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200rl_gridnet_workspace_bytes": (_sz, [_i64, _i64, _int]),
+    "b200rl_ppo_gridnet_workspace_bytes": (_sz, [_i64, _i64, _int, _i64]),
+    "b200rl_gridnet_fwd": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200rl_gridnet_bwd": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200rl_ppo_gridnet_loss": (
         _int,
         [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, C.POINTER(PpoArgs), _vp, _vp, _vp, _vp, _sz, _vp],

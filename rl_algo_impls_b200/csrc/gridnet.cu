@@ -1,45 +1,45 @@
 // K4c: GridNet per-cell MultiDiscrete heads (+ pick_position) -- forward, backward and the
-// fully fused PPO loss, one launch each.
+// fully fused PPO loss.
 //
 // Replaces shared/actor/gridnet.py:38-193 over shared/actor/categorical.py:12-54 and, in the
 // fused mode, ppo/ppo.py:326-361 with the autograd backward of the whole chain: ~60-80
 // eager launches forward and twice that backward in the reference.
 //
-// The kernel is driven by the action MASK.  A cell whose S mask bytes are all zero (no unit
-// on it: ~94-98 % of the cells of a MicroRTS / Lux map) contributes exactly 0 to the
-// log-prob, to the entropy and to the gradient (reference semantics: a fully masked row
-// normalises to uniform, log_prob 0, entropy -0, gradient blocked by torch.where), so its
-// logits are never read; its dlogits row is plain zero fill.
+// The work is driven by the action MASK.  A cell whose S mask bytes are all zero (no unit on
+// it: ~94-98 % of the cells of a MicroRTS / Lux map) contributes exactly 0 to the log-prob,
+// to the entropy and to the gradient (reference semantics: a fully masked row normalises to
+// uniform, log_prob 0, entropy -0, gradient blocked by torch.where), so its logits are never
+// read and its dlogits row is plain zero fill.  Two phases:
 //
-//   1. every thread zero-fills its share of the sample's dlogits (128-bit stores) and scans
-//      the mask bytes with 128-bit loads; a non-zero word flags its cell(s) in a shared bitmap;
-//   2. warp 0 compacts the bitmap into a list of "unit" cells;
-//   3. unit cells are processed by groups of G lanes (G = 8 or 16 for the reference's action
-//      planes): every lane owns one piece of <= PMAX adjacent logits of one head -- small
-//      heads are one lane, a wide head (MicroRTS' 49-way attack target) is spread over an
-//      aligned power-of-two block of lanes and reduced with xor shuffles.  Adjacent lanes read
-//      adjacent addresses, so a cell's row is one coalesced ~300-byte access;
-//   4. per-sample sums run in float64 through shuffles, shared memory and -- when a sample
-//      spans several CTAs -- distributed shared memory across the thread-block cluster; the
-//      pick_position categorical over all cells of the sample uses the same path;
-//   5. thread 0 turns the sample's log-prob into ratio / clipped surrogate / KL terms
-//      (ppo_terms.cuh), one warp handles the value heads;
-//   6. the same lanes revisit the unit cells (L1/L2 hits) and overwrite their zero-filled
-//      dlogits rows with d loss / d logits.
+//  S  streaming, one CTA per chunk of 256 cells:
+//     zero-fills the chunk's dlogits with 128-bit stores, scans its mask bytes (and the
+//     pick_position mask) with 128-bit loads, flags non-empty cells in a shared bitmap
+//     (the first flag prefetches that cell's logits row to L2), compacts the bitmap and
+//     writes the chunk's list of unit cells (+ count) to the workspace.  HBM-bound.
+//  C  fused compute, one CTA per sample -- masked logsumexp / log-prob / entropy, ratio / clip /
+//     value-clip / KL, and the backward into dlogits and dvalues in ONE launch: groups of G lanes (G = 16 for MicroRTS' planes, 8 for Lux') take one listed cell
+//     each; a lane owns <= 8 adjacent logits of one head, a wide head (the 49-way attack target)
+//     spans an aligned power-of-two block of lanes reduced with xor shuffles; per-sample sums
+//     run in float64; thread 0 forms the PPO terms (ppo_terms.cuh), one warp the value heads;
+//     the same lanes then overwrite the listed cells' zero-filled rows with d loss / d logits
+//     straight from registers.  The pick_position categorical over the (compacted) valid cells
+//     is an online-softmax reduction in the same pass.  Latency-bound, but on ~5 % of the cells.
+//
+// Maps of up to 256 cells (MicroRTS 16x16: one chunk per sample) run S and C in the SAME CTA of one
+// launch, so the zero-fill stores of one sample drain while its compute phase runs and CTAs at
+// different phases share an SM.  Larger maps (Lux 64x64: 16 chunks per sample) run S as its own
+// full-occupancy launch and C as a second launch (measured: 124 us vs 176-200 us fused, B=512).
 //
 // HBM traffic per sample: dlogits written once, masks read once, logits / actions read only
-// for unit cells.  No shared-memory tile => ~20 KB of shared memory per CTA and full occupancy.
-#include <cooperative_groups.h>
-
+// for unit cells.  Deterministic: lists are ascending per chunk, every reduction has a fixed order.
 #include "ppo_terms.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace b200rl {
 
-constexpr int kGridBlock = 128;
+constexpr int kStreamBlock = 256;   // threads of the streaming kernel
+constexpr int kChunkCells = 256;    // cells per streaming CTA
 constexpr int kMaxPick = 4;
-constexpr int kMaxCellsPerCta = 4096;
+constexpr int kStashCells = 512;    // unit cells whose (lse, entropy) are parked in shared memory
 
 enum GridMode { kFwd = 0, kBwd = 1, kPpo = 2 };
 
@@ -52,6 +52,7 @@ struct LaneSlot {
   uint8_t width;  // lanes of this head's block (power of two, block is width-aligned)
   uint8_t first;  // first lane of its block
 };
+
 
 struct GridDev {
   const void* logits;
@@ -68,10 +69,14 @@ struct GridDev {
   float* entropy;
   const float* dlogp_in;
   const float* dent_in;
-  int cluster;        // CTAs per sample
-  int cells_per_cta;  // HW / cluster
-  int G;              // lanes per cell group (power of two <= 32)
-  int max_width;      // widest head block
+  int chunks;        // streaming CTAs per sample = ceil(HW / kChunkCells)
+  int G;             // lanes per cell group (power of two <= 32)
+  int max_width;     // widest head block
+  // workspace (written by the streaming kernel, read by the compute kernel)
+  uint16_t* unit_list;   // [B][chunks * kChunkCells]  ascending cell ids per chunk
+  int* unit_count;       // [B][chunks]
+  uint16_t* pick_list;   // [B][n_pick][chunks * kChunkCells]
+  int* pick_count;       // [B][n_pick][chunks]
   LaneSlot slot[32];
 };
 
@@ -114,14 +119,8 @@ __device__ __noinline__ Soft soft_merge(const Soft& a, const Soft& b) {
 }
 __device__ __forceinline__ Soft soft_push(const Soft& a, float x) { return soft_merge(a, Soft{x, 1.f, 0.f}); }
 
-// What one warp / one CTA contributes to its sample.
-struct SamplePart {
-  double logp, ent;
-  Soft pick[kMaxPick];
-  float xa[kMaxPick];  // logit of the chosen pick cell (from the CTA that holds it)
-};
-
 // ---- zero fill / mask scan -----------------------------------------------------------------------
+template <int BLOCK>
 __device__ __forceinline__ void zero_fill(uint8_t* dst, uint32_t bytes) {
   const uint32_t tid = threadIdx.x;
   uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
@@ -131,10 +130,10 @@ __device__ __forceinline__ void zero_fill(uint8_t* dst, uint32_t bytes) {
   const uint32_t n4 = (bytes - head) >> 4;
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   uint32_t i = tid;
-  for (; i + 3u * kGridBlock < n4; i += 4u * kGridBlock) {
-    d4[i] = z, d4[i + kGridBlock] = z, d4[i + 2u * kGridBlock] = z, d4[i + 3u * kGridBlock] = z;
+  for (; i + 3u * BLOCK < n4; i += 4u * BLOCK) {
+    d4[i] = z, d4[i + BLOCK] = z, d4[i + 2u * BLOCK] = z, d4[i + 3u * BLOCK] = z;
   }
-  for (; i < n4; i += kGridBlock) d4[i] = z;
+  for (; i < n4; i += BLOCK) d4[i] = z;
   const uint32_t done = head + (n4 << 4);
   if (tid < bytes - done) dst[done + tid] = 0;
 }
@@ -188,6 +187,7 @@ __device__ __noinline__ void flag_word(uint32_t* bitmap, uint32_t base, const ui
 }
 
 // flags every cell of [mask, mask + bytes) that has a non-zero byte
+template <int BLOCK>
 __device__ __forceinline__ void scan_mask(const uint8_t* mask, uint32_t bytes, uint32_t S, uint32_t* bitmap,
                                           const RowPrefetch& pf) {
   const uint32_t tid = threadIdx.x;
@@ -197,24 +197,25 @@ __device__ __forceinline__ void scan_mask(const uint8_t* mask, uint32_t bytes, u
   const uint4* m4 = reinterpret_cast<const uint4*>(mask + head);
   const uint32_t n4 = (bytes - head) >> 4;
   constexpr uint32_t kUnroll = 4;
-  for (uint32_t i0 = tid; i0 < n4; i0 += kGridBlock * kUnroll) {
+  for (uint32_t i0 = tid; i0 < n4; i0 += BLOCK * kUnroll) {
     uint4 w[kUnroll];
 #pragma unroll
     for (uint32_t u = 0; u < kUnroll; ++u) {
-      const uint32_t i = i0 + u * kGridBlock;
+      const uint32_t i = i0 + u * BLOCK;
       // plain read-only loads (allocate in L1): the unit cells re-read their own mask bytes
       w[u] = i < n4 ? __ldg(m4 + i) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (uint32_t u = 0; u < kUnroll; ++u)
-      if ((w[u].x | w[u].y | w[u].z | w[u].w) != 0u) flag_word(bitmap, head + ((i0 + u * kGridBlock) << 4), w[u], S, pf);
+      if ((w[u].x | w[u].y | w[u].z | w[u].w) != 0u) flag_word(bitmap, head + ((i0 + u * BLOCK) << 4), w[u], S, pf);
   }
   const uint32_t done = head + (n4 << 4);
   if (tid < bytes - done && mask[done + tid]) flag_cell(bitmap, (done + tid) / S, pf);
 }
 
-// warp 0: bitmap -> ascending list of flagged cells; returns the count through *s_count
-__device__ __forceinline__ void compact_cells(const uint32_t* bitmap, int words, uint16_t* list, int* s_count) {
+// warp 0: bitmap -> ascending list of flagged cells (ids offset by `base`); count through *out_count
+__device__ __forceinline__ void compact_cells(const uint32_t* bitmap, int words, uint16_t* list, int base_id,
+                                              int* out_count) {
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
   int base = 0;
@@ -232,11 +233,11 @@ __device__ __forceinline__ void compact_cells(const uint32_t* bitmap, int words,
     while (bits) {
       const int b = __ffs(bits) - 1;
       bits &= bits - 1;
-      list[pos++] = (uint16_t)(w * 32 + b);
+      list[pos++] = (uint16_t)(base_id + w * 32 + b);
     }
     base += __shfl_sync(0xffffffffu, incl, 31);
   }
-  if (lane == 0) *s_count = base;
+  if (lane == 0) *out_count = base;
 }
 
 // ---- one piece of one head ------------------------------------------------------------------------
@@ -325,56 +326,114 @@ __device__ __forceinline__ void piece_backward(LT* out, const LaneSlot& s, uint3
   }
 }
 
-// ---- the kernel --------------------------------------------------------------------------------
-template <int MODE, typename LT, int PMAX, bool PICK>
-__global__ void __launch_bounds__(kGridBlock, PMAX <= 8 ? 8 : 4) gridnet_kernel(const __grid_constant__ GridDev G,
-                                                             const __grid_constant__ PpoDev P) {
+// ---- S: streaming phase ---------------------------------------------------------------------------
+// Where a chunk's lists go: the workspace (split launches) or the CTA's own shared memory.
+struct ChunkLists {
+  uint16_t* unit;      // this chunk's unit-cell list
+  int* unit_count;
+  uint16_t* pick;      // pick head 0's list; head kp is at pick + kp * pick_stride
+  int* pick_count;     // head kp's count is at pick_count + kp * pick_count_stride
+  long long pick_stride, pick_count_stride;
+};
+
+template <typename LT, bool ZERO, int BLOCK>
+__device__ __forceinline__ void stream_chunk(const GridDev& G, long long b, int chunk, uint32_t* bitmap,
+                                             const ChunkLists& out) {
+  const int tid = threadIdx.x;
+  const int cell0 = chunk * kChunkCells;
+  const int cells = (int)min((long long)kChunkCells, G.HW - cell0);
+  const long long row0 = b * G.HW + cell0;
+  const uint8_t* g_mask = G.mask + row0 * G.S;
+  const uint32_t mask_bytes = (uint32_t)cells * (uint32_t)G.S;
+
+  // the mask bytes are consumed right after the zero fill: start them towards L2 first
+  for (uint32_t o = (uint32_t)tid * 128u; o < mask_bytes; o += BLOCK * 128u) prefetch_l2(g_mask + o);
+  if (tid < kChunkCells / 32) bitmap[tid] = 0u;
+  if (ZERO)
+    zero_fill<BLOCK>(reinterpret_cast<uint8_t*>(static_cast<LT*>(G.dlogits) + row0 * G.Sp),
+              (uint32_t)cells * (uint32_t)G.Sp * (uint32_t)sizeof(LT));
+  __syncthreads();
+  scan_mask<BLOCK>(g_mask, mask_bytes, (uint32_t)G.S, bitmap,
+            RowPrefetch{reinterpret_cast<const uint8_t*>(static_cast<const LT*>(G.logits) + row0 * G.Sp),
+                        (uint32_t)G.Sp * (uint32_t)sizeof(LT)});
+  __syncthreads();
+  compact_cells(bitmap, (cells + 31) >> 5, out.unit, cell0, out.unit_count);
+  // pick_position masks: one byte per cell, same compaction (no row prefetch: one logit per cell)
+  for (int kp = 0; kp < G.n_pick; ++kp) {
+    __syncthreads();
+    if (tid < kChunkCells / 32) bitmap[tid] = 0u;
+    __syncthreads();
+    const uint8_t* pm = G.pick_mask + (b * G.n_pick + kp) * G.HW + cell0;
+    for (int c = tid; c < cells; c += BLOCK)
+      if (pm[c]) atomicOr(&bitmap[c >> 5], 1u << (c & 31));
+    __syncthreads();
+    compact_cells(bitmap, (cells + 31) >> 5, out.pick + kp * out.pick_stride, cell0,
+                  out.pick_count + kp * out.pick_count_stride);
+  }
+}
+
+template <typename LT, bool ZERO>
+__global__ void __launch_bounds__(kStreamBlock) gridnet_stream_kernel(const __grid_constant__ GridDev G) {
+  __shared__ uint32_t bitmap[kChunkCells / 32];
+  const long long b = blockIdx.x / G.chunks;
+  const int chunk = (int)(blockIdx.x - b * G.chunks);
+  const ChunkLists out{G.unit_list + (b * G.chunks + chunk) * kChunkCells, G.unit_count + b * G.chunks + chunk,
+                       G.pick_list + ((b * G.n_pick) * G.chunks + chunk) * kChunkCells,
+                       G.pick_count + (b * G.n_pick) * G.chunks + chunk, (long long)G.chunks * kChunkCells, G.chunks};
+  stream_chunk<LT, ZERO, kStreamBlock>(G, b, chunk, bitmap, out);
+}
+
+// ---- C: compute kernel ---------------------------------------------------------------------------
+// Flat position i of a sample's unit list -> cell id, through the per-chunk sub-lists.
+struct ListView {
+  const uint16_t* list;  // [chunks * kChunkCells]
+  const int* prefix;     // shared: exclusive prefix of the chunk counts, [chunks + 1]
+  int chunks;
+  __device__ __forceinline__ int at(int i) const {
+    int c = 0;
+    while (c + 1 < chunks && i >= prefix[c + 1]) ++c;
+    return (int)list[c * kChunkCells + (i - prefix[c])];
+  }
+};
+
+template <int MODE, typename LT, int PMAX, bool PICK, bool SELF_STREAM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
+    gridnet_kernel(const __grid_constant__ GridDev G, const __grid_constant__ PpoDev P) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ double s_wsum[2][kGridBlock / 32];        // per-warp (logp, entropy)
-  __shared__ Soft s_wpick[kMaxPick][kGridBlock / 32];  // per-warp pick statistics
-  __shared__ SamplePart s_cta;                         // this CTA's record, read by its cluster peers
+  __shared__ uint32_t s_bitmap[kChunkCells / 32];
+  __shared__ double s_wsum[2][BLOCK / 32];        // per-warp (logp, entropy)
+  __shared__ Soft s_wpick[kMaxPick][BLOCK / 32];  // per-warp pick statistics
   __shared__ float s_bcast[2];
   __shared__ float s_pick[kMaxPick * 3];  // lse, entropy, any per pick head
-  __shared__ int s_count;
 
   constexpr int NP = PICK ? kMaxPick : 1;  // pick heads compiled in (PICK == false: none)
   const int n_pick = PICK ? G.n_pick : 0;
   const int tid = threadIdx.x;
-  const int cluster_size = G.cluster;
-  const int rank = cluster_size > 1 ? (int)cg::this_cluster().block_rank() : 0;
-  const int cells = G.cells_per_cta;
-  const long long cell0 = (long long)rank * cells;  // first cell of this CTA within a sample
-  const long long n_clusters = gridDim.x / cluster_size;
-  const uint32_t out_bytes = (uint32_t)cells * (uint32_t)G.Sp * (uint32_t)sizeof(LT);
-  const uint32_t mask_bytes = (uint32_t)cells * (uint32_t)G.S;
+  const long long b = blockIdx.x;
+  const long long row0 = b * G.HW;
 
-  // dynamic shared memory: bitmap | unit-cell list | per (unit cell, head) lse and entropy
-  const int words = (cells + 31) >> 5;
-  uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem);
-  uint16_t* list = reinterpret_cast<uint16_t*>(bitmap + words);
-  float* s_lse = reinterpret_cast<float*>(smem + (((size_t)words * 4 + (size_t)cells * 2 + 15) & ~(size_t)15));
-  float* s_ent = s_lse + (size_t)cells * G.A;
+  // ---- S. single-chunk samples stream their own chunk here; larger maps ran the streaming launch -------------
+  __shared__ uint16_t s_list[SELF_STREAM ? kChunkCells : 1];
+  __shared__ uint16_t s_plist[SELF_STREAM && PICK ? kMaxPick * kChunkCells : 1];
+  __shared__ int s_counts[1 + kMaxPick];
+  if (SELF_STREAM) {  // the lists never leave the SM
+    const ChunkLists out{s_list, s_counts, s_plist, s_counts + 1, kChunkCells, 1};
+    stream_chunk<LT, MODE != kFwd, BLOCK>(G, b, 0, s_bitmap, out);
+    __syncthreads();
+  }
 
-  // A CTA (cluster) handles sample b, then b + n_clusters, ... (normally exactly one: the grid is
-  // one cluster per sample).  The streaming half of a sample (zero fill of its dlogits, its mask
-  // bytes on their way to L2) is issued before the latency-bound half of the previous one.
-  auto stream_ahead = [&](long long bn) {
-    const long long r0 = bn * G.HW + cell0;
-    const uint8_t* m = G.mask + r0 * G.S;
-    for (uint32_t o = (uint32_t)tid * 128u; o < mask_bytes; o += kGridBlock * 128u) prefetch_l2(m + o);
-    if (MODE != kFwd) zero_fill(reinterpret_cast<uint8_t*>(static_cast<LT*>(G.dlogits) + r0 * G.Sp), out_bytes);
-  };
-  const long long b_first = blockIdx.x / cluster_size;
-  if (b_first < G.B) stream_ahead(b_first);
+  // dynamic shared memory: chunk-count prefixes | (log-sum-exp, entropy) stash of later passes
+  int* prefix = reinterpret_cast<int*>(smem);                      // [chunks + 1]
+  int* pick_prefix = prefix + (G.chunks + 1);                      // [n_pick][chunks + 1]
+  float* s_lse = reinterpret_cast<float*>(smem + (((size_t)(G.chunks + 1) * (1 + kMaxPick) * 4 + 15) & ~(size_t)15));
+  float* s_ent = s_lse + (size_t)kStashCells * G.A;
 
-  for (long long b = b_first; b < G.B; b += n_clusters) {
-  const long long row0 = b * G.HW + cell0;  // global index of this CTA's first cell
   const LT* g_logits = static_cast<const LT*>(G.logits) + row0 * G.Sp;
   LT* g_out = static_cast<LT*>(G.dlogits) + row0 * G.Sp;
   const uint8_t* g_mask = G.mask + row0 * G.S;
 
   // the per-sample PPO scalars are consumed by one thread after the reductions: start pulling them now
-  if (MODE == kPpo && rank == 0) {
+  if (MODE == kPpo) {
     if (tid == 0) {
       prefetch_l1(P.old_logp + b);
       prefetch_l1(P.adv + b * P.adv_v);
@@ -385,27 +444,32 @@ __global__ void __launch_bounds__(kGridBlock, PMAX <= 8 ? 8 : 4) gridnet_kernel(
     }
   }
 
-  // ---- 1. mask scan (this sample's zero fill was issued one iteration ago) ------------------------
-  for (int w = tid; w < words; w += kGridBlock) bitmap[w] = 0u;
+  // ---- 1. this sample's lists ------------------------------------------------------------------------
+  if (tid == 0) {
+    int acc = 0;
+    for (int c = 0; c < G.chunks; ++c) prefix[c] = acc, acc += SELF_STREAM ? s_counts[0] : G.unit_count[b * G.chunks + c];
+    prefix[G.chunks] = acc;
+  } else if (PICK && tid >= 32 && tid < 32 + n_pick) {
+    const int kp = tid - 32;
+    int acc = 0;
+    int* pp = pick_prefix + kp * (G.chunks + 1);
+    for (int c = 0; c < G.chunks; ++c)
+      pp[c] = acc, acc += SELF_STREAM ? s_counts[1 + kp] : G.pick_count[(b * n_pick + kp) * G.chunks + c];
+    pp[G.chunks] = acc;
+  }
   __syncthreads();
-  scan_mask(g_mask, mask_bytes, (uint32_t)G.S, bitmap,
-            RowPrefetch{reinterpret_cast<const uint8_t*>(g_logits), (uint32_t)G.Sp * (uint32_t)sizeof(LT)});
-  __syncthreads();
-  if (b + n_clusters < G.B) stream_ahead(b + n_clusters);
+  const ListView units{SELF_STREAM ? s_list : G.unit_list + (b * G.chunks) * kChunkCells, prefix, G.chunks};
+  const int n_unit = prefix[G.chunks];
 
-  // ---- 2. compaction -------------------------------------------------------------------------------
-  compact_cells(bitmap, words, list, &s_count);
-  __syncthreads();
-  const int n_unit = s_count;
-
-  // ---- 3. forward over the unit cells -----------------------------------------------------------------
-  const int group = tid / G.G, n_groups = kGridBlock / G.G;
+  // ---- 2. forward over the unit cells -----------------------------------------------------------------
+  const int group = tid / G.G, n_groups = BLOCK / G.G;
   const LaneSlot slot = G.slot[tid & (G.G - 1)];
   const int gate_ref = slot.len ? G.gate_ref[slot.head] : -1;
   const int gate_val = slot.len ? G.gate_val[slot.head] : 0;
   double logp_acc = 0.0, ent_acc = 0.0;
-  // state of the first pass stays in registers for the backward (a CTA rarely has more unit cells
-  // than lane groups); later passes park (log-sum-exp, entropy) in shared memory and reload.
+  // state of the first pass stays in registers for the backward (a sample rarely has more unit
+  // cells than lane groups); later passes park (log-sum-exp, entropy) in shared memory, and cells
+  // beyond the stash recompute their forward in the backward pass.
   float k_d[PMAX], k_e[PMAX];
   uint32_t k_valid = 0u;
   float k_ls = 0.f, k_inv = 0.f, k_ent = 0.f;
@@ -415,7 +479,7 @@ __global__ void __launch_bounds__(kGridBlock, PMAX <= 8 ? 8 : 4) gridnet_kernel(
   for (int i0 = 0; i0 < n_unit; i0 += n_groups) {  // uniform trip count: shuffles stay converged
     const int i = i0 + group;
     const bool live = i < n_unit && slot.len > 0;
-    const int cell = live ? (int)list[i] : 0;
+    const int cell = live ? units.at(i) : 0;
     Piece<LT, PMAX> p;
     p.valid = 0u;
 #pragma unroll
@@ -445,15 +509,13 @@ __global__ void __launch_bounds__(kGridBlock, PMAX <= 8 ? 8 : 4) gridnet_kernel(
       for (int j = 0; j < PMAX; ++j) k_d[j] = d[j], k_e[j] = e[j];
       k_valid = h.any ? p.valid : 0u, k_ls = h.ls, k_inv = h.inv_sum, k_ent = h.ent;
       k_cell = cell, k_local = local, k_gated = gated_in;
-    } else if (slot.first) {
+    } else if (slot.first && i < kStashCells) {
       s_lse[i * G.A + slot.head] = h.any ? h.mx + h.ls : INFINITY;  // +inf marks a head with no valid entry
       s_ent[i * G.A + slot.head] = h.ent;
     }
   }
 
-  // ---- 4. pick_position: one online-softmax pass over this CTA's cells ---------------------------------
-  // (m, s, q) = running max, sum e^(x-m), sum e^(x-m)(x-m) over the valid cells; partials merge
-  // associatively, so the whole sample needs a single exchange (section 5).
+  // ---- 3. pick_position: one online-softmax pass over the valid cells of the sample ----------------------
   Soft pick[NP];
   float pick_xa[NP];
 #pragma unroll
@@ -461,17 +523,21 @@ __global__ void __launch_bounds__(kGridBlock, PMAX <= 8 ? 8 : 4) gridnet_kernel(
     pick[kp] = Soft{-INFINITY, 0.f, 0.f};
     pick_xa[kp] = 0.f;
     if (kp >= n_pick) continue;
-    const uint8_t* pm = G.pick_mask + (b * n_pick + kp) * G.HW + cell0;
+    const ListView pl{SELF_STREAM ? s_plist + kp * kChunkCells
+                                  : G.pick_list + ((b * n_pick + kp) * G.chunks) * kChunkCells,
+                      pick_prefix + kp * (G.chunks + 1), G.chunks};
+    const int n_valid = pl.prefix[G.chunks];
 #pragma unroll 1
-    for (int c = tid; c < cells; c += kGridBlock)
-      if (pm[c]) pick[kp] = soft_push(pick[kp], to_f32(g_logits[(long long)c * G.Sp + G.S + kp]));
-    if (MODE != kBwd && tid == 0) {  // the CTA that holds the chosen cell contributes its logit
-      const long long local = (long long)load_index(G.pick_actions, G.pick_dtype, b * n_pick + kp) - cell0;
-      if (local >= 0 && local < cells) pick_xa[kp] = pm[local] ? to_f32(g_logits[local * G.Sp + G.S + kp]) : kF32Lowest;
+    for (int i = tid; i < n_valid; i += BLOCK)
+      pick[kp] = soft_push(pick[kp], to_f32(g_logits[(long long)pl.at(i) * G.Sp + G.S + kp]));
+    if (MODE != kBwd && tid == 0) {
+      const long long a = (long long)load_index(G.pick_actions, G.pick_dtype, b * n_pick + kp);
+      if (a >= 0 && a < G.HW)
+        pick_xa[kp] = G.pick_mask[(b * n_pick + kp) * G.HW + a] ? to_f32(g_logits[a * G.Sp + G.S + kp]) : kF32Lowest;
     }
   }
 
-  // ---- 5. one exchange: warp partials -> CTA record -> (cluster) -> sample totals --------------------------
+  // ---- 4. per-sample totals: warp partials -> thread 0 ---------------------------------------------------
   {
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -497,95 +563,75 @@ __global__ void __launch_bounds__(kGridBlock, PMAX <= 8 ? 8 : 4) gridnet_kernel(
   }
   __syncthreads();
   float dlogp = 0.f, dent = 0.f;
-  double tot_logp = 0.0, tot_ent = 0.0;
-  if (tid == 0) {  // CTA totals = the eight warp partials, in warp order
+  if (tid == 0) {
+    double tot_logp = 0.0, tot_ent = 0.0;
 #pragma unroll
-    for (int w = 0; w < kGridBlock / 32; ++w) tot_logp += s_wsum[0][w], tot_ent += s_wsum[1][w];
+    for (int w = 0; w < BLOCK / 32; ++w) tot_logp += s_wsum[0][w], tot_ent += s_wsum[1][w];
 #pragma unroll
     for (int kp = 0; kp < NP; ++kp) {
       if (kp >= n_pick) continue;
       Soft t = s_wpick[kp][0];
 #pragma unroll 1
-      for (int w = 1; w < kGridBlock / 32; ++w) t = soft_merge(t, s_wpick[kp][w]);
-      s_cta.pick[kp] = t, s_cta.xa[kp] = pick_xa[kp];
-    }
-    if (cluster_size > 1) s_cta.logp = tot_logp, s_cta.ent = tot_ent;
-  }
-  if (cluster_size > 1) cg::this_cluster().sync();  // every CTA's record is published (all threads arrive)
-  if (tid == 0) {
-    if (cluster_size > 1) {
-      cg::cluster_group cluster = cg::this_cluster();
-      tot_logp = 0.0, tot_ent = 0.0;
-      for (int r = 0; r < cluster_size; ++r) {
-        const SamplePart* o = cluster.map_shared_rank(&s_cta, r);
-        tot_logp += o->logp, tot_ent += o->ent;
-      }
-    }
-    for (int kp = 0; kp < n_pick; ++kp) {
-      Soft t = s_cta.pick[kp];
-      float xa = s_cta.xa[kp];
-      if (cluster_size > 1) {
-        cg::cluster_group cluster = cg::this_cluster();
-        t = cluster.map_shared_rank(&s_cta, 0)->pick[kp], xa = cluster.map_shared_rank(&s_cta, 0)->xa[kp];
-#pragma unroll 1
-        for (int r = 1; r < cluster_size; ++r) {
-          const SamplePart* o = cluster.map_shared_rank(&s_cta, r);
-          t = soft_merge(t, o->pick[kp]);
-          xa += o->xa[kp];  // exactly one CTA holds the chosen cell
-        }
-      }
+      for (int w = 1; w < BLOCK / 32; ++w) t = soft_merge(t, s_wpick[kp][w]);
       const bool any = t.s > 0.f;
       float p_lse = 0.f, p_ent = 0.f;
       if (any) {
         const float ls = logf(t.s);
         p_lse = t.m + ls;
         p_ent = ls - t.q / t.s;
-        tot_logp += (double)(xa - p_lse);
+        tot_logp += (double)(pick_xa[kp] - p_lse);
         tot_ent += (double)p_ent;
       }
       s_pick[kp * 3] = p_lse, s_pick[kp * 3 + 1] = p_ent, s_pick[kp * 3 + 2] = any ? 1.f : 0.f;
     }
     if (MODE == kFwd) {
-      if (rank == 0) G.logp[b] = (float)tot_logp, G.entropy[b] = (float)tot_ent;
+      G.logp[b] = (float)tot_logp, G.entropy[b] = (float)tot_ent;
     } else if (MODE == kBwd) {
       s_bcast[0] = G.dlogp_in[b], s_bcast[1] = G.dent_in[b];
     } else {
-      // ---- 6. PPO scalar stage (every CTA of the cluster derives the same dlogp; rank 0 records) ----------
+      // ---- 5. PPO scalar stage ------------------------------------------------------------------------------
       PolicyTerms t = ppo_policy_terms(P, b, tot_logp);
       s_bcast[0] = t.dlogp, s_bcast[1] = ppo_dentropy(P, 1);
-      if (rank == 0) {
-        double* row = P.partials + b * ppo_nstat(P.V);
-        row[0] = t.surrogate, row[1] = tot_ent, row[2] = t.kl, row[3] = t.clipped;
-        if (G.logp) G.logp[b] = (float)tot_logp;
-        if (G.entropy) G.entropy[b] = (float)tot_ent;
-      }
+      double* row = P.partials + b * ppo_nstat(P.V);
+      row[0] = t.surrogate, row[1] = tot_ent, row[2] = t.kl, row[3] = t.clipped;
+      if (G.logp) G.logp[b] = (float)tot_logp;
+      if (G.entropy) G.entropy[b] = (float)tot_ent;
     }
   }
-  if (MODE == kPpo && rank == 0 && tid >= 32 && tid < 32 + P.V) {
+  if (MODE == kPpo && tid >= 32 && tid < 32 + P.V) {
     const int v = tid - 32;
     float2 r = ppo_value_terms(P, b, v);
     double* row = P.partials + b * ppo_nstat(P.V);
     row[kPolicyStats + v] = r.x, row[kPolicyStats + P.V + v] = r.y;
   }
+  if (MODE == kFwd) return;
   __syncthreads();
-  if (MODE == kFwd) {
-    if (cluster_size > 1) cg::this_cluster().sync();  // peers may still be reading this CTA's record
-    continue;
-  }
   dlogp = s_bcast[0], dent = s_bcast[1];
 
-  // ---- 7. backward over the unit cells: overwrite their zero-filled rows ------------------------------------
+  // ---- 6. backward over the unit cells: overwrite their zero-filled rows -----------------------------------
   if (k_valid)
     piece_backward<LT, PMAX>(g_out + (long long)k_cell * G.Sp + slot.off, slot, k_valid, k_d, k_e, k_ls, k_inv, k_ent,
                              k_local, k_gated ? dlogp : 0.f, dent);
 #pragma unroll 1
-  for (int i = n_groups + group; i < n_unit; i += n_groups) {  // cells beyond the first pass
-    if (slot.len == 0) continue;
-    const float lse = s_lse[i * G.A + slot.head];
-    if (lse == INFINITY) continue;  // no valid entry in this head: gradient stays zero
-    const float ent = s_ent[i * G.A + slot.head];
-    const int cell = (int)list[i];
-    const Piece<LT, PMAX> p = load_piece<LT, PMAX>(g_logits + (long long)cell * G.Sp, g_mask + (long long)cell * G.S, slot);
+  for (int i0 = n_groups; i0 < n_unit; i0 += n_groups) {  // cells beyond the first pass (uniform trip count)
+    const int i = i0 + group;
+    const bool live = i < n_unit && slot.len > 0;
+    const int cell = live ? units.at(i) : 0;
+    Piece<LT, PMAX> p;
+    p.valid = 0u;
+#pragma unroll
+    for (int j = 0; j < PMAX; ++j) p.x[j] = 0.f;
+    if (live) p = load_piece<LT, PMAX>(g_logits + (long long)cell * G.Sp, g_mask + (long long)cell * G.S, slot);
+    float lse, ent;
+    if (i0 + n_groups - 1 < kStashCells) {  // the whole pass is in the stash (warp-uniform test)
+      lse = live ? s_lse[i * G.A + slot.head] : INFINITY;
+      ent = live ? s_ent[i * G.A + slot.head] : 0.f;
+    } else {  // beyond the stash: redo the forward reductions
+      float d0[PMAX], e0[PMAX];
+      const HeadStat h = head_forward<LT, PMAX>(p, slot, G.max_width, d0, e0);
+      lse = h.any ? h.mx + h.ls : INFINITY, ent = h.ent;
+    }
+    if (!live || lse == INFINITY) continue;  // no valid entry in this head: gradient stays zero
     const long long abase = (row0 + cell) * G.A;
     const bool gated_in = gate_ref < 0 || load_index(G.actions, G.act_dtype, abase + gate_ref) == gate_val;
     const int local = load_index(G.actions, G.act_dtype, abase + slot.head) - (int)(slot.off - slot.head_off);
@@ -599,22 +645,23 @@ __global__ void __launch_bounds__(kGridBlock, PMAX <= 8 ? 8 : 4) gridnet_kernel(
     piece_backward<LT, PMAX>(g_out + (long long)cell * G.Sp + slot.off, slot, p.valid, d, e, 0.f, 1.f, ent, local,
                              gated_in ? dlogp : 0.f, dent);
   }
-  for (int kp = 0; kp < n_pick; ++kp) {
-    if (s_pick[kp * 3 + 2] == 0.f) continue;
+#pragma unroll
+  for (int kp = 0; kp < NP; ++kp) {
+    if (kp >= n_pick || s_pick[kp * 3 + 2] == 0.f) continue;
     const float p_lse = s_pick[kp * 3], p_ent = s_pick[kp * 3 + 1];
-    const uint8_t* pm = G.pick_mask + (b * n_pick + kp) * G.HW + cell0;
-    const long long a = (long long)load_index(G.pick_actions, G.pick_dtype, b * n_pick + kp) - cell0;
-    for (int c = tid; c < cells; c += kGridBlock)
-      if (pm[c]) {
-        const float lp = to_f32(g_logits[(long long)c * G.Sp + G.S + kp]) - p_lse;
-        const float pr = expf(lp);
-        g_out[(long long)c * G.Sp + G.S + kp] = from_f32<LT>(dlogp * ((a == c ? 1.f : 0.f) - pr) - dent * pr * (lp + p_ent));
-      }
+    const ListView pl{SELF_STREAM ? s_plist + kp * kChunkCells
+                                  : G.pick_list + ((b * n_pick + kp) * G.chunks) * kChunkCells,
+                      pick_prefix + kp * (G.chunks + 1), G.chunks};
+    const int n_valid = pl.prefix[G.chunks];
+    const long long a = (long long)load_index(G.pick_actions, G.pick_dtype, b * n_pick + kp);
+#pragma unroll 1
+    for (int i = tid; i < n_valid; i += BLOCK) {
+      const int c = pl.at(i);
+      const float lp = to_f32(g_logits[(long long)c * G.Sp + G.S + kp]) - p_lse;
+      const float pr = fast_exp(lp);
+      g_out[(long long)c * G.Sp + G.S + kp] = from_f32<LT>(dlogp * ((a == c ? 1.f : 0.f) - pr) - dent * pr * (lp + p_ent));
+    }
   }
-  // the next sample reuses the bitmap / list / stash, and peers may still be reading this CTA's record
-  if (cluster_size > 1) cg::this_cluster().sync();
-  else __syncthreads();
-  }  // samples
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -662,83 +709,80 @@ static bool plan_lanes(GridDev* G, const int* nvec, int pmax) {
   return true;
 }
 
-struct GridLaunch {
-  int cluster;
-  int cells_per_cta;
-  size_t smem;
-};
+static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-static size_t grid_smem(int cells, int A) {
-  const size_t words = (size_t)(cells + 31) / 32;
-  return ((words * 4 + (size_t)cells * 2 + 15) & ~(size_t)15) + (size_t)cells * A * 2 * sizeof(float);
+// workspace of the two-launch scheme: unit lists + counts (+ pick lists + counts)
+static size_t grid_workspace_bytes(long long B, long long HW, int n_pick) {
+  const long long chunks = (HW + kChunkCells - 1) / kChunkCells;
+  size_t n = align16((size_t)B * chunks * kChunkCells * sizeof(uint16_t)) + align16((size_t)B * chunks * sizeof(int));
+  n += align16((size_t)B * n_pick * chunks * kChunkCells * sizeof(uint16_t)) + align16((size_t)B * n_pick * chunks * sizeof(int));
+  return n + 64;
 }
 
-static int plan_launch(const GridDev& G, GridLaunch* out) {
-  // spread a sample over a cluster until a CTA holds <= 512 cells (one or two cells per thread of
-  // scan work, ~25 KB of shared memory); larger maps fall back to the biggest portable cluster
-  int cs = 1;
-  while (cs < 8 && (G.HW % (cs * 2) == 0) && G.HW / cs > 512) cs *= 2;
-  const long long cells = G.HW / cs;
-  if (cells > kMaxCellsPerCta) {
-    set_error("gridnet: HW=%lld cells needs %lld cells per CTA (max %d)", G.HW, cells, kMaxCellsPerCta);
-    return B200RL_EUNSUPPORTED;
-  }
-  *out = GridLaunch{cs, (int)cells, grid_smem((int)cells, G.A)};
+static int bind_workspace(GridDev* G, void* workspace, size_t workspace_bytes, const char* who) {
+  G->chunks = (int)((G->HW + kChunkCells - 1) / kChunkCells);
+  B200RL_REQUIRE(workspace != nullptr && workspace_bytes >= grid_workspace_bytes(G->B, G->HW, G->n_pick),
+                 "%s: workspace too small (%zu < %zu bytes)", who, workspace_bytes,
+                 grid_workspace_bytes(G->B, G->HW, G->n_pick));
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  w += (16 - (reinterpret_cast<uintptr_t>(w) & 15)) & 15;
+  G->unit_list = reinterpret_cast<uint16_t*>(w), w += align16((size_t)G->B * G->chunks * kChunkCells * sizeof(uint16_t));
+  G->unit_count = reinterpret_cast<int*>(w), w += align16((size_t)G->B * G->chunks * sizeof(int));
+  G->pick_list = reinterpret_cast<uint16_t*>(w), w += align16((size_t)G->B * G->n_pick * G->chunks * kChunkCells * sizeof(uint16_t));
+  G->pick_count = reinterpret_cast<int*>(w);
   return B200RL_OK;
+}
+
+static size_t compute_smem(const GridDev& G) {
+  return align16((size_t)(G.chunks + 1) * (1 + kMaxPick) * 4) + (size_t)kStashCells * G.A * 2 * sizeof(float);
+}
+
+template <int MODE, typename LT, int PMAX, bool PICK, bool SELF_STREAM>
+static int launch_compute(GridDev& G, const PpoDev& P, cudaStream_t stream) {
+  // a self-streaming CTA is mostly a streamer: 128 threads keep 8 of them per SM; the compute-only
+  // launch of the split path gets 256 threads (more lane groups per sample)
+  constexpr int BLOCK = SELF_STREAM ? 128 : 256;
+  auto kernel = gridnet_kernel<MODE, LT, PMAX, PICK, SELF_STREAM, BLOCK>;
+  const size_t smem = compute_smem(G);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("gridnet: cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(e));
+      return B200RL_ECUDA;
+    }
+  }
+  kernel<<<(unsigned)G.B, BLOCK, smem, stream>>>(G, P);
+  return check_launch("gridnet");
 }
 
 template <int MODE, typename LT, int PMAX, bool PICK>
-static int launch_one(GridDev& G, const PpoDev& P, const GridLaunch& L, cudaStream_t stream) {
-  auto kernel = gridnet_kernel<MODE, LT, PMAX, PICK>;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-  if (e != cudaSuccess) {
-    set_error("gridnet: cudaFuncSetAttribute(%zu bytes): %s", L.smem, cudaGetErrorString(e));
-    return B200RL_ECUDA;
+static int launch_pair(GridDev& G, const PpoDev& P, cudaStream_t stream) {
+  const long long stream_ctas = G.B * G.chunks;
+  if (stream_ctas > 0x7fffffffLL) {
+    set_error("gridnet: batch too large (%lld samples x %d chunks)", G.B, G.chunks);
+    return B200RL_EUNSUPPORTED;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)L.cluster);
-  cfg.blockDim = dim3(kGridBlock);
-  cfg.dynamicSmemBytes = L.smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)L.cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  // One cluster per sample while the grid fits (the hardware scheduler overlaps CTAs at different
-  // phases better than a persistent loop does: measured 116 vs 136 us on the C4 minibatch); beyond
-  // 2^31 - 1 CTAs the kernel's sample loop takes over.
-  long long ctas = G.B * L.cluster;
-  const long long max_ctas = 0x7fffffffLL - (0x7fffffffLL % L.cluster);
-  if (ctas > max_ctas) ctas = max_ctas;
-  cfg.gridDim = dim3((unsigned)ctas);
-  e = cudaLaunchKernelEx(&cfg, kernel, (const GridDev)G, P);
-  if (e != cudaSuccess) {
-    set_error("gridnet launch (cluster %d, %zu B smem): %s", L.cluster, L.smem, cudaGetErrorString(e));
-    return B200RL_ECUDA;
-  }
-  return B200RL_OK;
+  if (G.chunks == 1) return launch_compute<MODE, LT, PMAX, PICK, true>(G, P, stream);
+  if (MODE == kFwd) gridnet_stream_kernel<LT, false><<<(unsigned)stream_ctas, kStreamBlock, 0, stream>>>(G);
+  else gridnet_stream_kernel<LT, true><<<(unsigned)stream_ctas, kStreamBlock, 0, stream>>>(G);
+  int rc = check_launch("gridnet_stream");
+  if (rc) return rc;
+  return launch_compute<MODE, LT, PMAX, PICK, false>(G, P, stream);
 }
 
 template <int MODE>
 static int launch_mode(GridDev& G, const PpoDev& P, const int* nvec, int logits_dtype, cudaStream_t stream) {
-  GridLaunch L;
-  int rc = plan_launch(G, &L);
-  if (rc) return rc;
-  G.cluster = L.cluster, G.cells_per_cta = L.cells_per_cta;
+  B200RL_UNSUPPORTED(G.chunks * kChunkCells > 65536, "gridnet: HW=%lld cells exceeds 65536", G.HW);
   const bool bf16 = logits_dtype == B200RL_BF16;
   if (plan_lanes(&G, nvec, 8)) {
     if (G.n_pick == 0)
-      return bf16 ? launch_one<MODE, __nv_bfloat16, 8, false>(G, P, L, stream)
-                  : launch_one<MODE, float, 8, false>(G, P, L, stream);
-    return bf16 ? launch_one<MODE, __nv_bfloat16, 8, true>(G, P, L, stream)
-                : launch_one<MODE, float, 8, true>(G, P, L, stream);
+      return bf16 ? launch_pair<MODE, __nv_bfloat16, 8, false>(G, P, stream)
+                  : launch_pair<MODE, float, 8, false>(G, P, stream);
+    return bf16 ? launch_pair<MODE, __nv_bfloat16, 8, true>(G, P, stream) : launch_pair<MODE, float, 8, true>(G, P, stream);
   }
   if (plan_lanes(&G, nvec, 32)) {
-    return bf16 ? launch_one<MODE, __nv_bfloat16, 32, true>(G, P, L, stream)
-                : launch_one<MODE, float, 32, true>(G, P, L, stream);
+    return bf16 ? launch_pair<MODE, __nv_bfloat16, 32, true>(G, P, stream)
+                : launch_pair<MODE, float, 32, true>(G, P, stream);
   }
   set_error("gridnet: the action planes do not fit one warp (32 lanes x 32 logits)");
   return B200RL_EUNSUPPORTED;
@@ -782,15 +826,26 @@ static int make_grid(const b200rl_gridnet_desc* d, const void* logits, const uin
 
 }  // namespace b200rl
 
+extern "C" size_t b200rl_gridnet_workspace_bytes(int64_t B, int64_t HW, int n_pick) {
+  return b200rl::grid_workspace_bytes(B < 1 ? 1 : B, HW < 1 ? 1 : HW, n_pick < 0 ? 0 : n_pick);
+}
+
+extern "C" size_t b200rl_ppo_gridnet_workspace_bytes(int64_t B, int64_t HW, int n_pick, int64_t V) {
+  return b200rl_ppo_workspace_bytes(B, V) + b200rl_gridnet_workspace_bytes(B, HW, n_pick);
+}
+
 extern "C" int b200rl_gridnet_fwd(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
                                   const uint8_t* pick_mask, const void* actions, const void* pick_actions,
-                                  float* logp, float* entropy, b200rl_stream_t stream) {
+                                  float* logp, float* entropy, void* workspace, size_t workspace_bytes,
+                                  b200rl_stream_t stream) {
   using namespace b200rl;
   GridDev G;
   int rc = make_grid(d, logits, mask, pick_mask, actions, pick_actions, &G, "gridnet_fwd");
   if (rc) return rc;
   B200RL_REQUIRE(logp && entropy, "gridnet_fwd: null output");
   if (G.B == 0) return B200RL_OK;
+  rc = bind_workspace(&G, workspace, workspace_bytes, "gridnet_fwd");
+  if (rc) return rc;
   G.logp = logp, G.entropy = entropy;
   PpoDev P{};
   return launch_mode<kFwd>(G, P, d->nvec_host, d->logits_dtype, (cudaStream_t)stream);
@@ -798,14 +853,16 @@ extern "C" int b200rl_gridnet_fwd(const b200rl_gridnet_desc* d, const void* logi
 
 extern "C" int b200rl_gridnet_bwd(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
                                   const uint8_t* pick_mask, const void* actions, const void* pick_actions,
-                                  const float* dlogp, const float* dentropy, void* dlogits,
-                                  b200rl_stream_t stream) {
+                                  const float* dlogp, const float* dentropy, void* dlogits, void* workspace,
+                                  size_t workspace_bytes, b200rl_stream_t stream) {
   using namespace b200rl;
   GridDev G;
   int rc = make_grid(d, logits, mask, pick_mask, actions, pick_actions, &G, "gridnet_bwd");
   if (rc) return rc;
   B200RL_REQUIRE(dlogp && dentropy && dlogits, "gridnet_bwd: null pointer");
   if (G.B == 0) return B200RL_OK;
+  rc = bind_workspace(&G, workspace, workspace_bytes, "gridnet_bwd");
+  if (rc) return rc;
   G.dlogp_in = dlogp, G.dent_in = dentropy, G.dlogits = dlogits;
   PpoDev P{};
   return launch_mode<kBwd>(G, P, d->nvec_host, d->logits_dtype, (cudaStream_t)stream);
@@ -821,8 +878,13 @@ extern "C" int b200rl_ppo_gridnet_loss(const b200rl_gridnet_desc* d, const void*
   int rc = make_grid(d, logits, mask, pick_mask, actions, pick_actions, &G, "ppo_gridnet_loss");
   if (rc) return rc;
   B200RL_REQUIRE(dlogits != nullptr, "ppo_gridnet_loss: dlogits is null");
+  // workspace = [PPO partials | GridNet lists]; b200rl_ppo_gridnet_workspace_bytes() sizes both
+  const size_t ppo_bytes = b200rl_ppo_workspace_bytes(G.B, args ? args->V : 1);
+  B200RL_REQUIRE(workspace && workspace_bytes >= ppo_bytes, "ppo_gridnet_loss: workspace too small");
   PpoDev P;
-  rc = ppo_make_dev(args, G.B, workspace, workspace_bytes, &P);
+  rc = ppo_make_dev(args, G.B, workspace, ppo_bytes, &P);
+  if (rc) return rc;
+  rc = bind_workspace(&G, static_cast<uint8_t*>(workspace) + ppo_bytes, workspace_bytes - ppo_bytes, "ppo_gridnet_loss");
   if (rc) return rc;
   G.dlogits = dlogits, G.logp = logp_out, G.entropy = entropy_out;
   cudaStream_t s = (cudaStream_t)stream;

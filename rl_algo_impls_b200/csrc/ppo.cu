@@ -61,57 +61,18 @@ int ppo_launch_prepare(const PpoDev& P, cudaStream_t stream) {
   return check_launch("ppo_prepare");
 }
 
-// One block.  Column c of partials is summed over rows by the threads with tid % ns == c in a
-// fixed order, then the per-column thread sums are combined in a fixed order.
+// One block of 1024 threads over the per-sample (or per-block) partial rows; see ppo_finalize_block.
 __global__ void __launch_bounds__(1024) ppo_finalize_kernel(PpoDev P, long long rows, int ent_d) {
-  extern __shared__ double s_col[];  // [groups][ns]
-  const int ns = ppo_nstat(P.V);
-  const int groups = blockDim.x / ns;
-  const int tid = threadIdx.x;
-  const int c = tid % ns, g = tid / ns;
-  if (g < groups) {
-    double a = 0.0;
-    for (long long r = g; r < rows; r += groups) a += P.partials[r * ns + c];
-    s_col[g * ns + c] = a;
-  }
-  __syncthreads();
-  __shared__ double tot[kPolicyStats + 2 * B200RL_MAX_VALUE_HEADS];
-  if (tid < ns) {
-    double a = 0.0;
-    for (int k = 0; k < groups; ++k) a += s_col[k * ns + tid];
-    tot[tid] = a;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const double B = (double)P.B;
-    const float pi_coef = P.pi_coef_dev ? *P.pi_coef_dev : P.pi_coef;
-    const float pi_loss = (float)(-tot[0] / B);
-    const float ent_loss = (float)(-tot[1] / (B * ent_d));
-    float total = pi_coef * pi_loss + P.ent_coef * ent_loss;
-    float vsum = 0.f;
-    for (int v = 0; v < P.V; ++v) {
-      float vl = (float)(tot[kPolicyStats + v] / B);
-      if (P.halving) vl *= 0.5f;
-      P.stats_out[5 + v] = vl;
-      P.stats_out[5 + P.V + v] = (float)(tot[kPolicyStats + P.V + v] / B);
-      vsum += P.vf_coef[v] * vl;
-    }
-    total += vsum;
-    P.stats_out[0] = total * P.loss_scale;
-    P.stats_out[1] = pi_loss;
-    P.stats_out[2] = ent_loss;
-    P.stats_out[3] = (float)(tot[2] / B);
-    P.stats_out[4] = (float)(tot[3] / B);
-  }
+  extern __shared__ double s_scratch[];  // [nwarps][ns]
+  ppo_finalize_block(P, rows, ent_d, s_scratch);
 }
 
 int ppo_launch_finalize(const PpoDev& P, long long rows, int ent_d, cudaStream_t stream) {
   const int ns = ppo_nstat(P.V);
   int threads = 1024;
-  if (rows * ns < threads) threads = (int)(((rows * ns + 31) / 32) * 32);
-  if (threads < ns) threads = ((ns + 31) / 32) * 32;
-  const int groups = threads / ns;
-  ppo_finalize_kernel<<<1, threads, (size_t)groups * ns * sizeof(double), stream>>>(P, rows, ent_d);
+  if (rows < threads) threads = (int)(((rows + 31) / 32) * 32);
+  if (threads < ((ns + 31) / 32) * 32) threads = ((ns + 31) / 32) * 32;
+  ppo_finalize_kernel<<<1, threads, (size_t)(threads / 32) * ns * sizeof(double), stream>>>(P, rows, ent_d);
   return check_launch("ppo_finalize");
 }
 

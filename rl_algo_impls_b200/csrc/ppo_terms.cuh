@@ -139,6 +139,55 @@ __device__ __forceinline__ float2 ppo_value_terms(const PpoDev& P, long long i, 
   return make_float2(vl, clipped);
 }
 
+// partials [rows][4 + 2V] -> stats_out, by ONE block (any size that is a multiple of 32): thread t sums
+// rows t, t + blockDim, ... of every column, warps combine through `scratch` ([nwarps][ns] doubles of
+// shared memory), thread c < ns finishes column c.  Fixed order => deterministic.
+__device__ __forceinline__ void ppo_finalize_block(const PpoDev& P, long long rows, int ent_d, double* scratch) {
+  const int ns = ppo_nstat(P.V);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  __syncthreads();  // scratch may alias shared memory that was in use
+  for (int c = 0; c < ns; ++c) {
+    double a = 0.0;
+    for (long long r = tid; r < rows; r += blockDim.x) a += P.partials[r * ns + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      int lo = __double2loint(a), hi = __double2hiint(a);
+      lo = __shfl_xor_sync(0xffffffffu, lo, o), hi = __shfl_xor_sync(0xffffffffu, hi, o);
+      a += __hiloint2double(hi, lo);
+    }
+    if (lane == 0) scratch[warp * ns + c] = a;
+  }
+  __syncthreads();
+  __shared__ double tot[kPolicyStats + 2 * B200RL_MAX_VALUE_HEADS];
+  if (tid < ns) {
+    double a = 0.0;
+    for (int w = 0; w < nwarps; ++w) a += scratch[w * ns + tid];
+    tot[tid] = a;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double B = (double)P.B;
+    const float pi_coef = P.pi_coef_dev ? *P.pi_coef_dev : P.pi_coef;
+    const float pi_loss = (float)(-tot[0] / B);
+    const float ent_loss = (float)(-tot[1] / (B * ent_d));
+    float total = pi_coef * pi_loss + P.ent_coef * ent_loss;
+    float vsum = 0.f;
+    for (int v = 0; v < P.V; ++v) {
+      float vl = (float)(tot[kPolicyStats + v] / B);
+      if (P.halving) vl *= 0.5f;
+      P.stats_out[5 + v] = vl;
+      P.stats_out[5 + P.V + v] = (float)(tot[kPolicyStats + P.V + v] / B);
+      vsum += P.vf_coef[v] * vl;
+    }
+    total += vsum;
+    P.stats_out[0] = total * P.loss_scale;
+    P.stats_out[1] = pi_loss;
+    P.stats_out[2] = ent_loss;
+    P.stats_out[3] = (float)(tot[2] / B);
+    P.stats_out[4] = (float)(tot[3] / B);
+  }
+}
+
 // moments (f64 sum, sum of squares, count) -> norm (f32 mean, std + 1e-8); no-op for adv_mode 0.
 int ppo_launch_prepare(const PpoDev& P, cudaStream_t stream);
 

@@ -282,6 +282,7 @@ class PpoCall:
         new_values: torch.Tensor,
         moments: Optional[torch.Tensor] = None,
         need_dvalues: bool = True,
+        workspace_bytes: Optional[int] = None,
     ):
         B = old_logp.numel()
         dev = old_logp.device
@@ -305,7 +306,7 @@ class PpoCall:
         self._w = _f32_array(h.adv_weights) if h.adv_weights is not None else None
         self._vf = _f32_array(h.vf_coef)
         L = _lib.lib()
-        self.workspace = _workspace(L.b200rl_ppo_workspace_bytes(B, V), dev)
+        self.workspace = _workspace(workspace_bytes or L.b200rl_ppo_workspace_bytes(B, V), dev)
         a = PpoArgs()
         a.old_logp, a.adv, a.moments = old_logp.data_ptr(), adv.data_ptr(), _ptr(moments)
         a.adv_weights_host = self._w
@@ -557,9 +558,10 @@ def gridnet_fwd(spec, logits, mask, pick_mask, actions, pick_actions):
     g = _GridCall(spec, logits, mask, pick_mask, actions, pick_actions)
     logp = torch.empty(g.B, dtype=torch.float32, device=logits.device)
     ent = torch.empty(g.B, dtype=torch.float32, device=logits.device)
+    ws = _workspace(_lib.lib().b200rl_gridnet_workspace_bytes(g.B, g.HW, spec.n_pick), logits.device)
     rc = _call("b200rl_gridnet_fwd", 1, _lib.lib().b200rl_gridnet_fwd,
         C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), actions.data_ptr(),
-        _ptr(pick_actions), logp.data_ptr(), ent.data_ptr(), _stream(),
+        _ptr(pick_actions), logp.data_ptr(), ent.data_ptr(), ws.data_ptr(), ws.numel(), _stream(),
     )  # fmt: skip
     check(rc, "b200rl_gridnet_fwd")
     return logp, ent
@@ -570,9 +572,10 @@ def gridnet_bwd(spec, logits, mask, pick_mask, actions, pick_actions, dlogp, den
     dlogits = torch.empty_like(logits)
     dlogp = _cuda(dlogp.contiguous(), torch.float32, "dlogp")
     dent = _cuda(dent.contiguous(), torch.float32, "dentropy")
+    ws = _workspace(_lib.lib().b200rl_gridnet_workspace_bytes(g.B, g.HW, spec.n_pick), logits.device)
     rc = _call("b200rl_gridnet_bwd", 1, _lib.lib().b200rl_gridnet_bwd,
         C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), actions.data_ptr(),
-        _ptr(pick_actions), dlogp.data_ptr(), dent.data_ptr(), dlogits.data_ptr(), _stream(),
+        _ptr(pick_actions), dlogp.data_ptr(), dent.data_ptr(), dlogits.data_ptr(), ws.data_ptr(), ws.numel(), _stream(),
     )  # fmt: skip
     check(rc, "b200rl_gridnet_bwd")
     return dlogits
@@ -617,11 +620,13 @@ def ppo_gridnet_loss(
 ) -> LossOut:
     """One launch: masked log-prob/entropy forward, PPO loss, backward into dlogits / dvalues."""
     g = _GridCall(spec, logits, mask, pick_mask, actions, pick_actions)
-    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments)
+    V = new_values.numel() // max(g.B, 1)
+    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments,
+                   workspace_bytes=_lib.lib().b200rl_ppo_gridnet_workspace_bytes(g.B, g.HW, spec.n_pick, V))
     dlogits = torch.empty_like(logits)
     logp = torch.empty(g.B, dtype=torch.float32, device=logits.device) if want_logp else None
     ent = torch.empty(g.B, dtype=torch.float32, device=logits.device) if want_logp else None
-    rc = _call("b200rl_ppo_gridnet_loss", 2, _lib.lib().b200rl_ppo_gridnet_loss,
+    rc = _call("b200rl_ppo_gridnet_loss", 4, _lib.lib().b200rl_ppo_gridnet_loss,
         C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), actions.data_ptr(),
         _ptr(pick_actions), C.byref(call.args), dlogits.data_ptr(), _ptr(logp), _ptr(ent),
         call.workspace.data_ptr(), call.workspace.numel(), _stream(),
