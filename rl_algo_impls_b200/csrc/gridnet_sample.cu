@@ -9,13 +9,17 @@
 // launch geometry.  A row with no valid entry draws uniformly over all entries and contributes
 // log-prob 0, as the reference (probs = 1/n, normalised logits = 0).
 // One CTA per sample: rollouts have few samples (n_envs) and the pick categorical needs a
-// sample-wide argmax.
+// sample-wide argmax.  Like the fused loss, the kernel is mask driven: it zero-fills the sample's
+// action row, scans the mask bytes with 128-bit loads into a list of non-empty cells and only
+// those cells draw random numbers (a head with no valid entry returns action 0, log-prob 0).
 #include "categorical.cuh"
+#include "mask_scan.cuh"
 #include "philox.cuh"
 
 namespace b200rl {
 
 constexpr int kSampleBlock = 256;
+constexpr int kStashUnits = 1024;  // non-empty cells whose per-head log-probs are parked in shared memory
 
 struct SampleDev {
   const void* logits;
@@ -45,7 +49,8 @@ __device__ __forceinline__ void put_index(void* base, int dtype, long long i, lo
     default: static_cast<long long*>(base)[i] = v; break;
   }
 }
-__device__ __forceinline__ float gumbel(uint32_t bits) { return -logf(-logf(u01(bits))); }
+// -log(-log u): sampling noise only (never enters a reported log-prob), so the fast logarithms do
+__device__ __forceinline__ float gumbel(uint32_t bits) { return -__logf(-__logf(u01(bits))); }
 __device__ __forceinline__ uint64_t stream_id(uint64_t offset, int head, int kblock) {
   return (offset << 24) ^ ((uint64_t)head << 16) ^ (uint64_t)kblock;
 }
@@ -60,41 +65,94 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
   const uint64_t offset = G.offset + (G.offset_dev ? (uint64_t)*G.offset_dev : 0ull);
   float logp_acc = 0.f;
 
-  for (long long c = tid; c < G.HW; c += kSampleBlock) {
-    const long long cell = b * G.HW + c;
-    const long long xbase = cell * G.Sp;
-    const uint8_t* m = G.mask + cell * G.S;
+  // ---- non-empty cells of this sample -----------------------------------------------------------------
+  extern __shared__ uint16_t s_list[];  // [HW]
+  __shared__ uint32_t s_bitmap[kChunkCells / 32];
+  __shared__ int s_n, s_chunk_n;
+  const long long act_bytes = G.HW * G.A * (G.act_dtype == B200RL_U8 ? 1 : (G.act_dtype == B200RL_I32 ? 4 : 8));
+  zero_fill<kSampleBlock>(static_cast<uint8_t*>(G.actions_out) + b * act_bytes, (uint32_t)act_bytes);
+  if (tid == 0) s_n = 0;
+  for (long long c0 = 0; c0 < G.HW; c0 += kChunkCells) {
+    const int cells = (int)min((long long)kChunkCells, G.HW - c0);
+    if (tid < kChunkCells / 32) s_bitmap[tid] = 0u;
+    __syncthreads();
+    scan_mask<kSampleBlock>(G.mask + (b * G.HW + c0) * G.S, (uint32_t)cells * (uint32_t)G.S, (uint32_t)G.S, s_bitmap,
+                            RowPrefetch{nullptr, 0u});
+    __syncthreads();
+    compact_cells(s_bitmap, (cells + 31) >> 5, s_list + s_n, (int)c0, &s_chunk_n);
+    __syncthreads();
+    if (tid == 0) s_n += s_chunk_n;
+    __syncthreads();
+  }
+  const int n_unit = s_n;
+
+  // ---- one thread per (non-empty cell, head): Gumbel-max draw + log-prob in a single pass -----------------
+  // The pass keeps an online softmax (running max m, sum s of e^(x-m)) next to the running arg-max of
+  // x + gumbel, so the chosen entry's log-prob is x_best - (m + log s) without a second sweep.
+  __shared__ float s_lp[kStashUnits * B200RL_MAX_HEADS > 8192 ? 8192 : kStashUnits * B200RL_MAX_HEADS];
+  const int stash_units = 8192 / (G.A > 0 ? G.A : 1) < kStashUnits ? 8192 / G.A : kStashUnits;
+  auto sample_head = [&](long long cell, int h, float* lp_out) -> int {
+    const int off = G.off[h], n = G.nvec[h];
+    const long long xbase = cell * G.Sp + off;
+    const uint8_t* m = G.mask + cell * G.S + off;
+    int best = 0;
+    float best_score = -INFINITY, x_best = 0.f, mx = -INFINITY, sum = 0.f;
+    for (int k0 = 0; k0 < n; k0 += 4) {
+      uint32_t valid = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < n && m[k0 + j]) valid |= 1u << j;
+      if (!valid) continue;  // no random numbers spent on masked entries
+      const Philox4 r = philox4x32_10(G.seed, (uint64_t)cell, stream_id(offset, h, k0 >> 2));
+      const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!((valid >> j) & 1u)) continue;
+        const float x = logit_at(G, xbase + k0 + j);
+        const float score = x + gumbel(bits[j]);
+        if (score > best_score) best_score = score, best = k0 + j, x_best = x;
+        const float nm = fmaxf(mx, x);
+        sum = sum * __expf(mx - nm) + __expf(x - nm);  // exp(-inf) == 0 on the first valid entry
+        mx = nm;
+      }
+    }
+    *lp_out = sum > 0.f ? x_best - (mx + logf(sum)) : 0.f;  // a head with no valid entry: action 0, log-prob 0
+    return best;
+  };
+
+  const int n_items = (n_unit < stash_units ? n_unit : stash_units) * G.A;
+  for (int item = tid; item < n_items; item += kSampleBlock) {
+    const int u = item / G.A, h = item - u * G.A;
+    const long long cell = b * G.HW + s_list[u];
+    float lp;
+    const int a = sample_head(cell, h, &lp);
+    put_index(G.actions_out, G.act_dtype, cell * G.A + h, a);
+    s_lp[item] = lp;
+  }
+  __syncthreads();  // actions of the reference heads are written
+  for (int item = tid; item < n_items; item += kSampleBlock) {
+    const int u = item / G.A, h = item - u * G.A;
+    const int gr = G.gate_ref[h];
+    if (gr >= 0) {
+      const long long cell = b * G.HW + s_list[u];
+      long long a_ref;
+      switch (G.act_dtype) {
+        case B200RL_U8: a_ref = static_cast<const uint8_t*>(G.actions_out)[cell * G.A + gr]; break;
+        case B200RL_I32: a_ref = static_cast<const int32_t*>(G.actions_out)[cell * G.A + gr]; break;
+        default: a_ref = static_cast<const long long*>(G.actions_out)[cell * G.A + gr]; break;
+      }
+      if (a_ref != G.gate_val[h]) continue;
+    }
+    logp_acc += s_lp[item];
+  }
+  // cells beyond the shared-memory stash (dense masks on big maps): one thread walks all heads of a cell
+  for (int u = stash_units + tid; u < n_unit; u += kSampleBlock) {
+    const long long cell = b * G.HW + s_list[u];
     int chosen[B200RL_MAX_HEADS];
     float lp[B200RL_MAX_HEADS];
     for (int h = 0; h < G.A; ++h) {
-      const int off = G.off[h], n = G.nvec[h];
-      bool any = false;
-      for (int k = 0; k < n; ++k) any |= (m[off + k] != 0);
-      if (!any) {  // no unit / nothing to choose: action 0, log-prob 0, no random numbers spent
-        chosen[h] = 0, lp[h] = 0.f;
-        put_index(G.actions_out, G.act_dtype, cell * G.A + h, 0);
-        continue;
-      }
-      int best = 0;
-      float best_score = -INFINITY;
-      for (int k0 = 0; k0 < n; k0 += 4) {
-        const Philox4 r = philox4x32_10(G.seed, (uint64_t)cell, stream_id(offset, h, k0 >> 2));
-        const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
-        for (int j = 0; j < 4 && k0 + j < n; ++j) {
-          const int k = k0 + j;
-          if (any && !m[off + k]) continue;
-          const float score = (any ? logit_at(G, xbase + off + k) : 0.f) + gumbel(bits[j]);
-          if (score > best_score) best_score = score, best = k;
-        }
-      }
-      chosen[h] = best;
-      lp[h] = 0.f;
-      if (any) {
-        CatRow row = cat_forward([&](int k) { return logit_at(G, xbase + off + k); },
-                                 [&](int k) { return m[off + k] != 0; }, n, best);
-        lp[h] = row.logp;
-      }
-      put_index(G.actions_out, G.act_dtype, cell * G.A + h, best);
+      chosen[h] = sample_head(cell, h, &lp[h]);
+      put_index(G.actions_out, G.act_dtype, cell * G.A + h, chosen[h]);
     }
     for (int h = 0; h < G.A; ++h) {
       const int gr = G.gate_ref[h];
@@ -210,6 +268,7 @@ extern "C" int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* l
   G.seed = seed, G.offset = offset, G.offset_dev = reinterpret_cast<const long long*>(offset_dev);
   G.actions_out = actions_out, G.act_dtype = d->act_dtype, G.pick_out = pick_actions_out, G.pick_dtype = d->pick_dtype;
   G.logp = logp;
-  gridnet_sample_kernel<<<(unsigned)d->B, kSampleBlock, 0, (cudaStream_t)stream>>>(G);
+  B200RL_UNSUPPORTED(d->HW > 16384, "gridnet_sample: HW=%lld cells exceeds 16384", (long long)d->HW);
+  gridnet_sample_kernel<<<(unsigned)d->B, kSampleBlock, (size_t)d->HW * sizeof(uint16_t), (cudaStream_t)stream>>>(G);
   return check_launch("gridnet_sample");
 }

@@ -1,0 +1,132 @@
+// Mask-scan building blocks shared by the fused GridNet loss (gridnet.cu) and the rollout-time
+// sampler (gridnet_sample.cu): 128-bit zero fill, 128-bit scan of the action-mask bytes into a
+// shared bitmap of non-empty cells, and the bitmap -> ascending cell list compaction.
+#pragma once
+#include "common.cuh"
+
+namespace b200rl {
+
+constexpr int kChunkCells = 256;  // cells per scan chunk (one bitmap of 8 words)
+
+// ---- zero fill / mask scan -----------------------------------------------------------------------
+template <int BLOCK>
+__device__ __forceinline__ void zero_fill(uint8_t* dst, uint32_t bytes) {
+  const uint32_t tid = threadIdx.x;
+  uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+  if (head > bytes) head = bytes;
+  if (tid < head) dst[tid] = 0;
+  uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+  const uint32_t n4 = (bytes - head) >> 4;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t i = tid;
+  for (; i + 3u * BLOCK < n4; i += 4u * BLOCK) {
+    d4[i] = z, d4[i + BLOCK] = z, d4[i + 2u * BLOCK] = z, d4[i + 3u * BLOCK] = z;
+  }
+  for (; i < n4; i += BLOCK) d4[i] = z;
+  const uint32_t done = head + (n4 << 4);
+  if (tid < bytes - done) dst[done + tid] = 0;
+}
+
+// Row prefetch context: the logits row of a flagged cell is wanted a few microseconds from now.
+struct RowPrefetch {
+  const uint8_t* logits;  // first logit of the CTA's first cell
+  uint32_t row_bytes;     // Sp * sizeof(LT)
+};
+
+__device__ __forceinline__ void flag_cell(uint32_t* bitmap, uint32_t cell, const RowPrefetch& pf) {
+  const uint32_t bit = 1u << (cell & 31);
+  const uint32_t old = atomicOr(&bitmap[cell >> 5], bit);
+  if (!(old & bit) && pf.logits != nullptr) {  // first flag of this cell: pull its logits row towards L2
+    const uint8_t* row = pf.logits + (size_t)cell * pf.row_bytes;
+    for (uint32_t o = 0; o < pf.row_bytes + 127u; o += 128u) prefetch_l2(row + min(o, pf.row_bytes - 1u));
+  }
+}
+
+// A 16-byte word of the mask chunk with at least one non-zero byte: flag the cell(s) it covers.
+// Rows are S bytes, so for S >= 16 a word touches at most two cells; two 32-bit divisions and a
+// byte-boundary split decide which.  (Chunk sizes are < 2^31 bytes: cells <= 4096, S <= 65535.)
+static __device__ __noinline__ void flag_word(uint32_t* bitmap, uint32_t base, const uint4& w, uint32_t S, const RowPrefetch& pf) {
+  const uint32_t c0 = base / S, c1 = (base + 15u) / S;
+  if (c0 == c1) {
+    flag_cell(bitmap, c0, pf);
+    return;
+  }
+  if (S >= 16u) {
+    const uint32_t k = c1 * S - base;  // bytes [0, k) belong to c0, [k, 16) to c1; 1 <= k <= 15
+    const unsigned long long lo = (unsigned long long)w.x | ((unsigned long long)w.y << 32);
+    const unsigned long long hi = (unsigned long long)w.z | ((unsigned long long)w.w << 32);
+    unsigned long long first, second;
+    if (k < 8u) {
+      first = lo & ((1ull << (8u * k)) - 1ull);
+      second = (lo >> (8u * k)) | hi;
+    } else {
+      first = lo | (k == 8u ? 0ull : (hi & ((1ull << (8u * (k - 8u))) - 1ull)));
+      second = hi >> (8u * (k - 8u));
+    }
+    if (first) flag_cell(bitmap, c0, pf);
+    if (second) flag_cell(bitmap, c1, pf);
+    return;
+  }
+  const uint32_t word[4] = {w.x, w.y, w.z, w.w};  // narrow rows: several cells per word
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q)
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r)
+      if ((word[q] >> (8 * r)) & 0xffu) flag_cell(bitmap, (base + 4u * q + r) / S, pf);
+}
+
+// flags every cell of [mask, mask + bytes) that has a non-zero byte
+template <int BLOCK>
+__device__ __forceinline__ void scan_mask(const uint8_t* mask, uint32_t bytes, uint32_t S, uint32_t* bitmap,
+                                          const RowPrefetch& pf) {
+  const uint32_t tid = threadIdx.x;
+  uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(mask) & 15u)) & 15u;
+  if (head > bytes) head = bytes;
+  if (tid < head && mask[tid]) flag_cell(bitmap, tid / S, pf);
+  const uint4* m4 = reinterpret_cast<const uint4*>(mask + head);
+  const uint32_t n4 = (bytes - head) >> 4;
+  constexpr uint32_t kUnroll = 4;
+  for (uint32_t i0 = tid; i0 < n4; i0 += BLOCK * kUnroll) {
+    uint4 w[kUnroll];
+#pragma unroll
+    for (uint32_t u = 0; u < kUnroll; ++u) {
+      const uint32_t i = i0 + u * BLOCK;
+      // plain read-only loads (allocate in L1): the unit cells re-read their own mask bytes
+      w[u] = i < n4 ? __ldg(m4 + i) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (uint32_t u = 0; u < kUnroll; ++u)
+      if ((w[u].x | w[u].y | w[u].z | w[u].w) != 0u) flag_word(bitmap, head + ((i0 + u * BLOCK) << 4), w[u], S, pf);
+  }
+  const uint32_t done = head + (n4 << 4);
+  if (tid < bytes - done && mask[done + tid]) flag_cell(bitmap, (done + tid) / S, pf);
+}
+
+// warp 0: bitmap -> ascending list of flagged cells (ids offset by `base`); count through *out_count
+__device__ __forceinline__ void compact_cells(const uint32_t* bitmap, int words, uint16_t* list, int base_id,
+                                              int* out_count) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  int base = 0;
+  for (int w0 = 0; w0 < words; w0 += 32) {
+    const int w = w0 + lane;
+    uint32_t bits = w < words ? bitmap[w] : 0u;
+    const int cnt = __popc(bits);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int pos = base + incl - cnt;
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      list[pos++] = (uint16_t)(base_id + w * 32 + b);
+    }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) *out_count = base;
+}
+
+}  // namespace b200rl
