@@ -115,7 +115,10 @@ int b200rl_gather_rows(const void* const* src_host, void* const* dst_host, const
  *   kl_cutoff < 0 disables the cut-off; pi_coef_state is a device float (1 or 0) that the
  *   scalar kernel reads, zeroes when approx_kl > kl_cutoff and leaves sticky (ppo.py:279,354).
  * stats_out (device, f32): [0] loss [1] pi_loss [2] entropy_loss [3] approx_kl [4] clipped_frac
- *   [5 .. 5+V) v_loss per head (after halving) [5+V .. 5+2V) val_clipped_frac.
+ *   [5 .. 5+V) v_loss per head (after halving) [5+V .. 5+2V) val_clipped_frac [5+2V] teacher_kl_loss.
+ * Teacher-KL term (loss/teacher_kl_loss.py:35-50, ppo/ppo.py:363-371): when teacher_logp is non-NULL,
+ *   loss += teacher_kl_coef * mean(w * f(teacher_logp - new_logp)), f(d) = (e^d - 1) - d (unbiased) or
+ *   d^2 / 2, w = the PPO ratio (NOT detached, as the reference) when importance sampling is on.
  */
 typedef struct b200rl_ppo_args {
   const float* old_logp;
@@ -137,9 +140,13 @@ typedef struct b200rl_ppo_args {
   int vf_halving;
   float loss_scale;
   float* stats_out;
+  const float* teacher_logp; /* [B] or NULL */
+  float teacher_kl_coef;
+  int teacher_unbiased;   /* loss/teacher_kl_loss.py:14 `unbiased` */
+  int teacher_importance; /* ppo.py:139 teacher_loss_importance_sampling */
 } b200rl_ppo_args;
 
-#define B200RL_PPO_NSTATS(V) (5 + 2 * (V))
+#define B200RL_PPO_NSTATS(V) (6 + 2 * (V))
 
 /* Per-sample stage alone (distribution-level path): given new_logp [B] and entropy
  * [B, ent_d] produced by any differentiable head, writes dlogp [B], dentropy [B, ent_d],

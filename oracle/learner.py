@@ -43,6 +43,9 @@ class Hyper:
     kl_cutoff: Optional[float] = None
     normalize_advantages_after_scaling: bool = False
     learning_rate: float = 3e-4
+    teacher_kl_loss_coef: Optional[float] = None
+    teacher_unbiased: bool = True
+    teacher_loss_importance_sampling: bool = True
 
 
 class OraclePolicy:
@@ -138,7 +141,8 @@ def _take(a, idx):
     return a[idx]
 
 
-def learn_epoch(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict, hp: Hyper) -> dict:
+def learn_epoch(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict, hp: Hyper,
+                teacher: Optional[OraclePolicy] = None) -> dict:
     """vec_rollout.py:38-175 + ppo.py:258-447 on a collected rollout ``ro`` (numpy [T, N, ...] arrays)."""
     adv = gae_advantages(ro["rewards"], ro["values"], ro["episode_starts"], ro["next_episode_starts"],
                          ro["next_values"], hp.gamma, hp.gae_lambda)
@@ -146,6 +150,14 @@ def learn_epoch(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict
     b = dict(obs=_flat(ro["obs"]), logprobs=_flat(ro["logprobs"]), actions=_flat(ro["actions"]),
              masks=_flat(ro["masks"]), values=_flat(ro["values"]), adv=_flat(adv), returns=_flat(ret))
     total = b["logprobs"].shape[0]
+    teacher_logp = None
+    if teacher is not None:  # TeacherKLLoss.add_to_batch over num_envs-sized slices (ppo.py:259-262, vec_rollout.py:155-164)
+        n_envs = np.asarray(ro["rewards"]).shape[1]
+        with torch.no_grad():
+            teacher_logp = torch.cat([
+                teacher.forward(b["obs"][i:i + n_envs], _take(b["actions"], slice(i, i + n_envs)),
+                                _take(b["masks"], slice(i, i + n_envs)))[0]
+                for i in range(0, total, n_envs)])
     n_mb = total // hp.batch_size + (1 if total % hp.batch_size else 0)
     w = torch.tensor(np.asarray(hp.multi_reward_weights), dtype=torch.float32) if hp.multi_reward_weights is not None else None
     vf_coef = torch.tensor(np.asarray(hp.vf_coef), dtype=torch.float32)
@@ -171,7 +183,10 @@ def learn_epoch(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict
             parts = ppo_loss(logp, ent, v, b["logprobs"][idx], mb_adv, b["values"][idx], b["returns"][idx],
                              clip_range=hp.clip_range, clip_range_vf=hp.clip_range_vf, ent_coef=hp.ent_coef,
                              vf_coef=vf_coef, ppo2_vf_coef_halving=hp.ppo2_vf_coef_halving, pi_coef=pi_coef,
-                             kl_cutoff=hp.kl_cutoff, loss_divisor=n_mb if hp.gradient_accumulation else None)
+                             kl_cutoff=hp.kl_cutoff, loss_divisor=n_mb if hp.gradient_accumulation else None,
+                             teacher_logprobs=teacher_logp[idx] if teacher_logp is not None else None,
+                             teacher_kl_loss_coef=hp.teacher_kl_loss_coef, teacher_unbiased=hp.teacher_unbiased,
+                             teacher_loss_importance_sampling=hp.teacher_loss_importance_sampling)
             pi_coef = parts.pi_coef
             parts.loss.backward()
             if not hp.gradient_accumulation:
@@ -179,7 +194,8 @@ def learn_epoch(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict
             step_stats.append(dict(loss=parts.loss.item(), pi_loss=parts.pi_loss.item(),
                                    v_loss=parts.v_loss.detach().numpy().copy(), entropy_loss=parts.entropy_loss.item(),
                                    approx_kl=parts.approx_kl, clipped_frac=parts.clipped_frac,
-                                   val_clipped_frac=np.asarray(parts.val_clipped_frac)))
+                                   val_clipped_frac=np.asarray(parts.val_clipped_frac),
+                                   **({"teacher_kl_loss": parts.teacher_kl_loss.item()} if parts.teacher_kl_loss is not None else {})))
         if hp.gradient_accumulation:
             grad_norms.append(optimizer_step())
     y_true, y_pred = flatten_time_major(ret), flatten_time_major(ro["values"])

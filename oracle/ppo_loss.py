@@ -47,6 +47,7 @@ class LossParts:
     val_clipped_frac: np.ndarray
     pi_coef: float
     ratio: torch.Tensor = field(repr=False, default=None)
+    teacher_kl_loss: Optional[torch.Tensor] = None
 
 
 def ppo_loss(
@@ -68,6 +69,10 @@ def ppo_loss(
     kl_cutoff: Optional[float] = None,
     loss_divisor: Optional[int] = None,  # num_minibatches under gradient accumulation
     vf_loss_fn=F.mse_loss,
+    teacher_logprobs: Optional[torch.Tensor] = None,  # loss/teacher_kl_loss.py:35-50 + ppo.py:363-371
+    teacher_kl_loss_coef: Optional[float] = None,
+    teacher_unbiased: bool = True,
+    teacher_loss_importance_sampling: bool = True,
 ) -> LossParts:
     logratio = new_logprobs - old_logprobs
     ratio = torch.exp(logratio)
@@ -97,6 +102,14 @@ def ppo_loss(
         pi_coef = 0
 
     loss = pi_coef * pi_loss + ent_coef * entropy_loss + (vf_coef * v_loss).sum()
+    teacher_kl_loss = None
+    if teacher_kl_loss_coef:
+        t_logratio = teacher_logprobs - new_logprobs
+        t_loss = (torch.exp(t_logratio) - 1) - t_logratio if teacher_unbiased else 0.5 * t_logratio**2
+        if teacher_loss_importance_sampling:
+            t_loss = t_loss * ratio  # not detached, as the reference
+        teacher_kl_loss = t_loss.mean()
+        loss = loss + teacher_kl_loss_coef * teacher_kl_loss
     if loss_divisor is not None:
         loss = loss / loss_divisor
 
@@ -106,6 +119,8 @@ def ppo_loss(
             val_clipped_frac = ((new_values - old_values).abs() > clip_range_vf).float().mean(0).cpu().numpy()
         else:
             val_clipped_frac = np.zeros(v_loss.shape)
-    return LossParts(
+    parts = LossParts(
         loss, pi_loss, v_loss, entropy_loss, approx_kl, clipped_frac, val_clipped_frac, pi_coef, ratio.detach()
     )
+    parts.teacher_kl_loss = teacher_kl_loss
+    return parts

@@ -45,6 +45,10 @@ class PpoArgs(C.Structure):
         ("vf_halving", C.c_int),
         ("loss_scale", C.c_float),
         ("stats_out", C.c_void_p),
+        ("teacher_logp", C.c_void_p),
+        ("teacher_kl_coef", C.c_float),
+        ("teacher_unbiased", C.c_int),
+        ("teacher_importance", C.c_int),
     ]
 
 

@@ -55,10 +55,10 @@ __global__ void __launch_bounds__(kCatBlock) cat_bwd_kernel(const CatParams p) {
 
 template <typename ActT>
 __global__ void __launch_bounds__(kCatBlock) cat_ppo_kernel(const CatParams p, const PpoDev P) {
-  __shared__ double scratch[4 * 32];
+  __shared__ double scratch[5 * 32];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int ns = ppo_nstat(P.V);
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (i < p.R) {
     const float* x = p.logits + i * p.n;
     const uint8_t* m = p.mask ? p.mask + i * p.n : nullptr;
@@ -70,12 +70,12 @@ __global__ void __launch_bounds__(kCatBlock) cat_ppo_kernel(const CatParams p, c
       p.dlogits[i * p.n + k] = cat_grad(x[k], m ? m[k] != 0 : true, k == a, r, t.dlogp, de);
     if (p.logp) p.logp[i] = r.logp;
     if (p.entropy) p.entropy[i] = r.entropy;
-    acc[0] = t.surrogate, acc[1] = r.entropy, acc[2] = t.kl, acc[3] = t.clipped;
+    acc[0] = t.surrogate, acc[1] = r.entropy, acc[2] = t.kl, acc[3] = t.clipped, acc[4] = t.teacher;
   }
-  block_sum<double, 4>(acc, scratch);
+  block_sum<double, 5>(acc, scratch);
   double* row = P.partials + (long long)blockIdx.x * ns;
   if (threadIdx.x == 0)
-    for (int k = 0; k < 4; ++k) row[k] = acc[k];
+    for (int k = 0; k < 5; ++k) row[k] = acc[k];
   for (int v = 0; v < P.V; ++v) {
     double va[2] = {0.0, 0.0};
     if (i < p.R) {

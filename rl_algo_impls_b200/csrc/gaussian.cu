@@ -45,10 +45,10 @@ __global__ void __launch_bounds__(kGaussBlock) gauss_fwd_kernel(const GaussParam
 }
 
 __global__ void __launch_bounds__(kGaussBlock) gauss_ppo_kernel(const GaussParams p, const PpoDev P) {
-  __shared__ double scratch[4 * 32];
+  __shared__ double scratch[5 * 32];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int ns = ppo_nstat(P.V);
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   float dlogp = 0.f;
   const bool live = i < p.B;
   if (live) {
@@ -57,13 +57,13 @@ __global__ void __launch_bounds__(kGaussBlock) gauss_ppo_kernel(const GaussParam
     dlogp = t.dlogp;
     float ent_sum = 0.f;
     for (int d = 0; d < p.D; ++d) ent_sum += 0.5f + kHalfLog2Pi + logf(expf(p.log_std[d]));
-    acc[0] = t.surrogate, acc[1] = ent_sum, acc[2] = t.kl, acc[3] = t.clipped;
+    acc[0] = t.surrogate, acc[1] = ent_sum, acc[2] = t.kl, acc[3] = t.clipped, acc[4] = t.teacher;
     if (p.logp) p.logp[i] = lp;
   }
-  block_sum<double, 4>(acc, scratch);
+  block_sum<double, 5>(acc, scratch);
   double* row = P.partials + (long long)blockIdx.x * ns;
   if (threadIdx.x == 0)
-    for (int k = 0; k < 4; ++k) row[k] = acc[k];
+    for (int k = 0; k < 5; ++k) row[k] = acc[k];
   for (int v = 0; v < P.V; ++v) {
     double va[2] = {0.0, 0.0};
     if (live) {

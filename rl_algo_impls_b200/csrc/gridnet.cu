@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
       PolicyTerms t = ppo_policy_terms(P, b, tot_logp);
       s_bcast[0] = t.dlogp, s_bcast[1] = ppo_dentropy(P, 1);
       double* row = P.partials + b * ppo_nstat(P.V);
-      row[0] = t.surrogate, row[1] = tot_ent, row[2] = t.kl, row[3] = t.clipped;
+      row[0] = t.surrogate, row[1] = tot_ent, row[2] = t.kl, row[3] = t.clipped, row[4] = t.teacher;
       if (G.logp) G.logp[b] = (float)tot_logp;
       if (G.entropy) G.entropy[b] = (float)tot_ent;
     }

@@ -32,6 +32,8 @@ int ppo_make_dev(const b200rl_ppo_args* a, long long B, void* workspace, size_t 
   for (int v = 0; v < P.V; ++v) P.vf_coef[v] = a->vf_coef_host[v];
   P.ent_coef = a->ent_coef, P.pi_coef = a->pi_coef, P.pi_coef_dev = nullptr;
   P.halving = a->vf_halving, P.loss_scale = a->loss_scale;
+  P.teacher_logp = a->teacher_logp, P.teacher_coef = a->teacher_kl_coef;
+  P.teacher_unbiased = a->teacher_unbiased, P.teacher_importance = a->teacher_importance;
   P.B = B;
   P.partials = static_cast<double*>(workspace);
   // the last 2 * MAX_VALUE_HEADS floats of the workspace hold the derived (mean, denominator) pairs
@@ -103,10 +105,10 @@ __global__ void ppo_kl_decide_kernel(PpoDev P, int blocks, float kl_cutoff, floa
 
 __global__ void __launch_bounds__(kScalarBlock)
     ppo_scalar_kernel(PpoDev P, const float* new_logp, const float* entropy, int ent_d, float* dlogp, float* dentropy) {
-  __shared__ double scratch[4 * 32];
+  __shared__ double scratch[5 * 32];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int ns = ppo_nstat(P.V);
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (i < P.B) {
     PolicyTerms t = ppo_policy_terms(P, i, new_logp[i]);
     dlogp[i] = t.dlogp;
@@ -116,12 +118,12 @@ __global__ void __launch_bounds__(kScalarBlock)
       es += entropy[i * ent_d + d];
       dentropy[i * ent_d + d] = de;
     }
-    acc[0] = t.surrogate, acc[1] = es, acc[2] = t.kl, acc[3] = t.clipped;
+    acc[0] = t.surrogate, acc[1] = es, acc[2] = t.kl, acc[3] = t.clipped, acc[4] = t.teacher;
   }
-  block_sum<double, 4>(acc, scratch);
+  block_sum<double, 5>(acc, scratch);
   double* row = P.partials + (long long)blockIdx.x * ns;
   if (threadIdx.x == 0) {
-    for (int k = 0; k < 4; ++k) row[k] = acc[k];
+    for (int k = 0; k < 5; ++k) row[k] = acc[k];
   }
   for (int v = 0; v < P.V; ++v) {
     double va[2] = {0.0, 0.0};
@@ -141,7 +143,7 @@ extern "C" size_t b200rl_ppo_workspace_bytes(int64_t B, int64_t V) {
   if (V < 1) V = 1;
   // one row of partial stats per sample (grid-per-sample kernels) + per-block rows for the
   // Gaussian log_std gradient (<= 64 action dims)
-  return (size_t)B * (size_t)(4 + 2 * V) * sizeof(double) + ((size_t)B / 128 + 2) * 64 * sizeof(double) +
+  return (size_t)B * (size_t)(5 + 2 * V) * sizeof(double) + ((size_t)B / 128 + 2) * 64 * sizeof(double) +
          2 * B200RL_MAX_VALUE_HEADS * sizeof(float);
 }
 

@@ -11,7 +11,7 @@
 
 namespace b200rl {
 
-constexpr int kPolicyStats = 4;  // surrogate sum, entropy sum, kl sum, clipped count
+constexpr int kPolicyStats = 5;  // surrogate sum, entropy sum, kl sum, clipped count, teacher-KL sum
 
 struct PpoDev {
   const float* old_logp;
@@ -36,6 +36,9 @@ struct PpoDev {
   const float* pi_coef_dev;  // when non-null, overrides pi_coef (KL cut-off state on the device)
   int halving;
   float loss_scale;
+  const float* teacher_logp;  // null: no teacher-KL term
+  float teacher_coef;
+  int teacher_unbiased, teacher_importance;
   long long B;
   const float* norm;  // [2 * Vm] (mean, std + 1e-8) derived from `moments` by ppo_launch_prepare
   double* partials;  // [rows][4 + 2V]
@@ -77,6 +80,7 @@ struct PolicyTerms {
   float surrogate;  // min(ratio*A, clamp(ratio)*A)
   float kl;         // (ratio - 1) - logratio
   float clipped;    // |ratio - 1| > clip
+  float teacher;    // w * f(teacher_logp - new_logp), 0 without a teacher
 };
 
 // new_logp arrives in float64 when the caller summed it that way (GridNet: hundreds of per-cell
@@ -104,6 +108,25 @@ __device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long lo
   t.dlogp = -(pi_coef * P.loss_scale / (float)P.B) * dsurr * ratio;
   t.kl = (ratio - 1.f) - logratio;
   t.clipped = fabsf(ratio - 1.f) > P.clip ? 1.f : 0.f;
+  t.teacher = 0.f;
+  if (P.teacher_logp) {  // loss/teacher_kl_loss.py:35-50; the weight (ratio) carries gradient like in the reference
+    const float d = (float)((double)P.teacher_logp[i] - new_logp);
+    float f, df;  // f(d) and d f / d new_logp
+    if (P.teacher_unbiased) {
+      const float e = expf(d);
+      f = (e - 1.f) - d, df = 1.f - e;
+    } else {
+      f = 0.5f * d * d, df = -d;
+    }
+    const float scale = P.teacher_coef * P.loss_scale / (float)P.B;
+    if (P.teacher_importance) {
+      t.teacher = ratio * f;
+      t.dlogp += scale * ratio * (f + df);
+    } else {
+      t.teacher = f;
+      t.dlogp += scale * df;
+    }
+  }
   return t;
 }
 
@@ -180,6 +203,9 @@ __device__ __forceinline__ void ppo_finalize_block(const PpoDev& P, long long ro
       vsum += P.vf_coef[v] * vl;
     }
     total += vsum;
+    const float teacher_loss = (float)(tot[4] / B);
+    if (P.teacher_logp) total += P.teacher_coef * teacher_loss;
+    P.stats_out[5 + 2 * P.V] = teacher_loss;
     P.stats_out[0] = total * P.loss_scale;
     P.stats_out[1] = pi_loss;
     P.stats_out[2] = ent_loss;

@@ -267,6 +267,9 @@ class PpoHyper:
     loss_scale: float = 1.0
     adv_mode: int = ADV_NORMALIZE
     adv_weights: Optional[Sequence[float]] = None
+    teacher_kl_coef: float = 0.0  # > 0 with teacher_logp: adds the teacher-KL term (loss/teacher_kl_loss.py)
+    teacher_unbiased: bool = True
+    teacher_importance: bool = True
 
 
 class PpoCall:
@@ -283,6 +286,7 @@ class PpoCall:
         moments: Optional[torch.Tensor] = None,
         need_dvalues: bool = True,
         workspace_bytes: Optional[int] = None,
+        teacher_logp: Optional[torch.Tensor] = None,
     ):
         B = old_logp.numel()
         dev = old_logp.device
@@ -302,7 +306,7 @@ class PpoCall:
         self.B, self.V = B, V
         self.moments = moments
         self.dvalues = torch.empty_like(new_values) if need_dvalues else None
-        self.stats = torch.empty(5 + 2 * V, dtype=torch.float32, device=dev)
+        self.stats = torch.empty(6 + 2 * V, dtype=torch.float32, device=dev)
         self._w = _f32_array(h.adv_weights) if h.adv_weights is not None else None
         self._vf = _f32_array(h.vf_coef)
         L = _lib.lib()
@@ -320,8 +324,15 @@ class PpoCall:
         a.ent_coef, a.pi_coef = float(h.ent_coef), float(h.pi_coef)
         a.vf_halving, a.loss_scale = int(bool(h.vf_halving)), float(h.loss_scale)
         a.stats_out = self.stats.data_ptr()
+        if teacher_logp is not None and h.teacher_kl_coef:
+            _cuda(teacher_logp, torch.float32, "teacher_logp")
+            if teacher_logp.numel() != B:
+                raise ValueError("teacher_logp must be [B]")
+            a.teacher_logp = teacher_logp.data_ptr()
+            a.teacher_kl_coef = float(h.teacher_kl_coef)
+            a.teacher_unbiased, a.teacher_importance = int(h.teacher_unbiased), int(h.teacher_importance)
         self.args = a
-        self._keep = (old_logp, adv, old_values, returns, new_values, moments)
+        self._keep = (old_logp, adv, old_values, returns, new_values, moments, teacher_logp)
 
 
 @dataclass
@@ -347,12 +358,13 @@ def ppo_scalar_loss(
     moments: Optional[torch.Tensor] = None,
     kl_cutoff: Optional[float] = None,
     pi_coef_state: Optional[torch.Tensor] = None,
+    teacher_logp: Optional[torch.Tensor] = None,
 ) -> LossOut:
     """Per-sample stage for heads that produced (new_logp [B], entropy [B] or [B, D]) elsewhere."""
     _cuda(new_logp, torch.float32, "new_logp"), _cuda(entropy, torch.float32, "entropy")
     B = new_logp.numel()
     ent_d = entropy.numel() // B
-    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments)
+    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments, teacher_logp=teacher_logp)
     dlogp, dent = torch.empty_like(new_logp), torch.empty_like(entropy)
     if kl_cutoff is not None and pi_coef_state is None:
         raise ValueError("kl_cutoff needs a device pi_coef_state tensor")
@@ -376,12 +388,13 @@ def ppo_categorical_loss(
     returns: torch.Tensor,
     new_values: torch.Tensor,
     moments: Optional[torch.Tensor] = None,
+    teacher_logp: Optional[torch.Tensor] = None,
 ) -> LossOut:
     _cuda(logits, torch.float32, "logits")
     B, n = logits.shape
     m = _as_u8(mask, "mask")
     _cuda(actions, None, "actions")
-    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments)
+    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments, teacher_logp=teacher_logp)
     dlogits = torch.empty_like(logits)
     rc = _call("b200rl_ppo_categorical_loss_f32", 2, _lib.lib().b200rl_ppo_categorical_loss_f32,
         logits.data_ptr(), _ptr(m), actions.data_ptr(), _INDEX_DTYPES[actions.dtype], B, n, C.byref(call.args),
@@ -402,11 +415,12 @@ def ppo_gaussian_loss(
     returns: torch.Tensor,
     new_values: torch.Tensor,
     moments: Optional[torch.Tensor] = None,
+    teacher_logp: Optional[torch.Tensor] = None,
 ) -> LossOut:
     for name, t in (("mu", mu), ("log_std", log_std), ("actions", actions)):
         _cuda(t, torch.float32, name)
     B, D = mu.shape
-    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments)
+    call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments, teacher_logp=teacher_logp)
     dmu, dls = torch.empty_like(mu), torch.empty_like(log_std)
     rc = _call("b200rl_ppo_gaussian_loss_f32", 3, _lib.lib().b200rl_ppo_gaussian_loss_f32,
         mu.data_ptr(), log_std.data_ptr(), actions.data_ptr(), B, D, C.byref(call.args), dmu.data_ptr(),
@@ -617,12 +631,14 @@ def ppo_gridnet_loss(
     new_values: torch.Tensor,
     moments: Optional[torch.Tensor] = None,
     want_logp: bool = False,
+    teacher_logp: Optional[torch.Tensor] = None,
 ) -> LossOut:
     """One launch: masked log-prob/entropy forward, PPO loss, backward into dlogits / dvalues."""
     g = _GridCall(spec, logits, mask, pick_mask, actions, pick_actions)
     V = new_values.numel() // max(g.B, 1)
     call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments,
-                   workspace_bytes=_lib.lib().b200rl_ppo_gridnet_workspace_bytes(g.B, g.HW, spec.n_pick, V))
+                   workspace_bytes=_lib.lib().b200rl_ppo_gridnet_workspace_bytes(g.B, g.HW, spec.n_pick, V),
+                   teacher_logp=teacher_logp)
     dlogits = torch.empty_like(logits)
     logp = torch.empty(g.B, dtype=torch.float32, device=logits.device) if want_logp else None
     ent = torch.empty(g.B, dtype=torch.float32, device=logits.device) if want_logp else None

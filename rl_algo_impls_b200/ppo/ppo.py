@@ -294,8 +294,6 @@ class PPO(Algorithm):
         self.autocast_loss = autocast_loss
         if vf_loss_fn != "mse_loss":
             raise NotImplementedError(f"vf_loss_fn={vf_loss_fn!r}: the fused kernels implement the reference default, mse_loss")
-        if teacher_kl_loss_coef or teacher_kl_loss_fn is not None:
-            raise NotImplementedError("teacher-KL loss is outside the path built so far (SURVEY.md section 8f, rank 3)")
         self.teacher_kl_loss_coef = teacher_kl_loss_coef
         self.teacher_kl_loss_fn = teacher_kl_loss_fn
         self.teacher_loss_importance_sampling = teacher_loss_importance_sampling
@@ -344,7 +342,10 @@ class PPO(Algorithm):
         return ops.PpoHyper(clip_range=float(self.clip_range), clip_range_vf=self.clip_range_vf,
                             ent_coef=float(self.ent_coef), vf_coef=[float(x) for x in vf],
                             vf_halving=bool(self.ppo2_vf_coef_halving), pi_coef=pi_coef, loss_scale=loss_scale,
-                            adv_mode=mode, adv_weights=w)
+                            adv_mode=mode, adv_weights=w,
+                            teacher_kl_coef=float(self.teacher_kl_loss_coef or 0.0),
+                            teacher_unbiased=bool(getattr(self.teacher_kl_loss_fn, "unbiased", True)),
+                            teacher_importance=bool(self.teacher_loss_importance_sampling))
 
     def _moments_local(self, adv: torch.Tensor, h: ops.PpoHyper) -> Optional[torch.Tensor]:
         if h.adv_mode == ops.ADV_NONE:
@@ -366,6 +367,10 @@ class PPO(Algorithm):
             mb.additional)
         policy = self.policy
         B = obs.shape[0]
+        teacher_logp = None
+        if self.teacher_kl_loss_coef:
+            assert self.teacher_kl_loss_fn is not None, "teacher_kl_loss_coef needs teacher_kl_loss_fn"
+            teacher_logp = _additional["teacher_logprobs"]
         if moments is PPO._UNSET:
             moments = self._moments(adv, h)
         kind = getattr(policy, "kind", None)
@@ -388,19 +393,19 @@ class PPO(Algorithm):
                 if not logits.is_contiguous():
                     logits = logits.contiguous()
                 res = ops.ppo_gridnet_loss(h, policy.spec, logits, cmask, pmask, cells, pick, old_logp, adv,
-                                           old_values, returns, v32, moments=moments)
+                                           old_values, returns, v32, moments=moments, teacher_logp=teacher_logp)
                 grads = [res.grads[0].reshape(out.pi.shape)]
                 roots = [out.pi]
             elif kind == "categorical":
                 logits = out.pi.detach().float().contiguous()
                 res = ops.ppo_categorical_loss(h, logits, masks, actions, old_logp, adv, old_values, returns, v32,
-                                               moments=moments)
+                                               moments=moments, teacher_logp=teacher_logp)
                 grads, roots = [res.grads[0].to(out.pi.dtype)], [out.pi]
             else:
                 mu = out.pi.detach().float().contiguous()
                 res = ops.ppo_gaussian_loss(h, mu, out.log_std.detach().float().contiguous(),
                                             actions.float().contiguous(), old_logp, adv, old_values, returns, v32,
-                                            moments=moments)
+                                            moments=moments, teacher_logp=teacher_logp)
                 grads, roots = [res.grads[0].to(out.pi.dtype), res.grads[1]], [out.pi, out.log_std]
             roots.append(values)
             grads.append(res.dvalues.reshape(values.shape).to(values.dtype))
@@ -409,7 +414,8 @@ class PPO(Algorithm):
         # distribution-level path: any policy with forward(obs, actions, masks) -> (logp, entropy, v)
         res = ops.ppo_scalar_loss(h, logp_a.detach().float().contiguous(), entropy.detach().float().contiguous(),
                                   old_logp, adv, old_values, returns, new_values.detach().float().contiguous(),
-                                  moments=moments, kl_cutoff=self.kl_cutoff, pi_coef_state=pi_coef_state)
+                                  moments=moments, kl_cutoff=self.kl_cutoff, pi_coef_state=pi_coef_state,
+                                  teacher_logp=teacher_logp)
         torch.autograd.backward(
             [logp_a, entropy, new_values],
             [res.grads[0].to(logp_a.dtype).reshape(logp_a.shape), res.grads[1].to(entropy.dtype).reshape(entropy.shape),
@@ -432,7 +438,8 @@ class PPO(Algorithm):
         _, tensors = batch._flat()
         key = (self.batch_size, bool(self.gradient_accumulation), bool(self.autocast_loss), float(self.max_grad_norm),
                h.clip_range, h.clip_range_vf, h.ent_coef, tuple(h.vf_coef), h.vf_halving, h.loss_scale, h.adv_mode,
-               tuple(h.adv_weights) if h.adv_weights is not None else None, tuple(t.data_ptr() for t in tensors))
+               tuple(h.adv_weights) if h.adv_weights is not None else None, h.teacher_kl_coef, h.teacher_unbiased,
+               h.teacher_importance, tuple(t.data_ptr() for t in tensors))
         g = self._update_graphs.get(key)
         if g is not None:
             self._captures_in_a_row = 0
@@ -464,6 +471,8 @@ class PPO(Algorithm):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
         r = rollout_generator.rollout(gamma=self.gamma, gae_lambda=self.gae_lambda)
+        if self.teacher_kl_loss_fn is not None:  # ppo.py:259-262
+            r.add_to_batch(self.teacher_kl_loss_fn.add_to_batch, rollout_generator.vec_env.num_envs)
         if self.profile_stages:
             ev[1].record()
         timesteps_elapsed += r.total_steps
@@ -531,7 +540,8 @@ class PPO(Algorithm):
             explained_var = np.nan if var_y == 0 else 1 - np.var(r.y_true - r.y_pred).item() / var_y
         steps = [
             TrainStepStats(float(x[0]), float(x[1]), _vec(x[5:5 + V], V), float(x[2]), float(x[3]), float(x[4]),
-                           _vec(x[5 + V:5 + 2 * V], V), {})
+                           _vec(x[5 + V:5 + 2 * V], V),
+                           {"teacher_kl_loss": float(x[5 + 2 * V])} if self.teacher_kl_loss_coef else {})
             for x in rows
         ]
         train_stats = TrainStats(steps, explained_var, [float(g) for g in gn])

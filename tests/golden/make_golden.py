@@ -23,6 +23,7 @@ from tests.golden import _ref_shim  # noqa: E402
 
 _ref_shim.install()
 
+from rl_algo_impls.loss.teacher_kl_loss import TeacherKLLoss as RefTeacherKLLoss  # noqa: E402
 from rl_algo_impls.ppo.ppo import PPO as RefPPO  # noqa: E402
 from rl_algo_impls.rollout.vec_rollout import VecRollout as RefVecRollout  # noqa: E402
 from rl_algo_impls.shared.actor.categorical import MaskedCategorical as RefMaskedCategorical  # noqa: E402
@@ -178,6 +179,11 @@ class _Writer:
         pass
 
 
+import collections  # noqa: E402
+
+_ACForward = collections.namedtuple("_ACForward", "logp_a entropy v")
+
+
 class _RefPolicy(torch.nn.Module):
     """forward(obs, actions, action_masks) -> (logp_a, entropy, v) over the REFERENCE distributions."""
 
@@ -197,7 +203,7 @@ class _RefPolicy(torch.nn.Module):
             pi = RefMaskedCategorical(logits=out.pi, mask=action_masks)
         else:
             pi = RefGaussian(out.pi, torch.exp(out.log_std))
-        return pi.log_prob(actions), pi.entropy(), out.values
+        return _ACForward(pi.log_prob(actions), pi.entropy(), out.values)
 
 
 class _Gen:
@@ -250,6 +256,15 @@ def _learner_case(name, kind, make_net, T, N, obs_shape, hp: olearn.Hyper, nvec=
                                       "gradient_accumulation", "kl_cutoff", "normalize_advantages_after_scaling",
                                       "learning_rate")}
     as_list = lambda x: x.tolist() if isinstance(x, np.ndarray) else x
+    teacher_net = teacher_pol = None
+    if hp.teacher_kl_loss_coef:
+        torch.manual_seed(seed + 50)
+        teacher_net = make_net()
+        teacher_pol = _RefPolicy(teacher_net, kind, nvec, HW, gates)
+        mgr = type("Mgr", (), {"latest_checkpoint": teacher_pol})()
+        kw.update(teacher_kl_loss_coef=hp.teacher_kl_loss_coef,
+                  teacher_kl_loss_fn=RefTeacherKLLoss(mgr, unbiased=hp.teacher_unbiased),
+                  teacher_loss_importance_sampling=hp.teacher_loss_importance_sampling)
     algo = RefPPO(pol, torch.device("cpu"), _Writer(), gamma=as_list(hp.gamma), gae_lambda=as_list(hp.gae_lambda),
                   vf_coef=as_list(hp.vf_coef) if not np.isscalar(hp.vf_coef) else hp.vf_coef,
                   multi_reward_weights=list(hp.multi_reward_weights) if hp.multi_reward_weights is not None else None, **kw)
@@ -271,7 +286,10 @@ def _learner_case(name, kind, make_net, T, N, obs_shape, hp: olearn.Hyper, nvec=
     opol = olearn.OraclePolicy(net2, kind, nvec, HW, gates)
     opt = torch.optim.Adam(net2.parameters(), lr=hp.learning_rate, eps=1e-7)
     torch.manual_seed(seed + 100)
-    ostats = olearn.learn_epoch(opol, opt, ro, hp)
+    oteacher = olearn.OraclePolicy(teacher_net, kind, nvec, HW, gates) if teacher_net is not None else None
+    ostats = olearn.learn_epoch(opol, opt, ro, hp, teacher=oteacher)
+    if teacher_net is not None:
+        exact(np.float64(ostats["teacher_kl_loss"]), np.float64(s.additional_losses["teacher_kl_loss"]), f"learner {name} teacher_kl_loss")
     for k, v in net2.state_dict().items():
         exact(v, final[k], f"learner {name} param {k}")
     for k in ("loss", "pi_loss", "entropy_loss", "approx_kl", "clipped_frac", "grad_norm", "explained_var"):
@@ -291,6 +309,9 @@ def _learner_case(name, kind, make_net, T, N, obs_shape, hp: olearn.Hyper, nvec=
     out["stats.v_loss"] = np.asarray(s.v_loss, np.float64)
     out["stats.val_clipped_frac"] = np.asarray(s.val_clipped_frac, np.float64)
     out["seed"] = np.asarray(seed)
+    if teacher_net is not None:
+        out.update({f"teacher.{k}": v.detach().numpy() for k, v in teacher_net.state_dict().items()})
+        out["stats.teacher_kl_loss"] = np.float64(s.additional_losses["teacher_kl_loss"])
     save("learner_" + name, **out)
 
 

@@ -17,6 +17,15 @@ LEARNER_CASES = {
                      hp=olearn.Hyper(batch_size=20, n_epochs=2, gamma=0.999, gae_lambda=0.99, clip_range=0.1,
                                      clip_range_vf=0.1, ppo2_vf_coef_halving=True, ent_coef=0.01, vf_coef=0.5,
                                      learning_rate=1e-3)),
+    "microrts_teacher": dict(kind="gridnet", T=8, N=6, obs_shape=(5, 8, 8), nvec=MICRORTS_NVEC, side=8, gates=MICRORTS_GATES,
+                             V=1,
+                             hp=olearn.Hyper(batch_size=24, n_epochs=2, gamma=0.999, gae_lambda=0.99, clip_range=0.1,
+                                             clip_range_vf=0.1, ppo2_vf_coef_halving=True, ent_coef=0.01, vf_coef=0.5,
+                                             learning_rate=1e-3, teacher_kl_loss_coef=0.5)),
+    "cartpole_teacher_biased": dict(kind="categorical", T=16, N=8, obs_shape=(4,), nvec=(2,), V=1,
+                                    hp=olearn.Hyper(batch_size=32, n_epochs=2, gamma=0.98, gae_lambda=0.8, clip_range=0.2,
+                                                    learning_rate=1e-3, teacher_kl_loss_coef=1.0, teacher_unbiased=False,
+                                                    teacher_loss_importance_sampling=False)),
     "lux": dict(kind="gridnet", T=6, N=4, obs_shape=(5, 8, 8), nvec=LUX_NVEC, side=8, gates=LUX_GATES, n_pick=1, V=3,
                 hp=olearn.Hyper(batch_size=8, n_epochs=2, gamma=np.array([1.0, 1.0, 0.99]),
                                 gae_lambda=np.array([0.95, 0.95, 0.9]), clip_range=0.1, ent_coef=0.01,

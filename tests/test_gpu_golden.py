@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from tests.parity import close
-from tests.test_oracle_golden import cases, gates_of, learner_setup, load, rollout_from
+from tests.test_oracle_golden import LEARNER_CASES_ALL, cases, gates_of, learner_setup, load, rollout_from, teacher_net
 
 pytestmark = pytest.mark.gpu
 
@@ -100,7 +100,7 @@ def _device_policy(case, net, cuda):
     return ActorCritic(env, network=net, subaction_mask=case.get("gates")).to(cuda)
 
 
-@pytest.mark.parametrize("name", ["cartpole", "gaussian", "microrts", "lux"])
+@pytest.mark.parametrize("name", LEARNER_CASES_ALL)
 def test_learn_epoch_vs_reference_fixture(cuda, name):
     from rl_algo_impls_b200.ppo import PPO
     from rl_algo_impls_b200.rollout import VecRollout
@@ -114,6 +114,7 @@ def test_learn_epoch_vs_reference_fixture(cuda, name):
 
     class Gen:
         n_steps = case["T"]
+        vec_env = type("E", (), {"num_envs": case["N"]})()
 
         def rollout(self, gamma, gae_lambda):
             return VecRollout(cuda, ro["next_episode_starts"], ro["next_values"], ro["obs"], ro["actions"], ro["rewards"],
@@ -125,6 +126,15 @@ def test_learn_epoch_vs_reference_fixture(cuda, name):
                                       "ppo2_vf_coef_halving", "max_grad_norm", "multi_reward_weights",
                                       "gradient_accumulation", "kl_cutoff", "normalize_advantages_after_scaling",
                                       "learning_rate")}
+    tnet = teacher_net(case, z)
+    if tnet is not None:  # teacher-KL term: the teacher checkpoint is an ActorCritic over the stored teacher weights
+        from rl_algo_impls_b200.loss import TeacherKLLoss
+
+        teacher = _device_policy(case, tnet, cuda)
+        mgr = type("Mgr", (), {"latest_checkpoint": teacher})()
+        kw.update(teacher_kl_loss_coef=hp.teacher_kl_loss_coef,
+                  teacher_kl_loss_fn=TeacherKLLoss(mgr, unbiased=hp.teacher_unbiased),
+                  teacher_loss_importance_sampling=hp.teacher_loss_importance_sampling)
     algo = PPO(policy, cuda, None, **kw)
     box = {}
 
@@ -156,3 +166,6 @@ def test_learn_epoch_vs_reference_fixture(cuda, name):
         assert abs(got - want) <= tol * max(abs(want), 1e-2), f"{name} {k}: {got} vs {want}"
     np.testing.assert_allclose(np.asarray(s.v_loss, np.float64), z["stats.v_loss"], rtol=1e-4)
     assert abs(s.clipped_frac - float(z["stats.clipped_frac"])) <= 2.0 / hp.batch_size
+    if tnet is not None:
+        want = float(z["stats.teacher_kl_loss"])
+        assert abs(s.additional_losses["teacher_kl_loss"] - want) <= 2e-3 * max(abs(want), 1e-2)

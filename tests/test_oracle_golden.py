@@ -123,7 +123,22 @@ def learner_setup(name):
     return case, z, net
 
 
-@pytest.mark.parametrize("name", ["cartpole", "gaussian", "microrts", "lux"])
+LEARNER_CASES_ALL = ["cartpole", "gaussian", "microrts", "lux", "microrts_teacher", "cartpole_teacher_biased"]
+
+
+def teacher_net(case, z):
+    """The teacher checkpoint of a teacher-KL case (None otherwise)."""
+    from tests.golden.make_golden_cases import make_net_for
+
+    keys = [k for k in z if k.startswith("teacher.")]
+    if not keys:
+        return None
+    net = make_net_for(case)()
+    net.load_state_dict({k[8:]: torch.from_numpy(z[k]) for k in keys})
+    return net
+
+
+@pytest.mark.parametrize("name", LEARNER_CASES_ALL)
 def test_oracle_learn_epoch_reproduces_the_reference(name):
     """Same initial weights + rollout + randperm seed -> the reference PPO.learn_epoch's final
     parameters and TrainStats, bit for bit."""
@@ -131,8 +146,12 @@ def test_oracle_learn_epoch_reproduces_the_reference(name):
     hp = case["hp"]
     pol = olearn.OraclePolicy(net, case["kind"], case["nvec"], case.get("side", 0) ** 2, case.get("gates"))
     opt = torch.optim.Adam(net.parameters(), lr=hp.learning_rate, eps=1e-7)
+    tnet = teacher_net(case, z)  # before seeding: building a module draws from the generator
+    teacher = olearn.OraclePolicy(tnet, case["kind"], case["nvec"], case.get("side", 0) ** 2, case.get("gates")) if tnet else None
     torch.manual_seed(int(z["seed"]) + 100)
-    stats = olearn.learn_epoch(pol, opt, rollout_from(z), hp)
+    stats = olearn.learn_epoch(pol, opt, rollout_from(z), hp, teacher=teacher)
+    if teacher is not None:
+        assert np.float64(stats["teacher_kl_loss"]) == z["stats.teacher_kl_loss"]
     for k, v in net.state_dict().items():
         np.testing.assert_array_equal(v.numpy(), z[f"final.{k}"], err_msg=k)
     for k in ("loss", "pi_loss", "entropy_loss", "approx_kl", "clipped_frac", "grad_norm", "explained_var"):
