@@ -259,6 +259,21 @@ int b200rl_categorical_sample_f32(const float* logits, const uint8_t* mask, int6
 int b200rl_rollout_store_step(const void* const* src_host, void* const* dst_host, const int64_t* step_bytes_host,
                               int n_tensors, const int64_t* step_dev, int64_t T, b200rl_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K6  running-moment normalisers.  Replaces wrappers/normalize.py:18-122 over
+ * utils/running_mean_std.py:10-33.  State (mean[D], var[D], count[D] -- the reference's scalar count,
+ * kept per feature) is float64 on the device; with `training` the batch moments over the N envs are
+ * merged first (Chan), then
+ *   obs:    out = clip((x - mean) / sqrt(var + epsilon), -clip, clip)
+ *   reward: returns = returns * gamma + r; update(returns); out = clip(r / sqrt(var + epsilon), ...);
+ *           returns[done] = 0          (returns: [N, V] float64 accumulator)
+ */
+int b200rl_running_norm_obs_f32(const float* x, int64_t N, int64_t D, double* mean, double* var, double* count,
+                                int training, double epsilon, double clip, float* out, b200rl_stream_t stream);
+int b200rl_running_norm_reward_f32(const float* rewards, const uint8_t* dones, int64_t N, int64_t V, double gamma,
+                                   double* returns, double* mean, double* var, double* count, int training,
+                                   double epsilon, double clip, float* out, b200rl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

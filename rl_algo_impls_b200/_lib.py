@@ -103,6 +103,11 @@ PROTOTYPES = {
     ),
     "b200rl_gridnet_sample": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
     "b200rl_categorical_sample_f32": (_int, [_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
+    "b200rl_running_norm_obs_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _int, C.c_double, C.c_double, _vp, _vp]),
+    "b200rl_running_norm_reward_f32": (
+        _int,
+        [_vp, _vp, _i64, _i64, C.c_double, _vp, _vp, _vp, _vp, _int, C.c_double, C.c_double, _vp, _vp],
+    ),
     "b200rl_rollout_store_step": (_int, [C.POINTER(_vp), C.POINTER(_vp), c_i64p, _int, _vp, _i64, _vp]),
 }
 

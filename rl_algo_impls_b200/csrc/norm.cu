@@ -1,0 +1,121 @@
+// K6: running-moment observation / reward normalisers on the device.
+//
+// Replaces wrappers/normalize.py:18-122 over utils/running_mean_std.py:10-33 (RunningMeanStd):
+//   batch mean / variance over the N envs, Chan's parallel merge into the running (mean, var,
+//   count) in float64, then  clip((x - mean) / sqrt(var + eps), -clip, clip)   (observations) or
+//   returns = returns * gamma + r ; update(returns) ; clip(r / sqrt(var + eps), -clip, clip) ;
+//   returns[done] = 0                                                        (rewards).
+// One launch per env step: a CTA owns a tile of 32 features for ALL N rows, so it can reduce,
+// merge and normalise its own columns without a grid-wide barrier.  State lives in HBM as float64
+// (count is kept per feature so that no CTA reads a scalar another CTA is updating); everything
+// is asynchronous and address-stable, i.e. capturable in the rollout step's CUDA graph.
+#include "common.cuh"
+
+namespace b200rl {
+
+constexpr int kNormFeat = 32;  // features per CTA (one warp lane each)
+constexpr int kNormRows = 8;   // row groups per CTA
+constexpr int kNormBlock = kNormFeat * kNormRows;
+
+struct NormParams {
+  const float* x;      // [N, D] observations, or rewards
+  float* out;          // [N, D]
+  double* mean;        // [D]
+  double* var;         // [D]
+  double* count;       // [D]
+  double* returns;     // [N, D] discounted-return accumulator (reward mode) or null
+  const uint8_t* dones;  // [N] (reward mode) or null
+  long long N, D;
+  double gamma, epsilon, clip;
+  int training;
+};
+
+__global__ void __launch_bounds__(kNormBlock) running_norm_kernel(const NormParams p) {
+  __shared__ double s_sum[kNormRows][kNormFeat], s_sq[kNormRows][kNormFeat];
+  __shared__ double s_mean[kNormFeat], s_inv[kNormFeat];
+  const int fx = threadIdx.x % kNormFeat, ry = threadIdx.x / kNormFeat;
+  const long long f = (long long)blockIdx.x * kNormFeat + fx;
+  const bool live = f < p.D;
+  const bool reward = p.returns != nullptr;
+
+  // ---- 1. (reward mode) returns = returns * gamma + r ; batch moments of the tracked quantity --------
+  double sum = 0.0, sq = 0.0;
+  if (live && p.training) {
+    for (long long n = ry; n < p.N; n += kNormRows) {
+      double v;
+      if (reward) {
+        v = p.returns[n * p.D + f] * p.gamma + (double)p.x[n * p.D + f];
+        p.returns[n * p.D + f] = v;
+      } else {
+        v = (double)p.x[n * p.D + f];
+      }
+      sum += v;
+      sq += v * v;
+    }
+  }
+  s_sum[ry][fx] = sum, s_sq[ry][fx] = sq;
+  __syncthreads();
+
+  // ---- 2. Chan merge into the running moments (running_mean_std.py:16-29) --------------------------
+  if (ry == 0 && live) {
+    double mean = p.mean[f], var = p.var[f];
+    if (p.training) {
+      double a = 0.0, b = 0.0;
+      for (int r = 0; r < kNormRows; ++r) a += s_sum[r][fx], b += s_sq[r][fx];
+      const double count = p.count[f], n = (double)p.N;
+      const double batch_mean = a / n;
+      const double batch_var = fmax(0.0, b / n - batch_mean * batch_mean);
+      const double delta = batch_mean - mean, total = count + n;
+      mean += delta * n / total;
+      const double m2 = var * count + batch_var * n + delta * delta * count * n / total;
+      var = m2 / total;
+      p.mean[f] = mean, p.var[f] = var, p.count[f] = total;
+    }
+    s_mean[fx] = mean;
+    s_inv[fx] = 1.0 / sqrt(var + p.epsilon);
+  }
+  __syncthreads();
+
+  // ---- 3. normalise this tile's columns ------------------------------------------------------------
+  if (!live) return;
+  const double mean = reward ? 0.0 : s_mean[fx], inv = s_inv[fx];
+  for (long long n = ry; n < p.N; n += kNormRows) {
+    double v = ((double)p.x[n * p.D + f] - mean) * inv;
+    v = fmin(fmax(v, -p.clip), p.clip);
+    p.out[n * p.D + f] = (float)v;
+    if (reward && p.dones[n]) p.returns[n * p.D + f] = 0.0;  // wrappers/normalize.py:91
+  }
+}
+
+static int launch_norm(const NormParams& p, cudaStream_t stream) {
+  const long long tiles = (p.D + kNormFeat - 1) / kNormFeat;
+  if (tiles > 0x7fffffffLL) {
+    set_error("running_norm: too many features (%lld)", p.D);
+    return B200RL_EUNSUPPORTED;
+  }
+  running_norm_kernel<<<(unsigned)tiles, kNormBlock, 0, stream>>>(p);
+  return check_launch("running_norm");
+}
+
+}  // namespace b200rl
+
+extern "C" int b200rl_running_norm_obs_f32(const float* x, int64_t N, int64_t D, double* mean, double* var,
+                                           double* count, int training, double epsilon, double clip, float* out,
+                                           b200rl_stream_t stream) {
+  using namespace b200rl;
+  B200RL_REQUIRE(x && mean && var && count && out, "running_norm_obs: null pointer");
+  B200RL_REQUIRE(N >= 1 && D >= 1, "running_norm_obs: bad shape N=%lld D=%lld", (long long)N, (long long)D);
+  NormParams p{x, out, mean, var, count, nullptr, nullptr, N, D, 0.0, epsilon, clip, training};
+  return launch_norm(p, (cudaStream_t)stream);
+}
+
+extern "C" int b200rl_running_norm_reward_f32(const float* rewards, const uint8_t* dones, int64_t N, int64_t V,
+                                              double gamma, double* returns, double* mean, double* var, double* count,
+                                              int training, double epsilon, double clip, float* out,
+                                              b200rl_stream_t stream) {
+  using namespace b200rl;
+  B200RL_REQUIRE(rewards && dones && returns && mean && var && count && out, "running_norm_reward: null pointer");
+  B200RL_REQUIRE(N >= 1 && V >= 1, "running_norm_reward: bad shape N=%lld V=%lld", (long long)N, (long long)V);
+  NormParams p{rewards, out, mean, var, count, returns, dones, N, V, gamma, epsilon, clip, training};
+  return launch_norm(p, (cudaStream_t)stream);
+}

@@ -253,6 +253,51 @@ def rollout_store_step(step_tensors: Sequence[torch.Tensor], buffers: Sequence[t
 
 
 # ------------------------------------------------------------------------------------------------
+# K6
+def running_norm_obs(x: torch.Tensor, mean: torch.Tensor, var: torch.Tensor, count: torch.Tensor, training: bool,
+                     epsilon: float, clip: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NormalizeObservation.normalize (wrappers/normalize.py:39-48): update the running moments with
+    this batch (when training), then clip((x - mean) / sqrt(var + eps)).  x: [N, ...] float32."""
+    _cuda(x, torch.float32, "x")
+    N = x.shape[0]
+    D = x.numel() // N
+    for name, t in (("mean", mean), ("var", var), ("count", count)):
+        _cuda(t, torch.float64, name)
+        if t.numel() != D:
+            raise ValueError(f"{name} must have {D} entries")
+    out = torch.empty_like(x) if out is None else _cuda(out, torch.float32, "out")
+    rc = _call("b200rl_running_norm_obs_f32", 1, _lib.lib().b200rl_running_norm_obs_f32, x.data_ptr(), N, D,
+               mean.data_ptr(), var.data_ptr(), count.data_ptr(), int(training), float(epsilon), float(clip),
+               out.data_ptr(), _stream())
+    check(rc, "b200rl_running_norm_obs_f32")
+    return out
+
+
+def running_norm_reward(rewards: torch.Tensor, dones: torch.Tensor, returns: torch.Tensor, mean: torch.Tensor,
+                        var: torch.Tensor, count: torch.Tensor, gamma: float, training: bool, epsilon: float,
+                        clip: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NormalizeReward.step (wrappers/normalize.py:84-110): discounted-return accumulator, running
+    variance of the returns, clip(r / sqrt(var + eps)), returns[done] = 0.  rewards: [N] or [N, V]."""
+    _cuda(rewards, torch.float32, "rewards")
+    N = rewards.shape[0]
+    V = rewards.numel() // N
+    d = _as_u8(dones, "dones")
+    _cuda(returns, torch.float64, "returns")
+    if returns.numel() != N * V or d.numel() != N:
+        raise ValueError("returns must be [N, V] and dones [N]")
+    for name, t in (("mean", mean), ("var", var), ("count", count)):
+        _cuda(t, torch.float64, name)
+        if t.numel() != V:
+            raise ValueError(f"{name} must have {V} entries")
+    out = torch.empty_like(rewards) if out is None else _cuda(out, torch.float32, "out")
+    rc = _call("b200rl_running_norm_reward_f32", 1, _lib.lib().b200rl_running_norm_reward_f32, rewards.data_ptr(),
+               d.data_ptr(), N, V, float(gamma), returns.data_ptr(), mean.data_ptr(), var.data_ptr(), count.data_ptr(),
+               int(training), float(epsilon), float(clip), out.data_ptr(), _stream())
+    check(rc, "b200rl_running_norm_reward_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # PPO arguments shared by the fused-loss entry points
 @dataclass
 class PpoHyper:

@@ -1,0 +1,124 @@
+"""NormalizeObservation / NormalizeReward for device envs (CUDA tensors in, CUDA tensors out).
+
+Mirror ``rl_algo_impls/wrappers/normalize.py:18-122`` (constructor keywords, ``step`` / ``reset`` /
+``masked_reset`` / ``save`` / ``load`` / ``load_from``) over ``utils/running_mean_std.py:10-48``.
+The running moments are float64 tensors in HBM and one K6 launch per env step does the Chan merge
+and the normalisation; nothing synchronises, so the wrappers sit inside the rollout step's CUDA graph.
+A host (numpy) env keeps using the reference's own numpy wrappers: that side is not on this path.
+"""
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import ops
+
+
+class RunningMeanStd:
+    """Device-resident running (mean, var, count), float64 (running_mean_std.py:10-48)."""
+
+    def __init__(self, device, epsilon: float = 1e-4, shape: Tuple[int, ...] = ()) -> None:
+        self.shape = tuple(shape)
+        n = int(np.prod(self.shape)) if self.shape else 1
+        self.mean = torch.zeros(n, dtype=torch.float64, device=device)
+        self.var = torch.ones(n, dtype=torch.float64, device=device)
+        self._count = torch.full((n,), float(epsilon), dtype=torch.float64, device=device)  # scalar in the reference
+
+    @property
+    def count(self) -> float:
+        return float(self._count[0].item())
+
+    def save(self, path: str) -> None:
+        np.savez_compressed(path, mean=self.mean.cpu().numpy().reshape(self.shape),
+                            var=self.var.cpu().numpy().reshape(self.shape), count=self.count)
+
+    def load(self, path: str, count_override: Optional[int] = None) -> None:
+        data = np.load(path)
+        self.mean.copy_(torch.from_numpy(np.asarray(data["mean"], np.float64).reshape(-1)))
+        self.var.copy_(torch.from_numpy(np.asarray(data["var"], np.float64).reshape(-1)))
+        self._count.fill_(float(data["count"]) if count_override is None else float(count_override))
+
+    def load_from(self, existing: "RunningMeanStd") -> None:
+        self.mean.copy_(existing.mean), self.var.copy_(existing.var), self._count.copy_(existing._count)
+
+
+class _Wrapper:
+    def __init__(self, env) -> None:
+        self.env = env
+        if getattr(env, "device", None) is None:
+            raise RuntimeError("the device normalisers wrap a device env (CUDA tensors); host envs keep numpy wrappers")
+        self.device = env.device
+
+    def __getattr__(self, name):  # num_envs, spaces, get_action_mask, ...
+        return getattr(self.env, name)
+
+
+class NormalizeObservation(_Wrapper):
+    def __init__(self, env, training: bool = True, epsilon: float = 1e-8, clip: float = 10.0) -> None:
+        super().__init__(env)
+        self.rms = RunningMeanStd(self.device, shape=tuple(env.single_observation_space.shape))
+        self.training, self.epsilon, self.clip = training, epsilon, clip
+        self._out: Optional[torch.Tensor] = None
+
+    def normalize(self, obs: torch.Tensor) -> torch.Tensor:
+        x = obs.float().contiguous()
+        if self._out is None or self._out.shape != x.shape:
+            self._out = torch.empty_like(x)  # fixed output address: graph-capturable
+        return ops.running_norm_obs(x, self.rms.mean, self.rms.var, self.rms._count, self.training, self.epsilon,
+                                    self.clip, self._out)
+
+    def step(self, action):
+        obs, reward, terminations, truncations, info = self.env.step(action)
+        return self.normalize(obs), reward, terminations, truncations, info
+
+    def reset(self, **kwargs):
+        obs, info = self.env.reset(**kwargs)
+        return self.normalize(obs), info
+
+    def save(self, path: str) -> None:
+        self.rms.save(path)
+
+    def load(self, path: str) -> None:
+        self.rms.load(path)
+
+    def load_from(self, existing: "NormalizeObservation") -> None:
+        self.rms.load_from(existing.rms)
+
+
+class NormalizeReward(_Wrapper):
+    def __init__(self, env, training: bool = True, gamma: float = 0.99, epsilon: float = 1e-8, clip: float = 10.0,
+                 shape: Tuple[int, ...] = (), exponential_moving_mean_var: bool = False, emv_window_size=None) -> None:
+        super().__init__(env)
+        if exponential_moving_mean_var:
+            raise NotImplementedError("HybridMovingMeanVar (exponential_moving_mean_var) is not built")
+        self.rms = RunningMeanStd(self.device, shape=tuple(shape))
+        self.training, self.gamma, self.epsilon, self.clip = training, gamma, epsilon, clip
+        self.returns = torch.zeros((env.num_envs,) + tuple(shape), dtype=torch.float64, device=self.device)
+        self._out: Optional[torch.Tensor] = None
+
+    def step(self, action):
+        obs, reward, terminations, truncations, info = self.env.step(action)
+        r = reward.float().contiguous()
+        if self._out is None or self._out.shape != r.shape:
+            self._out = torch.empty_like(r)
+        done = torch.logical_or(terminations, truncations)
+        reward = ops.running_norm_reward(r, done, self.returns, self.rms.mean, self.rms.var, self.rms._count, self.gamma,
+                                         self.training, self.epsilon, self.clip, self._out)
+        return obs, reward, terminations, truncations, info
+
+    def reset(self, **kwargs):
+        self.returns.zero_()
+        return self.env.reset(**kwargs)
+
+    def masked_reset(self, env_mask):
+        self.returns[torch.as_tensor(env_mask, device=self.device)] = 0
+        return self.env.masked_reset(env_mask)
+
+    def save(self, path: str) -> None:
+        self.rms.save(path)
+
+    def load(self, path: str) -> None:
+        self.rms.load(path)
+
+    def load_from(self, existing: "NormalizeReward") -> None:
+        self.rms.load_from(existing.rms)

@@ -36,6 +36,7 @@ from rl_algo_impls.shared.policy.actor_critic import clamp_actions as ref_clamp_
 from oracle import learner as olearn  # noqa: E402
 from oracle.distributions import Gridnet, MaskedLogits, gates_from_subaction_mask, gaussian_logp_entropy  # noqa: E402
 from oracle.gae import gae_advantages, gae_returns  # noqa: E402
+from oracle.normalize import ObsNormalizer, RewardNormalizer  # noqa: E402
 from oracle.rollout import minibatch_index_stream, num_actions  # noqa: E402
 from tests.golden.stub_nets import TinyGrid, TinyMlp  # noqa: E402
 from tests.synth import (LUX_GATES, LUX_NVEC, MICRORTS_GATES, MICRORTS_NVEC, gae_inputs, gridnet_inputs,  # noqa: E402
@@ -348,7 +349,51 @@ def golden_index_stream_and_misc():
          sequential=np.concatenate(ref_seq), clamp_noscale=c1, clamp_squash=c2)
 
 
+def golden_normalizers():
+    """NormalizeObservation / NormalizeReward of the live reference over a few env steps."""
+    from rl_algo_impls.wrappers.normalize import NormalizeObservation as RefNormObs
+    from rl_algo_impls.wrappers.normalize import NormalizeReward as RefNormRew
+
+    rng = np.random.default_rng(21)
+    steps, N, D, V = 6, 64, 17, 3
+
+    class Env:
+        num_envs = N
+        single_observation_space = _ref_shim.Box(-np.inf, np.inf, (D,))
+        single_action_space = _ref_shim.Discrete(2)
+
+    obs = (rng.standard_normal((steps, N, D)) * np.linspace(0.1, 30.0, D) + np.linspace(-5, 5, D)).astype(np.float32)
+    ref = RefNormObs.__new__(RefNormObs)
+    RefNormObs.__init__(ref, Env())
+    ours = ObsNormalizer((D,))
+    outs = []
+    for t in range(steps):
+        want = ref.normalize(obs[t])
+        exact(ours.normalize(obs[t]), want, f"obs normalizer step {t}")
+        outs.append(want)
+    out = {"obs": obs, "obs_out": np.stack(outs), "obs_mean": ref.rms.mean, "obs_var": ref.rms.var,
+           "obs_count": np.float64(ref.rms.count)}
+    for tag, shape in (("scalar", ()), ("multi", (V,))):
+        rew = rng.standard_normal((steps, N) + shape).astype(np.float32) * 3
+        dones = rng.random((steps, N)) < 0.1
+        refr = RefNormRew.__new__(RefNormRew)
+        refr.num_envs = N  # the stubbed VectorWrapper base does not forward attributes
+        RefNormRew.__init__(refr, Env(), gamma=0.98, shape=shape)
+        oursr = RewardNormalizer(N, shape, gamma=0.98)
+        routs = []
+        for t in range(steps):
+            want = refr.normalize(rew[t])
+            refr.returns[dones[t]] = 0  # NormalizeReward.step, wrappers/normalize.py:91
+            exact(oursr.step(rew[t], dones[t]), want, f"reward normalizer {tag} step {t}")
+            routs.append(want)
+        out.update({f"rew_{tag}": rew, f"dones_{tag}": dones, f"rew_{tag}_out": np.stack(routs),
+                    f"rew_{tag}_var": np.asarray(refr.rms.var), f"rew_{tag}_mean": np.asarray(refr.rms.mean),
+                    f"rew_{tag}_returns": refr.returns, f"rew_{tag}_count": np.float64(refr.rms.count)})
+    save("normalizers", **out)
+
+
 if __name__ == "__main__":
+    golden_normalizers()
     golden_gae()
     golden_gridnet()
     golden_categorical_gaussian()

@@ -85,3 +85,31 @@ def test_vec_rollout_index_stream_and_batches(cuda):
         np.testing.assert_array_equal(mb.values.cpu().numpy(), inp["values"].reshape(-1)[i])
     got2 = list(r.minibatches(bs, shuffle=False))
     np.testing.assert_array_equal(got2[0].logprobs.cpu().numpy(), logprobs.reshape(-1)[:48])
+
+
+@pytest.mark.parametrize("kind", ["microrts", "lux"])
+def test_num_actions_matches_the_reference_rule(cuda, kind):
+    """a3: Batch.num_actions (rollout/rollout.py:130-180) -- cells with any valid action per head, with
+    the value-dependent gating, plus log(#valid pick cells) -- built lazily on the device."""
+    from oracle.distributions import gates_from_subaction_mask
+    from oracle.rollout import num_actions
+    from rl_algo_impls_b200 import spaces
+    from rl_algo_impls_b200.rollout import VecRollout
+    from tests.synth import LUX_GATES, LUX_NVEC, MICRORTS_GATES, MICRORTS_NVEC, gae_inputs, gridnet_inputs
+
+    T, N, HW = 3, 4, 64
+    nvec, gates, n_pick = (MICRORTS_NVEC, MICRORTS_GATES, 0) if kind == "microrts" else (LUX_NVEC, LUX_GATES, 1)
+    g = gridnet_inputs(5, T * N, HW, nvec, n_pick, 0.3)
+    acts = g["actions"].reshape(T, N, HW, len(nvec))
+    mask = g["mask"].reshape(T, N, HW, -1)
+    actions, masks = acts, mask
+    if n_pick:
+        actions = {"per_position": acts, "pick_position": g["pick_actions"].reshape(T, N, n_pick)}
+        masks = {"per_position": mask, "pick_position": g["pick_mask"].reshape(T, N, n_pick, HW)}
+    want = num_actions(actions, masks, gates_from_subaction_mask(gates), np.asarray(nvec))
+    inp = gae_inputs(1, T, N, 1, 0.1)
+    r = VecRollout(cuda, inp["next_episode_starts"], inp["next_values"], np.zeros((T, N, 2), np.float32), actions,
+                   inp["rewards"], inp["episode_starts"], inp["values"], np.zeros((T, N), np.float32), masks, 0.99, 0.95,
+                   subaction_mask=gates, action_plane_space=spaces.MultiDiscrete(nvec), include_num_actions=True)
+    got = r.batch().num_actions.cpu().numpy().reshape(T, N)
+    np.testing.assert_allclose(got, want, rtol=1e-6)

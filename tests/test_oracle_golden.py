@@ -157,3 +157,20 @@ def test_oracle_learn_epoch_reproduces_the_reference(name):
     for k in ("loss", "pi_loss", "entropy_loss", "approx_kl", "clipped_frac", "grad_norm", "explained_var"):
         assert np.float64(stats[k]) == z[f"stats.{k}"], k
     np.testing.assert_array_equal(np.asarray(stats["v_loss"], np.float64), z["stats.v_loss"])
+
+
+def test_normalizers_match_the_reference():
+    """oracle/normalize.py against NormalizeObservation / NormalizeReward of the live reference."""
+    from oracle.normalize import ObsNormalizer, RewardNormalizer
+
+    z = load("normalizers")
+    o = ObsNormalizer(z["obs"].shape[2:])
+    for t in range(z["obs"].shape[0]):
+        np.testing.assert_array_equal(o.normalize(z["obs"][t]), z["obs_out"][t])
+    np.testing.assert_array_equal(o.rms.var, z["obs_var"])
+    for tag in ("scalar", "multi"):
+        rew, dones = z[f"rew_{tag}"], z[f"dones_{tag}"]
+        r = RewardNormalizer(rew.shape[1], rew.shape[2:], gamma=0.98)
+        for t in range(rew.shape[0]):
+            np.testing.assert_array_equal(r.step(rew[t], dones[t]), z[f"rew_{tag}_out"][t])
+        np.testing.assert_array_equal(r.returns, z[f"rew_{tag}_returns"])
