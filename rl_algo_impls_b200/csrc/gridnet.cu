@@ -70,6 +70,7 @@ struct GridDev {
   const float* dlogp_in;
   const float* dent_in;
   int chunks;        // streaming CTAs per sample = ceil(HW / kChunkCells)
+  int stash;         // unit cells with a shared-memory (lse, entropy) slot = min(HW, kStashCells)
   int G;             // lanes per cell group (power of two <= 32)
   int max_width;     // widest head block
   // workspace (written by the streaming kernel, read by the compute kernel)
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
   int* prefix = reinterpret_cast<int*>(smem);                      // [chunks + 1]
   int* pick_prefix = prefix + (G.chunks + 1);                      // [n_pick][chunks + 1]
   float* s_lse = reinterpret_cast<float*>(smem + (((size_t)(G.chunks + 1) * (1 + kMaxPick) * 4 + 15) & ~(size_t)15));
-  float* s_ent = s_lse + (size_t)kStashCells * G.A;
+  float* s_ent = s_lse + (size_t)G.stash * G.A;
 
   const LT* g_logits = static_cast<const LT*>(G.logits) + row0 * G.Sp;
   LT* g_out = static_cast<LT*>(G.dlogits) + row0 * G.Sp;
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
       for (int j = 0; j < PMAX; ++j) k_d[j] = d[j], k_e[j] = e[j];
       k_valid = h.any ? p.valid : 0u, k_ls = h.ls, k_inv = h.inv_sum, k_ent = h.ent;
       k_cell = cell, k_local = local, k_gated = gated_in;
-    } else if (slot.first && i < kStashCells) {
+    } else if (slot.first && i < G.stash) {
       s_lse[i * G.A + slot.head] = h.any ? h.mx + h.ls : INFINITY;  // +inf marks a head with no valid entry
       s_ent[i * G.A + slot.head] = h.ent;
     }
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
     for (int j = 0; j < PMAX; ++j) p.x[j] = 0.f;
     if (live) p = load_piece<LT, PMAX>(g_logits + (long long)cell * G.Sp, g_mask + (long long)cell * G.S, slot);
     float lse, ent;
-    if (i0 + n_groups - 1 < kStashCells) {  // the whole pass is in the stash (warp-uniform test)
+    if (i0 + n_groups - 1 < G.stash) {  // the whole pass is in the stash (warp-uniform test)
       lse = live ? s_lse[i * G.A + slot.head] : INFINITY;
       ent = live ? s_ent[i * G.A + slot.head] : 0.f;
     } else {  // beyond the stash: redo the forward reductions
@@ -600,6 +601,7 @@ static size_t grid_workspace_bytes(long long B, long long HW, int n_pick) {
 
 static int bind_workspace(GridDev* G, void* workspace, size_t workspace_bytes, const char* who) {
   G->chunks = (int)((G->HW + kChunkCells - 1) / kChunkCells);
+  G->stash = (int)(G->HW < kStashCells ? G->HW : kStashCells);
   B200RL_REQUIRE(workspace != nullptr && workspace_bytes >= grid_workspace_bytes(G->B, G->HW, G->n_pick),
                  "%s: workspace too small (%zu < %zu bytes)", who, workspace_bytes,
                  grid_workspace_bytes(G->B, G->HW, G->n_pick));
@@ -613,7 +615,7 @@ static int bind_workspace(GridDev* G, void* workspace, size_t workspace_bytes, c
 }
 
 static size_t compute_smem(const GridDev& G) {
-  return align16((size_t)(G.chunks + 1) * (1 + kMaxPick) * 4) + (size_t)kStashCells * G.A * 2 * sizeof(float);
+  return align16((size_t)(G.chunks + 1) * (1 + kMaxPick) * 4) + (size_t)G.stash * G.A * 2 * sizeof(float);
 }
 
 template <int MODE, typename LT, int PMAX, bool PICK, bool SELF_STREAM>
