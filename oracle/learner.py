@@ -205,3 +205,66 @@ def learn_epoch(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict
     stats["grad_norm"] = float(np.mean(grad_norms))
     stats["total_steps"] = total
     return stats
+
+
+@dataclass
+class A2CHyper:
+    """The reference's A2C keyword arguments (a2c/a2c.py:24-43)."""
+
+    learning_rate: float = 7e-4
+    gamma: Union[float, np.ndarray] = 0.99
+    gae_lambda: Union[float, np.ndarray] = 1.0
+    ent_coef: float = 0.0
+    vf_coef: Union[float, Sequence[float]] = 0.5
+    max_grad_norm: float = 0.5
+    rms_prop_eps: float = 1e-5
+    use_rms_prop: bool = True
+    normalize_advantage: bool = False
+    multi_reward_weights: Optional[Sequence[float]] = None
+    gradient_accumulation: bool = False
+    num_minibatches: int = 1
+
+
+def a2c_learn_iteration(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict, hp: A2CHyper) -> dict:
+    """One iteration of A2C.learn (a2c/a2c.py:104-173) on a collected rollout."""
+    adv = gae_advantages(ro["rewards"], ro["values"], ro["episode_starts"], ro["next_episode_starts"],
+                         ro["next_values"], hp.gamma, hp.gae_lambda)
+    ret = gae_returns(adv, ro["values"])
+    b = dict(obs=_flat(ro["obs"]), actions=_flat(ro["actions"]), masks=_flat(ro["masks"]), adv=_flat(adv),
+             returns=_flat(ret))
+    total = b["adv"].shape[0]
+    w = torch.tensor(np.asarray(hp.multi_reward_weights), dtype=torch.float32) if hp.multi_reward_weights is not None else None
+    vf_coef = torch.tensor(np.asarray(hp.vf_coef), dtype=torch.float32)
+    params = list(policy.parameters())
+    step_stats = []
+
+    def optimizer_step():
+        nn.utils.clip_grad_norm_(params, hp.max_grad_norm)
+        optimizer.step()
+        optimizer.zero_grad(set_to_none=True)
+
+    for idx in minibatch_index_stream(total, total // hp.num_minibatches, shuffle=not hp.gradient_accumulation):
+        mb_adv = b["adv"][idx]
+        if hp.normalize_advantage:
+            mb_adv = (mb_adv - mb_adv.mean(0)) / (mb_adv.std(0) + 1e-8)
+        if w is not None:
+            mb_adv = mb_adv @ w
+        logp, ent, v = policy.forward(b["obs"][idx], _take(b["actions"], idx), _take(b["masks"], idx))
+        pi_loss = -(mb_adv * logp).mean()
+        value_loss = ((v - b["returns"][idx]) ** 2).mean(0)
+        entropy_loss = -ent.mean()
+        loss = pi_loss + (vf_coef * value_loss).sum() + hp.ent_coef * entropy_loss
+        if hp.gradient_accumulation:
+            loss = loss / hp.num_minibatches
+        loss.backward()
+        if not hp.gradient_accumulation:
+            optimizer_step()
+        step_stats.append(dict(loss=loss.item(), pi_loss=pi_loss.item(), v_loss=value_loss.detach().numpy().copy(),
+                               entropy_loss=entropy_loss.item()))
+    if hp.gradient_accumulation:
+        optimizer_step()
+    stats = {k: np.mean([s[k] for s in step_stats], axis=0) for k in step_stats[0]}
+    y_true, y_pred = flatten_time_major(ret), flatten_time_major(ro["values"])
+    var_y = np.var(y_true).item()
+    stats["explained_var"] = np.nan if var_y == 0 else 1 - np.var(y_true - y_pred).item() / var_y
+    return stats

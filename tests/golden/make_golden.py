@@ -23,6 +23,7 @@ from tests.golden import _ref_shim  # noqa: E402
 
 _ref_shim.install()
 
+from rl_algo_impls.a2c.a2c import A2C as RefA2C  # noqa: E402
 from rl_algo_impls.loss.teacher_kl_loss import TeacherKLLoss as RefTeacherKLLoss  # noqa: E402
 from rl_algo_impls.ppo.ppo import PPO as RefPPO  # noqa: E402
 from rl_algo_impls.rollout.vec_rollout import VecRollout as RefVecRollout  # noqa: E402
@@ -173,8 +174,11 @@ def golden_categorical_gaussian():
 
 # ---------------------------------------------------------------------------------------------
 class _Writer:
-    def add_scalar(self, *a, **k):
-        pass
+    def __init__(self):
+        self.scalars = {}
+
+    def add_scalar(self, name, value, *a, **k):
+        self.scalars[name] = value
 
     def on_steps(self, *a, **k):
         pass
@@ -349,6 +353,73 @@ def golden_index_stream_and_misc():
          sequential=np.concatenate(ref_seq), clamp_noscale=c1, clamp_squash=c2)
 
 
+def golden_a2c():
+    """One A2C.learn iteration of the live reference (a2c/a2c.py:104-173) on fixed rollouts."""
+    from tests.golden.make_golden_cases import A2C_CASES, make_net_for
+
+    for ci, (name, case) in enumerate(A2C_CASES.items()):
+        seed = 40 + ci
+        rng = np.random.default_rng(seed)
+        torch.manual_seed(seed)
+        make_net = make_net_for(case)
+        net = make_net()
+        init = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        T, N, V, kind, nvec = case["T"], case["N"], case["V"], case["kind"], case["nvec"]
+        side = case.get("side", 0)
+        HW = side * side
+        gates = case.get("gates")
+        ro = gae_inputs(seed + 1, T, N, V, 0.1)
+        ro["obs"] = rng.standard_normal((T, N) + case["obs_shape"], dtype=np.float32)
+        ro["masks"] = None
+        if kind == "categorical":
+            ro["actions"] = rng.integers(0, nvec[0], size=(T, N))
+        else:
+            g = gridnet_inputs(seed + 2, T * N, HW, nvec, 0, 0.2)
+            ro["actions"], ro["masks"] = g["actions"].reshape(T, N, HW, len(nvec)), g["mask"].reshape(T, N, HW, -1)
+        ro["logprobs"] = np.zeros((T, N), np.float32)
+        hp = case["hp"]
+        pol = _RefPolicy(net, kind, nvec, HW, gates)
+
+        def ref_rollout(gamma, gae_lambda):
+            return RefVecRollout(torch.device("cpu"), ro["next_episode_starts"], ro["next_values"], ro["obs"],
+                                 ro["actions"], ro["rewards"], ro["episode_starts"], ro["values"], ro["logprobs"],
+                                 ro["masks"], gamma, gae_lambda, subaction_mask=gates,
+                                 action_plane_space=_ref_shim.MultiDiscrete(nvec) if kind == "gridnet" else None)
+
+        as_list = lambda x: x.tolist() if isinstance(x, np.ndarray) else x
+        writer = _Writer()
+        algo = RefA2C(pol, torch.device("cpu"), writer, learning_rate=hp.learning_rate, gamma=as_list(hp.gamma),
+                      gae_lambda=as_list(hp.gae_lambda), ent_coef=hp.ent_coef, vf_coef=as_list(hp.vf_coef) if not np.isscalar(hp.vf_coef) else hp.vf_coef,
+                      max_grad_norm=hp.max_grad_norm, rms_prop_eps=hp.rms_prop_eps, use_rms_prop=hp.use_rms_prop,
+                      normalize_advantage=hp.normalize_advantage,
+                      multi_reward_weights=list(hp.multi_reward_weights) if hp.multi_reward_weights is not None else None,
+                      gradient_accumulation=hp.gradient_accumulation, num_minibatches=hp.num_minibatches)
+        torch.manual_seed(seed + 100)
+        algo.learn(T * N, _Gen(ref_rollout, N))
+        final = {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+        net2 = make_net()
+        net2.load_state_dict(init)
+        opol = olearn.OraclePolicy(net2, kind, nvec, HW, gates)
+        opt = (torch.optim.RMSprop(net2.parameters(), lr=hp.learning_rate, eps=hp.rms_prop_eps) if hp.use_rms_prop
+               else torch.optim.Adam(net2.parameters(), lr=hp.learning_rate))
+        torch.manual_seed(seed + 100)
+        ostats = olearn.a2c_learn_iteration(opol, opt, ro, hp)
+        for k, v in net2.state_dict().items():
+            exact(v, final[k], f"a2c {name} param {k}")
+        for k in ("loss", "pi_loss", "entropy_loss", "explained_var"):
+            exact(np.float64(ostats[k]), np.float64(writer.scalars[f"losses/{k}"]), f"a2c {name} stat {k}")
+        out = {f"init.{k}": v.numpy() for k, v in init.items()}
+        out.update({f"final.{k}": v.numpy() for k, v in final.items()})
+        for k, v in ro.items():
+            if v is not None:
+                out[f"ro.{k}"] = v
+        for k in ("loss", "pi_loss", "entropy_loss", "explained_var"):
+            out[f"stats.{k}"] = np.float64(writer.scalars[f"losses/{k}"])
+        out["seed"] = np.asarray(seed)
+        save("a2c_" + name, **out)
+
+
 def golden_normalizers():
     """NormalizeObservation / NormalizeReward of the live reference over a few env steps."""
     from rl_algo_impls.wrappers.normalize import NormalizeObservation as RefNormObs
@@ -393,6 +464,7 @@ def golden_normalizers():
 
 
 if __name__ == "__main__":
+    golden_a2c()
     golden_normalizers()
     golden_gae()
     golden_gridnet()

@@ -34,6 +34,16 @@ LEARNER_CASES = {
 }
 
 
+A2C_CASES = {
+    "cartpole": dict(kind="categorical", T=5, N=8, obs_shape=(4,), nvec=(2,), V=1,
+                     hp=olearn.A2CHyper(learning_rate=7e-4, gamma=0.99, gae_lambda=1.0, ent_coef=0.01, vf_coef=0.5)),
+    "microrts": dict(kind="gridnet", T=6, N=4, obs_shape=(5, 8, 8), nvec=MICRORTS_NVEC, side=8, gates=MICRORTS_GATES, V=1,
+                     hp=olearn.A2CHyper(learning_rate=1e-3, gamma=0.99, gae_lambda=0.95, ent_coef=0.01, vf_coef=0.5,
+                                        normalize_advantage=True, use_rms_prop=False, gradient_accumulation=True,
+                                        num_minibatches=3)),
+}
+
+
 def make_net_for(case):
     if case["kind"] == "gridnet":
         n_logits = sum(case["nvec"]) + case.get("n_pick", 0)

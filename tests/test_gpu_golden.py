@@ -169,3 +169,43 @@ def test_learn_epoch_vs_reference_fixture(cuda, name):
     if tnet is not None:
         want = float(z["stats.teacher_kl_loss"])
         assert abs(s.additional_losses["teacher_kl_loss"] - want) <= 2e-3 * max(abs(want), 1e-2)
+
+
+@pytest.mark.parametrize("name", ["cartpole", "microrts"])
+def test_a2c_iteration_vs_reference_fixture(cuda, name):
+    """A2C.learn (one iteration) on the device path vs the live reference's final parameters / losses."""
+    from rl_algo_impls_b200.a2c import A2C
+    from rl_algo_impls_b200.rollout import VecRollout
+    from tests.test_oracle_golden import a2c_setup
+
+    case, z, net = a2c_setup(name)
+    hp = case["hp"]
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    policy = _device_policy(case, net, cuda)
+    ro = rollout_from(z)
+
+    class Gen:
+        vec_env = type("E", (), {"num_envs": case["N"]})()
+
+        def rollout(self, gamma, gae_lambda):
+            return VecRollout(cuda, ro["next_episode_starts"], ro["next_values"], ro["obs"], ro["actions"], ro["rewards"],
+                              ro["episode_starts"], ro["values"], ro["logprobs"], ro["masks"], gamma, gae_lambda,
+                              subaction_mask=case.get("gates"))
+
+    algo = A2C(policy, cuda, None, learning_rate=hp.learning_rate, gamma=hp.gamma, gae_lambda=hp.gae_lambda,
+               ent_coef=hp.ent_coef, vf_coef=hp.vf_coef, max_grad_norm=hp.max_grad_norm, rms_prop_eps=hp.rms_prop_eps,
+               use_rms_prop=hp.use_rms_prop, normalize_advantage=hp.normalize_advantage,
+               gradient_accumulation=hp.gradient_accumulation, num_minibatches=hp.num_minibatches)
+    torch.manual_seed(int(z["seed"]) + 100)
+    algo.learn(case["T"] * case["N"], Gen())
+    stats = algo.last_train_stats.data
+    for k, tol in (("loss", 1e-4), ("pi_loss", 1e-3), ("entropy_loss", 1e-5), ("explained_var", 1e-5)):
+        want = float(z[f"stats.{k}"])
+        assert abs(stats[k] - want) <= tol * max(abs(want), 1e-2), (k, stats[k], want)
+    for k, v in policy.network.state_dict().items():
+        want, init = z[f"final.{k}"].astype(np.float64), z[f"init.{k}"].astype(np.float64)
+        got = v.cpu().numpy().astype(np.float64)
+        rms_update = np.sqrt(np.mean((want - init) ** 2))
+        rms_err = np.sqrt(np.mean((got - want) ** 2))
+        assert rms_err <= 1e-2 * rms_update + 1e-8, f"{name} param {k}: rms err {rms_err:.3e} vs rms update {rms_update:.3e}"

@@ -174,3 +174,28 @@ def test_normalizers_match_the_reference():
         for t in range(rew.shape[0]):
             np.testing.assert_array_equal(r.step(rew[t], dones[t]), z[f"rew_{tag}_out"][t])
         np.testing.assert_array_equal(r.returns, z[f"rew_{tag}_returns"])
+
+
+def a2c_setup(name):
+    from tests.golden.make_golden_cases import A2C_CASES, make_net_for
+
+    case = A2C_CASES[name]
+    z = load("a2c_" + name)
+    net = make_net_for(case)()
+    net.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("init.")})
+    return case, z, net
+
+
+@pytest.mark.parametrize("name", ["cartpole", "microrts"])
+def test_oracle_a2c_iteration_reproduces_the_reference(name):
+    case, z, net = a2c_setup(name)
+    hp = case["hp"]
+    pol = olearn.OraclePolicy(net, case["kind"], case["nvec"], case.get("side", 0) ** 2, case.get("gates"))
+    opt = (torch.optim.RMSprop(net.parameters(), lr=hp.learning_rate, eps=hp.rms_prop_eps) if hp.use_rms_prop
+           else torch.optim.Adam(net.parameters(), lr=hp.learning_rate))
+    torch.manual_seed(int(z["seed"]) + 100)
+    stats = olearn.a2c_learn_iteration(pol, opt, rollout_from(z), hp)
+    for k, v in net.state_dict().items():
+        np.testing.assert_array_equal(v.numpy(), z[f"final.{k}"], err_msg=k)
+    for k in ("loss", "pi_loss", "entropy_loss", "explained_var"):
+        assert np.float64(stats[k]) == z[f"stats.{k}"], k
