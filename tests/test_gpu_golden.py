@@ -209,3 +209,53 @@ def test_a2c_iteration_vs_reference_fixture(cuda, name):
         rms_update = np.sqrt(np.mean((want - init) ** 2))
         rms_err = np.sqrt(np.mean((got - want) ** 2))
         assert rms_err <= 1e-2 * rms_update + 1e-8, f"{name} param {k}: rms err {rms_err:.3e} vs rms update {rms_update:.3e}"
+
+
+def test_learn_epoch_with_kl_cutoff_matches_the_oracle(cuda):
+    """kl_cutoff (ppo.py:352-355): the cut-off decision is taken on the device between forward and
+    backward (no host sync) and stays sticky for the rest of the learn_epoch; same final parameters as
+    the oracle learner, whose cut-off logic is the reference's."""
+    from oracle import learner as olearn
+    from rl_algo_impls_b200.ppo import PPO
+    from rl_algo_impls_b200.rollout import VecRollout
+    from tests.golden.make_golden_cases import make_net_for
+
+    case, z, net = learner_setup("microrts")
+    import copy
+    import dataclasses
+
+    hp = dataclasses.replace(case["hp"], kl_cutoff=2e-3, batch_size=24, n_epochs=3)
+    ro = rollout_from(z)
+    ro["logprobs"] = ro["logprobs"] + 0.05  # push approx_kl over the cut-off after the first updates
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cpu_net = copy.deepcopy(net)
+    opol = olearn.OraclePolicy(cpu_net, case["kind"], case["nvec"], case["side"] ** 2, case["gates"])
+    opt = torch.optim.Adam(cpu_net.parameters(), lr=hp.learning_rate, eps=1e-7)
+    torch.manual_seed(7)
+    ostats = olearn.learn_epoch(opol, opt, ro, hp)
+
+    policy = _device_policy(case, net, cuda)
+
+    class Gen:
+        n_steps = case["T"]
+        vec_env = type("E", (), {"num_envs": case["N"]})()
+
+        def rollout(self, gamma, gae_lambda):
+            return VecRollout(cuda, ro["next_episode_starts"], ro["next_values"], ro["obs"], ro["actions"], ro["rewards"],
+                              ro["episode_starts"], ro["values"], ro["logprobs"], ro["masks"], gamma, gae_lambda,
+                              subaction_mask=case.get("gates"))
+
+    kw = {k: getattr(hp, k) for k in ("batch_size", "n_epochs", "gamma", "gae_lambda", "clip_range", "clip_range_vf",
+                                      "ent_coef", "vf_coef", "ppo2_vf_coef_halving", "max_grad_norm", "kl_cutoff",
+                                      "learning_rate")}
+    algo = PPO(policy, cuda, None, **kw)
+    torch.manual_seed(7)
+    algo.learn_epoch(0, case["T"] * case["N"], Gen(), None)
+    s = algo.last_train_stats
+    assert abs(s.approx_kl - ostats["approx_kl"]) <= 2e-3 * max(abs(ostats["approx_kl"]), 1e-3)
+    assert abs(s.loss - ostats["loss"]) <= 1e-3 * max(abs(ostats["loss"]), 1e-2)
+    for (k, v), w in zip(policy.network.state_dict().items(), cpu_net.state_dict().values()):
+        err = (v.cpu().double() - w.double()).pow(2).mean().sqrt().item()
+        scale = (w.double() - torch.from_numpy(z[f"init.{k}"]).double()).pow(2).mean().sqrt().item()
+        assert err <= 1e-2 * scale + 1e-8, (k, err, scale)

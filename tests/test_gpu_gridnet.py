@@ -182,3 +182,27 @@ def test_gridnet_bf16_logits(cuda):
                                     inp["actions"].to(cuda), None)
     close(logp_g, dist.log_prob(action), what="logp")
     close(ent_g, dist.entropy(), what="entropy")
+
+
+def test_fused_bf16_logits_and_gradients(cuda):
+    """autocast_loss: bf16 logits in, bf16 dlogits out, f32 math in between.  Against the f32 oracle on
+    the same (bf16-representable) logits: scalars to 1e-5 (conditioned), dlogits to bf16 rounding."""
+    from rl_algo_impls_b200 import ops
+
+    B, HW, nvec, gates = 24, 256, MICRORTS_NVEC, MICRORTS_GATES
+    inp = to_torch(gridnet_inputs(77, B, HW, nvec, 0, 0.08))
+    inp["logits"] = inp["logits"].bfloat16().float()
+    pp = to_torch(ppo_inputs(9, B, 1))
+    kw = dict(normalize_advantage=True)
+    o32 = _oracle_fused(inp, pp, nvec, gates, HW, torch.float32, None, 1, kw, 0.1, True, None)
+    o64 = _oracle_fused(inp, pp, nvec, gates, HW, torch.float64, o32["old_logp"], 1, kw, 0.1, True, None)
+    h = ops.PpoHyper(clip_range=0.1, clip_range_vf=0.1, ent_coef=0.01, vf_coef=[0.5], vf_halving=True)
+    out = ops.ppo_gridnet_loss(h, spec_of(nvec, gates, 0), inp["logits"].to(cuda).bfloat16(), inp["mask"].to(cuda), None,
+                               inp["actions"].to(cuda), None, o32["old_logp"].to(cuda), pp["adv"].to(cuda),
+                               pp["old_values"].to(cuda), pp["returns"].to(cuda), pp["new_values"].to(cuda), want_logp=True)
+    assert out.grads[0].dtype == torch.bfloat16
+    close(out.logp, o32["logp"], what="logp")
+    close_conditioned(out.stats[0].cpu(), o32["parts"].loss, o64["parts"].loss, what="loss")
+    got, want = out.grads[0].float().cpu(), o32["dlogits"]
+    assert ((got - want).abs() <= 2 ** -8 * want.abs() + 1e-3 * want.abs().max() * 2 ** -8).all()  # bf16: 8 bits of mantissa
+    assert (got[~inp["mask"]] == 0).all()
