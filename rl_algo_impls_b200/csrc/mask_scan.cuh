@@ -29,9 +29,15 @@ __device__ __forceinline__ void zero_fill(uint8_t* dst, uint32_t bytes) {
 
 // Row prefetch context: the logits row of a flagged cell is wanted a few microseconds from now.
 struct RowPrefetch {
-  const uint8_t* logits;  // first logit of the CTA's first cell
+  const uint8_t* logits;  // first logit of the CTA's first cell (NULL: no prefetch)
   uint32_t row_bytes;     // Sp * sizeof(LT)
 };
+
+// byte offset -> cell without an integer division: floor(n / S) == umulhi(n, ceil(2^32 / S)) for
+// n * S < 2^32 (checked by the caller); inv == 0 selects the plain division (S == 1 or huge chunks).
+__device__ __forceinline__ uint32_t cell_of(uint32_t n, uint32_t S, uint32_t inv) {
+  return inv ? __umulhi(n, inv) : n / S;
+}
 
 __device__ __forceinline__ void flag_cell(uint32_t* bitmap, uint32_t cell, const RowPrefetch& pf) {
   const uint32_t bit = 1u << (cell & 31);
@@ -45,8 +51,9 @@ __device__ __forceinline__ void flag_cell(uint32_t* bitmap, uint32_t cell, const
 // A 16-byte word of the mask chunk with at least one non-zero byte: flag the cell(s) it covers.
 // Rows are S bytes, so for S >= 16 a word touches at most two cells; two 32-bit divisions and a
 // byte-boundary split decide which.  (Chunk sizes are < 2^31 bytes: cells <= 4096, S <= 65535.)
-static __device__ __noinline__ void flag_word(uint32_t* bitmap, uint32_t base, const uint4& w, uint32_t S, const RowPrefetch& pf) {
-  const uint32_t c0 = base / S, c1 = (base + 15u) / S;
+static __device__ __noinline__ void flag_word(uint32_t* bitmap, uint32_t base, const uint4& w, uint32_t S, uint32_t inv,
+                                              const RowPrefetch& pf) {
+  const uint32_t c0 = cell_of(base, S, inv), c1 = cell_of(base + 15u, S, inv);
   if (c0 == c1) {
     flag_cell(bitmap, c0, pf);
     return;
@@ -72,7 +79,7 @@ static __device__ __noinline__ void flag_word(uint32_t* bitmap, uint32_t base, c
   for (int q = 0; q < 4; ++q)
 #pragma unroll 1
     for (int r = 0; r < 4; ++r)
-      if ((word[q] >> (8 * r)) & 0xffu) flag_cell(bitmap, (base + 4u * q + r) / S, pf);
+      if ((word[q] >> (8 * r)) & 0xffu) flag_cell(bitmap, cell_of(base + 4u * q + r, S, inv), pf);
 }
 
 // flags every cell of [mask, mask + bytes) that has a non-zero byte
@@ -80,6 +87,7 @@ template <int BLOCK>
 __device__ __forceinline__ void scan_mask(const uint8_t* mask, uint32_t bytes, uint32_t S, uint32_t* bitmap,
                                           const RowPrefetch& pf) {
   const uint32_t tid = threadIdx.x;
+  const uint32_t inv = (S > 1u && (unsigned long long)(bytes + 16u) * S < (1ull << 32)) ? 0xFFFFFFFFu / S + 1u : 0u;
   uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(mask) & 15u)) & 15u;
   if (head > bytes) head = bytes;
   if (tid < head && mask[tid]) flag_cell(bitmap, tid / S, pf);
@@ -96,7 +104,7 @@ __device__ __forceinline__ void scan_mask(const uint8_t* mask, uint32_t bytes, u
     }
 #pragma unroll
     for (uint32_t u = 0; u < kUnroll; ++u)
-      if ((w[u].x | w[u].y | w[u].z | w[u].w) != 0u) flag_word(bitmap, head + ((i0 + u * BLOCK) << 4), w[u], S, pf);
+      if ((w[u].x | w[u].y | w[u].z | w[u].w) != 0u) flag_word(bitmap, head + ((i0 + u * BLOCK) << 4), w[u], S, inv, pf);
   }
   const uint32_t done = head + (n4 << 4);
   if (tid < bytes - done && mask[done + tid]) flag_cell(bitmap, (done + tid) / S, pf);
