@@ -234,7 +234,11 @@ def main():
     cfg = CONFIGS[args.config]
     workload = {"workload": f"{cfg.key}: {cfg.title}", "env": cfg.env, "envs_per_gpu": cfg.n_envs,
                 "n_steps": cfg.n_steps, "batch_size": cfg.algo["batch_size"], "n_epochs": cfg.algo["n_epochs"],
-                "parallelism": f"env-sharded dp{args.gpus}", "l2": "minibatch tensors exceed L2 (logits+dlogits 490 MB at C4)"}
+                "parallelism": f"env-sharded dp{args.gpus}",
+                "l2": ("not flushed: every minibatch gathers fresh rows and the minibatch working set (logits + dlogits "
+                       "490 MB per launch at C4, 119 MB at C5; rollout buffer 0.4-5.5 GB) exceeds the 126 MB L2"
+                       if cfg.key in ("C4", "C5") else
+                       "not flushed and the working set fits L2: this config is launch-bound, reported for completeness")}
 
     if args.impl == "reference":
         if rank != 0:

@@ -11,24 +11,27 @@
 // uniform, log_prob 0, entropy -0, gradient blocked by torch.where), so its logits are never
 // read and its dlogits row is plain zero fill.  Two phases:
 //
-//  S  streaming, one CTA per chunk of 256 cells:
-//     zero-fills the chunk's dlogits with 128-bit stores, scans its mask bytes (and the
-//     pick_position mask) with 128-bit loads, flags non-empty cells in a shared bitmap
-//     (the first flag prefetches that cell's logits row to L2), compacts the bitmap and
-//     writes the chunk's list of unit cells (+ count) to the workspace.  HBM-bound.
+//  S  streaming, one chunk of 256 cells at a time: zero-fills the chunk's dlogits with 128-bit
+//     stores, scans its mask bytes (and the pick_position mask) with 128-bit loads, flags non-empty
+//     cells in a shared bitmap (the first flag prefetches that cell's logits row to L2) and
+//     compacts the bitmap into the chunk's ascending list of unit cells (+ count).  HBM-bound.
 //  C  fused compute, one CTA per sample -- masked logsumexp / log-prob / entropy, ratio / clip /
-//     value-clip / KL, and the backward into dlogits and dvalues in ONE launch: groups of G lanes (G = 16 for MicroRTS' planes, 8 for Lux') take one listed cell
-//     each; a lane owns <= 8 adjacent logits of one head, a wide head (the 49-way attack target)
+//     value-clip / KL, and the backward into dlogits and dvalues in ONE launch: groups of G lanes
+//     (G = 16 for MicroRTS' planes, 8 for Lux') take one listed cell each; a lane owns <= 8
+//     adjacent logits of one head, a wide head (the 49-way attack target)
 //     spans an aligned power-of-two block of lanes reduced with xor shuffles; per-sample sums
 //     run in float64; thread 0 forms the PPO terms (ppo_terms.cuh), one warp the value heads;
 //     the same lanes then overwrite the listed cells' zero-filled rows with d loss / d logits
 //     straight from registers.  The pick_position categorical over the (compacted) valid cells
 //     is an online-softmax reduction in the same pass.  Latency-bound, but on ~5 % of the cells.
 //
-// Maps of up to 256 cells (MicroRTS 16x16: one chunk per sample) run S and C in the SAME CTA of one
-// launch, so the zero-fill stores of one sample drain while its compute phase runs and CTAs at
-// different phases share an SM.  Larger maps (Lux 64x64: 16 chunks per sample) run S as its own
-// full-occupancy launch and C as a second launch (measured: 124 us vs 176-200 us fused, B=512).
+// Maps of up to 256 cells (MicroRTS 16x16: one chunk per sample) run S and C in the SAME 128-thread
+// CTA of one launch: the lists stay in shared memory, the zero-fill stores of a sample drain while
+// its compute phase runs and CTAs at different phases share an SM.  Larger maps (Lux 64x64: 16
+// chunks per sample) run S as its own launch (one CTA per chunk, lists to the workspace) and C as a
+// second launch: measured 130 us against 176-200 us for single-kernel variants (an 8-CTA cluster
+// exchanging through DSMEM; "the CTA that finishes a sample's last chunk computes", whose
+// __threadfence before the arrival counter serialises the zero-fill stores), B=512.
 //
 // HBM traffic per sample: dlogits written once, masks read once, logits / actions read only
 // for unit cells.  Deterministic: lists are ascending per chunk, every reduction has a fixed order.

@@ -320,9 +320,9 @@ class PPO(Algorithm):
     # ---------------------------------------------------------------------------------------------
     def _hyper(self, V: int, adv_v: int, loss_scale: float, pi_coef: float) -> ops.PpoHyper:
         """Host scalars of this epoch, re-read every learn_epoch (callbacks may have changed them)."""
-        vf = np.broadcast_to(np.asarray(self.vf_coef, dtype=np.float64).reshape(-1), (V,)).copy() \
-            if np.ndim(self.vf_coef) == 0 or len(np.atleast_1d(self.vf_coef)) == 1 \
-            else np.asarray(self.vf_coef, dtype=np.float64).reshape(-1)
+        vf = np.asarray(self.vf_coef, dtype=np.float64).reshape(-1)
+        if vf.size == 1:  # a scalar vf_coef applies to every value head
+            vf = np.repeat(vf, V)
         if self.vf_weights is not None:
             # v_loss @ vf_weights -> scalar value loss (ppo.py:344-345): fold the weights into vf_coef
             assert np.ndim(self.vf_coef) == 0 or np.size(self.vf_coef) == 1, "vf_weights needs a scalar vf_coef"
