@@ -107,37 +107,9 @@ class A2C(Algorithm):
             timesteps_elapsed += r.total_steps
 
             vf_coef = torch.as_tensor(np.array(self.vf_coef), dtype=torch.float32, device=self.device)
-            weights = None if self.multi_reward_weights is None else [float(x) for x in self.multi_reward_weights]
-            step_stats: List[torch.Tensor] = []
-            for mb in r.minibatches(r.total_steps // self.num_minibatches, shuffle=not self.gradient_accumulation):
-                adv = mb.advantages
-                B = adv.shape[0]
-                # a2c.py:133-138 on the device: K2 moments + normalise (+ reward-weight contraction)
-                mode = ops.ADV_NORMALIZE if self.normalize_advantage else ops.ADV_NONE
-                if self.normalize_advantage or weights is not None:
-                    moments = None
-                    if self.normalize_advantage:
-                        moments = ops.adv_moments(adv.reshape(B, -1), None, mode, weights)
-                        if _world() > 1:
-                            torch.distributed.all_reduce(moments)
-                    adv = ops.adv_normalize(adv.reshape(B, -1), None, mode, weights, moments).reshape(B)
-                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(self.autocast_loss)):
-                    logp_a, entropy, v = self.policy(mb.obs, mb.actions, action_masks=mb.action_masks)
-                    if self.scale_loss_by_num_actions:
-                        n_act = mb.num_actions
-                        logp_a = torch.where(n_act > 0, logp_a / n_act, 0)
-                    pi_loss = -(adv * logp_a).mean()
-                    value_loss = ((v - mb.returns) ** 2).mean(0)
-                    entropy_loss = -entropy.mean()
-                    loss = pi_loss + (vf_coef * value_loss).sum() + self.ent_coef * entropy_loss
-                    if self.gradient_accumulation:
-                        loss = loss / self.num_minibatches
-                loss.backward()
-                if not self.gradient_accumulation:
-                    self.optimizer_step()
-                step_stats.append(torch.cat([loss.detach().reshape(1).float(), pi_loss.detach().reshape(1).float(),
-                                             entropy_loss.detach().reshape(1).float(),
-                                             value_loss.detach().reshape(-1).float()]))
+            step_stats = [self._minibatch(mb, vf_coef)
+                          for mb in r.minibatches(r.total_steps // self.num_minibatches,
+                                                  shuffle=not self.gradient_accumulation)]
             if self.gradient_accumulation:
                 self.optimizer_step()
 
@@ -161,6 +133,39 @@ class A2C(Algorithm):
                     logging.info(f"Callback terminated training at {timesteps_elapsed} timesteps")
                     break
         return self
+
+    def _advantages(self, adv: torch.Tensor) -> torch.Tensor:
+        """a2c.py:133-138 on the device: K2 moments + normalise, then the reward-weight contraction."""
+        weights = None if self.multi_reward_weights is None else [float(x) for x in self.multi_reward_weights]
+        if not self.normalize_advantage and weights is None:
+            return adv
+        B = adv.shape[0]
+        mode = ops.ADV_NORMALIZE if self.normalize_advantage else ops.ADV_NONE
+        moments = None
+        if self.normalize_advantage:
+            moments = ops.adv_moments(adv.reshape(B, -1), None, mode, weights)
+            if _world() > 1:
+                torch.distributed.all_reduce(moments)
+        return ops.adv_normalize(adv.reshape(B, -1), None, mode, weights, moments).reshape(B)
+
+    def _minibatch(self, mb, vf_coef: torch.Tensor) -> torch.Tensor:
+        """Forward, A2C loss (a2c.py:140-161), backward (and the optimizer step unless gradients
+        accumulate).  Returns [loss, pi_loss, entropy_loss, v_loss...] on the device."""
+        adv = self._advantages(mb.advantages)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(self.autocast_loss)):
+            logp_a, entropy, v = self.policy(mb.obs, mb.actions, action_masks=mb.action_masks)
+            if self.scale_loss_by_num_actions:
+                logp_a = torch.where(mb.num_actions > 0, logp_a / mb.num_actions, 0)
+            pi_loss = -(adv * logp_a).mean()
+            value_loss = (v - mb.returns).square().mean(0)
+            entropy_loss = -entropy.mean()
+            loss = pi_loss + (vf_coef * value_loss).sum() + self.ent_coef * entropy_loss
+            if self.gradient_accumulation:
+                loss = loss / self.num_minibatches
+        loss.backward()
+        if not self.gradient_accumulation:
+            self.optimizer_step()
+        return torch.cat([t.detach().reshape(-1).float() for t in (loss, pi_loss, entropy_loss, value_loss)])
 
     def optimizer_step(self) -> None:
         params = [p for p in self.policy.parameters() if p.grad is not None]

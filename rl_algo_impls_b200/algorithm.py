@@ -1,8 +1,12 @@
-"""Algorithm ABC (mirrors rl_algo_impls/shared/algorithm.py:19-60: constructor fields, learn(), and
-optimizer-state save / load to ``optimizer.pt``)."""
+"""Base class of the learners (PPO, A2C).
+
+Keeps the surface the reference's runner relies on (``rl_algo_impls/shared/algorithm.py:19-60``):
+the five constructor fields, an abstract ``learn``, and ``save`` / ``load`` of the optimizer state
+under ``<dir>/optimizer.pt`` -- so checkpoints written by either implementation load in the other.
+"""
 import logging
-import os
 from abc import ABC, abstractmethod
+from pathlib import Path
 from typing import List, Optional, TypeVar
 
 import torch
@@ -10,38 +14,44 @@ from torch.optim import Optimizer
 
 OPTIMIZER_FILENAME = "optimizer.pt"
 AlgorithmSelf = TypeVar("AlgorithmSelf", bound="Algorithm")
+_log = logging.getLogger(__name__)
 
 
 class Algorithm(ABC):
+    policy: torch.nn.Module
+    device: torch.device
+    learning_rate: float
+    optimizer: Optimizer
+
     @abstractmethod
     def __init__(self, policy, device: torch.device, tb_writer, learning_rate: float, optimizer: Optimizer,
                  **kwargs) -> None:
         super().__init__()
-        self.policy = policy
-        self.device = device
-        self.tb_writer = tb_writer
-        self.learning_rate = learning_rate
-        self.optimizer = optimizer
+        self.policy, self.device, self.tb_writer = policy, device, tb_writer
+        self.learning_rate, self.optimizer = learning_rate, optimizer
 
     @abstractmethod
     def learn(self: AlgorithmSelf, train_timesteps: int, rollout_generator, callbacks: Optional[List] = None,
-              total_timesteps: Optional[int] = None, start_timesteps: int = 0) -> AlgorithmSelf: ...
+              total_timesteps: Optional[int] = None, start_timesteps: int = 0) -> AlgorithmSelf:
+        """Train for ``train_timesteps`` env steps drawn from ``rollout_generator``."""
 
     def save(self, path: str) -> None:
-        torch.save(self.optimizer.state_dict(), os.path.join(path, OPTIMIZER_FILENAME))
+        torch.save(self.optimizer.state_dict(), Path(path) / OPTIMIZER_FILENAME)
 
     def load(self, path: str) -> None:
-        optimizer_path = os.path.join(path, OPTIMIZER_FILENAME)
-        if os.path.exists(optimizer_path):
-            self.optimizer.load_state_dict(torch.load(optimizer_path, map_location=self.device))
-        else:
-            logging.info(f"Optimizer state not found at {optimizer_path}. Not overwriting optimizer state.")
+        state_file = Path(path) / OPTIMIZER_FILENAME
+        if not state_file.exists():
+            _log.info("no optimizer state at %s: the optimizer keeps its current state", state_file)
+            return
+        self.optimizer.load_state_dict(torch.load(state_file, map_location=self.device))
 
 
 def update_learning_rate(optimizer: Optimizer, learning_rate: float) -> None:
-    """shared/schedule.py:64-66"""
+    """Apply the (possibly scheduled) learning rate to every parameter group (shared/schedule.py:64-66).
+    A capturable optimizer keeps its rate in a device tensor: fill it instead of rebinding."""
     for group in optimizer.param_groups:
-        if isinstance(group["lr"], torch.Tensor):  # capturable optimizer: the value lives on the device
-            group["lr"].fill_(float(learning_rate))
+        current = group["lr"]
+        if isinstance(current, torch.Tensor):
+            current.fill_(float(learning_rate))
         else:
             group["lr"] = learning_rate

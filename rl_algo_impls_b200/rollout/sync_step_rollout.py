@@ -73,6 +73,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
     ) -> None:
         super().__init__(policy, vec_env)
         self.cuda_graph = cuda_graph
+        self.include_num_actions = False  # A2C's scale_loss_by_num_actions turns the Batch.num_actions field on
         self.n_steps = int(n_steps)
         self.sde_sample_freq = sde_sample_freq
         self.scale_advantage_by_values_accuracy = scale_advantage_by_values_accuracy
@@ -322,6 +323,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
             action_plane_space=getattr(self.vec_env, "action_plane_space", None),
             out_advantages=self.advantages,
             out_returns=self.returns,
+            include_num_actions=self.include_num_actions,
         )
 
     # -- masked resets (sync_step_rollout.py:218-278) ------------------------------------------------
