@@ -71,6 +71,20 @@ int b200rl_gae_scan_f32(const float* rewards, const float* values, const uint8_t
                         float* advantages, float* returns, int64_t T, int64_t N, int64_t V,
                         b200rl_stream_t stream);
 
+/* K1b  GAE over ragged trajectories (segments concatenated along the first axis, seg_offsets [n+1] on
+ * the device).  Replaces compute_advantages per Trajectory (rollout/trajectory.py:56-95) when
+ * `episode_starts` [total] is given (entry t = dones[t-1]; next_episode_starts[s] = dones[-1] of
+ * segment s), and DiscreteSkipsTrajectoryBuilder.trajectory
+ * (rollout/discrete_skips_trajectory_builder.py:84-100: gamma ** steps_elapsed[t] discounting, value 0
+ * after a finished trajectory) when `steps_elapsed` [total] i32 is given instead.  Exactly one of the two.
+ */
+int b200rl_gae_segments_f32(const float* rewards, const float* values, const uint8_t* episode_starts,
+                            const int32_t* steps_elapsed, const int64_t* seg_offsets,
+                            const uint8_t* next_episode_starts, const float* next_values,
+                            const double* gamma_host, const double* gae_lambda_host, int gamma_is_scalar,
+                            float* advantages, float* returns, int64_t n_segments, int64_t V,
+                            b200rl_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * K2  per-minibatch advantage moments and normalisation.  Replaces ppo/ppo.py:307-318.
  * adv_mode:

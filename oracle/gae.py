@@ -60,3 +60,29 @@ def gae_advantages(
 def gae_returns(advantages: np.ndarray, values: np.ndarray) -> np.ndarray:
     """vec_rollout.py:88 -- float32 add."""
     return advantages + values
+
+
+def discrete_skips_advantages(
+    rewards: np.ndarray,  # [T] or [T, V] float32
+    values: np.ndarray,
+    steps_elapsed: np.ndarray,  # [T] int32
+    done: bool,
+    next_values,  # [V] / scalar, used when not done
+    gamma: NumOrArray,
+    gae_lambda: NumOrArray,
+) -> np.ndarray:
+    """rollout/discrete_skips_trajectory_builder.py:84-100 (the trajectory() recurrence)."""
+    advantages = np.zeros_like(rewards)
+    last_advantage = np.zeros_like(advantages[-1])
+    n_steps = advantages.shape[0]
+    gamma = _head_broadcast(gamma, values.shape[1:])
+    gae_lambda = _head_broadcast(gae_lambda, values.shape[1:])
+    for t in reversed(range(n_steps)):
+        if t == n_steps - 1:
+            next_value = np.zeros_like(values[t]) if done else next_values
+        else:
+            next_value = values[t + 1]
+        delta = rewards[t] + gamma ** steps_elapsed[t] * next_value - values[t]
+        last_advantage = delta + gamma ** steps_elapsed[t] * gae_lambda * last_advantage
+        advantages[t] = last_advantage
+    return advantages

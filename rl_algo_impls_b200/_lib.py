@@ -76,6 +76,10 @@ PROTOTYPES = {
     "b200rl_version": (_int, []),
     "b200rl_last_error": (C.c_char_p, []),
     "b200rl_gae_scan_f32": (_int, [_vp, _vp, _vp, _vp, _vp, c_f64p, c_f64p, _int, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "b200rl_gae_segments_f32": (
+        _int,
+        [_vp, _vp, _vp, _vp, _vp, _vp, _vp, c_f64p, c_f64p, _int, _vp, _vp, _i64, _i64, _vp],
+    ),
     "b200rl_adv_moments_workspace_bytes": (_sz, [_i64, _i64]),
     "b200rl_adv_moments_f64": (_int, [_vp, _vp, _i64, _i64, _int, c_f32p, _vp, _vp, _sz, _vp]),
     "b200rl_adv_normalize_f32": (_int, [_vp, _vp, _i64, _i64, _int, c_f32p, _vp, _vp, _i64, _vp]),

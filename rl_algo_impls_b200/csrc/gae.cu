@@ -191,3 +191,90 @@ extern "C" int b200rl_gae_scan_f32(const float* rewards, const float* values, co
   if (vec4) return V == 1 ? launch<4, true>(p, s) : launch<4, false>(p, s);
   return V == 1 ? launch<1, true>(p, s) : launch<1, false>(p, s);
 }
+
+// ---- K1b: GAE over ragged trajectories ------------------------------------------------------------
+// Replaces compute_advantages per Trajectory (rollout/trajectory.py:56-95: shapes [T_i(, V)], the
+// episode start of step t+1 is dones[t], the step after the last one uses dones[-1] / next_values)
+// and DiscreteSkipsTrajectoryBuilder.trajectory (rollout/discrete_skips_trajectory_builder.py:84-100:
+// delta = r + gamma^k v' - v, adv = delta + gamma^k lambda adv', k = steps_elapsed[t]).
+// Segments are concatenated along the first axis; one thread walks one (segment, value head) lane.
+namespace b200rl {
+
+struct SegParams {
+  const float* rewards;
+  const float* values;
+  const uint8_t* episode_starts;  // [total] (standard) or null (skips)
+  const int32_t* steps_elapsed;   // [total] (skips) or null
+  const long long* offsets;       // [n_seg + 1]
+  const uint8_t* next_starts;     // [n_seg]: standard: dones[-1]; skips: trajectory done
+  const float* next_values;       // [n_seg, V]
+  float* advantages;
+  float* returns;
+  long long n_seg, V;
+  int gamma_is_scalar;
+  double gamma[B200RL_MAX_VALUE_HEADS], lambda[B200RL_MAX_VALUE_HEADS];
+};
+
+__global__ void __launch_bounds__(128) gae_segments_kernel(const SegParams p) {
+  const long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane >= p.n_seg * p.V) return;
+  const long long seg = lane / p.V;
+  const int h = (int)(lane - seg * p.V);
+  const long long begin = p.offsets[seg], end = p.offsets[seg + 1];
+  const double g = p.gamma[h], lam = p.lambda[h], gl = __dmul_rn(g, lam);
+  const bool skips = p.steps_elapsed != nullptr;
+  double carry = 0.0;
+  float v_next = p.next_values[seg * p.V + h];
+  bool start_next = p.next_starts[seg] != 0;
+  for (long long t = end - 1; t >= begin; --t) {
+    const float r = p.rewards[t * p.V + h], v = p.values[t * p.V + h];
+    double adv;
+    if (skips) {
+      // the step after a finished trajectory has value 0; every product is float64 (numpy scalar gamma^k)
+      const double gk = pow(g, (double)p.steps_elapsed[t]);
+      const double nv = (t == end - 1 && start_next) ? 0.0 : (double)v_next;
+      const double delta = __dsub_rn(__dadd_rn((double)r, __dmul_rn(gk, nv)), (double)v);
+      carry = __dadd_rn(delta, __dmul_rn(__dmul_rn(gk, lam), carry));
+      adv = carry;
+    } else {
+      const double alive = start_next ? 0.0 : 1.0;
+      const double boot = p.gamma_is_scalar ? __dmul_rn((double)__fmul_rn((float)g, v_next), alive)
+                                            : __dmul_rn(__dmul_rn(g, (double)v_next), alive);
+      const double delta = __dsub_rn(__dadd_rn((double)r, boot), (double)v);
+      carry = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, alive), carry));
+      adv = carry;
+      start_next = p.episode_starts[t] != 0;
+    }
+    const float a32 = __double2float_rn(adv);
+    p.advantages[t * p.V + h] = a32;
+    if (p.returns) p.returns[t * p.V + h] = __fadd_rn(a32, v);
+    v_next = v;
+  }
+}
+
+}  // namespace b200rl
+
+extern "C" int b200rl_gae_segments_f32(const float* rewards, const float* values, const uint8_t* episode_starts,
+                                       const int32_t* steps_elapsed, const int64_t* seg_offsets,
+                                       const uint8_t* next_episode_starts, const float* next_values,
+                                       const double* gamma_host, const double* gae_lambda_host, int gamma_is_scalar,
+                                       float* advantages, float* returns, int64_t n_segments, int64_t V,
+                                       b200rl_stream_t stream) {
+  using namespace b200rl;
+  B200RL_REQUIRE(rewards && values && seg_offsets && next_episode_starts && next_values && advantages,
+                 "gae_segments: null pointer");
+  B200RL_REQUIRE((episode_starts != nullptr) != (steps_elapsed != nullptr),
+                 "gae_segments: pass episode_starts (trajectory GAE) or steps_elapsed (discrete skips), not both");
+  B200RL_REQUIRE(gamma_host && gae_lambda_host && n_segments >= 0 && V >= 1, "gae_segments: bad arguments");
+  B200RL_UNSUPPORTED(V > B200RL_MAX_VALUE_HEADS, "gae_segments: V=%lld exceeds %d", (long long)V, B200RL_MAX_VALUE_HEADS);
+  if (n_segments == 0) return B200RL_OK;
+  SegParams p{};
+  p.rewards = rewards, p.values = values, p.episode_starts = episode_starts, p.steps_elapsed = steps_elapsed;
+  p.offsets = reinterpret_cast<const long long*>(seg_offsets), p.next_starts = next_episode_starts;
+  p.next_values = next_values, p.advantages = advantages, p.returns = returns;
+  p.n_seg = n_segments, p.V = V, p.gamma_is_scalar = gamma_is_scalar;
+  for (int v = 0; v < V; ++v) p.gamma[v] = gamma_host[v], p.lambda[v] = gae_lambda_host[v];
+  const long long lanes = n_segments * V;
+  gae_segments_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+  return check_launch("gae_segments");
+}

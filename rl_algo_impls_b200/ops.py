@@ -154,6 +154,49 @@ def gae_scan(
     return adv, ret
 
 
+def gae_segments(
+    rewards: torch.Tensor,
+    values: torch.Tensor,
+    seg_offsets: torch.Tensor,
+    next_episode_starts: torch.Tensor,
+    next_values: torch.Tensor,
+    gamma: NumOrArray,
+    gae_lambda: NumOrArray,
+    episode_starts: Optional[torch.Tensor] = None,
+    steps_elapsed: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """advantages, returns over ragged trajectories concatenated along axis 0 ([total] or [total, V]):
+    `episode_starts` -> the reference's per-Trajectory compute_advantages (rollout/trajectory.py:56-95),
+    `steps_elapsed`  -> the discrete-skips recurrence (discrete_skips_trajectory_builder.py:84-100)."""
+    _cuda(rewards, torch.float32, "rewards"), _cuda(values, torch.float32, "values")
+    _cuda(next_values, torch.float32, "next_values"), _cuda(seg_offsets, torch.int64, "seg_offsets")
+    if (episode_starts is None) == (steps_elapsed is None):
+        raise ValueError("pass exactly one of episode_starts / steps_elapsed")
+    total = rewards.shape[0]
+    V = rewards.numel() // max(total, 1) if total else (next_values.numel() // max(seg_offsets.numel() - 1, 1))
+    n_seg = seg_offsets.numel() - 1
+    nes = _as_u8(next_episode_starts, "next_episode_starts")
+    es = _as_u8(episode_starts, "episode_starts") if episode_starts is not None else None
+    if steps_elapsed is not None:
+        _cuda(steps_elapsed, torch.int32, "steps_elapsed")
+    gamma_is_scalar = not isinstance(gamma, (np.ndarray, list, tuple))
+
+    def per_head(x):
+        a = np.asarray(x, dtype=np.float64).reshape(-1)
+        a = np.repeat(a, V) if a.size == 1 else a
+        return (C.c_double * V)(*a.tolist())
+
+    adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+    if total == 0 or n_seg <= 0:
+        return adv, ret
+    rc = _call("b200rl_gae_segments_f32", 1, _lib.lib().b200rl_gae_segments_f32, rewards.data_ptr(), values.data_ptr(),
+               _ptr(es), _ptr(steps_elapsed), seg_offsets.data_ptr(), nes.data_ptr(), next_values.data_ptr(),
+               per_head(gamma), per_head(gae_lambda), int(gamma_is_scalar), adv.data_ptr(), ret.data_ptr(), n_seg, V,
+               _stream())
+    check(rc, "b200rl_gae_segments_f32")
+    return adv, ret
+
+
 # ------------------------------------------------------------------------------------------------
 # K2
 def adv_moments(

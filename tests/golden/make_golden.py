@@ -420,6 +420,55 @@ def golden_a2c():
         save("a2c_" + name, **out)
 
 
+def golden_trajectories():
+    """Ragged trajectories through the live reference's TrajectoryBuilder.trajectory (rollout/trajectory.py)
+    and DiscreteSkipsTrajectoryBuilder.trajectory (rollout/discrete_skips_trajectory_builder.py)."""
+    from rl_algo_impls.rollout.discrete_skips_trajectory_builder import DiscreteSkipsTrajectoryBuilder
+    from rl_algo_impls.rollout.trajectory import TrajectoryBuilder
+
+    from oracle.gae import discrete_skips_advantages
+
+    rng = np.random.default_rng(33)
+    out = {}
+    for tag, V, gamma, lam in (("scalar", 1, 0.99, 0.95), ("heads", 3, np.array([1.0, 0.99, 0.9]), np.array([0.95, 0.9, 0.8]))):
+        lengths = [1, 7, 12, 3, 30]
+        shape = () if V == 1 else (V,)
+        cat = {k: [] for k in ("rewards", "values", "starts", "steps", "adv", "skip_adv", "skip_rewards")}
+        nxt_v, nxt_d, skip_done = [], [], []
+        for L in lengths:
+            rew = rng.standard_normal((L,) + shape).astype(np.float32)
+            val = rng.standard_normal((L,) + shape).astype(np.float32)
+            dones = rng.random(L) < 0.15
+            next_values = rng.standard_normal(shape).astype(np.float32)
+            tb = TrajectoryBuilder()
+            for t in range(L):
+                tb.add(np.zeros(2, np.float32), rew[t], bool(dones[t]), val[t], 0.0, np.zeros(1, np.int64), None)
+            traj = tb.trajectory(gamma, lam, next_values=next_values)
+            starts = np.concatenate([[True], dones[:-1]])
+            exact(gae_advantages(rew, val, starts, np.array(dones[-1]), next_values, gamma, lam), traj.advantages,
+                  f"trajectory GAE {tag} L={L}")
+            # discrete skips: every kept step absorbed k - 1 skipped env steps
+            steps = rng.integers(1, 5, size=L).astype(np.int32)
+            done = bool(rng.random() < 0.5)
+            sb = DiscreteSkipsTrajectoryBuilder()
+            sb.obs = [np.zeros(2, np.float32)] * L
+            sb.rewards, sb.values = list(rew), list(val)
+            sb.logprobs, sb.actions, sb.action_masks = [0.0] * L, [np.zeros(1, np.int64)] * L, [None] * L
+            sb.steps_elapsed, sb.done = list(steps), done
+            straj = sb.trajectory(gamma, lam, next_values=None if done else next_values)
+            exact(discrete_skips_advantages(rew, val, steps, done, next_values, gamma, lam), straj.advantages,
+                  f"discrete skips {tag} L={L}")
+            cat["rewards"].append(rew), cat["values"].append(val), cat["starts"].append(starts), cat["steps"].append(steps)
+            cat["adv"].append(traj.advantages), cat["skip_adv"].append(straj.advantages)
+            nxt_v.append(next_values), nxt_d.append(dones[-1]), skip_done.append(done)
+        out.update({f"{tag}.{k}": np.concatenate(v) for k, v in cat.items() if v})
+        out[f"{tag}.offsets"] = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+        out[f"{tag}.next_values"] = np.stack(nxt_v)
+        out[f"{tag}.next_starts"], out[f"{tag}.skip_done"] = np.asarray(nxt_d), np.asarray(skip_done)
+        out[f"{tag}.gamma"], out[f"{tag}.gae_lambda"] = np.asarray(gamma), np.asarray(lam)
+    save("trajectories", **out)
+
+
 def golden_normalizers():
     """NormalizeObservation / NormalizeReward of the live reference over a few env steps."""
     from rl_algo_impls.wrappers.normalize import NormalizeObservation as RefNormObs
@@ -464,6 +513,7 @@ def golden_normalizers():
 
 
 if __name__ == "__main__":
+    golden_trajectories()
     golden_a2c()
     golden_normalizers()
     golden_gae()

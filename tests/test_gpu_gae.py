@@ -82,3 +82,24 @@ def test_gae_empty(cuda):
     adv, ret = ops.gae_scan(z, z, torch.empty((0, 4), dtype=torch.bool, device=cuda),
                             torch.zeros(4, dtype=torch.bool, device=cuda), torch.zeros(4, device=cuda), 0.99, 0.95)
     assert adv.shape == (0, 4)
+
+
+@pytest.mark.parametrize("tag", ["scalar", "heads"])
+def test_segmented_gae_vs_reference_fixture(cuda, tag):
+    """K1b: ragged trajectories in one launch vs the live reference's TrajectoryBuilder.trajectory
+    (bit-exact) and DiscreteSkipsTrajectoryBuilder.trajectory (gamma ** steps_elapsed; float64 pow, 1e-6)."""
+    from rl_algo_impls_b200 import ops
+    from tests.test_oracle_golden import load
+
+    z = load("trajectories")
+    g = lambda k: z[f"{tag}.{k}"]
+    t = lambda k: torch.from_numpy(np.ascontiguousarray(g(k))).to(cuda)
+    scalar = g("gamma").ndim == 0
+    gamma, lam = (float(g("gamma")), float(g("gae_lambda"))) if scalar else (g("gamma"), g("gae_lambda"))
+    adv, ret = ops.gae_segments(t("rewards"), t("values"), t("offsets"), t("next_starts"), t("next_values"), gamma, lam,
+                                episode_starts=t("starts"))
+    np.testing.assert_array_equal(adv.cpu().numpy(), g("adv"))
+    np.testing.assert_array_equal(ret.cpu().numpy(), g("adv") + g("values"))
+    sk, _ = ops.gae_segments(t("rewards"), t("values"), t("offsets"), t("skip_done"), t("next_values"), gamma, lam,
+                             steps_elapsed=t("steps"))
+    np.testing.assert_allclose(sk.cpu().numpy(), g("skip_adv"), rtol=1e-6, atol=1e-6)

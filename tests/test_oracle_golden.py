@@ -199,3 +199,22 @@ def test_oracle_a2c_iteration_reproduces_the_reference(name):
         np.testing.assert_array_equal(v.numpy(), z[f"final.{k}"], err_msg=k)
     for k in ("loss", "pi_loss", "entropy_loss", "explained_var"):
         assert np.float64(stats[k]) == z[f"stats.{k}"], k
+
+
+@pytest.mark.parametrize("tag", ["scalar", "heads"])
+def test_trajectory_gae_matches_the_reference(tag):
+    """oracle GAE over ragged trajectories (TrajectoryBuilder / DiscreteSkipsTrajectoryBuilder of the reference)."""
+    from oracle.gae import discrete_skips_advantages
+
+    z = load("trajectories")
+    g = lambda k: z[f"{tag}.{k}"]
+    gamma, lam = (float(g("gamma")), float(g("gae_lambda"))) if g("gamma").ndim == 0 else (g("gamma"), g("gae_lambda"))
+    off = g("offsets")
+    for s in range(len(off) - 1):
+        sl = slice(off[s], off[s + 1])
+        adv = gae_advantages(g("rewards")[sl], g("values")[sl], g("starts")[sl], np.array(g("next_starts")[s]),
+                             g("next_values")[s], gamma, lam)
+        np.testing.assert_array_equal(adv, g("adv")[sl])
+        sk = discrete_skips_advantages(g("rewards")[sl], g("values")[sl], g("steps")[sl], bool(g("skip_done")[s]),
+                                       g("next_values")[s], gamma, lam)
+        np.testing.assert_array_equal(sk, g("skip_adv")[sl])
