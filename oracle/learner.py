@@ -268,3 +268,39 @@ def a2c_learn_iteration(policy: OraclePolicy, optimizer: torch.optim.Optimizer, 
     var_y = np.var(y_true).item()
     stats["explained_var"] = np.nan if var_y == 0 else 1 - np.var(y_true - y_pred).item() / var_y
     return stats
+
+
+def acbc_learn_iteration(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict, batch_size: int, n_epochs: int,
+                         gamma, gae_lambda, vf_coef, max_grad_norm: float = 0.5, gradient_accumulation: bool = False) -> dict:
+    """One iteration of ACBC.learn (acbc/acbc.py:75-141) on a collected rollout."""
+    adv = gae_advantages(ro["rewards"], ro["values"], ro["episode_starts"], ro["next_episode_starts"],
+                         ro["next_values"], gamma, gae_lambda)
+    ret = gae_returns(adv, ro["values"])
+    b = dict(obs=_flat(ro["obs"]), actions=_flat(ro["actions"]), masks=_flat(ro["masks"]), returns=_flat(ret))
+    total = b["returns"].shape[0]
+    n_mb = total // batch_size + (1 if total % batch_size else 0)
+    vf = torch.tensor(np.asarray(vf_coef), dtype=torch.float32)
+    params = list(policy.parameters())
+    stats: List[dict] = []
+
+    def optimizer_step():
+        nn.utils.clip_grad_norm_(params, max_grad_norm)
+        optimizer.step()
+        optimizer.zero_grad(set_to_none=True)
+
+    for _ in range(n_epochs):
+        stats.clear()
+        for idx in minibatch_index_stream(total, batch_size, shuffle=not gradient_accumulation):
+            logp, _, v = policy.forward(b["obs"][idx], _take(b["actions"], idx), _take(b["masks"], idx))
+            pi_loss = -logp.mean()
+            v_loss = ((v - b["returns"][idx]) ** 2).mean(0)
+            loss = pi_loss + (vf * v_loss).sum()
+            if gradient_accumulation:
+                loss = loss / n_mb
+            loss.backward()
+            if not gradient_accumulation:
+                optimizer_step()
+            stats.append(dict(loss=loss.item(), pi_loss=pi_loss.item(), v_loss=v_loss.detach().numpy().copy()))
+        if gradient_accumulation:
+            optimizer_step()
+    return {k: np.mean([s[k] for s in stats], axis=0) for k in stats[0]}

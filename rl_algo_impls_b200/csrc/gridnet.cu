@@ -43,6 +43,8 @@ namespace b200rl {
 constexpr int kStreamBlock = 256;   // threads of the streaming kernel
 constexpr int kMaxPick = 4;
 constexpr int kStashCells = 512;    // unit cells whose (lse, entropy) are parked in shared memory
+constexpr int kStashCellsSelf = 64;  // ... in a self-streaming CTA (maps of <= 256 cells)
+constexpr size_t kMaxImageBytes = 40 * 1024;  // widest chunk mask (256 cells x S bytes) staged through shared memory
 
 enum GridMode { kFwd = 0, kBwd = 1, kPpo = 2 };
 
@@ -76,6 +78,7 @@ struct GridDev {
   int stash;         // unit cells with a shared-memory (lse, entropy) slot = min(HW, kStashCells)
   int G;             // lanes per cell group (power of two <= 32)
   int max_width;     // widest head block
+  int image_bytes;   // shared-memory mask image of a streaming CTA (0: masks too wide, plain loads)
   // workspace (written by the streaming kernel, read by the compute kernel)
   uint16_t* unit_list;   // [B][chunks * kChunkCells]  ascending cell ids per chunk
   int* unit_count;       // [B][chunks]
@@ -219,26 +222,63 @@ struct ChunkLists {
   long long pick_stride, pick_count_stride;
 };
 
+// Shared-memory staging of a streaming CTA.  `image` == nullptr selects the plain load / store path (mask
+// rows too wide for the staging buffer).
+struct StreamStage {
+  uint8_t* image;   // 16-byte aligned, >= chunk mask bytes + 32
+  uint8_t* zeros;   // kZeroBuf bytes, 16-byte aligned
+  uint64_t* bar;    // mbarrier the mask image completes on (phase 0; one chunk per CTA)
+};
+
+// Returns the skew of the mask image (byte k of the chunk's mask is image[skew + k]).
 template <typename LT, bool ZERO, int BLOCK>
-__device__ __forceinline__ void stream_chunk(const GridDev& G, long long b, int chunk, uint32_t* bitmap,
-                                             const ChunkLists& out) {
+__device__ __forceinline__ uint32_t stream_chunk(const GridDev& G, long long b, int chunk, uint32_t* bitmap,
+                                                 const ChunkLists& out, const StreamStage& st) {
   const int tid = threadIdx.x;
   const int cell0 = chunk * kChunkCells;
   const int cells = (int)min((long long)kChunkCells, G.HW - cell0);
   const long long row0 = b * G.HW + cell0;
   const uint8_t* g_mask = G.mask + row0 * G.S;
   const uint32_t mask_bytes = (uint32_t)cells * (uint32_t)G.S;
-
-  // the mask bytes are consumed right after the zero fill: start them towards L2 first
-  for (uint32_t o = (uint32_t)tid * 128u; o < mask_bytes; o += BLOCK * 128u) prefetch_l2(g_mask + o);
-  if (tid < kChunkCells / 32) bitmap[tid] = 0u;
-  if (ZERO)
-    zero_fill<BLOCK>(reinterpret_cast<uint8_t*>(static_cast<LT*>(G.dlogits) + row0 * G.Sp),
-              (uint32_t)cells * (uint32_t)G.Sp * (uint32_t)sizeof(LT));
-  __syncthreads();
-  scan_mask<BLOCK>(g_mask, mask_bytes, (uint32_t)G.S, bitmap,
-            RowPrefetch{reinterpret_cast<const uint8_t*>(static_cast<const LT*>(G.logits) + row0 * G.Sp),
-                        (uint32_t)G.Sp * (uint32_t)sizeof(LT)});
+  uint8_t* g_zero = reinterpret_cast<uint8_t*>(static_cast<LT*>(G.dlogits) + row0 * G.Sp);
+  const uint32_t zero_bytes = (uint32_t)cells * (uint32_t)G.Sp * (uint32_t)sizeof(LT);
+  const RowPrefetch pf{reinterpret_cast<const uint8_t*>(static_cast<const LT*>(G.logits) + row0 * G.Sp),
+                       (uint32_t)G.Sp * (uint32_t)sizeof(LT)};
+  uint32_t skew = 0;
+  if (st.image != nullptr) {
+    // TMA path: ONE bulk copy lands the chunk's mask bytes in shared memory while bulk copies of a zeroed
+    // shared buffer fill the chunk's dlogits; the threads only scan shared memory, one cell each.
+    skew = (uint32_t)(reinterpret_cast<uintptr_t>(g_mask) & 15u);
+    uint32_t head = skew ? 16u - skew : 0u;
+    if (head > mask_bytes) head = mask_bytes;
+    const uint32_t body = (mask_bytes - head) & ~15u;
+    const uint32_t tail = mask_bytes - head - body;
+    if (tid == 0) {
+      mbar_init(st.bar, 1);
+      fence_async_smem();
+      mbar_expect_tx(st.bar, body);
+      if (body) bulk_load(st.image + skew + head, g_mask + head, body, st.bar);
+    } else if (tid >= 32 && (uint32_t)tid < 32u + head) {
+      st.image[skew + tid - 32] = g_mask[tid - 32];
+    } else if (tid >= 64 && (uint32_t)tid < 64u + tail) {
+      st.image[skew + head + body + tid - 64] = g_mask[head + body + tid - 64];
+    }
+    if (ZERO) {
+      for (uint32_t i = tid; i < kZeroBuf / 16u; i += BLOCK) reinterpret_cast<uint4*>(st.zeros)[i] = make_uint4(0u, 0u, 0u, 0u);
+      fence_async_smem();
+    }
+    __syncthreads();  // barrier initialised, zero buffer and head / tail bytes in place
+    if (ZERO) zero_fill_bulk(g_zero, zero_bytes, st.zeros);
+    mbar_wait(st.bar, 0);
+    scan_cells_image<BLOCK>(st.image + skew, cells, (uint32_t)G.S, bitmap, pf);
+  } else {
+    // the mask bytes are consumed right after the zero fill: start them towards L2 first
+    for (uint32_t o = (uint32_t)tid * 128u; o < mask_bytes; o += BLOCK * 128u) prefetch_l2(g_mask + o);
+    if (tid < kChunkCells / 32) bitmap[tid] = 0u;
+    if (ZERO) zero_fill<BLOCK>(g_zero, zero_bytes);
+    __syncthreads();
+    scan_mask<BLOCK>(g_mask, mask_bytes, (uint32_t)G.S, bitmap, pf);
+  }
   __syncthreads();
   compact_cells(bitmap, (cells + 31) >> 5, out.unit, cell0, out.unit_count);
   // pick_position masks: one byte per cell, same compaction (no row prefetch: one logit per cell)
@@ -253,17 +293,22 @@ __device__ __forceinline__ void stream_chunk(const GridDev& G, long long b, int 
     compact_cells(bitmap, (cells + 31) >> 5, out.pick + kp * out.pick_stride, cell0,
                   out.pick_count + kp * out.pick_count_stride);
   }
+  return skew;
 }
 
 template <typename LT, bool ZERO>
 __global__ void __launch_bounds__(kStreamBlock) gridnet_stream_kernel(const __grid_constant__ GridDev G) {
+  extern __shared__ __align__(16) uint8_t stream_smem[];  // mask image (G.image_bytes; 0: plain path)
+  __shared__ __align__(16) uint8_t zeros[kZeroBuf];
+  __shared__ uint64_t bar;
   __shared__ uint32_t bitmap[kChunkCells / 32];
   const long long b = blockIdx.x / G.chunks;
   const int chunk = (int)(blockIdx.x - b * G.chunks);
   const ChunkLists out{G.unit_list + (b * G.chunks + chunk) * kChunkCells, G.unit_count + b * G.chunks + chunk,
                        G.pick_list + ((b * G.n_pick) * G.chunks + chunk) * kChunkCells,
                        G.pick_count + (b * G.n_pick) * G.chunks + chunk, (long long)G.chunks * kChunkCells, G.chunks};
-  stream_chunk<LT, ZERO, kStreamBlock>(G, b, chunk, bitmap, out);
+  stream_chunk<LT, ZERO, kStreamBlock>(G, b, chunk, bitmap, out, StreamStage{G.image_bytes ? stream_smem : nullptr, zeros, &bar});
+  if (ZERO && G.image_bytes && threadIdx.x == 0) bulk_wait_read();  // the zero buffer must outlive the copies that read it
 }
 
 // ---- C: compute kernel ---------------------------------------------------------------------------
@@ -299,28 +344,35 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
   __shared__ uint16_t s_list[SELF_STREAM ? kChunkCells : 1];
   __shared__ uint16_t s_plist[SELF_STREAM && PICK ? kMaxPick * kChunkCells : 1];
   __shared__ int s_counts[1 + kMaxPick];
-  if (SELF_STREAM) {  // the lists never leave the SM
-    const ChunkLists out{s_list, s_counts, s_plist, s_counts + 1, kChunkCells, 1};
-    stream_chunk<LT, MODE != kFwd, BLOCK>(G, b, 0, s_bitmap, out);
-    __syncthreads();
-  }
-
-  // dynamic shared memory: chunk-count prefixes | (log-sum-exp, entropy) stash of later passes
+  // dynamic shared memory: chunk-count prefixes | (log-sum-exp, entropy) stash of later passes | mask image
   int* prefix = reinterpret_cast<int*>(smem);                      // [chunks + 1]
   int* pick_prefix = prefix + (G.chunks + 1);                      // [n_pick][chunks + 1]
   float* s_lse = reinterpret_cast<float*>(smem + (((size_t)(G.chunks + 1) * (1 + kMaxPick) * 4 + 15) & ~(size_t)15));
   float* s_ent = s_lse + (size_t)G.stash * G.A;
+  uint8_t* s_image = reinterpret_cast<uint8_t*>(s_lse) + (((size_t)G.stash * G.A * 2 * sizeof(float) + 15) & ~(size_t)15);
 
   const LT* g_logits = static_cast<const LT*>(G.logits) + row0 * G.Sp;
   LT* g_out = static_cast<LT*>(G.dlogits) + row0 * G.Sp;
   const uint8_t* g_mask = G.mask + row0 * G.S;
+  __shared__ __align__(16) uint8_t s_zeros[SELF_STREAM && MODE != kFwd ? kZeroBuf : 16];
+  __shared__ uint64_t s_bar;
+  if (SELF_STREAM) {  // the lists never leave the SM
+    const ChunkLists out{s_list, s_counts, s_plist, s_counts + 1, kChunkCells, 1};
+    const uint32_t skew = stream_chunk<LT, MODE != kFwd, BLOCK>(G, b, 0, s_bitmap, out,
+                                                               StreamStage{G.image_bytes ? s_image : nullptr, s_zeros, &s_bar});
+    if (G.image_bytes) g_mask = s_image + skew;  // the unit cells re-read their mask bytes from the image
+    __syncthreads();
+  }
 
-  // the per-sample PPO scalars are consumed by one thread after the reductions: start pulling them now
+  // the per-sample PPO scalars are consumed by one thread after the reductions: start pulling them now; the
+  // advantage normaliser (mean, std + 1e-8) is derived from the float64 moments here, off the critical path
+  __shared__ float s_norm[2 * B200RL_MAX_VALUE_HEADS];
   if (MODE == kPpo) {
+    const int Vm = P.adv_mode == 3 ? 1 : P.adv_v;
+    if (P.adv_mode != 0 && tid >= 64 && tid < 64 + Vm) ppo_norm_pair(P, Vm, tid - 64, s_norm);
     if (tid == 0) {
       prefetch_l1(P.old_logp + b);
       prefetch_l1(P.adv + b * P.adv_v);
-      if (P.adv_mode) prefetch_l1(P.norm);
     } else if (tid >= 32 && tid < 32 + P.V) {
       const long long o = b * P.V + (tid - 32);
       prefetch_l1(P.new_values + o), prefetch_l1(P.old_values + o), prefetch_l1(P.returns + o);
@@ -473,7 +525,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
       s_bcast[0] = G.dlogp_in[b], s_bcast[1] = G.dent_in[b];
     } else {
       // ---- 5. PPO scalar stage ------------------------------------------------------------------------------
-      PolicyTerms t = ppo_policy_terms(P, b, tot_logp);
+      PolicyTerms t = ppo_policy_terms(P, b, tot_logp, s_norm);
       s_bcast[0] = t.dlogp, s_bcast[1] = ppo_dentropy(P, 1);
       double* row = P.partials + b * ppo_nstat(P.V);
       row[0] = t.surrogate, row[1] = tot_ent, row[2] = t.kl, row[3] = t.clipped, row[4] = t.teacher;
@@ -488,6 +540,10 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
     row[kPolicyStats + v] = r.x, row[kPolicyStats + P.V + v] = r.y;
   }
   if (MODE == kFwd) return;
+  if (SELF_STREAM && G.image_bytes && tid == 0) {  // the zero fill of this sample's rows must have landed
+    bulk_wait_all();
+    fence_async_all();
+  }
   __syncthreads();
   dlogp = s_bcast[0], dent = s_bcast[1];
 
@@ -605,6 +661,9 @@ static size_t grid_workspace_bytes(long long B, long long HW, int n_pick) {
 static int bind_workspace(GridDev* G, void* workspace, size_t workspace_bytes, const char* who) {
   G->chunks = (int)((G->HW + kChunkCells - 1) / kChunkCells);
   G->stash = (int)(G->HW < kStashCells ? G->HW : kStashCells);
+  if (G->chunks == 1 && G->stash > kStashCellsSelf) G->stash = kStashCellsSelf;  // self-streaming CTAs: shared memory buys CTAs / SM
+  const size_t image = align16((size_t)(G->HW < kChunkCells ? G->HW : kChunkCells) * G->S) + 32;
+  G->image_bytes = image <= kMaxImageBytes ? (int)image : 0;
   B200RL_REQUIRE(workspace != nullptr && workspace_bytes >= grid_workspace_bytes(G->B, G->HW, G->n_pick),
                  "%s: workspace too small (%zu < %zu bytes)", who, workspace_bytes,
                  grid_workspace_bytes(G->B, G->HW, G->n_pick));
@@ -617,8 +676,9 @@ static int bind_workspace(GridDev* G, void* workspace, size_t workspace_bytes, c
   return B200RL_OK;
 }
 
-static size_t compute_smem(const GridDev& G) {
-  return align16((size_t)(G.chunks + 1) * (1 + kMaxPick) * 4) + (size_t)G.stash * G.A * 2 * sizeof(float);
+static size_t compute_smem(const GridDev& G, bool self_stream) {
+  return align16((size_t)(G.chunks + 1) * (1 + kMaxPick) * 4) + align16((size_t)G.stash * G.A * 2 * sizeof(float)) +
+         (self_stream ? (size_t)G.image_bytes : 0);
 }
 
 template <int MODE, typename LT, int PMAX, bool PICK, bool SELF_STREAM>
@@ -627,7 +687,7 @@ static int launch_compute(GridDev& G, const PpoDev& P, cudaStream_t stream) {
   // launch of the split path gets 256 threads (more lane groups per sample)
   constexpr int BLOCK = SELF_STREAM ? 128 : 256;
   auto kernel = gridnet_kernel<MODE, LT, PMAX, PICK, SELF_STREAM, BLOCK>;
-  const size_t smem = compute_smem(G);
+  const size_t smem = compute_smem(G, SELF_STREAM);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -647,8 +707,8 @@ static int launch_pair(GridDev& G, const PpoDev& P, cudaStream_t stream) {
     return B200RL_EUNSUPPORTED;
   }
   if (G.chunks == 1) return launch_compute<MODE, LT, PMAX, PICK, true>(G, P, stream);
-  if (MODE == kFwd) gridnet_stream_kernel<LT, false><<<(unsigned)stream_ctas, kStreamBlock, 0, stream>>>(G);
-  else gridnet_stream_kernel<LT, true><<<(unsigned)stream_ctas, kStreamBlock, 0, stream>>>(G);
+  if (MODE == kFwd) gridnet_stream_kernel<LT, false><<<(unsigned)stream_ctas, kStreamBlock, G.image_bytes, stream>>>(G);
+  else gridnet_stream_kernel<LT, true><<<(unsigned)stream_ctas, kStreamBlock, G.image_bytes, stream>>>(G);
   int rc = check_launch("gridnet_stream");
   if (rc) return rc;
   return launch_compute<MODE, LT, PMAX, PICK, false>(G, P, stream);
@@ -772,9 +832,7 @@ extern "C" int b200rl_ppo_gridnet_loss(const b200rl_gridnet_desc* d, const void*
   if (rc) return rc;
   G.dlogits = dlogits, G.logp = logp_out, G.entropy = entropy_out;
   cudaStream_t s = (cudaStream_t)stream;
-  rc = ppo_launch_prepare(P, s);
-  if (rc) return rc;
-  rc = launch_mode<kPpo>(G, P, d->nvec_host, d->logits_dtype, s);
+  rc = launch_mode<kPpo>(G, P, d->nvec_host, d->logits_dtype, s);  // derives the advantage normaliser itself
   if (rc) return rc;
   return ppo_launch_finalize(P, G.B, 1, s);
 }

@@ -2,6 +2,7 @@
 // sampler (gridnet_sample.cu): 128-bit zero fill, 128-bit scan of the action-mask bytes into a
 // shared bitmap of non-empty cells, and the bitmap -> ascending cell list compaction.
 #pragma once
+#include "bulk.cuh"
 #include "common.cuh"
 
 namespace b200rl {
@@ -25,6 +26,26 @@ __device__ __forceinline__ void zero_fill(uint8_t* dst, uint32_t bytes) {
   for (; i < n4; i += BLOCK) d4[i] = z;
   const uint32_t done = head + (n4 << 4);
   if (tid < bytes - done) dst[done + tid] = 0;
+}
+
+// Same fill through the TMA: the unaligned head / tail bytes with plain stores, the 16-byte aligned body as
+// bulk copies of a zeroed shared buffer (`zeros`, kZeroBuf bytes, already fenced towards the async proxy
+// and followed by a CTA barrier).  Thread 0 issues and commits; the caller waits (bulk_wait_*).
+constexpr uint32_t kZeroBuf = 2048;
+__device__ __forceinline__ void zero_fill_bulk(uint8_t* dst, uint32_t bytes, const uint8_t* zeros) {
+  const uint32_t tid = threadIdx.x;
+  uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+  if (head > bytes) head = bytes;
+  const uint32_t body = (bytes - head) & ~15u;
+  const uint32_t tail = bytes - head - body;
+  if (tid == 0) {
+    for (uint32_t o = 0; o < body; o += kZeroBuf) bulk_store(dst + head + o, zeros, min(kZeroBuf, body - o));
+    bulk_commit();
+  } else if (tid >= 32u && tid < 32u + head) {
+    dst[tid - 32u] = 0;
+  } else if (tid >= 64u && tid < 64u + tail) {
+    dst[head + body + tid - 64u] = 0;
+  }
 }
 
 // Row prefetch context: the logits row of a flagged cell is wanted a few microseconds from now.
@@ -108,6 +129,41 @@ __device__ __forceinline__ void scan_mask(const uint8_t* mask, uint32_t bytes, u
   }
   const uint32_t done = head + (n4 << 4);
   if (tid < bytes - done && mask[done + tid]) flag_cell(bitmap, (done + tid) / S, pf);
+}
+
+// The scan over a shared-memory image of the chunk's mask (landed there by a bulk copy): thread t ORs the S
+// bytes of cells t, t + BLOCK, ... with aligned 32-bit loads (edge words masked), and one ballot per warp IS a
+// word of the bitmap -- no atomics, no per-word cell arithmetic.  `m` = byte 0 of the chunk's first cell.
+template <int BLOCK>
+__device__ __forceinline__ void scan_cells_image(const uint8_t* m, int cells, uint32_t S, uint32_t* bitmap,
+                                                 const RowPrefetch& pf) {
+  static_assert(kChunkCells % BLOCK == 0 && BLOCK % 32 == 0, "one ballot per bitmap word");
+  const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll 1
+  for (int c = threadIdx.x; c < kChunkCells; c += BLOCK) {  // warp-uniform trip count
+    uint32_t any = 0u;
+    if (c < cells) {
+      const uintptr_t lo = reinterpret_cast<uintptr_t>(m) + (uintptr_t)c * S, hi = lo + S;  // [lo, hi)
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(lo & ~(uintptr_t)3);
+      const uint32_t* w_end = reinterpret_cast<const uint32_t*>((hi + 3) & ~(uintptr_t)3);
+      const uint32_t lead = (uint32_t)(lo & 3u), trail = (uint32_t)((0u - (uint32_t)hi) & 3u);  // bytes outside the row
+      const int n = (int)(w_end - w);
+      uint32_t first = w[0] & (0xFFFFFFFFu << (8u * lead));  // little-endian: low bytes come first
+      if (n == 1) {
+        any = first & (0xFFFFFFFFu >> (8u * trail));
+      } else {
+        any = first | (w[n - 1] & (0xFFFFFFFFu >> (8u * trail)));
+#pragma unroll 4
+        for (int k = 1; k < n - 1; ++k) any |= w[k];
+      }
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, any != 0u);
+    if (lane == 0) bitmap[c >> 5] = bits;
+    if (any != 0u && pf.logits != nullptr) {  // pull the unit cell's logits row towards L2
+      const uint8_t* row = pf.logits + (size_t)c * pf.row_bytes;
+      for (uint32_t o = 0; o < pf.row_bytes + 127u; o += 128u) prefetch_l2(row + min(o, pf.row_bytes - 1u));
+    }
+  }
 }
 
 // warp 0: bitmap -> ascending list of flagged cells (ids offset by `base`); count through *out_count

@@ -44,17 +44,9 @@ int ppo_make_dev(const b200rl_ppo_args* a, long long B, void* workspace, size_t 
   return B200RL_OK;
 }
 
-// (sum, sum of squares, count) in f64 -> (mean, unbiased std + 1e-8) in f32, exactly the values the
-// reference's mb_adv.mean(0) / mb_adv.std(0) + 1e-8 feed into the division (ppo.py:307-316).
 __global__ void ppo_prepare_kernel(PpoDev P) {
   const int Vm = P.adv_mode == 3 ? 1 : P.adv_v;
-  const int v = threadIdx.x;
-  if (v >= Vm) return;
-  const double n = P.moments[2 * Vm], mean = P.moments[v] / n;
-  const double var = fmax(0.0, (P.moments[Vm + v] - P.moments[v] * mean) / (n - 1.0));
-  float* norm = const_cast<float*>(P.norm);
-  norm[v] = (float)mean;
-  norm[Vm + v] = (float)sqrt(var) + 1e-8f;
+  if ((int)threadIdx.x < Vm) ppo_norm_pair(P, Vm, threadIdx.x, const_cast<float*>(P.norm));
 }
 
 int ppo_launch_prepare(const PpoDev& P, cudaStream_t stream) {

@@ -50,7 +50,8 @@ __host__ __device__ inline int ppo_nstat(int V) { return kPolicyStats + 2 * V; }
 // (A - mean) / (std + 1e-8) etc. for one sample, then the reward-weight contraction.  The float64
 // moments were turned into float (mean, denominator) pairs once per launch (ppo_prepare_kernel),
 // so the per-sample path has no double-precision division or square root on it.
-__device__ __forceinline__ float ppo_sample_advantage(const PpoDev& P, long long i) {
+// `norm` is P.norm (written by ppo_prepare_kernel) or a CTA-local copy made with ppo_norm_pair.
+__device__ __forceinline__ float ppo_sample_advantage(const PpoDev& P, long long i, const float* norm) {
   const float* row = P.adv + i * P.adv_v;
   if (P.adv_mode == 3) {
     float a = row[0];
@@ -59,15 +60,15 @@ __device__ __forceinline__ float ppo_sample_advantage(const PpoDev& P, long long
 #pragma unroll 1
       for (int v = 0; v < P.adv_v; ++v) a = fmaf(row[v], P.w[v], a);
     }
-    return (a - P.norm[0]) / P.norm[1];
+    return (a - norm[0]) / norm[1];
   }
   float acc = 0.f;
 #pragma unroll 1
   for (int v = 0; v < P.adv_v; ++v) {
     float a = row[v];
     if (P.adv_mode != 0) {
-      const float denom = P.norm[P.adv_v + v];
-      a = (P.adv_mode == 1) ? (a - P.norm[v]) / denom : a / denom;
+      const float denom = norm[P.adv_v + v];
+      a = (P.adv_mode == 1) ? (a - norm[v]) / denom : a / denom;
     }
     if (!P.has_w) return a;  // adv_v == 1 (checked on the host)
     acc = fmaf(a, P.w[v], acc);
@@ -85,8 +86,9 @@ struct PolicyTerms {
 
 // new_logp arrives in float64 when the caller summed it that way (GridNet: hundreds of per-cell
 // terms); the subtraction is exact in float64 and rounds once, like an f32 subtraction of f32 inputs.
-__device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long long i, double new_logp) {
-  const float A = ppo_sample_advantage(P, i);
+__device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long long i, double new_logp,
+                                                        const float* norm) {
+  const float A = ppo_sample_advantage(P, i, norm);
   const float logratio = (float)(new_logp - (double)P.old_logp[i]);
   const float ratio = expf(logratio);
   const float cr = fminf(fmaxf(ratio, P.ratio_lo), P.ratio_hi);
@@ -130,6 +132,20 @@ __device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long lo
   return t;
 }
 
+__device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long long i, double new_logp) {
+  return ppo_policy_terms(P, i, new_logp, P.norm);
+}
+
+// (sum, sum of squares, count) in f64 -> (mean, unbiased std + 1e-8) in f32 for head v, exactly the values the
+// reference's mb_adv.mean(0) / mb_adv.std(0) + 1e-8 feed into the division (ppo.py:307-316).  Vm = heads
+// the moments were taken over (1 for the after-weighting mode).
+__device__ __forceinline__ void ppo_norm_pair(const PpoDev& P, int Vm, int v, float* norm) {
+  const double n = P.moments[2 * Vm], mean = P.moments[v] / n;
+  const double var = fmax(0.0, (P.moments[Vm + v] - P.moments[v] * mean) / (n - 1.0));
+  norm[v] = (float)mean;
+  norm[Vm + v] = (float)sqrt(var) + 1e-8f;
+}
+
 // d loss / d entropy element (entropy_loss = -mean over B * ent_d elements)
 __device__ __forceinline__ float ppo_dentropy(const PpoDev& P, int ent_d) {
   return -(P.ent_coef * P.loss_scale) / ((float)P.B * (float)ent_d);
@@ -162,23 +178,34 @@ __device__ __forceinline__ float2 ppo_value_terms(const PpoDev& P, long long i, 
   return make_float2(vl, clipped);
 }
 
-// partials [rows][4 + 2V] -> stats_out, by ONE block (any size that is a multiple of 32): thread t sums
-// rows t, t + blockDim, ... of every column, warps combine through `scratch` ([nwarps][ns] doubles of
-// shared memory), thread c < ns finishes column c.  Fixed order => deterministic.
+// partials [rows][5 + 2V] -> stats_out, by ONE block (any size that is a multiple of 32): thread t sums rows
+// t, t + blockDim, ... -- a row's columns are adjacent, so every load of a tile of 8 columns is in flight
+// at once -- warps combine through `scratch` ([nwarps][ns] doubles of shared memory), thread c < ns finishes
+// column c.  Fixed order => deterministic.
 __device__ __forceinline__ void ppo_finalize_block(const PpoDev& P, long long rows, int ent_d, double* scratch) {
   const int ns = ppo_nstat(P.V);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   __syncthreads();  // scratch may alias shared memory that was in use
-  for (int c = 0; c < ns; ++c) {
-    double a = 0.0;
-    for (long long r = tid; r < rows; r += blockDim.x) a += P.partials[r * ns + c];
+  for (int c0 = 0; c0 < ns; c0 += 8) {
+    double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (long long r = tid; r < rows; r += blockDim.x) {
+      const double* row = P.partials + r * ns + c0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      int lo = __double2loint(a), hi = __double2hiint(a);
-      lo = __shfl_xor_sync(0xffffffffu, lo, o), hi = __shfl_xor_sync(0xffffffffu, hi, o);
-      a += __hiloint2double(hi, lo);
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < ns) a[j] += row[j];
     }
-    if (lane == 0) scratch[warp * ns + c] = a;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (c0 + j >= ns) break;
+      double x = a[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        int lo = __double2loint(x), hi = __double2hiint(x);
+        lo = __shfl_xor_sync(0xffffffffu, lo, o), hi = __shfl_xor_sync(0xffffffffu, hi, o);
+        x += __hiloint2double(hi, lo);
+      }
+      if (lane == 0) scratch[warp * ns + c0 + j] = x;
+    }
   }
   __syncthreads();
   __shared__ double tot[kPolicyStats + 2 * B200RL_MAX_VALUE_HEADS];

@@ -24,6 +24,7 @@ from tests.golden import _ref_shim  # noqa: E402
 _ref_shim.install()
 
 from rl_algo_impls.a2c.a2c import A2C as RefA2C  # noqa: E402
+from rl_algo_impls.acbc.acbc import ACBC as RefACBC  # noqa: E402
 from rl_algo_impls.loss.teacher_kl_loss import TeacherKLLoss as RefTeacherKLLoss  # noqa: E402
 from rl_algo_impls.ppo.ppo import PPO as RefPPO  # noqa: E402
 from rl_algo_impls.rollout.vec_rollout import VecRollout as RefVecRollout  # noqa: E402
@@ -420,6 +421,57 @@ def golden_a2c():
         save("a2c_" + name, **out)
 
 
+def golden_acbc():
+    """One ACBC.learn iteration of the live reference (acbc/acbc.py:75-141) on the microrts A2C rollout shape."""
+    from tests.golden.make_golden_cases import A2C_CASES, make_net_for
+
+    case = A2C_CASES["microrts"]
+    seed = 60
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    make_net = make_net_for(case)
+    net = make_net()
+    init = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    T, N, nvec, side, gates = case["T"], case["N"], case["nvec"], case["side"], case["gates"]
+    HW = side * side
+    ro = gae_inputs(seed + 1, T, N, 1, 0.1)
+    ro["obs"] = rng.standard_normal((T, N) + case["obs_shape"], dtype=np.float32)
+    g = gridnet_inputs(seed + 2, T * N, HW, nvec, 0, 0.2)
+    ro["actions"], ro["masks"] = g["actions"].reshape(T, N, HW, len(nvec)), g["mask"].reshape(T, N, HW, -1)
+    ro["logprobs"] = np.zeros((T, N), np.float32)
+    pol = _RefPolicy(net, "gridnet", nvec, HW, gates)
+
+    def ref_rollout(gamma, gae_lambda):
+        return RefVecRollout(torch.device("cpu"), ro["next_episode_starts"], ro["next_values"], ro["obs"], ro["actions"],
+                             ro["rewards"], ro["episode_starts"], ro["values"], ro["logprobs"], ro["masks"], gamma,
+                             gae_lambda, subaction_mask=gates, action_plane_space=_ref_shim.MultiDiscrete(nvec))
+
+    kw = dict(learning_rate=1e-3, batch_size=8, n_epochs=2, gamma=0.99, gae_lambda=0.95, vf_coef=0.25)
+    writer = _Writer()
+    algo = RefACBC(pol, torch.device("cpu"), writer, **kw)
+    torch.manual_seed(seed + 100)
+    algo.learn(T * N, _Gen(ref_rollout, N))
+    final = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net2 = make_net()
+    net2.load_state_dict(init)
+    opol = olearn.OraclePolicy(net2, "gridnet", nvec, HW, gates)
+    opt = torch.optim.Adam(net2.parameters(), lr=kw["learning_rate"])
+    torch.manual_seed(seed + 100)
+    ostats = olearn.acbc_learn_iteration(opol, opt, ro, kw["batch_size"], kw["n_epochs"], kw["gamma"], kw["gae_lambda"],
+                                         kw["vf_coef"])
+    for k, v in net2.state_dict().items():
+        exact(v, final[k], f"acbc param {k}")
+    for k in ("loss", "pi_loss"):
+        exact(np.float64(ostats[k]), np.float64(writer.scalars[f"losses/{k}"]), f"acbc stat {k}")
+    out = {f"init.{k}": v.numpy() for k, v in init.items()}
+    out.update({f"final.{k}": v.numpy() for k, v in final.items()})
+    out.update({f"ro.{k}": v for k, v in ro.items() if v is not None})
+    out.update({f"stats.{k}": np.float64(writer.scalars[f"losses/{k}"]) for k in ("loss", "pi_loss")})
+    out.update({f"hp.{k}": np.asarray(v) for k, v in kw.items()})
+    out["seed"] = np.asarray(seed)
+    save("acbc_microrts", **out)
+
+
 def golden_trajectories():
     """Ragged trajectories through the live reference's TrajectoryBuilder.trajectory (rollout/trajectory.py)
     and DiscreteSkipsTrajectoryBuilder.trajectory (rollout/discrete_skips_trajectory_builder.py)."""
@@ -513,6 +565,7 @@ def golden_normalizers():
 
 
 if __name__ == "__main__":
+    golden_acbc()
     golden_trajectories()
     golden_a2c()
     golden_normalizers()

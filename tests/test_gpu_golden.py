@@ -211,6 +211,45 @@ def test_a2c_iteration_vs_reference_fixture(cuda, name):
         assert rms_err <= 1e-2 * rms_update + 1e-8, f"{name} param {k}: rms err {rms_err:.3e} vs rms update {rms_update:.3e}"
 
 
+def test_acbc_iteration_vs_reference_fixture(cuda):
+    """ACBC.learn (one iteration, two epochs) on the device path vs the live reference."""
+    from rl_algo_impls_b200.acbc import ACBC
+    from rl_algo_impls_b200.rollout import VecRollout
+    from tests.golden.make_golden_cases import A2C_CASES, make_net_for
+    from tests.test_oracle_golden import load
+
+    case, z = A2C_CASES["microrts"], load("acbc_microrts")
+    net = make_net_for(case)()
+    net.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("init.")})
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    policy = _device_policy(case, net, cuda)
+    ro = rollout_from(z)
+
+    class Gen:
+        vec_env = type("E", (), {"num_envs": case["N"]})()
+
+        def rollout(self, gamma, gae_lambda):
+            return VecRollout(cuda, ro["next_episode_starts"], ro["next_values"], ro["obs"], ro["actions"], ro["rewards"],
+                              ro["episode_starts"], ro["values"], ro["logprobs"], ro["masks"], gamma, gae_lambda,
+                              subaction_mask=case["gates"])
+
+    algo = ACBC(policy, cuda, None, learning_rate=float(z["hp.learning_rate"]), batch_size=int(z["hp.batch_size"]),
+                n_epochs=int(z["hp.n_epochs"]), gamma=float(z["hp.gamma"]), gae_lambda=float(z["hp.gae_lambda"]),
+                vf_coef=float(z["hp.vf_coef"]))
+    torch.manual_seed(int(z["seed"]) + 100)
+    algo.learn(case["T"] * case["N"], Gen())
+    for k, tol in (("loss", 1e-4), ("pi_loss", 1e-4)):
+        want = float(z[f"stats.{k}"])
+        assert abs(algo.last_stats[k] - want) <= tol * max(abs(want), 1e-2), (k, algo.last_stats[k], want)
+    for k, v in policy.network.state_dict().items():
+        want, init = z[f"final.{k}"].astype(np.float64), z[f"init.{k}"].astype(np.float64)
+        got = v.cpu().numpy().astype(np.float64)
+        rms_update = np.sqrt(np.mean((want - init) ** 2))
+        rms_err = np.sqrt(np.mean((got - want) ** 2))
+        assert rms_err <= 1e-2 * rms_update + 1e-8, f"acbc param {k}: rms err {rms_err:.3e} vs rms update {rms_update:.3e}"
+
+
 def test_learn_epoch_with_kl_cutoff_matches_the_oracle(cuda):
     """kl_cutoff (ppo.py:352-355): the cut-off decision is taken on the device between forward and
     backward (no host sync) and stays sticky for the rest of the learn_epoch; same final parameters as

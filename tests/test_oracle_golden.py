@@ -201,6 +201,24 @@ def test_oracle_a2c_iteration_reproduces_the_reference(name):
         assert np.float64(stats[k]) == z[f"stats.{k}"], k
 
 
+def test_oracle_acbc_iteration_reproduces_the_reference():
+    """behaviour cloning (acbc/acbc.py:75-141): final parameters of the live reference, bit for bit."""
+    from tests.golden.make_golden_cases import A2C_CASES, make_net_for
+
+    case, z = A2C_CASES["microrts"], load("acbc_microrts")
+    net = make_net_for(case)()
+    net.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in z.items() if k.startswith("init.")})
+    pol = olearn.OraclePolicy(net, "gridnet", case["nvec"], case["side"] ** 2, case["gates"])
+    opt = torch.optim.Adam(net.parameters(), lr=float(z["hp.learning_rate"]))
+    torch.manual_seed(int(z["seed"]) + 100)
+    stats = olearn.acbc_learn_iteration(pol, opt, rollout_from(z), int(z["hp.batch_size"]), int(z["hp.n_epochs"]),
+                                        float(z["hp.gamma"]), float(z["hp.gae_lambda"]), float(z["hp.vf_coef"]))
+    for k, v in net.state_dict().items():
+        np.testing.assert_array_equal(v.numpy(), z[f"final.{k}"], err_msg=k)
+    for k in ("loss", "pi_loss"):
+        assert np.float64(stats[k]) == z[f"stats.{k}"], k
+
+
 @pytest.mark.parametrize("tag", ["scalar", "heads"])
 def test_trajectory_gae_matches_the_reference(tag):
     """oracle GAE over ragged trajectories (TrajectoryBuilder / DiscreteSkipsTrajectoryBuilder of the reference)."""
