@@ -143,6 +143,12 @@ def main():
     if a.what == "loss_c4":  # one shape, few launches: the ncu target
         rows.append(bench_loss(3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 0.06))
         print(json.dumps(rows[-1]), flush=True)
+    if a.what == "loss_dense":
+        rows.append(bench_loss(3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 1.0))
+        print(json.dumps(rows[-1]), flush=True)
+    if a.what == "loss_bf16":
+        rows.append(bench_loss(3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 0.06, torch.bfloat16))
+        print(json.dumps(rows[-1]), flush=True)
     if a.what == "loss_c5":
         rows.append(bench_loss(512, 4096, LUX_NVEC, LUX_GATES, 1, 13, 0.02))
         print(json.dumps(rows[-1]), flush=True)

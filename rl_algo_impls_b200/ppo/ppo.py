@@ -434,7 +434,7 @@ class PPO(Algorithm):
             return None
         if r.total_steps % self.batch_size != 0:
             return None
-        batch = r.batch()
+        batch = r.batch() if callable(r.batch) else r.batch  # VecRollout builds it lazily, TrajectoryRollout holds it
         _, tensors = batch._flat()
         key = (self.batch_size, bool(self.gradient_accumulation), bool(self.autocast_loss), float(self.max_grad_norm),
                h.clip_range, h.clip_range_vf, h.ent_coef, tuple(h.vf_coef), h.vf_halving, h.loss_scale, h.adv_mode,
@@ -477,7 +477,7 @@ class PPO(Algorithm):
             ev[1].record()
         timesteps_elapsed += r.total_steps
 
-        V = int(np.prod(r.values.shape[2:])) if hasattr(r, "values") else 1
+        V = int(getattr(r, "value_heads", 1))
         n_mb = r.num_minibatches(self.batch_size)
         loss_scale = 1.0 / n_mb if self.gradient_accumulation else 1.0
         h = self._hyper(V, V, loss_scale, 1.0)

@@ -126,6 +126,10 @@ class VecRollout(Rollout):
     def total_steps(self) -> int:
         return int(self.rewards.shape[0] * self.rewards.shape[1])
 
+    @property
+    def value_heads(self) -> int:
+        return int(np.prod(self.values.shape[2:]))
+
     def num_minibatches(self, batch_size: int) -> int:
         return self.total_steps // batch_size + (1 if self.total_steps % batch_size else 0)
 

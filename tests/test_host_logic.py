@@ -1,6 +1,7 @@
 """Host-side logic that needs no GPU: the Batch contract, spaces, synthetic envs, configs, the lane
 plan of the GridNet kernel's host mirror, TrainStats, and the loud failure without a CUDA device."""
 import dataclasses
+import os
 
 import numpy as np
 import pytest
@@ -119,3 +120,44 @@ def test_ppo_constructor_keeps_the_reference_attribute_names():
     assert algo.optimizer.defaults["eps"] == 1e-7  # ppo.py:146
     with pytest.raises(AssertionError):
         PPO(ActorCritic(env), torch.device("cpu"), None, normalize_advantage=True, standardize_advantage=True)
+
+
+def test_discrete_skips_builder_host_bookkeeping():
+    """rollout/discrete_skips_trajectory_builder.py:30-62: skipped steps fold reward * gamma ** steps_elapsed into
+    the last kept step in float32 (numpy's scalar arithmetic, as the reference) -- host logic, no device needed."""
+    from rl_algo_impls_b200.rollout.trajectory import DiscreteSkipsTrajectoryBuilder
+
+    rng = np.random.default_rng(3)
+    b = DiscreteSkipsTrajectoryBuilder(device="cpu")  # explicit-row mode never touches the device before trajectory()
+    gamma = 0.97
+    want_rewards, want_steps = [], []
+    for t in range(40):
+        r = np.float32(rng.standard_normal())
+        if t == 0 or rng.random() < 0.4:
+            b.step_add(np.zeros(2, np.float32), r, False, np.float32(0), 0.0, np.zeros(1, np.int64), None, gamma)
+            want_rewards.append(np.zeros_like(r)), want_steps.append(0)
+        else:
+            b.step_no_add(r, False, gamma)
+        want_rewards[-1] += r * gamma ** want_steps[-1]
+        want_steps[-1] += 1
+    assert b.steps_elapsed == want_steps and len(b) == len(want_steps)
+    assert all(np.float32(x) == np.float32(y) and np.asarray(x).dtype == np.float32 for x, y in zip(b.rewards, want_rewards))
+    b.step_no_add(np.float32(1), True, gamma)
+    with pytest.raises(AssertionError):
+        b.step_no_add(np.float32(1), False, gamma)
+
+
+def test_guided_rollout_host_helpers():
+    from rl_algo_impls_b200.rollout.guided_learner_rollout import has_actions, rearrange
+
+    assert rearrange(["c", "a", "b"], [2, 0, 1]) == ["a", "b", "c"]
+    m = np.zeros((3, 4, 5), np.bool_)
+    m[1, 2, 3] = True
+    assert has_actions(m).tolist() == [False, True, False]
+    assert has_actions({"per_position": m, "pick_position": np.zeros((3, 1, 4), np.bool_)}).tolist() == [False, True, False]
+
+
+def test_trajectory_rollout_fixture_is_present():
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "trajectory_rollouts.npz"))
+    for case in ("guided", "random_guided", "random_guided_skip", "reference_ai"):
+        assert int(z[f"{case}.r0.total_steps"]) == z[f"{case}.r0.obs"].shape[0] > 0
