@@ -288,6 +288,18 @@ int b200rl_running_norm_reward_f32(const float* rewards, const uint8_t* dones, i
                                    double* returns, double* mean, double* var, double* count, int training,
                                    double epsilon, double clip, float* out, b200rl_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K7  multi-head reward assembly.  Replaces wrappers/info_rewards_wrapper.py:39-57
+ * (InfoRewardsWrapper.step): out[n] = concat(base[n, :V0], series_0[n], ..., series_{K-1}[n]) where a series
+ * flagged in episode_end_host[k] is zeroed unless terminations[n] | truncations[n] (:45-53) and every
+ * series is multiplied by multiplier_host[k] when multiplier_host is not NULL (:54-55).  series_host is a
+ * HOST array of K device pointers to [N] float32 vectors (the leaves of the env's infos dict).
+ */
+int b200rl_reward_assemble_f32(const float* base, int64_t V0, const float* const* series_host, int K,
+                               const uint8_t* terminations, const uint8_t* truncations,
+                               const uint8_t* episode_end_host, const float* multiplier_host, float* out, int64_t N,
+                               b200rl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

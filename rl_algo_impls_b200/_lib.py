@@ -113,6 +113,10 @@ PROTOTYPES = {
         [_vp, _vp, _i64, _i64, C.c_double, _vp, _vp, _vp, _vp, _int, C.c_double, C.c_double, _vp, _vp],
     ),
     "b200rl_rollout_store_step": (_int, [C.POINTER(_vp), C.POINTER(_vp), c_i64p, _int, _vp, _i64, _vp]),
+    "b200rl_reward_assemble_f32": (
+        _int,
+        [_vp, _i64, C.POINTER(_vp), _int, _vp, _vp, C.POINTER(C.c_uint8), c_f32p, _vp, _i64, _vp],
+    ),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -341,6 +341,38 @@ def running_norm_reward(rewards: torch.Tensor, dones: torch.Tensor, returns: tor
 
 
 # ------------------------------------------------------------------------------------------------
+# K7
+def reward_assemble(base: torch.Tensor, series: Sequence[torch.Tensor], terminations: Optional[torch.Tensor],
+                    truncations: Optional[torch.Tensor], episode_end: Sequence[bool],
+                    multiplier: Optional[Sequence[float]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """InfoRewardsWrapper.step (wrappers/info_rewards_wrapper.py:39-57): [N, V0 + K] rewards = the env's own
+    reward head(s) followed by K per-env info series, episode-end gated and scaled.  base: [N] or [N, V0]."""
+    _cuda(base, torch.float32, "base")
+    N = base.shape[0]
+    V0 = base.numel() // max(N, 1) if base.dim() > 1 else 1
+    K = len(series)
+    if len(episode_end) != K or (multiplier is not None and len(multiplier) != K):
+        raise ValueError("episode_end / multiplier need one entry per series")
+    ptrs = (C.c_void_p * max(K, 1))()
+    for k, t in enumerate(series):
+        _cuda(t, torch.float32, f"series[{k}]")
+        if t.numel() != N:
+            raise ValueError(f"series[{k}] must have one value per env")
+        ptrs[k] = t.data_ptr()
+    term = _as_u8(terminations, "terminations") if terminations is not None else None
+    trunc = _as_u8(truncations, "truncations") if truncations is not None else None
+    out = torch.empty((N, V0 + K), dtype=torch.float32, device=base.device) if out is None else _cuda(out, torch.float32, "out")
+    if out.numel() != N * (V0 + K):
+        raise ValueError("out must be [N, V0 + K]")
+    ends = (C.c_uint8 * max(K, 1))(*[int(bool(e)) for e in episode_end])
+    mult = _f32_array(multiplier) if multiplier is not None else None
+    rc = _call("b200rl_reward_assemble_f32", 1, _lib.lib().b200rl_reward_assemble_f32, base.data_ptr(), V0, ptrs, K,
+               _ptr(term), _ptr(trunc), ends, mult, out.data_ptr(), N, _stream())
+    check(rc, "b200rl_reward_assemble_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # PPO arguments shared by the fused-loss entry points
 @dataclass
 class PpoHyper:

@@ -1,3 +1,4 @@
+from .info_rewards_wrapper import InfoRewardsWrapper
 from .normalize import NormalizeObservation, NormalizeReward, RunningMeanStd
 
-__all__ = ["NormalizeObservation", "NormalizeReward", "RunningMeanStd"]
+__all__ = ["InfoRewardsWrapper", "NormalizeObservation", "NormalizeReward", "RunningMeanStd"]

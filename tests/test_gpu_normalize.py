@@ -71,3 +71,52 @@ def test_normalizers_inside_the_graphed_rollout(cuda):
     r2 = gen.rollout(gamma=0.98, gae_lambda=0.92)
     assert env.rms.count > c1 and env.env.rms.count > obs_count1  # replays update the device state
     assert r2.obs.abs().max().item() <= 10.0 + 1e-6 and torch.isfinite(r2.rewards).all()
+
+
+class _ScriptedDeviceEnv:
+    """Replays (reward, terminations, truncations, infos) tuples as CUDA tensors."""
+
+    def __init__(self, script, device):
+        self.script, self.t, self.device = script, 0, device
+        self.num_envs = script[0][0].shape[0]
+
+    def step(self, action):
+        out = self.script[self.t]
+        self.t += 1
+        return (None,) + out
+
+
+@pytest.mark.parametrize("case", ["lux_like", "all_episode_end", "scalar_multiplier", "multi_base"])
+def test_info_rewards_wrapper_vs_reference_fixture(cuda, case):
+    """K7 behind InfoRewardsWrapper (device env) vs the live reference's wrapper: bit-exact [N, V0 + K] rewards."""
+    from rl_algo_impls_b200.wrappers import InfoRewardsWrapper
+    from tests.test_oracle_golden import load
+
+    z = load("info_rewards")
+    g = lambda k: z[f"{case}.{k}"]
+    K = g("series").shape[1]
+    paths = [["stats", f"s{k}"] if k % 2 else [f"s{k}"] for k in range(K)]
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    script = []
+    for t in range(g("base").shape[0]):
+        infos = {"stats": {}}
+        for k, path in enumerate(paths):
+            (infos["stats"] if len(path) == 2 else infos)[path[-1]] = to(g("series")[t, k])
+        script.append((to(g("base")[t]), to(g("terminations")[t]), to(g("truncations")[t]), infos))
+    mult = g("multiplier").tolist() if f"{case}.multiplier" in z else None
+    env = InfoRewardsWrapper(_ScriptedDeviceEnv(script, cuda), paths, episode_end=g("episode_end").tolist(), multiplier=mult)
+    for t in range(len(script)):
+        _, rewards, _, _, _ = env.step(None)
+        np.testing.assert_array_equal(rewards.cpu().numpy(), g("rewards")[t])
+
+
+def test_reward_assemble_rejects_bad_arguments(cuda):
+    from rl_algo_impls_b200 import ops
+
+    base = torch.zeros(4, device=cuda)
+    with pytest.raises(ValueError):
+        ops.reward_assemble(base, [torch.zeros(3, device=cuda)], None, None, [False])
+    with pytest.raises(Exception):  # episode-end gating without the terminations flags
+        ops.reward_assemble(base, [torch.zeros(4, device=cuda)], None, None, [True])
+    out = ops.reward_assemble(base, [], None, None, [])
+    assert out.shape == (4, 1)

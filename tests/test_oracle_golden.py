@@ -236,3 +236,16 @@ def test_trajectory_gae_matches_the_reference(tag):
         sk = discrete_skips_advantages(g("rewards")[sl], g("values")[sl], g("steps")[sl], bool(g("skip_done")[s]),
                                        g("next_values")[s], gamma, lam)
         np.testing.assert_array_equal(sk, g("skip_adv")[sl])
+
+
+@pytest.mark.parametrize("case", ["lux_like", "all_episode_end", "scalar_multiplier", "multi_base"])
+def test_reward_assembly_matches_the_reference(case):
+    """oracle/rewards.py vs the live reference's InfoRewardsWrapper.step (wrappers/info_rewards_wrapper.py:39-57)."""
+    from oracle.rewards import assemble_rewards
+
+    z = load("info_rewards")
+    mult = z[f"{case}.multiplier"] if f"{case}.multiplier" in z else None
+    for t in range(z[f"{case}.base"].shape[0]):
+        got = assemble_rewards(z[f"{case}.base"][t], [s.copy() for s in z[f"{case}.series"][t]], z[f"{case}.terminations"][t],
+                               z[f"{case}.truncations"][t], z[f"{case}.episode_end"], mult)
+        np.testing.assert_array_equal(got, z[f"{case}.rewards"][t])
