@@ -330,7 +330,7 @@ def main():
                "h2d_bytes_per_step": (hgen._upload.bytes - h2d0) // e2e_steps,
                "d2h_bytes_per_step": (hgen.d2h_bytes - d2h0) // e2e_steps + halgo.d2h_bytes_last_epoch,
                "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-               "path": "host numpy VectorEnv -> pinned staging -> HBM rollout buffer; sampled actions -> host"}
+               "path": "host numpy VectorEnv -> DMA out of the env buffers (page-locked in place; small fields via pinned staging) -> HBM rollout buffer; sampled actions -> host"}
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
     cpu = None

@@ -27,19 +27,67 @@ def _torch_dtype(np_dtype) -> torch.dtype:
 
 
 class _Uploader:
-    """numpy -> CUDA through a reusable pinned staging buffer (one per distinct field)."""
+    """numpy -> CUDA.  Large arrays that keep coming from the same host buffer (a vec env that reuses its output
+    arrays, or cycles through a pool of them) are page-locked IN PLACE with cudaHostRegister the second time
+    their buffer is seen, so the H2D copy is one DMA straight out of the env's memory; everything else goes
+    through a reusable pinned staging buffer (one per distinct field), which also does dtype conversion."""
+
+    REGISTER_MIN_BYTES = 256 << 10   # below this a staging memcpy is cheaper than bookkeeping
+    REGISTER_MAX_BYTES = 8 << 30     # total page-locked in place
 
     def __init__(self, device: torch.device):
         self.device = device
         self._pinned: Dict[str, torch.Tensor] = {}
         self._done: Dict[str, torch.cuda.Event] = {}
+        self._seen: Dict[tuple, int] = {}        # (root pointer, nbytes) -> sightings before registration
+        self._registered: Dict[tuple, bool] = {}  # (root pointer, nbytes) -> cudaHostRegister succeeded
+        self._registered_bytes = 0
         self.bytes = 0  # host -> device bytes moved so far
+
+    def _page_locked(self, a: np.ndarray) -> bool:
+        """True when `a` lives in a host buffer this uploader has page-locked (registering it on its second sighting)."""
+        root = a
+        while isinstance(root.base, np.ndarray):
+            root = root.base
+        if root.base is not None or not root.flags.c_contiguous:  # memory owned by something else (mmap, torch, ...)
+            return False
+        key = (root.ctypes.data, root.nbytes)
+        state = self._registered.get(key)
+        if state is not None:
+            return state
+        self._seen[key] = self._seen.get(key, 0) + 1
+        if self._seen[key] < 2 or self._registered_bytes + root.nbytes > self.REGISTER_MAX_BYTES:
+            if len(self._seen) > 4096:  # an env that allocates fresh arrays every step: stop tracking
+                self._seen.clear()
+            return False
+        rc = torch.cuda.cudart().cudaHostRegister(root.ctypes.data, root.nbytes, 0)
+        ok = int(rc) == 0
+        self._registered[key] = ok
+        if ok:
+            self._registered_bytes += root.nbytes
+            self._roots = getattr(self, "_roots", []) + [root]  # keep the buffer alive while it is registered
+        return ok
+
+    def close(self) -> None:
+        for (ptr, _), ok in self._registered.items():
+            if ok:
+                torch.cuda.cudart().cudaHostUnregister(ptr)
+        self._registered.clear()
+        self._roots = []
 
     def __call__(self, name: str, src, dst: torch.Tensor) -> None:
         if isinstance(src, torch.Tensor):
             dst.copy_(src, non_blocking=True)
             return
         a = np.ascontiguousarray(src)
+        if a.nbytes >= self.REGISTER_MIN_BYTES and a.shape == tuple(dst.shape):
+            t = torch.from_numpy(a)
+            if t.dtype == dst.dtype and self._page_locked(a):
+                # DMA out of the env's own buffer.  The caller must not overwrite it before the copy has run:
+                # the step loops read the sampled actions back (a stream synchronisation) before the next env.step.
+                self.bytes += a.nbytes
+                dst.copy_(t, non_blocking=True)
+                return
         stage = self._pinned.get(name)
         if stage is None or stage.shape != a.shape or stage.dtype != dst.dtype:
             stage = torch.empty(a.shape, dtype=dst.dtype, pin_memory=True)
