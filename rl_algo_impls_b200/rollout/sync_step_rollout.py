@@ -156,6 +156,9 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         self._graph_outputs = None
         self._kernels_per_replay = 0
         self.d2h_bytes = 0  # device -> host bytes (sampled actions handed to a host env)
+        self._host_actions = None  # pinned landing zone of the sampled actions (host env)
+        self._host_rewards: Optional[torch.Tensor] = None  # pinned [T, N(, V)]: a host env's rewards, uploaded per rollout
+        self._host_starts: Optional[torch.Tensor] = None   # pinned [T + 1, N]: episode-start flags, row T carries over
         self.get_action_mask = getattr(vec_env, "get_action_mask", None)
 
         T = self.n_steps
@@ -207,19 +210,24 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         else:
             self._upload("mask", m, self.next_action_masks)
 
-    def _env_actions(self, a):
-        """What vec_env.step receives: CUDA tensors for a device env, numpy (int64 / f32) for a host env."""
+    def _env_actions(self, a, landed: bool = False):
+        """What vec_env.step receives: CUDA tensors for a device env, numpy (int64 / f32) for a host env.
+        ``landed``: the step already copied `a` into the pinned ``_host_actions`` (wait for it, read it there)."""
         if getattr(self.vec_env, "device", None) is not None:
             return a
         from ..policy.actor_critic import clamp_actions
 
+        if landed:
+            torch.cuda.current_stream().synchronize()
+            fetch = lambda k, t: (self._host_actions[k] if k is not None else self._host_actions).numpy()
+        else:
+            fetch = lambda k, t: t.cpu().numpy()
         if isinstance(a, dict):
             self.d2h_bytes += sum(t.numel() * t.element_size() for t in a.values())
-            return {k: t.cpu().numpy().astype(np.int64) for k, t in a.items()}
+            return {k: fetch(k, t).astype(np.int64) for k, t in a.items()}
         self.d2h_bytes += a.numel() * a.element_size()
-        a_np = a.cpu().numpy()
-        if a_np.dtype == np.uint8:
-            a_np = a_np.astype(np.int64)
+        a_np = fetch(None, a)
+        a_np = a_np.astype(np.int64) if a_np.dtype == np.uint8 else (a_np.copy() if landed else a_np)
         return clamp_actions(a_np, self.vec_env.single_action_space, getattr(self.policy, "squash_output", False))
 
     def prepare(self) -> None:
@@ -230,9 +238,11 @@ class SyncStepRolloutGenerator(RolloutGenerator):
             self._reset_envs(0, self.rolling_num_envs_reset_every_prepare_step, 0)
 
     # -- the step loop (sync_step_rollout.py:181-216) ------------------------------------------------
-    def _fields(self, a, v, logp, rewards=None):
+    def _fields(self, a, v, logp, rewards=None, with_starts: bool = True):
         """(this step's slices, their [T, ...] buffers) in one list pair for the K0 store."""
-        src, dst = [self.next_obs, self.next_episode_starts], [self.obs, self.episode_starts]
+        src, dst = [self.next_obs], [self.obs]
+        if with_starts:
+            src.append(self.next_episode_starts), dst.append(self.episode_starts)
         if self.action_masks is not None:
             if isinstance(self.action_masks, dict):
                 for k, buf in self.action_masks.items():
@@ -252,13 +262,24 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         return src, dst
 
     def _policy_step(self):
-        """Sample + evaluate on the current next_obs / masks and write the pre-env fields of this
-        step into row (step_count % T) of the buffers.  Static addresses only: graph-capturable."""
+        """Host-env half step: sample + evaluate on the current next_obs / masks, write the pre-env fields of
+        this step into row (step_count % T) of the buffers and start the sampled actions towards pinned host
+        memory.  Static addresses only: graph-capturable (the D2H copy becomes a memcpy node).  Rewards and
+        episode-start flags never take part: a host env hands them over on the host, where they are collected
+        in pinned [T, N] arrays and uploaded once per rollout."""
         from .. import ops
 
         a, v, logp = self.policy.step_device(self.next_obs, self.next_action_masks, offset_dev=self.step_count)
-        src, dst = self._fields(a, v, logp)
+        src, dst = self._fields(a, v, logp, with_starts=False)
         ops.rollout_store_step(src, dst, self.step_count)
+        if self._host_actions is None:
+            pin = lambda t: torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+            self._host_actions = {k: pin(t) for k, t in a.items()} if isinstance(a, dict) else pin(a)
+        if isinstance(a, dict):
+            for k, t in a.items():
+                self._host_actions[k].copy_(t, non_blocking=True)
+        else:
+            self._host_actions.copy_(a, non_blocking=True)
         return a
 
     def _device_env_step(self):
@@ -317,6 +338,14 @@ class SyncStepRolloutGenerator(RolloutGenerator):
                     self._graph, self._graph_outputs = self._capture(policy_part)
         self.step_count.fill_(self._rollouts_done * T)  # row 0 of the buffer, fresh RNG offsets
         self._rollouts_done += 1
+        if not device_env:
+            if self._host_rewards is None:
+                self._host_rewards = torch.zeros(tuple(self.rewards.shape), dtype=torch.float32, pin_memory=True)
+                self._host_starts = torch.ones((T + 1, self.rewards.shape[1]), dtype=torch.bool, pin_memory=True)
+            else:
+                torch.cuda.current_stream().synchronize()  # last rollout's upload out of these arrays has run
+                self._host_starts[0].copy_(self._host_starts[T])
+            host_rewards, host_starts = self._host_rewards.numpy(), self._host_starts.numpy()
         for s in range(T):
             if self.sde_sample_freq > 0 and s > 0 and s % self.sde_sample_freq == 0:
                 self.policy.reset_noise()
@@ -337,12 +366,17 @@ class SyncStepRolloutGenerator(RolloutGenerator):
                 with torch.no_grad():
                     a = self._policy_step()
                     self.step_count.add_(1)
-            next_obs, rewards, terminations, truncations, _ = self.vec_env.step(self._env_actions(a))
+            next_obs, rewards, terminations, truncations, _ = self.vec_env.step(self._env_actions(a, landed=True))
             self._upload("obs", next_obs, self.next_obs)
-            self._upload("rewards", rewards, self.rewards[s])
-            self._upload("starts", np.logical_or(terminations, truncations), self.next_episode_starts)
             if self.get_action_mask is not None and self.next_action_masks is not None:
                 self._upload_masks(self.get_action_mask())
+            host_rewards[s] = np.asarray(rewards, dtype=np.float32).reshape(host_rewards.shape[1:])
+            np.logical_or(terminations, truncations, out=host_starts[s + 1])
+        if not device_env:  # one upload per rollout for the scalars the env produced on the host
+            self._upload.bytes += self._host_rewards.numel() * 4 + self._host_starts.numel()
+            self.rewards.copy_(self._host_rewards, non_blocking=True)
+            self.episode_starts.copy_(self._host_starts[:T], non_blocking=True)
+            self.next_episode_starts.copy_(self._host_starts[T], non_blocking=True)
         next_values = self.policy.value_device(self.next_obs) if output_next_values else None
         self.policy.train()
         return next_values
