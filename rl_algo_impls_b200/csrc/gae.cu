@@ -56,46 +56,61 @@ __device__ __forceinline__ void store_lanes(float* p, const Lanes<VEC>& r) {
   }
 }
 
-// episode_starts flags of the VEC lanes at one time row.  V == 1 && VEC == 4: one 32-bit load.
-// V > 1 && VEC == 4: four adjacent lanes (lane0 a multiple of 4) belong to at most two envs, the
-// first lane's and the last lane's, so two byte loads cover them.
+// episode_starts flags of the VEC lanes at one time row, one byte per lane in a 32-bit word.
+// V == 1 && VEC == 4: one 32-bit load.  V > 1 && VEC == 4: four adjacent lanes (lane0 a multiple of 4) belong
+// to at most two envs, the first lane's and the last lane's, so two byte loads cover them; `pat_lo` / `pat_hi`
+// hold 0x01 in the byte of every lane that belongs to the first / last env.
+struct LaneEnvs {
+  int lo, hi;               // env of the first / last lane
+  uint32_t pat_lo, pat_hi;  // byte masks of the lanes of each
+};
 template <int VEC, bool V1>
-__device__ __forceinline__ uint32_t load_starts(const uint8_t* row, const long long (&env)[VEC]) {
+__device__ __forceinline__ uint32_t load_starts(const uint8_t* row, const LaneEnvs& e) {
   if constexpr (V1 && VEC == 4) {
-    return __ldg(reinterpret_cast<const unsigned int*>(row + env[0]));
-  } else if constexpr (VEC == 4) {
-    const uint32_t lo = __ldg(row + env[0]) != 0, hi = __ldg(row + env[3]) != 0;
-    uint32_t packed = 0;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) packed |= (env[i] == env[0] ? lo : hi) << (8 * i);
-    return packed;
+    return __ldg(reinterpret_cast<const unsigned int*>(row + e.lo));
+  } else if constexpr (V1) {
+    return (uint32_t)(__ldg(row + e.lo) != 0);
   } else {
-    uint32_t packed = 0;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) packed |= (uint32_t)(__ldg(row + env[i]) != 0) << (8 * i);
-    return packed;
+    const uint32_t lo = __ldg(row + e.lo) != 0, hi = __ldg(row + e.hi) != 0;
+    return lo * e.pat_lo | hi * e.pat_hi;
   }
 }
 
-template <int VEC, bool V1, int UNROLL>
-__global__ void __launch_bounds__(128) gae_scan_kernel(const GaeParams p) {
+// Occupancy is what hides HBM latency here: 8 CTAs of 128 threads per SM (<= 64 registers, no spills) with the
+// loads of UNROLL = 2 steps in flight per thread measured 0.91 of the HBM peak on both roofline shapes; deeper
+// unrolling at 4-6 CTAs / SM measured 0.72-0.83 (V = 13) and 0.90 (V = 1).  The per-lane constants are kept
+// small for that budget: envs / heads are packed into a few 32-bit words and the per-head discount factors are
+// read from shared memory where they are used instead of living in 16 double registers.
+template <int VEC, bool V1, int UNROLL, int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS) gae_scan_kernel(const __grid_constant__ GaeParams p) {
   const long long group = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long lane0 = group * VEC;
-  if (lane0 >= p.L) return;
 
-  double g[VEC], gl[VEC];
-  long long env[VEC];  // env of each lane: constant over time, so the division happens once
+  // env / value head of each lane are constant over time, so the division happens once; packed small
+  LaneEnvs envs{(int)lane0, (int)lane0, 0u, 0u};
+  uint32_t heads = 0u;  // byte i: value head of lane i
+  if (!V1) {
+    envs.lo = (int)(lane0 / p.V), envs.hi = (int)((lane0 + VEC - 1) / p.V);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    env[i] = V1 ? (lane0 + i) : (lane0 + i) / p.V;
-    int h = V1 ? 0 : (int)((lane0 + i) - env[i] * p.V);
-    g[i] = p.gamma[h];
-    gl[i] = p.gamma_lambda[h];
+    for (int i = 0; i < VEC; ++i) {
+      const int e = (int)((lane0 + i) / p.V);
+      heads |= (uint32_t)((lane0 + i) - (long long)e * p.V) << (8 * i);
+      if (e == envs.lo) envs.pat_lo |= 1u << (8 * i);
+      else envs.pat_hi |= 1u << (8 * i);
+    }
   }
   const bool scalar_gamma = p.gamma_is_scalar != 0;
+  // per-head discount factors: read where they are used (volatile shared loads) so that the compiler does not
+  // park 4 x 2 doubles per thread in registers for the whole scan
+  __shared__ double s_g[B200RL_MAX_VALUE_HEADS], s_gl[B200RL_MAX_VALUE_HEADS];
+  if (!V1) {
+    if (threadIdx.x < B200RL_MAX_VALUE_HEADS) s_g[threadIdx.x] = p.gamma[threadIdx.x], s_gl[threadIdx.x] = p.gamma_lambda[threadIdx.x];
+    __syncthreads();
+  }
+  if (lane0 >= p.L) return;
 
   Lanes<VEC> v_next = load_lanes<VEC>(p.next_values + lane0);
-  uint32_t started_next = load_starts<VEC, V1>(p.next_episode_starts, env);
+  uint32_t started_next = load_starts<VEC, V1>(p.next_episode_starts, envs);
   double carry[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) carry[i] = 0.0;
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(128) gae_scan_kernel(const GaeParams p) {
       if (tu >= 0) {
         r[u] = load_lanes<VEC>(p.rewards + tu * p.L + lane0);
         v[u] = load_lanes<VEC>(p.values + tu * p.L + lane0);
-        st[u] = load_starts<VEC, V1>(p.episode_starts + tu * p.N, env);
+        st[u] = load_starts<VEC, V1>(p.episode_starts + tu * p.N, envs);
       }
     }
 #pragma unroll
@@ -122,14 +137,16 @@ __global__ void __launch_bounds__(128) gae_scan_kernel(const GaeParams p) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           const double alive = ((started_next >> (8 * i)) & 0xffu) ? 0.0 : 1.0;  // 1.0 - episode_starts[t+1]
+          const double g = V1 ? p.gamma[0] : *(volatile double*)&s_g[(heads >> (8 * i)) & 0xffu];
+          const double gl = V1 ? p.gamma_lambda[0] : *(volatile double*)&s_gl[(heads >> (8 * i)) & 0xffu];
           double boot;
           if (scalar_gamma) {
-            boot = __dmul_rn((double)__fmul_rn((float)g[i], v_next.x[i]), alive);
+            boot = __dmul_rn((double)__fmul_rn((float)g, v_next.x[i]), alive);
           } else {
-            boot = __dmul_rn(__dmul_rn(g[i], (double)v_next.x[i]), alive);
+            boot = __dmul_rn(__dmul_rn(g, (double)v_next.x[i]), alive);
           }
           const double delta = __dsub_rn(__dadd_rn((double)r[u].x[i], boot), (double)v[u].x[i]);
-          carry[i] = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl[i], alive), carry[i]));
+          carry[i] = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, alive), carry[i]));
           adv.x[i] = __double2float_rn(carry[i]);
           ret.x[i] = __fadd_rn(adv.x[i], v[u].x[i]);
         }
@@ -152,7 +169,12 @@ static int launch(const GaeParams& p, cudaStream_t stream) {
     set_error("gae_scan: too many lanes (%lld)", p.L);
     return B200RL_EUNSUPPORTED;
   }
-  gae_scan_kernel<VEC, V1, 4><<<(unsigned)grid, block, 0, stream>>>(p);
+  // A rollout that fills the machine (>= 8 CTAs on every SM) runs the occupancy-first configuration; smaller
+  // ones are a serial chain of dependent round trips per thread and measured best with 4 steps in flight
+  // (T=512, N=24: 145 us against 173-207 us for 2, 8 or 16).
+  const long long full = (long long)device_info().sm_count * 8 * block;
+  if (groups >= full) gae_scan_kernel<VEC, V1, 2, 8><<<(unsigned)grid, block, 0, stream>>>(p);
+  else gae_scan_kernel<VEC, V1, 4, 4><<<(unsigned)grid, block, 0, stream>>>(p);
   return check_launch("gae_scan");
 }
 
