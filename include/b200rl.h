@@ -158,7 +158,14 @@ typedef struct b200rl_ppo_args {
   float teacher_kl_coef;
   int teacher_unbiased;   /* loss/teacher_kl_loss.py:14 `unbiased` */
   int teacher_importance; /* ppo.py:139 teacher_loss_importance_sampling */
+  int vf_loss;            /* ppo.py:186 vf_loss_fn = getattr(F, name): B200RL_VF_* (0 = mse_loss, the default) */
 } b200rl_ppo_args;
+
+/* element-wise value losses of torch.nn.functional with their default delta / beta = 1 */
+#define B200RL_VF_MSE 0       /* (x - y)^2 */
+#define B200RL_VF_HUBER 1     /* |d| < 1 ? d^2 / 2 : |d| - 1/2 */
+#define B200RL_VF_SMOOTH_L1 2 /* the same function at beta = 1 */
+#define B200RL_VF_L1 3        /* |d| */
 
 #define B200RL_PPO_NSTATS(V) (6 + 2 * (V))
 

@@ -46,6 +46,7 @@ class Hyper:
     teacher_kl_loss_coef: Optional[float] = None
     teacher_unbiased: bool = True
     teacher_loss_importance_sampling: bool = True
+    vf_loss_fn: str = "mse_loss"  # ppo.py:135,186: getattr(torch.nn.functional, vf_loss_fn)
 
 
 class OraclePolicy:
@@ -186,7 +187,8 @@ def learn_epoch(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict
                              kl_cutoff=hp.kl_cutoff, loss_divisor=n_mb if hp.gradient_accumulation else None,
                              teacher_logprobs=teacher_logp[idx] if teacher_logp is not None else None,
                              teacher_kl_loss_coef=hp.teacher_kl_loss_coef, teacher_unbiased=hp.teacher_unbiased,
-                             teacher_loss_importance_sampling=hp.teacher_loss_importance_sampling)
+                             teacher_loss_importance_sampling=hp.teacher_loss_importance_sampling,
+                             vf_loss_fn=getattr(torch.nn.functional, hp.vf_loss_fn))
             pi_coef = parts.pi_coef
             parts.loss.backward()
             if not hp.gradient_accumulation:

@@ -49,6 +49,7 @@ class PpoArgs(C.Structure):
         ("teacher_kl_coef", C.c_float),
         ("teacher_unbiased", C.c_int),
         ("teacher_importance", C.c_int),
+        ("vf_loss", C.c_int),
     ]
 
 

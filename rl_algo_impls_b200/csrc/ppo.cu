@@ -32,6 +32,8 @@ int ppo_make_dev(const b200rl_ppo_args* a, long long B, void* workspace, size_t 
   for (int v = 0; v < P.V; ++v) P.vf_coef[v] = a->vf_coef_host[v];
   P.ent_coef = a->ent_coef, P.pi_coef = a->pi_coef, P.pi_coef_dev = nullptr;
   P.halving = a->vf_halving, P.loss_scale = a->loss_scale;
+  B200RL_UNSUPPORTED(a->vf_loss < B200RL_VF_MSE || a->vf_loss > B200RL_VF_L1, "ppo: vf_loss=%d", a->vf_loss);
+  P.vf_loss = a->vf_loss;
   P.teacher_logp = a->teacher_logp, P.teacher_coef = a->teacher_kl_coef;
   P.teacher_unbiased = a->teacher_unbiased, P.teacher_importance = a->teacher_importance;
   P.B = B;

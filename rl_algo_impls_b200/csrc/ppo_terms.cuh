@@ -35,6 +35,7 @@ struct PpoDev {
   float pi_coef;
   const float* pi_coef_dev;  // when non-null, overrides pi_coef (KL cut-off state on the device)
   int halving;
+  int vf_loss;  // B200RL_VF_*
   float loss_scale;
   const float* teacher_logp;  // null: no teacher-KL term
   float teacher_coef;
@@ -151,19 +152,40 @@ __device__ __forceinline__ float ppo_dentropy(const PpoDev& P, int ent_d) {
   return -(P.ent_coef * P.loss_scale) / ((float)P.B * (float)ent_d);
 }
 
+// element of vf_loss_fn(x, y, reduction="none") and its derivative in x, e = x - y (ppo.py:186,331-339): the
+// torch.nn.functional losses at their default delta / beta = 1, forward and autograd backward formulas
+__device__ __forceinline__ void vf_element(int kind, float e, float& loss, float& grad) {
+  const float a = fabsf(e);
+  switch (kind) {
+    case B200RL_VF_HUBER:
+    case B200RL_VF_SMOOTH_L1:
+      if (a < 1.f) {
+        loss = 0.5f * e * e, grad = e;
+      } else {
+        loss = a - 0.5f, grad = e < 0.f ? -1.f : 1.f;
+      }
+      break;
+    case B200RL_VF_L1:
+      loss = a, grad = e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f);
+      break;
+    default:
+      loss = e * e, grad = 2.f * e;
+  }
+}
+
 // value head v of sample i: writes dvalues[i, v]; returns (loss element, clipped indicator)
 __device__ __forceinline__ float2 ppo_value_terms(const PpoDev& P, long long i, int v) {
   const long long o = i * P.V + v;
   const float nv = P.new_values[o], ov = P.old_values[o], rt = P.returns[o];
-  const float eu = nv - rt;
-  const float u = eu * eu;
-  float vl = u, g = 2.f * eu, clipped = 0.f;
+  float u, g;
+  vf_element(P.vf_loss, nv - rt, u, g);
+  float vl = u, clipped = 0.f;
   if (P.vclip >= 0.f) {
     const float d = nv - ov;
     const float c = ov + fminf(fmaxf(d, -P.vclip), P.vclip);
-    const float ec = c - rt;
-    const float cl = ec * ec;
-    const float gc = (d >= -P.vclip && d <= P.vclip) ? 2.f * ec : 0.f;
+    float cl, gc;
+    vf_element(P.vf_loss, c - rt, cl, gc);
+    if (!(d >= -P.vclip && d <= P.vclip)) gc = 0.f;  // clamp passes no gradient outside the band
     if (u > cl) {
       vl = u;
     } else if (u < cl) {

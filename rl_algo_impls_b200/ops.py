@@ -390,6 +390,11 @@ class PpoHyper:
     teacher_kl_coef: float = 0.0  # > 0 with teacher_logp: adds the teacher-KL term (loss/teacher_kl_loss.py)
     teacher_unbiased: bool = True
     teacher_importance: bool = True
+    vf_loss: int = 0  # VF_LOSSES[vf_loss_fn]
+
+
+# ppo.py:186 vf_loss_fn = getattr(F, name) -> b200rl.h B200RL_VF_*
+VF_LOSSES = {"mse_loss": 0, "huber_loss": 1, "smooth_l1_loss": 2, "l1_loss": 3}
 
 
 class PpoCall:
@@ -443,6 +448,7 @@ class PpoCall:
         a.vf_coef_host = self._vf
         a.ent_coef, a.pi_coef = float(h.ent_coef), float(h.pi_coef)
         a.vf_halving, a.loss_scale = int(bool(h.vf_halving)), float(h.loss_scale)
+        a.vf_loss = int(h.vf_loss)
         a.stats_out = self.stats.data_ptr()
         if teacher_logp is not None and h.teacher_kl_coef:
             _cuda(teacher_logp, torch.float32, "teacher_logp")

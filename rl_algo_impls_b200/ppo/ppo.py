@@ -292,8 +292,9 @@ class PPO(Algorithm):
         self.guide_probability = guide_probability
         self.normalize_advantages_after_scaling = normalize_advantages_after_scaling
         self.autocast_loss = autocast_loss
-        if vf_loss_fn != "mse_loss":
-            raise NotImplementedError(f"vf_loss_fn={vf_loss_fn!r}: the fused kernels implement the reference default, mse_loss")
+        if vf_loss_fn not in ops.VF_LOSSES:
+            raise NotImplementedError(f"vf_loss_fn={vf_loss_fn!r}: the fused kernels implement {sorted(ops.VF_LOSSES)}")
+        self.vf_loss_fn = vf_loss_fn
         self.teacher_kl_loss_coef = teacher_kl_loss_coef
         self.teacher_kl_loss_fn = teacher_kl_loss_fn
         self.teacher_loss_importance_sampling = teacher_loss_importance_sampling
@@ -345,7 +346,8 @@ class PPO(Algorithm):
                             adv_mode=mode, adv_weights=w,
                             teacher_kl_coef=float(self.teacher_kl_loss_coef or 0.0),
                             teacher_unbiased=bool(getattr(self.teacher_kl_loss_fn, "unbiased", True)),
-                            teacher_importance=bool(self.teacher_loss_importance_sampling))
+                            teacher_importance=bool(self.teacher_loss_importance_sampling),
+                            vf_loss=ops.VF_LOSSES[self.vf_loss_fn])
 
     def _moments_local(self, adv: torch.Tensor, h: ops.PpoHyper) -> Optional[torch.Tensor]:
         if h.adv_mode == ops.ADV_NONE:
@@ -438,7 +440,7 @@ class PPO(Algorithm):
         _, tensors = batch._flat()
         key = (self.batch_size, bool(self.gradient_accumulation), bool(self.autocast_loss), float(self.max_grad_norm),
                h.clip_range, h.clip_range_vf, h.ent_coef, tuple(h.vf_coef), h.vf_halving, h.loss_scale, h.adv_mode,
-               tuple(h.adv_weights) if h.adv_weights is not None else None, h.teacher_kl_coef, h.teacher_unbiased,
+               tuple(h.adv_weights) if h.adv_weights is not None else None, h.vf_loss, h.teacher_kl_coef, h.teacher_unbiased,
                h.teacher_importance, tuple(t.data_ptr() for t in tensors))
         g = self._update_graphs.get(key)
         if g is not None:

@@ -260,7 +260,7 @@ def _learner_case(name, kind, make_net, T, N, obs_shape, hp: olearn.Hyper, nvec=
     kw = {k: getattr(hp, k) for k in ("batch_size", "n_epochs", "clip_range", "clip_range_vf", "normalize_advantage",
                                       "standardize_advantage", "ent_coef", "ppo2_vf_coef_halving", "max_grad_norm",
                                       "gradient_accumulation", "kl_cutoff", "normalize_advantages_after_scaling",
-                                      "learning_rate")}
+                                      "learning_rate", "vf_loss_fn")}
     as_list = lambda x: x.tolist() if isinstance(x, np.ndarray) else x
     teacher_net = teacher_pol = None
     if hp.teacher_kl_loss_coef:
@@ -324,8 +324,10 @@ def _learner_case(name, kind, make_net, T, N, obs_shape, hp: olearn.Hyper, nvec=
 from tests.golden.make_golden_cases import LEARNER_CASES, make_net_for  # noqa: E402
 
 
-def golden_learner():
+def golden_learner(only=None):
     for i, (name, case) in enumerate(LEARNER_CASES.items()):
+        if only is not None and name not in only:
+            continue
         _learner_case(name, case["kind"], make_net_for(case), case["T"], case["N"], case["obs_shape"], case["hp"],
                       nvec=case["nvec"], side=case.get("side", 0), gates=case.get("gates"), n_pick=case.get("n_pick", 0),
                       V=case["V"], seed=10 + i)
@@ -565,6 +567,9 @@ def golden_normalizers():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "learner":  # python make_golden.py learner <case> [<case> ...]
+        golden_learner(set(sys.argv[2:]))
+        sys.exit(0)
     golden_acbc()
     golden_trajectories()
     golden_a2c()

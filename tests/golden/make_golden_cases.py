@@ -31,6 +31,13 @@ LEARNER_CASES = {
                                 gae_lambda=np.array([0.95, 0.95, 0.9]), clip_range=0.1, ent_coef=0.01,
                                 vf_coef=[0.5, 0.25, 0.25], multi_reward_weights=[0.6, 0.3, 0.1],
                                 gradient_accumulation=True, learning_rate=1e-3)),
+    "cartpole_huber": dict(kind="categorical", T=16, N=8, obs_shape=(4,), nvec=(2,), V=1,
+                           hp=olearn.Hyper(batch_size=32, n_epochs=2, gamma=0.98, gae_lambda=0.8, clip_range=0.2,
+                                           clip_range_vf=0.3, vf_coef=0.7, learning_rate=1e-3, vf_loss_fn="huber_loss")),
+    "gaussian_l1": dict(kind="gaussian", T=8, N=8, obs_shape=(17,), nvec=(6,), V=1,
+                        hp=olearn.Hyper(batch_size=32, n_epochs=2, gamma=0.98, gae_lambda=0.92, clip_range=0.1,
+                                        ent_coef=4e-4, vf_coef=0.581, max_grad_norm=0.8, learning_rate=1e-3,
+                                        vf_loss_fn="l1_loss")),
 }
 
 

@@ -125,7 +125,7 @@ def test_learn_epoch_vs_reference_fixture(cuda, name):
                                       "normalize_advantage", "standardize_advantage", "ent_coef", "vf_coef",
                                       "ppo2_vf_coef_halving", "max_grad_norm", "multi_reward_weights",
                                       "gradient_accumulation", "kl_cutoff", "normalize_advantages_after_scaling",
-                                      "learning_rate")}
+                                      "learning_rate", "vf_loss_fn")}
     tnet = teacher_net(case, z)
     if tnet is not None:  # teacher-KL term: the teacher checkpoint is an ActorCritic over the stored teacher weights
         from rl_algo_impls_b200.loss import TeacherKLLoss

@@ -154,3 +154,33 @@ def test_scalar_stage_and_kl_cutoff(cuda):
         close(out.dvalues, nv.grad, what="dvalues")
         if kl_cutoff is not None:
             assert parts.pi_coef == 0 and state.item() == 0.0
+
+
+@pytest.mark.parametrize("name", ["mse_loss", "huber_loss", "smooth_l1_loss", "l1_loss"])
+@pytest.mark.parametrize("clip_vf", [None, 0.3])
+def test_value_loss_functions(cuda, name, clip_vf):
+    """vf_loss_fn = getattr(F, name) (ppo.py:186,331-343): value loss, its max with the clipped variant and
+    dvalues of the fused scalar stage vs the oracle evaluated with torch.nn.functional."""
+    import torch.nn.functional as F
+
+    from rl_algo_impls_b200 import ops
+
+    B, V = 1024, 2
+    pp = to_torch(ppo_inputs(11, B, V))
+    g = torch.Generator().manual_seed(5)
+    new_logp, entropy = torch.randn(B, generator=g), torch.rand(B, generator=g)
+    old_logp = new_logp + pp["old_logp_noise"]
+    nv = (pp["new_values"] * 2).clone().requires_grad_(True)  # |new - returns| on both sides of delta = 1
+    w, vf = torch.tensor([0.7, 0.3]), torch.tensor([0.5, 0.25])
+    adv = normalize_advantages(pp["adv"], multi_reward_weights=w)
+    parts = ppo_loss(new_logp, entropy, nv, old_logp, adv, pp["old_values"], pp["returns"], clip_range=0.1,
+                     clip_range_vf=clip_vf, ent_coef=0.01, vf_coef=vf, vf_loss_fn=getattr(F, name))
+    parts.loss.backward()
+    h = ops.PpoHyper(clip_range=0.1, clip_range_vf=clip_vf, ent_coef=0.01, vf_coef=vf.tolist(), adv_weights=w.tolist(),
+                     vf_loss=ops.VF_LOSSES[name])
+    out = ops.ppo_scalar_loss(h, new_logp.to(cuda), entropy.to(cuda), old_logp.to(cuda), pp["adv"].to(cuda),
+                              pp["old_values"].to(cuda), pp["returns"].to(cuda), nv.detach().to(cuda))
+    stats = out.stats.cpu()
+    close(stats[0], parts.loss, what="loss")
+    close(stats[5:5 + V], parts.v_loss, what="v_loss")
+    close(out.dvalues, nv.grad, what="dvalues")

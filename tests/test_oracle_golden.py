@@ -123,7 +123,8 @@ def learner_setup(name):
     return case, z, net
 
 
-LEARNER_CASES_ALL = ["cartpole", "gaussian", "microrts", "lux", "microrts_teacher", "cartpole_teacher_biased"]
+LEARNER_CASES_ALL = ["cartpole", "gaussian", "microrts", "lux", "microrts_teacher", "cartpole_teacher_biased",
+                     "cartpole_huber", "gaussian_l1"]
 
 
 def teacher_net(case, z):
