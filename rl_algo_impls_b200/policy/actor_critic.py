@@ -101,10 +101,37 @@ class ActorCritic(nn.Module):
         pass
 
     def freeze(self, freeze_policy_head: bool, freeze_value_head: bool, freeze_backbone: bool = True) -> None:
-        raise NotImplementedError("freeze_* is outside the PPO data path built here (SURVEY.md section 8)")
+        """actor_critic.py:384-395 over the networks' freeze (backbone_actor_critic.py:254-265, unet.py:221-245):
+        requires_grad of the policy head, the value head(s) and everything else (the backbone).  A trunk names its
+        heads in ``policy_head_modules`` / ``value_head_modules`` (attribute names); or implements ``freeze`` itself."""
+        net = self.network
+        if hasattr(net, "freeze"):
+            net.freeze(freeze_policy_head, freeze_value_head, freeze_backbone=freeze_backbone)
+            return
+        if not hasattr(net, "policy_head_modules") or not hasattr(net, "value_head_modules"):
+            raise NotImplementedError(f"{type(net).__name__} does not say which of its modules are the policy / value heads")
+
+        def params_of(names):
+            out = []
+            for n in names:
+                try:
+                    out += list(net.get_submodule(n).parameters())
+                except AttributeError:
+                    out.append(net.get_parameter(n))
+            return out
+
+        policy, value = params_of(net.policy_head_modules), params_of(net.value_head_modules)
+        head_ids = {id(p) for p in policy + value}
+        for p in policy:
+            p.requires_grad = not freeze_policy_head
+        for p in value:
+            p.requires_grad = not freeze_value_head
+        for p in net.parameters():
+            if id(p) not in head_ids:
+                p.requires_grad = not freeze_backbone
 
     def unfreeze(self) -> None:
-        pass
+        self.freeze(False, False, freeze_backbone=False)
 
     # -- device-resident path ---------------------------------------------------------------------
     def head_outputs(self, obs: torch.Tensor) -> HeadOutputs:

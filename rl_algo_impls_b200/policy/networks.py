@@ -55,6 +55,9 @@ class MlpActorCritic(nn.Module):
         self.pi = mlp([obs_dim, *pi_hidden, pi_out], activation, out_std=0.01)
         self.v = mlp([obs_dim, *v_hidden, 1], activation, out_std=1.0)
         self.log_std = nn.Parameter(torch.full((pi_out,), float(log_std_init))) if gaussian else None
+        # freeze_* (separate_actor_critic.py:115-126): the output layers are the heads, the hidden layers the backbone
+        self.policy_head_modules = [f"pi.{len(self.pi) - 1}"] + (["log_std"] if gaussian else [])
+        self.value_head_modules = [f"v.{len(self.v) - 1}"]
 
     def forward(self, obs: torch.Tensor) -> HeadOutputs:
         x = obs.float().reshape(obs.shape[0], -1)
@@ -76,6 +79,7 @@ class NatureCnnActorCritic(nn.Module):
         self.fc = nn.Sequential(ortho_(nn.Linear(n, flatten_dim)), nn.ReLU())
         self.pi = ortho_(nn.Linear(flatten_dim, n_actions), 0.01)
         self.v = ortho_(nn.Linear(flatten_dim, 1), 1.0)
+        self.policy_head_modules, self.value_head_modules = ["pi"], ["v"]  # freeze_*: cnn + fc are the backbone
         self.to(memory_format=torch.channels_last)
 
     def forward(self, obs: torch.Tensor) -> HeadOutputs:
@@ -107,6 +111,7 @@ class GridEncoderDecoderActorCritic(nn.Module):
             feat = self.encoder(torch.zeros(1, in_channels, *map_hw))
         self.critic = nn.Sequential(nn.Flatten(), mlp([int(np.prod(feat.shape[1:])), *v_hidden, n_values], "relu", 1.0))
         self.n_values = n_values
+        self.policy_head_modules, self.value_head_modules = ["decoder"], ["critic"]  # freeze_* (backbone_actor_critic.py:254-265)
         # NHWC in memory: cuDNN's native layout on sm_100 (no nchw<->nhwc transposes around every conv),
         # and the decoder output is then physically [B, H, W, S] -- the layout the fused loss kernel
         # reads and writes -- so permute(0, 2, 3, 1) is a free view instead of a 245 MB copy per minibatch.
@@ -149,6 +154,7 @@ class UShapedActorCritic(nn.Module):
         self.critic_conv = nn.Sequential(nn.Conv2d(channels[0], critic_channels, 3, stride=2, padding=1), nn.GELU())
         self.critic_out = ortho_(nn.Linear(critic_channels, n_values), 1.0)
         self.n_values = n_values
+        self.policy_head_modules, self.value_head_modules = ["actor"], ["critic_conv", "critic_out"]  # freeze_* (unet.py:221-245)
         self.to(memory_format=torch.channels_last)  # see GridEncoderDecoderActorCritic
 
     def forward(self, obs: torch.Tensor) -> HeadOutputs:

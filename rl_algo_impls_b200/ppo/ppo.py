@@ -411,14 +411,14 @@ class PPO(Algorithm):
                 grads, roots = [res.grads[0].to(out.pi.dtype), res.grads[1]], [out.pi, out.log_std]
             roots.append(values)
             grads.append(res.dvalues.reshape(values.shape).to(values.dtype))
-            torch.autograd.backward(roots, grads)
+            _backward(roots, grads)
             return res.stats, 1
         # distribution-level path: any policy with forward(obs, actions, masks) -> (logp, entropy, v)
         res = ops.ppo_scalar_loss(h, logp_a.detach().float().contiguous(), entropy.detach().float().contiguous(),
                                   old_logp, adv, old_values, returns, new_values.detach().float().contiguous(),
                                   moments=moments, kl_cutoff=self.kl_cutoff, pi_coef_state=pi_coef_state,
                                   teacher_logp=teacher_logp)
-        torch.autograd.backward(
+        _backward(
             [logp_a, entropy, new_values],
             [res.grads[0].to(logp_a.dtype).reshape(logp_a.shape), res.grads[1].to(entropy.dtype).reshape(entropy.shape),
              res.dvalues.reshape(new_values.shape).to(new_values.dtype)])
@@ -434,6 +434,8 @@ class PPO(Algorithm):
         kind = getattr(self.policy, "kind", None)
         if kind is None or not hasattr(self.policy, "head_outputs") or self.kl_cutoff is not None:
             return None
+        if self.freeze_policy_head or self.freeze_value_head or self.freeze_backbone:
+            return None  # requires_grad flips between epochs: a captured backward would keep the old graph
         if r.total_steps % self.batch_size != 0:
             return None
         batch = r.batch() if callable(r.batch) else r.batch  # VecRollout builds it lazily, TrajectoryRollout holds it
@@ -599,6 +601,13 @@ class PPO(Algorithm):
                     self.tb_writer.add_scalar(f"charts/{name}_{i}", float(v), timesteps_elapsed)
             else:
                 self.tb_writer.add_scalar(f"charts/{name}", float(value), timesteps_elapsed)
+
+
+def _backward(roots, grads) -> None:
+    """autograd.backward through the outputs that still lead to a trainable parameter (freeze_* can cut some off)."""
+    live = [(r, g) for r, g in zip(roots, grads) if r.requires_grad]
+    if live:
+        torch.autograd.backward([r for r, _ in live], [g for _, g in live])
 
 
 def _vec(x: np.ndarray, V: int):

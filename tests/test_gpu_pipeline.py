@@ -162,3 +162,31 @@ def test_gridnet_sampler_draws_from_the_masked_softmax(cuda):
         sigma = torch.sqrt(p * (1 - p) / B)
         assert ((freq - p).abs() <= 4.5 * sigma + 1e-4).all(), (h, freq, p)
         start += n
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C4"])
+@pytest.mark.parametrize("frozen", ["backbone", "policy_head", "value_head"])
+def test_freeze_flags_keep_the_frozen_group_fixed(cuda, cfg, frozen):
+    """freeze_policy_head / freeze_value_head / freeze_backbone (ppo.py:275-278,392-397): only the other groups move,
+    and every parameter trains again afterwards (the policy is unfrozen at the end of learn_epoch)."""
+    from rl_algo_impls_b200.envs import make_synthetic_env
+    from rl_algo_impls_b200.policy import ActorCritic
+    from rl_algo_impls_b200.ppo import PPO
+    from rl_algo_impls_b200.rollout import SyncStepRolloutGenerator
+
+    name, n_envs, n_steps, batch, pkw, akw = CONFIGS[cfg]
+    torch.manual_seed(0)
+    env = make_synthetic_env(name, n_envs, seed=1, device=cuda, pool=3)
+    policy = ActorCritic(env, subaction_mask=env.spec.subaction_mask, **pkw).to(cuda)
+    gen = SyncStepRolloutGenerator(policy, env, n_steps=n_steps, subaction_mask=env.spec.subaction_mask)
+    flags = {f"freeze_{k}": k == frozen for k in ("backbone", "policy_head", "value_head")}
+    algo = PPO(policy, cuda, None, batch_size=batch, **akw, **flags)
+    policy.freeze(flags["freeze_policy_head"], flags["freeze_value_head"], freeze_backbone=flags["freeze_backbone"])
+    fixed = {n for n, p in policy.named_parameters() if not p.requires_grad}
+    policy.unfreeze()
+    assert fixed and len(fixed) < len(list(policy.parameters()))
+    before = {n: p.detach().clone() for n, p in policy.named_parameters()}
+    algo.learn_epoch(0, 1 << 30, gen, None)
+    moved = {n for n, p in policy.named_parameters() if (p.detach() != before[n]).any().item()}
+    assert moved and not (moved & fixed), f"frozen parameters moved: {sorted(moved & fixed)}"
+    assert all(p.requires_grad for p in policy.parameters())

@@ -161,3 +161,25 @@ def test_trajectory_rollout_fixture_is_present():
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "trajectory_rollouts.npz"))
     for case in ("guided", "random_guided", "random_guided_skip", "reference_ai"):
         assert int(z[f"{case}.r0.total_steps"]) == z[f"{case}.r0.obs"].shape[0] > 0
+
+
+@pytest.mark.parametrize("key", ["C1", "C2", "C3", "C4"])
+def test_freeze_and_unfreeze_parameter_groups(key):
+    """ActorCritic.freeze (actor_critic.py:384-395): heads and backbone toggle independently; unfreeze restores all."""
+    cfg = CONFIGS[key]
+    env = make_synthetic_env(cfg.env, 2, seed=0)
+    policy = ActorCritic(env, **cfg.policy)
+    total = sum(p.numel() for p in policy.parameters())
+    count = lambda: sum(p.numel() for p in policy.parameters() if p.requires_grad)
+    policy.freeze(True, False, freeze_backbone=False)
+    without_policy_head = count()
+    policy.freeze(False, True, freeze_backbone=False)
+    without_value_head = count()
+    policy.freeze(False, False, freeze_backbone=True)
+    heads_only = count()
+    assert 0 < heads_only < total and without_policy_head < total and without_value_head < total
+    assert (total - without_policy_head) + (total - without_value_head) == heads_only
+    policy.freeze(True, True, freeze_backbone=True)
+    assert count() == 0
+    policy.unfreeze()
+    assert count() == total
