@@ -295,6 +295,19 @@ int b200rl_running_norm_reward_f32(const float* rewards, const uint8_t* dones, i
                                    double* returns, double* mean, double* var, double* count, int training,
                                    double epsilon, double clip, float* out, b200rl_stream_t stream);
 
+/* NormalizeReward(exponential_moving_mean_var=True) (wrappers/normalize.py:74-78): the variance the reward is
+ * divided by is HybridMovingMeanVar.var (utils/running_mean_std.py:120-170) -- the running moments above blended
+ * into exponential-moving ones (ExponentialMovingMeanVar.update, :79-96: weights alpha (1-alpha)^(N-1-n) over
+ * the batch rows, first batch = plain batch moments) as count / window grows to 1, window = 2 / alpha - 1.
+ * ema_* are float64 [V] device arrays, ema_init int32 [V] (0 before the first update).
+ * per_env != 0 (V must be 1) reproduces what the reference computes for SCALAR rewards (shape == ()): its update
+ * broadcasts weights[:, None] against the 1-D batch, so after the first update every env keeps its own moving
+ * moments (mean_j = sum_i w_i x_j + (1 - sum w) mean_j); ema_mean / ema_sq / ema_var then hold N entries. */
+int b200rl_running_norm_reward_ema_f32(const float* rewards, const uint8_t* dones, int64_t N, int64_t V, double gamma,
+                                       double* returns, double* mean, double* var, double* count, double* ema_mean,
+                                       double* ema_sq, double* ema_var, int* ema_init, double alpha, int per_env,
+                                       int training, double epsilon, double clip, float* out, b200rl_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * K7  multi-head reward assembly.  Replaces wrappers/info_rewards_wrapper.py:39-57
  * (InfoRewardsWrapper.step): out[n] = concat(base[n, :V0], series_0[n], ..., series_{K-1}[n]) where a series

@@ -26,6 +26,53 @@ class RunningMeanStd:
         self.count = total_count
 
 
+class ExponentialMovingMeanVar:
+    """utils/running_mean_std.py:56-96"""
+
+    def __init__(self, alpha=None, window_size=None, shape: Tuple[int, ...] = ()) -> None:
+        if window_size is not None:
+            alpha = 2 / (window_size + 1)
+        self.alpha = alpha
+        self.window_size = window_size if window_size is not None else (2 / alpha - 1)
+        self.mean, self.squared_mean = np.zeros(shape, np.float64), np.zeros(shape, np.float64)
+        self.var = np.ones(shape, np.float64)
+        self.initialized = False
+
+    def update(self, x: np.ndarray) -> None:
+        if not self.initialized:
+            self.mean = np.mean(x, axis=0, dtype=np.float64)
+            self.squared_mean = np.mean(x**2, axis=0, dtype=np.float64)
+            self.var = np.var(x, axis=0, dtype=np.float64)
+            self.initialized = True
+            return
+        weights = (self.alpha * ((1 - self.alpha) ** np.arange(x.shape[0] - 1, -1, -1)))[:, None]
+        self.mean = np.sum(weights * x, axis=0) + (1 - np.sum(weights)) * self.mean
+        self.squared_mean = np.sum(weights * (x**2), axis=0) + (1 - np.sum(weights)) * self.squared_mean
+        self.var = self.squared_mean - self.mean**2
+
+
+class HybridMovingMeanVar:
+    """utils/running_mean_std.py:120-153"""
+
+    def __init__(self, alpha=None, window_size=None, shape: Tuple[int, ...] = ()) -> None:
+        self.rms = RunningMeanStd(shape=shape)
+        self.emmv = ExponentialMovingMeanVar(alpha=alpha, window_size=window_size, shape=shape)
+
+    @property
+    def var(self):
+        frac = self.rms.count / self.emmv.window_size
+        return self.emmv.var if frac >= 1 else self.rms.var * (1 - frac) + self.emmv.var * frac
+
+    @property
+    def mean(self):
+        frac = self.rms.count / self.emmv.window_size
+        return self.emmv.mean if frac >= 1 else self.rms.mean * (1 - frac) + self.emmv.mean * frac
+
+    def update(self, x: np.ndarray) -> None:
+        self.rms.update(x)
+        self.emmv.update(x)
+
+
 class ObsNormalizer:
     def __init__(self, shape, epsilon: float = 1e-8, clip: float = 10.0, training: bool = True):
         self.rms, self.epsilon, self.clip, self.training = RunningMeanStd(shape=shape), epsilon, clip, training
@@ -38,8 +85,9 @@ class ObsNormalizer:
 
 class RewardNormalizer:
     def __init__(self, num_envs: int, shape=(), gamma: float = 0.99, epsilon: float = 1e-8, clip: float = 10.0,
-                 training: bool = True):
-        self.rms = RunningMeanStd(shape=shape)
+                 training: bool = True, exponential_moving_mean_var: bool = False, emv_window_size=None):
+        self.rms = (HybridMovingMeanVar(window_size=emv_window_size, shape=shape) if exponential_moving_mean_var
+                    else RunningMeanStd(shape=shape))
         self.gamma, self.epsilon, self.clip, self.training = gamma, epsilon, clip, training
         self.returns = np.zeros((num_envs,) + tuple(shape))
 

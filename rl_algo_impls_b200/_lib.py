@@ -113,6 +113,11 @@ PROTOTYPES = {
         _int,
         [_vp, _vp, _i64, _i64, C.c_double, _vp, _vp, _vp, _vp, _int, C.c_double, C.c_double, _vp, _vp],
     ),
+    "b200rl_running_norm_reward_ema_f32": (
+        _int,
+        [_vp, _vp, _i64, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _int, _int, C.c_double,
+         C.c_double, _vp, _vp],
+    ),
     "b200rl_rollout_store_step": (_int, [C.POINTER(_vp), C.POINTER(_vp), c_i64p, _int, _vp, _i64, _vp]),
     "b200rl_reward_assemble_f32": (
         _int,

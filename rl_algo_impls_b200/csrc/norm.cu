@@ -28,10 +28,25 @@ struct NormParams {
   long long N, D;
   double gamma, epsilon, clip;
   int training;
+  // exponential-moving moments next to the running ones (HybridMovingMeanVar, running_mean_std.py:56-170) or null
+  double* ema_mean;     // [D]
+  double* ema_sq;       // [D] moving mean of x^2
+  double* ema_var;      // [D]
+  int* ema_init;        // [D] 0 until the first update (kept per feature, like count)
+  double alpha, window;
+  // The reference's ExponentialMovingMeanVar.update broadcasts weights[:, None] against a 1-D batch (scalar
+  // rewards, shape == ()), which turns its moving moments into PER-ENV vectors after the first update
+  // (running_mean_std.py:88-96: mean_j = sum_i w_i x_j + (1 - sum w) mean_j).  per_row reproduces exactly that:
+  // D == 1 and ema_mean / ema_sq / ema_var hold N entries.
+  int per_row;
 };
 
 __global__ void __launch_bounds__(kNormBlock) running_norm_kernel(const NormParams p) {
   __shared__ double s_sum[kNormRows][kNormFeat], s_sq[kNormRows][kNormFeat];
+  __shared__ double s_wsum[kNormRows][kNormFeat], s_wsq[kNormRows][kNormFeat];
+  __shared__ double s_batch[5];  // per_row mode: batch mean, mean of squares, variance, count / window, running variance
+  __shared__ int s_first;
+  const bool ema = p.ema_mean != nullptr;
   __shared__ double s_mean[kNormFeat], s_inv[kNormFeat];
   const int fx = threadIdx.x % kNormFeat, ry = threadIdx.x / kNormFeat;
   const long long f = (long long)blockIdx.x * kNormFeat + fx;
@@ -39,8 +54,9 @@ __global__ void __launch_bounds__(kNormBlock) running_norm_kernel(const NormPara
   const bool reward = p.returns != nullptr;
 
   // ---- 1. (reward mode) returns = returns * gamma + r ; batch moments of the tracked quantity --------
-  double sum = 0.0, sq = 0.0;
+  double sum = 0.0, sq = 0.0, wsum = 0.0, wsq = 0.0;
   if (live && p.training) {
+    const double decay = 1.0 - p.alpha;
     for (long long n = ry; n < p.N; n += kNormRows) {
       double v;
       if (reward) {
@@ -51,9 +67,15 @@ __global__ void __launch_bounds__(kNormBlock) running_norm_kernel(const NormPara
       }
       sum += v;
       sq += v * v;
+      if (ema) {  // weights alpha (1 - alpha)^(N-1-n): the batch is a time-ordered window (running_mean_std.py:88-90)
+        const double w = p.alpha * pow(decay, (double)(p.N - 1 - n));
+        wsum += w * v;
+        wsq += w * (v * v);
+      }
     }
   }
   s_sum[ry][fx] = sum, s_sq[ry][fx] = sq;
+  s_wsum[ry][fx] = wsum, s_wsq[ry][fx] = wsq;
   __syncthreads();
 
   // ---- 2. Chan merge into the running moments (running_mean_std.py:16-29) --------------------------
@@ -70,6 +92,36 @@ __global__ void __launch_bounds__(kNormBlock) running_norm_kernel(const NormPara
       const double m2 = var * count + batch_var * n + delta * delta * count * n / total;
       var = m2 / total;
       p.mean[f] = mean, p.var[f] = var, p.count[f] = total;
+      if (ema && p.per_row) {
+        s_first = !p.ema_init[0];
+        s_batch[0] = batch_mean, s_batch[1] = b / n, s_batch[2] = batch_var;
+        p.ema_init[0] = 1;
+      } else if (ema) {
+        double em, esq, ev;
+        if (!p.ema_init[f]) {  // first batch: plain batch moments (running_mean_std.py:81-86)
+          em = batch_mean, esq = b / n, ev = batch_var;
+          p.ema_init[f] = 1;
+        } else {
+          double wa = 0.0, wb = 0.0;
+          for (int r = 0; r < kNormRows; ++r) wa += s_wsum[r][fx], wb += s_wsq[r][fx];
+          const double keep = pow(1.0 - p.alpha, n);  // 1 - sum of the weights
+          em = wa + keep * p.ema_mean[f];
+          esq = wb + keep * p.ema_sq[f];
+          ev = esq - em * em;
+        }
+        p.ema_mean[f] = em, p.ema_sq[f] = esq, p.ema_var[f] = ev;
+      }
+    }
+    if (ema && p.per_row) {
+      s_batch[3] = p.count[f] / p.window, s_batch[4] = var;
+    } else if (ema) {  // HybridMovingMeanVar.mean / .var: running moments until `window` samples were seen, then the moving ones
+      const double frac = p.count[f] / p.window;
+      if (frac >= 1.0) {
+        mean = p.ema_mean[f], var = p.ema_var[f];
+      } else {
+        mean = mean * (1.0 - frac) + p.ema_mean[f] * frac;
+        var = var * (1.0 - frac) + p.ema_var[f] * frac;
+      }
     }
     s_mean[fx] = mean;
     s_inv[fx] = 1.0 / sqrt(var + p.epsilon);
@@ -78,8 +130,26 @@ __global__ void __launch_bounds__(kNormBlock) running_norm_kernel(const NormPara
 
   // ---- 3. normalise this tile's columns ------------------------------------------------------------
   if (!live) return;
-  const double mean = reward ? 0.0 : s_mean[fx], inv = s_inv[fx];
+  const double mean = reward ? 0.0 : s_mean[fx];
+  double inv = s_inv[fx];
+  const double keep = ema && p.per_row ? pow(1.0 - p.alpha, (double)p.N) : 0.0;
   for (long long n = ry; n < p.N; n += kNormRows) {
+    if (ema && p.per_row) {  // env n's own moving moments of its discounted return (D == 1)
+      double em = p.ema_mean[n], esq = p.ema_sq[n], ev = p.ema_var[n];
+      if (p.training) {
+        if (s_first) {
+          em = s_batch[0], esq = s_batch[1], ev = s_batch[2];
+        } else {
+          const double r = p.returns[n];
+          em = (1.0 - keep) * r + keep * em;
+          esq = (1.0 - keep) * (r * r) + keep * esq;
+          ev = esq - em * em;
+        }
+        p.ema_mean[n] = em, p.ema_sq[n] = esq, p.ema_var[n] = ev;
+      }
+      const double frac = s_batch[3];
+      inv = 1.0 / sqrt((frac >= 1.0 ? ev : s_batch[4] * (1.0 - frac) + ev * frac) + p.epsilon);
+    }
     double v = ((double)p.x[n * p.D + f] - mean) * inv;
     v = fmin(fmax(v, -p.clip), p.clip);
     p.out[n * p.D + f] = (float)v;
@@ -105,7 +175,8 @@ extern "C" int b200rl_running_norm_obs_f32(const float* x, int64_t N, int64_t D,
   using namespace b200rl;
   B200RL_REQUIRE(x && mean && var && count && out, "running_norm_obs: null pointer");
   B200RL_REQUIRE(N >= 1 && D >= 1, "running_norm_obs: bad shape N=%lld D=%lld", (long long)N, (long long)D);
-  NormParams p{x, out, mean, var, count, nullptr, nullptr, N, D, 0.0, epsilon, clip, training};
+  NormParams p{x, out, mean, var, count, nullptr, nullptr, N, D, 0.0, epsilon, clip, training,
+               nullptr, nullptr, nullptr, nullptr, 0.0, 1.0, 0};
   return launch_norm(p, (cudaStream_t)stream);
 }
 
@@ -116,6 +187,23 @@ extern "C" int b200rl_running_norm_reward_f32(const float* rewards, const uint8_
   using namespace b200rl;
   B200RL_REQUIRE(rewards && dones && returns && mean && var && count && out, "running_norm_reward: null pointer");
   B200RL_REQUIRE(N >= 1 && V >= 1, "running_norm_reward: bad shape N=%lld V=%lld", (long long)N, (long long)V);
-  NormParams p{rewards, out, mean, var, count, returns, dones, N, V, gamma, epsilon, clip, training};
+  NormParams p{rewards, out, mean, var, count, returns, dones, N, V, gamma, epsilon, clip, training,
+               nullptr, nullptr, nullptr, nullptr, 0.0, 1.0, 0};
+  return launch_norm(p, (cudaStream_t)stream);
+}
+
+extern "C" int b200rl_running_norm_reward_ema_f32(const float* rewards, const uint8_t* dones, int64_t N, int64_t V,
+                                                  double gamma, double* returns, double* mean, double* var,
+                                                  double* count, double* ema_mean, double* ema_sq, double* ema_var,
+                                                  int* ema_init, double alpha, int per_env, int training,
+                                                  double epsilon, double clip, float* out, b200rl_stream_t stream) {
+  using namespace b200rl;
+  B200RL_REQUIRE(rewards && dones && returns && mean && var && count && out, "running_norm_reward_ema: null pointer");
+  B200RL_REQUIRE(ema_mean && ema_sq && ema_var && ema_init, "running_norm_reward_ema: null moving-moment pointer");
+  B200RL_REQUIRE(N >= 1 && V >= 1, "running_norm_reward_ema: bad shape N=%lld V=%lld", (long long)N, (long long)V);
+  B200RL_REQUIRE(alpha > 0.0 && alpha < 1.0, "running_norm_reward_ema: alpha=%g must be in (0, 1)", alpha);
+  B200RL_REQUIRE(!per_env || V == 1, "running_norm_reward_ema: per-env moving moments are the scalar-reward case (V=1)");
+  NormParams p{rewards, out, mean, var, count, returns, dones, N, V, gamma, epsilon, clip, training,
+               ema_mean, ema_sq, ema_var, ema_init, alpha, 2.0 / alpha - 1.0, per_env};
   return launch_norm(p, (cudaStream_t)stream);
 }

@@ -340,6 +340,37 @@ def running_norm_reward(rewards: torch.Tensor, dones: torch.Tensor, returns: tor
     return out
 
 
+def running_norm_reward_ema(rewards: torch.Tensor, dones: torch.Tensor, returns: torch.Tensor, mean: torch.Tensor,
+                            var: torch.Tensor, count: torch.Tensor, ema_mean: torch.Tensor, ema_sq: torch.Tensor,
+                            ema_var: torch.Tensor, ema_init: torch.Tensor, alpha: float, gamma: float, training: bool,
+                            epsilon: float, clip: float, out: Optional[torch.Tensor] = None,
+                            per_env: bool = False) -> torch.Tensor:
+    """NormalizeReward.step with exponential_moving_mean_var=True (wrappers/normalize.py:74-110 over
+    HybridMovingMeanVar, utils/running_mean_std.py:120-170): running and exponential-moving moments of the
+    discounted returns updated together, the reward divided by the blended standard deviation."""
+    _cuda(rewards, torch.float32, "rewards")
+    N = rewards.shape[0]
+    V = rewards.numel() // N
+    d = _as_u8(dones, "dones")
+    _cuda(returns, torch.float64, "returns")
+    if returns.numel() != N * V or d.numel() != N:
+        raise ValueError("returns must be [N, V] and dones [N]")
+    for name, t in (("mean", mean), ("var", var), ("count", count), ("ema_mean", ema_mean), ("ema_sq", ema_sq),
+                    ("ema_var", ema_var)):
+        _cuda(t, torch.float64, name)
+        want = N if per_env and name.startswith("ema_") else V
+        if t.numel() != want:
+            raise ValueError(f"{name} must have {want} entries")
+    _cuda(ema_init, torch.int32, "ema_init")
+    out = torch.empty_like(rewards) if out is None else _cuda(out, torch.float32, "out")
+    rc = _call("b200rl_running_norm_reward_ema_f32", 1, _lib.lib().b200rl_running_norm_reward_ema_f32,
+               rewards.data_ptr(), d.data_ptr(), N, V, float(gamma), returns.data_ptr(), mean.data_ptr(), var.data_ptr(),
+               count.data_ptr(), ema_mean.data_ptr(), ema_sq.data_ptr(), ema_var.data_ptr(), ema_init.data_ptr(),
+               float(alpha), int(bool(per_env)), int(training), float(epsilon), float(clip), out.data_ptr(), _stream())
+    check(rc, "b200rl_running_norm_reward_ema_f32")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # K7
 def reward_assemble(base: torch.Tensor, series: Sequence[torch.Tensor], terminations: Optional[torch.Tensor],

@@ -1,4 +1,6 @@
 from .info_rewards_wrapper import InfoRewardsWrapper
-from .normalize import NormalizeObservation, NormalizeReward, RunningMeanStd
+from .normalize import (ExponentialMovingMeanVar, HybridMovingMeanVar, NormalizeObservation, NormalizeReward,
+                        RunningMeanStd)
 
-__all__ = ["InfoRewardsWrapper", "NormalizeObservation", "NormalizeReward", "RunningMeanStd"]
+__all__ = ["InfoRewardsWrapper", "NormalizeObservation", "NormalizeReward", "RunningMeanStd", "ExponentialMovingMeanVar",
+           "HybridMovingMeanVar"]

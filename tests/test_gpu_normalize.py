@@ -120,3 +120,28 @@ def test_reward_assemble_rejects_bad_arguments(cuda):
         ops.reward_assemble(base, [torch.zeros(4, device=cuda)], None, None, [True])
     out = ops.reward_assemble(base, [], None, None, [])
     assert out.shape == (4, 1)
+
+
+@pytest.mark.parametrize("tag", ["scalar", "multi"])
+def test_ema_reward_normalizer_vs_reference_fixture(cuda, tag):
+    """NormalizeReward(exponential_moving_mean_var=True) on a device env vs the live reference: normalised rewards
+    1e-6, float64 moments 1e-10 (the kernel's pow / summation order differ from numpy's in the last bits)."""
+    from rl_algo_impls_b200.wrappers import NormalizeReward
+
+    z = load("normalizers_ema")
+    rew, dones = z[f"{tag}.rewards"], z[f"{tag}.dones"]
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    script = [(to(rew[t]), to(dones[t]), torch.zeros(rew.shape[1], dtype=torch.bool, device=cuda), {}) for t in range(rew.shape[0])]
+    env = NormalizeReward(_ScriptedDeviceEnv(script, cuda), gamma=0.98, shape=tuple(rew.shape[2:]),
+                          exponential_moving_mean_var=True, emv_window_size=float(z[f"{tag}.window"]))
+    for t in range(rew.shape[0]):
+        _, out, _, _, _ = env.step(None)
+        np.testing.assert_allclose(out.cpu().numpy(), z[f"{tag}.out"][t], rtol=1e-6, atol=1e-6)
+    # scalar rewards: the reference's moving moments are per-env vectors [N] (its update broadcasts against the 1-D batch)
+    flat = lambda a: np.asarray(a, np.float64).reshape(-1)
+    np.testing.assert_allclose(flat(env.rms.var.cpu().numpy()), flat(z[f"{tag}.var"]), rtol=1e-10)
+    np.testing.assert_allclose(flat(env.rms.emmv.mean.cpu().numpy()), flat(z[f"{tag}.ema_mean"]), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(flat(env.rms.emmv.var.cpu().numpy()), flat(z[f"{tag}.ema_var"]), rtol=1e-10)
+    np.testing.assert_allclose(flat(env.rms.rms.var.cpu().numpy()), flat(z[f"{tag}.rms_var"]), rtol=1e-12)
+    np.testing.assert_allclose(env.returns.cpu().numpy(), z[f"{tag}.returns"], rtol=1e-12, atol=1e-12)
+    assert env.rms.rms.count == float(z[f"{tag}.count"]) and env.rms.emmv.initialized

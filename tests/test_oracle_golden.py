@@ -250,3 +250,17 @@ def test_reward_assembly_matches_the_reference(case):
         got = assemble_rewards(z[f"{case}.base"][t], [s.copy() for s in z[f"{case}.series"][t]], z[f"{case}.terminations"][t],
                                z[f"{case}.truncations"][t], z[f"{case}.episode_end"], mult)
         np.testing.assert_array_equal(got, z[f"{case}.rewards"][t])
+
+
+@pytest.mark.parametrize("tag", ["scalar", "multi"])
+def test_ema_reward_normalizer_matches_the_reference(tag):
+    """oracle HybridMovingMeanVar / ExponentialMovingMeanVar vs NormalizeReward(exponential_moving_mean_var=True)."""
+    from oracle.normalize import RewardNormalizer
+
+    z = load("normalizers_ema")
+    rew, dones = z[f"{tag}.rewards"], z[f"{tag}.dones"]
+    r = RewardNormalizer(rew.shape[1], rew.shape[2:], gamma=0.98, exponential_moving_mean_var=True,
+                         emv_window_size=float(z[f"{tag}.window"]))
+    for t in range(rew.shape[0]):
+        np.testing.assert_array_equal(r.step(rew[t], dones[t]), z[f"{tag}.out"][t])
+    np.testing.assert_array_equal(np.asarray(r.rms.var), z[f"{tag}.var"])
