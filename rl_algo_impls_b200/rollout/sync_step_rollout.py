@@ -42,6 +42,7 @@ class _Uploader:
         self._seen: Dict[tuple, int] = {}        # (root pointer, nbytes) -> sightings before registration
         self._registered: Dict[tuple, bool] = {}  # (root pointer, nbytes) -> cudaHostRegister succeeded
         self._registered_bytes = 0
+        self._roots: list = []  # the page-locked arrays, kept alive while they are registered
         self.bytes = 0  # host -> device bytes moved so far
 
     def _page_locked(self, a: np.ndarray) -> bool:
@@ -65,7 +66,7 @@ class _Uploader:
         self._registered[key] = ok
         if ok:
             self._registered_bytes += root.nbytes
-            self._roots = getattr(self, "_roots", []) + [root]  # keep the buffer alive while it is registered
+            self._roots.append(root)
         return ok
 
     def close(self) -> None:
