@@ -27,12 +27,7 @@ struct GatherParams {
   long long B, n_src_rows;
 };
 
-// ITER 128-bit loads per thread: a chunk is ITER * 4 KB.  16 KB chunks keep the most bytes in flight per CTA; a
-// call with few chunks (short minibatches of mid-sized rows, e.g. Atari frames) takes smaller ones so that the
-// grid still covers the machine several times over and its last wave is not half empty.
-template <int ITER>
 __global__ void __launch_bounds__(kGatherBlock) gather_wide_kernel(const GatherParams p) {
-  constexpr int kChunk = ITER * 16 * kGatherBlock;
   const long long item = blockIdx.x;
   int t = 0;
   while (t + 1 < p.n && item >= p.first_item[t + 1]) ++t;
@@ -42,8 +37,8 @@ __global__ void __launch_bounds__(kGatherBlock) gather_wide_kernel(const GatherP
   const long long row = p.idx[b];
   if (row < 0 || row >= p.n_src_rows) return;
   const long long rb = p.row_bytes[t];
-  const long long begin = (long long)chunk * kChunk;
-  const long long bytes = (rb - begin < kChunk) ? rb - begin : kChunk;
+  const long long begin = (long long)chunk * kChunkBytes;
+  const long long bytes = (rb - begin < kChunkBytes) ? rb - begin : kChunkBytes;
   const uint8_t* s = p.src[t] + row * rb + begin;
   uint8_t* d = p.dst[t] + b * rb + begin;
   const int tid = threadIdx.x;
@@ -51,7 +46,7 @@ __global__ void __launch_bounds__(kGatherBlock) gather_wide_kernel(const GatherP
     const uint4* s4 = reinterpret_cast<const uint4*>(s);
     uint4* d4 = reinterpret_cast<uint4*>(d);
     const int n4 = (int)(bytes >> 4);
-    constexpr int kIter = ITER;
+    constexpr int kIter = kChunkBytes / 16 / kGatherBlock;  // 4
     uint4 v[kIter];
 #pragma unroll
     for (int i = 0; i < kIter; ++i) {
@@ -179,6 +174,7 @@ extern "C" int b200rl_gather_rows(const void* const* src_host, void* const* dst_
   wide.idx = narrow.idx = reinterpret_cast<const long long*>(idx);
   wide.B = narrow.B = B;
   wide.n_src_rows = narrow.n_src_rows = n_src_rows;
+  long long items = 0;
   for (int t = 0; t < n_tensors; ++t) {
     B200RL_REQUIRE(src_host[t] && dst_host[t] && row_bytes_host[t] >= 0, "gather_rows: tensor %d is null", t);
     if (row_bytes_host[t] == 0) continue;
@@ -187,28 +183,17 @@ extern "C" int b200rl_gather_rows(const void* const* src_host, void* const* dst_
     g.src[k] = static_cast<const uint8_t*>(src_host[t]);
     g.dst[k] = static_cast<uint8_t*>(dst_host[t]);
     g.row_bytes[k] = row_bytes_host[t];
+    if (&g == &wide) {
+      g.chunks_per_row[k] = (int)((row_bytes_host[t] + kChunkBytes - 1) / kChunkBytes);
+      g.first_item[k] = items;
+      items += B * g.chunks_per_row[k];
+      g.first_item[k + 1] = items;
+    }
   }
   cudaStream_t s = (cudaStream_t)stream;
   if (wide.n) {
-    // chunk size: the largest of 16 / 8 / 4 KB that still yields >= 4 waves of CTAs (8 CTAs per SM)
-    const long long enough = (long long)device_info().sm_count * 8 * 4;
-    long long items = 0;
-    int iter = 4;
-    for (;; iter >>= 1) {
-      const long long chunk = (long long)iter * 16 * kGatherBlock;
-      items = 0;
-      for (int k = 0; k < wide.n; ++k) {
-        wide.chunks_per_row[k] = (int)((wide.row_bytes[k] + chunk - 1) / chunk);
-        wide.first_item[k] = items;
-        items += B * wide.chunks_per_row[k];
-        wide.first_item[k + 1] = items;
-      }
-      if (items >= enough || iter == 1) break;
-    }
     B200RL_UNSUPPORTED(items > 0x7fffffffLL, "gather_rows: %lld chunks in one call", items);
-    if (iter == 4) gather_wide_kernel<4><<<(unsigned)items, kGatherBlock, 0, s>>>(wide);
-    else if (iter == 2) gather_wide_kernel<2><<<(unsigned)items, kGatherBlock, 0, s>>>(wide);
-    else gather_wide_kernel<1><<<(unsigned)items, kGatherBlock, 0, s>>>(wide);
+    gather_wide_kernel<<<(unsigned)items, kGatherBlock, 0, s>>>(wide);
   }
   if (narrow.n) {
     const long long threads = B * narrow.n;
