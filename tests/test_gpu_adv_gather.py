@@ -113,3 +113,28 @@ def test_num_actions_matches_the_reference_rule(cuda, kind):
                    subaction_mask=gates, action_plane_space=spaces.MultiDiscrete(nvec), include_num_actions=True)
     got = r.batch().num_actions.cpu().numpy().reshape(T, N)
     np.testing.assert_allclose(got, want, rtol=1e-6)
+
+
+def test_gather_full_size_round_trip(cuda):
+    """The whole C4 rollout (12,288 rows: 75,776 B observations, 19,968 B masks, 1,792 B actions, four scalars)
+    shuffled by one gather and unshuffled by a second: bit-identical to the source; every minibatch slice of the
+    shuffled copy equals the rows its indices name."""
+    from rl_algo_impls_b200 import ops
+
+    M = 12288
+    g = torch.Generator(device=cuda).manual_seed(1)
+    srcs = [torch.rand((M, 74, 16, 16), device=cuda, generator=g),
+            torch.rand((M, 256, 78), device=cuda, generator=g) < 0.5,
+            torch.randint(0, 49, (M, 256, 7), device=cuda, generator=g, dtype=torch.uint8),
+            torch.randn(M, device=cuda, generator=g), torch.randn(M, device=cuda, generator=g),
+            torch.randn(M, device=cuda, generator=g), torch.randn(M, device=cuda, generator=g)]
+    perm = torch.randperm(M, device=cuda, generator=g)
+    inverse = torch.empty_like(perm)
+    inverse[perm] = torch.arange(M, device=cuda)
+    shuffled = ops.gather_rows(srcs, perm)
+    restored = ops.gather_rows(shuffled, inverse)
+    for s, r in zip(srcs, restored):
+        assert torch.equal(s, r)
+    mb = perm[3 * 3072:4 * 3072]
+    for s, sh, o in zip(srcs, shuffled, ops.gather_rows(srcs, mb)):
+        assert torch.equal(o, sh[3 * 3072:4 * 3072]) and torch.equal(o[:5], s[mb[:5]])

@@ -206,3 +206,72 @@ def test_fused_bf16_logits_and_gradients(cuda):
     got, want = out.grads[0].float().cpu(), o32["dlogits"]
     assert ((got - want).abs() <= 2 ** -8 * want.abs() + 1e-3 * want.abs().max() * 2 ** -8).all()  # bf16: 8 bits of mantissa
     assert (got[~inp["mask"]] == 0).all()
+
+
+@pytest.mark.parametrize("B,HW,nvec,gates,n_pick,V,unit_p", [
+    (3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 0.06),   # the C4 minibatch (558 MB of logits + gradients)
+    (512, 4096, LUX_NVEC, LUX_GATES, 1, 13, 0.02),            # the C5 roofline shape, pick head, 13 value heads
+])
+def test_fused_loss_at_full_size_properties(cuda, B, HW, nvec, gates, n_pick, V, unit_p):
+    """BASELINE-size launches, checked through properties that do not need a full-size oracle run:
+    a slice of samples against the oracle; per-sample results independent of the batch they sit in (bit-exact);
+    gradients of masked entries exactly zero; gradients linear in loss_scale (exact for a power of two);
+    the total loss equal to the combination of its own reported parts; determinism across launches."""
+    from benchmarks.kernels import gridnet_tensors
+    from rl_algo_impls_b200 import ops
+
+    logits, mask, pick_mask, actions, pick = gridnet_tensors(B, HW, nvec, n_pick, unit_p)
+    spec = spec_of(nvec, gates, n_pick)
+    g = torch.Generator(device=cuda).manual_seed(3)
+    # legal actions (a masked action drives the log-prob to -inf in the reference and here alike)
+    start, chosen = 0, []
+    for n in nvec:
+        score = torch.rand((B, HW, n), device=cuda, generator=g).masked_fill(~mask[..., start:start + n], -1.0)
+        chosen.append(score.argmax(-1))
+        start += n
+    actions = torch.stack(chosen, -1).to(actions.dtype)
+    if n_pick:
+        pick = torch.rand((B, n_pick, HW), device=cuda, generator=g).masked_fill(~pick_mask, -1.0).argmax(-1)
+    vs = (B,) if V == 1 else (B, V)
+    rnd = lambda *s: torch.randn(*s, device=cuda, generator=g)
+    adv, ov, rt, nv = rnd(*vs), rnd(*vs), rnd(*vs), rnd(*vs)
+    w = np.linspace(0.2, 1.0, V).tolist() if V > 1 else None
+    vf = np.linspace(0.5, 1.0, V).tolist()
+    fwd_logp, fwd_ent = ops.gridnet_fwd(spec, logits, mask, pick_mask, actions, pick)
+    old_logp = fwd_logp + rnd(B) * 0.05
+
+    def run(scale, rows=slice(None)):
+        h = ops.PpoHyper(clip_range=0.1, clip_range_vf=0.1, ent_coef=0.01, vf_coef=vf, adv_weights=w, loss_scale=scale,
+                         adv_mode=ops.ADV_NONE if V == 1 else ops.ADV_NORMALIZE)
+        sub = lambda t: None if t is None else t[rows].contiguous()
+        return ops.ppo_gridnet_loss(h, spec, sub(logits), sub(mask), sub(pick_mask), sub(actions), sub(pick), sub(old_logp),
+                                    sub(adv), sub(ov), sub(rt), sub(nv), want_logp=True)
+
+    full = run(1.0)
+    S = sum(nvec)
+    # (1) the forward-only kernel and the fused kernel agree bit for bit on log-prob / entropy
+    assert torch.equal(full.logp, fwd_logp) and torch.equal(full.entropy, fwd_ent)
+    # (2) a slice against the oracle
+    rows = slice(B // 3, B // 3 + 8)
+    cpu = lambda t: None if t is None else t[rows].cpu()
+    inp = dict(logits=cpu(logits), mask=cpu(mask), pick_mask=cpu(pick_mask), actions=cpu(actions).long(),
+               pick_actions=cpu(pick))
+    _, dist, action = oracle_dist(inp, nvec, gates, HW)
+    close(full.logp[rows], dist.log_prob(action).detach(), what="logp slice")
+    close(full.entropy[rows], dist.entropy().detach(), what="entropy slice")
+    # (3) a sample's log-prob / entropy do not depend on the batch around it
+    part = run(1.0, rows)
+    assert torch.equal(part.logp, full.logp[rows]) and torch.equal(part.entropy, full.entropy[rows])
+    # (4) masked entries: exactly zero gradient, everywhere
+    assert int((full.grads[0][..., :S][~mask] != 0).sum().item()) == 0
+    empty = ~mask.any(-1).any(-1)
+    if n_pick == 0 and bool(empty.any()):
+        assert float(full.logp[empty].abs().max()) == 0.0 and float(full.entropy[empty].abs().max()) == 0.0
+    # (5) linear in loss_scale, deterministic
+    half, again = run(0.5), run(1.0)
+    assert torch.equal(half.grads[0] * 2, full.grads[0]) and torch.equal(half.dvalues * 2, full.dvalues)
+    assert torch.equal(again.grads[0], full.grads[0]) and torch.equal(again.stats, full.stats)
+    # (6) the reported total is the combination of the reported parts (ppo.py:357-361)
+    st = full.stats.cpu().double()
+    total = st[1] + 0.01 * st[2] + sum(vf[v] * st[5 + v] for v in range(V))
+    assert abs(float(total - st[0])) <= 1e-5 * max(1.0, abs(float(st[0])))
