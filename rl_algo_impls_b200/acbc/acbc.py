@@ -31,51 +31,62 @@ class ACBC(Algorithm):
         self.scale_loss_by_num_actions = scale_loss_by_num_actions
         self.last_stats: Optional[Dict[str, Union[float, np.ndarray]]] = None
 
+    # -- one minibatch: imitation log-likelihood + value regression (acbc.py:111-121) -----------------------------
+    def _minibatch(self, mb, value_weights: torch.Tensor, n_accumulate: int) -> torch.Tensor:
+        """Backward of one minibatch; returns the detached [loss, pi_loss, v_loss...] row on the device."""
+        self.policy.reset_noise(self.batch_size)
+        logp, _, values = self.policy(mb.obs, mb.actions, action_masks=mb.action_masks)
+        if self.scale_loss_by_num_actions:  # per-sample mean over the cells that had a legal action
+            logp = torch.where(mb.num_actions > 0, logp / mb.num_actions, 0)
+        imitation = -logp.mean()
+        regression = (values - mb.returns).square().mean(0)
+        objective = imitation + (value_weights * regression).sum()
+        scaled = objective / n_accumulate if n_accumulate > 1 else objective  # acbc.py:123-124
+        scaled.backward()
+        return torch.cat([t.detach().reshape(-1).float() for t in (scaled, imitation, regression)])
+
+    def _epochs(self, r) -> np.ndarray:
+        """n_epochs passes over the rollout; mean of the LAST epoch's minibatch rows (one device -> host read)."""
+        value_weights = torch.as_tensor(np.array(self.vf_coef), dtype=torch.float32, device=self.device)
+        accumulate = r.num_minibatches(self.batch_size) if self.gradient_accumulation else 1
+        rows: List[torch.Tensor] = []
+        for _ in range(self.n_epochs):
+            rows = []  # only the last epoch's rows are reported
+            for mb in r.minibatches(self.batch_size, shuffle=not self.gradient_accumulation):
+                rows.append(self._minibatch(mb, value_weights, accumulate))
+                if accumulate == 1:
+                    self.optimizer_step()
+            if accumulate > 1:
+                self.optimizer_step()
+        return torch.stack(rows).double().mean(0).cpu().numpy()
+
+    def _report(self, r, host: np.ndarray, seconds: float) -> None:
+        spread = np.var(r.y_true).item()
+        self.last_stats = {"loss": float(host[0]), "pi_loss": float(host[1]),
+                           "v_loss": host[2:] if host.size > 3 else float(host[2]),
+                           "explained_var": np.nan if spread == 0 else 1 - np.var(r.y_true - r.y_pred).item() / spread}
+        if self.tb_writer is None:
+            return
+        for name, value in self.last_stats.items():
+            for i, x in enumerate(np.atleast_1d(value)):
+                self.tb_writer.add_scalar(f"losses/{name}" + (f"_{i}" if np.ndim(value) else ""), float(x))
+        self.tb_writer.add_scalar("train/steps_per_second", r.total_steps / seconds)
+        if hasattr(self.tb_writer, "on_steps"):
+            self.tb_writer.on_steps(r.total_steps)
+
     def learn(self: ACBCSelf, train_timesteps: int, rollout_generator, callbacks: Optional[List] = None,
               total_timesteps: Optional[int] = None, start_timesteps: int = 0) -> ACBCSelf:
-        total_timesteps = train_timesteps if total_timesteps is None else total_timesteps
-        assert start_timesteps + train_timesteps <= total_timesteps
-        elapsed = start_timesteps
-        while elapsed < start_timesteps + train_timesteps:
-            t0 = perf_counter()
+        budget_end = start_timesteps + train_timesteps
+        assert budget_end <= (train_timesteps if total_timesteps is None else total_timesteps)
+        if self.scale_loss_by_num_actions and hasattr(rollout_generator, "include_num_actions"):
+            rollout_generator.include_num_actions = True
+        done = start_timesteps
+        while done < budget_end:
+            began = perf_counter()
             update_learning_rate(self.optimizer, self.learning_rate)
-            if self.scale_loss_by_num_actions and hasattr(rollout_generator, "include_num_actions"):
-                rollout_generator.include_num_actions = True
             r = rollout_generator.rollout(self.gamma, self.gae_lambda)
-            elapsed += r.total_steps
-            vf_coef = torch.as_tensor(np.array(self.vf_coef), dtype=torch.float32, device=self.device)
-            n_mb = r.num_minibatches(self.batch_size)
-            rows: List[torch.Tensor] = []
-            for _ in range(self.n_epochs):
-                rows.clear()  # the last epoch's losses are the ones reported
-                for mb in r.minibatches(self.batch_size, shuffle=not self.gradient_accumulation):
-                    self.policy.reset_noise(self.batch_size)
-                    logp, _, values = self.policy(mb.obs, mb.actions, action_masks=mb.action_masks)
-                    if self.scale_loss_by_num_actions:
-                        logp = torch.where(mb.num_actions > 0, logp / mb.num_actions, 0)
-                    pi_loss = -logp.mean()
-                    v_loss = (values - mb.returns).square().mean(0)
-                    loss = pi_loss + (vf_coef * v_loss).sum()
-                    if self.gradient_accumulation:
-                        loss = loss / n_mb
-                    loss.backward()
-                    if not self.gradient_accumulation:
-                        self.optimizer_step()
-                    rows.append(torch.cat([t.detach().reshape(-1).float() for t in (loss, pi_loss, v_loss)]))
-                if self.gradient_accumulation:
-                    self.optimizer_step()
-            host = torch.stack(rows).double().mean(0).cpu().numpy()  # one device -> host read per iteration
-            var_y = np.var(r.y_true).item()
-            self.last_stats = {"loss": float(host[0]), "pi_loss": float(host[1]),
-                               "v_loss": host[2:] if host.size > 3 else float(host[2]),
-                               "explained_var": np.nan if var_y == 0 else 1 - np.var(r.y_true - r.y_pred).item() / var_y}
-            if self.tb_writer is not None:
-                for k, v in self.last_stats.items():
-                    for i, x in enumerate(np.atleast_1d(v)):
-                        self.tb_writer.add_scalar(f"losses/{k}" + (f"_{i}" if np.ndim(v) else ""), float(x))
-                self.tb_writer.add_scalar("train/steps_per_second", r.total_steps / (perf_counter() - t0))
-                if hasattr(self.tb_writer, "on_steps"):
-                    self.tb_writer.on_steps(r.total_steps)
+            done += r.total_steps
+            self._report(r, self._epochs(r), perf_counter() - began)
             if callbacks and not all(c.on_step(timesteps_elapsed=r.total_steps) for c in callbacks):
                 break
         return self

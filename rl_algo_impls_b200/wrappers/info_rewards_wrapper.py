@@ -6,7 +6,6 @@ Mirrors ``rl_algo_impls/wrappers/info_rewards_wrapper.py:13-64`` (constructor ke
 reward row a multi-head critic trains on -- one K7 launch, no host synchronisation, output at a fixed address
 (capturable in the rollout step's CUDA graph).  A host (numpy) env keeps the reference's numpy wrapper.
 """
-import collections.abc
 from typing import Dict, List, Optional, Union
 
 import numpy as np
@@ -29,17 +28,11 @@ class InfoRewardsWrapper(_Wrapper):
         super().__init__(env)
         self.info_paths = info_paths
         K = len(info_paths)
-        if isinstance(episode_end, collections.abc.Sequence):
-            self.episode_end = np.array(episode_end, dtype=np.bool_)
-        else:
-            self.episode_end = np.full((K,), episode_end, dtype=np.bool_)
-        if isinstance(multiplier, collections.abc.Sequence):
-            self.multiplier: Optional[np.ndarray] = np.array(multiplier, dtype=np.float32)
-        elif multiplier is not None and multiplier != 1.0:
-            self.multiplier = np.full((K,), multiplier, dtype=np.float32)
-        else:
-            self.multiplier = None
-        assert len(self.episode_end) == K and (self.multiplier is None or len(self.multiplier) == K)
+        per_series = lambda x, dtype: np.array(np.broadcast_to(np.asarray(x, dtype=dtype), (K,)))
+        # one flag / factor per series; a scalar applies to all of them (info_rewards_wrapper.py:23-37)
+        self.episode_end = per_series(episode_end, np.bool_)
+        no_scaling = multiplier is None or (np.isscalar(multiplier) and multiplier == 1.0)
+        self.multiplier: Optional[np.ndarray] = None if no_scaling else per_series(multiplier, np.float32)
         self._out: Optional[torch.Tensor] = None
 
     def step(self, action):
