@@ -100,6 +100,14 @@ __device__ __forceinline__ void stg_stream_u4(uint4* p, const uint4& v) {
                : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while the kernel ahead of
+// it on the stream is still running: its launch latency and prologue overlap that kernel's tail.  pdl_wait()
+// blocks until the kernel ahead has completed and its memory is visible (a no-op without the attribute);
+// pdl_trigger() in the kernel ahead lets the dependent grid be scheduled once every CTA has called it or exited.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 

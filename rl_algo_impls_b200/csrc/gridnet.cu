@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(kStreamBlock) gridnet_stream_kernel(const __gr
                        G.pick_list + ((b * G.n_pick) * G.chunks + chunk) * kChunkCells,
                        G.pick_count + (b * G.n_pick) * G.chunks + chunk, (long long)G.chunks * kChunkCells, G.chunks};
   stream_chunk<LT, ZERO, kStreamBlock>(G, b, chunk, bitmap, out, StreamStage{G.image_bytes ? stream_smem : nullptr, zeros, &bar});
+  pdl_trigger();  // the compute launch may be scheduled: it waits for this grid's completion before reading the lists
   if (ZERO && G.image_bytes && threadIdx.x == 0) bulk_wait_read();  // the zero buffer must outlive the copies that read it
 }
 
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
   }
 
   // ---- 1. this sample's lists ------------------------------------------------------------------------
+  if (!SELF_STREAM) pdl_wait();  // the streaming launch ahead of this one wrote them (programmatic dependent launch)
   if (tid == 0) {
     int acc = 0;
     for (int c = 0; c < G.chunks; ++c) prefix[c] = acc, acc += SELF_STREAM ? s_counts[0] : G.unit_count[b * G.chunks + c];
@@ -540,6 +542,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
     row[kPolicyStats + v] = r.x, row[kPolicyStats + P.V + v] = r.y;
   }
   if (MODE == kFwd) return;
+  if (MODE == kPpo) pdl_trigger();  // the stats finaliser may be scheduled; it waits for this grid to complete
   if (SELF_STREAM && G.image_bytes && tid == 0) {  // the zero fill of this sample's rows must have landed
     bulk_wait_all();
     fence_async_all();
@@ -695,7 +698,17 @@ static int launch_compute(GridDev& G, const PpoDev& P, cudaStream_t stream) {
       return B200RL_ECUDA;
     }
   }
-  kernel<<<(unsigned)G.B, BLOCK, smem, stream>>>(G, P);
+  if (SELF_STREAM) {
+    kernel<<<(unsigned)G.B, BLOCK, smem, stream>>>(G, P);
+  } else {  // dependent of the streaming launch: prologue (normaliser, prefetches) overlaps its tail
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)G.B), cfg.blockDim = dim3(BLOCK), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, G, P);
+  }
   return check_launch("gridnet");
 }
 

@@ -60,6 +60,7 @@ int ppo_launch_prepare(const PpoDev& P, cudaStream_t stream) {
 // One block of 1024 threads over the per-sample (or per-block) partial rows; see ppo_finalize_block.
 __global__ void __launch_bounds__(1024) ppo_finalize_kernel(PpoDev P, long long rows, int ent_d) {
   extern __shared__ double s_scratch[];  // [nwarps][ns]
+  pdl_wait();  // launched as a programmatic dependent of the kernel that writes the partial rows
   ppo_finalize_block(P, rows, ent_d, s_scratch);
 }
 
@@ -68,7 +69,14 @@ int ppo_launch_finalize(const PpoDev& P, long long rows, int ent_d, cudaStream_t
   int threads = 1024;
   if (rows < threads) threads = (int)(((rows + 31) / 32) * 32);
   if (threads < ((ns + 31) / 32) * 32) threads = ((ns + 31) / 32) * 32;
-  ppo_finalize_kernel<<<1, threads, (size_t)(threads / 32) * ns * sizeof(double), stream>>>(P, rows, ent_d);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1), cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = (size_t)(threads / 32) * ns * sizeof(double), cfg.stream = stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr, cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, ppo_finalize_kernel, P, rows, ent_d) != cudaSuccess) return check_launch("ppo_finalize");
   return check_launch("ppo_finalize");
 }
 
