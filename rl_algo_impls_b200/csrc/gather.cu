@@ -28,6 +28,7 @@ struct GatherParams {
 };
 
 __global__ void __launch_bounds__(kGatherBlock) gather_wide_kernel(const GatherParams p) {
+  pdl_trigger();  // the narrow-row launch behind this one is independent of it and may start right away
   const long long item = blockIdx.x;
   int t = 0;
   while (t + 1 < p.n && item >= p.first_item[t + 1]) ++t;
@@ -197,7 +198,18 @@ extern "C" int b200rl_gather_rows(const void* const* src_host, void* const* dst_
   }
   if (narrow.n) {
     const long long threads = B * narrow.n;
-    gather_narrow_kernel<<<(unsigned)((threads + kGatherBlock - 1) / kGatherBlock), kGatherBlock, 0, s>>>(narrow);
+    const unsigned blocks = (unsigned)((threads + kGatherBlock - 1) / kGatherBlock);
+    if (wide.n) {  // overlaps the wide launch (programmatic dependent launch; no data dependence between the two)
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(blocks), cfg.blockDim = dim3(kGatherBlock), cfg.stream = s;
+      cudaLaunchAttribute attr{};
+      attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr.val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = &attr, cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, gather_narrow_kernel, narrow);
+    } else {
+      gather_narrow_kernel<<<blocks, kGatherBlock, 0, s>>>(narrow);
+    }
   }
   return check_launch("gather_rows");
 }
