@@ -36,7 +36,16 @@ struct SampleDev {
   void* pick_out;
   int pick_dtype;
   float* logp;
+  // wide heads are cut into parts of kPartEntries entries that adjacent lanes of one warp draw in parallel:
+  // part slot p of a cell covers entries [part_lo[p], part_lo[p] + part_len[p]) of head part_head[p];
+  // n_parts == 0: the plan does not fit a warp (one thread per head instead)
+  int n_parts;
+  int8_t part_head[32];
+  int16_t part_lo[32], part_len[32];
+  int8_t part_count[32];  // parts of this slot's head (valid on the head's first slot), 0 on the others
+  int max_part_count;
 };
+constexpr int kPartEntries = 16;  // a multiple of the 4 entries one Philox block serves
 
 __device__ __forceinline__ float logit_at(const SampleDev& G, long long i) {
   return G.logits_dtype == B200RL_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(G.logits)[i])
@@ -91,17 +100,21 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
   // x + gumbel, so the chosen entry's log-prob is x_best - (m + log s) without a second sweep.
   __shared__ float s_lp[kStashUnits * B200RL_MAX_HEADS > 8192 ? 8192 : kStashUnits * B200RL_MAX_HEADS];
   const int stash_units = 8192 / (G.A > 0 ? G.A : 1) < kStashUnits ? 8192 / G.A : kStashUnits;
-  auto sample_head = [&](long long cell, int h, float* lp_out) -> int {
-    const int off = G.off[h], n = G.nvec[h];
+  // running statistics of a draw over a range of entries: Gumbel arg-max and online softmax
+  struct Draw {
+    float best_score, x_best, mx, sum;
+    int best;
+  };
+  auto draw_range = [&](long long cell, int h, int k_lo, int k_hi) -> Draw {  // k_lo a multiple of 4
+    const int off = G.off[h];
     const long long xbase = cell * G.Sp + off;
     const uint8_t* m = G.mask + cell * G.S + off;
-    int best = 0;
-    float best_score = -INFINITY, x_best = 0.f, mx = -INFINITY, sum = 0.f;
-    for (int k0 = 0; k0 < n; k0 += 4) {
+    Draw d{-INFINITY, 0.f, -INFINITY, 0.f, 0};
+    for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
       uint32_t valid = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (k0 + j < n && m[k0 + j]) valid |= 1u << j;
+        if (k0 + j < k_hi && m[k0 + j]) valid |= 1u << j;
       if (!valid) continue;  // no random numbers spent on masked entries
       const Philox4 r = philox4x32_10(G.seed, (uint64_t)cell, stream_id(offset, h, k0 >> 2));
       const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
@@ -110,24 +123,71 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
         if (!((valid >> j) & 1u)) continue;
         const float x = logit_at(G, xbase + k0 + j);
         const float score = x + gumbel(bits[j]);
-        if (score > best_score) best_score = score, best = k0 + j, x_best = x;
-        const float nm = fmaxf(mx, x);
-        sum = sum * __expf(mx - nm) + __expf(x - nm);  // exp(-inf) == 0 on the first valid entry
-        mx = nm;
+        if (score > d.best_score) d.best_score = score, d.best = k0 + j, d.x_best = x;
+        const float nm = fmaxf(d.mx, x);
+        d.sum = d.sum * __expf(d.mx - nm) + __expf(x - nm);  // exp(-inf) == 0 on the first valid entry
+        d.mx = nm;
       }
     }
-    *lp_out = sum > 0.f ? x_best - (mx + logf(sum)) : 0.f;  // a head with no valid entry: action 0, log-prob 0
-    return best;
+    return d;
+  };
+  // `b` covers the entries after `a`'s: the earlier entry wins a tie, as one sequential scan would decide
+  auto merge = [](Draw a, const Draw& b) -> Draw {
+    if (b.best_score > a.best_score) a.best_score = b.best_score, a.best = b.best, a.x_best = b.x_best;
+    const float nm = fmaxf(a.mx, b.mx);
+    if (nm > -INFINITY) a.sum = a.sum * __expf(a.mx - nm) + b.sum * __expf(b.mx - nm);
+    a.mx = nm;
+    return a;
+  };
+  auto finish = [](const Draw& d, float* lp_out) -> int {
+    *lp_out = d.sum > 0.f ? d.x_best - (d.mx + logf(d.sum)) : 0.f;  // a head with no valid entry: action 0, log-prob 0
+    return d.best;
+  };
+  auto sample_head = [&](long long cell, int h, float* lp_out) -> int {
+    return finish(draw_range(cell, h, 0, G.nvec[h]), lp_out);
   };
 
-  const int n_items = (n_unit < stash_units ? n_unit : stash_units) * G.A;
-  for (int item = tid; item < n_items; item += kSampleBlock) {
-    const int u = item / G.A, h = item - u * G.A;
-    const long long cell = b * G.HW + s_list[u];
-    float lp;
-    const int a = sample_head(cell, h, &lp);
-    put_index(G.actions_out, G.act_dtype, cell * G.A + h, a);
-    s_lp[item] = lp;
+  const int n_stashed = n_unit < stash_units ? n_unit : stash_units;
+  const int n_items = n_stashed * G.A;
+  if (G.n_parts > 0) {
+    // a warp takes 32 / n_parts cells at a time; lane = (cell slot, part slot); the first lane of a head folds the
+    // partial draws of its other parts in, in entry order, through shuffles (every lane takes part in them)
+    const int per_warp = 32 / G.n_parts;
+    const int slot = lane / G.n_parts, p = lane - slot * G.n_parts;
+    const bool lane_used = slot < per_warp;
+    const int h = lane_used ? G.part_head[p] : 0;
+    for (int u0 = warp * per_warp; u0 < n_stashed; u0 += (kSampleBlock / 32) * per_warp) {  // warp-uniform trips
+      const int u = u0 + slot;
+      const bool live = lane_used && u < n_stashed;
+      const long long cell = live ? b * G.HW + s_list[u] : 0;
+      Draw d{-INFINITY, 0.f, -INFINITY, 0.f, 0};
+      if (live) d = draw_range(cell, h, G.part_lo[p], G.part_lo[p] + G.part_len[p]);
+      const int my_parts = live ? G.part_count[p] : 0;
+      for (int q = 1; q < G.max_part_count; ++q) {
+        Draw o;
+        o.best_score = __shfl_down_sync(0xffffffffu, d.best_score, q);
+        o.x_best = __shfl_down_sync(0xffffffffu, d.x_best, q);
+        o.mx = __shfl_down_sync(0xffffffffu, d.mx, q);
+        o.sum = __shfl_down_sync(0xffffffffu, d.sum, q);
+        o.best = __shfl_down_sync(0xffffffffu, d.best, q);
+        if (q < my_parts) d = merge(d, o);  // only a head's first lane accumulates; it never reads its own merges back
+      }
+      if (my_parts > 0) {
+        float lp;
+        const int a = finish(d, &lp);
+        put_index(G.actions_out, G.act_dtype, cell * G.A + h, a);
+        s_lp[u * G.A + h] = lp;
+      }
+    }
+  } else {
+    for (int item = tid; item < n_items; item += kSampleBlock) {
+      const int u = item / G.A, h = item - u * G.A;
+      const long long cell = b * G.HW + s_list[u];
+      float lp;
+      const int a = sample_head(cell, h, &lp);
+      put_index(G.actions_out, G.act_dtype, cell * G.A + h, a);
+      s_lp[item] = lp;
+    }
   }
   __syncthreads();  // actions of the reference heads are written
   for (int item = tid; item < n_items; item += kSampleBlock) {
@@ -265,6 +325,27 @@ extern "C" int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* l
     G.gate_val[h] = (gr >= 0 && d->gate_val_host) ? d->gate_val_host[h] : 0;
   }
   G.S = S, G.Sp = S + d->n_pick;
+  {  // part plan: heads in order, each cut into parts of kPartEntries entries on adjacent lanes
+    int np = 0, max_count = 1;
+    bool fits = true;
+    for (int h = 0; h < d->A && fits; ++h) {
+      const int count = (G.nvec[h] + kPartEntries - 1) / kPartEntries;
+      if (np + count > 32 || count > 127) {
+        fits = false;
+        break;
+      }
+      for (int q = 0; q < count; ++q, ++np) {
+        G.part_head[np] = (int8_t)h;
+        G.part_lo[np] = (int16_t)(q * kPartEntries);
+        const int len = G.nvec[h] - q * kPartEntries;
+        G.part_len[np] = (int16_t)(len < kPartEntries ? len : kPartEntries);
+        G.part_count[np] = (int8_t)(q == 0 ? count : 0);
+      }
+      if (count > max_count) max_count = count;
+    }
+    G.n_parts = fits ? np : 0;
+    G.max_part_count = max_count;
+  }
   G.seed = seed, G.offset = offset, G.offset_dev = reinterpret_cast<const long long*>(offset_dev);
   G.actions_out = actions_out, G.act_dtype = d->act_dtype, G.pick_out = pick_actions_out, G.pick_dtype = d->pick_dtype;
   G.logp = logp;
