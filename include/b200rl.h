@@ -53,6 +53,13 @@ typedef void* b200rl_stream_t; /* cudaStream_t */
 int b200rl_version(void);
 const char* b200rl_last_error(void);
 
+/* Page-lock (cudaHostRegister) / release a HOST buffer the caller owns -- a host vec env's observation or mask
+ * array (rollout/sync_step_rollout.py:202-212 hands them over every step) -- so that the per-step upload is a
+ * DMA straight out of it instead of a copy through a staging buffer.  A refusal returns B200RL_ECUDA and leaves
+ * no pending CUDA error behind. */
+int b200rl_host_register(void* ptr, size_t bytes);
+int b200rl_host_unregister(void* ptr);
+
 /* ---------------------------------------------------------------------------------------
  * K1  GAE(lambda) reverse-time scan + returns.
  * Replaces shared/gae.py:97-124 (compute_advantages) and rollout/vec_rollout.py:88 (returns).

@@ -76,6 +76,8 @@ _vp, _i64, _int, _sz, _u64, _f = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c
 PROTOTYPES = {
     "b200rl_version": (_int, []),
     "b200rl_last_error": (C.c_char_p, []),
+    "b200rl_host_register": (_int, [_vp, _sz]),
+    "b200rl_host_unregister": (_int, [_vp]),
     "b200rl_gae_scan_f32": (_int, [_vp, _vp, _vp, _vp, _vp, c_f64p, c_f64p, _int, _vp, _vp, _i64, _i64, _i64, _vp]),
     "b200rl_gae_segments_f32": (
         _int,

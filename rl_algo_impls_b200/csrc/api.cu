@@ -44,3 +44,30 @@ const DeviceInfo& device_info() {
 
 extern "C" int b200rl_version(void) { return B200RL_VERSION; }
 extern "C" const char* b200rl_last_error(void) { return b200rl::g_error; }
+
+// Page-lock / release a host buffer the caller already owns (a vec env's output array), so that H2D copies out of
+// it are plain DMAs.  A refusal (range already registered, not registrable, ...) is reported as a code and the
+// runtime's last-error state is cleared: the caller simply keeps using a staging buffer.
+extern "C" int b200rl_host_register(void* ptr, size_t bytes) {
+  using namespace b200rl;
+  B200RL_REQUIRE(ptr != nullptr && bytes > 0, "host_register: null pointer or empty range");
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    set_error("host_register: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return B200RL_ECUDA;
+  }
+  return B200RL_OK;
+}
+
+extern "C" int b200rl_host_unregister(void* ptr) {
+  using namespace b200rl;
+  B200RL_REQUIRE(ptr != nullptr, "host_unregister: null pointer");
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    set_error("host_unregister: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return B200RL_ECUDA;
+  }
+  return B200RL_OK;
+}

@@ -15,6 +15,7 @@ from typing import Dict, Optional, Union
 import numpy as np
 import torch
 
+from .. import _lib
 from .rollout import RolloutGenerator
 from .vec_rollout import VecRollout
 
@@ -61,8 +62,7 @@ class _Uploader:
             if len(self._seen) > 4096:  # an env that allocates fresh arrays every step: stop tracking
                 self._seen.clear()
             return False
-        rc = torch.cuda.cudart().cudaHostRegister(root.ctypes.data, root.nbytes, 0)
-        ok = int(rc) == 0
+        ok = _lib.lib().b200rl_host_register(root.ctypes.data, root.nbytes) == 0  # a refusal leaves no CUDA error behind
         self._registered[key] = ok
         if ok:
             self._registered_bytes += root.nbytes
@@ -70,11 +70,19 @@ class _Uploader:
         return ok
 
     def close(self) -> None:
+        """Release the page locks (before the arrays can be freed: a stale registration would make a later
+        registration of recycled memory fail)."""
         for (ptr, _), ok in self._registered.items():
             if ok:
-                torch.cuda.cudart().cudaHostUnregister(ptr)
+                _lib.lib().b200rl_host_unregister(ptr)
         self._registered.clear()
         self._roots = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: the library / driver may already be gone
+            pass
 
     def __call__(self, name: str, src, dst: torch.Tensor) -> None:
         if isinstance(src, torch.Tensor):
