@@ -286,6 +286,12 @@ int b200rl_categorical_sample_f32(const float* logits, const uint8_t* mask, int6
  */
 int b200rl_rollout_store_step(const void* const* src_host, void* const* dst_host, const int64_t* step_bytes_host,
                               int n_tensors, const int64_t* step_dev, int64_t T, b200rl_stream_t stream);
+/* ... and the carry-over of sync_step_rollout.py:202-212 (self.next_obs = ..., self.next_action_masks = ...) in the
+ * same launch: where carry_host[t] is non-NULL, src[t] (which must be writable) is overwritten with carry_host[t]
+ * -- the env's output for the NEXT step -- right after its current content went to the buffer row. */
+int b200rl_rollout_store_step_carry(const void* const* src_host, void* const* dst_host, const int64_t* step_bytes_host,
+                                    const void* const* carry_host, int n_tensors, const int64_t* step_dev, int64_t T,
+                                    b200rl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K6  running-moment normalisers.  Replaces wrappers/normalize.py:18-122 over

@@ -121,6 +121,10 @@ PROTOTYPES = {
          C.c_double, _vp, _vp],
     ),
     "b200rl_rollout_store_step": (_int, [C.POINTER(_vp), C.POINTER(_vp), c_i64p, _int, _vp, _i64, _vp]),
+    "b200rl_rollout_store_step_carry": (
+        _int,
+        [C.POINTER(_vp), C.POINTER(_vp), c_i64p, C.POINTER(_vp), _int, _vp, _i64, _vp],
+    ),
     "b200rl_reward_assemble_f32": (
         _int,
         [_vp, _i64, C.POINTER(_vp), _int, _vp, _vp, C.POINTER(C.c_uint8), c_f32p, _vp, _i64, _vp],

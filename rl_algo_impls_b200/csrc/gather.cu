@@ -95,21 +95,14 @@ struct StoreParams {
   uint8_t* dst[B200RL_MAX_GATHER];
   long long step_bytes[B200RL_MAX_GATHER];
   long long first_chunk[B200RL_MAX_GATHER + 1];
+  const uint8_t* carry[B200RL_MAX_GATHER];  // non-null: after the row write, src[t] <- carry[t] (the next step's slice)
   int n;
   const long long* step_dev;
   long long T;
 };
 
-__global__ void __launch_bounds__(kGatherBlock) store_step_kernel(const StoreParams p) {
-  const long long item = blockIdx.x;
-  int t = 0;
-  while (t + 1 < p.n && item >= p.first_chunk[t + 1]) ++t;
-  const long long begin = (item - p.first_chunk[t]) * kChunkBytes;
-  const long long sb = p.step_bytes[t];
-  const long long bytes = sb - begin < kChunkBytes ? sb - begin : kChunkBytes;
-  const long long step = *p.step_dev % p.T;
-  const uint8_t* s = p.src[t] + begin;
-  uint8_t* d = p.dst[t] + step * sb + begin;
+// one chunk src -> dst by the whole CTA; every load is issued before the first store
+__device__ __forceinline__ void copy_chunk(const uint8_t* s, uint8_t* d, long long bytes) {
   const int tid = threadIdx.x;
   if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15u) == 0) {
     const uint4* s4 = reinterpret_cast<const uint4*>(s);
@@ -133,11 +126,37 @@ __global__ void __launch_bounds__(kGatherBlock) store_step_kernel(const StorePar
   }
 }
 
+__global__ void __launch_bounds__(kGatherBlock) store_step_kernel(const StoreParams p) {
+  const long long item = blockIdx.x;
+  int t = 0;
+  while (t + 1 < p.n && item >= p.first_chunk[t + 1]) ++t;
+  const long long begin = (item - p.first_chunk[t]) * kChunkBytes;
+  const long long sb = p.step_bytes[t];
+  const long long bytes = sb - begin < kChunkBytes ? sb - begin : kChunkBytes;
+  const long long step = *p.step_dev % p.T;
+  const uint8_t* s = p.src[t] + begin;
+  copy_chunk(s, p.dst[t] + step * sb + begin, bytes);
+  // carry-over: this CTA, which alone touches this chunk of the step slice, overwrites it with the next step's once
+  // every thread's loads of the old content have returned (the barrier: the two copies may split the chunk
+  // differently across threads when their alignments differ)
+  if (p.carry[t] != nullptr) {
+    __syncthreads();
+    copy_chunk(p.carry[t] + begin, const_cast<uint8_t*>(s), bytes);
+  }
+}
+
 }  // namespace b200rl
 
 extern "C" int b200rl_rollout_store_step(const void* const* src_host, void* const* dst_host,
                                          const int64_t* step_bytes_host, int n_tensors, const int64_t* step_dev,
                                          int64_t T, b200rl_stream_t stream) {
+  return b200rl_rollout_store_step_carry(src_host, dst_host, step_bytes_host, nullptr, n_tensors, step_dev, T, stream);
+}
+
+extern "C" int b200rl_rollout_store_step_carry(const void* const* src_host, void* const* dst_host,
+                                               const int64_t* step_bytes_host, const void* const* carry_host,
+                                               int n_tensors, const int64_t* step_dev, int64_t T,
+                                               b200rl_stream_t stream) {
   using namespace b200rl;
   B200RL_REQUIRE(src_host && dst_host && step_bytes_host && step_dev, "rollout_store_step: null pointer");
   B200RL_REQUIRE(n_tensors >= 0 && n_tensors <= B200RL_MAX_GATHER, "rollout_store_step: n_tensors=%d (max %d)",
@@ -151,6 +170,7 @@ extern "C" int b200rl_rollout_store_step(const void* const* src_host, void* cons
     if (step_bytes_host[t] == 0) continue;
     const int k = p.n++;
     p.src[k] = static_cast<const uint8_t*>(src_host[t]), p.dst[k] = static_cast<uint8_t*>(dst_host[t]);
+    p.carry[k] = carry_host ? static_cast<const uint8_t*>(carry_host[t]) : nullptr;
     p.step_bytes[k] = step_bytes_host[t];
     p.first_chunk[k] = chunks;
     chunks += (step_bytes_host[t] + kChunkBytes - 1) / kChunkBytes;

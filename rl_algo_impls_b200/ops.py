@@ -274,9 +274,12 @@ def gather_rows(sources: Sequence[torch.Tensor], idx: torch.Tensor) -> List[torc
 
 # ------------------------------------------------------------------------------------------------
 # K0
-def rollout_store_step(step_tensors: Sequence[torch.Tensor], buffers: Sequence[torch.Tensor], step_dev: torch.Tensor) -> None:
+def rollout_store_step(step_tensors: Sequence[torch.Tensor], buffers: Sequence[torch.Tensor], step_dev: torch.Tensor,
+                       carry: Optional[Sequence[Optional[torch.Tensor]]] = None) -> None:
     """buffers[t][*step_dev % T] = step_tensors[t] for every rollout field in one launch
-    (sync_step_rollout.py:188-201); the step index is read on the device (CUDA-graph friendly)."""
+    (sync_step_rollout.py:188-201); the step index is read on the device (CUDA-graph friendly).
+    ``carry[t]`` (same shape / dtype as step_tensors[t], or None) is then copied INTO step_tensors[t] by the same
+    launch: the env's output for the next step replaces the slice that was just stored (:202-212)."""
     _cuda(step_dev, torch.int64, "step_dev")
     n = len(step_tensors)
     if n == 0:
@@ -284,15 +287,21 @@ def rollout_store_step(step_tensors: Sequence[torch.Tensor], buffers: Sequence[t
     if n > _lib.MAX_GATHER:
         raise ValueError(f"at most {_lib.MAX_GATHER} fields per call")
     T = buffers[0].shape[0]
-    src_arr, dst_arr, sb_arr = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_int64 * n)()
+    src_arr, dst_arr, sb_arr, carry_arr = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_int64 * n)(), (C.c_void_p * n)()
     for k, (s, d) in enumerate(zip(step_tensors, buffers)):
         _cuda(s, None, f"step_tensors[{k}]"), _cuda(d, None, f"buffers[{k}]")
         if d.shape[0] != T or s.dtype != d.dtype or s.numel() * T != d.numel():
             raise ValueError(f"field {k}: step slice {tuple(s.shape)} {s.dtype} does not fit buffer {tuple(d.shape)} {d.dtype}")
         src_arr[k], dst_arr[k], sb_arr[k] = s.data_ptr(), d.data_ptr(), s.numel() * s.element_size()
-    rc = _call("b200rl_rollout_store_step", 1, _lib.lib().b200rl_rollout_store_step, src_arr, dst_arr, sb_arr, n,
-               step_dev.data_ptr(), T, _stream())
-    check(rc, "b200rl_rollout_store_step")
+        c = carry[k] if carry is not None else None
+        if c is not None:
+            _cuda(c, None, f"carry[{k}]")
+            if c.dtype != s.dtype or c.numel() != s.numel():
+                raise ValueError(f"carry[{k}] {tuple(c.shape)} {c.dtype} does not match the step slice {tuple(s.shape)} {s.dtype}")
+            carry_arr[k] = c.data_ptr()
+    rc = _call("b200rl_rollout_store_step_carry", 1, _lib.lib().b200rl_rollout_store_step_carry, src_arr, dst_arr, sb_arr,
+               carry_arr if carry is not None else None, n, step_dev.data_ptr(), T, _stream())
+    check(rc, "b200rl_rollout_store_step_carry")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -299,16 +299,23 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         a, v, logp = self.policy.step_device(self.next_obs, self.next_action_masks, offset_dev=self.step_count)
         next_obs, rewards, terminations, truncations, _ = self.vec_env.step(a)
         src, dst = self._fields(a, v, logp, rewards.reshape(self.rewards.shape[1:]))
-        ops.rollout_store_step(src, dst, self.step_count)  # before next_obs / masks are overwritten
-        self.next_obs.copy_(next_obs)
+        # the env's outputs for the next step replace next_obs / next masks inside the same K0 launch
+        fits = lambda new, cur: (isinstance(new, torch.Tensor) and new.dtype == cur.dtype and new.shape == cur.shape
+                                 and new.is_contiguous() and new.data_ptr() != cur.data_ptr())
+        carry = {id(self.next_obs): next_obs} if fits(next_obs, self.next_obs) else {}
+        masks = self.get_action_mask() if self.next_action_masks is not None else None
+        if masks is not None:
+            pairs = ([(self.next_action_masks[k], masks[k]) for k in self.next_action_masks]
+                     if isinstance(self.next_action_masks, dict) else [(self.next_action_masks, masks)])
+            carry.update({id(cur): new for cur, new in pairs if fits(new, cur)})
+        ops.rollout_store_step(src, dst, self.step_count, carry=[carry.get(id(t)) for t in src])
+        if id(self.next_obs) not in carry:
+            self.next_obs.copy_(next_obs)
         torch.logical_or(terminations, truncations, out=self.next_episode_starts)
-        if self.next_action_masks is not None:
-            m = self.get_action_mask()
-            if isinstance(m, dict):
-                for k, dst_m in self.next_action_masks.items():
-                    dst_m.copy_(m[k])
-            else:
-                self.next_action_masks.copy_(m)
+        if masks is not None:
+            for cur, new in pairs:
+                if id(cur) not in carry:
+                    cur.copy_(new)
         self.step_count.add_(1)
 
     def _capture(self, fn):

@@ -95,6 +95,34 @@ def test_rollout_store_step(cuda):
         assert b[:3].cpu().count_nonzero() == 0 and b[4:].cpu().count_nonzero() == 0
 
 
+def test_rollout_store_step_with_carry_over(cuda):
+    """K0 with carry: the step slice goes to its buffer row and is then overwritten by the next step's slice in the
+    same launch (aligned 16 KB-chunked fields, an odd-sized one, a misaligned carry source, and a field without)."""
+    from rl_algo_impls_b200 import ops
+
+    T, N = 4, 3
+    g = torch.Generator().manual_seed(1)
+    shapes = [((N, 74, 16, 16), torch.float32), ((N, 256, 78), torch.bool), ((N, 7, 3), torch.uint8), ((N,), torch.float32)]
+    mk = lambda shape, dt: (torch.randn(shape, generator=g) if dt == torch.float32 else
+                            (torch.rand(shape, generator=g) < 0.5 if dt == torch.bool else
+                             torch.randint(0, 255, shape, generator=g).to(dt)))
+    cur = [mk(*sd) for sd in shapes]
+    nxt = [mk(*sd) for sd in shapes]
+    dev_cur = [t.to(cuda) for t in cur]
+    pad = torch.zeros(nxt[2].numel() + 1, dtype=torch.uint8, device=cuda)
+    pad[1:] = nxt[2].reshape(-1).to(cuda)  # a carry source that is not 16-byte aligned
+    carry = [nxt[0].to(cuda), nxt[1].to(cuda), pad[1:].view(nxt[2].shape), None]
+    bufs = [torch.zeros((T,) + tuple(t.shape), dtype=t.dtype, device=cuda) for t in cur]
+    counter = torch.tensor([2], dtype=torch.int64, device=cuda)
+    ops.rollout_store_step(dev_cur, bufs, counter, carry=carry)
+    for k, (t, b) in enumerate(zip(cur, bufs)):
+        assert torch.equal(b[2].cpu(), t), k
+        assert b[:2].cpu().count_nonzero() == 0 and b[3:].cpu().count_nonzero() == 0
+        assert torch.equal(dev_cur[k].cpu(), nxt[k] if carry[k] is not None else t), k
+    with pytest.raises(ValueError):
+        ops.rollout_store_step(dev_cur, bufs, counter, carry=[None, None, None, torch.zeros(N + 1, device=cuda)])
+
+
 @pytest.mark.parametrize("cfg", ["C1", "C3", "C4", "C5"])
 def test_graph_replayed_rollout_equals_eager(cuda, cfg):
     """The CUDA-graph path (one replay per env step) fills the rollout buffer with exactly what the
