@@ -183,3 +183,42 @@ def test_freeze_and_unfreeze_parameter_groups(key):
     assert count() == 0
     policy.unfreeze()
     assert count() == total
+
+
+def test_uploader_page_lock_policy(monkeypatch):
+    """_Uploader._page_locked: a host buffer is page-locked in place on its SECOND sighting, by its owning array
+    (views of one pool share a registration), a refusal is remembered, and close() releases what was locked."""
+    from rl_algo_impls_b200 import _lib
+    from rl_algo_impls_b200.rollout.sync_step_rollout import _Uploader
+
+    calls = {"register": [], "unregister": []}
+
+    class FakeLib:
+        refuse = set()
+
+        def b200rl_host_register(self, ptr, nbytes):
+            calls["register"].append((ptr, nbytes))
+            return -3 if ptr in self.refuse else 0
+
+        def b200rl_host_unregister(self, ptr):
+            calls["unregister"].append(ptr)
+            return 0
+
+    fake = FakeLib()
+    monkeypatch.setattr(_lib, "lib", lambda: fake)
+    up = _Uploader(torch.device("cpu"))
+    pool = np.zeros((4, 1 << 16), np.float32)
+    assert not up._page_locked(pool[0])          # first sighting: not yet
+    assert up._page_locked(pool[1])              # second sighting of the same owning array (another slot)
+    assert up._page_locked(pool[2]) and len(calls["register"]) == 1
+    assert calls["register"][0] == (pool.ctypes.data, pool.nbytes)
+    other = np.ones(1 << 18, np.float32)
+    fake.refuse.add(other.ctypes.data)
+    assert not up._page_locked(other) and not up._page_locked(other) and not up._page_locked(other)
+    assert len(calls["register"]) == 2           # the refusal is remembered, not retried
+    borrowed = np.frombuffer(bytearray(1 << 20), dtype=np.uint8)  # memory owned by something that is not an ndarray
+    assert not up._page_locked(borrowed) and not up._page_locked(borrowed)
+    up.close()
+    assert calls["unregister"] == [pool.ctypes.data]
+    up.close()
+    assert calls["unregister"] == [pool.ctypes.data]
