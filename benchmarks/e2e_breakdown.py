@@ -4,13 +4,11 @@ import os
 import sys
 import time
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from rl_algo_impls_b200 import ops  # noqa: E402
 from rl_algo_impls_b200.configs import CONFIGS, build  # noqa: E402
 
 

@@ -5,7 +5,7 @@ the reference's own keyword names, so they splat into ``ActorCritic`` / ``SyncSt
 / ``PPO`` exactly like ``runner/train.py:104-191`` does with the YAML.  Deviations forced by the
 BASELINE config text (synthetic envs, scaled env counts) are stated in ``notes``.
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Dict
 
 _LUX_V = 13

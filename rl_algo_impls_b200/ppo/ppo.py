@@ -16,8 +16,7 @@ with the statistics left on the device and read back once per ``learn_epoch``.  
 ``torch.distributed`` (one process per GPU, envs sharded) the advantage moments and the gradients
 are all-reduced so that the update equals the single-process update on the concatenated minibatch.
 """
-import gc
-from dataclasses import asdict, astuple, dataclass
+from dataclasses import asdict, dataclass
 from time import perf_counter
 from typing import Dict, List, NamedTuple, Optional, Sequence, Tuple, TypeVar, Union
 

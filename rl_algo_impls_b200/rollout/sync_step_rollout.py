@@ -10,7 +10,7 @@ numpy out -- the reference's contract) still works: its observations / masks are
 pinned staging buffers and the sampled actions are downloaded for ``env.step``; a device env
 (CUDA tensors in / out) never touches PCIe.
 """
-from typing import Dict, Optional, Union
+from typing import Dict, Optional
 
 import numpy as np
 import torch

@@ -16,7 +16,6 @@ from typing import DefaultDict, Dict, Iterator, List, Optional
 import numpy as np
 import torch
 
-from .. import ops
 from .rollout import Batch, BatchMapFn, Rollout
 from .trajectory import Trajectory, _split_fields, segmented_gae
 
