@@ -119,8 +119,12 @@ int b200rl_adv_normalize_f32(const float* adv, const int64_t* idx, int64_t B, in
  * K3  minibatch row gather.  Replaces rollout/rollout.py:56-69 (Batch.__getitem__) and
  * shared/tensor_utils.py:66-72: dst[t][b, :] = src[t][idx[b], :] for n_tensors tensors in one
  * launch.  src_host / dst_host / row_bytes_host are HOST arrays of device pointers / sizes.
- * Rows whose size and base addresses are 16-byte multiples move through shared memory with
- * bulk async copies; other rows take a scalar path.  idx is int64 [B] on the device.
+ * Rows wider than 256 bytes are cut into 16 KB chunks, one CTA each, staged through REGISTERS:
+ * 128-bit streaming loads (L1 no-allocate), every load of a chunk issued before its first store
+ * (16-byte aligned rows; 4-byte and byte paths otherwise).  Narrow rows go one per thread in a
+ * second grid that overlaps the first and completes after it, so whatever follows on the stream
+ * sees every gathered row.  idx is int64 [B] on the device; rows with idx outside [0, n_src_rows)
+ * are left untouched.
  */
 int b200rl_gather_rows(const void* const* src_host, void* const* dst_host, const int64_t* row_bytes_host,
                        int n_tensors, const int64_t* idx, int64_t B, int64_t n_src_rows,

@@ -56,19 +56,25 @@ CONFIGS: Dict[str, RunConfig] = {
                     dict(n_steps=512, subaction_mask={0: {1: 1, 2: 2, 3: 3, 4: 4, 5: 4, 6: 5}}),
                     dict(batch_size=3072, n_epochs=4, learning_rate=2.5e-4, clip_range=0.1, vf_coef=0.5, ent_coef=0.01,
                          clip_range_vf=0.1, ppo2_vf_coef_halving=True, max_grad_norm=0.5)),
-    # hyperparams/ppo-LuxAI_S2.yml:1299-1322 + 2468-2517 (j1024 squnet 64x64)
-    "C5": RunConfig("C5", "PPO Lux AI S2 U-shaped net 64x64, 1024 envs x 32 steps sharded over 8 GPUs (128 envs / GPU)",
-                    "LuxAI_S2-64x64", 128,
-                    dict(actor_head_style="squeeze_unet", num_additional_critics=_LUX_V - 1,
-                         channels_per_level=[64, 128, 256], strides_per_level=[4, 4],
-                         encoder_residual_blocks_per_level=[1, 1, 1], critic_channels=128,
-                         subaction_mask={1: {2: 0, 3: 1, 4: 1, 5: 2}}),
+    # hyperparams/ppo-LuxAI_S2.yml: the 64x64 squeeze-U-net entry (LuxAI_S2-v0-sSqnet-j512env64-80m-close-ore-ice2,
+    # :2468-2517 over its anchors: policy 4,719,274 parameters, batch 128, gradient accumulation, bf16 autocast) at the
+    # rollout shape BASELINE.json names (1024 envs x 32 steps, :1299-1322).  n_envs is the GLOBAL env count: R ranks
+    # take 1024 / R envs each (bench.py); the reference's 256 contiguous minibatches of 128 are then the union of the
+    # ranks' own minibatches, so the sharded epoch accumulates exactly the reference's gradient.
+    "C5": RunConfig("C5", "PPO Lux AI S2 squeeze U-net 64x64, 1024 envs x 32 steps, envs sharded across the GPUs",
+                    "LuxAI_S2-64x64", 1024,
+                    dict(actor_head_style="squeeze_unet", channels_per_level=[128, 128, 128], strides_per_level=[4, 4],
+                         deconv_strides_per_level=[[2, 2], [2, 2]], encoder_residual_blocks_per_level=[3, 2, 2],
+                         decoder_residual_blocks_per_level=[2, 3], output_activation_fn="tanh",
+                         additional_critic_activation_functions=["identity"] * (_LUX_V - 1), critic_shares_backbone=True,
+                         shared_critic_head=True, critic_channels=128, subaction_mask={1: {2: 0, 3: 1, 4: 1, 5: 2}}),
                     dict(n_steps=32, subaction_mask={1: {2: 0, 3: 1, 4: 1, 5: 2}}, full_batch_off_accelerator=True),
                     dict(batch_size=128, n_epochs=2, gamma=[1.0] * _LUX_V, gae_lambda=[0.95] * _LUX_V, clip_range=0.1,
-                         ent_coef=0.01, vf_coef=[0.5] + [0.1] * (_LUX_V - 1),
-                         multi_reward_weights=[0.9] + [0.1 / (_LUX_V - 1)] * (_LUX_V - 1), max_grad_norm=0.5,
-                         learning_rate=1e-4, gradient_accumulation=True, autocast_loss=True),
-                    notes="128 envs per GPU = the 1024-env config sharded 8 ways; one GPU alone runs its own shard"),
+                         clip_range_vf=None, ppo2_vf_coef_halving=True, ent_coef=0.01, vf_coef=[0.2] + [0.1] * (_LUX_V - 1),
+                         multi_reward_weights=[1, 0.1, 0.1, 0.1, 0.1, 0, 0.1, 0.1, 0.1, 0.1, 0.1, 0, 0], max_grad_norm=0.5,
+                         learning_rate=1e-4, gradient_accumulation=True, autocast_loss=True,
+                         normalize_advantages_after_scaling=False),
+                    notes="global env count; bench.py --gpus R runs 1024 / R envs per GPU (strong scaling)"),
 }
 
 

@@ -73,20 +73,25 @@ __global__ void __launch_bounds__(kGatherBlock) gather_wide_kernel(const GatherP
 
 __global__ void __launch_bounds__(kGatherBlock) gather_narrow_kernel(const GatherParams p) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= p.B * p.n) return;
   const int t = (int)(e / p.B);  // tensor-major: threads of a warp share the tensor, walk rows
   const long long b = e - (long long)t * p.B;
-  const long long row = p.idx[b];
-  if (row < 0 || row >= p.n_src_rows) return;
-  const long long rb = p.row_bytes[t];
-  const uint8_t* s = p.src[t] + row * rb;
-  uint8_t* d = p.dst[t] + b * rb;
-  if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | (uintptr_t)rb) & 3u) == 0) {
-    for (long long o = 0; o < rb; o += 4)
-      *reinterpret_cast<uint32_t*>(d + o) = __ldg(reinterpret_cast<const uint32_t*>(s + o));
-  } else {
-    for (long long o = 0; o < rb; ++o) d[o] = s[o];
+  const long long row = e < p.B * p.n ? p.idx[b] : -1;
+  if (row >= 0 && row < p.n_src_rows) {
+    const long long rb = p.row_bytes[t];
+    const uint8_t* s = p.src[t] + row * rb;
+    uint8_t* d = p.dst[t] + b * rb;
+    if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | (uintptr_t)rb) & 3u) == 0) {
+      for (long long o = 0; o < rb; o += 4)
+        *reinterpret_cast<uint32_t*>(d + o) = __ldg(reinterpret_cast<const uint32_t*>(s + o));
+    } else {
+      for (long long o = 0; o < rb; ++o) d[o] = s[o];
+    }
   }
+  // Launched as a programmatic dependent of the wide-row grid (no data dependence, so the copies above run beside
+  // it), this grid must not COMPLETE before the wide grid has: the next kernel on the stream (the trunk reading the
+  // gathered observations) is ordered after this grid only.  Every thread waits here, which makes stream order
+  // transitive; without the launch attribute the wait returns at once.
+  pdl_wait();
 }
 
 // K0: one env step's [N, ...] slices -> row (*step % T) of the [T, N, ...] rollout buffers.

@@ -36,6 +36,8 @@ class EnvSpec:
     subaction_mask: Optional[Dict[int, Dict[int, int]]] = None
 
 
+_GEN_ENVS = 128
+
 MICRORTS_NVEC = (6, 4, 4, 4, 4, 7, 49)
 LUX_NVEC = (4, 6, 4, 4, 5, 5)
 
@@ -68,7 +70,12 @@ class SyntheticVecEnv:
                  pool: int = 8) -> None:
         self.spec, self.num_envs, self.device, self.pool = spec, int(num_envs), device, int(pool)
         rng = np.random.default_rng(seed)
-        N, V = self.num_envs, spec.n_values
+        N_all, V = self.num_envs, spec.n_values
+        # Large env counts (the 1024-env Lux config) draw the pool for a block of `_GEN_ENVS` envs and repeat it over
+        # the env axis (on the device for a device env): the data path moves the same bytes either way, and
+        # drawing 5 GB of Bernoulli planes on the host would take longer than the benchmark.
+        N = N_all if N_all <= _GEN_ENVS or N_all % _GEN_ENVS else _GEN_ENVS
+        reps = N_all // N
         if spec.obs_dtype == "uint8":
             obs = rng.integers(0, 256, size=(pool, N) + spec.obs_shape, dtype=np.uint8)
             self.single_observation_space = spaces.Box(0, 255, spec.obs_shape, np.uint8)
@@ -100,12 +107,19 @@ class SyntheticVecEnv:
             else:
                 self.single_action_space = per_pos
                 masks = cells
+        N = N_all
+        if reps > 1 and device is None:
+            tile = lambda a: np.tile(a, (1, reps) + (1,) * (a.ndim - 2))
+            obs, rewards, dones = tile(obs), tile(rewards), tile(dones)
+            if masks is not None:
+                masks = {k: tile(v) for k, v in masks.items()} if isinstance(masks, dict) else tile(masks)
         self._obs, self._rewards, self._dones, self._masks = obs, rewards, dones, masks
         if device is not None:
             # Device env: the pool lives in HBM, the slot counter is a device scalar and every output is
             # a fixed tensor refreshed in place (index_select with out=), so a step is a short, sync-free
             # kernel sequence with static addresses -- capturable in a CUDA graph like a Jux-style env.
-            to = lambda a: torch.from_numpy(a).to(device)
+            up = lambda a: torch.from_numpy(a).to(device)
+            to = up if reps == 1 else (lambda a: up(a).repeat((1, reps) + (1,) * (a.ndim - 2)))
             self._obs, self._rewards, self._dones = to(obs), to(rewards), to(dones)
             if masks is not None:
                 self._masks = {k: to(v) for k, v in masks.items()} if isinstance(masks, dict) else to(masks)

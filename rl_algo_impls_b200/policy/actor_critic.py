@@ -21,7 +21,7 @@ from ..actor.categorical import MaskedCategorical
 from ..actor.gridnet import GridnetDistribution, ValueDependentMask
 from ..actor.rng import current_seed, next_sample_stream
 from .networks import (GridEncoderDecoderActorCritic, HeadOutputs, MlpActorCritic, NatureCnnActorCritic,
-                       UShapedActorCritic)
+                       SqueezeUnetActorCritic)
 
 TensorOrDict = Union[torch.Tensor, Dict[str, torch.Tensor]]
 NumpyOrDict = Union[np.ndarray, Dict[str, np.ndarray]]
@@ -253,23 +253,38 @@ class _GaussianFn(torch.autograd.Function):
 
 def default_network(env, policy: ActorCritic, pi_hidden_sizes=None, v_hidden_sizes=None, activation_fn: str = "tanh",
                     log_std_init: float = -0.5, cnn_flatten_dim: int = 512, actor_head_style: str = "single",
-                    channels_per_level=None, strides_per_level=None, encoder_residual_blocks_per_level=None,
-                    critic_channels: int = 128, num_additional_critics: int = 0, **_ignored) -> nn.Module:
+                    channels_per_level=None, strides_per_level=None, deconv_strides_per_level=None,
+                    encoder_residual_blocks_per_level=None, decoder_residual_blocks_per_level=None,
+                    critic_channels: int = 64, num_additional_critics: int = 0,
+                    additional_critic_activation_functions=None, output_activation_fn: str = "identity",
+                    shared_critic_head: bool = False, increment_kernel_size_on_down_conv: bool = False,
+                    normalization=None, critic_shares_backbone: bool = True, **_ignored) -> nn.Module:
     """Trunk chosen from the spaces and the reference's policy hyperparameter names
-    (runner/running_utils.py:187-210 -> ActorCritic(env, **policy_hyperparams))."""
+    (runner/running_utils.py:187-210 -> ActorCritic(env, **policy_hyperparams)).  Trunks are plain PyTorch modules
+    and out of this repo's scope: the families of the five BASELINE configs are built here; for any other
+    (``unet``, ``double_cone``, ``sacus``, normalised variants) pass the module itself as ``network=``."""
     obs_shape = tuple(env.single_observation_space.shape)
     if policy.kind == "gridnet":
         n_logits = sum(policy.nvec) + policy.n_pick
         side = int(round(np.sqrt(policy.map_size)))
-        n_values = 1 + int(num_additional_critics)
-        if actor_head_style in ("squeeze_unet", "unet", "double_cone", "sacus") or policy.n_pick:
-            return UShapedActorCritic(obs_shape[0], n_logits, n_values,
-                                      channels=tuple(channels_per_level or (64, 128, 256)),
-                                      strides=tuple(strides_per_level or (4, 4)),
-                                      blocks=tuple(encoder_residual_blocks_per_level or (1, 1, 1)),
-                                      critic_channels=critic_channels)
+        if actor_head_style == "squeeze_unet" or (policy.n_pick and actor_head_style == "single"):
+            if normalization is not None or not critic_shares_backbone:
+                raise NotImplementedError("squeeze_unet with normalization / a separate critic backbone: pass network=")
+            extra = list(additional_critic_activation_functions or ["identity"] * int(num_additional_critics))
+            space = env.single_observation_space
+            obs_range = float(np.max(space.high) - np.min(space.low)) if spaces.is_box(space) else 1.0
+            return SqueezeUnetActorCritic(
+                obs_shape[0], n_logits, channels_per_level=tuple(channels_per_level or (64, 128, 256)),
+                strides_per_level=strides_per_level, deconv_strides_per_level=deconv_strides_per_level,
+                encoder_residual_blocks_per_level=encoder_residual_blocks_per_level,
+                decoder_residual_blocks_per_level=decoder_residual_blocks_per_level, critic_channels=critic_channels,
+                critic_activations=[output_activation_fn] + extra, shared_critic_head=shared_critic_head,
+                increment_kernel_size_on_down_conv=increment_kernel_size_on_down_conv,
+                obs_range=obs_range if np.isfinite(obs_range) and obs_range > 0 else 1.0)
+        if actor_head_style in ("unet", "double_cone", "sacus"):
+            raise NotImplementedError(f"actor_head_style={actor_head_style!r}: pass the trunk module as network=")
         return GridEncoderDecoderActorCritic(obs_shape[0], (side, side), n_logits, tuple(v_hidden_sizes or (128,)),
-                                             n_values)
+                                             1 + int(num_additional_critics))
     if len(obs_shape) == 3:
         return NatureCnnActorCritic(obs_shape[0], policy.action_space.n, obs_shape[1:], cnn_flatten_dim)
     obs_dim = int(np.prod(obs_shape))

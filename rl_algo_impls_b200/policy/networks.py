@@ -5,8 +5,8 @@ and values) so that the fused loss kernels have something real to differentiate 
 Architectures follow the families the reference configs name:
 MLP actor-critic (CartPole / HalfCheetah, shared/policy/actor_critic_network/connected_trio.py),
 NatureCNN (Atari, shared/encoder/nature_cnn.py), a conv encoder + transposed-conv decoder for
-MicroRTS GridNet (shared/encoder/gridnet_encoder.py + shared/actor/gridnet_decoder.py) and a
-U-shaped residual backbone with several critic heads for Lux (actor_critic_network/squeeze_unet.py).
+MicroRTS GridNet (shared/encoder/gridnet_encoder.py + shared/actor/gridnet_decoder.py) and the
+squeeze U-net with SE-residual blocks and several critic outputs for Lux (actor_critic_network/squeeze_unet.py).
 """
 from typing import List, Optional, Sequence, Tuple
 
@@ -124,49 +124,133 @@ class GridEncoderDecoderActorCritic(nn.Module):
         return HeadOutputs(logits, v.squeeze(-1) if self.n_values == 1 else v)
 
 
-class _ResBlock(nn.Module):
+class _SqueezeExcite(nn.Module):
+    """Channel gate: global mean -> C/16 bottleneck (GELU) -> sigmoid scale (double_cone.py:18-47)."""
+
+    def __init__(self, c: int, reduction: int = 16):
+        super().__init__()
+        self.fc = nn.Sequential(nn.Linear(c, c // reduction, bias=False), nn.GELU(), nn.Linear(c // reduction, c, bias=False),
+                                nn.Sigmoid())
+
+    def forward(self, x):
+        return x * self.fc(x.mean(dim=(2, 3)))[:, :, None, None]
+
+
+class _SEResBlock(nn.Module):
+    """gelu(x + SE(conv3x3(gelu(conv3x3(x))))) (double_cone.py:50-86, normalization=None)."""
+
     def __init__(self, c: int):
         super().__init__()
-        self.a, self.b = nn.Conv2d(c, c, 3, padding=1), nn.Conv2d(c, c, 3, padding=1)
+        self.residual = nn.Sequential(nn.Conv2d(c, c, 3, padding=1), nn.GELU(), nn.Conv2d(c, c, 3, padding=1), _SqueezeExcite(c))
         self.act = nn.GELU()
 
     def forward(self, x):
-        return x + self.b(self.act(self.a(self.act(x))))
+        return self.act(x + self.residual(x))
 
 
-class UShapedActorCritic(nn.Module):
-    """Lux-style U-shaped residual backbone: stride-4 down levels with residual blocks, transposed
-    convs back up with skip connections, a 3x3 conv actor head emitting [B, H, W, S'] logits and
-    `n_values` critic heads (conv + global average pool + linear) on the backbone output."""
+def _stride_list(s) -> List[int]:
+    return [int(v) for v in s] if isinstance(s, (list, tuple)) else [int(s)]
 
-    def __init__(self, in_channels: int, n_logits: int, n_values: int = 1, channels=(64, 128, 256),
-                 strides=(4, 4), blocks=(1, 1, 1), critic_channels: int = 128):
+
+class SqueezeUnetActorCritic(nn.Module):
+    """The Lux / MicroRTS "squeeze U-net" (actor_critic_network/squeeze_unet.py:20-196 backbone +
+    backbone_actor_critic.py:94-187 heads), same layer list and therefore the same parameter count (4,719,274 at the
+    Lux 64x64 YAML entry): a 3x3 stem and SE-residual blocks per level, strided convs down (kernel = stride), chains of
+    transposed convs up (``deconv_strides_per_level``; a level's encoder output is ADDED to what comes up from below),
+    a 3x3 conv actor head emitting [B, H, W, S'] logits, and critic head(s) of strided convs -> global average pool ->
+    two linears with a per-head output activation (``shared_critic_head``: one head with ``n_values`` outputs)."""
+
+    def __init__(self, in_channels: int, n_logits: int, channels_per_level=(64, 128, 256), strides_per_level=None,
+                 deconv_strides_per_level=None, encoder_residual_blocks_per_level=None,
+                 decoder_residual_blocks_per_level=None, critic_channels: int = 64,
+                 critic_activations: Sequence[str] = ("identity",), shared_critic_head: bool = False,
+                 increment_kernel_size_on_down_conv: bool = False, obs_range: float = 1.0):
         super().__init__()
-        self.stem = nn.Conv2d(in_channels, channels[0], 3, padding=1)
-        self.enc = nn.ModuleList([nn.Sequential(*[_ResBlock(c) for _ in range(n)]) for c, n in zip(channels, blocks)])
-        self.down = nn.ModuleList([nn.Conv2d(channels[i], channels[i + 1], strides[i], stride=strides[i])
-                                   for i in range(len(strides))])
-        self.up = nn.ModuleList([nn.ConvTranspose2d(channels[i + 1], channels[i], strides[i], stride=strides[i])
-                                 for i in range(len(strides))])
-        self.dec = nn.ModuleList([nn.Sequential(*[_ResBlock(c) for _ in range(n)])
-                                  for c, n in zip(channels[:-1], blocks[:-1])])
-        self.actor = ortho_(nn.Conv2d(channels[0], n_logits, 3, padding=1), 0.01)
-        self.critic_conv = nn.Sequential(nn.Conv2d(channels[0], critic_channels, 3, stride=2, padding=1), nn.GELU())
-        self.critic_out = ortho_(nn.Linear(critic_channels, n_values), 1.0)
-        self.n_values = n_values
-        self.policy_head_modules, self.value_head_modules = ["actor"], ["critic_conv", "critic_out"]  # freeze_* (unet.py:221-245)
+        ch = [int(c) for c in channels_per_level]
+        L = len(ch)
+        strides = list(strides_per_level) if strides_per_level is not None else [2] * (L - 1)
+        up_strides = list(deconv_strides_per_level) if deconv_strides_per_level is not None else strides
+        enc_blocks = list(encoder_residual_blocks_per_level) if encoder_residual_blocks_per_level is not None else [1] * L
+        dec_blocks = list(decoder_residual_blocks_per_level) if decoder_residual_blocks_per_level is not None else enc_blocks[:-1]
+        assert len(strides) == L - 1 and len(enc_blocks) == L and len(dec_blocks) == L - 1
+        self.obs_range = float(obs_range)
+
+        def down(cin: int, cout: int, stride) -> List[nn.Module]:
+            layers: List[nn.Module] = []
+            for i, s in enumerate(_stride_list(stride)):
+                k, pad = (s + 1, 1) if increment_kernel_size_on_down_conv and s % 2 == 0 else (s, 0)
+                layers += [nn.Conv2d(cin if i == 0 else cout, cout, k, stride=s, padding=pad), nn.GELU()]
+            return layers
+
+        def up(cin: int, cout: int, stride) -> List[nn.Module]:
+            layers: List[nn.Module] = []
+            for i, s in enumerate(_stride_list(stride)):
+                layers += [nn.ConvTranspose2d(cin if i == 0 else cout, cout, s, stride=s), nn.GELU()]
+            return layers
+
+        self.encoders = nn.ModuleList([nn.Sequential(nn.Conv2d(in_channels, ch[0], 3, padding=1), nn.GELU(),
+                                                     *[_SEResBlock(ch[0]) for _ in range(enc_blocks[0])])])
+        for lvl in range(1, L):
+            self.encoders.append(nn.Sequential(*down(ch[lvl - 1], ch[lvl], strides[lvl - 1]),
+                                               *[_SEResBlock(ch[lvl]) for _ in range(enc_blocks[lvl])]))
+        # decoders, deepest first: level L-1 only goes up; a middle level runs its blocks, then goes up; level 0 only blocks
+        self.decoders = nn.ModuleList([nn.Sequential(*up(ch[-1], ch[-2], up_strides[-1]))])
+        for lvl in range(L - 2, 0, -1):
+            # squeeze_unet.py:153-158 pairs level lvl with decoder_residual_blocks_per_level[lvl - 1] (its zip runs over
+            # the list without its LAST entry, which is therefore never used); kept, or parameter counts would differ
+            self.decoders.append(nn.Sequential(*[_SEResBlock(ch[lvl]) for _ in range(dec_blocks[lvl - 1])],
+                                               *up(ch[lvl], ch[lvl - 1], up_strides[lvl - 1])))
+        self.decoders.append(nn.Sequential(*[_SEResBlock(ch[0]) for _ in range(dec_blocks[0])]))
+        self.actor = ortho_(nn.Conv2d(ch[0], n_logits, 3, padding=1), 0.01)
+
+        flat_strides = [s for st in strides for s in _stride_list(st)]
+
+        def critic(n_out: int) -> nn.Sequential:
+            layers: List[nn.Module] = []
+            cin = ch[0]
+            for s in flat_strides:
+                k = max(3, s)
+                layers += [nn.Conv2d(cin, critic_channels, k, stride=s, padding=1 if k % 2 else 0), nn.GELU()]
+                cin = critic_channels
+            layers += [nn.AdaptiveAvgPool2d(1), nn.Flatten(), ortho_(nn.Linear(critic_channels, critic_channels)), nn.GELU(),
+                       ortho_(nn.Linear(critic_channels, n_out), 1.0)]
+            return nn.Sequential(*layers)
+
+        self.critic_activations = [a for a in critic_activations]
+        self.n_values = len(self.critic_activations)
+        self.shared_critic_head = bool(shared_critic_head)
+        self.critics = nn.ModuleList([critic(self.n_values)] if shared_critic_head else [critic(1) for _ in range(self.n_values)])
+        self.policy_head_modules, self.value_head_modules = ["actor"], ["critics"]  # freeze_* (backbone_actor_critic.py:254-265)
         self.to(memory_format=torch.channels_last)  # see GridEncoderDecoderActorCritic
 
+    def _values(self, x: torch.Tensor) -> torch.Tensor:
+        v = self.critics[0](x) if self.shared_critic_head else torch.cat([c(x) for c in self.critics], dim=1)
+        if any(a != "identity" for a in self.critic_activations):  # ChannelwiseActivation: one activation per head
+            v = torch.stack([_apply_activation(a, v[:, i]) for i, a in enumerate(self.critic_activations)], dim=1)
+        return v.squeeze(-1) if self.n_values == 1 else v
+
     def forward(self, obs: torch.Tensor) -> HeadOutputs:
-        x = self.stem(obs.float().contiguous(memory_format=torch.channels_last))
+        x = obs.float().contiguous(memory_format=torch.channels_last)
+        if self.obs_range != 1.0:
+            x = x / self.obs_range  # backbone_actor_critic.py:189-192
         skips = []
-        for i, enc in enumerate(self.enc):
+        for enc in self.encoders:
             x = enc(x)
-            if i < len(self.down):
-                skips.append(x)
-                x = self.down[i](x)
-        for i in reversed(range(len(self.up))):
-            x = self.dec[i](self.up[i](x) + skips[i])
+            skips.append(x)
+        x = self.decoders[0](skips[-1])
+        for skip, dec in zip(reversed(skips[:-1]), list(self.decoders)[1:]):
+            x = dec(skip + x)
         logits = self.actor(x).permute(0, 2, 3, 1)  # [B, H, W, S']
-        v = self.critic_out(self.critic_conv(x).mean(dim=(2, 3)))
-        return HeadOutputs(logits, v.squeeze(-1) if self.n_values == 1 else v)
+        return HeadOutputs(logits, self._values(x))
+
+
+def _apply_activation(name: str, x: torch.Tensor) -> torch.Tensor:
+    if name == "identity":
+        return x
+    if name == "tanh":
+        return torch.tanh(x)
+    if name == "relu":
+        return torch.relu(x)
+    if name == "sigmoid":
+        return torch.sigmoid(x)
+    raise NotImplementedError(f"critic output activation {name!r}")

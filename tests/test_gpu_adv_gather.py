@@ -138,3 +138,39 @@ def test_gather_full_size_round_trip(cuda):
     mb = perm[3 * 3072:4 * 3072]
     for s, sh, o in zip(srcs, shuffled, ops.gather_rows(srcs, mb)):
         assert torch.equal(o, sh[3 * 3072:4 * 3072]) and torch.equal(o[:5], s[mb[:5]])
+
+
+def test_gather_consumer_on_stream_without_sync(cuda):
+    """The narrow-row grid is a programmatic dependent of the wide-row grid.  Whatever follows on the stream (the
+    trunk reading the gathered observations) must see EVERY wide row: a consumer kernel that reads the last wide
+    rows immediately, on the same stream with no synchronisation, inside a captured graph at the C4 minibatch size,
+    replayed with fresh indices -- a wide grid still running when the consumer starts would leave stale rows."""
+    from rl_algo_impls_b200 import ops
+
+    M, B = 12288, 3072
+    g = torch.Generator(device=cuda).manual_seed(5)
+    obs = torch.rand((M, 74, 16, 16), device=cuda, generator=g)      # 75,776 B rows: wide path
+    masks = torch.rand((M, 256, 78), device=cuda, generator=g) < 0.5  # 19,968 B rows: wide path
+    logp = torch.randn(M, device=cuda, generator=g)                   # narrow path
+    idx = torch.zeros(B, dtype=torch.int64, device=cuda)
+    tail = 64  # the consumer reads the LAST gathered rows: the wide grid's last CTAs write them
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            o, m, lp = ops.gather_rows([obs, masks, logp], idx)
+            _ = o[-tail:].clone()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        o, m, lp = ops.gather_rows([obs, masks, logp], idx)
+        got_obs, got_mask, got_lp = o[-tail:].clone(), m[-tail:].clone(), lp.clone()  # consumers, same stream
+        o.zero_(), m.zero_()  # stale rows of an earlier replay can never pass for fresh ones
+    for rep in range(12):
+        perm = torch.randperm(M, device=cuda, generator=g)[:B]
+        idx.copy_(perm)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(got_obs, obs[perm[-tail:]]), f"replay {rep}: consumer saw a partially gathered obs"
+        assert torch.equal(got_mask, masks[perm[-tail:]]), f"replay {rep}: consumer saw partially gathered masks"
+        assert torch.equal(got_lp, logp[perm])

@@ -88,9 +88,9 @@ def test_policies_match_the_reference_parameter_counts(key):
     env = make_synthetic_env(cfg.env, 2, pool=1)
     policy = ActorCritic(env, **cfg.policy)
     n = sum(p.numel() for p in policy.parameters())
-    want = {"C1": 9155, "C2": 1686693, "C3": 142605, "C4": 851727}.get(key)
-    if want is not None:
-        assert n == want, (key, n)
+    # C5: the reference's squeeze_unet at the 64x64 Lux YAML entry (squeeze_unet.py:20/:198)
+    want = {"C1": 9155, "C2": 1686693, "C3": 142605, "C4": 851727, "C5": 4719274}[key]
+    assert n == want, (key, n)
     assert policy.value_shape == (() if SPECS[cfg.env].n_values == 1 else (SPECS[cfg.env].n_values,))
     if key == "C5":
         assert policy.action_shape == {"per_position": (4096, 6), "pick_position": (1,)}
@@ -163,7 +163,7 @@ def test_trajectory_rollout_fixture_is_present():
         assert int(z[f"{case}.r0.total_steps"]) == z[f"{case}.r0.obs"].shape[0] > 0
 
 
-@pytest.mark.parametrize("key", ["C1", "C2", "C3", "C4"])
+@pytest.mark.parametrize("key", ["C1", "C2", "C3", "C4", "C5"])
 def test_freeze_and_unfreeze_parameter_groups(key):
     """ActorCritic.freeze (actor_critic.py:384-395): heads and backbone toggle independently; unfreeze restores all."""
     cfg = CONFIGS[key]
