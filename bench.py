@@ -14,12 +14,18 @@ JSON line (rank 0):
              every env step uploads obs / masks / rewards and downloads the sampled actions
   roofline   the fused GridNet PPO-loss kernel (K4), CUDA events around every launch inside the
              timed region, algorithmic bytes / mean duration against MEASURED_PEAKS.json
-  cpu_baseline  the oracle restatement of the reference learner timed on the host cores (bounded sample)
+  cpu_baseline  the unmodified reference learner (oracle/_ref) timed on the host cores (bounded sample)
 
-N > 1 (torchrun, one process per GPU): envs shard across ranks (weak scaling: every rank runs the
-config's per-GPU env slice), gradients and advantage moments are all-reduced over NCCL.
-``--impl reference`` times the reference's own CPU path (the oracle port; the reference is pure
-Python + torch-CPU and cannot travel to the GPU box) on a bounded sample of the same config.
+Workloads.  N = 1 runs **C4** (GridNet MicroRTS 16x16, 24 envs x 512 steps: the largest config the reference's own CPU
+path can also run at full size) and adds ``scale_base``: the C5 single-GPU point of the scaling curve.  N > 1
+(torchrun, one process per GPU) runs **C5** (Lux 64x64, 1024 envs x 32 steps -- the config BASELINE.json names for the
+8-GPU split) with the 1024 envs sharded 1024 / N per GPU: ``"scaling": "strong"``.  Gradients are all-reduced over
+NCCL once per epoch (gradient accumulation); nothing else crosses ranks.  ``--config`` overrides the workload.
+
+``--impl reference`` times the UNMODIFIED reference (``rl_algo_impls.ppo.ppo.PPO`` + ``SyncStepRolloutGenerator`` +
+``ActorCritic`` from oracle/_ref, imported through oracle/ref_shim.py) on the host cores with all threads, on the same
+config: C1-C4 at full size with the number of timed steps bounded by a time budget (the line's ``steps`` / ``warmup``
+are what actually ran); C5 on a bounded env count stated in ``config``.
 """
 import argparse
 import json
@@ -40,15 +46,13 @@ import torch.distributed as dist  # noqa: E402
 METRIC = "PPO env-steps/sec (rollout+GAE+update)"
 UNIT = "env-steps/s"
 
-# bounded CPU samples per config: (n_envs, n_steps, batch_size, n_epochs) -- same maps / heads / trunk,
-# fewer env-steps per learn_epoch so that the CPU leg ends in tens of seconds
-CPU_SAMPLE = {
-    "C1": (8, 32, 256, 20),
-    "C2": (8, 32, 64, 4),
-    "C3": (512, 16, 2048, 4),
-    "C4": (24, 32, 192, 4),
-    "C5": (2, 4, 4, 2),
-}
+# The reference arm runs the full config; only C5 (50 GB of host buffers, minutes per minibatch on a CPU) is
+# sampled: the same map, heads, trunk, T and batch on fewer envs (env-steps/s is per-env linear on the CPU path).
+REF_ENVS = {"C5": 4}
+REF_BUDGET_S = 240.0  # the reference arm stops timing new learn_epochs after this much wall time
+# cpu_baseline inside the GPU arm (rank 0, N = 1): a bounded sample of the same reference learner,
+# (n_envs, n_steps, batch_size) -- tens of seconds of CPU work; the full-size number is the reference arm's
+CPU_SAMPLE = {"C1": (8, 32, 256), "C2": (8, 32, 64), "C3": (512, 16, 2048), "C4": (24, 64, 384), "C5": (2, 8, 16)}
 
 
 def peak_hbm_gbs():
@@ -119,12 +123,14 @@ class ClockSampler(threading.Thread):
 
 
 def measured_traffic(cfg_key: str, batch: int):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01/traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01", "traffic.json")
-    if not os.path.exists(p):
-        return None
-    entry = json.load(open(p)).get(cfg_key)
-    return int(entry["traffic_bytes_per_sample"] * batch) if entry else None
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r0N/traffic.json)."""
+    for rnd in ("r02", "r01"):
+        p = os.path.join(ROOT, "profiles", rnd, "traffic.json")
+        if os.path.exists(p):
+            entry = json.load(open(p)).get(cfg_key)
+            if entry:
+                return int(entry["traffic_bytes_per_sample"] * batch)
+    return None
 
 
 def loss_kernel_bytes(policy, batch: int, V: int, logits_bytes: int) -> int:
@@ -159,46 +165,132 @@ def timed_epochs(algo, gen, steps: int, world: int):
     return float(ms.item())
 
 
-def run_cpu_learner(cfg_key: str, steps: int, warmup: int, threads: int):
-    """The oracle learner (CPU restatement of the reference, oracle/learner.py) on a bounded sample."""
-    from oracle import learner as olearn
-    from rl_algo_impls_b200.configs import CONFIGS
-    from rl_algo_impls_b200.envs import make_synthetic_env
-    from rl_algo_impls_b200.policy import ActorCritic
+def workload_of(cfg, world: int, envs_per_gpu: int, n_steps: int, batch: int, n_epochs: int) -> dict:
+    big = cfg.key in ("C4", "C5")
+    return {"workload": f"{cfg.key}: {cfg.title}", "env": cfg.env, "n_envs_total": envs_per_gpu * world,
+            "envs_per_gpu": envs_per_gpu, "n_steps": n_steps, "batch_size": batch, "n_epochs": n_epochs,
+            "parallelism": f"env-sharded dp{world}",
+            "l2": ("not flushed: every minibatch gathers fresh rows and the minibatch working set (logits + dlogits "
+                   "490 MB per launch at C4, 119 MB at C5; rollout buffer 0.4-45 GB) exceeds the 126 MB L2" if big else
+                   "not flushed and the working set fits L2: this config is launch-bound, reported for completeness")}
 
-    cfg = CONFIGS[cfg_key]
-    n_envs, n_steps, batch, n_epochs = CPU_SAMPLE[cfg_key]
-    torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    env = make_synthetic_env(cfg.env, n_envs, seed=0, device=None, pool=2)
-    ac = ActorCritic(env, **cfg.policy)  # the trunk (plain torch modules) on the CPU
-    pol = olearn.OraclePolicy(ac.network, ac.kind, getattr(ac, "nvec", ()), getattr(ac, "map_size", 0),
-                              cfg.policy.get("subaction_mask"))
-    a = cfg.algo
-    as_np = lambda x: np.asarray(x, dtype=np.float64) if isinstance(x, (list, tuple)) else x
-    hp = olearn.Hyper(batch_size=batch, n_epochs=n_epochs, gamma=as_np(a.get("gamma", 0.99)),
-                      gae_lambda=as_np(a.get("gae_lambda", 0.95)), clip_range=a.get("clip_range", 0.2),
-                      clip_range_vf=a.get("clip_range_vf"), ent_coef=a.get("ent_coef", 0.0),
-                      vf_coef=a.get("vf_coef", 0.5), ppo2_vf_coef_halving=a.get("ppo2_vf_coef_halving", False),
-                      max_grad_norm=a.get("max_grad_norm", 0.5), multi_reward_weights=a.get("multi_reward_weights"),
-                      gradient_accumulation=a.get("gradient_accumulation", False),
-                      learning_rate=a.get("learning_rate", 3e-4))
-    opt = torch.optim.Adam(ac.parameters(), lr=hp.learning_rate, eps=1e-7)
-    state = {}
 
-    def epoch():
-        ro = olearn.collect_rollout(pol, env, n_steps, state)
-        olearn.learn_epoch(pol, opt, ro, hp)
+def run_reference_arm(args, cfg, threads: int):
+    """The unmodified reference on the host cores (oracle/_ref through oracle/ref_shim.py)."""
+    from oracle import ref_runner, ref_shim
 
-    for _ in range(warmup):
-        epoch()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        epoch()
-    dt = time.perf_counter() - t0
-    sample = (f"{cfg.key} shapes, {n_envs} envs x {n_steps} steps, batch {batch}, {n_epochs} epochs per learn_epoch; "
-              f"{steps} learn_epochs after {warmup} warm-up")
-    return n_envs * n_steps * steps / dt, dt / steps * 1e3, sample
+    if not ref_shim.available():
+        emit({"impl": "reference", "unavailable": "oracle/_ref is missing: run oracle/make_ref.sh where /root/reference exists"})
+        return
+    n_envs = REF_ENVS.get(cfg.key, cfg.n_envs)
+    value, ms, done, warm, sample = ref_runner.time_learn_epochs(cfg, max(1, args.steps), max(1, args.warmup), threads,
+                                                                 n_envs=n_envs, budget_s=REF_BUDGET_S)
+    w = workload_of(cfg, 1, n_envs, cfg.n_steps, cfg.algo["batch_size"], cfg.algo["n_epochs"])
+    w["parallelism"] = f"one CPU process, {threads} torch threads"
+    w["same_config_as_gpu_arm"] = n_envs == cfg.n_envs
+    if n_envs != cfg.n_envs:
+        w["sample"] = f"{n_envs} of the config's {cfg.n_envs} envs (same map, heads, trunk, n_steps and batch size)"
+    emit({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong" if cfg.key == "C5" else "weak", "vs_baseline": None,
+        "dtype": "f32" if not cfg.algo.get("autocast_loss") else "bf16 autocast (CPU) / f32",
+        "data": "synthetic", "config": w,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    })
+
+
+def run_cpu_baseline(cfg, threads: int):
+    """cpu_baseline of the GPU arm: the same unmodified reference learner on a bounded sample (tens of seconds)."""
+    from oracle import ref_runner, ref_shim
+
+    if not ref_shim.available():
+        return None
+    n_envs, n_steps, batch = CPU_SAMPLE[cfg.key]
+    v, _, _, _, sample = ref_runner.time_learn_epochs(cfg, 2, 1, threads, n_envs=n_envs, n_steps=n_steps,
+                                                      algo_overrides={"batch_size": batch}, budget_s=45.0)
+    return {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample}
+
+
+def gpu_leg(cfg, dev, rank: int, world: int, envs_per_gpu: int, steps: int, warmup: int, e2e_steps: int, local_rank: int):
+    """Device-resident leg (value, roofline, kernels, stages) + end-to-end leg of one config on this rank."""
+    from rl_algo_impls_b200 import ops
+    from rl_algo_impls_b200.configs import build
+
+    env, policy, gen, algo = build(cfg, dev, env_device=dev, seed=1234 + rank, n_envs=envs_per_gpu)
+    # The roofline leg brackets every fused-loss launch with CUDA events, which a graph replay would
+    # hide.  On the GridNet configs the update is GPU-bound on the trunk (measured: graphed 181.2 vs
+    # eager 181.9 ms per C4 step), so their update runs eagerly here; the rollout stays graph-replayed.
+    if policy.kind == "gridnet":
+        algo.cuda_graph_update = False
+    for _ in range(max(3, warmup)):
+        algo.learn_epoch(0, 1 << 40, gen, None)
+    algo.profile_stages = True
+    algo.learn_epoch(0, 1 << 40, gen, None)
+    algo.profile_stages = False
+    stages = algo.stage_ms
+    timer = ops.KernelTimer(["b200rl_ppo_gridnet_loss", "b200rl_gae_scan_f32", "b200rl_gather_rows",
+                             "b200rl_ppo_categorical_loss_f32", "b200rl_ppo_gaussian_loss_f32"])
+    ops.set_kernel_timer(timer)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms = timed_epochs(algo, gen, steps, world)
+    clock_info = clocks.stop()
+    ops.set_kernel_timer(None)
+    launches = algo.launches_last_epoch * steps
+    kernel_ms = timer.summary()
+    rollout_steps = envs_per_gpu * cfg.n_steps
+    value = rollout_steps * world * steps / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    peak, peak_src = peak_hbm_gbs()
+    V = max(1, int(np.prod(policy.value_shape)))
+    roofline = None
+    if "b200rl_ppo_gridnet_loss" in kernel_ms:
+        n, mean_ms = kernel_ms["b200rl_ppo_gridnet_loss"]
+        nbytes = loss_kernel_bytes(policy, cfg.algo["batch_size"], V, 2 if cfg.algo.get("autocast_loss") else 4)
+        achieved = nbytes / (mean_ms * 1e-3) / 1e9
+        roofline = {"kernel": "gridnet_kernel<kPpo> via b200rl_ppo_gridnet_loss (+ its 1-block stats finaliser"
+                              + ("" if policy.map_size <= 256 else " and the streaming pre-pass launch") + ")",
+                    "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": measured_traffic(cfg.key, cfg.algo["batch_size"]), "bytes_per_launch": nbytes,
+                    "ms_per_launch": mean_ms, "launches_timed": n, "peak_source": peak_src,
+                    "note": "mask-driven kernel: logits are read only for cells with a valid action, so DRAM "
+                            "traffic is below the algorithmic bytes (DESIGN.md 4.1)"}
+    elif "b200rl_gae_scan_f32" in kernel_ms:
+        n, mean_ms = kernel_ms["b200rl_gae_scan_f32"]
+        nbytes = rollout_steps * (16 * V + 1)
+        achieved = nbytes / (mean_ms * 1e-3) / 1e9
+        roofline = {"kernel": "gae_scan_kernel via b200rl_gae_scan_f32", "bound": "hbm", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "bytes_per_launch": nbytes,
+                    "ms_per_launch": mean_ms, "launches_timed": n, "peak_source": peak_src}
+    kernels = {k: {"launches": n, "ms_mean": m} for k, (n, m) in kernel_ms.items()}
+
+    # ---- end-to-end leg: host env, PCIe inside the timed region ------------------------------------
+    e2e = None
+    if e2e_steps > 0:
+        del gen, env
+        henv, _, hgen, halgo = build(cfg, dev, env_device=None, seed=1234 + rank, n_envs=envs_per_gpu)
+        halgo.cuda_graph_update = algo.cuda_graph_update
+        halgo.policy = policy
+        hgen.policy = policy
+        halgo.optimizer = algo.optimizer
+        halgo._params_broadcast = True
+        for _ in range(3):
+            halgo.learn_epoch(0, 1 << 40, hgen, None)
+        h2d0, d2h0 = hgen._upload.bytes, hgen.d2h_bytes
+        ms_e2e = timed_epochs(halgo, hgen, e2e_steps, world)
+        e2e = {"value": rollout_steps * world * e2e_steps / (ms_e2e / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": (hgen._upload.bytes - h2d0) // e2e_steps,
+               "d2h_bytes_per_step": (hgen.d2h_bytes - d2h0) // e2e_steps + halgo.d2h_bytes_last_epoch,
+               "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "bytes_are": "per rank",
+               "path": "host numpy VectorEnv -> DMA out of the env buffers (page-locked in place; small fields via pinned staging) -> HBM rollout buffer; sampled actions -> host"}
+        del hgen, henv, halgo
+    del algo, policy
+    torch.cuda.empty_cache()
+    return dict(value=value, ms=ms, clocks=clock_info, launches=launches, roofline=roofline, kernels=kernels,
+                stages=stages, e2e=e2e)
 
 
 def emit(line: dict) -> None:
@@ -219,38 +311,26 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--config", default=None, choices=["C1", "C2", "C3", "C4", "C5"],
+                    help="default: C4 on one GPU, C5 (1024 envs sharded) on several")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=None, help="override the env count per GPU (weak-scaling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scale-base", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = os.cpu_count() or 1
 
-    from rl_algo_impls_b200.configs import CONFIGS, build
+    from rl_algo_impls_b200.configs import CONFIGS
 
-    cfg = CONFIGS[args.config]
-    workload = {"workload": f"{cfg.key}: {cfg.title}", "env": cfg.env, "envs_per_gpu": cfg.n_envs,
-                "n_steps": cfg.n_steps, "batch_size": cfg.algo["batch_size"], "n_epochs": cfg.algo["n_epochs"],
-                "parallelism": f"env-sharded dp{args.gpus}",
-                "l2": ("not flushed: every minibatch gathers fresh rows and the minibatch working set (logits + dlogits "
-                       "490 MB per launch at C4, 119 MB at C5; rollout buffer 0.4-5.5 GB) exceeds the 126 MB L2"
-                       if cfg.key in ("C4", "C5") else
-                       "not flushed and the working set fits L2: this config is launch-bound, reported for completeness")}
-
+    key = args.config or ("C4" if max(args.gpus, world) == 1 else "C5")
+    cfg = CONFIGS[key]
     if args.impl == "reference":
-        if rank != 0:
-            return
-        value, ms, sample = run_cpu_learner(args.config, max(1, args.steps), max(1, min(args.warmup, 2)), threads)
-        emit({
-            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        })
+        if rank == 0:
+            run_reference_arm(args, cfg, threads)
         return
 
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (there is no CPU path)"
@@ -258,94 +338,41 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from rl_algo_impls_b200 import ops
+    sharded = key == "C5" and args.envs_per_gpu is None  # the config's GLOBAL env count split over the ranks
+    envs_per_gpu = args.envs_per_gpu or (cfg.n_envs // world if key == "C5" else cfg.n_envs)
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 5 if key == "C5" else 10))
+    res = gpu_leg(cfg, dev, rank, world, envs_per_gpu, args.steps, args.warmup, e2e_steps, local_rank)
 
-    # ---- device-resident leg -------------------------------------------------------------------
-    env, policy, gen, algo = build(cfg, dev, env_device=dev, seed=1234 + rank)
-    # The roofline leg brackets every fused-loss launch with CUDA events, which a graph replay would
-    # hide.  On the GridNet configs the update is GPU-bound on the trunk (measured: graphed 181.2 vs
-    # eager 181.9 ms per C4 step), so their update runs eagerly here; the rollout stays graph-replayed.
-    if policy.kind == "gridnet":
-        algo.cuda_graph_update = False
-    if world > 1:  # replicas start from rank 0's weights
-        for p in policy.parameters():
-            dist.broadcast(p.data, 0)
-    for _ in range(max(3, args.warmup)):
-        algo.learn_epoch(0, 1 << 40, gen, None)
-    algo.profile_stages = True
-    algo.learn_epoch(0, 1 << 40, gen, None)
-    algo.profile_stages = False
-    stages = algo.stage_ms
-    timer = ops.KernelTimer(["b200rl_ppo_gridnet_loss", "b200rl_gae_scan_f32", "b200rl_gather_rows",
-                             "b200rl_ppo_categorical_loss_f32", "b200rl_ppo_gaussian_loss_f32"])
-    ops.set_kernel_timer(timer)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    ms = timed_epochs(algo, gen, args.steps, world)
-    clock_info = clocks.stop()
-    ops.set_kernel_timer(None)
-    launches = algo.launches_last_epoch * args.steps
-    kernel_ms = timer.summary()
-    steps_total = cfg.rollout_steps * world * args.steps
-    value = steps_total / (ms / 1e3)
-
-    # ---- roofline of the dominant kernel ---------------------------------------------------------
-    peak, peak_src = peak_hbm_gbs()
-    V = max(1, int(np.prod(policy.value_shape)))
-    roofline = None
-    if "b200rl_ppo_gridnet_loss" in kernel_ms:
-        n, mean_ms = kernel_ms["b200rl_ppo_gridnet_loss"]
-        nbytes = loss_kernel_bytes(policy, cfg.algo["batch_size"], V, 2 if cfg.algo.get("autocast_loss") else 4)
-        achieved = nbytes / (mean_ms * 1e-3) / 1e9
-        roofline = {"kernel": "gridnet_kernel<kPpo> via b200rl_ppo_gridnet_loss (+ its 1-block stats finaliser)",
-                    "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": measured_traffic(cfg.key, cfg.algo["batch_size"]), "bytes_per_launch": nbytes,
-                    "ms_per_launch": mean_ms, "launches_timed": n, "peak_source": peak_src,
-                    "note": "mask-driven kernel: logits are read only for cells with a valid action, so DRAM "
-                            "traffic is below the algorithmic bytes (DESIGN.md 4.1)"}
-    elif "b200rl_gae_scan_f32" in kernel_ms:
-        n, mean_ms = kernel_ms["b200rl_gae_scan_f32"]
-        nbytes = cfg.rollout_steps * (16 * V + 1)
-        achieved = nbytes / (mean_ms * 1e-3) / 1e9
-        roofline = {"kernel": "gae_scan_kernel via b200rl_gae_scan_f32", "bound": "hbm", "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "bytes_per_launch": nbytes,
-                    "ms_per_launch": mean_ms, "launches_timed": n, "peak_source": peak_src}
-    kernels = {k: {"launches": n, "ms_mean": m} for k, (n, m) in kernel_ms.items()}
-
-    # ---- end-to-end leg: host env, PCIe inside the timed region ------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        del gen, env
-        henv, _, hgen, halgo = build(cfg, dev, env_device=None, seed=1234 + rank)
-        halgo.cuda_graph_update = algo.cuda_graph_update
-        halgo.policy = policy
-        hgen.policy = policy
-        halgo.optimizer = algo.optimizer
-        for _ in range(3):
-            halgo.learn_epoch(0, 1 << 40, hgen, None)
-        h2d0, d2h0 = hgen._upload.bytes, hgen.d2h_bytes
-        e2e_steps = max(1, min(args.steps, 3))
-        ms_e2e = timed_epochs(halgo, hgen, e2e_steps, world)
-        e2e = {"value": cfg.rollout_steps * world * e2e_steps / (ms_e2e / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": (hgen._upload.bytes - h2d0) // e2e_steps,
-               "d2h_bytes_per_step": (hgen.d2h_bytes - d2h0) // e2e_steps + halgo.d2h_bytes_last_epoch,
-               "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-               "path": "host numpy VectorEnv -> DMA out of the env buffers (page-locked in place; small fields via pinned staging) -> HBM rollout buffer; sampled actions -> host"}
+    # ---- the single-GPU point of the multi-GPU (C5, strong-scaling) curve ----------------------------
+    scale_base = None
+    if world == 1 and key == "C4" and args.config is None and not args.no_scale_base:
+        c5 = CONFIGS["C5"]
+        b = gpu_leg(c5, dev, rank, 1, c5.n_envs, 3, 3, 0, local_rank)
+        scale_base = {"workload": workload_of(c5, 1, c5.n_envs, c5.n_steps, c5.algo["batch_size"], c5.algo["n_epochs"]),
+                      "value": b["value"], "unit": UNIT, "steps": 3, "warmup": 3, "ms_per_step": b["ms"] / 3,
+                      "roofline": b["roofline"], "kernels": b["kernels"], "stages_ms": b["stages"],
+                      "note": "what `bench.py --gpus N` (N > 1) runs, on one GPU: divide the N-GPU values by this one"}
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, _, sample = run_cpu_learner(args.config, 2, 1, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        cpu = run_cpu_baseline(cfg, threads)
 
     if rank == 0:
+        bf16 = bool(cfg.algo.get("autocast_loss"))
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if not cfg.algo.get("autocast_loss") else "bf16 trunk / f32 loss math",
-            "data": "synthetic", "config": workload, "clocks": clock_info, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "stages_ms": stages,
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": res["ms"] / args.steps, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+            "dtype": ("bf16 autocast trunk / f32 loss math on bf16 logits" if bf16 else
+                      "f32 (loss kernels, GAE f64 carry); trunk convolutions run cuDNN's default TF32 tensor-op kernels"),
+            "data": "synthetic",
+            "config": workload_of(cfg, world, envs_per_gpu, cfg.n_steps, cfg.algo["batch_size"], cfg.algo["n_epochs"]),
+            "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["launches"], "roofline": res["roofline"],
+            "cpu_baseline": cpu, "kernels": res["kernels"], "stages_ms": res["stages"],
         }
+        if scale_base is not None:
+            line["scale_base"] = scale_base
         emit(line)
     if world > 1:
         dist.destroy_process_group()

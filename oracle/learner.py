@@ -47,6 +47,11 @@ class Hyper:
     teacher_unbiased: bool = True
     teacher_loss_importance_sampling: bool = True
     vf_loss_fn: str = "mse_loss"  # ppo.py:135,186: getattr(torch.nn.functional, vf_loss_fn)
+    vf_weights: Optional[Sequence[float]] = None  # ppo.py:344-345: v_loss @ vf_weights before the batch mean
+    # ppo.py:321 + shared/autocast.py:8-12: bf16 autocast around forward + loss -- ONLY on a CUDA device with bf16
+    # support; on the CPU (where this oracle and the live reference run) the flag changes nothing
+    autocast_loss: bool = False
+    logp_shift: float = 0.0  # fixture knob, not a reference keyword: added to the stored behaviour log-probs
 
 
 class OraclePolicy:
@@ -160,8 +165,10 @@ def learn_epoch(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict
                                 _take(b["masks"], slice(i, i + n_envs)))[0]
                 for i in range(0, total, n_envs)])
     n_mb = total // hp.batch_size + (1 if total % hp.batch_size else 0)
-    w = torch.tensor(np.asarray(hp.multi_reward_weights), dtype=torch.float32) if hp.multi_reward_weights is not None else None
-    vf_coef = torch.tensor(np.asarray(hp.vf_coef), dtype=torch.float32)
+    dt = b["adv"].dtype  # float32 (the reference's torch.Tensor(...) constants); float64 in the generators' f64 runs
+    w = torch.tensor(np.asarray(hp.multi_reward_weights), dtype=dt) if hp.multi_reward_weights is not None else None
+    vf_coef = torch.tensor(np.asarray(hp.vf_coef), dtype=dt)
+    vf_weights = torch.tensor(np.asarray(hp.vf_weights), dtype=dt) if hp.vf_weights is not None else None
     params = list(policy.parameters())
     pi_coef = 1
     step_stats: List[dict] = []
@@ -183,8 +190,8 @@ def learn_epoch(policy: OraclePolicy, optimizer: torch.optim.Optimizer, ro: dict
             logp, ent, v = policy.forward(b["obs"][idx], _take(b["actions"], idx), _take(b["masks"], idx))
             parts = ppo_loss(logp, ent, v, b["logprobs"][idx], mb_adv, b["values"][idx], b["returns"][idx],
                              clip_range=hp.clip_range, clip_range_vf=hp.clip_range_vf, ent_coef=hp.ent_coef,
-                             vf_coef=vf_coef, ppo2_vf_coef_halving=hp.ppo2_vf_coef_halving, pi_coef=pi_coef,
-                             kl_cutoff=hp.kl_cutoff, loss_divisor=n_mb if hp.gradient_accumulation else None,
+                             vf_coef=vf_coef, ppo2_vf_coef_halving=hp.ppo2_vf_coef_halving, vf_weights=vf_weights,
+                             pi_coef=pi_coef, kl_cutoff=hp.kl_cutoff, loss_divisor=n_mb if hp.gradient_accumulation else None,
                              teacher_logprobs=teacher_logp[idx] if teacher_logp is not None else None,
                              teacher_kl_loss_coef=hp.teacher_kl_loss_coef, teacher_unbiased=hp.teacher_unbiased,
                              teacher_loss_importance_sampling=hp.teacher_loss_importance_sampling,

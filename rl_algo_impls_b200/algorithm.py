@@ -2,7 +2,9 @@
 
 Keeps the surface the reference's runner relies on (``rl_algo_impls/shared/algorithm.py:19-60``):
 the five constructor fields, an abstract ``learn``, and ``save`` / ``load`` of the optimizer state
-under ``<dir>/optimizer.pt`` -- so checkpoints written by either implementation load in the other.
+under ``<dir>/optimizer.pt``.  ``load`` takes a state dict written by either implementation: the reference's has
+``capturable=False``, a Python-float learning rate and CPU step counters, which ``load`` converts back to what this
+optimizer was built with (device step counters, the SAME device learning-rate tensor captured graphs point at).
 """
 import logging
 from abc import ABC, abstractmethod
@@ -43,7 +45,29 @@ class Algorithm(ABC):
         if not state_file.exists():
             _log.info("no optimizer state at %s: the optimizer keeps its current state", state_file)
             return
-        self.optimizer.load_state_dict(torch.load(state_file, map_location=self.device))
+        self.load_optimizer_state(torch.load(state_file, map_location=self.device))
+
+    def load_optimizer_state(self, state: dict) -> None:
+        opt = self.optimizer
+        before = [(g.get("capturable"), g.get("lr")) for g in opt.param_groups]
+        opt.load_state_dict(state)
+        for group, (capturable, lr) in zip(opt.param_groups, before):
+            if isinstance(lr, torch.Tensor):  # keep the tensor object: captured update graphs read it
+                loaded = group["lr"]
+                lr.fill_(float(loaded))
+                group["lr"] = lr
+            if capturable is not None:
+                group["capturable"] = capturable
+            if capturable:
+                for p in group["params"]:
+                    st = opt.state.get(p)
+                    if st and "step" in st:
+                        step = st["step"]
+                        st["step"] = (step.to(device=p.device, dtype=torch.float32) if isinstance(step, torch.Tensor)
+                                      else torch.tensor(float(step), dtype=torch.float32, device=p.device))
+        graphs = getattr(self, "_update_graphs", None)
+        if graphs:  # captured updates hold the old state tensors
+            graphs.clear()
 
 
 def update_learning_rate(optimizer: Optimizer, learning_rate: float) -> None:

@@ -95,54 +95,81 @@ def _world() -> int:
 
 
 
+class _FlatGrads:
+    """Every trainable parameter's ``.grad`` as a view into ONE flat float32 buffer (same strides as the parameter, so
+    channels-last conv weights keep channels-last gradients and the optimizer's multi-tensor path stays on).  The
+    backward pass accumulates into the views; the data-parallel all-reduce, the norm and the clip then each touch one
+    contiguous buffer in place -- no flatten / unflatten copies and no per-parameter launches (ppo.py:441-447 does
+    ``clip_grad_norm_`` + ``zero_grad(set_to_none=True)``; here "none" is a zeroed buffer)."""
+
+    def __init__(self, params: List[nn.Parameter]):
+        self.params = params
+        self.key = tuple(id(p) for p in params)
+        n = sum(p.numel() for p in params)
+        self.flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
+        self.views: List[torch.Tensor] = []
+        off = 0
+        for p in params:
+            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+            v = (torch.as_strided(self.flat, tuple(p.shape), tuple(p.stride()), off) if dense
+                 else self.flat[off:off + p.numel()].view(p.shape))
+            self.views.append(v)
+            off += p.numel()
+
+    def attach(self) -> None:
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                p.grad = v
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+
 class _GraphedUpdate:
     """One minibatch update -- K3 gather, K2 moments, trunk forward, K4 fused loss, trunk backward and
     (unless gradients accumulate) clip + Adam -- captured once per (batch size, hyperparameters, buffer
     addresses) and replayed per minibatch.  Collectives stay outside the captured segments: at world
     size R > 1 the update is three segments with the moments all-reduce and the gradient all-reduce
-    between them; at R == 1 it is a single graph."""
+    between them; at R == 1 (or under gradient accumulation, where a minibatch needs no collective at all)
+    it is a single graph."""
 
-    def __init__(self, algo: "PPO", batch, B: int, h: ops.PpoHyper, accumulate: bool):
-        self.algo, self.B, self.accumulate = algo, B, accumulate
+    def __init__(self, algo: "PPO", batch, B: int, h: ops.PpoHyper, accumulate: bool, flat: _FlatGrads):
+        self.algo, self.B, self.accumulate, self.flat = algo, B, accumulate, flat
         self.world = _world()
         dev = algo.device
         self.idx = torch.zeros(B, dtype=torch.int64, device=dev)
-        self.params = [p for p in algo.policy.parameters() if p.requires_grad]
+        self.params = flat.params
         self.pool = torch.cuda.graph_pool_handle()
         self.graphs: List[torch.cuda.CUDAGraph] = []
         self.kernels_per_replay = 0
         self.stats: Optional[torch.Tensor] = None
         self.grad_norm: Optional[torch.Tensor] = None
-        self._mb = self._moments = self._flat = None
+        self._mb = self._moments = None
+        self.collectives = self.world > 1 and not accumulate
 
         def seg_a():
             self._mb = batch[self.idx]
             self._moments = algo._moments_local(self._mb.advantages, h)
 
         def seg_b():
+            if not accumulate:
+                flat.zero()
             self.stats, _ = algo._minibatch(self._mb, h, None, moments=self._moments)
-            if self.world > 1:
-                self._flat = torch._utils._flatten_dense_tensors([p.grad for p in self.params])
 
         def seg_c():
-            if self.world > 1:
-                for p, f in zip(self.params, torch._utils._unflatten_dense_tensors(self._flat, [p.grad for p in self.params])):
-                    p.grad.copy_(f)
-            self.grad_norm = nn.utils.clip_grad_norm_(self.params, algo.max_grad_norm).detach()
-            algo.optimizer.step()
+            self.grad_norm = algo._clip_and_step(flat, self.world)
 
         self.segments = [seg_a, seg_b] + ([] if accumulate else [seg_c])
         self._capture()
 
     def _between(self, k: int) -> None:
         """Collectives between segment k and k + 1 (eager, on the same stream)."""
-        if self.world == 1:
+        if not self.collectives:
             return
         if k == 0 and self._moments is not None:
             dist.all_reduce(self._moments)
         if k == 1:
-            dist.all_reduce(self._flat)
-            self._flat.div_(self.world)
+            dist.all_reduce(self.flat.flat)
 
     def _run_eager(self) -> None:
         for k, seg in enumerate(self.segments):
@@ -157,23 +184,16 @@ class _GraphedUpdate:
         had_state = {id(p): (p in opt.state and len(opt.state[p]) > 0) for p in self.params}
         saved_s = {id(p): {k: v.detach().clone() for k, v in opt.state[p].items() if torch.is_tensor(v)}
                    for p in self.params if had_state[id(p)]}
-        if self.accumulate:
-            for p in self.params:  # backward must ACCUMULATE into fixed buffers
-                if p.grad is None:
-                    p.grad = torch.zeros_like(p)
-        else:
-            opt.zero_grad(set_to_none=True)  # backward must ASSIGN fresh (graph-pool) gradients
+        self.flat.attach()
+        self.flat.zero()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
                 self._run_eager()
-                if not self.accumulate:
-                    opt.zero_grad(set_to_none=True)
         torch.cuda.current_stream().wait_stream(side)
         before = ops.LAUNCHES
-        merged = self.world == 1
-        if merged:
+        if not self.collectives:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=self.pool):
                 for seg in self.segments:
@@ -197,17 +217,11 @@ class _GraphedUpdate:
                     for v in st.values():
                         if torch.is_tensor(v):
                             v.zero_()
-            if self.accumulate:
-                for p in self.params:
-                    p.grad.zero_()
-        self.grad_buffers = [p.grad for p in self.params] if self.accumulate else None
+            self.flat.zero()
 
     def attach(self) -> None:
-        """Accumulating graphs add into fixed gradient buffers: make sure they are the parameters' .grad."""
-        if self.accumulate:
-            for p, g in zip(self.params, self.grad_buffers):
-                if p.grad is not g:
-                    p.grad = g
+        """The captured backward adds into the flat gradient buffer: make sure its views are the parameters' .grad."""
+        self.flat.attach()
 
     def run(self, idx: torch.Tensor):
         self.idx.copy_(idx, non_blocking=True)
@@ -264,6 +278,9 @@ class PPO(Algorithm):
         super().__init__(policy, device, tb_writer, learning_rate,
                          Adam(policy.parameters(), lr=lr, eps=1e-7, capturable=on_cuda))
         self.cuda_graph_update = on_cuda  # replay the minibatch update from CUDA graphs when possible
+        self.flat_gradients = on_cuda  # gradients live in one flat buffer (see _FlatGrads) unless freeze_* is active
+        self._flat: Optional[_FlatGrads] = None
+        self._params_broadcast = False  # data-parallel replicas take rank 0's weights before the first update
         self._update_graphs: Dict[tuple, "_GraphedUpdate"] = {}
         self._captures_in_a_row = 0
         self.policy = policy
@@ -354,8 +371,13 @@ class PPO(Algorithm):
         return ops.adv_moments(adv.reshape(adv.shape[0], -1), None, h.adv_mode, h.adv_weights)
 
     def _moments(self, adv: torch.Tensor, h: ops.PpoHyper) -> Optional[torch.Tensor]:
+        """Per-minibatch advantage statistics (ppo.py:307-318).  Data-parallel ranks stepping per minibatch form ONE
+        global minibatch out of their local ones: (sum, sumsq, count) are additive, so one all-reduce gives its exact
+        statistics.  Under gradient accumulation the minibatches are the reference's own contiguous index ranges
+        (shuffle=False) and every rank walks its env shard's ranges, so each local minibatch IS a reference minibatch
+        and is normalised by its own statistics, as there: no collective per minibatch."""
         moments = self._moments_local(adv, h)
-        if moments is not None and _world() > 1:  # exact global-minibatch statistics: (sum, sumsq, count) are additive
+        if moments is not None and _world() > 1 and not self.gradient_accumulation:
             dist.all_reduce(moments)
         return moments
 
@@ -442,7 +464,8 @@ class PPO(Algorithm):
         key = (self.batch_size, bool(self.gradient_accumulation), bool(self.autocast_loss), float(self.max_grad_norm),
                h.clip_range, h.clip_range_vf, h.ent_coef, tuple(h.vf_coef), h.vf_halving, h.loss_scale, h.adv_mode,
                tuple(h.adv_weights) if h.adv_weights is not None else None, h.vf_loss, h.teacher_kl_coef, h.teacher_unbiased,
-               h.teacher_importance, tuple(t.data_ptr() for t in tensors))
+               h.teacher_importance, tuple(t.data_ptr() for t in tensors),
+               tuple(id(p) for p in self.policy.parameters() if p.requires_grad))
         g = self._update_graphs.get(key)
         if g is not None:
             self._captures_in_a_row = 0
@@ -452,7 +475,10 @@ class PPO(Algorithm):
         self._captures_in_a_row += 1
         if len(self._update_graphs) >= 4:
             self._update_graphs.pop(next(iter(self._update_graphs)))
-        g = _GraphedUpdate(self, batch, self.batch_size, h, bool(self.gradient_accumulation))
+        flat = self._flat_grads()
+        if flat is None:
+            return None
+        g = _GraphedUpdate(self, batch, self.batch_size, h, bool(self.gradient_accumulation), flat)
         self._update_graphs[key] = g
         return g
 
@@ -490,28 +516,31 @@ class PPO(Algorithm):
 
         step_stats: List[torch.Tensor] = []
         grad_norms: List[torch.Tensor] = []
+        self._broadcast_parameters_once()
         graphed = self._graphed_update(r, h)
-        if graphed is None:
-            self.optimizer.zero_grad(set_to_none=True)  # a captured update may have left its gradient buffers attached
+        flat = graphed.flat if graphed is not None else self._flat_grads()
+        if flat is None:
+            self.optimizer.zero_grad(set_to_none=True)  # a flat buffer of an earlier epoch may still be attached
         else:
-            graphed.attach()
+            flat.attach()
         for _ in range(self.n_epochs):
             step_stats.clear()  # only the last epoch's stats are reported (ppo.py:287-289)
             grad_norms.clear()
+            if flat is not None and self.gradient_accumulation:
+                flat.zero()
             if graphed is not None:
-                if self.gradient_accumulation:
-                    for p in graphed.params:
-                        p.grad.zero_()
                 for idx in r.minibatch_indices(self.batch_size, shuffle=not self.gradient_accumulation):
                     stats, gn = graphed.run(idx)
                     step_stats.append(stats)
                     if gn is not None:
                         grad_norms.append(gn)
                 if self.gradient_accumulation:
-                    grad_norms.append(self.optimizer_step_device(keep_grad_buffers=True))
+                    grad_norms.append(self.optimizer_step_device())
                 continue
             for mb in r.minibatches(self.batch_size, shuffle=not self.gradient_accumulation):
                 self.policy.reset_noise(self.batch_size)
+                if flat is not None and not self.gradient_accumulation:
+                    flat.zero()
                 stats, _ = self._minibatch(mb, h, pi_coef_state)
                 step_stats.append(stats)
                 if not self.gradient_accumulation:
@@ -541,9 +570,17 @@ class PPO(Algorithm):
         else:
             var_y = np.var(r.y_true).item()
             explained_var = np.nan if var_y == 0 else 1 - np.var(r.y_true - r.y_pred).item() / var_y
+        if self.vf_weights is not None:
+            # ppo.py:344-345 contracts the per-head value losses with vf_weights BEFORE the batch mean, so the reported
+            # v_loss is their weighted sum (a scalar) and, without value clipping, so is the zero clip fraction (:394)
+            vw = np.asarray(self.vf_weights, dtype=np.float64).reshape(-1)
+            v_loss_of = lambda x: np.asarray(np.dot(x[5:5 + V], vw), dtype=np.float64)
+            vclip_of = lambda x: _vec(x[5 + V:5 + 2 * V], V) if self.clip_range_vf is not None else np.zeros(())
+        else:
+            v_loss_of = lambda x: _vec(x[5:5 + V], V)
+            vclip_of = lambda x: _vec(x[5 + V:5 + 2 * V], V)
         steps = [
-            TrainStepStats(float(x[0]), float(x[1]), _vec(x[5:5 + V], V), float(x[2]), float(x[3]), float(x[4]),
-                           _vec(x[5 + V:5 + 2 * V], V),
+            TrainStepStats(float(x[0]), float(x[1]), v_loss_of(x), float(x[2]), float(x[3]), float(x[4]), vclip_of(x),
                            {"teacher_kl_loss": float(x[5 + 2 * V])} if self.teacher_kl_loss_coef else {})
             for x in rows
         ]
@@ -561,8 +598,33 @@ class PPO(Algorithm):
         return timesteps_elapsed, True
 
     # ---------------------------------------------------------------------------------------------
+    def _flat_grads(self) -> Optional[_FlatGrads]:
+        """The flat gradient buffer of the trainable parameters, or None when the per-parameter path must run: a CPU
+        policy, ``flat_gradients`` off, or freeze_* in force (a frozen parameter must keep ``grad is None`` so that
+        Adam skips it, exactly like the reference's zero_grad(set_to_none=True))."""
+        if not self.flat_gradients or self.freeze_policy_head or self.freeze_value_head or self.freeze_backbone:
+            if self._flat is not None:
+                for p in self._flat.params:
+                    p.grad = None
+                self._flat = None
+            return None
+        params = [p for p in self.policy.parameters() if p.requires_grad]
+        if not params or not params[0].is_cuda or any(p.dtype != params[0].dtype for p in params):
+            return None
+        if self._flat is None or self._flat.key != tuple(id(p) for p in params):
+            self._flat = _FlatGrads(params)
+        return self._flat
+
+    def _broadcast_parameters_once(self) -> None:
+        """Data-parallel replicas (one process per GPU) must start from the same weights: rank 0's."""
+        if self._params_broadcast or _world() == 1:
+            return
+        for t in list(self.policy.parameters()) + list(self.policy.buffers()):
+            dist.broadcast(t.data, 0)
+        self._params_broadcast = True
+
     def _sync_grads(self, params: List[nn.Parameter]) -> None:
-        """Data-parallel ranks (envs sharded): one all-reduce of the flattened gradients, then / R,
+        """Data-parallel ranks (envs sharded), per-parameter path: one all-reduce of the flattened gradients, then / R,
         issued before the clip so that clipping sees the global gradient (ppo.py:441-447)."""
         world = _world()
         if world == 1:
@@ -574,13 +636,30 @@ class PPO(Algorithm):
         for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
             g.copy_(f)
 
-    def optimizer_step_device(self, keep_grad_buffers: bool = False) -> torch.Tensor:
+    def _clip_and_step(self, flat: _FlatGrads, world: int) -> torch.Tensor:
+        """clip_grad_norm_ + Adam.step over the flat buffer, which holds the SUM of the ranks' gradients (already
+        all-reduced): the mean's norm is |sum| / R, and the / R is folded into the clip coefficient -- one norm and one
+        scale over one contiguous buffer (torch.nn.utils.clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)))."""
+        norm = torch.linalg.vector_norm(flat.flat)
+        if world > 1:
+            norm = norm / world
+        coef = torch.clamp(self.max_grad_norm / (norm + 1e-6), max=1.0)
+        flat.flat.mul_(coef / world if world > 1 else coef)
+        self.optimizer.step()
+        return norm.detach()
+
+    def optimizer_step_device(self) -> torch.Tensor:
+        flat = self._flat
+        if flat is not None and all(p.grad is v for p, v in zip(flat.params, flat.views)):
+            world = _world()
+            if world > 1:  # in place, no flatten / unflatten copies; before the clip, so clipping sees the global gradient
+                dist.all_reduce(flat.flat)
+            return self._clip_and_step(flat, world)
         params = [p for p in self.policy.parameters() if p.grad is not None]
         self._sync_grads(params)
         grad_norm = nn.utils.clip_grad_norm_(params, self.max_grad_norm)
         self.optimizer.step()
-        if not keep_grad_buffers:  # the captured accumulate-backward writes into fixed gradient buffers
-            self.optimizer.zero_grad(set_to_none=True)
+        self.optimizer.zero_grad(set_to_none=True)
         return grad_norm.detach()
 
     def optimizer_step(self) -> float:

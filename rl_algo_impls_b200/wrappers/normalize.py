@@ -69,14 +69,26 @@ class ExponentialMovingMeanVar:
     def initialized(self) -> bool:
         return bool(self._initialized[0].item())
 
+    def _state_shape(self) -> Tuple[int, ...]:
+        """Shape of the arrays the reference would hold right now: `shape` before the first update and for vector
+        rewards; (N,) once scalar rewards went through its broadcasting update (running_mean_std.py:79-96)."""
+        return (self.per_env,) if self.per_env and self.initialized else self.shape
+
     def save(self, path: str) -> None:
-        np.savez_compressed(path, mean=self.mean.cpu().numpy().reshape(self.shape),
-                            var=self.var.cpu().numpy().reshape(self.shape), initialized=self.initialized)
+        shape = self._state_shape()
+        take = (lambda t: t.cpu().numpy().reshape(shape)) if shape != () or not self.per_env else (
+            lambda t: t[:1].cpu().numpy().reshape(()))
+        np.savez_compressed(path, mean=take(self.mean), var=take(self.var), initialized=self.initialized)
 
     def load(self, path: str, count_override: Optional[int] = None) -> None:
+        """Accepts what either implementation wrote: arrays of the state's own size, or a single value that every
+        entry takes (a reference file saved before its first update, shape ())."""
         data = np.load(path)
-        self.mean.copy_(torch.from_numpy(np.asarray(data["mean"], np.float64).reshape(-1)))
-        self.var.copy_(torch.from_numpy(np.asarray(data["var"], np.float64).reshape(-1)))
+        for name, dst in (("mean", self.mean), ("var", self.var)):
+            src = torch.from_numpy(np.asarray(data[name], np.float64).reshape(-1))
+            if src.numel() not in (1, dst.numel()):
+                raise ValueError(f"{path}: {name} has {src.numel()} entries, this normaliser holds {dst.numel()}")
+            dst.copy_(src.expand(dst.numel()) if src.numel() == 1 else src)
         self.squared_mean.copy_(self.var + self.mean ** 2)
         self._initialized.fill_(int(bool(data["initialized"].item())))
 

@@ -97,11 +97,16 @@ def golden_gridnet():
         "microrts_8x8_ungated_dense": (3, 8, MICRORTS_NVEC, None, 0, 0.6),
         "lux_8x8_pick": (4, 8, LUX_NVEC, LUX_GATES, 1, 0.1),
         "all_masked": (2, 4, LUX_NVEC, LUX_GATES, 1, 0.0),
+        # round 2: the chosen action lands on a MASKED entry of a head that has valid entries (categorical.py:25-36 keeps
+        # the finfo.min logit: log-prob finfo.min, -inf once two of them meet in one sample's sum)
+        "microrts_8x8_masked_actions": (6, 8, MICRORTS_NVEC, MICRORTS_GATES, 0, 0.2, 0.05),
+        "lux_8x8_pick_masked_actions": (6, 8, LUX_NVEC, LUX_GATES, 1, 0.15, 0.05),
     }
     out = {}
-    for name, (B, side, nvec, gates, n_pick, unit_p) in cases.items():
+    for name, (B, side, nvec, gates, n_pick, unit_p, *rest) in cases.items():
         HW = side * side
-        inp = to_torch(gridnet_inputs(zlib.crc32(name.encode()) % 1000, B, HW, nvec, n_pick, unit_p, logit_scale=2.0))
+        inp = to_torch(gridnet_inputs(zlib.crc32(name.encode()) % 1000, B, HW, nvec, n_pick, unit_p, logit_scale=2.0,
+                                      masked_action_p=rest[0] if rest else 0.0))
         logits, dist, action, masks = _ref_gridnet(inp, nvec, gates, HW, side)
         logp, ent = dist.log_prob(action), dist.entropy()
         g = torch.Generator().manual_seed(1)
@@ -212,6 +217,43 @@ class _RefPolicy(torch.nn.Module):
         return _ACForward(pi.log_prob(actions), pi.entropy(), out.values)
 
 
+def _f64(a):
+    if a is None:
+        return None
+    a = np.asarray(a)
+    return a.astype(np.float64) if a.dtype == np.float32 else a
+
+
+class _StopAfterFirstGradient(Exception):
+    pass
+
+
+class _FirstGradients:
+    """Instruments the run from OUTSIDE: wraps torch.nn.utils.clip_grad_norm_ (what optimizer_step calls first,
+    ppo.py:441-443) and keeps a copy of every parameter's gradient at its first call -- the gradient of the first
+    minibatch (of the first whole epoch under gradient accumulation), before clipping and before Adam."""
+
+    def __init__(self, net, stop: bool = False):
+        self.net, self.stop, self.grads = net, stop, {}
+
+    def __enter__(self):
+        self._orig = torch.nn.utils.clip_grad_norm_
+
+        def wrapped(parameters, *a, **k):
+            if not self.grads:
+                self.grads = {n: p.grad.detach().clone() for n, p in self.net.named_parameters() if p.grad is not None}
+                if self.stop:
+                    raise _StopAfterFirstGradient()
+            return self._orig(parameters, *a, **k)
+
+        torch.nn.utils.clip_grad_norm_ = wrapped
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        torch.nn.utils.clip_grad_norm_ = self._orig
+        return exc_type is _StopAfterFirstGradient
+
+
 class _Gen:
     def __init__(self, rollout, num_envs):
         self._r = rollout
@@ -250,6 +292,8 @@ def _learner_case(name, kind, make_net, T, N, obs_shape, hp: olearn.Hyper, nvec=
     with torch.no_grad():
         lp = pol(flat(ro["obs"]), flat(ro["actions"]), flat(ro["masks"]))[0]
     ro["logprobs"] = (lp.numpy().reshape(T, N) + rng.standard_normal((T, N)).astype(np.float32) * 0.1).astype(np.float32)
+    if hp.logp_shift:
+        ro["logprobs"] = (ro["logprobs"] + np.float32(hp.logp_shift)).astype(np.float32)
 
     def ref_rollout(gamma, gae_lambda):
         return RefVecRollout(torch.device("cpu"), ro["next_episode_starts"], ro["next_values"], ro["obs"], ro["actions"],
@@ -260,7 +304,9 @@ def _learner_case(name, kind, make_net, T, N, obs_shape, hp: olearn.Hyper, nvec=
     kw = {k: getattr(hp, k) for k in ("batch_size", "n_epochs", "clip_range", "clip_range_vf", "normalize_advantage",
                                       "standardize_advantage", "ent_coef", "ppo2_vf_coef_halving", "max_grad_norm",
                                       "gradient_accumulation", "kl_cutoff", "normalize_advantages_after_scaling",
-                                      "learning_rate", "vf_loss_fn")}
+                                      "learning_rate", "vf_loss_fn", "autocast_loss")}
+    if hp.vf_weights is not None:
+        kw["vf_weights"] = list(hp.vf_weights)
     as_list = lambda x: x.tolist() if isinstance(x, np.ndarray) else x
     teacher_net = teacher_pol = None
     if hp.teacher_kl_loss_coef:
@@ -282,7 +328,8 @@ def _learner_case(name, kind, make_net, T, N, obs_shape, hp: olearn.Hyper, nvec=
             return True
 
     torch.manual_seed(seed + 100)  # the randperm stream of the minibatch loop
-    algo.learn_epoch(0, T * N, _Gen(ref_rollout, N), [_CB()])
+    with _FirstGradients(net) as ref_grads:  # the gradient the reference hands to its FIRST clip_grad_norm_ (ppo.py:441-443)
+        algo.learn_epoch(0, T * N, _Gen(ref_rollout, N), [_CB()])
     s = stats_box["s"]
     final = {k: v.detach().clone() for k, v in net.state_dict().items()}
 
@@ -293,7 +340,23 @@ def _learner_case(name, kind, make_net, T, N, obs_shape, hp: olearn.Hyper, nvec=
     opt = torch.optim.Adam(net2.parameters(), lr=hp.learning_rate, eps=1e-7)
     torch.manual_seed(seed + 100)
     oteacher = olearn.OraclePolicy(teacher_net, kind, nvec, HW, gates) if teacher_net is not None else None
-    ostats = olearn.learn_epoch(opol, opt, ro, hp, teacher=oteacher)
+    with _FirstGradients(net2) as oracle_grads:
+        ostats = olearn.learn_epoch(opol, opt, ro, hp, teacher=oteacher)
+    for k, g in ref_grads.grads.items():
+        exact(oracle_grads.grads[k], g, f"learner {name} first gradient {k}")
+    # the same first gradient evaluated in float64 (the conditioned bar of tests/parity.py needs it)
+    net64 = make_net()
+    net64.load_state_dict(init)
+    net64.double()
+    ro64 = {k: ({kk: _f64(vv) for kk, vv in v.items()} if isinstance(v, dict) else _f64(v)) for k, v in ro.items()}
+    torch.manual_seed(seed + 100)
+    teacher64 = None
+    if teacher_net is not None:
+        import copy
+        teacher64 = olearn.OraclePolicy(copy.deepcopy(teacher_net).double(), kind, nvec, HW, gates)
+    with _FirstGradients(net64, stop=True) as grads64:
+        olearn.learn_epoch(olearn.OraclePolicy(net64, kind, nvec, HW, gates),
+                           torch.optim.Adam(net64.parameters(), lr=hp.learning_rate, eps=1e-7), ro64, hp, teacher=teacher64)
     if teacher_net is not None:
         exact(np.float64(ostats["teacher_kl_loss"]), np.float64(s.additional_losses["teacher_kl_loss"]), f"learner {name} teacher_kl_loss")
     for k, v in net2.state_dict().items():
@@ -304,6 +367,8 @@ def _learner_case(name, kind, make_net, T, N, obs_shape, hp: olearn.Hyper, nvec=
 
     out = {f"init.{k}": v.numpy() for k, v in init.items()}
     out.update({f"final.{k}": v.numpy() for k, v in final.items()})
+    out.update({f"grad0.{k}": v.numpy() for k, v in ref_grads.grads.items()})
+    out.update({f"grad0_f64.{k}": v.numpy() for k, v in grads64.grads.items()})
     for k, v in ro.items():
         if isinstance(v, dict):
             for kk, vv in v.items():

@@ -38,6 +38,38 @@ LEARNER_CASES = {
                         hp=olearn.Hyper(batch_size=32, n_epochs=2, gamma=0.98, gae_lambda=0.92, clip_range=0.1,
                                         ent_coef=4e-4, vf_coef=0.581, max_grad_norm=0.8, learning_rate=1e-3,
                                         vf_loss_fn="l1_loss")),
+    # ---- round 2: the branches of ppo.py:307-355 that had no live-reference fixture ------------------------------
+    # kl_cutoff (ppo.py:352-355): the stored behaviour log-probs are shifted so that approx_kl crosses the cut-off
+    "microrts_kl_cutoff": dict(kind="gridnet", T=8, N=6, obs_shape=(5, 8, 8), nvec=MICRORTS_NVEC, side=8,
+                               gates=MICRORTS_GATES, V=1,
+                               hp=olearn.Hyper(batch_size=24, n_epochs=3, gamma=0.999, gae_lambda=0.99, clip_range=0.1,
+                                               clip_range_vf=0.1, ppo2_vf_coef_halving=True, ent_coef=0.01, vf_coef=0.5,
+                                               learning_rate=1e-3, kl_cutoff=2e-3, logp_shift=0.05)),
+    # standardize_advantage (ppo.py:315-316)
+    "cartpole_standardize": dict(kind="categorical", T=16, N=8, obs_shape=(4,), nvec=(2,), V=1,
+                                 hp=olearn.Hyper(batch_size=32, n_epochs=2, gamma=0.98, gae_lambda=0.8, clip_range=0.2,
+                                                 normalize_advantage=False, standardize_advantage=True,
+                                                 learning_rate=1e-3)),
+    # normalize_advantages_after_scaling with multi-head rewards (ppo.py:307-311)
+    "lux_after_scaling": dict(kind="gridnet", T=6, N=4, obs_shape=(5, 8, 8), nvec=LUX_NVEC, side=8, gates=LUX_GATES,
+                              n_pick=1, V=3,
+                              hp=olearn.Hyper(batch_size=8, n_epochs=2, gamma=np.array([1.0, 1.0, 0.99]),
+                                              gae_lambda=np.array([0.95, 0.95, 0.9]), clip_range=0.1, ent_coef=0.01,
+                                              vf_coef=[0.5, 0.25, 0.25], multi_reward_weights=[0.6, 0.3, 0.1],
+                                              normalize_advantages_after_scaling=True, learning_rate=1e-3)),
+    # vf_weights (ppo.py:344-345): the per-head value losses are contracted before the batch mean; scalar vf_coef
+    "lux_vf_weights": dict(kind="gridnet", T=6, N=4, obs_shape=(5, 8, 8), nvec=LUX_NVEC, side=8, gates=LUX_GATES,
+                           n_pick=1, V=3,
+                           hp=olearn.Hyper(batch_size=12, n_epochs=2, gamma=np.array([1.0, 1.0, 0.99]),
+                                           gae_lambda=np.array([0.95, 0.95, 0.9]), clip_range=0.1, clip_range_vf=0.2,
+                                           ent_coef=0.01, vf_coef=0.5, vf_weights=[1.0, 0.5, 0.25],
+                                           multi_reward_weights=[0.6, 0.3, 0.1], learning_rate=1e-3)),
+    # autocast_loss (ppo.py:321): a no-op on the CPU reference (shared/autocast.py:8-12 enables it on CUDA only), so
+    # this fixture pins the f32 result; the GPU path under the flag runs the trunk in bf16 and is held to a bf16 bar
+    "microrts_autocast": dict(kind="gridnet", T=8, N=6, obs_shape=(5, 8, 8), nvec=MICRORTS_NVEC, side=8,
+                              gates=MICRORTS_GATES, V=1,
+                              hp=olearn.Hyper(batch_size=24, n_epochs=2, gamma=0.999, gae_lambda=0.99, clip_range=0.1,
+                                              ent_coef=0.01, vf_coef=0.5, learning_rate=1e-3, autocast_loss=True)),
 }
 
 

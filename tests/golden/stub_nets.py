@@ -16,7 +16,7 @@ class TinyMlp(nn.Module):
         self.n_values = n_values
 
     def forward(self, obs):
-        x = self.body(obs.float().reshape(obs.shape[0], -1))
+        x = self.body(obs.to(self.pi.weight.dtype).reshape(obs.shape[0], -1))  # f32; f64 in the generators' float64 runs
         v = self.v(x)
         return SimpleNamespace(pi=self.pi(x), values=v.squeeze(-1) if self.n_values == 1 else v, log_std=self.log_std)
 
@@ -32,7 +32,7 @@ class TinyGrid(nn.Module):
         self.n_values = n_values
 
     def forward(self, obs):
-        x = torch.tanh(self.conv(obs.float()))
+        x = torch.tanh(self.conv(obs.to(self.conv.weight.dtype)))
         v = self.v(x.mean(dim=(2, 3)))
         return SimpleNamespace(pi=self.actor(x).permute(0, 2, 3, 1), values=v.squeeze(-1) if self.n_values == 1 else v,
                                log_std=None)

@@ -45,9 +45,12 @@ def gridnet_inputs(
     n_pick: int = 0,
     unit_p: float = 0.06,
     logit_scale: float = 1.0,
+    masked_action_p: float = 0.0,
 ):
     """logits [B, HW, S + n_pick] f32, mask [B, HW, S] bool, pick_mask [B, n_pick, HW] bool or None,
-    actions [B, HW, A] int64 (valid wherever the head has a valid entry), pick_actions [B, n_pick] or None."""
+    actions [B, HW, A] int64 (valid wherever the head has a valid entry), pick_actions [B, n_pick] or None.
+    ``masked_action_p`` > 0: that fraction of the heads (and pick heads) that have both valid and masked entries get a
+    MASKED entry as their action -- the reference then keeps the finfo.min logit for it (categorical.py:25-36)."""
     rng = np.random.default_rng(seed)
     S, A = int(sum(nvec)), len(nvec)
     logits = (rng.standard_normal((B, HW, S + n_pick)) * logit_scale).astype(np.float32)
@@ -60,6 +63,9 @@ def gridnet_inputs(
         any_valid = m.any(-1)
         actions[..., h] = np.where(any_valid, np.argmax(np.where(any_valid[..., None], score, 0.0), -1),
                                    rng.integers(0, n, size=(B, HW)))
+        if masked_action_p > 0:
+            can = any_valid & (~m).any(-1) & (rng.random((B, HW)) < masked_action_p)
+            actions[..., h] = np.where(can, np.argmax(np.where(~m, rng.random(m.shape), -1.0), -1), actions[..., h])
         start += n
     pick_mask = pick_actions = None
     if n_pick:
@@ -73,6 +79,10 @@ def gridnet_inputs(
         anyp = pick_mask.any(-1)
         pick_actions = np.where(anyp, np.argmax(np.where(anyp[..., None], score, 0.0), -1),
                                 rng.integers(0, HW, size=(B, n_pick))).astype(np.int64)
+        if masked_action_p > 0:
+            can = anyp & (rng.random((B, n_pick)) < max(masked_action_p, 0.3))
+            pick_actions = np.where(can, np.argmax(np.where(~pick_mask, rng.random(pick_mask.shape), -1.0), -1),
+                                    pick_actions).astype(np.int64)
     return dict(logits=logits, mask=mask, pick_mask=pick_mask, actions=actions, pick_actions=pick_actions)
 
 

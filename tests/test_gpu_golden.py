@@ -6,8 +6,9 @@ import numpy as np
 import pytest
 import torch
 
-from tests.parity import close
-from tests.test_oracle_golden import LEARNER_CASES_ALL, cases, gates_of, learner_setup, load, rollout_from, teacher_net
+from tests.parity import close, rel_err
+from tests.test_oracle_golden import (LEARNER_CASES_ALL, FirstGradients, cases, gates_of, learner_setup, load, rollout_from,
+                                      teacher_net)
 
 pytestmark = pytest.mark.gpu
 
@@ -44,7 +45,13 @@ def test_gridnet_vs_reference_fixture(cuda, name):
     logp, ent = ops.gridnet_logp_entropy(spec, logits, t("mask"), t("pick_mask"), t("actions"), t("pick_actions"))
     (logp * t("dlogp") + ent * t("dentropy")).sum().backward()
     atol = 4e-7 * float(np.abs(g("logits")).max())
-    close(logp, g("logp"), atol=atol, what="logp")
+    # a chosen action on a masked entry gives finfo.min (one per sample) or -inf (several): those must match exactly
+    want_logp, got_logp = g("logp"), logp.detach().cpu().numpy()
+    huge = ~np.isfinite(want_logp) | (np.abs(want_logp) > 1e30)
+    np.testing.assert_array_equal(got_logp[huge], want_logp[huge])
+    if "masked_actions" in name:
+        assert huge.any(), "the fixture is meant to exercise the masked-chosen-action branch"
+    close(got_logp[~huge], want_logp[~huge], atol=atol, what="logp")
     close(ent, g("entropy"), atol=atol, what="entropy")
     close(logits.grad, g("dlogits"), atol=atol * 0.1, what="dlogits")
     S = int(g("nvec").sum())
@@ -100,8 +107,9 @@ def _device_policy(case, net, cuda):
     return ActorCritic(env, network=net, subaction_mask=case.get("gates")).to(cuda)
 
 
+@pytest.mark.parametrize("graphed", [False, True], ids=["eager", "graphed"])
 @pytest.mark.parametrize("name", LEARNER_CASES_ALL)
-def test_learn_epoch_vs_reference_fixture(cuda, name):
+def test_learn_epoch_vs_reference_fixture(cuda, name, graphed):
     from rl_algo_impls_b200.ppo import PPO
     from rl_algo_impls_b200.rollout import VecRollout
 
@@ -125,7 +133,7 @@ def test_learn_epoch_vs_reference_fixture(cuda, name):
                                       "normalize_advantage", "standardize_advantage", "ent_coef", "vf_coef",
                                       "ppo2_vf_coef_halving", "max_grad_norm", "multi_reward_weights",
                                       "gradient_accumulation", "kl_cutoff", "normalize_advantages_after_scaling",
-                                      "learning_rate", "vf_loss_fn")}
+                                      "learning_rate", "vf_loss_fn", "vf_weights", "autocast_loss")}
     tnet = teacher_net(case, z)
     if tnet is not None:  # teacher-KL term: the teacher checkpoint is an ActorCritic over the stored teacher weights
         from rl_algo_impls_b200.loss import TeacherKLLoss
@@ -136,6 +144,7 @@ def test_learn_epoch_vs_reference_fixture(cuda, name):
                   teacher_kl_loss_fn=TeacherKLLoss(mgr, unbiased=hp.teacher_unbiased),
                   teacher_loss_importance_sampling=hp.teacher_loss_importance_sampling)
     algo = PPO(policy, cuda, None, **kw)
+    algo.cuda_graph_update = graphed
     box = {}
 
     class CB:
@@ -143,10 +152,39 @@ def test_learn_epoch_vs_reference_fixture(cuda, name):
             box["s"] = train_stats
             return True
 
+    # the gradient handed to the first clip + Adam (flat-buffer path: PPO._clip_and_step; per-parameter path:
+    # torch.nn.utils.clip_grad_norm_), copied out before anything scales it
+    first = FirstGradients(policy.network.named_parameters())
+    orig_step = algo._clip_and_step
+
+    def spy(flat, world):
+        first.capture()
+        return orig_step(flat, world)
+
+    algo._clip_and_step = spy
     torch.manual_seed(int(z["seed"]) + 100)  # same randperm stream as the reference run
-    steps, cont = algo.learn_epoch(0, case["T"] * case["N"], Gen(), [CB()])
+    with first:
+        steps, cont = algo.learn_epoch(0, case["T"] * case["N"], Gen(), [CB()])
     assert steps == case["T"] * case["N"] and cont
     s = box["s"]
+    # bf16 autocast (CUDA only in the reference: shared/autocast.py:8-12) runs the trunk in bf16; the CPU reference that
+    # made the fixture ran f32, so that case is held to a bf16 bar: 2^-8 relative steps through the trunk
+    bf16 = bool(hp.autocast_loss)
+    # ---- pre-Adam gradient of the first minibatch: 1e-5 of the tensor's largest entry, conditioned (tests/parity.py) ----
+    if not graphed:  # a captured update takes its first step inside the warm-up runs of the capture
+        assert first.grads, "no gradient was captured"
+        for k, g in first.grads.items():
+            want32, want64 = z[f"grad0.{k}"], z[f"grad0_f64.{k}"]
+            e32 = rel_err(g, torch.from_numpy(want32))
+            if bf16:
+                assert e32 <= 5e-2, f"{name} first gradient {k}: {e32:.2e} (bf16 trunk)"
+                continue
+            if e32 <= 1e-5:
+                continue
+            e64 = rel_err(g, torch.from_numpy(want64))
+            ref = rel_err(torch.from_numpy(want32), torch.from_numpy(want64))
+            assert e64 <= max(1e-5, 3 * ref), (f"{name} first gradient {k}: {e32:.2e} from the f32 reference, {e64:.2e} from "
+                                               f"the f64 oracle (the f32 reference itself: {ref:.2e})")
     # parameters after n_epochs x minibatches of Adam steps: each step is lr * a unit-scale update, so
     # compare against the parameter *change* (final - init), not the parameter magnitude
     # Adam divides by sqrt(v): an element whose gradient is ~0 takes a +-lr step on rounding noise
@@ -158,14 +196,18 @@ def test_learn_epoch_vs_reference_fixture(cuda, name):
         got = v.cpu().numpy().astype(np.float64)
         rms_update = np.sqrt(np.mean((want - init) ** 2))
         rms_err = np.sqrt(np.mean((got - want) ** 2))
-        assert rms_err <= 1e-2 * rms_update + 1e-8, f"{name} param {k}: rms err {rms_err:.3e} vs rms update {rms_update:.3e}"
+        bar = 2e-1 if bf16 else 1e-2
+        assert rms_err <= bar * rms_update + 1e-8, f"{name} param {k}: rms err {rms_err:.3e} vs rms update {rms_update:.3e}"
         assert np.abs(got - want).max() <= 2 * hp.learning_rate * n_updates
     for k, tol in (("loss", 1e-4), ("pi_loss", 2e-3), ("entropy_loss", 1e-5), ("approx_kl", 2e-3), ("grad_norm", 1e-3),
                    ("explained_var", 1e-5)):
         got, want = getattr(s, k), float(z[f"stats.{k}"])
+        if bf16 and k != "explained_var":  # explained_var comes from the rollout alone
+            tol = 5e-2
         assert abs(got - want) <= tol * max(abs(want), 1e-2), f"{name} {k}: {got} vs {want}"
-    np.testing.assert_allclose(np.asarray(s.v_loss, np.float64), z["stats.v_loss"], rtol=1e-4)
-    assert abs(s.clipped_frac - float(z["stats.clipped_frac"])) <= 2.0 / hp.batch_size
+    np.testing.assert_allclose(np.asarray(s.v_loss, np.float64), z["stats.v_loss"], rtol=2e-2 if bf16 else 1e-4)
+    assert np.asarray(s.v_loss).shape == z["stats.v_loss"].shape
+    assert abs(s.clipped_frac - float(z["stats.clipped_frac"])) <= (4.0 if bf16 else 2.0) / hp.batch_size
     if tnet is not None:
         want = float(z["stats.teacher_kl_loss"])
         assert abs(s.additional_losses["teacher_kl_loss"] - want) <= 2e-3 * max(abs(want), 1e-2)

@@ -275,3 +275,52 @@ def test_fused_loss_at_full_size_properties(cuda, B, HW, nvec, gates, n_pick, V,
     st = full.stats.cpu().double()
     total = st[1] + 0.01 * st[2] + sum(vf[v] * st[5 + v] for v in range(V))
     assert abs(float(total - st[0])) <= 1e-5 * max(1.0, abs(float(st[0])))
+
+
+@pytest.mark.parametrize("nvec,gates,n_pick,HW,p", [(MICRORTS_NVEC, MICRORTS_GATES, 0, 256, 0.02),
+                                                    (LUX_NVEC, LUX_GATES, 1, 1024, 0.002)])
+def test_fused_with_masked_chosen_actions(cuda, nvec, gates, n_pick, HW, p):
+    """The chosen action lands on a MASKED entry of a head that has valid entries (gridnet.cu: `da == kF32Lowest`;
+    categorical.py:25-36 keeps the finfo.min logit).  The new log-prob is finfo.min (-inf once two meet in a sample's
+    sum), the ratio against a finite behaviour log-prob is exactly 0, the policy gradient of that sample vanishes
+    and its entropy / value terms are untouched: every output equals the oracle's, non-finite values included."""
+    from rl_algo_impls_b200 import ops
+
+    B, V = 24, 1
+    inp = to_torch(gridnet_inputs(91 + HW, B, HW, nvec, n_pick, 0.05, masked_action_p=p))
+    pp = to_torch(ppo_inputs(9, B, V))
+    logits, dist, action = oracle_dist(inp, nvec, gates, HW)
+    logp, ent = dist.log_prob(action), dist.entropy()
+    hit = ~torch.isfinite(logp.detach()) | (logp.detach() < -1e30)
+    assert hit.any() and not hit.all(), "the inputs are meant to mix regular and masked-chosen samples"
+    # a finite behaviour log-prob everywhere (the stored one of a masked-chosen sample cannot be finfo.min in practice)
+    old_logp = (torch.where(hit, torch.full_like(logp, -60.0), logp.detach()) + pp["old_logp_noise"]).float()
+    nv = pp["new_values"].clone().requires_grad_(True)
+    parts = ppo_loss(logp, ent, nv, old_logp, normalize_advantages(pp["adv"]), pp["old_values"], pp["returns"],
+                     clip_range=0.1, clip_range_vf=0.1, ent_coef=0.01, vf_coef=torch.tensor(0.5), ppo2_vf_coef_halving=True)
+    parts.loss.backward()
+    assert torch.isfinite(logits.grad).all() and torch.isfinite(parts.loss)
+    h = ops.PpoHyper(clip_range=0.1, clip_range_vf=0.1, ent_coef=0.01, vf_coef=[0.5], vf_halving=True)
+    dv = {k: (v.to(cuda) if v is not None else None) for k, v in inp.items()}
+    out = ops.ppo_gridnet_loss(h, spec_of(nvec, gates, n_pick), dv["logits"], dv["mask"], dv["pick_mask"], dv["actions"],
+                               dv["pick_actions"], old_logp.to(cuda), pp["adv"].to(cuda), pp["old_values"].to(cuda),
+                               pp["returns"].to(cuda), pp["new_values"].to(cuda), want_logp=True)
+    torch.cuda.synchronize()
+    got_logp = out.logp.cpu()
+    assert torch.equal(got_logp[hit], logp.detach()[hit])  # finfo.min / -inf, exactly
+    close(got_logp[~hit], logp.detach()[~hit], what="logp of the regular samples")
+    close(out.entropy, ent.detach(), what="entropy")
+    stats = out.stats.cpu()
+    close(stats[0], parts.loss, rtol=3e-5, what="loss")
+    close(stats[1], parts.pi_loss, rtol=3e-5, what="pi_loss")
+    close(stats[2], parts.entropy_loss, what="entropy_loss")
+    if np.isfinite(parts.approx_kl):  # one masked-chosen sample: (0 - 1) + 3.4e38, averaged
+        close(stats[3], torch.tensor(parts.approx_kl), what="approx_kl")
+    else:  # several: the reference's f32 batch sum overflows to inf; the kernel sums in f64 and stays (hugely) finite
+        assert stats[3].item() > 1e36
+    assert abs(stats[4].item() - parts.clipped_frac) <= 1.5 / B
+    close(out.grads[0], logits.grad, rtol=3e-5, what="dlogits")
+    close(out.dvalues, nv.grad, what="dvalues")
+    # the masked-chosen samples' policy gradient is exactly the entropy term alone: same as the oracle's rows
+    S = sum(nvec)
+    assert (out.grads[0].cpu()[..., :S][~inp["mask"]] == 0).all()

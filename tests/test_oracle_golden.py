@@ -124,7 +124,35 @@ def learner_setup(name):
 
 
 LEARNER_CASES_ALL = ["cartpole", "gaussian", "microrts", "lux", "microrts_teacher", "cartpole_teacher_biased",
-                     "cartpole_huber", "gaussian_l1"]
+                     "cartpole_huber", "gaussian_l1", "microrts_kl_cutoff", "cartpole_standardize", "lux_after_scaling",
+                     "lux_vf_weights", "microrts_autocast"]
+
+
+class FirstGradients:
+    """Keeps a copy of every parameter's gradient at the first clip (the reference clips first in optimizer_step,
+    ppo.py:441-443): the gradient of the first minibatch -- of the first epoch under gradient accumulation -- before
+    clipping and before Adam.  `fn` is called as the wrapped callable's replacement."""
+
+    def __init__(self, named_parameters):
+        self.named, self.grads = list(named_parameters), {}
+
+    def capture(self):
+        if not self.grads:
+            self.grads = {n: p.grad.detach().clone() for n, p in self.named if p.grad is not None}
+
+    def __enter__(self):
+        self._orig = torch.nn.utils.clip_grad_norm_
+
+        def wrapped(parameters, *a, **k):
+            self.capture()
+            return self._orig(parameters, *a, **k)
+
+        torch.nn.utils.clip_grad_norm_ = wrapped
+        return self
+
+    def __exit__(self, *exc):
+        torch.nn.utils.clip_grad_norm_ = self._orig
+        return False
 
 
 def teacher_net(case, z):
@@ -150,9 +178,12 @@ def test_oracle_learn_epoch_reproduces_the_reference(name):
     tnet = teacher_net(case, z)  # before seeding: building a module draws from the generator
     teacher = olearn.OraclePolicy(tnet, case["kind"], case["nvec"], case.get("side", 0) ** 2, case.get("gates")) if tnet else None
     torch.manual_seed(int(z["seed"]) + 100)
-    stats = olearn.learn_epoch(pol, opt, rollout_from(z), hp, teacher=teacher)
+    with FirstGradients(net.named_parameters()) as first:
+        stats = olearn.learn_epoch(pol, opt, rollout_from(z), hp, teacher=teacher)
     if teacher is not None:
         assert np.float64(stats["teacher_kl_loss"]) == z["stats.teacher_kl_loss"]
+    for k, g in first.grads.items():  # the pre-Adam gradient of the first minibatch, bit for bit
+        np.testing.assert_array_equal(g.numpy(), z[f"grad0.{k}"], err_msg=f"first gradient {k}")
     for k, v in net.state_dict().items():
         np.testing.assert_array_equal(v.numpy(), z[f"final.{k}"], err_msg=k)
     for k in ("loss", "pi_loss", "entropy_loss", "approx_kl", "clipped_frac", "grad_norm", "explained_var"):

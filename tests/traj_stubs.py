@@ -71,8 +71,10 @@ class ScriptedVecEnv:
         return self.masks[self.t % self.pool].copy()
 
     def masked_reset(self, mask):
-        k = self.t % self.pool
-        return self.obs[k][mask].copy(), self.masks[k][mask].copy(), {}
+        """Fresh episodes for the envs in `mask`: observations / masks that differ from what step() just returned
+        (another pool slot, negated), so that a generator which forgets to fold them in is caught."""
+        k = (self.t + 7) % self.pool
+        return (-self.obs[k][mask]).copy(), self.masks[k][mask].copy(), {}
 
 
 class Step(NamedTuple):
