@@ -135,7 +135,7 @@ class _GraphedUpdate:
 
     def __init__(self, algo: "PPO", batch, B: int, h: ops.PpoHyper, accumulate: bool, flat: _FlatGrads):
         self.algo, self.B, self.accumulate, self.flat = algo, B, accumulate, flat
-        self.world = _world()
+        self.world = algo._dp_world()
         dev = algo.device
         self.idx = torch.zeros(B, dtype=torch.int64, device=dev)
         self.params = flat.params
@@ -281,6 +281,9 @@ class PPO(Algorithm):
         self.flat_gradients = on_cuda  # gradients live in one flat buffer (see _FlatGrads) unless freeze_* is active
         self._flat: Optional[_FlatGrads] = None
         self._params_broadcast = False  # data-parallel replicas take rank 0's weights before the first update
+        # One process per GPU with torch.distributed initialised = data-parallel learner (envs sharded across the
+        # ranks, moments + gradients all-reduced).  False keeps this learner local to its process even then.
+        self.data_parallel = True
         self._update_graphs: Dict[tuple, "_GraphedUpdate"] = {}
         self._captures_in_a_row = 0
         self.policy = policy
@@ -365,6 +368,9 @@ class PPO(Algorithm):
                             teacher_importance=bool(self.teacher_loss_importance_sampling),
                             vf_loss=ops.VF_LOSSES[self.vf_loss_fn])
 
+    def _dp_world(self) -> int:
+        return _world() if self.data_parallel else 1
+
     def _moments_local(self, adv: torch.Tensor, h: ops.PpoHyper) -> Optional[torch.Tensor]:
         if h.adv_mode == ops.ADV_NONE:
             return None
@@ -377,7 +383,7 @@ class PPO(Algorithm):
         (shuffle=False) and every rank walks its env shard's ranges, so each local minibatch IS a reference minibatch
         and is normalised by its own statistics, as there: no collective per minibatch."""
         moments = self._moments_local(adv, h)
-        if moments is not None and _world() > 1 and not self.gradient_accumulation:
+        if moments is not None and self._dp_world() > 1 and not self.gradient_accumulation:
             dist.all_reduce(moments)
         return moments
 
@@ -617,7 +623,7 @@ class PPO(Algorithm):
 
     def _broadcast_parameters_once(self) -> None:
         """Data-parallel replicas (one process per GPU) must start from the same weights: rank 0's."""
-        if self._params_broadcast or _world() == 1:
+        if self._params_broadcast or self._dp_world() == 1:
             return
         for t in list(self.policy.parameters()) + list(self.policy.buffers()):
             dist.broadcast(t.data, 0)
@@ -626,7 +632,7 @@ class PPO(Algorithm):
     def _sync_grads(self, params: List[nn.Parameter]) -> None:
         """Data-parallel ranks (envs sharded), per-parameter path: one all-reduce of the flattened gradients, then / R,
         issued before the clip so that clipping sees the global gradient (ppo.py:441-447)."""
-        world = _world()
+        world = self._dp_world()
         if world == 1:
             return
         grads = [p.grad for p in params]
@@ -651,7 +657,7 @@ class PPO(Algorithm):
     def optimizer_step_device(self) -> torch.Tensor:
         flat = self._flat
         if flat is not None and all(p.grad is v for p, v in zip(flat.params, flat.views)):
-            world = _world()
+            world = self._dp_world()
             if world > 1:  # in place, no flatten / unflatten copies; before the clip, so clipping sees the global gradient
                 dist.all_reduce(flat.flat)
             return self._clip_and_step(flat, world)

@@ -222,3 +222,91 @@ def test_uploader_page_lock_policy(monkeypatch):
     assert calls["unregister"] == [pool.ctypes.data]
     up.close()
     assert calls["unregister"] == [pool.ctypes.data]
+
+
+def test_moving_normaliser_checkpoints_round_trip(tmp_path):
+    """ExponentialMovingMeanVar / HybridMovingMeanVar save -> load, per-env mode included: the reference writes the
+    arrays it holds (utils/running_mean_std.py:98-112) -- shape () before the first update and for vector rewards,
+    (N,) once scalar rewards went through its broadcasting update -- and load must take either."""
+    from rl_algo_impls_b200.wrappers.normalize import ExponentialMovingMeanVar, HybridMovingMeanVar, RunningMeanStd
+
+    cpu = torch.device("cpu")
+    h = HybridMovingMeanVar(cpu, window_size=5.0, shape=(), per_env=4)
+    h.emmv.mean.copy_(torch.tensor([1.0, 2.0, 3.0, 4.0], dtype=torch.float64))
+    h.emmv.var.copy_(torch.tensor([0.5, 0.25, 2.0, 1.0], dtype=torch.float64))
+    h.emmv._initialized.fill_(1)
+    h.rms.mean.fill_(0.75), h.rms.var.fill_(1.5), h.rms._count.fill_(12.0)
+    h.save(str(tmp_path / "norm_reward.npz"))
+    z = np.load(str(tmp_path / "norm_reward.npz-emmv.npz"))
+    assert z["mean"].shape == (4,) and bool(z["initialized"])  # the (N,) arrays the reference holds after an update
+    h2 = HybridMovingMeanVar(cpu, window_size=5.0, shape=(), per_env=4)
+    h2.load(str(tmp_path / "norm_reward.npz"))
+    assert torch.equal(h2.emmv.mean, h.emmv.mean) and torch.equal(h2.emmv.var, h.emmv.var) and h2.emmv.initialized
+    assert torch.equal(h2.emmv.squared_mean, h.emmv.var + h.emmv.mean ** 2)
+    assert h2.rms.count == 12.0 and torch.equal(h2.rms.mean, h.rms.mean)
+    # a file the reference wrote BEFORE its first update: shape-() arrays, not initialised
+    np.savez_compressed(str(tmp_path / "fresh.npz"), mean=np.zeros(()), var=np.ones(()), initialized=False)
+    e = ExponentialMovingMeanVar(cpu, window_size=5.0, shape=(), per_env=4)
+    e.load(str(tmp_path / "fresh.npz"))
+    assert not e.initialized and (e.var == 1).all() and e.mean.numel() == 4
+    e.save(str(tmp_path / "fresh_out.npz"))
+    assert np.load(str(tmp_path / "fresh_out.npz"))["mean"].shape == ()
+    # vector rewards: plain [V] state
+    v = ExponentialMovingMeanVar(cpu, alpha=0.1, shape=(3,))
+    v.mean.copy_(torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)), v._initialized.fill_(1)
+    v.save(str(tmp_path / "vec.npz"))
+    v2 = ExponentialMovingMeanVar(cpu, alpha=0.1, shape=(3,))
+    v2.load(str(tmp_path / "vec.npz"))
+    assert torch.equal(v2.mean, v.mean) and np.load(str(tmp_path / "vec.npz"))["mean"].shape == (3,)
+    with pytest.raises(ValueError):
+        ExponentialMovingMeanVar(cpu, alpha=0.1, shape=(2,)).load(str(tmp_path / "vec.npz"))
+    r = RunningMeanStd(cpu, shape=(3,))
+    r.mean.copy_(torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64))
+    r.save(str(tmp_path / "rms.npz"))
+    r2 = RunningMeanStd(cpu, shape=(3,))
+    r2.load(str(tmp_path / "rms.npz"))
+    assert torch.equal(r2.mean, r.mean)
+
+
+def test_optimizer_state_written_by_the_reference_loads(tmp_path):
+    """Algorithm.load (shared/algorithm.py:48-60): a reference checkpoint carries capturable=False, a Python-float
+    learning rate and CPU step counters; loading it must not rebind the learning-rate object this optimizer was built
+    with (captured update graphs read it) nor change its capturable flag, and must drop captured update graphs."""
+    env = make_synthetic_env("CartPole-v1", 2, pool=1)
+    policy = ActorCritic(env)
+    algo = PPO(policy, torch.device("cpu"), None, learning_rate=3e-4)
+    ref_opt = torch.optim.Adam(policy.parameters(), lr=7e-4, eps=1e-7)  # ppo.py:146
+    for p in policy.parameters():
+        p.grad = torch.ones_like(p)
+    ref_opt.step()
+    torch.save(ref_opt.state_dict(), tmp_path / "optimizer.pt")
+    group = algo.optimizer.param_groups[0]
+    group["lr"] = torch.tensor(3e-4)  # what PPO builds on a CUDA device: a tensor learning rate, capturable
+    group["capturable"] = True
+    lr_obj = group["lr"]
+    algo._update_graphs["stale"] = object()
+    algo.load(str(tmp_path))
+    group = algo.optimizer.param_groups[0]
+    assert group["lr"] is lr_obj and abs(float(lr_obj) - 7e-4) < 1e-9 and group["capturable"] is True
+    assert not algo._update_graphs
+    for p in policy.parameters():
+        st = algo.optimizer.state[p]
+        assert isinstance(st["step"], torch.Tensor) and st["step"].dtype == torch.float32 and float(st["step"]) == 1.0
+        assert torch.equal(st["exp_avg"], ref_opt.state[p]["exp_avg"])
+
+
+def test_reference_copy_matches_its_manifest():
+    """oracle/_ref (made by oracle/make_ref.sh, git-ignored, shipped to the GPU box) is byte-identical to the
+    reference sources the tracked manifest pins."""
+    import hashlib
+
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    root = os.path.join(here, "_ref")
+    if not os.path.isdir(root):
+        pytest.skip("oracle/_ref has not been made here (oracle/make_ref.sh)")
+    lines = open(os.path.join(here, "ref_manifest.sha256")).read().split("\n")
+    entries = [line.split(None, 1) for line in lines if line.strip()]
+    assert len(entries) > 100
+    for digest, rel in entries:
+        with open(os.path.join(root, rel.strip()), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == digest, rel
