@@ -95,6 +95,7 @@ class StubPolicy:
         self.device = torch.device(device)
         self.action_shape = (HW, A)
         self.value_shape = ()
+        self.kind = "gridnet"  # per-cell actions are uint8 on the device (rollout buffers are typed from this)
         self.training = True
 
     # control-plane no-ops the generators call
