@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200RL_VERSION 100 /* major*100 + minor */
+#define B200RL_VERSION 101 /* major*100 + minor */
 
 #define B200RL_OK 0
 #define B200RL_EINVAL (-1)
@@ -224,6 +224,9 @@ int b200rl_ppo_gaussian_loss_f32(const float* mu, const float* log_std, const fl
  *   actions [B, HW, A] (act_dtype U8/I32/I64); pick_actions [B, n_pick] (pick_dtype I32/I64)
  *   nvec_host [A]; gate_ref_host / gate_val_host [A]: head h only counts where
  *     actions[.., gate_ref[h]] == gate_val[h] (gate_ref[h] < 0: ungated)  (gridnet.py:119-127)
+ *   logits_ld: elements between the logit rows of consecutive cells, in logits AND dlogits (0 = S + n_pick, dense).
+ *     A trunk whose head emits channel-padded NHWC ([B, H, W, 80] for S = 78: the layout the convolution library
+ *     wants) passes its padded width here; columns S + n_pick .. logits_ld of dlogits are written as zeros.
  * Mask semantics are the reference's, bit for bit: masked logits become finfo.min; a row
  * with no valid entry has log-prob 0, entropy -0 and zero gradient.
  */
@@ -238,6 +241,7 @@ typedef struct b200rl_gridnet_desc {
   const int32_t* nvec_host;
   const int32_t* gate_ref_host;
   const int32_t* gate_val_host;
+  int64_t logits_ld;
 } b200rl_gridnet_desc;
 
 /* Scratch for the two-launch scheme (streaming pre-pass writes per-sample lists of the cells that
@@ -262,6 +266,21 @@ int b200rl_ppo_gridnet_loss(const b200rl_gridnet_desc* d, const void* logits, co
                             const b200rl_ppo_args* args, void* dlogits, float* logp_out /*nullable*/,
                             float* entropy_out /*nullable*/, void* workspace, size_t workspace_bytes,
                             b200rl_stream_t stream);
+/* The same launch for a dlogits buffer that PERSISTS across calls (one minibatch after another of the same shape).
+ * d loss / d logits is zero everywhere except the rows of cells with a valid action (2-6 % of a MicroRTS / Lux map), so
+ * a buffer that was correct after the previous call only needs those rows cleared before this call's rows are
+ * written: `rows` (device, b200rl_gridnet_rows_bytes(), owned by the caller together with dlogits) remembers which
+ * rows a call wrote.  rows_valid == 0: `rows` holds nothing yet -- the whole of dlogits is zero-filled as in
+ * b200rl_ppo_gridnet_loss and the written rows are recorded.  rows_valid != 0: the caller asserts that dlogits is
+ * exactly what the previous call with this `rows` left (same shape, not written since); the previous rows are
+ * cleared, this call's recorded.  dlogits traffic drops from HW * logits_ld elements per sample to the unit rows.
+ * The result is bit-identical to b200rl_ppo_gridnet_loss. */
+size_t b200rl_gridnet_rows_bytes(int64_t B, int64_t HW, int n_pick);
+int b200rl_ppo_gridnet_loss_inplace(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
+                                    const uint8_t* pick_mask, const void* actions, const void* pick_actions,
+                                    const b200rl_ppo_args* args, void* dlogits, float* logp_out /*nullable*/,
+                                    float* entropy_out /*nullable*/, void* workspace, size_t workspace_bytes,
+                                    void* rows, size_t rows_bytes, int rows_valid, b200rl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K5  rollout-time sampling: one action per head per cell (+ pick) from the masked logits and

@@ -67,6 +67,7 @@ class GridnetDesc(C.Structure):
         ("nvec_host", c_i32p),
         ("gate_ref_host", c_i32p),
         ("gate_val_host", c_i32p),
+        ("logits_ld", C.c_int64),
     ]
 
 
@@ -107,6 +108,11 @@ PROTOTYPES = {
     "b200rl_ppo_gridnet_loss": (
         _int,
         [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, C.POINTER(PpoArgs), _vp, _vp, _vp, _vp, _sz, _vp],
+    ),
+    "b200rl_gridnet_rows_bytes": (_sz, [_i64, _i64, _int]),
+    "b200rl_ppo_gridnet_loss_inplace": (
+        _int,
+        [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, C.POINTER(PpoArgs), _vp, _vp, _vp, _vp, _sz, _vp, _sz, _int, _vp],
     ),
     "b200rl_gridnet_sample": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
     "b200rl_categorical_sample_f32": (_int, [_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),

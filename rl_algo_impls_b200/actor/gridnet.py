@@ -131,7 +131,7 @@ class GridnetDistribution:
             [chunk.argmax(dim=-1) for chunk in torch.split(masked, self.action_vec.tolist(), dim=-1)], dim=-1
         )
         if self.spec.n_pick:
-            pick_logits = self.logits[..., S:].float().transpose(-1, -2)
+            pick_logits = self.logits[..., S:S + self.spec.n_pick].float().transpose(-1, -2)
             pick_logits = torch.where(self.pick_mask.bool(), pick_logits, torch.finfo(torch.float32).min)
             return {"per_position": cells, "pick_position": pick_logits.argmax(dim=-1)}
         return cells

@@ -47,6 +47,7 @@ constexpr int kStashCellsSelf = 64;  // ... in a self-streaming CTA (maps of <= 
 constexpr size_t kMaxImageBytes = 40 * 1024;  // widest chunk mask (256 cells x S bytes) staged through shared memory
 
 enum GridMode { kFwd = 0, kBwd = 1, kPpo = 2 };
+enum RowsMode { kRowsOff = 0, kRowsRecord = 1, kRowsClear = 2 };
 
 // One lane slot of a G-lane group: a piece of `len` adjacent logits of head `head`.
 struct LaneSlot {
@@ -68,6 +69,9 @@ struct GridDev {
   const void* pick_actions;
   long long B, HW;
   int A, S, Sp, n_pick;
+  int ld;            // elements between consecutive cells' rows of logits / dlogits (>= Sp; padded NHWC heads)
+  int rows_mode;     // kRowsOff: dlogits is zero-filled; kRowsRecord: ... and the written rows are recorded in the
+                     // lists; kRowsClear: the lists hold the rows of the previous call -- only those are cleared
   int act_dtype, pick_dtype;
   int gate_ref[B200RL_MAX_HEADS], gate_val[B200RL_MAX_HEADS];
   float* logp;
@@ -230,20 +234,42 @@ struct StreamStage {
   uint64_t* bar;    // mbarrier the mask image completes on (phase 0; one chunk per CTA)
 };
 
+// The rows a previous call wrote into a persistent dlogits buffer (b200rl_ppo_gridnet_loss_inplace): the unit cells of
+// this chunk's previous list get their whole row cleared, the previous pick lists their pick column.  Generic stores
+// by the whole CTA; the caller separates them from this call's gradient stores with a barrier / a grid dependency.
+template <typename LT, int BLOCK>
+__device__ __forceinline__ void clear_previous_rows(const GridDev& G, long long b, const ChunkLists& prev) {
+  LT* out = static_cast<LT*>(G.dlogits) + b * G.HW * G.ld;
+  const int n = *prev.unit_count;
+  const uint32_t Sp = (uint32_t)G.Sp;
+  for (uint32_t i = threadIdx.x; i < (uint32_t)n * Sp; i += BLOCK) {
+    const uint32_t k = i / Sp;
+    out[(long long)prev.unit[k] * G.ld + (i - k * Sp)] = from_f32<LT>(0.f);
+  }
+  for (int kp = 0; kp < G.n_pick; ++kp) {
+    const int np = prev.pick_count[kp * prev.pick_count_stride];
+    const uint16_t* pl = prev.pick + kp * prev.pick_stride;
+    for (int i = threadIdx.x; i < np; i += BLOCK) out[(long long)pl[i] * G.ld + G.S + kp] = from_f32<LT>(0.f);
+  }
+}
+
 // Returns the skew of the mask image (byte k of the chunk's mask is image[skew + k]).
+// `ZERO`: the mode writes dlogits.  With G.rows_mode == kRowsClear the rows listed in `out` (the previous call's)
+// are cleared instead of the whole chunk being filled; `out` is then overwritten with this call's lists.
 template <typename LT, bool ZERO, int BLOCK>
 __device__ __forceinline__ uint32_t stream_chunk(const GridDev& G, long long b, int chunk, uint32_t* bitmap,
-                                                 const ChunkLists& out, const StreamStage& st) {
+                                                 const ChunkLists& out, const StreamStage& st, const ChunkLists* prev = nullptr) {
   const int tid = threadIdx.x;
   const int cell0 = chunk * kChunkCells;
   const int cells = (int)min((long long)kChunkCells, G.HW - cell0);
   const long long row0 = b * G.HW + cell0;
   const uint8_t* g_mask = G.mask + row0 * G.S;
   const uint32_t mask_bytes = (uint32_t)cells * (uint32_t)G.S;
-  uint8_t* g_zero = reinterpret_cast<uint8_t*>(static_cast<LT*>(G.dlogits) + row0 * G.Sp);
-  const uint32_t zero_bytes = (uint32_t)cells * (uint32_t)G.Sp * (uint32_t)sizeof(LT);
-  const RowPrefetch pf{reinterpret_cast<const uint8_t*>(static_cast<const LT*>(G.logits) + row0 * G.Sp),
-                       (uint32_t)G.Sp * (uint32_t)sizeof(LT)};
+  uint8_t* g_zero = reinterpret_cast<uint8_t*>(static_cast<LT*>(G.dlogits) + row0 * G.ld);
+  const uint32_t zero_bytes = (uint32_t)cells * (uint32_t)G.ld * (uint32_t)sizeof(LT);
+  const RowPrefetch pf{reinterpret_cast<const uint8_t*>(static_cast<const LT*>(G.logits) + row0 * G.ld),
+                       (uint32_t)G.Sp * (uint32_t)sizeof(LT), (uint32_t)G.ld * (uint32_t)sizeof(LT)};
+  const bool fill = ZERO && G.rows_mode != kRowsClear;
   uint32_t skew = 0;
   if (st.image != nullptr) {
     // TMA path: ONE bulk copy lands the chunk's mask bytes in shared memory while bulk copies of a zeroed
@@ -263,23 +289,25 @@ __device__ __forceinline__ uint32_t stream_chunk(const GridDev& G, long long b, 
     } else if (tid >= 64 && (uint32_t)tid < 64u + tail) {
       st.image[skew + head + body + tid - 64] = g_mask[head + body + tid - 64];
     }
-    if (ZERO) {
+    if (fill) {
       for (uint32_t i = tid; i < kZeroBuf / 16u; i += BLOCK) reinterpret_cast<uint4*>(st.zeros)[i] = make_uint4(0u, 0u, 0u, 0u);
       fence_async_smem();
     }
     __syncthreads();  // barrier initialised, zero buffer and head / tail bytes in place
-    if (ZERO) zero_fill_bulk(g_zero, zero_bytes, st.zeros);
+    if (fill) zero_fill_bulk(g_zero, zero_bytes, st.zeros);
+    if (ZERO && !fill) clear_previous_rows<LT, BLOCK>(G, b, *prev);  // while the mask image is in flight
     mbar_wait(st.bar, 0);
     scan_cells_image<BLOCK>(st.image + skew, cells, (uint32_t)G.S, bitmap, pf);
   } else {
     // the mask bytes are consumed right after the zero fill: start them towards L2 first
     for (uint32_t o = (uint32_t)tid * 128u; o < mask_bytes; o += BLOCK * 128u) prefetch_l2(g_mask + o);
     if (tid < kChunkCells / 32) bitmap[tid] = 0u;
-    if (ZERO) zero_fill<BLOCK>(g_zero, zero_bytes);
+    if (fill) zero_fill<BLOCK>(g_zero, zero_bytes);
+    if (ZERO && !fill) clear_previous_rows<LT, BLOCK>(G, b, *prev);
     __syncthreads();
     scan_mask<BLOCK>(g_mask, mask_bytes, (uint32_t)G.S, bitmap, pf);
   }
-  __syncthreads();
+  __syncthreads();  // (also: every read of the previous lists above is done before `out` may alias them below)
   compact_cells(bitmap, (cells + 31) >> 5, out.unit, cell0, out.unit_count);
   // pick_position masks: one byte per cell, same compaction (no row prefetch: one logit per cell)
   for (int kp = 0; kp < G.n_pick; ++kp) {
@@ -307,9 +335,10 @@ __global__ void __launch_bounds__(kStreamBlock) gridnet_stream_kernel(const __gr
   const ChunkLists out{G.unit_list + (b * G.chunks + chunk) * kChunkCells, G.unit_count + b * G.chunks + chunk,
                        G.pick_list + ((b * G.n_pick) * G.chunks + chunk) * kChunkCells,
                        G.pick_count + (b * G.n_pick) * G.chunks + chunk, (long long)G.chunks * kChunkCells, G.chunks};
-  stream_chunk<LT, ZERO, kStreamBlock>(G, b, chunk, bitmap, out, StreamStage{G.image_bytes ? stream_smem : nullptr, zeros, &bar});
+  // in the rows modes the list workspace persists across calls: what it holds on entry are the previous call's rows
+  stream_chunk<LT, ZERO, kStreamBlock>(G, b, chunk, bitmap, out, StreamStage{G.image_bytes ? stream_smem : nullptr, zeros, &bar}, &out);
   pdl_trigger();  // the compute launch may be scheduled: it waits for this grid's completion before reading the lists
-  if (ZERO && G.image_bytes && threadIdx.x == 0) bulk_wait_read();  // the zero buffer must outlive the copies that read it
+  if (ZERO && G.rows_mode != kRowsClear && G.image_bytes && threadIdx.x == 0) bulk_wait_read();  // the zero buffer must outlive the copies that read it
 }
 
 // ---- C: compute kernel ---------------------------------------------------------------------------
@@ -352,17 +381,30 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
   float* s_ent = s_lse + (size_t)G.stash * G.A;
   uint8_t* s_image = reinterpret_cast<uint8_t*>(s_lse) + (((size_t)G.stash * G.A * 2 * sizeof(float) + 15) & ~(size_t)15);
 
-  const LT* g_logits = static_cast<const LT*>(G.logits) + row0 * G.Sp;
-  LT* g_out = static_cast<LT*>(G.dlogits) + row0 * G.Sp;
+  const LT* g_logits = static_cast<const LT*>(G.logits) + row0 * G.ld;
+  LT* g_out = static_cast<LT*>(G.dlogits) + row0 * G.ld;
   const uint8_t* g_mask = G.mask + row0 * G.S;
   __shared__ __align__(16) uint8_t s_zeros[SELF_STREAM && MODE != kFwd ? kZeroBuf : 16];
   __shared__ uint64_t s_bar;
-  if (SELF_STREAM) {  // the lists never leave the SM
+  if constexpr (SELF_STREAM) {  // the lists never leave the SM
     const ChunkLists out{s_list, s_counts, s_plist, s_counts + 1, kChunkCells, 1};
+    // the rows the previous call wrote into this (persistent) dlogits buffer, recorded in the list workspace
+    const ChunkLists prev{G.unit_list + b * kChunkCells, G.unit_count + b, G.pick_list + (b * G.n_pick) * kChunkCells,
+                          G.pick_count + b * G.n_pick, kChunkCells, 1};
     const uint32_t skew = stream_chunk<LT, MODE != kFwd, BLOCK>(G, b, 0, s_bitmap, out,
-                                                               StreamStage{G.image_bytes ? s_image : nullptr, s_zeros, &s_bar});
+                                                               StreamStage{G.image_bytes ? s_image : nullptr, s_zeros, &s_bar}, &prev);
     if (G.image_bytes) g_mask = s_image + skew;  // the unit cells re-read their mask bytes from the image
     __syncthreads();
+    if (MODE == kPpo && G.rows_mode != kRowsOff) {  // record this call's rows for the next one (the previous were read above)
+      const int n = s_counts[0];
+      for (int i = tid; i < n; i += BLOCK) prev.unit[i] = s_list[i];
+      if (tid == 0) *prev.unit_count = n;
+      for (int kp = 0; kp < n_pick; ++kp) {
+        const int np = s_counts[1 + kp];
+        for (int i = tid; i < np; i += BLOCK) prev.pick[kp * kChunkCells + i] = s_plist[kp * kChunkCells + i];
+        if (tid == 0) prev.pick_count[kp] = np;
+      }
+    }
   }
 
   // the per-sample PPO scalars are consumed by one thread after the reductions: start pulling them now; the
@@ -423,7 +465,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
     for (int j = 0; j < PMAX; ++j) p.x[j] = 0.f;
     int a_head = 0, a_ref = gate_val;
     if (live) {
-      p = load_piece<LT, PMAX>(g_logits + (long long)cell * G.Sp, g_mask + (long long)cell * G.S, slot);
+      p = load_piece<LT, PMAX>(g_logits + (long long)cell * G.ld, g_mask + (long long)cell * G.S, slot);
       const long long abase = (row0 + cell) * G.A;
       a_head = load_index(G.actions, G.act_dtype, abase + slot.head);
       if (gate_ref >= 0) a_ref = load_index(G.actions, G.act_dtype, abase + gate_ref);
@@ -466,11 +508,11 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
     const int n_valid = pl.prefix[G.chunks];
 #pragma unroll 1
     for (int i = tid; i < n_valid; i += BLOCK)
-      pick[kp] = soft_push(pick[kp], to_f32(g_logits[(long long)pl.at(i) * G.Sp + G.S + kp]));
+      pick[kp] = soft_push(pick[kp], to_f32(g_logits[(long long)pl.at(i) * G.ld + G.S + kp]));
     if (MODE != kBwd && tid == 0) {
       const long long a = (long long)load_index(G.pick_actions, G.pick_dtype, b * n_pick + kp);
       if (a >= 0 && a < G.HW)
-        pick_xa[kp] = G.pick_mask[(b * n_pick + kp) * G.HW + a] ? to_f32(g_logits[a * G.Sp + G.S + kp]) : kF32Lowest;
+        pick_xa[kp] = G.pick_mask[(b * n_pick + kp) * G.HW + a] ? to_f32(g_logits[a * G.ld + G.S + kp]) : kF32Lowest;
     }
   }
 
@@ -543,7 +585,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
   }
   if (MODE == kFwd) return;
   if (MODE == kPpo) pdl_trigger();  // the stats finaliser may be scheduled; it waits for this grid to complete
-  if (SELF_STREAM && G.image_bytes && tid == 0) {  // the zero fill of this sample's rows must have landed
+  if (SELF_STREAM && G.image_bytes && G.rows_mode != kRowsClear && tid == 0) {  // the zero fill of this sample's rows must have landed
     bulk_wait_all();
     fence_async_all();
   }
@@ -552,7 +594,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
 
   // ---- 6. backward over the unit cells: overwrite their zero-filled rows -----------------------------------
   if (k_valid)
-    piece_backward<LT, PMAX>(g_out + (long long)k_cell * G.Sp + slot.off, slot, k_valid, k_d, k_e, k_ls, k_inv, k_ent,
+    piece_backward<LT, PMAX>(g_out + (long long)k_cell * G.ld + slot.off, slot, k_valid, k_d, k_e, k_ls, k_inv, k_ent,
                              k_local, k_gated ? dlogp : 0.f, dent);
 #pragma unroll 1
   for (int i0 = n_groups; i0 < n_unit; i0 += n_groups) {  // cells beyond the first pass (uniform trip count)
@@ -563,7 +605,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
     p.valid = 0u;
 #pragma unroll
     for (int j = 0; j < PMAX; ++j) p.x[j] = 0.f;
-    if (live) p = load_piece<LT, PMAX>(g_logits + (long long)cell * G.Sp, g_mask + (long long)cell * G.S, slot);
+    if (live) p = load_piece<LT, PMAX>(g_logits + (long long)cell * G.ld, g_mask + (long long)cell * G.S, slot);
     float lse, ent;
     if (i0 + n_groups - 1 < G.stash) {  // the whole pass is in the stash (warp-uniform test)
       lse = live ? s_lse[i * G.A + slot.head] : INFINITY;
@@ -584,7 +626,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
       d[j] = v ? p.x[j] - lse : 0.f;  // log p_j directly
       e[j] = v ? fast_exp(d[j]) : 0.f;
     }
-    piece_backward<LT, PMAX>(g_out + (long long)cell * G.Sp + slot.off, slot, p.valid, d, e, 0.f, 1.f, ent, local,
+    piece_backward<LT, PMAX>(g_out + (long long)cell * G.ld + slot.off, slot, p.valid, d, e, 0.f, 1.f, ent, local,
                              gated_in ? dlogp : 0.f, dent);
   }
 #pragma unroll
@@ -599,9 +641,9 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
 #pragma unroll 1
     for (int i = tid; i < n_valid; i += BLOCK) {
       const int c = pl.at(i);
-      const float lp = to_f32(g_logits[(long long)c * G.Sp + G.S + kp]) - p_lse;
+      const float lp = to_f32(g_logits[(long long)c * G.ld + G.S + kp]) - p_lse;
       const float pr = fast_exp(lp);
-      g_out[(long long)c * G.Sp + G.S + kp] = from_f32<LT>(dlogp * ((a == c ? 1.f : 0.f) - pr) - dent * pr * (lp + p_ent));
+      g_out[(long long)c * G.ld + G.S + kp] = from_f32<LT>(dlogp * ((a == c ? 1.f : 0.f) - pr) - dent * pr * (lp + p_ent));
     }
   }
 }
@@ -684,11 +726,8 @@ static size_t compute_smem(const GridDev& G, bool self_stream) {
          (self_stream ? (size_t)G.image_bytes : 0);
 }
 
-template <int MODE, typename LT, int PMAX, bool PICK, bool SELF_STREAM>
-static int launch_compute(GridDev& G, const PpoDev& P, cudaStream_t stream) {
-  // a self-streaming CTA is mostly a streamer: 128 threads keep 8 of them per SM; the compute-only
-  // launch of the split path gets 256 threads (more lane groups per sample)
-  constexpr int BLOCK = SELF_STREAM ? 128 : 256;
+template <int MODE, typename LT, int PMAX, bool PICK, bool SELF_STREAM, int BLOCK>
+static int launch_compute_block(GridDev& G, const PpoDev& P, cudaStream_t stream) {
   auto kernel = gridnet_kernel<MODE, LT, PMAX, PICK, SELF_STREAM, BLOCK>;
   const size_t smem = compute_smem(G, SELF_STREAM);
   if (smem > 48 * 1024) {
@@ -710,6 +749,18 @@ static int launch_compute(GridDev& G, const PpoDev& P, cudaStream_t stream) {
     cudaLaunchKernelEx(&cfg, kernel, G, P);
   }
   return check_launch("gridnet");
+}
+
+template <int MODE, typename LT, int PMAX, bool PICK, bool SELF_STREAM>
+static int launch_compute(GridDev& G, const PpoDev& P, cudaStream_t stream) {
+  // a self-streaming CTA is mostly a streamer: 128 threads keep 8 of them per SM; the compute-only
+  // launch of the split path gets 256 threads (more lane groups per sample) -- and 1024 when the minibatch has fewer
+  // samples than the GPU has SMs (one C5 per-GPU minibatch: B = 128 on 148 SMs): one CTA per SM either way, so
+  // the sample's unit cells are taken in ONE pass of 128 lane groups instead of 3-4 passes of 32
+  if (SELF_STREAM) return launch_compute_block<MODE, LT, PMAX, PICK, true, 128>(G, P, stream);
+  if (MODE == kPpo && PMAX <= 8 && G.B <= device_info().sm_count)
+    return launch_compute_block<MODE, LT, PMAX, PICK, false, (MODE == kPpo && PMAX <= 8) ? 1024 : 256>(G, P, stream);
+  return launch_compute_block<MODE, LT, PMAX, PICK, false, 256>(G, P, stream);
 }
 
 template <int MODE, typename LT, int PMAX, bool PICK>
@@ -777,6 +828,11 @@ static int make_grid(const b200rl_gridnet_desc* d, const void* logits, const uin
   }
   B200RL_UNSUPPORTED(S > 65535, "%s: sum(nvec)=%d exceeds 65535", who, S);
   G.S = S, G.Sp = S + d->n_pick;
+  B200RL_REQUIRE(d->logits_ld == 0 || d->logits_ld >= G.Sp, "%s: logits_ld=%lld is narrower than a row (%d)", who,
+                 (long long)d->logits_ld, G.Sp);
+  B200RL_UNSUPPORTED(d->logits_ld > 65535, "%s: logits_ld=%lld exceeds 65535", who, (long long)d->logits_ld);
+  G.ld = d->logits_ld ? (int)d->logits_ld : G.Sp;
+  G.rows_mode = kRowsOff;
   *out = G;
   return B200RL_OK;
 }
@@ -825,27 +881,60 @@ extern "C" int b200rl_gridnet_bwd(const b200rl_gridnet_desc* d, const void* logi
   return launch_mode<kBwd>(G, P, d->nvec_host, d->logits_dtype, (cudaStream_t)stream);
 }
 
+namespace b200rl {
+// rows == nullptr: the lists live in the call's workspace and dlogits is zero-filled; otherwise they live in the
+// caller's persistent `rows` buffer and say which rows of the (persistent) dlogits the previous call wrote.
+static int ppo_gridnet_loss_impl(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
+                                 const uint8_t* pick_mask, const void* actions, const void* pick_actions,
+                                 const b200rl_ppo_args* args, void* dlogits, float* logp_out, float* entropy_out,
+                                 void* workspace, size_t workspace_bytes, void* rows, size_t rows_bytes, int rows_valid,
+                                 cudaStream_t s, const char* who) {
+  GridDev G;
+  int rc = make_grid(d, logits, mask, pick_mask, actions, pick_actions, &G, who);
+  if (rc) return rc;
+  B200RL_REQUIRE(dlogits != nullptr, "%s: dlogits is null", who);
+  // workspace = [PPO partials | GridNet lists]; b200rl_ppo_gridnet_workspace_bytes() sizes both
+  const size_t ppo_bytes = b200rl_ppo_workspace_bytes(G.B, args ? args->V : 1);
+  B200RL_REQUIRE(workspace && workspace_bytes >= ppo_bytes, "%s: workspace too small", who);
+  PpoDev P;
+  rc = ppo_make_dev(args, G.B, workspace, ppo_bytes, &P);
+  if (rc) return rc;
+  if (rows != nullptr) {
+    rc = bind_workspace(&G, rows, rows_bytes, who);
+    G.rows_mode = rows_valid ? kRowsClear : kRowsRecord;
+  } else {
+    rc = bind_workspace(&G, static_cast<uint8_t*>(workspace) + ppo_bytes, workspace_bytes - ppo_bytes, who);
+  }
+  if (rc) return rc;
+  G.dlogits = dlogits, G.logp = logp_out, G.entropy = entropy_out;
+  rc = launch_mode<kPpo>(G, P, d->nvec_host, d->logits_dtype, s);  // derives the advantage normaliser itself
+  if (rc) return rc;
+  return ppo_launch_finalize(P, G.B, 1, s);
+}
+}  // namespace b200rl
+
 extern "C" int b200rl_ppo_gridnet_loss(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
                                        const uint8_t* pick_mask, const void* actions, const void* pick_actions,
                                        const b200rl_ppo_args* args, void* dlogits, float* logp_out,
                                        float* entropy_out, void* workspace, size_t workspace_bytes,
                                        b200rl_stream_t stream) {
+  return b200rl::ppo_gridnet_loss_impl(d, logits, mask, pick_mask, actions, pick_actions, args, dlogits, logp_out,
+                                       entropy_out, workspace, workspace_bytes, nullptr, 0, 0, (cudaStream_t)stream,
+                                       "ppo_gridnet_loss");
+}
+
+extern "C" size_t b200rl_gridnet_rows_bytes(int64_t B, int64_t HW, int n_pick) {
+  return b200rl_gridnet_workspace_bytes(B, HW, n_pick);
+}
+
+extern "C" int b200rl_ppo_gridnet_loss_inplace(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
+                                               const uint8_t* pick_mask, const void* actions, const void* pick_actions,
+                                               const b200rl_ppo_args* args, void* dlogits, float* logp_out,
+                                               float* entropy_out, void* workspace, size_t workspace_bytes, void* rows,
+                                               size_t rows_bytes, int rows_valid, b200rl_stream_t stream) {
   using namespace b200rl;
-  GridDev G;
-  int rc = make_grid(d, logits, mask, pick_mask, actions, pick_actions, &G, "ppo_gridnet_loss");
-  if (rc) return rc;
-  B200RL_REQUIRE(dlogits != nullptr, "ppo_gridnet_loss: dlogits is null");
-  // workspace = [PPO partials | GridNet lists]; b200rl_ppo_gridnet_workspace_bytes() sizes both
-  const size_t ppo_bytes = b200rl_ppo_workspace_bytes(G.B, args ? args->V : 1);
-  B200RL_REQUIRE(workspace && workspace_bytes >= ppo_bytes, "ppo_gridnet_loss: workspace too small");
-  PpoDev P;
-  rc = ppo_make_dev(args, G.B, workspace, ppo_bytes, &P);
-  if (rc) return rc;
-  rc = bind_workspace(&G, static_cast<uint8_t*>(workspace) + ppo_bytes, workspace_bytes - ppo_bytes, "ppo_gridnet_loss");
-  if (rc) return rc;
-  G.dlogits = dlogits, G.logp = logp_out, G.entropy = entropy_out;
-  cudaStream_t s = (cudaStream_t)stream;
-  rc = launch_mode<kPpo>(G, P, d->nvec_host, d->logits_dtype, s);  // derives the advantage normaliser itself
-  if (rc) return rc;
-  return ppo_launch_finalize(P, G.B, 1, s);
+  B200RL_REQUIRE(rows != nullptr, "ppo_gridnet_loss_inplace: rows is null");
+  return ppo_gridnet_loss_impl(d, logits, mask, pick_mask, actions, pick_actions, args, dlogits, logp_out, entropy_out,
+                               workspace, workspace_bytes, rows, rows_bytes, rows_valid, (cudaStream_t)stream,
+                               "ppo_gridnet_loss_inplace");
 }

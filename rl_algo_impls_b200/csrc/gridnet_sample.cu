@@ -28,6 +28,7 @@ struct SampleDev {
   const uint8_t* pick_mask;
   long long B, HW;
   int A, S, Sp, n_pick;
+  int ld;  // elements between consecutive cells' logit rows (>= Sp)
   int nvec[B200RL_MAX_HEADS], off[B200RL_MAX_HEADS], gate_ref[B200RL_MAX_HEADS], gate_val[B200RL_MAX_HEADS];
   uint64_t seed, offset;
   const long long* offset_dev;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
     if (tid < kChunkCells / 32) s_bitmap[tid] = 0u;
     __syncthreads();
     scan_mask<kSampleBlock>(G.mask + (b * G.HW + c0) * G.S, (uint32_t)cells * (uint32_t)G.S, (uint32_t)G.S, s_bitmap,
-                            RowPrefetch{nullptr, 0u});
+                            RowPrefetch{nullptr, 0u, 0u});
     __syncthreads();
     compact_cells(s_bitmap, (cells + 31) >> 5, s_list + s_n, (int)c0, &s_chunk_n);
     __syncthreads();
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
   };
   auto draw_range = [&](long long cell, int h, int k_lo, int k_hi) -> Draw {  // k_lo a multiple of 4
     const int off = G.off[h];
-    const long long xbase = cell * G.Sp + off;
+    const long long xbase = cell * G.ld + off;
     const uint8_t* m = G.mask + cell * G.S + off;
     Draw d{-INFINITY, 0.f, -INFINITY, 0.f, 0};
     for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
     for (long long c = tid; c < G.HW; c += kSampleBlock) {
       if (any && !pm[c]) continue;
       const Philox4 r = philox4x32_10(G.seed, (uint64_t)(b * G.HW + c), stream_id(offset, G.A + kp, 0));
-      const float x = any ? logit_at(G, (b * G.HW + c) * G.Sp + G.S + kp) : 0.f;
+      const float x = any ? logit_at(G, (b * G.HW + c) * G.ld + G.S + kp) : 0.f;
       const float score = x + gumbel(r.x);
       if (score > best_score) best_score = score, best = c;
       mx = fmaxf(mx, x);
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
     float se = 0.f;
     if (any)
       for (long long c = tid; c < G.HW; c += kSampleBlock)
-        if (pm[c]) se += expf(logit_at(G, (b * G.HW + c) * G.Sp + G.S + kp) - mx);
+        if (pm[c]) se += expf(logit_at(G, (b * G.HW + c) * G.ld + G.S + kp) - mx);
     se = warp_sum(se);
     __syncthreads();
     if (lane == 0) s_red[warp] = se;
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
       float tot = 0.f;
       for (int w = 0; w < kSampleBlock / 32; ++w) tot += s_red[w];
       put_index(G.pick_out, G.pick_dtype, b * G.n_pick + kp, pick);
-      if (any) logp_acc += logit_at(G, (b * G.HW + pick) * G.Sp + G.S + kp) - (mx + logf(tot));
+      if (any) logp_acc += logit_at(G, (b * G.HW + pick) * G.ld + G.S + kp) - (mx + logf(tot));
     }
     __syncthreads();
   }
@@ -325,6 +326,9 @@ extern "C" int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* l
     G.gate_val[h] = (gr >= 0 && d->gate_val_host) ? d->gate_val_host[h] : 0;
   }
   G.S = S, G.Sp = S + d->n_pick;
+  B200RL_REQUIRE(d->logits_ld == 0 || d->logits_ld >= G.Sp, "gridnet_sample: logits_ld=%lld is narrower than a row (%d)",
+                 (long long)d->logits_ld, G.Sp);
+  G.ld = d->logits_ld ? (int)d->logits_ld : G.Sp;
   {  // part plan: heads in order, each cut into parts of kPartEntries entries on adjacent lanes
     int np = 0, max_count = 1;
     bool fits = true;

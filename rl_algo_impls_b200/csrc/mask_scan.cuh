@@ -51,7 +51,8 @@ __device__ __forceinline__ void zero_fill_bulk(uint8_t* dst, uint32_t bytes, con
 // Row prefetch context: the logits row of a flagged cell is wanted a few microseconds from now.
 struct RowPrefetch {
   const uint8_t* logits;  // first logit of the CTA's first cell (NULL: no prefetch)
-  uint32_t row_bytes;     // Sp * sizeof(LT)
+  uint32_t row_bytes;     // Sp * sizeof(LT): the bytes of a row that will be read
+  uint32_t stride;        // ld * sizeof(LT): bytes between consecutive cells' rows
 };
 
 // byte offset -> cell without an integer division: floor(n / S) == umulhi(n, ceil(2^32 / S)) for
@@ -64,7 +65,7 @@ __device__ __forceinline__ void flag_cell(uint32_t* bitmap, uint32_t cell, const
   const uint32_t bit = 1u << (cell & 31);
   const uint32_t old = atomicOr(&bitmap[cell >> 5], bit);
   if (!(old & bit) && pf.logits != nullptr) {  // first flag of this cell: pull its logits row towards L2
-    const uint8_t* row = pf.logits + (size_t)cell * pf.row_bytes;
+    const uint8_t* row = pf.logits + (size_t)cell * pf.stride;
     for (uint32_t o = 0; o < pf.row_bytes + 127u; o += 128u) prefetch_l2(row + min(o, pf.row_bytes - 1u));
   }
 }
@@ -160,7 +161,7 @@ __device__ __forceinline__ void scan_cells_image(const uint8_t* m, int cells, ui
     const uint32_t bits = __ballot_sync(0xffffffffu, any != 0u);
     if (lane == 0) bitmap[c >> 5] = bits;
     if (any != 0u && pf.logits != nullptr) {  // pull the unit cell's logits row towards L2
-      const uint8_t* row = pf.logits + (size_t)c * pf.row_bytes;
+      const uint8_t* row = pf.logits + (size_t)c * pf.stride;
       for (uint32_t o = 0; o < pf.row_bytes + 127u; o += 128u) prefetch_l2(row + min(o, pf.row_bytes - 1u));
     }
   }

@@ -702,11 +702,14 @@ class _GridCall:
         _cuda(logits, None, "logits")
         A, S = len(spec.nvec), sum(spec.nvec)
         Sp = S + spec.n_pick
-        if logits.shape[-1] != Sp:
-            raise ValueError(f"logits last dim {logits.shape[-1]} != sum(nvec) + n_pick = {Sp}")
+        # the last dim may be WIDER than a row of logits: a head that emits channel-padded NHWC (80 channels for
+        # S = 78) hands its tensor over as is; columns Sp.. are ignored and get zero gradient (b200rl.h logits_ld)
+        ld = logits.shape[-1]
+        if ld < Sp:
+            raise ValueError(f"logits last dim {ld} < sum(nvec) + n_pick = {Sp}")
         B = logits.shape[0]
-        HW = logits.numel() // (B * Sp) if B else 0
-        self.B, self.HW, self.A, self.S, self.Sp = B, HW, A, S, Sp
+        HW = logits.numel() // (B * ld) if B else 0
+        self.B, self.HW, self.A, self.S, self.Sp, self.ld = B, HW, A, S, Sp, ld
         self.mask = _as_u8(mask, "mask")
         if self.mask.numel() != B * HW * S:
             raise ValueError(f"mask has {self.mask.numel()} elements, expected {B * HW * S}")
@@ -731,6 +734,7 @@ class _GridCall:
         d.act_dtype = _INDEX_DTYPES[actions.dtype] if actions is not None else _lib.U8
         d.pick_dtype = _INDEX_DTYPES[pick_actions.dtype] if pick_actions is not None else _lib.I64
         d.nvec_host, d.gate_ref_host, d.gate_val_host = self._nvec, self._gref, self._gval
+        d.logits_ld = 0 if ld == Sp else ld
         self.desc = d
 
 
@@ -782,6 +786,27 @@ def gridnet_logp_entropy(spec, logits, mask, pick_mask, actions, pick_actions):
     return _GridnetFn.apply(logits, spec, mask, pick_mask, actions, pick_actions)
 
 
+class _PersistentGrad:
+    """A d loss / d logits buffer that outlives the call, plus the record of the rows the last call wrote into it
+    (b200rl_ppo_gridnet_loss_inplace): the next call of the same shape clears those rows instead of zero-filling the
+    tensor.  One per (device, shape, dtype, head layout); allocated on first use, outside any CUDA-graph pool when the
+    first use is a warm-up run, so eager calls and captured replays share it and all keep its invariant."""
+
+    def __init__(self, logits: torch.Tensor, rows_bytes: int):
+        self.dlogits = torch.empty_like(logits)
+        self.rows = torch.empty(rows_bytes, dtype=torch.uint8, device=logits.device)
+        self.valid = False
+
+
+_persistent_grads: Dict[tuple, _PersistentGrad] = {}
+
+
+def clear_caches() -> None:
+    """Drop the persistent gradient buffers and per-stream workspaces (they are re-created on demand)."""
+    _persistent_grads.clear()
+    _workspaces.clear()
+
+
 def ppo_gridnet_loss(
     h: PpoHyper,
     spec: GridnetSpec,
@@ -798,17 +823,39 @@ def ppo_gridnet_loss(
     moments: Optional[torch.Tensor] = None,
     want_logp: bool = False,
     teacher_logp: Optional[torch.Tensor] = None,
+    inplace: bool = False,
 ) -> LossOut:
-    """One launch: masked log-prob/entropy forward, PPO loss, backward into dlogits / dvalues."""
+    """One launch: masked log-prob/entropy forward, PPO loss, backward into dlogits / dvalues.
+
+    ``inplace``: the returned ``grads[0]`` is a buffer this module keeps across calls of the same shape and is only
+    valid until the next such call (the learner consumes it in the trunk's backward right away).  The gradient is zero
+    outside the rows of cells with a valid action, so the kernel then clears just the rows the previous call wrote
+    instead of zero-filling the whole tensor -- same bits, a fraction of the HBM traffic."""
     g = _GridCall(spec, logits, mask, pick_mask, actions, pick_actions)
     V = new_values.numel() // max(g.B, 1)
+    L = _lib.lib()
     call = PpoCall(h, old_logp, adv, old_values, returns, new_values, moments,
-                   workspace_bytes=_lib.lib().b200rl_ppo_gridnet_workspace_bytes(g.B, g.HW, spec.n_pick, V),
+                   workspace_bytes=L.b200rl_ppo_gridnet_workspace_bytes(g.B, g.HW, spec.n_pick, V),
                    teacher_logp=teacher_logp)
-    dlogits = torch.empty_like(logits)
     logp = torch.empty(g.B, dtype=torch.float32, device=logits.device) if want_logp else None
     ent = torch.empty(g.B, dtype=torch.float32, device=logits.device) if want_logp else None
-    rc = _call("b200rl_ppo_gridnet_loss", 4, _lib.lib().b200rl_ppo_gridnet_loss,
+    if inplace and g.B > 0:
+        dev = logits.device.index if logits.device.index is not None else torch.cuda.current_device()
+        key = (dev, tuple(logits.shape), logits.dtype, spec.nvec, spec.n_pick)
+        st = _persistent_grads.get(key)
+        if st is None:
+            st = _persistent_grads[key] = _PersistentGrad(logits, L.b200rl_gridnet_rows_bytes(g.B, g.HW, spec.n_pick))
+        valid, st.valid = st.valid, False  # a failed launch leaves the buffer's state unknown
+        rc = _call("b200rl_ppo_gridnet_loss", 4, L.b200rl_ppo_gridnet_loss_inplace,
+            C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), actions.data_ptr(),
+            _ptr(pick_actions), C.byref(call.args), st.dlogits.data_ptr(), _ptr(logp), _ptr(ent),
+            call.workspace.data_ptr(), call.workspace.numel(), st.rows.data_ptr(), st.rows.numel(), int(valid), _stream(),
+        )  # fmt: skip
+        check(rc, "b200rl_ppo_gridnet_loss_inplace")
+        st.valid = True
+        return LossOut(call.stats, call.dvalues, (st.dlogits,), logp, ent)
+    dlogits = torch.empty_like(logits)
+    rc = _call("b200rl_ppo_gridnet_loss", 4, L.b200rl_ppo_gridnet_loss,
         C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), actions.data_ptr(),
         _ptr(pick_actions), C.byref(call.args), dlogits.data_ptr(), _ptr(logp), _ptr(ent),
         call.workspace.data_ptr(), call.workspace.numel(), _stream(),

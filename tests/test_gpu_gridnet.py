@@ -324,3 +324,95 @@ def test_fused_with_masked_chosen_actions(cuda, nvec, gates, n_pick, HW, p):
     # the masked-chosen samples' policy gradient is exactly the entropy term alone: same as the oracle's rows
     S = sum(nvec)
     assert (out.grads[0].cpu()[..., :S][~inp["mask"]] == 0).all()
+
+
+def _pad_rows(logits: torch.Tensor, ld: int) -> torch.Tensor:
+    """[B, HW, Sp] -> [B, HW, ld] with NaN in the pad columns: a kernel that read them would poison its sums."""
+    out = torch.full(logits.shape[:-1] + (ld,), float("nan"), dtype=logits.dtype, device=logits.device)
+    out[..., :logits.shape[-1]] = logits
+    return out
+
+
+@pytest.mark.parametrize("nvec,gates,n_pick,HW,ld", [(MICRORTS_NVEC, MICRORTS_GATES, 0, 256, 80), (LUX_NVEC, LUX_GATES, 1, 4096, 32),
+                                                     ((3, 5), None, 1, 100, 16)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_channel_padded_logit_rows(cuda, nvec, gates, n_pick, HW, ld, dtype):
+    """logits_ld (b200rl.h): a head that emits channel-padded NHWC rows (80 wide for S = 78, 32 for S' = 29) hands
+    them over as they are.  Forward, fused loss, backward and sampling give exactly the dense-row results; the pad
+    columns (NaN on input here) are never read and come back as zero gradient."""
+    from rl_algo_impls_b200 import ops
+
+    B, V = 9, 1
+    inp = to_torch(gridnet_inputs(3 + HW, B, HW, nvec, n_pick, 0.06), cuda)
+    pp = to_torch(ppo_inputs(4, B, V), cuda)
+    spec = spec_of(nvec, gates, n_pick)
+    dense = inp["logits"].to(dtype)
+    padded = _pad_rows(dense, ld)
+    Sp = dense.shape[-1]
+    lp0, en0 = ops.gridnet_fwd(spec, dense, inp["mask"], inp["pick_mask"], inp["actions"], inp["pick_actions"])
+    lp1, en1 = ops.gridnet_fwd(spec, padded, inp["mask"], inp["pick_mask"], inp["actions"], inp["pick_actions"])
+    assert torch.equal(lp0, lp1) and torch.equal(en0, en1)
+    old_logp = lp0 + pp["old_logp_noise"]
+    h = ops.PpoHyper(clip_range=0.1, clip_range_vf=0.1, ent_coef=0.01, vf_coef=[0.5], vf_halving=True)
+    args = (inp["mask"], inp["pick_mask"], inp["actions"], inp["pick_actions"], old_logp, pp["adv"], pp["old_values"],
+            pp["returns"], pp["new_values"])
+    o0 = ops.ppo_gridnet_loss(h, spec, dense, *args)
+    o1 = ops.ppo_gridnet_loss(h, spec, padded, *args)
+    assert torch.equal(o0.stats, o1.stats) and torch.equal(o0.dvalues, o1.dvalues)
+    assert torch.equal(o1.grads[0][..., :Sp], o0.grads[0]) and (o1.grads[0][..., Sp:] == 0).all()
+    dl, de = torch.randn(B, device=cuda), torch.randn(B, device=cuda)
+    g0 = ops.gridnet_bwd(spec, dense, inp["mask"], inp["pick_mask"], inp["actions"], inp["pick_actions"], dl, de)
+    g1 = ops.gridnet_bwd(spec, padded, inp["mask"], inp["pick_mask"], inp["actions"], inp["pick_actions"], dl, de)
+    assert torch.equal(g1[..., :Sp], g0) and (g1[..., Sp:] == 0).all()
+    a0, p0, s0 = ops.gridnet_sample(spec, dense, inp["mask"], inp["pick_mask"], 77, 5)
+    a1, p1, s1 = ops.gridnet_sample(spec, padded, inp["mask"], inp["pick_mask"], 77, 5)
+    assert torch.equal(a0, a1) and torch.equal(s0, s1) and (p0 is None or torch.equal(p0, p1))
+
+
+@pytest.mark.parametrize("nvec,gates,n_pick,HW,ld,B", [(MICRORTS_NVEC, MICRORTS_GATES, 0, 256, 0, 64),
+                                                       (MICRORTS_NVEC, MICRORTS_GATES, 0, 256, 80, 300),
+                                                       (LUX_NVEC, LUX_GATES, 1, 4096, 0, 20),
+                                                       (LUX_NVEC, LUX_GATES, 1, 4096, 32, 160),
+                                                       ((3, 5), None, 1, 100, 0, 33)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_persistent_gradient_buffer_equals_fresh_buffers(cuda, nvec, gates, n_pick, HW, ld, B, dtype):
+    """b200rl_ppo_gridnet_loss_inplace: over a sequence of minibatches of one shape whose unit cells move around
+    (dense, sparse, empty, dense again), the buffer that only has its previously written rows cleared holds, after
+    every call, bit for bit what a freshly zero-filled one holds -- inside a captured graph too."""
+    from rl_algo_impls_b200 import ops
+
+    ops.clear_caches()
+    spec = spec_of(nvec, gates, n_pick)
+    h = ops.PpoHyper(clip_range=0.1, clip_range_vf=None, ent_coef=0.01, vf_coef=[0.5])
+    static = None
+    graph = None
+    for step, unit_p in enumerate([0.3, 0.02, 0.0, 0.5, 0.06, 0.06, 0.9, 0.01]):
+        inp = to_torch(gridnet_inputs(100 + step, B, HW, nvec, n_pick, unit_p), cuda)
+        pp = to_torch(ppo_inputs(step, B, 1), cuda)
+        logits = inp["logits"].to(dtype)
+        if ld:
+            logits = _pad_rows(logits, ld)
+        old_logp = torch.full((B,), -30.0, device=cuda) + pp["old_logp_noise"]
+        tensors = [logits, inp["mask"], inp["pick_mask"], inp["actions"], inp["pick_actions"], old_logp, pp["adv"],
+                   pp["old_values"], pp["returns"], pp["new_values"]]
+        fresh = ops.ppo_gridnet_loss(h, spec, *tensors)
+        if step < 4:  # eager calls
+            got = ops.ppo_gridnet_loss(h, spec, *tensors, inplace=True)
+        else:  # the same buffer, driven by replays of ONE captured launch over static inputs
+            if static is None:
+                static = [t.clone() if t is not None else None for t in tensors]
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    ops.ppo_gridnet_loss(h, spec, *static, inplace=True)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    got = ops.ppo_gridnet_loss(h, spec, *static, inplace=True)
+            for s_t, t in zip(static, tensors):
+                if s_t is not None:
+                    s_t.copy_(t)
+            graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(got.grads[0], fresh.grads[0]), f"call {step} (unit density {unit_p})"
+        assert torch.equal(got.stats, fresh.stats) and torch.equal(got.dvalues, fresh.dvalues)
