@@ -137,6 +137,17 @@ class ActorCritic(nn.Module):
     def head_outputs(self, obs: torch.Tensor) -> HeadOutputs:
         return self.network(obs)
 
+    @property
+    def packed_obs_shape(self):
+        """Shape of one observation in the layout the trunk consumes without a copy ((H, W, Cp): channels last, planes
+        padded to a multiple of 8), or None when the trunk takes the env's layout as is.  A rollout generator that
+        stores observations packed hands the learner trunk-ready minibatch rows (networks._PaddedEnds)."""
+        fn = getattr(self.network, "packed_obs_shape", None)
+        return fn() if fn is not None else None
+
+    def pack_observations(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.network.pack_observations(obs, out)
+
     def _grid_logits(self, out: HeadOutputs) -> torch.Tensor:
         lg = out.pi
         return lg.reshape(lg.shape[0], self.map_size, lg.shape[-1])
@@ -280,7 +291,7 @@ def default_network(env, policy: ActorCritic, pi_hidden_sizes=None, v_hidden_siz
                 decoder_residual_blocks_per_level=decoder_residual_blocks_per_level, critic_channels=critic_channels,
                 critic_activations=[output_activation_fn] + extra, shared_critic_head=shared_critic_head,
                 increment_kernel_size_on_down_conv=increment_kernel_size_on_down_conv,
-                obs_range=obs_range if np.isfinite(obs_range) and obs_range > 0 else 1.0)
+                obs_range=obs_range if np.isfinite(obs_range) and obs_range > 0 else 1.0, obs_hw=tuple(obs_shape[1:]))
         if actor_head_style in ("unet", "double_cone", "sacus"):
             raise NotImplementedError(f"actor_head_style={actor_head_style!r}: pass the trunk module as network=")
         return GridEncoderDecoderActorCritic(obs_shape[0], (side, side), n_logits, tuple(v_hidden_sizes or (128,)),

@@ -13,6 +13,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 _ACTIVATIONS = {"tanh": nn.Tanh, "relu": nn.ReLU, "gelu": nn.GELU, "identity": nn.Identity}
 
@@ -87,9 +88,101 @@ class NatureCnnActorCritic(nn.Module):
         return HeadOutputs(self.pi(x), self.v(x).squeeze(-1))
 
 
-class GridEncoderDecoderActorCritic(nn.Module):
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class _PaddedEnds(nn.Module):
+    """Channel padding at the two ends of a grid trunk, so that the convolution library never has to repair a layout.
+
+    cuDNN's NHWC tensor-op kernels want channel counts that are multiples of 8 (16 bytes of bf16, 32 of f32); with 74 /
+    75 observation planes and 78 / 29 logit planes it pads both tensors itself, on every call (`nhwcAddPaddingKernel`,
+    `nchwToFoldedNhwcKernel`: 11 % of a C4 step's GPU time in round 1).  Here the padding is part of the data layout:
+
+    * observations arrive PACKED -- [B, H, W, Cp] with the planes beyond C zero (``pack_observations``; the rollout
+      buffer stores them like this, so the minibatch gather hands over trunk-ready rows) -- and the first convolution
+      runs on its weight zero-padded to Cp input channels;
+    * the head that emits the logits runs on its weight / bias zero-padded to Lp output channels, so the logits are
+      physically [B, H, W, Lp]: rows of 80 (32) elements, 16-byte aligned, handed to the loss kernels as they are
+      (b200rl.h ``logits_ld``); columns L.. are exact zeros forward and receive zero gradient.
+
+    Both paddings are mathematically inert (zero weights meet zero inputs / produce zero outputs) and leave the
+    parameters, their count and the state dict untouched.  During a no-grad evaluation pass (the rollout) the padded
+    weights come from buffers refreshed when the module enters eval mode; with gradients on they are padded on the fly."""
+
+    def _init_padding(self, in_channels: int, n_logits: int, obs_hw: Tuple[int, int], first: nn.Module, head: nn.Module) -> None:
+        self.in_channels, self.n_logits, self.obs_hw = int(in_channels), int(n_logits), (int(obs_hw[0]), int(obs_hw[1]))
+        self.cin_pad, self.logit_pad = _pad8(in_channels), _pad8(n_logits)
+        self._first, self._head = [first], [head]  # lists: not registered twice as submodules
+        self.register_buffer("_first_w", None, persistent=False)
+        self.register_buffer("_head_w", None, persistent=False)
+        self.register_buffer("_head_b", None, persistent=False)
+        self._pad_versions = None
+
+    def _padded_now(self):
+        first, head = self._first[0], self._head[0]
+        w0 = F.pad(first.weight, (0, 0, 0, 0, 0, self.cin_pad - self.in_channels))       # [out, in -> Cp, k, k]
+        if isinstance(head, nn.ConvTranspose2d):
+            wh = F.pad(head.weight, (0, 0, 0, 0, 0, self.logit_pad - self.n_logits))      # [in, out -> Lp, k, k]
+        else:
+            wh = F.pad(head.weight, (0, 0, 0, 0, 0, 0, 0, self.logit_pad - self.n_logits))  # [out -> Lp, in, k, k]
+        bh = F.pad(head.bias, (0, self.logit_pad - self.n_logits))
+        return (w0.contiguous(memory_format=torch.channels_last), wh.contiguous(memory_format=torch.channels_last), bh)
+
+    def _versions(self):
+        first, head = self._first[0], self._head[0]
+        return (first.weight._version, head.weight._version, head.bias._version, first.weight.data_ptr(), head.weight.data_ptr())
+
+    @torch.no_grad()
+    def refresh_padded_weights(self) -> None:
+        w0, wh, bh = self._padded_now()
+        if self._first_w is None or self._first_w.shape != w0.shape or self._first_w.device != w0.device:
+            self._first_w, self._head_w, self._head_b = w0.clone(), wh.clone(), bh.clone()
+        else:  # in place: a captured rollout step keeps reading the same addresses
+            self._first_w.copy_(w0), self._head_w.copy_(wh), self._head_b.copy_(bh)
+        self._pad_versions = self._versions()
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        if not mode and self._first[0].weight.is_cuda:
+            self.refresh_padded_weights()
+        return self
+
+    def _padded_weights(self):
+        if self.training or torch.is_grad_enabled():
+            return self._padded_now()
+        if self._first_w is None or self._pad_versions != self._versions():
+            self.refresh_padded_weights()
+        return self._first_w, self._head_w, self._head_b
+
+    def packed_obs_shape(self) -> Optional[Tuple[int, int, int]]:
+        """(H, W, Cp), the shape of one packed observation; None when it could not be told from a raw (C, H, W) one."""
+        H, W = self.obs_hw
+        packed = (H, W, self.cin_pad)
+        return None if packed == (self.in_channels, H, W) else packed
+
+    def pack_observations(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[B, C, H, W] (any real dtype) -> [B, H, W, Cp] float32, planes C.. zero.  `out` (already zero beyond C) is
+        written in place."""
+        B, C, H, W = obs.shape
+        if out is None:
+            out = torch.zeros((B, H, W, self.cin_pad), dtype=torch.float32, device=obs.device)
+        out[..., :C].copy_(obs.permute(0, 2, 3, 1))
+        return out
+
+    def _packed_input(self, obs: torch.Tensor) -> torch.Tensor:
+        """The trunk's input as a channels-last [B, Cp, H, W] view, from packed or raw observations."""
+        packed_shape = self.packed_obs_shape()
+        if packed_shape is not None and tuple(obs.shape[1:]) == packed_shape:
+            packed = obs if obs.dtype == torch.float32 else obs.float()
+        else:
+            packed = self.pack_observations(obs)
+        return packed.permute(0, 3, 1, 2)
+
+
+class GridEncoderDecoderActorCritic(_PaddedEnds):
     """MicroRTS GridNet: 4 x (conv3x3 + maxpool/2) encoder, 4 x transposed-conv decoder emitting
-    [B, H, W, S] logits, and an MLP critic on the encoded map."""
+    [B, H, W, S] logits (physically [B, H, W, pad8(S)], see _PaddedEnds), and an MLP critic on the encoded map."""
 
     def __init__(self, in_channels: int, map_hw: Tuple[int, int], n_logits: int, v_hidden=(128,), n_values: int = 1):
         super().__init__()
@@ -113,13 +206,17 @@ class GridEncoderDecoderActorCritic(nn.Module):
         self.n_values = n_values
         self.policy_head_modules, self.value_head_modules = ["decoder"], ["critic"]  # freeze_* (backbone_actor_critic.py:254-265)
         # NHWC in memory: cuDNN's native layout on sm_100 (no nchw<->nhwc transposes around every conv),
-        # and the decoder output is then physically [B, H, W, S] -- the layout the fused loss kernel
+        # and the decoder output is then physically [B, H, W, pad8(S)] -- the layout the fused loss kernel
         # reads and writes -- so permute(0, 2, 3, 1) is a free view instead of a 245 MB copy per minibatch.
         self.to(memory_format=torch.channels_last)
+        self._init_padding(in_channels, n_logits, map_hw, self.encoder[0], self.decoder[-1])
 
     def forward(self, obs: torch.Tensor) -> HeadOutputs:
-        z = self.encoder(obs.float().contiguous(memory_format=torch.channels_last))
-        logits = self.decoder(z).permute(0, 2, 3, 1)  # [B, H, W, S]
+        w0, wh, bh = self._padded_weights()
+        x = F.conv2d(self._packed_input(obs), w0, self.encoder[0].bias, padding=1)
+        z = self.encoder[1:](x)
+        y = self.decoder[:-1](z)
+        logits = F.conv_transpose2d(y, wh, bh, stride=2, padding=1, output_padding=1).permute(0, 2, 3, 1)  # [B, H, W, Lp]
         v = self.critic(z)
         return HeadOutputs(logits, v.squeeze(-1) if self.n_values == 1 else v)
 
@@ -152,7 +249,7 @@ def _stride_list(s) -> List[int]:
     return [int(v) for v in s] if isinstance(s, (list, tuple)) else [int(s)]
 
 
-class SqueezeUnetActorCritic(nn.Module):
+class SqueezeUnetActorCritic(_PaddedEnds):
     """The Lux / MicroRTS "squeeze U-net" (actor_critic_network/squeeze_unet.py:20-196 backbone +
     backbone_actor_critic.py:94-187 heads), same layer list and therefore the same parameter count (4,719,274 at the
     Lux 64x64 YAML entry): a 3x3 stem and SE-residual blocks per level, strided convs down (kernel = stride), chains of
@@ -164,7 +261,8 @@ class SqueezeUnetActorCritic(nn.Module):
                  deconv_strides_per_level=None, encoder_residual_blocks_per_level=None,
                  decoder_residual_blocks_per_level=None, critic_channels: int = 64,
                  critic_activations: Sequence[str] = ("identity",), shared_critic_head: bool = False,
-                 increment_kernel_size_on_down_conv: bool = False, obs_range: float = 1.0):
+                 increment_kernel_size_on_down_conv: bool = False, obs_range: float = 1.0,
+                 obs_hw: Tuple[int, int] = (0, 0)):
         super().__init__()
         ch = [int(c) for c in channels_per_level]
         L = len(ch)
@@ -222,6 +320,7 @@ class SqueezeUnetActorCritic(nn.Module):
         self.critics = nn.ModuleList([critic(self.n_values)] if shared_critic_head else [critic(1) for _ in range(self.n_values)])
         self.policy_head_modules, self.value_head_modules = ["actor"], ["critics"]  # freeze_* (backbone_actor_critic.py:254-265)
         self.to(memory_format=torch.channels_last)  # see GridEncoderDecoderActorCritic
+        self._init_padding(in_channels, n_logits, obs_hw, self.encoders[0][0], self.actor)
 
     def _values(self, x: torch.Tensor) -> torch.Tensor:
         v = self.critics[0](x) if self.shared_critic_head else torch.cat([c(x) for c in self.critics], dim=1)
@@ -230,17 +329,20 @@ class SqueezeUnetActorCritic(nn.Module):
         return v.squeeze(-1) if self.n_values == 1 else v
 
     def forward(self, obs: torch.Tensor) -> HeadOutputs:
-        x = obs.float().contiguous(memory_format=torch.channels_last)
+        w0, wh, bh = self._padded_weights()
+        x = self._packed_input(obs)
         if self.obs_range != 1.0:
             x = x / self.obs_range  # backbone_actor_critic.py:189-192
-        skips = []
-        for enc in self.encoders:
+        stem = self.encoders[0]
+        x = stem[1:](F.conv2d(x, w0, stem[0].bias, padding=1))
+        skips = [x]
+        for enc in list(self.encoders)[1:]:
             x = enc(x)
             skips.append(x)
         x = self.decoders[0](skips[-1])
         for skip, dec in zip(reversed(skips[:-1]), list(self.decoders)[1:]):
             x = dec(skip + x)
-        logits = self.actor(x).permute(0, 2, 3, 1)  # [B, H, W, S']
+        logits = F.conv2d(x, wh, bh, padding=1).permute(0, 2, 3, 1)  # [B, H, W, Lp]
         return HeadOutputs(logits, self._values(x))
 
 

@@ -278,6 +278,7 @@ class PPO(Algorithm):
         super().__init__(policy, device, tb_writer, learning_rate,
                          Adam(policy.parameters(), lr=lr, eps=1e-7, capturable=on_cuda))
         self.cuda_graph_update = on_cuda  # replay the minibatch update from CUDA graphs when possible
+        self.persistent_dlogits = True  # the fused GridNet loss keeps its dlogits buffer across minibatches (ops.ppo_gridnet_loss)
         self.flat_gradients = on_cuda  # gradients live in one flat buffer (see _FlatGrads) unless freeze_* is active
         self._flat: Optional[_FlatGrads] = None
         self._params_broadcast = False  # data-parallel replicas take rank 0's weights before the first update
@@ -421,8 +422,11 @@ class PPO(Algorithm):
                 logits = logits.reshape(B, policy.map_size, logits.shape[-1])
                 if not logits.is_contiguous():
                     logits = logits.contiguous()
+                # inplace: d loss / d logits lives in a buffer kept across minibatches -- only the rows the previous
+                # minibatch wrote are cleared (the gradient is zero outside the unit cells); consumed right below
                 res = ops.ppo_gridnet_loss(h, policy.spec, logits, cmask, pmask, cells, pick, old_logp, adv,
-                                           old_values, returns, v32, moments=moments, teacher_logp=teacher_logp)
+                                           old_values, returns, v32, moments=moments, teacher_logp=teacher_logp,
+                                           inplace=self.persistent_dlogits)
                 grads = [res.grads[0].reshape(out.pi.shape)]
                 roots = [out.pi]
             elif kind == "categorical":

@@ -175,7 +175,15 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         obs_space = vec_env.single_observation_space
         value_shape = tuple(policy.value_shape)
         act_shape = policy.action_shape
-        self.obs = torch.zeros((T, N) + tuple(obs_space.shape), dtype=_torch_dtype(obs_space.dtype), device=dev)
+        # Observations are stored in the layout the trunk consumes without a copy when the policy names one
+        # (ActorCritic.packed_obs_shape: channels last, planes padded to a multiple of 8): packed once per env step,
+        # so that the minibatch gather hands the learner trunk-ready rows.  Otherwise the env's own layout / dtype.
+        self._packed = getattr(policy, "packed_obs_shape", None) if len(tuple(obs_space.shape)) == 3 else None
+        obs_shape = tuple(self._packed) if self._packed else tuple(obs_space.shape)
+        obs_dtype = torch.float32 if self._packed else _torch_dtype(obs_space.dtype)
+        self._raw_obs = (torch.zeros((N,) + tuple(obs_space.shape), dtype=_torch_dtype(obs_space.dtype), device=dev)
+                         if self._packed else None)  # landing zone of a host env's upload, packed from there
+        self.obs = torch.zeros((T, N) + obs_shape, dtype=obs_dtype, device=dev)
         self.rewards = torch.zeros((T, N) + value_shape, dtype=torch.float32, device=dev)
         self.episode_starts = torch.zeros((T, N), dtype=torch.bool, device=dev)
         self.values = torch.zeros((T, N) + value_shape, dtype=torch.float32, device=dev)
@@ -184,7 +192,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         self.advantages = torch.zeros((T, N) + value_shape, dtype=torch.float32, device=dev)
         self.returns = torch.zeros((T, N) + value_shape, dtype=torch.float32, device=dev)
         self.next_episode_starts = torch.ones((N,), dtype=torch.bool, device=dev)
-        self.next_obs = torch.zeros((N,) + tuple(obs_space.shape), dtype=self.obs.dtype, device=dev)
+        self.next_obs = torch.zeros((N,) + obs_shape, dtype=self.obs.dtype, device=dev)
 
         kind = getattr(policy, "kind", None)
         if isinstance(act_shape, dict):
@@ -197,7 +205,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
             self.actions = torch.zeros((T, N) + tuple(act_shape), dtype=adt, device=dev)
 
         first_obs, _ = vec_env.reset()
-        self._upload("obs", first_obs, self.next_obs)
+        self._set_next_obs(first_obs)
         self.action_masks = None
         self.next_action_masks = None
         if self.get_action_mask is not None:
@@ -212,6 +220,17 @@ class SyncStepRolloutGenerator(RolloutGenerator):
                 self._upload_masks(m)
 
     # -- helpers -------------------------------------------------------------------------------
+    def _set_next_obs(self, obs) -> None:
+        """The env's observation for the next step -> self.next_obs (uploaded if it is a host array, packed into the
+        trunk's layout if the policy names one)."""
+        if not self._packed:
+            self._upload("obs", obs, self.next_obs)
+            return
+        if not isinstance(obs, torch.Tensor):
+            self._upload("obs", obs, self._raw_obs)
+            obs = self._raw_obs
+        self.policy.pack_observations(obs, out=self.next_obs)
+
     def _upload_masks(self, m) -> None:
         if isinstance(m, dict):
             for k, v in m.items():
@@ -310,7 +329,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
             carry.update({id(cur): new for cur, new in pairs if fits(new, cur)})
         ops.rollout_store_step(src, dst, self.step_count, carry=[carry.get(id(t)) for t in src])
         if id(self.next_obs) not in carry:
-            self.next_obs.copy_(next_obs)
+            self._set_next_obs(next_obs)
         torch.logical_or(terminations, truncations, out=self.next_episode_starts)
         if masks is not None:
             for cur, new in pairs:
@@ -383,7 +402,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
                     a = self._policy_step()
                     self.step_count.add_(1)
             next_obs, rewards, terminations, truncations, _ = self.vec_env.step(self._env_actions(a, landed=True))
-            self._upload("obs", next_obs, self.next_obs)
+            self._set_next_obs(next_obs)
             if self.get_action_mask is not None and self.next_action_masks is not None:
                 self._upload_masks(self.get_action_mask())
             host_rewards[s] = np.asarray(rewards, dtype=np.float32).reshape(host_rewards.shape[1:])
@@ -454,7 +473,8 @@ class SyncStepRolloutGenerator(RolloutGenerator):
             return
         next_obs, action_mask, _ = self.vec_env.masked_reset(reset)
         rows = torch.from_numpy(np.nonzero(reset)[0]).to(self.device)
-        self.next_obs[rows] = torch.as_tensor(next_obs).to(self.device, dtype=self.next_obs.dtype)
+        fresh = torch.as_tensor(next_obs).to(self.device)
+        self.next_obs[rows] = self.policy.pack_observations(fresh) if self._packed else fresh.to(self.next_obs.dtype)
         if self.next_action_masks is not None and action_mask is not None:
             if isinstance(self.next_action_masks, dict):
                 for k, dst in self.next_action_masks.items():

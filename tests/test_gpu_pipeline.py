@@ -145,7 +145,7 @@ def test_graph_replayed_rollout_equals_eager(cuda, cfg):
         if graph:  # capture (which steps the env a few times), then put env + carry-over back to the start
             gen._rollout(output_next_values=False)
             env.reset()
-            gen.next_obs.copy_(env.reset()[0])
+            gen._set_next_obs(env.reset()[0])
             gen.next_episode_starts.fill_(True)
             if gen.next_action_masks is not None:
                 gen._upload_masks(env.get_action_mask())
@@ -218,3 +218,43 @@ def test_freeze_flags_keep_the_frozen_group_fixed(cuda, cfg, frozen):
     moved = {n for n, p in policy.named_parameters() if (p.detach() != before[n]).any().item()}
     assert moved and not (moved & fixed), f"frozen parameters moved: {sorted(moved & fixed)}"
     assert all(p.requires_grad for p in policy.parameters())
+
+
+@pytest.mark.parametrize("cfg", ["C4", "C5"])
+def test_packed_observation_layout_changes_no_number(cuda, cfg):
+    """The rollout buffer stores observations in the trunk's layout (channels last, planes padded to a multiple of 8:
+    ActorCritic.packed_obs_shape) so that the gather hands over trunk-ready rows.  Same seeds with the packing switched
+    off (the trunk then packs every batch itself): identical rollout tensors, identical parameters after learn_epoch."""
+    from rl_algo_impls_b200.actor import rng
+    from rl_algo_impls_b200.envs import make_synthetic_env
+    from rl_algo_impls_b200.policy import ActorCritic
+    from rl_algo_impls_b200.ppo import PPO
+    from rl_algo_impls_b200.rollout import SyncStepRolloutGenerator
+
+    name, n_envs, n_steps, batch, pkw, akw = CONFIGS[cfg]
+    finals = []
+    for packed in (True, False):
+        torch.manual_seed(0)
+        rng.reseed(99)
+        env = make_synthetic_env(name, n_envs, seed=1, device=cuda, pool=3)
+        policy = ActorCritic(env, subaction_mask=env.spec.subaction_mask, **pkw).to(cuda)
+        assert policy.packed_obs_shape is not None
+        C, H, W = env.single_observation_space.shape
+        if not packed:
+            policy.network.packed_obs_shape = lambda: None
+        gen = SyncStepRolloutGenerator(policy, env, n_steps=n_steps, subaction_mask=env.spec.subaction_mask)
+        algo = PPO(policy, cuda, None, batch_size=batch, **akw)
+        algo.learn_epoch(0, 1 << 30, gen, None)
+        if packed:
+            assert tuple(gen.obs.shape[2:]) == (H, W, (C + 7) // 8 * 8) and (gen.obs[..., C:] == 0).all()
+            obs_nchw = gen.obs[..., :C].permute(0, 1, 4, 2, 3).contiguous()
+        else:
+            assert tuple(gen.obs.shape[2:]) == (C, H, W)
+            obs_nchw = gen.obs.float()
+        finals.append((obs_nchw, gen.logprobs.clone(), gen.values.clone(), [p.detach().clone() for p in policy.parameters()],
+                       algo.last_train_stats))
+    a, b = finals
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    for pa, pb in zip(a[3], b[3]):
+        assert torch.equal(pa, pb)
+    assert a[4].loss == b[4].loss and a[4].grad_norm == b[4].grad_norm
