@@ -82,9 +82,14 @@ def gridnet_tensors(B, HW, nvec, n_pick, unit_p, dtype=torch.float32, act_dtype=
     return logits, mask, pick_mask, actions, pick
 
 
-def bench_loss(B, HW, nvec, gates, n_pick, V, unit_p, dtype=torch.float32):
+def bench_loss(B, HW, nvec, gates, n_pick, V, unit_p, dtype=torch.float32, inplace=False, ld=0):
+    """inplace: the learner's call (persistent dlogits, previous rows cleared); ld: channel-padded logit rows."""
     dev = "cuda"
     logits, mask, pick_mask, actions, pick = gridnet_tensors(B, HW, nvec, n_pick, unit_p, dtype)
+    if ld:
+        padded = torch.zeros(logits.shape[:-1] + (ld,), dtype=dtype, device=dev)
+        padded[..., :logits.shape[-1]] = logits
+        logits = padded
     spec = ops.GridnetSpec.from_subaction_mask(nvec, gates, n_pick)
     vs = (B,) if V == 1 else (B, V)
     old_logp = torch.randn(B, device=dev) * 0.1 - 20
@@ -94,12 +99,13 @@ def bench_loss(B, HW, nvec, gates, n_pick, V, unit_p, dtype=torch.float32):
     h = ops.PpoHyper(clip_range=0.1, clip_range_vf=0.1, ent_coef=0.01, vf_coef=[0.5] * V, adv_weights=w)
     moments = ops.adv_moments(adv.view(B, V), None, ops.ADV_NORMALIZE, w)
     fn = lambda: ops.ppo_gridnet_loss(h, spec, logits, mask, pick_mask, actions, pick, old_logp, adv, ov, rt, nv,
-                                      moments=moments)
+                                      moments=moments, inplace=inplace)
     med, best = time_kernel(fn, 'b200rl_ppo_gridnet_loss')
     S, A, es = sum(nvec), len(nvec), logits.element_size()
     nbytes = B * (2 * es * HW * (S + n_pick) + HW * S + n_pick * HW + HW * A + 2 * n_pick + 4 * (2 + 5 * V))
-    return dict(kernel="ppo_gridnet_loss", B=B, HW=HW, S=S + n_pick, V=V, unit_p=unit_p, dtype=str(dtype), ms_median=med,
-                ms_best=best, bytes=nbytes, gbs=nbytes / med / 1e6, frac=nbytes / med / 1e6 / peak_gbs())
+    return dict(kernel="ppo_gridnet_loss" + ("_inplace" if inplace else ""), B=B, HW=HW, S=S + n_pick, ld=ld or S + n_pick,
+                V=V, unit_p=unit_p, dtype=str(dtype), ms_median=med, ms_best=best, bytes=nbytes, gbs=nbytes / med / 1e6,
+                frac=nbytes / med / 1e6 / peak_gbs())
 
 
 def bench_gather(M, B, row_shapes):
@@ -139,6 +145,23 @@ def main():
         rows.append(bench_loss(3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 1.0))
         print(json.dumps(rows[-1]), flush=True)
         rows.append(bench_loss(512, 4096, LUX_NVEC, LUX_GATES, 1, 13, 1.0))
+        print(json.dumps(rows[-1]), flush=True)
+    if a.what in ("loss_inplace", "all"):  # what the learner launches: persistent dlogits, padded rows
+        for B, up in ((3072, 0.06), (3072, 0.12), (3072, 0.25), (3072, 1.0), (256, 0.06)):
+            rows.append(bench_loss(B, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, up, inplace=True, ld=80))
+            print(json.dumps(rows[-1]), flush=True)
+        rows.append(bench_loss(3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 0.06, torch.bfloat16, inplace=True, ld=80))
+        print(json.dumps(rows[-1]), flush=True)
+        for B, dt in ((128, torch.bfloat16), (128, torch.float32), (512, torch.bfloat16), (512, torch.float32)):
+            rows.append(bench_loss(B, 4096, LUX_NVEC, LUX_GATES, 1, 13, 0.02, dt, inplace=True, ld=32))
+            print(json.dumps(rows[-1]), flush=True)
+        rows.append(bench_loss(512, 4096, LUX_NVEC, LUX_GATES, 1, 13, 1.0, torch.bfloat16, inplace=True, ld=32))
+        print(json.dumps(rows[-1]), flush=True)
+    if a.what == "loss_c4_inplace":  # the ncu target of round 2
+        rows.append(bench_loss(3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 0.06, inplace=True, ld=80))
+        print(json.dumps(rows[-1]), flush=True)
+    if a.what == "loss_c5_inplace":
+        rows.append(bench_loss(128, 4096, LUX_NVEC, LUX_GATES, 1, 13, 0.02, torch.bfloat16, inplace=True, ld=32))
         print(json.dumps(rows[-1]), flush=True)
     if a.what == "loss_c4":  # one shape, few launches: the ncu target
         rows.append(bench_loss(3072, 256, MICRORTS_NVEC, MICRORTS_GATES, 0, 1, 0.06))
