@@ -232,6 +232,7 @@ struct StreamStage {
   uint8_t* image;   // 16-byte aligned, >= chunk mask bytes + 32
   uint8_t* zeros;   // kZeroBuf bytes, 16-byte aligned
   uint64_t* bar;    // mbarrier the mask image completes on (phase 0; one chunk per CTA)
+  uint32_t* pick_bitmap;  // [kMaxPick][kChunkCells / 32] words: valid pick cells of the chunk, per pick head
 };
 
 // The rows a previous call wrote into a persistent dlogits buffer (b200rl_ppo_gridnet_loss_inplace): the unit cells of
@@ -241,10 +242,20 @@ template <typename LT, int BLOCK>
 __device__ __forceinline__ void clear_previous_rows(const GridDev& G, long long b, const ChunkLists& prev) {
   LT* out = static_cast<LT*>(G.dlogits) + b * G.HW * G.ld;
   const int n = *prev.unit_count;
-  const uint32_t Sp = (uint32_t)G.Sp;
-  for (uint32_t i = threadIdx.x; i < (uint32_t)n * Sp; i += BLOCK) {
-    const uint32_t k = i / Sp;
-    out[(long long)prev.unit[k] * G.ld + (i - k * Sp)] = from_f32<LT>(0.f);
+  const uint32_t row_bytes = (uint32_t)G.ld * (uint32_t)sizeof(LT);
+  if (((reinterpret_cast<uintptr_t>(out) | row_bytes) & 15u) == 0) {
+    // padded rows (ld = 80 / 32: 16-byte multiples, 16-byte aligned): whole rows with 128-bit stores
+    const uint32_t q = row_bytes >> 4;  // 16-byte words per row
+    for (uint32_t i = threadIdx.x; i < (uint32_t)n * q; i += BLOCK) {
+      const uint32_t k = i / q;
+      reinterpret_cast<uint4*>(out + (long long)prev.unit[k] * G.ld)[i - k * q] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  } else {
+    const uint32_t Sp = (uint32_t)G.Sp;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)n * Sp; i += BLOCK) {
+      const uint32_t k = i / Sp;
+      out[(long long)prev.unit[k] * G.ld + (i - k * Sp)] = from_f32<LT>(0.f);
+    }
   }
   for (int kp = 0; kp < G.n_pick; ++kp) {
     const int np = prev.pick_count[kp * prev.pick_count_stride];
@@ -270,6 +281,16 @@ __device__ __forceinline__ uint32_t stream_chunk(const GridDev& G, long long b, 
   const RowPrefetch pf{reinterpret_cast<const uint8_t*>(static_cast<const LT*>(G.logits) + row0 * G.ld),
                        (uint32_t)G.Sp * (uint32_t)sizeof(LT), (uint32_t)G.ld * (uint32_t)sizeof(LT)};
   const bool fill = ZERO && G.rows_mode != kRowsClear;
+  // pick_position masks are one byte per cell: a ballot over the chunk's bytes IS the bitmap word
+  auto scan_pick_masks = [&]() {
+    for (int kp = 0; kp < G.n_pick; ++kp) {
+      const uint8_t* pm = G.pick_mask + (b * G.n_pick + kp) * G.HW + cell0;
+      for (int c = tid; c < kChunkCells; c += BLOCK) {  // warp-uniform trip count
+        const uint32_t bits = __ballot_sync(0xffffffffu, c < cells && pm[c] != 0);
+        if ((tid & 31) == 0) st.pick_bitmap[kp * (kChunkCells / 32) + (c >> 5)] = bits;
+      }
+    }
+  };
   uint32_t skew = 0;
   if (st.image != nullptr) {
     // TMA path: ONE bulk copy lands the chunk's mask bytes in shared memory while bulk copies of a zeroed
@@ -296,6 +317,7 @@ __device__ __forceinline__ uint32_t stream_chunk(const GridDev& G, long long b, 
     __syncthreads();  // barrier initialised, zero buffer and head / tail bytes in place
     if (fill) zero_fill_bulk(g_zero, zero_bytes, st.zeros);
     if (ZERO && !fill) clear_previous_rows<LT, BLOCK>(G, b, *prev);  // while the mask image is in flight
+    scan_pick_masks();
     mbar_wait(st.bar, 0);
     scan_cells_image<BLOCK>(st.image + skew, cells, (uint32_t)G.S, bitmap, pf);
   } else {
@@ -304,22 +326,18 @@ __device__ __forceinline__ uint32_t stream_chunk(const GridDev& G, long long b, 
     if (tid < kChunkCells / 32) bitmap[tid] = 0u;
     if (fill) zero_fill<BLOCK>(g_zero, zero_bytes);
     if (ZERO && !fill) clear_previous_rows<LT, BLOCK>(G, b, *prev);
+    scan_pick_masks();
     __syncthreads();
     scan_mask<BLOCK>(g_mask, mask_bytes, (uint32_t)G.S, bitmap, pf);
   }
   __syncthreads();  // (also: every read of the previous lists above is done before `out` may alias them below)
-  compact_cells(bitmap, (cells + 31) >> 5, out.unit, cell0, out.unit_count);
-  // pick_position masks: one byte per cell, same compaction (no row prefetch: one logit per cell)
-  for (int kp = 0; kp < G.n_pick; ++kp) {
-    __syncthreads();
-    if (tid < kChunkCells / 32) bitmap[tid] = 0u;
-    __syncthreads();
-    const uint8_t* pm = G.pick_mask + (b * G.n_pick + kp) * G.HW + cell0;
-    for (int c = tid; c < cells; c += BLOCK)
-      if (pm[c]) atomicOr(&bitmap[c >> 5], 1u << (c & 31));
-    __syncthreads();
-    compact_cells(bitmap, (cells + 31) >> 5, out.pick + kp * out.pick_stride, cell0,
-                  out.pick_count + kp * out.pick_count_stride);
+  // one warp per list: the unit cells, then each pick head's valid cells
+  for (int job = tid >> 5; job < 1 + G.n_pick; job += BLOCK / 32) {
+    if (job == 0)
+      compact_cells_warp(bitmap, (cells + 31) >> 5, out.unit, cell0, out.unit_count);
+    else
+      compact_cells_warp(st.pick_bitmap + (job - 1) * (kChunkCells / 32), (cells + 31) >> 5,
+                         out.pick + (job - 1) * out.pick_stride, cell0, out.pick_count + (job - 1) * out.pick_count_stride);
   }
   return skew;
 }
@@ -330,13 +348,14 @@ __global__ void __launch_bounds__(kStreamBlock) gridnet_stream_kernel(const __gr
   __shared__ __align__(16) uint8_t zeros[kZeroBuf];
   __shared__ uint64_t bar;
   __shared__ uint32_t bitmap[kChunkCells / 32];
+  __shared__ uint32_t pick_bitmap[kMaxPick * (kChunkCells / 32)];
   const long long b = blockIdx.x / G.chunks;
   const int chunk = (int)(blockIdx.x - b * G.chunks);
   const ChunkLists out{G.unit_list + (b * G.chunks + chunk) * kChunkCells, G.unit_count + b * G.chunks + chunk,
                        G.pick_list + ((b * G.n_pick) * G.chunks + chunk) * kChunkCells,
                        G.pick_count + (b * G.n_pick) * G.chunks + chunk, (long long)G.chunks * kChunkCells, G.chunks};
   // in the rows modes the list workspace persists across calls: what it holds on entry are the previous call's rows
-  stream_chunk<LT, ZERO, kStreamBlock>(G, b, chunk, bitmap, out, StreamStage{G.image_bytes ? stream_smem : nullptr, zeros, &bar}, &out);
+  stream_chunk<LT, ZERO, kStreamBlock>(G, b, chunk, bitmap, out, StreamStage{G.image_bytes ? stream_smem : nullptr, zeros, &bar, pick_bitmap}, &out);
   pdl_trigger();  // the compute launch may be scheduled: it waits for this grid's completion before reading the lists
   if (ZERO && G.rows_mode != kRowsClear && G.image_bytes && threadIdx.x == 0) bulk_wait_read();  // the zero buffer must outlive the copies that read it
 }
@@ -359,6 +378,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
     gridnet_kernel(const __grid_constant__ GridDev G, const __grid_constant__ PpoDev P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_bitmap[kChunkCells / 32];
+  __shared__ uint32_t s_pick_bitmap[SELF_STREAM && PICK ? kMaxPick * (kChunkCells / 32) : 1];
   __shared__ double s_wsum[2][BLOCK / 32];        // per-warp (logp, entropy)
   __shared__ Soft s_wpick[kMaxPick][BLOCK / 32];  // per-warp pick statistics
   __shared__ float s_bcast[2];
@@ -392,7 +412,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
     const ChunkLists prev{G.unit_list + b * kChunkCells, G.unit_count + b, G.pick_list + (b * G.n_pick) * kChunkCells,
                           G.pick_count + b * G.n_pick, kChunkCells, 1};
     const uint32_t skew = stream_chunk<LT, MODE != kFwd, BLOCK>(G, b, 0, s_bitmap, out,
-                                                               StreamStage{G.image_bytes ? s_image : nullptr, s_zeros, &s_bar}, &prev);
+                                                               StreamStage{G.image_bytes ? s_image : nullptr, s_zeros, &s_bar, s_pick_bitmap}, &prev);
     if (G.image_bytes) g_mask = s_image + skew;  // the unit cells re-read their mask bytes from the image
     __syncthreads();
     if (MODE == kPpo && G.rows_mode != kRowsOff) {  // record this call's rows for the next one (the previous were read above)
@@ -423,18 +443,33 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
   }
 
   // ---- 1. this sample's lists ------------------------------------------------------------------------
+  // the lane layout: a thread's slot depends on its lane, and a divergent read of the kernel parameters (constant
+  // bank) serialises, so one warp copies the table to shared memory (13 % of the stall samples before)
+  __shared__ LaneSlot s_slot[32];
+  if (tid >= BLOCK - 32) s_slot[tid - (BLOCK - 32)] = G.slot[tid - (BLOCK - 32)];
   if (!SELF_STREAM) pdl_wait();  // the streaming launch ahead of this one wrote them (programmatic dependent launch)
-  if (tid == 0) {
+  // exclusive prefixes of the per-chunk counts: one warp per list, counts loaded side by side (a serial walk of 16
+  // dependent global loads by one thread cost ~10 us at 64x64) and scanned with shuffles
+  for (int job = tid >> 5; job < 1 + n_pick; job += BLOCK / 32) {
+    const int lane = tid & 31;
+    int* pp = job == 0 ? prefix : pick_prefix + (job - 1) * (G.chunks + 1);
     int acc = 0;
-    for (int c = 0; c < G.chunks; ++c) prefix[c] = acc, acc += SELF_STREAM ? s_counts[0] : G.unit_count[b * G.chunks + c];
-    prefix[G.chunks] = acc;
-  } else if (PICK && tid >= 32 && tid < 32 + n_pick) {
-    const int kp = tid - 32;
-    int acc = 0;
-    int* pp = pick_prefix + kp * (G.chunks + 1);
-    for (int c = 0; c < G.chunks; ++c)
-      pp[c] = acc, acc += SELF_STREAM ? s_counts[1 + kp] : G.pick_count[(b * n_pick + kp) * G.chunks + c];
-    pp[G.chunks] = acc;
+    for (int c0 = 0; c0 < G.chunks; c0 += 32) {
+      const int c = c0 + lane;
+      int v = 0;
+      if (c < G.chunks)
+        v = SELF_STREAM ? s_counts[job]
+                        : (job == 0 ? G.unit_count[b * G.chunks + c] : G.pick_count[(b * n_pick + job - 1) * G.chunks + c]);
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (c < G.chunks) pp[c] = acc + incl - v;
+      acc += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) pp[G.chunks] = acc;
   }
   __syncthreads();
   const ListView units{SELF_STREAM ? s_list : G.unit_list + (b * G.chunks) * kChunkCells, prefix, G.chunks};
@@ -442,7 +477,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
 
   // ---- 2. forward over the unit cells -----------------------------------------------------------------
   const int group = tid / G.G, n_groups = BLOCK / G.G;
-  const LaneSlot slot = G.slot[tid & (G.G - 1)];
+  const LaneSlot slot = s_slot[tid & (G.G - 1)];
   const int gate_ref = slot.len ? G.gate_ref[slot.head] : -1;
   const int gate_val = slot.len ? G.gate_val[slot.head] : 0;
   double logp_acc = 0.0, ent_acc = 0.0;
@@ -542,16 +577,36 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
   }
   __syncthreads();
   float dlogp = 0.f, dent = 0.f;
-  if (tid == 0) {
-    double tot_logp = 0.0, tot_ent = 0.0;
+  // warp 0 folds the per-warp partials with shuffles (fixed order), thread 0 finishes the sample
+  double tot_logp = 0.0, tot_ent = 0.0;
+  Soft tot_pick[NP];
+  if (tid < 32) {
+    constexpr int NW = BLOCK / 32;
+    tot_logp = tid < NW ? s_wsum[0][tid] : 0.0, tot_ent = tid < NW ? s_wsum[1][tid] : 0.0;
 #pragma unroll
-    for (int w = 0; w < BLOCK / 32; ++w) tot_logp += s_wsum[0][w], tot_ent += s_wsum[1][w];
+    for (int kp = 0; kp < NP; ++kp) tot_pick[kp] = (kp < n_pick && tid < NW) ? s_wpick[kp][tid] : Soft{-INFINITY, 0.f, 0.f};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      if (o < NW) {
+        tot_logp += shfl_xor_f64(tot_logp, o);
+        tot_ent += shfl_xor_f64(tot_ent, o);
+#pragma unroll
+        for (int kp = 0; kp < NP; ++kp)
+          if (kp < n_pick) {
+            Soft other;
+            other.m = __shfl_xor_sync(0xffffffffu, tot_pick[kp].m, o);
+            other.s = __shfl_xor_sync(0xffffffffu, tot_pick[kp].s, o);
+            other.q = __shfl_xor_sync(0xffffffffu, tot_pick[kp].q, o);
+            tot_pick[kp] = soft_merge(tot_pick[kp], other);
+          }
+      }
+    }
+  }
+  if (tid == 0) {
 #pragma unroll
     for (int kp = 0; kp < NP; ++kp) {
       if (kp >= n_pick) continue;
-      Soft t = s_wpick[kp][0];
-#pragma unroll 1
-      for (int w = 1; w < BLOCK / 32; ++w) t = soft_merge(t, s_wpick[kp][w]);
+      const Soft t = tot_pick[kp];
       const bool any = t.s > 0.f;
       float p_lse = 0.f, p_ent = 0.f;
       if (any) {

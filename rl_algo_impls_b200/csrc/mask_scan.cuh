@@ -167,11 +167,11 @@ __device__ __forceinline__ void scan_cells_image(const uint8_t* m, int cells, ui
   }
 }
 
-// warp 0: bitmap -> ascending list of flagged cells (ids offset by `base`); count through *out_count
-__device__ __forceinline__ void compact_cells(const uint32_t* bitmap, int words, uint16_t* list, int base_id,
-                                              int* out_count) {
-  if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
+// ONE warp (every lane of it calls): bitmap -> ascending list of flagged cells (ids offset by `base_id`); count
+// through *out_count
+__device__ __forceinline__ void compact_cells_warp(const uint32_t* bitmap, int words, uint16_t* list, int base_id,
+                                                   int* out_count) {
+  const int lane = threadIdx.x & 31;
   int base = 0;
   for (int w0 = 0; w0 < words; w0 += 32) {
     const int w = w0 + lane;
@@ -192,6 +192,13 @@ __device__ __forceinline__ void compact_cells(const uint32_t* bitmap, int words,
     base += __shfl_sync(0xffffffffu, incl, 31);
   }
   if (lane == 0) *out_count = base;
+}
+
+// warp 0 of the CTA does the compaction
+__device__ __forceinline__ void compact_cells(const uint32_t* bitmap, int words, uint16_t* list, int base_id,
+                                              int* out_count) {
+  if (threadIdx.x >= 32) return;
+  compact_cells_warp(bitmap, words, list, base_id, out_count);
 }
 
 }  // namespace b200rl
