@@ -32,9 +32,37 @@ def flush_l2():
     _flush.zero_()
 
 
+GRAPH = False  # --graph: time replays of ONE captured call (what the learner's graphed update replays)
+
+
+def time_graph(fn, iters=20, warmup=3, flush=True):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    times = []
+    for _ in range(iters):
+        if flush:
+            flush_l2()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        times.append(s.elapsed_time(e))
+    return float(np.median(times)), float(np.min(times))
+
+
 def time_kernel(fn, name, iters=20, warmup=3, flush=True):
     """CUDA events recorded immediately around the C-ABI call `name` (ops.KernelTimer), so that the
     Python-side argument marshalling of the wrapper is outside the bracket."""
+    if GRAPH:
+        return time_graph(fn, iters, warmup, flush)
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -125,7 +153,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
     ap.add_argument("--json", default=None)
+    ap.add_argument("--graph", action="store_true", help="time graph replays of one captured call instead of eager calls")
     a = ap.parse_args()
+    global GRAPH
+    GRAPH = a.graph
     rows = []
     if a.what in ("gae", "all"):
         for T, N, V in [(32, 8, 1), (128, 8, 1), (64, 4096, 1), (512, 24, 1), (32, 1024, 13), (128, 1 << 20, 1),

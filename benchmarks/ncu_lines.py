@@ -1,5 +1,6 @@
 """Per-source-line instruction / stall-sample totals of one captured kernel.
-Usage: python benchmarks/ncu_lines.py <report.ncu-rep> [top]   (reads `ncu -i ... --page source --print-source cuda,sass --csv`)"""
+Usage: python benchmarks/ncu_lines.py <report.ncu-rep> [top] [kernel-name regex]
+(reads `ncu -i ... --page source --print-source cuda,sass --csv`)"""
 import csv
 import io
 import subprocess
@@ -7,9 +8,11 @@ import sys
 from collections import defaultdict
 
 
-def main(rep, top=40):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
-                         capture_output=True, text=True).stdout
+def main(rep, top=40, kernel=None):
+    cmd = ["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"]
+    if kernel:
+        cmd += ["-k", "regex:" + kernel]
+    raw = subprocess.run(cmd, capture_output=True, text=True).stdout
     inst, samp, text = defaultdict(int), defaultdict(int), {}
     path, hdr = None, None
     for r in csv.reader(io.StringIO(raw)):
@@ -33,4 +36,4 @@ def main(rep, top=40):
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:3])
+    main(*sys.argv[1:4])

@@ -88,6 +88,8 @@ struct GridDev {
   int* unit_count;       // [B][chunks]
   uint16_t* pick_list;   // [B][n_pick][chunks * kChunkCells]
   int* pick_count;       // [B][n_pick][chunks]
+  int* done_counter;     // split path: compute CTAs that have written their partial rows (zeroed by the streaming launch)
+  int fused_finalize;    // the last compute CTA to arrive reduces the partial rows itself (no finaliser launch)
   LaneSlot slot[32];
 };
 
@@ -239,9 +241,9 @@ struct StreamStage {
 // this chunk's previous list get their whole row cleared, the previous pick lists their pick column.  Generic stores
 // by the whole CTA; the caller separates them from this call's gradient stores with a barrier / a grid dependency.
 template <typename LT, int BLOCK>
-__device__ __forceinline__ void clear_previous_rows(const GridDev& G, long long b, const ChunkLists& prev) {
+__device__ __forceinline__ void clear_previous_rows(const GridDev& G, long long b, const ChunkLists& prev, int n,
+                                                    const int (&np)[kMaxPick]) {
   LT* out = static_cast<LT*>(G.dlogits) + b * G.HW * G.ld;
-  const int n = *prev.unit_count;
   const uint32_t row_bytes = (uint32_t)G.ld * (uint32_t)sizeof(LT);
   if (((reinterpret_cast<uintptr_t>(out) | row_bytes) & 15u) == 0) {
     // padded rows (ld = 80 / 32: 16-byte multiples, 16-byte aligned): whole rows with 128-bit stores
@@ -258,9 +260,8 @@ __device__ __forceinline__ void clear_previous_rows(const GridDev& G, long long 
     }
   }
   for (int kp = 0; kp < G.n_pick; ++kp) {
-    const int np = prev.pick_count[kp * prev.pick_count_stride];
     const uint16_t* pl = prev.pick + kp * prev.pick_stride;
-    for (int i = threadIdx.x; i < np; i += BLOCK) out[(long long)pl[i] * G.ld + G.S + kp] = from_f32<LT>(0.f);
+    for (int i = threadIdx.x; i < np[kp]; i += BLOCK) out[(long long)pl[i] * G.ld + G.S + kp] = from_f32<LT>(0.f);
   }
 }
 
@@ -281,15 +282,32 @@ __device__ __forceinline__ uint32_t stream_chunk(const GridDev& G, long long b, 
   const RowPrefetch pf{reinterpret_cast<const uint8_t*>(static_cast<const LT*>(G.logits) + row0 * G.ld),
                        (uint32_t)G.Sp * (uint32_t)sizeof(LT), (uint32_t)G.ld * (uint32_t)sizeof(LT)};
   const bool fill = ZERO && G.rows_mode != kRowsClear;
-  // pick_position masks are one byte per cell: a ballot over the chunk's bytes IS the bitmap word
-  auto scan_pick_masks = [&]() {
-    for (int kp = 0; kp < G.n_pick; ++kp) {
-      const uint8_t* pm = G.pick_mask + (b * G.n_pick + kp) * G.HW + cell0;
-      for (int c = tid; c < kChunkCells; c += BLOCK) {  // warp-uniform trip count
-        const uint32_t bits = __ballot_sync(0xffffffffu, c < cells && pm[c] != 0);
-        if ((tid & 31) == 0) st.pick_bitmap[kp * (kChunkCells / 32) + (c >> 5)] = bits;
-      }
+  // Independent global loads first, so that they are all in flight together: the counts of the previous call's rows
+  // (the lists they index come next) and this chunk's pick_position mask bytes (one byte per cell: a ballot over them
+  // IS a bitmap word).
+  int n_prev = 0, np_prev[kMaxPick] = {0, 0, 0, 0};
+  if (ZERO && !fill) {
+    n_prev = *prev->unit_count;
+    for (int kp = 0; kp < G.n_pick; ++kp) np_prev[kp] = prev->pick_count[kp * prev->pick_count_stride];
+  }
+  constexpr int kCellIters = kChunkCells / BLOCK;
+  uint8_t pmv[kMaxPick][kCellIters];
+#pragma unroll
+  for (int kp = 0; kp < kMaxPick; ++kp)
+#pragma unroll
+    for (int it = 0; it < kCellIters; ++it) {
+      const int c = tid + it * BLOCK;
+      pmv[kp][it] = (kp < G.n_pick && c < cells) ? G.pick_mask[(b * G.n_pick + kp) * G.HW + cell0 + c] : (uint8_t)0;
     }
+  auto scan_pick_masks = [&]() {
+#pragma unroll
+    for (int kp = 0; kp < kMaxPick; ++kp)
+#pragma unroll
+      for (int it = 0; it < kCellIters; ++it) {
+        if (kp >= G.n_pick) continue;  // warp-uniform
+        const uint32_t bits = __ballot_sync(0xffffffffu, pmv[kp][it] != 0);
+        if ((tid & 31) == 0) st.pick_bitmap[kp * (kChunkCells / 32) + ((tid + it * BLOCK) >> 5)] = bits;
+      }
   };
   uint32_t skew = 0;
   if (st.image != nullptr) {
@@ -316,7 +334,7 @@ __device__ __forceinline__ uint32_t stream_chunk(const GridDev& G, long long b, 
     }
     __syncthreads();  // barrier initialised, zero buffer and head / tail bytes in place
     if (fill) zero_fill_bulk(g_zero, zero_bytes, st.zeros);
-    if (ZERO && !fill) clear_previous_rows<LT, BLOCK>(G, b, *prev);  // while the mask image is in flight
+    if (ZERO && !fill) clear_previous_rows<LT, BLOCK>(G, b, *prev, n_prev, np_prev);  // while the mask image is in flight
     scan_pick_masks();
     mbar_wait(st.bar, 0);
     scan_cells_image<BLOCK>(st.image + skew, cells, (uint32_t)G.S, bitmap, pf);
@@ -325,7 +343,7 @@ __device__ __forceinline__ uint32_t stream_chunk(const GridDev& G, long long b, 
     for (uint32_t o = (uint32_t)tid * 128u; o < mask_bytes; o += BLOCK * 128u) prefetch_l2(g_mask + o);
     if (tid < kChunkCells / 32) bitmap[tid] = 0u;
     if (fill) zero_fill<BLOCK>(g_zero, zero_bytes);
-    if (ZERO && !fill) clear_previous_rows<LT, BLOCK>(G, b, *prev);
+    if (ZERO && !fill) clear_previous_rows<LT, BLOCK>(G, b, *prev, n_prev, np_prev);
     scan_pick_masks();
     __syncthreads();
     scan_mask<BLOCK>(g_mask, mask_bytes, (uint32_t)G.S, bitmap, pf);
@@ -354,6 +372,7 @@ __global__ void __launch_bounds__(kStreamBlock) gridnet_stream_kernel(const __gr
   const ChunkLists out{G.unit_list + (b * G.chunks + chunk) * kChunkCells, G.unit_count + b * G.chunks + chunk,
                        G.pick_list + ((b * G.n_pick) * G.chunks + chunk) * kChunkCells,
                        G.pick_count + (b * G.n_pick) * G.chunks + chunk, (long long)G.chunks * kChunkCells, G.chunks};
+  if (blockIdx.x == 0 && threadIdx.x == 0) *G.done_counter = 0;  // the compute launch behind this one counts up from here
   // in the rows modes the list workspace persists across calls: what it holds on entry are the previous call's rows
   stream_chunk<LT, ZERO, kStreamBlock>(G, b, chunk, bitmap, out, StreamStage{G.image_bytes ? stream_smem : nullptr, zeros, &bar, pick_bitmap}, &out);
   pdl_trigger();  // the compute launch may be scheduled: it waits for this grid's completion before reading the lists
@@ -475,6 +494,20 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
   const ListView units{SELF_STREAM ? s_list : G.unit_list + (b * G.chunks) * kChunkCells, prefix, G.chunks};
   const int n_unit = prefix[G.chunks];
 
+  // the pick_position logit of this thread's first valid cell, per pick head: the loads are issued here, unconsumed, so
+  // that they travel together with the forward pass's loads instead of after its reductions
+  LT pick_raw[NP];
+#pragma unroll
+  for (int kp = 0; kp < NP; ++kp) {
+    pick_raw[kp] = from_f32<LT>(0.f);
+    if (kp < n_pick) {
+      const ListView pl{SELF_STREAM ? s_plist + kp * kChunkCells
+                                    : G.pick_list + ((b * n_pick + kp) * G.chunks) * kChunkCells,
+                        pick_prefix + kp * (G.chunks + 1), G.chunks};
+      if (tid < pl.prefix[G.chunks]) pick_raw[kp] = g_logits[(long long)pl.at(tid) * G.ld + G.S + kp];
+    }
+  }
+
   // ---- 2. forward over the unit cells -----------------------------------------------------------------
   const int group = tid / G.G, n_groups = BLOCK / G.G;
   const LaneSlot slot = s_slot[tid & (G.G - 1)];
@@ -541,8 +574,9 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
                                   : G.pick_list + ((b * n_pick + kp) * G.chunks) * kChunkCells,
                       pick_prefix + kp * (G.chunks + 1), G.chunks};
     const int n_valid = pl.prefix[G.chunks];
+    if (tid < n_valid) pick[kp] = Soft{to_f32(pick_raw[kp]), 1.f, 0.f};
 #pragma unroll 1
-    for (int i = tid; i < n_valid; i += BLOCK)
+    for (int i = tid + BLOCK; i < n_valid; i += BLOCK)
       pick[kp] = soft_push(pick[kp], to_f32(g_logits[(long long)pl.at(i) * G.ld + G.S + kp]));
     if (MODE != kBwd && tid == 0) {
       const long long a = (long long)load_index(G.pick_actions, G.pick_dtype, b * n_pick + kp);
@@ -630,6 +664,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
       row[0] = t.surrogate, row[1] = tot_ent, row[2] = t.kl, row[3] = t.clipped, row[4] = t.teacher;
       if (G.logp) G.logp[b] = (float)tot_logp;
       if (G.entropy) G.entropy[b] = (float)tot_ent;
+      if (!SELF_STREAM && G.fused_finalize) __threadfence();  // the row is read by whichever CTA arrives last
     }
   }
   if (MODE == kPpo && tid >= 32 && tid < 32 + P.V) {
@@ -637,6 +672,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
     float2 r = ppo_value_terms(P, b, v);
     double* row = P.partials + b * ppo_nstat(P.V);
     row[kPolicyStats + v] = r.x, row[kPolicyStats + P.V + v] = r.y;
+    if (!SELF_STREAM && G.fused_finalize) __threadfence();
   }
   if (MODE == kFwd) return;
   if (MODE == kPpo) pdl_trigger();  // the stats finaliser may be scheduled; it waits for this grid to complete
@@ -699,6 +735,17 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
       const float lp = to_f32(g_logits[(long long)c * G.ld + G.S + kp]) - p_lse;
       const float pr = fast_exp(lp);
       g_out[(long long)c * G.ld + G.S + kp] = from_f32<LT>(dlogp * ((a == c ? 1.f : 0.f) - pr) - dent * pr * (lp + p_ent));
+    }
+  }
+  // ---- 7. small minibatches: the last CTA to arrive turns the partial rows into the stats vector --------------
+  if (MODE == kPpo && !SELF_STREAM && G.fused_finalize) {
+    __shared__ int s_last;
+    __syncthreads();  // every writer of this CTA's partial row has fenced its stores
+    if (tid == 0) s_last = atomicAdd(G.done_counter, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      ppo_finalize_block(P, G.B, 1, reinterpret_cast<double*>(s_lse));  // the stash is free by now
     }
   }
 }
@@ -772,7 +819,9 @@ static int bind_workspace(GridDev* G, void* workspace, size_t workspace_bytes, c
   G->unit_list = reinterpret_cast<uint16_t*>(w), w += align16((size_t)G->B * G->chunks * kChunkCells * sizeof(uint16_t));
   G->unit_count = reinterpret_cast<int*>(w), w += align16((size_t)G->B * G->chunks * sizeof(int));
   G->pick_list = reinterpret_cast<uint16_t*>(w), w += align16((size_t)G->B * G->n_pick * G->chunks * kChunkCells * sizeof(uint16_t));
-  G->pick_count = reinterpret_cast<int*>(w);
+  G->pick_count = reinterpret_cast<int*>(w), w += align16((size_t)G->B * G->n_pick * G->chunks * sizeof(int));
+  G->done_counter = reinterpret_cast<int*>(w);  // inside the 64 spare bytes of grid_workspace_bytes()
+  G->fused_finalize = 0;
   return B200RL_OK;
 }
 
@@ -962,9 +1011,14 @@ static int ppo_gridnet_loss_impl(const b200rl_gridnet_desc* d, const void* logit
   }
   if (rc) return rc;
   G.dlogits = dlogits, G.logp = logp_out, G.entropy = entropy_out;
+  // Split path with few samples (a C5 per-GPU minibatch is 128 CTAs): the finaliser is folded into the compute
+  // launch -- the last CTA to arrive reduces the rows (one fence + one atomic per CTA, cheap at this grid size; at
+  // thousands of CTAs the fences delay every CTA's exit and the separate 1-block launch wins).
+  const size_t need = (size_t)32 * ppo_nstat(P.V) * sizeof(double);  // scratch of ppo_finalize_block at 1024 threads
+  G.fused_finalize = G.chunks > 1 && G.B <= 1024 && (size_t)G.stash * G.A * 2 * sizeof(float) >= need;
   rc = launch_mode<kPpo>(G, P, d->nvec_host, d->logits_dtype, s);  // derives the advantage normaliser itself
   if (rc) return rc;
-  return ppo_launch_finalize(P, G.B, 1, s);
+  return G.fused_finalize ? B200RL_OK : ppo_launch_finalize(P, G.B, 1, s);
 }
 }  // namespace b200rl
 
