@@ -88,8 +88,6 @@ struct GridDev {
   int* unit_count;       // [B][chunks]
   uint16_t* pick_list;   // [B][n_pick][chunks * kChunkCells]
   int* pick_count;       // [B][n_pick][chunks]
-  int* done_counter;     // split path: compute CTAs that have written their partial rows (zeroed by the streaming launch)
-  int fused_finalize;    // the last compute CTA to arrive reduces the partial rows itself (no finaliser launch)
   LaneSlot slot[32];
 };
 
@@ -372,7 +370,6 @@ __global__ void __launch_bounds__(kStreamBlock) gridnet_stream_kernel(const __gr
   const ChunkLists out{G.unit_list + (b * G.chunks + chunk) * kChunkCells, G.unit_count + b * G.chunks + chunk,
                        G.pick_list + ((b * G.n_pick) * G.chunks + chunk) * kChunkCells,
                        G.pick_count + (b * G.n_pick) * G.chunks + chunk, (long long)G.chunks * kChunkCells, G.chunks};
-  if (blockIdx.x == 0 && threadIdx.x == 0) *G.done_counter = 0;  // the compute launch behind this one counts up from here
   // in the rows modes the list workspace persists across calls: what it holds on entry are the previous call's rows
   stream_chunk<LT, ZERO, kStreamBlock>(G, b, chunk, bitmap, out, StreamStage{G.image_bytes ? stream_smem : nullptr, zeros, &bar, pick_bitmap}, &out);
   pdl_trigger();  // the compute launch may be scheduled: it waits for this grid's completion before reading the lists
@@ -449,16 +446,26 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
   // the per-sample PPO scalars are consumed by one thread after the reductions: start pulling them now; the
   // advantage normaliser (mean, std + 1e-8) is derived from the float64 moments here, off the critical path
   __shared__ float s_norm[2 * B200RL_MAX_VALUE_HEADS];
+  __shared__ float s_ahead[2];           // normalised advantage and behaviour log-prob of this sample
+  __shared__ float s_pick_xa[kMaxPick];  // the chosen pick cell's logit (finfo.min when that cell is masked)
   if (MODE == kPpo) {
     const int Vm = P.adv_mode == 3 ? 1 : P.adv_v;
     if (P.adv_mode != 0 && tid >= 64 && tid < 64 + Vm) ppo_norm_pair(P, Vm, tid - 64, s_norm);
-    if (tid == 0) {
-      prefetch_l1(P.old_logp + b);
-      prefetch_l1(P.adv + b * P.adv_v);
-    } else if (tid >= 32 && tid < 32 + P.V) {
+    if (tid >= 32 && tid < 32 + P.V) {
       const long long o = b * P.V + (tid - 32);
       prefetch_l1(P.new_values + o), prefetch_l1(P.old_values + o), prefetch_l1(P.returns + o);
     }
+  }
+  // Three dependent global loads (pick action -> its mask byte -> its logit) that do not depend on the lists: done
+  // here, by a thread of the last warp, instead of on thread 0's path between the reductions and the PPO terms
+  if (PICK && MODE != kBwd && tid >= BLOCK - kMaxPick && tid - (BLOCK - kMaxPick) < n_pick) {
+    const int kp = tid - (BLOCK - kMaxPick);
+    const long long a = (long long)load_index(G.pick_actions, G.pick_dtype, b * n_pick + kp);
+    float xa = 0.f;
+    if (a >= 0 && a < G.HW)
+      xa = G.pick_mask[(b * n_pick + kp) * G.HW + a]
+               ? to_f32((static_cast<const LT*>(G.logits) + row0 * G.ld)[a * G.ld + G.S + kp]) : kF32Lowest;
+    s_pick_xa[kp] = xa;
   }
 
   // ---- 1. this sample's lists ------------------------------------------------------------------------
@@ -491,6 +498,10 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
     if (lane == 0) pp[G.chunks] = acc;
   }
   __syncthreads();
+  if (MODE == kPpo && tid == BLOCK - 33) {  // s_norm is in place: the sample's advantage and behaviour log-prob, ahead of time
+    s_ahead[0] = ppo_sample_advantage(P, b, s_norm);
+    s_ahead[1] = P.old_logp[b];
+  }
   const ListView units{SELF_STREAM ? s_list : G.unit_list + (b * G.chunks) * kChunkCells, prefix, G.chunks};
   const int n_unit = prefix[G.chunks];
 
@@ -564,11 +575,9 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
 
   // ---- 3. pick_position: one online-softmax pass over the valid cells of the sample ----------------------
   Soft pick[NP];
-  float pick_xa[NP];
 #pragma unroll
   for (int kp = 0; kp < NP; ++kp) {
     pick[kp] = Soft{-INFINITY, 0.f, 0.f};
-    pick_xa[kp] = 0.f;
     if (kp >= n_pick) continue;
     const ListView pl{SELF_STREAM ? s_plist + kp * kChunkCells
                                   : G.pick_list + ((b * n_pick + kp) * G.chunks) * kChunkCells,
@@ -578,11 +587,6 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
 #pragma unroll 1
     for (int i = tid + BLOCK; i < n_valid; i += BLOCK)
       pick[kp] = soft_push(pick[kp], to_f32(g_logits[(long long)pl.at(i) * G.ld + G.S + kp]));
-    if (MODE != kBwd && tid == 0) {
-      const long long a = (long long)load_index(G.pick_actions, G.pick_dtype, b * n_pick + kp);
-      if (a >= 0 && a < G.HW)
-        pick_xa[kp] = G.pick_mask[(b * n_pick + kp) * G.HW + a] ? to_f32(g_logits[a * G.ld + G.S + kp]) : kF32Lowest;
-    }
   }
 
   // ---- 4. per-sample totals: warp partials -> thread 0 ---------------------------------------------------
@@ -647,7 +651,7 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
         const float ls = logf(t.s);
         p_lse = t.m + ls;
         p_ent = ls - t.q / t.s;
-        tot_logp += (double)(pick_xa[kp] - p_lse);
+        tot_logp += (double)(s_pick_xa[kp] - p_lse);
         tot_ent += (double)p_ent;
       }
       s_pick[kp * 3] = p_lse, s_pick[kp * 3 + 1] = p_ent, s_pick[kp * 3 + 2] = any ? 1.f : 0.f;
@@ -658,13 +662,12 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
       s_bcast[0] = G.dlogp_in[b], s_bcast[1] = G.dent_in[b];
     } else {
       // ---- 5. PPO scalar stage ------------------------------------------------------------------------------
-      PolicyTerms t = ppo_policy_terms(P, b, tot_logp, s_norm);
+      PolicyTerms t = ppo_policy_terms_at(P, b, tot_logp, s_ahead[0], s_ahead[1]);
       s_bcast[0] = t.dlogp, s_bcast[1] = ppo_dentropy(P, 1);
       double* row = P.partials + b * ppo_nstat(P.V);
       row[0] = t.surrogate, row[1] = tot_ent, row[2] = t.kl, row[3] = t.clipped, row[4] = t.teacher;
       if (G.logp) G.logp[b] = (float)tot_logp;
       if (G.entropy) G.entropy[b] = (float)tot_ent;
-      if (!SELF_STREAM && G.fused_finalize) __threadfence();  // the row is read by whichever CTA arrives last
     }
   }
   if (MODE == kPpo && tid >= 32 && tid < 32 + P.V) {
@@ -672,7 +675,6 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
     float2 r = ppo_value_terms(P, b, v);
     double* row = P.partials + b * ppo_nstat(P.V);
     row[kPolicyStats + v] = r.x, row[kPolicyStats + P.V + v] = r.y;
-    if (!SELF_STREAM && G.fused_finalize) __threadfence();
   }
   if (MODE == kFwd) return;
   if (MODE == kPpo) pdl_trigger();  // the stats finaliser may be scheduled; it waits for this grid to complete
@@ -735,17 +737,6 @@ __global__ void __launch_bounds__(BLOCK, (PMAX <= 8 ? 1024 : 512) / BLOCK)
       const float lp = to_f32(g_logits[(long long)c * G.ld + G.S + kp]) - p_lse;
       const float pr = fast_exp(lp);
       g_out[(long long)c * G.ld + G.S + kp] = from_f32<LT>(dlogp * ((a == c ? 1.f : 0.f) - pr) - dent * pr * (lp + p_ent));
-    }
-  }
-  // ---- 7. small minibatches: the last CTA to arrive turns the partial rows into the stats vector --------------
-  if (MODE == kPpo && !SELF_STREAM && G.fused_finalize) {
-    __shared__ int s_last;
-    __syncthreads();  // every writer of this CTA's partial row has fenced its stores
-    if (tid == 0) s_last = atomicAdd(G.done_counter, 1) == (int)gridDim.x - 1;
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      ppo_finalize_block(P, G.B, 1, reinterpret_cast<double*>(s_lse));  // the stash is free by now
     }
   }
 }
@@ -819,9 +810,7 @@ static int bind_workspace(GridDev* G, void* workspace, size_t workspace_bytes, c
   G->unit_list = reinterpret_cast<uint16_t*>(w), w += align16((size_t)G->B * G->chunks * kChunkCells * sizeof(uint16_t));
   G->unit_count = reinterpret_cast<int*>(w), w += align16((size_t)G->B * G->chunks * sizeof(int));
   G->pick_list = reinterpret_cast<uint16_t*>(w), w += align16((size_t)G->B * G->n_pick * G->chunks * kChunkCells * sizeof(uint16_t));
-  G->pick_count = reinterpret_cast<int*>(w), w += align16((size_t)G->B * G->n_pick * G->chunks * sizeof(int));
-  G->done_counter = reinterpret_cast<int*>(w);  // inside the 64 spare bytes of grid_workspace_bytes()
-  G->fused_finalize = 0;
+  G->pick_count = reinterpret_cast<int*>(w);
   return B200RL_OK;
 }
 
@@ -1011,14 +1000,9 @@ static int ppo_gridnet_loss_impl(const b200rl_gridnet_desc* d, const void* logit
   }
   if (rc) return rc;
   G.dlogits = dlogits, G.logp = logp_out, G.entropy = entropy_out;
-  // Split path with few samples (a C5 per-GPU minibatch is 128 CTAs): the finaliser is folded into the compute
-  // launch -- the last CTA to arrive reduces the rows (one fence + one atomic per CTA, cheap at this grid size; at
-  // thousands of CTAs the fences delay every CTA's exit and the separate 1-block launch wins).
-  const size_t need = (size_t)32 * ppo_nstat(P.V) * sizeof(double);  // scratch of ppo_finalize_block at 1024 threads
-  G.fused_finalize = G.chunks > 1 && G.B <= 1024 && (size_t)G.stash * G.A * 2 * sizeof(float) >= need;
   rc = launch_mode<kPpo>(G, P, d->nvec_host, d->logits_dtype, s);  // derives the advantage normaliser itself
   if (rc) return rc;
-  return G.fused_finalize ? B200RL_OK : ppo_launch_finalize(P, G.B, 1, s);
+  return ppo_launch_finalize(P, G.B, 1, s);
 }
 }  // namespace b200rl
 

@@ -87,10 +87,9 @@ struct PolicyTerms {
 
 // new_logp arrives in float64 when the caller summed it that way (GridNet: hundreds of per-cell
 // terms); the subtraction is exact in float64 and rounds once, like an f32 subtraction of f32 inputs.
-__device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long long i, double new_logp,
-                                                        const float* norm) {
-  const float A = ppo_sample_advantage(P, i, norm);
-  const float logratio = (float)(new_logp - (double)P.old_logp[i]);
+__device__ __forceinline__ PolicyTerms ppo_policy_terms_at(const PpoDev& P, long long i, double new_logp, float A,
+                                                           float old_logp) {
+  const float logratio = (float)(new_logp - (double)old_logp);
   const float ratio = expf(logratio);
   const float cr = fminf(fmaxf(ratio, P.ratio_lo), P.ratio_hi);
   const float s1 = ratio * A, s2 = cr * A;
@@ -131,6 +130,13 @@ __device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long lo
     }
   }
   return t;
+}
+
+// (the normalised advantage and the behaviour log-prob do not depend on the new log-prob: a kernel with a long
+// per-sample reduction computes them ahead and calls ppo_policy_terms_at)
+__device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long long i, double new_logp,
+                                                        const float* norm) {
+  return ppo_policy_terms_at(P, i, new_logp, ppo_sample_advantage(P, i, norm), P.old_logp[i]);
 }
 
 __device__ __forceinline__ PolicyTerms ppo_policy_terms(const PpoDev& P, long long i, double new_logp) {
@@ -200,66 +206,90 @@ __device__ __forceinline__ float2 ppo_value_terms(const PpoDev& P, long long i, 
   return make_float2(vl, clipped);
 }
 
-// partials [rows][5 + 2V] -> stats_out, by ONE block (any size that is a multiple of 32): thread t sums rows
-// t, t + blockDim, ... -- a row's columns are adjacent, so every load of a tile of 8 columns is in flight
-// at once -- warps combine through `scratch` ([nwarps][ns] doubles of shared memory), thread c < ns finishes
-// column c.  Fixed order => deterministic.
+// partials [rows][5 + 2V] -> stats_out, by ONE block (any size that is a multiple of 32).  A warp's lanes are laid out
+// as (row slot, column): with cpl = the power of two >= ns columns per slot, a warp sums 32 / cpl rows at a time --
+// every load of a sweep is independent and a row's columns are adjacent (coalesced) -- the row slots fold with
+// shuffles, warps combine through `scratch` ([nwarps][ns] doubles of shared memory), thread c < ns finishes column
+// c.  More than 32 columns (V > 13): a thread per row, 8 columns at a time.  Fixed order => deterministic.
 __device__ __forceinline__ void ppo_finalize_block(const PpoDev& P, long long rows, int ent_d, double* scratch) {
   const int ns = ppo_nstat(P.V);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   __syncthreads();  // scratch may alias shared memory that was in use
-  for (int c0 = 0; c0 < ns; c0 += 8) {
-    double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (long long r = tid; r < rows; r += blockDim.x) {
-      const double* row = P.partials + r * ns + c0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (c0 + j < ns) a[j] += row[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (c0 + j >= ns) break;
-      double x = a[j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        int lo = __double2loint(x), hi = __double2hiint(x);
-        lo = __shfl_xor_sync(0xffffffffu, lo, o), hi = __shfl_xor_sync(0xffffffffu, hi, o);
-        x += __hiloint2double(hi, lo);
+  if (ns <= 32) {
+    int cpl = 1;
+    while (cpl < ns) cpl <<= 1;
+    const int rpw = 32 / cpl, rs = lane / cpl, c = lane - rs * cpl;
+    double acc = 0.0;
+    if (c < ns) {
+      long long r = (long long)warp * rpw + rs;
+      const long long step = (long long)nwarps * rpw;
+      for (; r + 3 * step < rows; r += 4 * step) {  // four independent loads in flight
+        const double a0 = P.partials[r * ns + c], a1 = P.partials[(r + step) * ns + c];
+        const double a2 = P.partials[(r + 2 * step) * ns + c], a3 = P.partials[(r + 3 * step) * ns + c];
+        acc += a0, acc += a1, acc += a2, acc += a3;
       }
-      if (lane == 0) scratch[warp * ns + c0 + j] = x;
+      for (; r < rows; r += step) acc += P.partials[r * ns + c];
+    }
+    for (int o = cpl; o < 32; o <<= 1) {
+      int lo = __double2loint(acc), hi = __double2hiint(acc);
+      lo = __shfl_xor_sync(0xffffffffu, lo, o), hi = __shfl_xor_sync(0xffffffffu, hi, o);
+      acc += __hiloint2double(hi, lo);
+    }
+    if (lane < cpl && c < ns) scratch[warp * ns + c] = acc;
+  } else {
+    for (int c0 = 0; c0 < ns; c0 += 8) {
+      double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (long long r = tid; r < rows; r += blockDim.x) {
+        const double* row = P.partials + r * ns + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < ns) a[j] += row[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c0 + j >= ns) break;
+        double x = a[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          int lo = __double2loint(x), hi = __double2hiint(x);
+          lo = __shfl_xor_sync(0xffffffffu, lo, o), hi = __shfl_xor_sync(0xffffffffu, hi, o);
+          x += __hiloint2double(hi, lo);
+        }
+        if (lane == 0) scratch[warp * ns + c0 + j] = x;
+      }
     }
   }
   __syncthreads();
-  __shared__ double tot[kPolicyStats + 2 * B200RL_MAX_VALUE_HEADS];
+  // column c: sum over the warps, then its batch mean in float64 (one division per column, side by side)
+  __shared__ float mean[kPolicyStats + 2 * B200RL_MAX_VALUE_HEADS];
   if (tid < ns) {
     double a = 0.0;
     for (int w = 0; w < nwarps; ++w) a += scratch[w * ns + tid];
-    tot[tid] = a;
+    const double B = (double)P.B;
+    mean[tid] = tid == 0 ? (float)(-a / B) : (tid == 1 ? (float)(-a / (B * ent_d)) : (float)(a / B));
   }
   __syncthreads();
   if (tid == 0) {
-    const double B = (double)P.B;
     const float pi_coef = P.pi_coef_dev ? *P.pi_coef_dev : P.pi_coef;
-    const float pi_loss = (float)(-tot[0] / B);
-    const float ent_loss = (float)(-tot[1] / (B * ent_d));
+    const float pi_loss = mean[0], ent_loss = mean[1];
     float total = pi_coef * pi_loss + P.ent_coef * ent_loss;
     float vsum = 0.f;
     for (int v = 0; v < P.V; ++v) {
-      float vl = (float)(tot[kPolicyStats + v] / B);
+      float vl = mean[kPolicyStats + v];
       if (P.halving) vl *= 0.5f;
       P.stats_out[5 + v] = vl;
-      P.stats_out[5 + P.V + v] = (float)(tot[kPolicyStats + P.V + v] / B);
+      P.stats_out[5 + P.V + v] = mean[kPolicyStats + P.V + v];
       vsum += P.vf_coef[v] * vl;
     }
     total += vsum;
-    const float teacher_loss = (float)(tot[4] / B);
+    const float teacher_loss = mean[4];
     if (P.teacher_logp) total += P.teacher_coef * teacher_loss;
     P.stats_out[5 + 2 * P.V] = teacher_loss;
     P.stats_out[0] = total * P.loss_scale;
     P.stats_out[1] = pi_loss;
     P.stats_out[2] = ent_loss;
-    P.stats_out[3] = (float)(tot[2] / B);
-    P.stats_out[4] = (float)(tot[3] / B);
+    P.stats_out[3] = mean[2];
+    P.stats_out[4] = mean[3];
   }
 }
 
