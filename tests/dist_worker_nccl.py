@@ -9,8 +9,10 @@ exactly the union of the ranks' minibatches.  Three runs per rank:
   C  single process (data_parallel=False) on     all-reduces between the replays)
      the concatenated rollout, batch R x B
 Bars: all-reduced moments == moments of the concatenated minibatch (1e-14: f64 sums in a different order); gradient of
-the first minibatch 1e-5 of each tensor's largest entry; final parameters RMS error <= 1 % of the RMS update (Adam's
-sign-like step amplifies rounding on near-zero gradients); B == A to 1e-6 of the update.
+the first minibatch 1e-5 of each tensor's largest entry; final parameters (A vs C, and B vs A: cuDNN picks other
+algorithms under capture, so the two data-parallel runs agree to rounding, not to the bit) RMS error <= 1 % of the RMS
+update -- Adam's sign-like step amplifies rounding on near-zero gradients, while a missing or misplaced all-reduce
+would show as O(100 %) -- and the last epoch's losses within 1e-3.
 """
 import copy
 import json
@@ -108,10 +110,11 @@ def main():
         algo._clip_and_step = spy
         algo.learn_epoch(0, 1 << 30, Gen(ro, orders, n_envs), None)
         torch.cuda.synchronize()
+        algo.graphed_used = bool(algo._update_graphs)
         return policy, first, algo
 
     pol_a, grads_a, algo_a = run(False, True, mine, mine["idx"], N, B)
-    pol_b, _, _ = run(True, True, mine, mine["idx"], N, B)
+    pol_b, _, algo_b = run(True, True, mine, mine["idx"], N, B)
 
     # ---- C: the concatenated problem, single process --------------------------------------------------------------
     cat = {}
@@ -162,8 +165,23 @@ def main():
 
     report["params_dp_vs_single"], good = param_check(pol_a, pol_c, 1e-2)
     ok &= good
-    report["params_graphed_vs_eager"], good = param_check(pol_b, pol_a, 1e-6)
+    report["params_graphed_vs_eager"], good = param_check(pol_b, pol_a, 1e-2)
     ok &= good
+    report["graphed_path_used"] = algo_b.graphed_used and not algo_a.graphed_used
+    ok &= report["graphed_path_used"]
+    sa, sb, sc = algo_a.last_train_stats, algo_b.last_train_stats, algo_c.last_train_stats
+    # the data-parallel stats are this rank's local means; their average over the ranks is the global minibatch's
+    def mean_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return (t / world).item()
+    worst = 0.0
+    for k in ("loss", "pi_loss", "entropy_loss", "approx_kl"):
+        for s_dp in (sa, sb):
+            got, want = mean_over_ranks(getattr(s_dp, k)), getattr(sc, k)
+            worst = max(worst, abs(got - want) / max(abs(want), 1e-2))
+    report["stats_rel"] = worst
+    ok &= worst <= 1e-3
     # replicas stay identical across ranks
     flat = torch.cat([p.detach().reshape(-1) for p in pol_a.parameters()])
     ref = flat.clone()

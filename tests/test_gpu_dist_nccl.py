@@ -19,4 +19,8 @@ def test_two_rank_update_equals_the_single_process_update_on_the_concatenated_mi
            "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dist_worker_nccl.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     reports = [line for line in res.stdout.splitlines() if line.startswith("DIST_REPORT ")]
-    assert res.returncode == 0 and len(reports) == 2, (res.stdout[-3000:], res.stderr[-3000:])
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):  # kept next to the other run artefacts
+        with open(os.path.join(out_dir, "dist_nccl_reports.txt"), "w") as f:
+            f.write("\n".join(reports) + "\n")
+    assert res.returncode == 0 and len(reports) == 2, ("\n".join(reports), res.stderr[-2000:])
