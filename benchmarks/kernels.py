@@ -95,6 +95,61 @@ def bench_gae(T, N, V):
                 gbs=nbytes / med / 1e6, frac=nbytes / med / 1e6 / peak_gbs())
 
 
+def bench_gae_segments(n_seg, mean_len, V, skips=False):
+    """K1b: ragged trajectories concatenated along axis 0 (rollout/trajectory.py, discrete_skips_trajectory_builder.py)."""
+    dev = "cuda"
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(max(1, mean_len // 2), mean_len * 3 // 2 + 1, (n_seg,), generator=g)
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(lens, 0)]).to(dev)
+    total = int(offsets[-1].item())
+    shape = (total,) if V == 1 else (total, V)
+    r, v = torch.randn(shape, device=dev), torch.randn(shape, device=dev)
+    nes = torch.rand(n_seg, device=dev) < 0.5
+    nv = torch.randn((n_seg,) if V == 1 else (n_seg, V), device=dev)
+    gamma = 0.99 if V == 1 else np.full(V, 0.99)
+    lam = 0.95 if V == 1 else np.full(V, 0.95)
+    kw = (dict(steps_elapsed=torch.randint(1, 5, (total,), device=dev, dtype=torch.int32)) if skips
+          else dict(episode_starts=torch.rand(total, device=dev) < 0.02))
+    fn = lambda: ops.gae_segments(r, v, offsets, nes, nv, gamma, lam, **kw)
+    med, best = time_kernel(fn, 'b200rl_gae_segments_f32', flush=False)
+    nbytes = total * (16 * V + (4 if skips else 1))
+    return dict(kernel="gae_segments" + ("_skips" if skips else ""), segments=n_seg, steps=total, V=V, ms_median=med,
+                ms_best=best, bytes=nbytes, gbs=nbytes / med / 1e6, frac=nbytes / med / 1e6 / peak_gbs())
+
+
+def bench_small(name):
+    """K6 / K7: per-env-step kernels (launch-bound by construction: one env step's [N, D] at a time)."""
+    dev = "cuda"
+    if name == "norm_obs":
+        N, D = 4096, 17
+        x = torch.randn(N, D, device=dev)
+        st = [torch.zeros(D, dtype=torch.float64, device=dev), torch.ones(D, dtype=torch.float64, device=dev),
+              torch.full((D,), 1e-4, dtype=torch.float64, device=dev)]
+        out = torch.empty_like(x)
+        fn = lambda: ops.running_norm_obs(x, *st, True, 1e-8, 10.0, out)
+        nbytes, cname = 2 * x.numel() * 4, "b200rl_running_norm_obs_f32"
+    elif name == "norm_reward":
+        N, V = 1024, 13
+        r = torch.randn(N, V, device=dev)
+        d = torch.rand(N, device=dev) < 0.01
+        ret = torch.zeros(N, V, dtype=torch.float64, device=dev)
+        st = [torch.zeros(V, dtype=torch.float64, device=dev), torch.ones(V, dtype=torch.float64, device=dev),
+              torch.full((V,), 1e-4, dtype=torch.float64, device=dev)]
+        out = torch.empty_like(r)
+        fn = lambda: ops.running_norm_reward(r, d, ret, *st, 0.99, True, 1e-8, 10.0, out)
+        nbytes, cname = r.numel() * (4 + 4 + 16) + N, "b200rl_running_norm_reward_f32"
+    else:
+        N, K = 1024, 12
+        base = torch.randn(N, device=dev)
+        series = [torch.randn(N, device=dev) for _ in range(K)]
+        term, trunc = torch.rand(N, device=dev) < 0.01, torch.zeros(N, dtype=torch.bool, device=dev)
+        out = torch.empty(N, 1 + K, device=dev)
+        fn = lambda: ops.reward_assemble(base, series, term, trunc, [False] * (K - 1) + [True], [1.0] * (K - 1) + [0.001], out)
+        nbytes, cname = N * (1 + K) * 8 + 2 * N, "b200rl_reward_assemble_f32"
+    med, best = time_kernel(fn, cname, flush=False)
+    return dict(kernel=name, ms_median=med, ms_best=best, bytes=nbytes, gbs=nbytes / med / 1e6, note="launch-bound by construction")
+
+
 def gridnet_tensors(B, HW, nvec, n_pick, unit_p, dtype=torch.float32, act_dtype=torch.uint8):
     dev = "cuda"
     S, A = sum(nvec), len(nvec)
@@ -161,6 +216,20 @@ def main():
     if a.what in ("gae", "all"):
         for T, N, V in [(32, 8, 1), (128, 8, 1), (64, 4096, 1), (512, 24, 1), (32, 1024, 13), (128, 1 << 20, 1),
                         (32, 131072, 13)]:
+            rows.append(bench_gae(T, N, V))
+            print(json.dumps(rows[-1]), flush=True)
+    if a.what in ("gae", "gae_small", "all"):
+        rows.append(bench_gae_segments(24, 512, 1))
+        print(json.dumps(rows[-1]), flush=True)
+        rows.append(bench_gae_segments(2048, 32, 13))
+        print(json.dumps(rows[-1]), flush=True)
+        rows.append(bench_gae_segments(2048, 32, 1, skips=True))
+        print(json.dumps(rows[-1]), flush=True)
+        for name in ("norm_obs", "norm_reward", "reward_assemble"):
+            rows.append(bench_small(name))
+            print(json.dumps(rows[-1]), flush=True)
+    if a.what == "gae_small":
+        for T, N, V in [(32, 8, 1), (128, 8, 1), (64, 4096, 1), (512, 24, 1), (32, 1024, 13), (2048, 24, 1), (512, 4096, 1)]:
             rows.append(bench_gae(T, N, V))
             print(json.dumps(rows[-1]), flush=True)
     if a.what in ("loss", "all"):

@@ -160,6 +160,98 @@ __global__ void __launch_bounds__(128, MIN_CTAS) gae_scan_kernel(const __grid_co
   }
 }
 
+// ---- K1, cooperative form for rollouts that do not fill the machine -----------------------------------
+// At the config shapes (T=512 x 24 lanes, T=64 x 4096, T=32 x 13,312) the lane-per-thread scan above is a chain of
+// T / 4 dependent global round trips per thread -- 135 us at T=512 -- although only TWO operations per step actually
+// depend on the previous step: carry = delta_t + c_t * carry.  delta_t = r_t + gamma v_{t+1} alive_{t+1} - v_t and
+// c_t = gamma lambda alive_{t+1} depend on the inputs alone.  So a CTA takes VEC adjacent lanes and
+//   1. all its threads compute (delta_t, c_t) for a chunk of time steps side by side, in float64, into shared memory
+//      (every global load independent of every other);
+//   2. VEC threads walk the chunk backwards out of shared memory: two dependent float64 operations per step;
+//   3. all threads store advantages / returns of the chunk.
+// Same operations in the same order per lane as the reference loop, so it stays BIT-EXACT -- nothing is
+// re-associated (a parallel affine scan would have to be, and would only meet 1e-5).
+constexpr int kCoopBlock = 128;
+constexpr int kCoopChunk = 512;  // time steps per chunk: VEC * 512 * (8 + 8 + 4 + 4) bytes = 48 KB at VEC = 4
+
+template <int VEC, bool V1>
+__global__ void __launch_bounds__(kCoopBlock) gae_coop_kernel(const __grid_constant__ GaeParams p) {
+  __shared__ double s_delta[kCoopChunk * VEC];
+  __shared__ double s_c[kCoopChunk * VEC];
+  __shared__ float s_v[kCoopChunk * VEC];
+  __shared__ float s_adv[kCoopChunk * VEC];
+  const int tid = threadIdx.x;
+  const long long lane0 = (long long)blockIdx.x * VEC;
+  LaneEnvs envs{(int)lane0, (int)lane0, 0u, 0u};
+  uint32_t heads = 0u;
+  if (!V1) {
+    envs.lo = (int)(lane0 / p.V), envs.hi = (int)((lane0 + VEC - 1) / p.V);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int e = (int)((lane0 + i) / p.V);
+      heads |= (uint32_t)((lane0 + i) - (long long)e * p.V) << (8 * i);
+      if (e == envs.lo) envs.pat_lo |= 1u << (8 * i);
+      else envs.pat_hi |= 1u << (8 * i);
+    }
+  }
+  const bool scalar_gamma = p.gamma_is_scalar != 0;
+  double carry = 0.0;  // threads 0 .. VEC-1: the lane's running advantage
+  for (long long hi = p.T; hi > 0; hi -= kCoopChunk) {
+    const long long lo = hi > kCoopChunk ? hi - kCoopChunk : 0;
+    // 1. (delta, c) of every step of the chunk, side by side
+    for (long long t = lo + tid; t < hi; t += kCoopBlock) {
+      const Lanes<VEC> r = load_lanes<VEC>(p.rewards + t * p.L + lane0);
+      const Lanes<VEC> v = load_lanes<VEC>(p.values + t * p.L + lane0);
+      const bool last = t + 1 == p.T;
+      const Lanes<VEC> vn = load_lanes<VEC>(last ? p.next_values + lane0 : p.values + (t + 1) * p.L + lane0);
+      const uint32_t started_next = load_starts<VEC, V1>(last ? p.next_episode_starts : p.episode_starts + (t + 1) * p.N, envs);
+      const int row = (int)(t - lo) * VEC;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const double alive = ((started_next >> (8 * i)) & 0xffu) ? 0.0 : 1.0;  // 1.0 - episode_starts[t+1]
+        const int h = V1 ? 0 : (int)((heads >> (8 * i)) & 0xffu);
+        const double g = p.gamma[h], gl = p.gamma_lambda[h];
+        const double boot = scalar_gamma ? __dmul_rn((double)__fmul_rn((float)g, vn.x[i]), alive)
+                                         : __dmul_rn(__dmul_rn(g, (double)vn.x[i]), alive);
+        s_delta[row + i] = __dsub_rn(__dadd_rn((double)r.x[i], boot), (double)v.x[i]);
+        s_c[row + i] = __dmul_rn(gl, alive);
+        s_v[row + i] = v.x[i];
+      }
+    }
+    __syncthreads();
+    // 2. the recurrence: one thread per lane, operands from shared memory, eight steps' loads ahead of their use
+    if (tid < VEC && lane0 + tid < p.L) {
+      int k = (int)(hi - lo) - 1;
+      for (; k >= 7; k -= 8) {
+        double d[8], c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = s_delta[(k - u) * VEC + tid], c[u] = s_c[(k - u) * VEC + tid];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          carry = __dadd_rn(d[u], __dmul_rn(c[u], carry));
+          s_adv[(k - u) * VEC + tid] = __double2float_rn(carry);
+        }
+      }
+      for (; k >= 0; --k) {
+        carry = __dadd_rn(s_delta[k * VEC + tid], __dmul_rn(s_c[k * VEC + tid], carry));
+        s_adv[k * VEC + tid] = __double2float_rn(carry);
+      }
+    }
+    __syncthreads();
+    // 3. stores
+    for (long long t = lo + tid; t < hi; t += kCoopBlock) {
+      const int row = (int)(t - lo) * VEC;
+      Lanes<VEC> adv, ret;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) adv.x[i] = s_adv[row + i], ret.x[i] = __fadd_rn(adv.x[i], s_v[row + i]);
+      if (VEC == 1 && lane0 >= p.L) break;
+      store_lanes<VEC>(p.advantages + t * p.L + lane0, adv);
+      if (p.returns) store_lanes<VEC>(p.returns + t * p.L + lane0, ret);
+    }
+    __syncthreads();  // the next chunk overwrites the shared arrays
+  }
+}
+
 template <int VEC, bool V1>
 static int launch(const GaeParams& p, cudaStream_t stream) {
   const long long groups = (p.L + VEC - 1) / VEC;
@@ -169,11 +261,13 @@ static int launch(const GaeParams& p, cudaStream_t stream) {
     set_error("gae_scan: too many lanes (%lld)", p.L);
     return B200RL_EUNSUPPORTED;
   }
-  // A rollout that fills the machine (>= 8 CTAs on every SM) runs the occupancy-first configuration; smaller
-  // ones are a serial chain of dependent round trips per thread and measured best with 4 steps in flight
-  // (T=512, N=24: 145 us against 173-207 us for 2, 8 or 16).
+  // A rollout that fills the machine (>= 8 CTAs on every SM) streams at the HBM roofline with the lane-per-thread
+  // scan (occupancy-first configuration).  Smaller ones are latency-bound there (a serial chain of dependent global
+  // round trips per thread): they take the cooperative form, as long as the problem is small enough to sit in L2.
   const long long full = (long long)device_info().sm_count * 8 * block;
+  const long long bytes = p.T * p.L * 17;
   if (groups >= full) gae_scan_kernel<VEC, V1, 2, 8><<<(unsigned)grid, block, 0, stream>>>(p);
+  else if (bytes <= (64ll << 20) && groups <= 0x7fffffffLL) gae_coop_kernel<VEC, V1><<<(unsigned)groups, kCoopBlock, 0, stream>>>(p);
   else gae_scan_kernel<VEC, V1, 4, 4><<<(unsigned)grid, block, 0, stream>>>(p);
   return check_launch("gae_scan");
 }
@@ -219,7 +313,7 @@ extern "C" int b200rl_gae_scan_f32(const float* rewards, const float* values, co
 // episode start of step t+1 is dones[t], the step after the last one uses dones[-1] / next_values)
 // and DiscreteSkipsTrajectoryBuilder.trajectory (rollout/discrete_skips_trajectory_builder.py:84-100:
 // delta = r + gamma^k v' - v, adv = delta + gamma^k lambda adv', k = steps_elapsed[t]).
-// Segments are concatenated along the first axis; one thread walks one (segment, value head) lane.
+// Segments are concatenated along the first axis; one CTA takes one segment.
 namespace b200rl {
 
 struct SegParams {
@@ -237,40 +331,68 @@ struct SegParams {
   double gamma[B200RL_MAX_VALUE_HEADS], lambda[B200RL_MAX_VALUE_HEADS];
 };
 
-__global__ void __launch_bounds__(128) gae_segments_kernel(const SegParams p) {
-  const long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane >= p.n_seg * p.V) return;
-  const long long seg = lane / p.V;
-  const int h = (int)(lane - seg * p.V);
+// One CTA per trajectory, same three phases as gae_coop_kernel: (delta, c) of a chunk of steps for every value head side
+// by side (rows [t, V] are contiguous: coalesced; the discrete-skips gamma ** k -- a float64 pow -- is computed here, in
+// parallel), then one thread per head runs the two-operation recurrence out of shared memory, then all threads store.
+// A thread per (trajectory, head) walking global memory step by step, as before, is a chain of dependent round trips
+// with strided, uncoalesced accesses.
+constexpr int kSegBlock = 128;
+constexpr int kSegEntries = 2048;  // (step, head) pairs per chunk: 2048 * (8 + 8 + 4 + 4) bytes = 48 KB
+
+__global__ void __launch_bounds__(kSegBlock) gae_segments_kernel(const __grid_constant__ SegParams p) {
+  __shared__ double s_delta[kSegEntries];
+  __shared__ double s_c[kSegEntries];
+  __shared__ float s_v[kSegEntries];
+  __shared__ float s_adv[kSegEntries];
+  const int tid = threadIdx.x;
+  const long long seg = blockIdx.x;
+  const int V = (int)p.V;
   const long long begin = p.offsets[seg], end = p.offsets[seg + 1];
-  const double g = p.gamma[h], lam = p.lambda[h], gl = __dmul_rn(g, lam);
   const bool skips = p.steps_elapsed != nullptr;
-  double carry = 0.0;
-  float v_next = p.next_values[seg * p.V + h];
-  bool start_next = p.next_starts[seg] != 0;
-  for (long long t = end - 1; t >= begin; --t) {
-    const float r = p.rewards[t * p.V + h], v = p.values[t * p.V + h];
-    double adv;
-    if (skips) {
-      // the step after a finished trajectory has value 0; every product is float64 (numpy scalar gamma^k)
-      const double gk = pow(g, (double)p.steps_elapsed[t]);
-      const double nv = (t == end - 1 && start_next) ? 0.0 : (double)v_next;
-      const double delta = __dsub_rn(__dadd_rn((double)r, __dmul_rn(gk, nv)), (double)v);
-      carry = __dadd_rn(delta, __dmul_rn(__dmul_rn(gk, lam), carry));
-      adv = carry;
-    } else {
-      const double alive = start_next ? 0.0 : 1.0;
-      const double boot = p.gamma_is_scalar ? __dmul_rn((double)__fmul_rn((float)g, v_next), alive)
-                                            : __dmul_rn(__dmul_rn(g, (double)v_next), alive);
-      const double delta = __dsub_rn(__dadd_rn((double)r, boot), (double)v);
-      carry = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, alive), carry));
-      adv = carry;
-      start_next = p.episode_starts[t] != 0;
+  const bool seg_start_next = p.next_starts[seg] != 0;
+  const int chunk = kSegEntries / V;  // steps per chunk
+  double carry = 0.0;                 // threads 0 .. V-1
+  for (long long hi = end; hi > begin; hi -= chunk) {
+    const long long lo = hi - begin > chunk ? hi - chunk : begin;
+    const int n = (int)(hi - lo) * V;
+    for (int e = tid; e < n; e += kSegBlock) {
+      const long long t = lo + e / V;
+      const int h = e - (int)(t - lo) * V;
+      const float r = p.rewards[t * V + h], v = p.values[t * V + h];
+      const bool last = t == end - 1;
+      const float v_next = last ? p.next_values[seg * V + h] : p.values[(t + 1) * V + h];
+      const double g = p.gamma[h], lam = p.lambda[h];
+      double delta, c;
+      if (skips) {
+        // the step after a finished trajectory has value 0; every product is float64 (numpy scalar gamma^k)
+        const double gk = pow(g, (double)p.steps_elapsed[t]);
+        const double nv = (last && seg_start_next) ? 0.0 : (double)v_next;
+        delta = __dsub_rn(__dadd_rn((double)r, __dmul_rn(gk, nv)), (double)v);
+        c = __dmul_rn(gk, lam);
+      } else {
+        const bool start_next = last ? seg_start_next : p.episode_starts[t + 1] != 0;
+        const double alive = start_next ? 0.0 : 1.0;
+        const double boot = p.gamma_is_scalar ? __dmul_rn((double)__fmul_rn((float)g, v_next), alive)
+                                              : __dmul_rn(__dmul_rn(g, (double)v_next), alive);
+        delta = __dsub_rn(__dadd_rn((double)r, boot), (double)v);
+        c = __dmul_rn(__dmul_rn(g, lam), alive);
+      }
+      s_delta[e] = delta, s_c[e] = c, s_v[e] = v;
     }
-    const float a32 = __double2float_rn(adv);
-    p.advantages[t * p.V + h] = a32;
-    if (p.returns) p.returns[t * p.V + h] = __fadd_rn(a32, v);
-    v_next = v;
+    __syncthreads();
+    if (tid < V) {
+      for (int k = (int)(hi - lo) - 1; k >= 0; --k) {
+        carry = __dadd_rn(s_delta[k * V + tid], __dmul_rn(s_c[k * V + tid], carry));
+        s_adv[k * V + tid] = __double2float_rn(carry);
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < n; e += kSegBlock) {
+      const float a32 = s_adv[e];
+      p.advantages[lo * V + e] = a32;
+      if (p.returns) p.returns[lo * V + e] = __fadd_rn(a32, s_v[e]);
+    }
+    __syncthreads();
   }
 }
 
@@ -296,7 +418,7 @@ extern "C" int b200rl_gae_segments_f32(const float* rewards, const float* values
   p.next_values = next_values, p.advantages = advantages, p.returns = returns;
   p.n_seg = n_segments, p.V = V, p.gamma_is_scalar = gamma_is_scalar;
   for (int v = 0; v < V; ++v) p.gamma[v] = gamma_host[v], p.lambda[v] = gae_lambda_host[v];
-  const long long lanes = n_segments * V;
-  gae_segments_kernel<<<(unsigned)((lanes + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+  B200RL_UNSUPPORTED(n_segments > 0x7fffffffLL, "gae_segments: %lld trajectories in one call", (long long)n_segments);
+  gae_segments_kernel<<<(unsigned)n_segments, kSegBlock, 0, (cudaStream_t)stream>>>(p);
   return check_launch("gae_segments");
 }
