@@ -283,6 +283,19 @@ int b200rl_ppo_gridnet_loss_inplace(const b200rl_gridnet_desc* d, const void* lo
                                     void* rows, size_t rows_bytes, int rows_valid, b200rl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * a3  Batch.num_actions.  Replaces rollout/rollout.py:130-180 (num_actions / per_position_num_actions) over a whole
+ * rollout in one launch (d->B = T * N steps; d->logits_dtype / logits_ld are ignored):
+ *   cells_out[r] = without gates (every gate_ref < 0): the number of cells of step r with any valid mask entry;
+ *                  with gates (a subaction mask is configured): the number of (cell, action plane) pairs with a valid
+ *                  entry, a gated plane counting only where actions[r, cell, gate_ref[h]] == gate_val[h];
+ *   picks_out[r] = the number of cells any pick_position head may choose (n_pick > 0; NULL otherwise) -- the
+ *                  reference adds log(picks) where picks > 0 (rollout.py:143-149), which the caller does.
+ * Exact (integer counts).
+ */
+int b200rl_gridnet_num_actions(const b200rl_gridnet_desc* d, const uint8_t* mask, const uint8_t* pick_mask,
+                               const void* actions, int32_t* cells_out, int32_t* picks_out, b200rl_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * K5  rollout-time sampling: one action per head per cell (+ pick) from the masked logits and
  * its log-prob, in one launch.  Replaces shared/actor/gridnet.py:195-207 (sample) +
  * log_prob at shared/policy/actor_critic.py:311-314.  Gumbel-max over a counter-based RNG

@@ -114,6 +114,7 @@ PROTOTYPES = {
         _int,
         [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, C.POINTER(PpoArgs), _vp, _vp, _vp, _vp, _sz, _vp, _sz, _int, _vp],
     ),
+    "b200rl_gridnet_num_actions": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200rl_gridnet_sample": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
     "b200rl_categorical_sample_f32": (_int, [_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
     "b200rl_running_norm_obs_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _int, C.c_double, C.c_double, _vp, _vp]),

@@ -142,29 +142,31 @@ class GridnetDistribution:
 
 
 def num_actions_device(actions, action_masks, subaction_mask, action_plane_space) -> Optional[torch.Tensor]:
-    """rollout.py:130-180 on device tensors (only built on request; PPO ignores it, ppo.py:300)."""
+    """rollout.py:130-180 over the whole device-resident rollout in ONE launch (ops.gridnet_num_actions; only built on
+    request: PPO ignores the field, ppo.py:300).  Same result types as the reference: an integer count per step, or
+    float32 count + log(#pick cells) for a dict action space."""
     if action_masks is None:
         return None
-    gates = ValueDependentMask.from_reference_index_to_index_to_value(subaction_mask) if subaction_mask else None
-
-    def per_position(acts: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
-        masks = masks.bool()
-        if not gates:
-            return masks.any(dim=-1).sum(dim=-1)
+    cells_mask = action_masks["per_position"] if isinstance(action_masks, dict) else action_masks
+    pick_mask = action_masks.get("pick_position") if isinstance(action_masks, dict) else None
+    cells_act = actions["per_position"] if isinstance(actions, dict) else actions
+    lead = tuple(cells_mask.shape[:-2])  # [T, N] or [M]
+    HW, S = cells_mask.shape[-2], cells_mask.shape[-1]
+    if subaction_mask:
         assert action_plane_space is not None
-        count = torch.zeros(acts.shape[:-2], dtype=torch.int32, device=acts.device)
-        start = 0
-        for h, n in enumerate(int(x) for x in action_plane_space.nvec):
-            m = masks[..., start : start + n]
-            if h in gates:
-                ref, value = gates[h]
-                m = m & (acts[..., ref] == value).unsqueeze(-1)
-            count += m.any(dim=-1).sum(dim=-1).to(torch.int32)
-            start += n
-        return count
-
+        nvec = [int(n) for n in action_plane_space.nvec]
+        gates = subaction_mask if not isinstance(next(iter(subaction_mask.values())), dict) else \
+            ValueDependentMask.from_reference_index_to_index_to_value(subaction_mask)
+    else:
+        nvec, gates = [int(S)], None  # no gating: "any valid entry in the cell" is one plane of S entries
+    n_pick = int(pick_mask.shape[-2]) if pick_mask is not None else 0
+    spec = _spec(nvec, gates, n_pick)
+    R = int(np.prod(lead)) if lead else 1
+    act = cells_act.reshape(R, HW, -1).contiguous() if gates else None
+    cells, picks = ops.gridnet_num_actions(spec, cells_mask.reshape(R, HW, S).contiguous(),
+                                           pick_mask.reshape(R, n_pick, HW).contiguous() if n_pick else None, act)
     if isinstance(action_masks, dict):
-        cells = per_position(actions["per_position"], action_masks["per_position"])
-        picks = action_masks["pick_position"].bool().any(dim=-2).sum(dim=-1)
-        return (cells + torch.where(picks > 0, torch.log(picks.float()), torch.zeros_like(picks, dtype=torch.float32))).float()
-    return per_position(actions, action_masks)
+        p = picks.double()
+        out = (cells.double() + torch.where(p > 0, torch.log(p.clamp_min(1.0)), torch.zeros_like(p))).float()
+        return out.reshape(lead)
+    return (cells if gates else cells.long()).reshape(lead)

@@ -864,6 +864,39 @@ def ppo_gridnet_loss(
     return LossOut(call.stats, call.dvalues, (dlogits,), logp, ent)
 
 
+def gridnet_num_actions(spec: GridnetSpec, mask: torch.Tensor, pick_mask: Optional[torch.Tensor],
+                        actions: Optional[torch.Tensor]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """(cells [R] int32, picks [R] int32 or None) over R steps (rollout.py:130-180): mask [R, HW, S], pick_mask
+    [R, n_pick, HW], actions [R, HW, A] (needed when the spec has gates).  See b200rl.h for what the counts are."""
+    m = _as_u8(mask, "mask")
+    A, S = len(spec.nvec), sum(spec.nvec)
+    R = m.shape[0]
+    HW = m.numel() // max(R * S, 1)
+    if m.numel() != R * HW * S:
+        raise ValueError(f"mask has {m.numel()} elements, not a multiple of sum(nvec) = {S} per step")
+    pm = _as_u8(pick_mask, "pick_mask") if spec.n_pick else None
+    if spec.gates:
+        _cuda(actions, None, "actions")
+        if actions.numel() != R * HW * A:
+            raise ValueError(f"actions has {actions.numel()} elements, expected {R * HW * A}")
+    nvec = (C.c_int32 * A)(*spec.nvec)
+    gate_ref, gate_val = [-1] * A, [0] * A
+    for head, ref, value in spec.gates:
+        gate_ref[head], gate_val[head] = ref, value
+    gref, gval = (C.c_int32 * A)(*gate_ref), (C.c_int32 * A)(*gate_val)
+    d = GridnetDesc()
+    d.B, d.HW, d.A, d.n_pick = R, HW, A, spec.n_pick
+    d.act_dtype = _INDEX_DTYPES[actions.dtype] if (spec.gates and actions is not None) else _lib.U8
+    d.nvec_host, d.gate_ref_host, d.gate_val_host = nvec, gref, gval
+    cells = torch.empty(R, dtype=torch.int32, device=m.device)
+    picks = torch.empty(R, dtype=torch.int32, device=m.device) if spec.n_pick else None
+    if R:
+        rc = _call("b200rl_gridnet_num_actions", 1, _lib.lib().b200rl_gridnet_num_actions, C.byref(d), m.data_ptr(), _ptr(pm),
+                   _ptr(actions) if spec.gates else None, cells.data_ptr(), _ptr(picks), _stream())
+        check(rc, "b200rl_gridnet_num_actions")
+    return cells, picks
+
+
 def gridnet_sample(spec: GridnetSpec, logits, mask, pick_mask, seed: int, offset: int, act_dtype=torch.uint8,
                    offset_dev: Optional[torch.Tensor] = None):
     """Sample per-cell actions (+ pick) and their joint log-prob in one launch (gridnet.py:195-207)."""
