@@ -323,6 +323,7 @@ class PPO(Algorithm):
         self.d2h_bytes_last_epoch = 0
         self.profile_stages = False  # bench.py: CUDA events around rollout / update of the next learn_epoch
         self.stage_ms: Optional[Dict[str, float]] = None
+        self._allreduce_events: List[tuple] = []
 
     # ---------------------------------------------------------------------------------------------
     def learn(self: PPOSelf, train_timesteps: int, rollout_generator, callbacks: Optional[List] = None,
@@ -509,6 +510,7 @@ class PPO(Algorithm):
         if self.profile_stages:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
+            self._allreduce_events = []
         r = rollout_generator.rollout(gamma=self.gamma, gae_lambda=self.gae_lambda)
         if self.teacher_kl_loss_fn is not None:  # ppo.py:259-262
             r.add_to_batch(self.teacher_kl_loss_fn.add_to_batch, rollout_generator.vec_env.num_envs)
@@ -564,6 +566,11 @@ class PPO(Algorithm):
             ev[2].record()
             torch.cuda.synchronize()
             self.stage_ms = {"rollout_and_gae": ev[0].elapsed_time(ev[1]), "update": ev[1].elapsed_time(ev[2])}
+            if self._allreduce_events:  # data-parallel: the in-place gradient all-reduce(s) of this learn_epoch
+                times = [a.elapsed_time(b) for a, b in self._allreduce_events]
+                self.stage_ms["grad_allreduce"] = sum(times)
+                self.stage_ms["grad_allreduce_calls"] = len(times)
+                self.stage_ms["grad_allreduce_bytes"] = self._flat.flat.numel() * self._flat.flat.element_size()
         # one device -> host read for the whole epoch
         exv = r.explained_variance() if hasattr(r, "explained_variance") else None
         packed = torch.stack(step_stats).double()
@@ -663,7 +670,14 @@ class PPO(Algorithm):
         if flat is not None and all(p.grad is v for p, v in zip(flat.params, flat.views)):
             world = self._dp_world()
             if world > 1:  # in place, no flatten / unflatten copies; before the clip, so clipping sees the global gradient
-                dist.all_reduce(flat.flat)
+                if self.profile_stages:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
+                    dist.all_reduce(flat.flat)
+                    ev[1].record()
+                    self._allreduce_events.append(ev)
+                else:
+                    dist.all_reduce(flat.flat)
             return self._clip_and_step(flat, world)
         params = [p for p in self.policy.parameters() if p.grad is not None]
         self._sync_grads(params)
