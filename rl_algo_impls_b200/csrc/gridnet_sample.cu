@@ -44,6 +44,7 @@ struct SampleDev {
   int8_t part_head[32];
   int16_t part_lo[32], part_len[32];
   int8_t part_count[32];  // parts of this slot's head (valid on the head's first slot), 0 on the others
+  int8_t head_first_part[B200RL_MAX_HEADS];  // part slot of each head's first part
   int max_part_count;
 };
 constexpr int kPartEntries = 16;  // a multiple of the 4 entries one Philox block serves
@@ -67,36 +68,33 @@ __device__ __forceinline__ uint64_t stream_id(uint64_t offset, int head, int kbl
 
 __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const SampleDev G) {
   __shared__ float s_red[32];
-  __shared__ float s_best[32];
+  __shared__ float s_best[32], s_xbest[32], s_mx[32], s_sum[32];
   __shared__ long long s_arg[32];
-  __shared__ float s_scalar[2];
   const long long b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t offset = G.offset + (G.offset_dev ? (uint64_t)*G.offset_dev : 0ull);
   float logp_acc = 0.f;
 
   // ---- non-empty cells of this sample -----------------------------------------------------------------
-  extern __shared__ uint16_t s_list[];  // [HW]
-  __shared__ uint32_t s_bitmap[kChunkCells / 32];
-  __shared__ int s_n, s_chunk_n;
+  // ONE scan of the whole sample's mask bytes (independent 128-bit loads, flags into a shared bitmap of HW bits),
+  // one compaction by warp 0: two barriers whatever the map size (was four per chunk of 256 cells)
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_dyn);                                 // [ceil(HW / 32)]
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(s_dyn + (((G.HW + 31) >> 5) << 2));       // [HW]
+  __shared__ int s_n;
   const long long act_bytes = G.HW * G.A * (G.act_dtype == B200RL_U8 ? 1 : (G.act_dtype == B200RL_I32 ? 4 : 8));
+  const int words = (int)((G.HW + 31) >> 5);
+  for (int w = tid; w < words; w += kSampleBlock) s_bitmap[w] = 0u;
   zero_fill<kSampleBlock>(static_cast<uint8_t*>(G.actions_out) + b * act_bytes, (uint32_t)act_bytes);
-  if (tid == 0) s_n = 0;
-  for (long long c0 = 0; c0 < G.HW; c0 += kChunkCells) {
-    const int cells = (int)min((long long)kChunkCells, G.HW - c0);
-    if (tid < kChunkCells / 32) s_bitmap[tid] = 0u;
-    __syncthreads();
-    scan_mask<kSampleBlock>(G.mask + (b * G.HW + c0) * G.S, (uint32_t)cells * (uint32_t)G.S, (uint32_t)G.S, s_bitmap,
-                            RowPrefetch{nullptr, 0u, 0u});
-    __syncthreads();
-    compact_cells(s_bitmap, (cells + 31) >> 5, s_list + s_n, (int)c0, &s_chunk_n);
-    __syncthreads();
-    if (tid == 0) s_n += s_chunk_n;
-    __syncthreads();
-  }
+  __syncthreads();
+  scan_mask<kSampleBlock>(G.mask + b * G.HW * G.S, (uint32_t)G.HW * (uint32_t)G.S, (uint32_t)G.S, s_bitmap,
+                          RowPrefetch{nullptr, 0u, 0u});
+  __syncthreads();
+  compact_cells(s_bitmap, words, s_list, 0, &s_n);
+  __syncthreads();
   const int n_unit = s_n;
 
-  // ---- one thread per (non-empty cell, head): Gumbel-max draw + log-prob in a single pass -----------------
+  // ---- one thread per (non-empty cell, head or part of a head): Gumbel-max draw + log-prob in a single pass ----
   // The pass keeps an online softmax (running max m, sum s of e^(x-m)) next to the running arg-max of
   // x + gumbel, so the chosen entry's log-prob is x_best - (m + log s) without a second sweep.
   __shared__ float s_lp[kStashUnits * B200RL_MAX_HEADS > 8192 ? 8192 : kStashUnits * B200RL_MAX_HEADS];
@@ -106,28 +104,46 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
     float best_score, x_best, mx, sum;
     int best;
   };
-  auto draw_range = [&](long long cell, int h, int k_lo, int k_hi) -> Draw {  // k_lo a multiple of 4
+  // Entries [k_lo, k_hi) of head h of `cell`, kPartEntries at a time: the mask bytes and the logits of a stretch are
+  // loaded first, all independent (a load per valid entry behind its mask test serialised 16 round trips), then
+  // consumed four entries per Philox block.  k_lo is a multiple of 4.
+  auto draw_range = [&](long long cell, int h, int k_lo, int k_hi) -> Draw {
     const int off = G.off[h];
     const long long xbase = cell * G.ld + off;
     const uint8_t* m = G.mask + cell * G.S + off;
     Draw d{-INFINITY, 0.f, -INFINITY, 0.f, 0};
-    for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
-      uint32_t valid = 0;
+#pragma unroll 1
+    for (int c0 = k_lo; c0 < k_hi; c0 += kPartEntries) {
+      const int n = k_hi - c0 < kPartEntries ? k_hi - c0 : kPartEntries;
+      float x[kPartEntries];
+      uint32_t valid = 0u;
+      if (G.logits_dtype == B200RL_BF16) {
+        const __nv_bfloat16* row = static_cast<const __nv_bfloat16*>(G.logits) + xbase + c0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (k0 + j < k_hi && m[k0 + j]) valid |= 1u << j;
-      if (!valid) continue;  // no random numbers spent on masked entries
-      const Philox4 r = philox4x32_10(G.seed, (uint64_t)cell, stream_id(offset, h, k0 >> 2));
-      const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+        for (int j = 0; j < kPartEntries; ++j) x[j] = j < n ? __bfloat162float(row[j]) : 0.f;
+      } else {
+        const float* row = static_cast<const float*>(G.logits) + xbase + c0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (!((valid >> j) & 1u)) continue;
-        const float x = logit_at(G, xbase + k0 + j);
-        const float score = x + gumbel(bits[j]);
-        if (score > d.best_score) d.best_score = score, d.best = k0 + j, d.x_best = x;
-        const float nm = fmaxf(d.mx, x);
-        d.sum = d.sum * __expf(d.mx - nm) + __expf(x - nm);  // exp(-inf) == 0 on the first valid entry
-        d.mx = nm;
+        for (int j = 0; j < kPartEntries; ++j) x[j] = j < n ? row[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kPartEntries; ++j)
+        if (j < n && m[c0 + j]) valid |= 1u << j;
+#pragma unroll
+      for (int q = 0; q < kPartEntries / 4; ++q) {
+        if (!((valid >> (4 * q)) & 15u)) continue;  // no random numbers spent on masked entries
+        const Philox4 r = philox4x32_10(G.seed, (uint64_t)cell, stream_id(offset, h, (c0 >> 2) + q));
+        const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!((valid >> (4 * q + j)) & 1u)) continue;
+          const float xv = x[4 * q + j];
+          const float score = xv + gumbel(bits[j]);
+          if (score > d.best_score) d.best_score = score, d.best = c0 + 4 * q + j, d.x_best = xv;
+          const float nm = fmaxf(d.mx, xv);
+          d.sum = d.sum * __expf(d.mx - nm) + __expf(xv - nm);  // exp(-inf) == 0 on the first valid entry
+          d.mx = nm;
+        }
       }
     }
     return d;
@@ -148,18 +164,21 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
     return finish(draw_range(cell, h, 0, G.nvec[h]), lp_out);
   };
 
-  const int n_stashed = n_unit < stash_units ? n_unit : stash_units;
-  const int n_items = n_stashed * G.A;
   if (G.n_parts > 0) {
     // a warp takes 32 / n_parts cells at a time; lane = (cell slot, part slot); the first lane of a head folds the
-    // partial draws of its other parts in, in entry order, through shuffles (every lane takes part in them)
+    // partial draws of its other parts in, in entry order, through shuffles (every lane takes part in them).  All the
+    // heads of a cell sit in one warp, so a gated head reads its reference head's action through a shuffle too: no
+    // log-prob stash, no second pass.
     const int per_warp = 32 / G.n_parts;
     const int slot = lane / G.n_parts, p = lane - slot * G.n_parts;
     const bool lane_used = slot < per_warp;
     const int h = lane_used ? G.part_head[p] : 0;
-    for (int u0 = warp * per_warp; u0 < n_stashed; u0 += (kSampleBlock / 32) * per_warp) {  // warp-uniform trips
+    const int gr = lane_used ? G.gate_ref[h] : -1;
+    const int gate_val = G.gate_val[h];
+    const int ref_lane = gr >= 0 ? slot * G.n_parts + G.head_first_part[gr] : lane;
+    for (int u0 = warp * per_warp; u0 < n_unit; u0 += (kSampleBlock / 32) * per_warp) {  // warp-uniform trips
       const int u = u0 + slot;
-      const bool live = lane_used && u < n_stashed;
+      const bool live = lane_used && u < n_unit;
       const long long cell = live ? b * G.HW + s_list[u] : 0;
       Draw d{-INFINITY, 0.f, -INFINITY, 0.f, 0};
       if (live) d = draw_range(cell, h, G.part_lo[p], G.part_lo[p] + G.part_len[p]);
@@ -173,14 +192,18 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
         o.best = __shfl_down_sync(0xffffffffu, d.best, q);
         if (q < my_parts) d = merge(d, o);  // only a head's first lane accumulates; it never reads its own merges back
       }
+      int a = 0;
+      float lp = 0.f;
       if (my_parts > 0) {
-        float lp;
-        const int a = finish(d, &lp);
+        a = finish(d, &lp);
         put_index(G.actions_out, G.act_dtype, cell * G.A + h, a);
-        s_lp[u * G.A + h] = lp;
       }
+      const int a_ref = __shfl_sync(0xffffffffu, a, ref_lane);
+      if (my_parts > 0 && (gr < 0 || a_ref == gate_val)) logp_acc += lp;
     }
   } else {
+    const int n_stashed = n_unit < stash_units ? n_unit : stash_units;
+    const int n_items = n_stashed * G.A;
     for (int item = tid; item < n_items; item += kSampleBlock) {
       const int u = item / G.A, h = item - u * G.A;
       const long long cell = b * G.HW + s_list[u];
@@ -189,104 +212,85 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
       put_index(G.actions_out, G.act_dtype, cell * G.A + h, a);
       s_lp[item] = lp;
     }
-  }
-  __syncthreads();  // actions of the reference heads are written
-  for (int item = tid; item < n_items; item += kSampleBlock) {
-    const int u = item / G.A, h = item - u * G.A;
-    const int gr = G.gate_ref[h];
-    if (gr >= 0) {
-      const long long cell = b * G.HW + s_list[u];
-      long long a_ref;
-      switch (G.act_dtype) {
-        case B200RL_U8: a_ref = static_cast<const uint8_t*>(G.actions_out)[cell * G.A + gr]; break;
-        case B200RL_I32: a_ref = static_cast<const int32_t*>(G.actions_out)[cell * G.A + gr]; break;
-        default: a_ref = static_cast<const long long*>(G.actions_out)[cell * G.A + gr]; break;
-      }
-      if (a_ref != G.gate_val[h]) continue;
-    }
-    logp_acc += s_lp[item];
-  }
-  // cells beyond the shared-memory stash (dense masks on big maps): one thread walks all heads of a cell
-  for (int u = stash_units + tid; u < n_unit; u += kSampleBlock) {
-    const long long cell = b * G.HW + s_list[u];
-    int chosen[B200RL_MAX_HEADS];
-    float lp[B200RL_MAX_HEADS];
-    for (int h = 0; h < G.A; ++h) {
-      chosen[h] = sample_head(cell, h, &lp[h]);
-      put_index(G.actions_out, G.act_dtype, cell * G.A + h, chosen[h]);
-    }
-    for (int h = 0; h < G.A; ++h) {
+    __syncthreads();  // actions of the reference heads are written
+    for (int item = tid; item < n_items; item += kSampleBlock) {
+      const int u = item / G.A, h = item - u * G.A;
       const int gr = G.gate_ref[h];
-      if (gr < 0 || chosen[gr] == G.gate_val[h]) logp_acc += lp[h];
+      if (gr >= 0) {
+        const long long cell = b * G.HW + s_list[u];
+        long long a_ref;
+        switch (G.act_dtype) {
+          case B200RL_U8: a_ref = static_cast<const uint8_t*>(G.actions_out)[cell * G.A + gr]; break;
+          case B200RL_I32: a_ref = static_cast<const int32_t*>(G.actions_out)[cell * G.A + gr]; break;
+          default: a_ref = static_cast<const long long*>(G.actions_out)[cell * G.A + gr]; break;
+        }
+        if (a_ref != G.gate_val[h]) continue;
+      }
+      logp_acc += s_lp[item];
+    }
+    // cells beyond the shared-memory stash (dense masks on big maps): one thread walks all heads of a cell
+    for (int u = stash_units + tid; u < n_unit; u += kSampleBlock) {
+      const long long cell = b * G.HW + s_list[u];
+      int chosen[B200RL_MAX_HEADS];
+      float lp[B200RL_MAX_HEADS];
+      for (int h = 0; h < G.A; ++h) {
+        chosen[h] = sample_head(cell, h, &lp[h]);
+        put_index(G.actions_out, G.act_dtype, cell * G.A + h, chosen[h]);
+      }
+      for (int h = 0; h < G.A; ++h) {
+        const int gr = G.gate_ref[h];
+        if (gr < 0 || chosen[gr] == G.gate_val[h]) logp_acc += lp[h];
+      }
     }
   }
 
-  // pick_position: Gumbel arg-max over the cells of the sample, then its log-prob
+  // pick_position: Gumbel arg-max over the valid cells of the sample and the online softmax of their logits in ONE pass
+  // (was: an any-valid pass, the arg-max pass, a sum-exp pass, each with its own block reductions).  No valid cell:
+  // a uniform draw over all cells, log-prob 0 (the reference's all-masked row) -- a second pass, rare.
   for (int kp = 0; kp < G.n_pick; ++kp) {
     const uint8_t* pm = G.pick_mask + (b * G.n_pick + kp) * G.HW;
-    // does any cell qualify?
-    float anyf = 0.f;
-    for (long long c = tid; c < G.HW; c += kSampleBlock) anyf = fmaxf(anyf, pm[c] ? 1.f : 0.f);
-    anyf = warp_max(anyf);
-    if (lane == 0) s_red[warp] = anyf;
-    __syncthreads();
-    if (warp == 0) {
-      float x = lane < kSampleBlock / 32 ? s_red[lane] : 0.f;
-      x = warp_max(x);
-      if (lane == 0) s_scalar[0] = x;
-    }
-    __syncthreads();
-    const bool any = s_scalar[0] > 0.f;
-    float best_score = -INFINITY, mx = -INFINITY;
-    long long best = 0x7fffffffffffLL;
-    for (long long c = tid; c < G.HW; c += kSampleBlock) {
-      if (any && !pm[c]) continue;
-      const Philox4 r = philox4x32_10(G.seed, (uint64_t)(b * G.HW + c), stream_id(offset, G.A + kp, 0));
-      const float x = any ? logit_at(G, (b * G.HW + c) * G.ld + G.S + kp) : 0.f;
-      const float score = x + gumbel(r.x);
-      if (score > best_score) best_score = score, best = c;
-      mx = fmaxf(mx, x);
-    }
-    // block arg-max (ties -> lowest cell index, so the result does not depend on warp order)
-    for (int o = 16; o > 0; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, best_score, o);
-      const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
-      if (os > best_score || (os == best_score && ob < best)) best_score = os, best = ob;
-    }
-    mx = warp_max(mx);
-    __syncthreads();
-    if (lane == 0) s_best[warp] = best_score, s_arg[warp] = best, s_red[warp] = mx;
-    __syncthreads();
-    if (warp == 0) {
-      float bs = lane < kSampleBlock / 32 ? s_best[lane] : -INFINITY;
-      long long ba = lane < kSampleBlock / 32 ? s_arg[lane] : 0x7fffffffffffLL;
-      float m2 = lane < kSampleBlock / 32 ? s_red[lane] : -INFINITY;
-      for (int o = 16; o > 0; o >>= 1) {
-        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-        const long long ob = __shfl_xor_sync(0xffffffffu, ba, o);
-        if (os > bs || (os == bs && ob < ba)) bs = os, ba = ob;
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0: valid cells; pass 1 (only if there is none): every cell, x = 0
+      float best_score = -INFINITY, x_best = 0.f, mx = -INFINITY, sum = 0.f;
+      long long best = 0x7fffffffffffLL;
+      for (long long c = tid; c < G.HW; c += kSampleBlock) {
+        if (pass == 0 && !pm[c]) continue;
+        const Philox4 r = philox4x32_10(G.seed, (uint64_t)(b * G.HW + c), stream_id(offset, G.A + kp, 0));
+        const float x = pass == 0 ? logit_at(G, (b * G.HW + c) * G.ld + G.S + kp) : 0.f;
+        const float score = x + gumbel(r.x);
+        if (score > best_score) best_score = score, best = c, x_best = x;
+        const float nm = fmaxf(mx, x);
+        sum = sum * __expf(mx - nm) + __expf(x - nm);
+        mx = nm;
       }
-      m2 = warp_max(m2);
-      if (lane == 0) s_arg[0] = ba, s_scalar[1] = m2;
+      // block arg-max (ties -> lowest cell index, so the result does not depend on warp order) + softmax merge
+      auto fold = [&](float os, long long ob, float ox, float om, float osum) {
+        if (os > best_score || (os == best_score && ob < best)) best_score = os, best = ob, x_best = ox;
+        const float nm = fmaxf(mx, om);
+        if (nm > -INFINITY) sum = sum * __expf(mx - nm) + osum * __expf(om - nm);
+        mx = nm;
+      };
+      for (int o = 16; o > 0; o >>= 1)
+        fold(__shfl_xor_sync(0xffffffffu, best_score, o), __shfl_xor_sync(0xffffffffu, best, o),
+             __shfl_xor_sync(0xffffffffu, x_best, o), __shfl_xor_sync(0xffffffffu, mx, o),
+             __shfl_xor_sync(0xffffffffu, sum, o));
+      __syncthreads();  // the previous round's readers of the partial arrays are done
+      if (lane == 0) s_best[warp] = best_score, s_arg[warp] = best, s_xbest[warp] = x_best, s_mx[warp] = mx, s_sum[warp] = sum;
+      __syncthreads();
+      constexpr int NW = kSampleBlock / 32;
+      const int wl = lane & (NW - 1);  // every group of NW lanes of every warp folds the same partials: no broadcast needed
+      best_score = s_best[wl], best = s_arg[wl], x_best = s_xbest[wl], mx = s_mx[wl], sum = s_sum[wl];
+      for (int o = NW / 2; o > 0; o >>= 1)
+        fold(__shfl_xor_sync(0xffffffffu, best_score, o), __shfl_xor_sync(0xffffffffu, best, o),
+             __shfl_xor_sync(0xffffffffu, x_best, o), __shfl_xor_sync(0xffffffffu, mx, o),
+             __shfl_xor_sync(0xffffffffu, sum, o));
+      const bool any = sum > 0.f;  // block-uniform
+      if (pass == 0 && !any) continue;
+      if (tid == 0) {
+        put_index(G.pick_out, G.pick_dtype, b * G.n_pick + kp, best);
+        if (pass == 0) logp_acc += x_best - (mx + logf(sum));
+      }
+      break;
     }
-    __syncthreads();
-    const long long pick = s_arg[0];
-    mx = s_scalar[1];
-    float se = 0.f;
-    if (any)
-      for (long long c = tid; c < G.HW; c += kSampleBlock)
-        if (pm[c]) se += expf(logit_at(G, (b * G.HW + c) * G.ld + G.S + kp) - mx);
-    se = warp_sum(se);
-    __syncthreads();
-    if (lane == 0) s_red[warp] = se;
-    __syncthreads();
-    if (tid == 0) {
-      float tot = 0.f;
-      for (int w = 0; w < kSampleBlock / 32; ++w) tot += s_red[w];
-      put_index(G.pick_out, G.pick_dtype, b * G.n_pick + kp, pick);
-      if (any) logp_acc += logit_at(G, (b * G.HW + pick) * G.ld + G.S + kp) - (mx + logf(tot));
-    }
-    __syncthreads();
   }
 
   logp_acc = warp_sum(logp_acc);
@@ -338,6 +342,7 @@ extern "C" int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* l
         fits = false;
         break;
       }
+      G.head_first_part[h] = (int8_t)np;
       for (int q = 0; q < count; ++q, ++np) {
         G.part_head[np] = (int8_t)h;
         G.part_lo[np] = (int16_t)(q * kPartEntries);
@@ -354,6 +359,7 @@ extern "C" int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* l
   G.actions_out = actions_out, G.act_dtype = d->act_dtype, G.pick_out = pick_actions_out, G.pick_dtype = d->pick_dtype;
   G.logp = logp;
   B200RL_UNSUPPORTED(d->HW > 16384, "gridnet_sample: HW=%lld cells exceeds 16384", (long long)d->HW);
-  gridnet_sample_kernel<<<(unsigned)d->B, kSampleBlock, (size_t)d->HW * sizeof(uint16_t), (cudaStream_t)stream>>>(G);
+  const size_t smem = (size_t)((d->HW + 31) / 32) * sizeof(uint32_t) + (size_t)d->HW * sizeof(uint16_t);
+  gridnet_sample_kernel<<<(unsigned)d->B, kSampleBlock, smem, (cudaStream_t)stream>>>(G);
   return check_launch("gridnet_sample");
 }
