@@ -369,6 +369,33 @@ int b200rl_reward_assemble_f32(const float* base, int64_t V0, const float* const
                                const uint8_t* episode_end_host, const float* multiplier_host, float* out, int64_t N,
                                b200rl_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K8  channels-last glue between the convolutions of the GridNet encoder / decoder, float32.
+ * Replaces, around the cuDNN convolutions of shared/encoder/gridnet_encoder.py:26-51 (conv -> MaxPool2d(3, 2, 1) ->
+ * ReLU) and shared/actor/gridnet_decoder.py:36-53 (transposed conv -> ReLU), PyTorch's separate bias-add, max-pool,
+ * ReLU, their backward kernels and the bias-gradient reduction on the NHWC tensors the path hands the trunk.
+ * Forward bit-identical to the PyTorch sequence (same adds, torch's arg-max rule: first maximum of the kh, kw scan,
+ * NaN propagates); backward deterministic (gather form, fixed order).
+ *
+ *   x [N, H, W, C], bias [C] (nullable: no bias), out [N, Ho, Wo, C], Ho = (H + 2 padding - kernel) / stride + 1;
+ *   argmax [N, Ho, Wo, C] uint8 (nullable when no backward follows): kh * kernel + kw of the maximum, 255 where
+ *   the ReLU zeroed the output.  relu == 0: plain bias + max-pool.
+ *   _bwd: dx [N, H, W, C] is written everywhere (zero where no window routes a gradient); dbias [C] nullable;
+ *   workspace: b200rl_nhwc_bias_grad_workspace_bytes(N * Ho * Wo, C) bytes (only read / written when dbias != NULL).
+ *   b200rl_nhwc_bias_relu_*: out = relu(x + bias) over [rows, C]; out may alias x, dx may alias dout;
+ *   workspace: b200rl_nhwc_bias_grad_workspace_bytes(rows, C). */
+size_t b200rl_nhwc_bias_grad_workspace_bytes(int64_t rows, int64_t C);
+int b200rl_nhwc_bias_pool_relu_fwd(const float* x, const float* bias /*nullable*/, float* out, uint8_t* argmax /*nullable*/,
+                                   int64_t N, int64_t H, int64_t W, int64_t C, int kernel, int stride, int padding,
+                                   int relu, b200rl_stream_t stream);
+int b200rl_nhwc_bias_pool_relu_bwd(const float* dout, const uint8_t* argmax, float* dx, float* dbias /*nullable*/,
+                                   void* workspace, size_t workspace_bytes, int64_t N, int64_t H, int64_t W, int64_t C,
+                                   int kernel, int stride, int padding, b200rl_stream_t stream);
+int b200rl_nhwc_bias_relu_fwd(const float* x, const float* bias, float* out, int64_t rows, int64_t C,
+                              b200rl_stream_t stream);
+int b200rl_nhwc_bias_relu_bwd(const float* dout, const float* out, float* dx, float* dbias /*nullable*/, void* workspace,
+                              size_t workspace_bytes, int64_t rows, int64_t C, b200rl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

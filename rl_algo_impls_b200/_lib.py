@@ -136,6 +136,11 @@ PROTOTYPES = {
         _int,
         [_vp, _i64, C.POINTER(_vp), _int, _vp, _vp, C.POINTER(C.c_uint8), c_f32p, _vp, _i64, _vp],
     ),
+    "b200rl_nhwc_bias_grad_workspace_bytes": (_sz, [_i64, _i64]),
+    "b200rl_nhwc_bias_pool_relu_fwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),
+    "b200rl_nhwc_bias_pool_relu_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _i64, _i64, _i64, _i64, _int, _int, _int, _vp]),
+    "b200rl_nhwc_bias_relu_fwd": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "b200rl_nhwc_bias_relu_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _i64, _i64, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

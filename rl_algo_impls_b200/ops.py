@@ -912,3 +912,106 @@ def gridnet_sample(spec: GridnetSpec, logits, mask, pick_mask, seed: int, offset
     )  # fmt: skip
     check(rc, "b200rl_gridnet_sample")
     return actions, pick, logp
+
+
+# ------------------------------------------------------------------------------------------------
+# K8: channels-last glue between the convolutions of the GridNet encoder / decoder
+def nhwc_glue_supported(y: torch.Tensor) -> bool:
+    """The fused bias (+ max-pool) + ReLU kernels take float32 CUDA feature maps; anything else (CPU construction
+    passes, autocast's bfloat16 maps) stays on the PyTorch modules the trunk was built from."""
+    return y.is_cuda and y.dtype == torch.float32 and y.dim() == 4
+
+
+def _check_map(y: torch.Tensor) -> None:
+    if not isinstance(y, torch.Tensor) or not y.is_cuda:
+        raise _lib.B200RLError("feature map: expected a CUDA tensor (rl_algo_impls_b200 has no CPU path)")
+    if y.dtype != torch.float32 or y.dim() != 4:
+        raise TypeError(f"feature map: expected a float32 [N, C, H, W] tensor, got {y.dtype} {tuple(y.shape)}")
+
+
+def _nhwc(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+class _BiasPoolReluFn(torch.autograd.Function):
+    """relu(max_pool2d(y + bias)) on a channels-last [N, C, H, W] map in one launch; one gather launch (+ the
+    two-stage bias-gradient sum) backward.  Forward bit-identical to the PyTorch sequence."""
+
+    @staticmethod
+    def forward(ctx, y, bias, kernel, stride, padding, relu):
+        y = _nhwc(y)
+        N, Cc, H, W = y.shape
+        Ho, Wo = (H + 2 * padding - kernel) // stride + 1, (W + 2 * padding - kernel) // stride + 1
+        out = torch.empty((N, Cc, Ho, Wo), dtype=y.dtype, device=y.device, memory_format=torch.channels_last)
+        need = ctx.needs_input_grad[0] or (bias is not None and ctx.needs_input_grad[1])
+        argmax = torch.empty((N, Ho, Wo, Cc), dtype=torch.uint8, device=y.device) if need else None
+        rc = _call("b200rl_nhwc_bias_pool_relu_fwd", 1, _lib.lib().b200rl_nhwc_bias_pool_relu_fwd, y.data_ptr(), _ptr(bias),
+                   out.data_ptr(), _ptr(argmax), N, H, W, Cc, kernel, stride, padding, int(relu), _stream())
+        check(rc, "b200rl_nhwc_bias_pool_relu_fwd")
+        if need:
+            ctx.save_for_backward(argmax)
+            ctx.geometry = (N, Cc, H, W, kernel, stride, padding, bias is not None and ctx.needs_input_grad[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (argmax,) = ctx.saved_tensors
+        N, Cc, H, W, kernel, stride, padding, want_bias = ctx.geometry
+        dout = _nhwc(dout)
+        dx = torch.empty((N, Cc, H, W), dtype=dout.dtype, device=dout.device, memory_format=torch.channels_last)
+        dbias = torch.empty(Cc, dtype=torch.float32, device=dout.device) if want_bias else None
+        L = _lib.lib()
+        ws = _workspace(L.b200rl_nhwc_bias_grad_workspace_bytes(argmax.numel() // Cc, Cc), dout.device)
+        rc = _call("b200rl_nhwc_bias_pool_relu_bwd", 3 if want_bias else 1, L.b200rl_nhwc_bias_pool_relu_bwd, dout.data_ptr(),
+                   argmax.data_ptr(), dx.data_ptr(), _ptr(dbias), ws.data_ptr(), ws.numel(), N, H, W, Cc, kernel, stride,
+                   padding, _stream())
+        check(rc, "b200rl_nhwc_bias_pool_relu_bwd")
+        return dx, dbias, None, None, None, None
+
+
+class _BiasReluFn(torch.autograd.Function):
+    """relu(y + bias) on a channels-last map in one launch; backward = ReLU mask + two-stage bias-gradient sum."""
+
+    @staticmethod
+    def forward(ctx, y, bias):
+        y = _nhwc(y)
+        N, Cc, H, W = y.shape
+        out = torch.empty_like(y, memory_format=torch.channels_last)
+        rc = _call("b200rl_nhwc_bias_relu_fwd", 1, _lib.lib().b200rl_nhwc_bias_relu_fwd, y.data_ptr(), bias.data_ptr(),
+                   out.data_ptr(), N * H * W, Cc, _stream())
+        check(rc, "b200rl_nhwc_bias_relu_fwd")
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            ctx.save_for_backward(out)
+            ctx.want_bias = ctx.needs_input_grad[1]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        N, Cc, H, W = out.shape
+        dout = _nhwc(dout)
+        dx = torch.empty_like(out, memory_format=torch.channels_last)
+        dbias = torch.empty(Cc, dtype=torch.float32, device=dout.device) if ctx.want_bias else None
+        L = _lib.lib()
+        ws = _workspace(L.b200rl_nhwc_bias_grad_workspace_bytes(N * H * W, Cc), dout.device)
+        rc = _call("b200rl_nhwc_bias_relu_bwd", 3 if ctx.want_bias else 1, L.b200rl_nhwc_bias_relu_bwd, dout.data_ptr(),
+                   out.data_ptr(), dx.data_ptr(), _ptr(dbias), ws.data_ptr(), ws.numel(), N * H * W, Cc, _stream())
+        check(rc, "b200rl_nhwc_bias_relu_bwd")
+        return dx, dbias
+
+
+def bias_pool_relu(y: torch.Tensor, bias: Optional[torch.Tensor], kernel: int = 3, stride: int = 2, padding: int = 1,
+                   relu: bool = True) -> torch.Tensor:
+    """``relu(max_pool2d(y + bias[None, :, None, None], kernel, stride, padding))`` for a float32 CUDA map, channels-last
+    in memory (gridnet_encoder.py:26-51 between its convolutions)."""
+    _check_map(y)
+    if bias is not None:
+        _cuda(bias.detach(), torch.float32, "bias")
+    return _BiasPoolReluFn.apply(y, bias, int(kernel), int(stride), int(padding), bool(relu))
+
+
+def bias_relu(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """``relu(y + bias[None, :, None, None])`` for a float32 CUDA map, channels-last in memory (gridnet_decoder.py:36-53)."""
+    _check_map(y)
+    _cuda(bias.detach(), torch.float32, "bias")
+    return _BiasReluFn.apply(y, bias)

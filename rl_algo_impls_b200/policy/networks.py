@@ -8,12 +8,15 @@ NatureCNN (Atari, shared/encoder/nature_cnn.py), a conv encoder + transposed-con
 MicroRTS GridNet (shared/encoder/gridnet_encoder.py + shared/actor/gridnet_decoder.py) and the
 squeeze U-net with SE-residual blocks and several critic outputs for Lux (actor_critic_network/squeeze_unet.py).
 """
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from .. import ops
 
 _ACTIVATIONS = {"tanh": nn.Tanh, "relu": nn.ReLU, "gelu": nn.GELU, "identity": nn.Identity}
 
@@ -210,12 +213,28 @@ class GridEncoderDecoderActorCritic(_PaddedEnds):
         # reads and writes -- so permute(0, 2, 3, 1) is a free view instead of a 245 MB copy per minibatch.
         self.to(memory_format=torch.channels_last)
         self._init_padding(in_channels, n_logits, map_hw, self.encoder[0], self.decoder[-1])
+        # False (or B200RL_FUSED_GLUE=0): the PyTorch modules between the convolutions (parity tests compare the two)
+        self.fused_glue = os.environ.get("B200RL_FUSED_GLUE", "1") != "0"
 
     def forward(self, obs: torch.Tensor) -> HeadOutputs:
         w0, wh, bh = self._padded_weights()
-        x = F.conv2d(self._packed_input(obs), w0, self.encoder[0].bias, padding=1)
-        z = self.encoder[1:](x)
-        y = self.decoder[:-1](z)
+        x_in = self._packed_input(obs)
+        if self.fused_glue and ops.nhwc_glue_supported(x_in):
+            # float32 on the device: the convolutions run without their bias, and what sits between them -- bias +
+            # max-pool + ReLU in the encoder, bias + ReLU in the decoder -- is one launch each (ops.bias_pool_relu /
+            # ops.bias_relu: same arithmetic, bit-identical forward) instead of three / two PyTorch launches
+            z = ops.bias_pool_relu(F.conv2d(x_in, w0, None, padding=1), self.encoder[0].bias)
+            for i in (3, 6, 9):
+                conv = self.encoder[i]
+                z = ops.bias_pool_relu(F.conv2d(z, conv.weight, None, padding=1), conv.bias)
+            y = z
+            for i in (0, 2, 4):
+                up = self.decoder[i]
+                y = ops.bias_relu(F.conv_transpose2d(y, up.weight, None, stride=2, padding=1, output_padding=1), up.bias)
+        else:
+            x = F.conv2d(x_in, w0, self.encoder[0].bias, padding=1)
+            z = self.encoder[1:](x)
+            y = self.decoder[:-1](z)
         logits = F.conv_transpose2d(y, wh, bh, stride=2, padding=1, output_padding=1).permute(0, 2, 3, 1)  # [B, H, W, Lp]
         v = self.critic(z)
         return HeadOutputs(logits, v.squeeze(-1) if self.n_values == 1 else v)
