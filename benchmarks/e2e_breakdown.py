@@ -34,7 +34,7 @@ def main(key="C4"):
         t2 = time.perf_counter()
         next_obs, rewards, term, trunc, _ = env.step(acts)
         t3 = time.perf_counter()
-        gen._upload("obs", next_obs, gen.next_obs)
+        gen._set_next_obs(next_obs)
         gen._upload_masks(gen.get_action_mask())
         t4 = time.perf_counter()
         sync()

@@ -329,6 +329,26 @@ int b200rl_rollout_store_step_carry(const void* const* src_host, void* const* ds
                                     const void* const* carry_host, int n_tensors, const int64_t* step_dev, int64_t T,
                                     b200rl_stream_t stream);
 
+/* ... and the rest of the step's bookkeeping in that launch (b200rl_rollout_store_step_fused):
+ *  - carry_or_host[t] non-NULL (with carry_host[t]): src[t] <- carry[t] | carry_or[t], bytewise -- the episode-start
+ *    flags of the next step are terminations | truncations (sync_step_rollout.py:204-206);
+ *  - pack (nullable): field pack->field holds observations in the trunk's layout, src [N, HW, Cp] float32 (planes C..
+ *    zero); its carry is the env's RAW observation [N, C, HW] float32, transposed into that layout on the way
+ *    (the per-step permute copy of the packed-observation path);
+ *  - advance != 0: *step_dev is incremented once every CTA has read it (the last CTA to finish does it; `ticket` is a
+ *    zero-initialised device int32 the caller keeps, left at zero again). */
+typedef struct b200rl_store_pack {
+  int field;             /* index into src_host / dst_host / carry_host */
+  int64_t N;             /* envs */
+  int64_t C;             /* observation planes */
+  int64_t HW;            /* map cells */
+  int64_t Cp;            /* planes per packed cell row (>= C, <= 128) */
+} b200rl_store_pack;
+int b200rl_rollout_store_step_fused(const void* const* src_host, void* const* dst_host, const int64_t* step_bytes_host,
+                                    const void* const* carry_host, const void* const* carry_or_host, int n_tensors,
+                                    const b200rl_store_pack* pack /*nullable*/, int64_t* step_dev, int64_t T, int advance,
+                                    int32_t* ticket /*nullable unless advance*/, b200rl_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * K6  running-moment normalisers.  Replaces wrappers/normalize.py:18-122 over
  * utils/running_mean_std.py:10-33.  State (mean[D], var[D], count[D] -- the reference's scalar count,

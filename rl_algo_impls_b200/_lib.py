@@ -71,6 +71,12 @@ class GridnetDesc(C.Structure):
     ]
 
 
+class StorePack(C.Structure):
+    """b200rl_store_pack"""
+
+    _fields_ = [("field", C.c_int), ("N", C.c_int64), ("C", C.c_int64), ("HW", C.c_int64), ("Cp", C.c_int64)]
+
+
 _vp, _i64, _int, _sz, _u64, _f = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_uint64, C.c_float
 
 # name -> (restype, argtypes); the single source of truth for tests/test_abi.py
@@ -131,6 +137,11 @@ PROTOTYPES = {
     "b200rl_rollout_store_step_carry": (
         _int,
         [C.POINTER(_vp), C.POINTER(_vp), c_i64p, C.POINTER(_vp), _int, _vp, _i64, _vp],
+    ),
+    "b200rl_rollout_store_step_fused": (
+        _int,
+        [C.POINTER(_vp), C.POINTER(_vp), c_i64p, C.POINTER(_vp), C.POINTER(_vp), _int, C.POINTER(StorePack), _vp, _i64,
+         _int, _vp, _vp],
     ),
     "b200rl_reward_assemble_f32": (
         _int,

@@ -101,10 +101,19 @@ struct StoreParams {
   long long step_bytes[B200RL_MAX_GATHER];
   long long first_chunk[B200RL_MAX_GATHER + 1];
   const uint8_t* carry[B200RL_MAX_GATHER];  // non-null: after the row write, src[t] <- carry[t] (the next step's slice)
+  const uint8_t* carry_or[B200RL_MAX_GATHER];  // non-null (with carry[t]): src[t] <- carry[t] | carry_or[t], bytewise
   int n;
   const long long* step_dev;
   long long T;
+  // packed-observation field (pack_field >= 0): src[t] is [N, HW, Cp] float32, carry[t] the env's raw [N, C, HW] float32
+  // observation; a work item is a tile of kPackCells cells of one sample instead of a 16 KB chunk
+  int pack_field, pack_C, pack_HW, pack_Cp, pack_tiles;
+  // advance != 0: the last CTA to finish writes *step_dev + 1 back (ticket: a zeroed int the caller keeps)
+  long long* step_mut;
+  int* ticket;
 };
+constexpr int kPackCells = 32;
+constexpr int kPackMaxCp = 128;
 
 // one chunk src -> dst by the whole CTA; every load is issued before the first store
 __device__ __forceinline__ void copy_chunk(const uint8_t* s, uint8_t* d, long long bytes) {
@@ -131,22 +140,67 @@ __device__ __forceinline__ void copy_chunk(const uint8_t* s, uint8_t* d, long lo
   }
 }
 
+__global__ void advance_step_kernel(long long* step) { *step += 1; }
+
+// src <- a | b (bytewise), whole CTA
+__device__ __forceinline__ void or_chunk(const uint8_t* a, const uint8_t* b, uint8_t* d, long long bytes) {
+  for (long long o = threadIdx.x; o < bytes; o += kGatherBlock) d[o] = a[o] | b[o];
+}
+
 __global__ void __launch_bounds__(kGatherBlock) store_step_kernel(const StoreParams p) {
+  __shared__ float s_tile[kPackCells][kPackMaxCp + 1];
   const long long item = blockIdx.x;
   int t = 0;
   while (t + 1 < p.n && item >= p.first_chunk[t + 1]) ++t;
-  const long long begin = (item - p.first_chunk[t]) * kChunkBytes;
   const long long sb = p.step_bytes[t];
-  const long long bytes = sb - begin < kChunkBytes ? sb - begin : kChunkBytes;
-  const long long step = *p.step_dev % p.T;
-  const uint8_t* s = p.src[t] + begin;
-  copy_chunk(s, p.dst[t] + step * sb + begin, bytes);
-  // carry-over: this CTA, which alone touches this chunk of the step slice, overwrites it with the next step's once
-  // every thread's loads of the old content have returned (the barrier: the two copies may split the chunk
-  // differently across threads when their alignments differ)
-  if (p.carry[t] != nullptr) {
+  const long long step_raw = *p.step_dev;
+  const long long step = step_raw % p.T;
+  if (t == p.pack_field) {
+    // this tile's cells of one sample: their packed rows go to the buffer row, then the env's raw [C, HW] planes of
+    // the same cells are transposed through shared memory into [cells, Cp] rows (planes C.. written as zeros)
+    const long long local = item - p.first_chunk[t];
+    const long long n = local / p.pack_tiles;
+    const int cell0 = (int)(local - n * p.pack_tiles) * kPackCells;
+    const int cells = p.pack_HW - cell0 < kPackCells ? p.pack_HW - cell0 : kPackCells;
+    const long long begin = (n * p.pack_HW + cell0) * p.pack_Cp * 4;
+    const long long bytes = (long long)cells * p.pack_Cp * 4;
+    uint8_t* region = const_cast<uint8_t*>(p.src[t]) + begin;
+    copy_chunk(region, p.dst[t] + step * sb + begin, bytes);
+    const float* raw = reinterpret_cast<const float*>(p.carry[t]) + n * p.pack_C * p.pack_HW + cell0;
+    for (int i = threadIdx.x; i < p.pack_C * kPackCells; i += kGatherBlock) {
+      const int c = i / kPackCells, j = i - c * kPackCells;  // adjacent threads read adjacent cells of one plane
+      if (j < cells) s_tile[j][c] = raw[(long long)c * p.pack_HW + j];
+    }
+    __syncthreads();  // (also: every load of the old packed rows above has returned)
+    float* out = reinterpret_cast<float*>(region);
+    for (int i = threadIdx.x; i < cells * p.pack_Cp; i += kGatherBlock) {
+      const int j = i / p.pack_Cp, c = i - j * p.pack_Cp;
+      out[i] = c < p.pack_C ? s_tile[j][c] : 0.f;
+    }
+  } else {
+    const long long begin = (item - p.first_chunk[t]) * kChunkBytes;
+    const long long bytes = sb - begin < kChunkBytes ? sb - begin : kChunkBytes;
+    const uint8_t* s = p.src[t] + begin;
+    copy_chunk(s, p.dst[t] + step * sb + begin, bytes);
+    // carry-over: this CTA, which alone touches this chunk of the step slice, overwrites it with the next step's once
+    // every thread's loads of the old content have returned (the barrier: the two copies may split the chunk
+    // differently across threads when their alignments differ)
+    if (p.carry[t] != nullptr) {
+      __syncthreads();
+      if (p.carry_or[t] != nullptr) or_chunk(p.carry[t] + begin, p.carry_or[t] + begin, const_cast<uint8_t*>(s), bytes);
+      else copy_chunk(p.carry[t] + begin, const_cast<uint8_t*>(s), bytes);
+    }
+  }
+  if (p.step_mut != nullptr) {
+    // every thread of this CTA has read the step index; the CTA that arrives last (all have read it) advances it
     __syncthreads();
-    copy_chunk(p.carry[t] + begin, const_cast<uint8_t*>(s), bytes);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(p.ticket, 1) == (int)gridDim.x - 1) {
+        *p.step_mut = step_raw + 1;
+        *p.ticket = 0;
+      }
+    }
   }
 }
 
@@ -158,33 +212,81 @@ extern "C" int b200rl_rollout_store_step(const void* const* src_host, void* cons
   return b200rl_rollout_store_step_carry(src_host, dst_host, step_bytes_host, nullptr, n_tensors, step_dev, T, stream);
 }
 
-extern "C" int b200rl_rollout_store_step_carry(const void* const* src_host, void* const* dst_host,
-                                               const int64_t* step_bytes_host, const void* const* carry_host,
-                                               int n_tensors, const int64_t* step_dev, int64_t T,
-                                               b200rl_stream_t stream) {
-  using namespace b200rl;
+namespace b200rl {
+static int store_step_impl(const void* const* src_host, void* const* dst_host, const int64_t* step_bytes_host,
+                           const void* const* carry_host, const void* const* carry_or_host, int n_tensors,
+                           const b200rl_store_pack* pack, int64_t* step_dev, int64_t T, int advance, int32_t* ticket,
+                           cudaStream_t stream) {
   B200RL_REQUIRE(src_host && dst_host && step_bytes_host && step_dev, "rollout_store_step: null pointer");
   B200RL_REQUIRE(n_tensors >= 0 && n_tensors <= B200RL_MAX_GATHER, "rollout_store_step: n_tensors=%d (max %d)",
                  n_tensors, B200RL_MAX_GATHER);
   B200RL_REQUIRE(T >= 1, "rollout_store_step: T=%lld", (long long)T);
+  B200RL_REQUIRE(!advance || ticket, "rollout_store_step: advance needs a ticket counter");
   StoreParams p{};
   p.step_dev = reinterpret_cast<const long long*>(step_dev), p.T = T;
+  p.pack_field = -1;
   long long chunks = 0;
   for (int t = 0; t < n_tensors; ++t) {
     B200RL_REQUIRE(src_host[t] && dst_host[t] && step_bytes_host[t] >= 0, "rollout_store_step: tensor %d is null", t);
-    if (step_bytes_host[t] == 0) continue;
+    B200RL_REQUIRE(!(carry_or_host && carry_or_host[t]) || (carry_host && carry_host[t]),
+                   "rollout_store_step: carry_or[%d] without carry[%d]", t, t);
+    const bool packed = pack != nullptr && pack->field == t;
+    if (step_bytes_host[t] == 0) {
+      B200RL_REQUIRE(!packed, "rollout_store_step: the packed field is empty");
+      continue;
+    }
     const int k = p.n++;
     p.src[k] = static_cast<const uint8_t*>(src_host[t]), p.dst[k] = static_cast<uint8_t*>(dst_host[t]);
     p.carry[k] = carry_host ? static_cast<const uint8_t*>(carry_host[t]) : nullptr;
+    p.carry_or[k] = carry_or_host ? static_cast<const uint8_t*>(carry_or_host[t]) : nullptr;
     p.step_bytes[k] = step_bytes_host[t];
     p.first_chunk[k] = chunks;
-    chunks += (step_bytes_host[t] + kChunkBytes - 1) / kChunkBytes;
+    if (packed) {
+      B200RL_REQUIRE(pack->N >= 1 && pack->C >= 1 && pack->HW >= 1 && pack->Cp >= pack->C, "rollout_store_step: bad pack shape");
+      B200RL_UNSUPPORTED(pack->Cp > kPackMaxCp, "rollout_store_step: Cp=%d exceeds %d", (int)pack->Cp, kPackMaxCp);
+      B200RL_REQUIRE(step_bytes_host[t] == pack->N * pack->HW * pack->Cp * 4, "rollout_store_step: packed field is not [N, HW, Cp] float32");
+      B200RL_REQUIRE(p.carry[k] != nullptr && p.carry_or[k] == nullptr, "rollout_store_step: the packed field carries the raw observation");
+      B200RL_REQUIRE(((reinterpret_cast<uintptr_t>(p.src[k]) | reinterpret_cast<uintptr_t>(p.carry[k])) & 3u) == 0,
+                     "rollout_store_step: packed field is not 4-byte aligned");
+      p.pack_field = k, p.pack_C = (int)pack->C, p.pack_HW = (int)pack->HW, p.pack_Cp = (int)pack->Cp;
+      p.pack_tiles = (int)((pack->HW + kPackCells - 1) / kPackCells);
+      chunks += pack->N * p.pack_tiles;
+    } else {
+      chunks += (step_bytes_host[t] + kChunkBytes - 1) / kChunkBytes;
+    }
     p.first_chunk[k + 1] = chunks;
   }
-  if (chunks == 0) return B200RL_OK;
+  if (advance) p.step_mut = reinterpret_cast<long long*>(step_dev), p.ticket = ticket;
+  if (chunks == 0) {
+    if (!advance) return B200RL_OK;
+    // nothing to store, the step still advances: one CTA through the empty field list
+    p.n = 0;
+  }
   B200RL_UNSUPPORTED(chunks > 0x7fffffffLL, "rollout_store_step: %lld chunks", chunks);
-  store_step_kernel<<<(unsigned)chunks, kGatherBlock, 0, (cudaStream_t)stream>>>(p);
+  if (chunks == 0) {
+    advance_step_kernel<<<1, 1, 0, stream>>>(p.step_mut);
+    return check_launch("rollout_store_step");
+  }
+  store_step_kernel<<<(unsigned)chunks, kGatherBlock, 0, stream>>>(p);
   return check_launch("rollout_store_step");
+}
+}  // namespace b200rl
+
+extern "C" int b200rl_rollout_store_step_carry(const void* const* src_host, void* const* dst_host,
+                                               const int64_t* step_bytes_host, const void* const* carry_host,
+                                               int n_tensors, const int64_t* step_dev, int64_t T,
+                                               b200rl_stream_t stream) {
+  return b200rl::store_step_impl(src_host, dst_host, step_bytes_host, carry_host, nullptr, n_tensors, nullptr,
+                                 const_cast<int64_t*>(step_dev), T, 0, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b200rl_rollout_store_step_fused(const void* const* src_host, void* const* dst_host,
+                                               const int64_t* step_bytes_host, const void* const* carry_host,
+                                               const void* const* carry_or_host, int n_tensors,
+                                               const b200rl_store_pack* pack, int64_t* step_dev, int64_t T, int advance,
+                                               int32_t* ticket, b200rl_stream_t stream) {
+  return b200rl::store_step_impl(src_host, dst_host, step_bytes_host, carry_host, carry_or_host, n_tensors, pack, step_dev,
+                                 T, advance, ticket, (cudaStream_t)stream);
 }
 
 extern "C" int b200rl_gather_rows(const void* const* src_host, void* const* dst_host, const int64_t* row_bytes_host,

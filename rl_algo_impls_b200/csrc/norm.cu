@@ -5,17 +5,16 @@
 //   count) in float64, then  clip((x - mean) / sqrt(var + eps), -clip, clip)   (observations) or
 //   returns = returns * gamma + r ; update(returns) ; clip(r / sqrt(var + eps), -clip, clip) ;
 //   returns[done] = 0                                                        (rewards).
-// One launch per env step: a CTA owns a tile of 32 features for ALL N rows, so it can reduce,
-// merge and normalise its own columns without a grid-wide barrier.  State lives in HBM as float64
+// One launch per env step: a CTA owns a tile of FEAT features (1 / 4 / 16 / 32: the smallest that covers min(D, 32))
+// for ALL N rows, so it can reduce, merge and normalise its own columns without a grid-wide barrier; its other
+// BLOCK / FEAT thread rows split the N envs (BLOCK = 1024 when a 256-thread CTA would walk more than 8 rows per
+// thread: narrow observations over thousands of envs), partial moments fold through a shared-memory tree.  State lives in HBM as float64
 // (count is kept per feature so that no CTA reads a scalar another CTA is updating); everything
 // is asynchronous and address-stable, i.e. capturable in the rollout step's CUDA graph.
 #include "common.cuh"
 
 namespace b200rl {
 
-constexpr int kNormFeat = 32;  // features per CTA (one warp lane each)
-constexpr int kNormRows = 8;   // row groups per CTA
-constexpr int kNormBlock = kNormFeat * kNormRows;
 
 struct NormParams {
   const float* x;      // [N, D] observations, or rewards
@@ -41,7 +40,9 @@ struct NormParams {
   int per_row;
 };
 
+template <int kNormFeat, int kNormBlock>
 __global__ void __launch_bounds__(kNormBlock) running_norm_kernel(const NormParams p) {
+  constexpr int kNormRows = kNormBlock / kNormFeat;
   __shared__ double s_sum[kNormRows][kNormFeat], s_sq[kNormRows][kNormFeat];
   __shared__ double s_wsum[kNormRows][kNormFeat], s_wsq[kNormRows][kNormFeat];
   __shared__ double s_batch[5];  // per_row mode: batch mean, mean of squares, variance, count / window, running variance
@@ -77,13 +78,19 @@ __global__ void __launch_bounds__(kNormBlock) running_norm_kernel(const NormPara
   s_sum[ry][fx] = sum, s_sq[ry][fx] = sq;
   s_wsum[ry][fx] = wsum, s_wsq[ry][fx] = wsq;
   __syncthreads();
+  for (int half = kNormRows / 2; half > 0; half >>= 1) {  // fixed tree over the thread rows: row 0 ends with the totals
+    if (ry < half) {
+      s_sum[ry][fx] += s_sum[ry + half][fx], s_sq[ry][fx] += s_sq[ry + half][fx];
+      if (ema) s_wsum[ry][fx] += s_wsum[ry + half][fx], s_wsq[ry][fx] += s_wsq[ry + half][fx];
+    }
+    __syncthreads();
+  }
 
   // ---- 2. Chan merge into the running moments (running_mean_std.py:16-29) --------------------------
   if (ry == 0 && live) {
     double mean = p.mean[f], var = p.var[f];
     if (p.training) {
-      double a = 0.0, b = 0.0;
-      for (int r = 0; r < kNormRows; ++r) a += s_sum[r][fx], b += s_sq[r][fx];
+      const double a = s_sum[0][fx], b = s_sq[0][fx];
       const double count = p.count[f], n = (double)p.N;
       const double batch_mean = a / n;
       const double batch_var = fmax(0.0, b / n - batch_mean * batch_mean);
@@ -102,8 +109,7 @@ __global__ void __launch_bounds__(kNormBlock) running_norm_kernel(const NormPara
           em = batch_mean, esq = b / n, ev = batch_var;
           p.ema_init[f] = 1;
         } else {
-          double wa = 0.0, wb = 0.0;
-          for (int r = 0; r < kNormRows; ++r) wa += s_wsum[r][fx], wb += s_wsq[r][fx];
+          const double wa = s_wsum[0][fx], wb = s_wsq[0][fx];
           const double keep = pow(1.0 - p.alpha, n);  // 1 - sum of the weights
           em = wa + keep * p.ema_mean[f];
           esq = wb + keep * p.ema_sq[f];
@@ -157,13 +163,23 @@ __global__ void __launch_bounds__(kNormBlock) running_norm_kernel(const NormPara
   }
 }
 
+template <int FEAT>
+static void launch_norm_feat(const NormParams& p, cudaStream_t stream) {
+  const unsigned tiles = (unsigned)((p.D + FEAT - 1) / FEAT);
+  // 256 threads unless each would walk more than 8 rows (narrow observations over thousands of envs)
+  if (p.N > 8 * (256 / FEAT)) running_norm_kernel<FEAT, 1024><<<tiles, 1024, 0, stream>>>(p);
+  else running_norm_kernel<FEAT, 256><<<tiles, 256, 0, stream>>>(p);
+}
+
 static int launch_norm(const NormParams& p, cudaStream_t stream) {
-  const long long tiles = (p.D + kNormFeat - 1) / kNormFeat;
-  if (tiles > 0x7fffffffLL) {
+  if (p.D > 0x7fffffffLL) {
     set_error("running_norm: too many features (%lld)", p.D);
     return B200RL_EUNSUPPORTED;
   }
-  running_norm_kernel<<<(unsigned)tiles, kNormBlock, 0, stream>>>(p);
+  if (p.D <= 1) launch_norm_feat<1>(p, stream);
+  else if (p.D <= 4) launch_norm_feat<4>(p, stream);
+  else if (p.D <= 16) launch_norm_feat<16>(p, stream);
+  else launch_norm_feat<32>(p, stream);
   return check_launch("running_norm");
 }
 

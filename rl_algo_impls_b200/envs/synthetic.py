@@ -124,12 +124,10 @@ class SyntheticVecEnv:
             if masks is not None:
                 self._masks = {k: to(v) for k, v in masks.items()} if isinstance(masks, dict) else to(masks)
             self._no_trunc = torch.zeros(N, dtype=torch.bool, device=device)
-            self._slot_dev = torch.zeros(1, dtype=torch.int64, device=device)
-            one = lambda a: torch.empty((1,) + tuple(a.shape[1:]), dtype=a.dtype, device=device)
-            self._out_obs, self._out_rew, self._out_done = one(self._obs), one(self._rewards), one(self._dones)
-            if masks is not None:
-                self._out_masks = ({k: one(v) for k, v in self._masks.items()} if isinstance(self._masks, dict)
-                                   else one(self._masks))
+            # [this step's slot, the next one]: rewards / dones are read at the first, the observation and masks the
+            # step returns at the second; both advance together
+            self._slots = torch.tensor([0, 1 % self.pool], dtype=torch.int64, device=device)
+            self._out_obs = self._out_rew = self._out_done = self._out_masks = None
         else:
             self._no_trunc = np.zeros(N, dtype=np.bool_)
         self._t = 0
@@ -141,30 +139,35 @@ class SyntheticVecEnv:
     def _slot(self) -> int:
         return self._t % self.pool
 
-    def _refresh_device_outputs(self) -> None:
-        torch.index_select(self._obs, 0, self._slot_dev, out=self._out_obs)
+    def _gather_device_outputs(self, scalars: bool) -> None:
+        """The pool rows of the current slot pair -> this step's outputs: one gather launch for the observation and the
+        masks (slot 1), one for rewards and dones (slot 0) -- the minibatch gather kernel with a single index."""
+        from .. import ops
+
+        wide = [self._obs]
         if self._masks is not None:
-            if isinstance(self._masks, dict):
-                for n, m in self._masks.items():
-                    torch.index_select(m, 0, self._slot_dev, out=self._out_masks[n])
-            else:
-                torch.index_select(self._masks, 0, self._slot_dev, out=self._out_masks)
+            wide += list(self._masks.values()) if isinstance(self._masks, dict) else [self._masks]
+        got = ops.gather_rows(wide, self._slots[1:2])
+        self._out_obs = got[0]
+        if self._masks is not None:
+            self._out_masks = dict(zip(self._masks, got[1:])) if isinstance(self._masks, dict) else got[1]
+        if scalars:
+            self._out_rew, self._out_done = ops.gather_rows([self._rewards, self._dones], self._slots[0:1])
 
     def reset(self, **_kwargs):
         self._t = 0
         if self.device is not None:
-            self._slot_dev.zero_()
-            self._refresh_device_outputs()
+            self._slots.copy_(torch.tensor([self.pool - 1, 0], dtype=torch.int64))  # the observation of slot 0 comes first
+            self._gather_device_outputs(scalars=False)
+            self._slots.add_(1).remainder_(self.pool)
             return self._out_obs[0], {}
         return self._obs[0], {}
 
     def step(self, actions):
         """-> (next_obs, rewards, terminations, truncations, infos); actions are accepted and ignored."""
         if self.device is not None:
-            torch.index_select(self._rewards, 0, self._slot_dev, out=self._out_rew)
-            torch.index_select(self._dones, 0, self._slot_dev, out=self._out_done)
-            self._slot_dev.add_(1).remainder_(self.pool)
-            self._refresh_device_outputs()
+            self._gather_device_outputs(scalars=True)
+            self._slots.add_(1).remainder_(self.pool)
             return self._out_obs[0], self._out_rew[0], self._out_done[0], self._no_trunc, {}
         k = self._slot()
         self._t += 1

@@ -275,33 +275,68 @@ def gather_rows(sources: Sequence[torch.Tensor], idx: torch.Tensor) -> List[torc
 # ------------------------------------------------------------------------------------------------
 # K0
 def rollout_store_step(step_tensors: Sequence[torch.Tensor], buffers: Sequence[torch.Tensor], step_dev: torch.Tensor,
-                       carry: Optional[Sequence[Optional[torch.Tensor]]] = None) -> None:
+                       carry: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                       carry_or: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                       pack: Optional[Tuple[int, int, int, int, int]] = None,
+                       advance_ticket: Optional[torch.Tensor] = None) -> None:
     """buffers[t][*step_dev % T] = step_tensors[t] for every rollout field in one launch
     (sync_step_rollout.py:188-201); the step index is read on the device (CUDA-graph friendly).
     ``carry[t]`` (same shape / dtype as step_tensors[t], or None) is then copied INTO step_tensors[t] by the same
-    launch: the env's output for the next step replaces the slice that was just stored (:202-212)."""
+    launch: the env's output for the next step replaces the slice that was just stored (:202-212).
+    ``carry_or[t]``: step_tensors[t] <- carry[t] | carry_or[t] (bool / uint8 fields: terminations | truncations).
+    ``pack = (field, N, C, HW, Cp)``: step_tensors[field] is a packed [N, HW, Cp] float32 observation and carry[field]
+    the env's raw [N, C, HW] float32 one, transposed into that layout by the launch.
+    ``advance_ticket`` (zeroed int32 device scalar, kept by the caller): ``step_dev += 1`` once every CTA has read it."""
     _cuda(step_dev, torch.int64, "step_dev")
     n = len(step_tensors)
-    if n == 0:
+    if n == 0 and advance_ticket is None:
         return
     if n > _lib.MAX_GATHER:
         raise ValueError(f"at most {_lib.MAX_GATHER} fields per call")
-    T = buffers[0].shape[0]
-    src_arr, dst_arr, sb_arr, carry_arr = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_int64 * n)(), (C.c_void_p * n)()
+    T = buffers[0].shape[0] if n else 1
+    src_arr, dst_arr, sb_arr = (C.c_void_p * max(n, 1))(), (C.c_void_p * max(n, 1))(), (C.c_int64 * max(n, 1))()
+    carry_arr, or_arr = (C.c_void_p * max(n, 1))(), (C.c_void_p * max(n, 1))()
     for k, (s, d) in enumerate(zip(step_tensors, buffers)):
         _cuda(s, None, f"step_tensors[{k}]"), _cuda(d, None, f"buffers[{k}]")
         if d.shape[0] != T or s.dtype != d.dtype or s.numel() * T != d.numel():
             raise ValueError(f"field {k}: step slice {tuple(s.shape)} {s.dtype} does not fit buffer {tuple(d.shape)} {d.dtype}")
         src_arr[k], dst_arr[k], sb_arr[k] = s.data_ptr(), d.data_ptr(), s.numel() * s.element_size()
         c = carry[k] if carry is not None else None
+        packed = pack is not None and pack[0] == k
         if c is not None:
             _cuda(c, None, f"carry[{k}]")
-            if c.dtype != s.dtype or c.numel() != s.numel():
+            if packed:
+                _, N, Cc, HW, Cp = pack
+                if c.dtype != torch.float32 or s.dtype != torch.float32 or c.numel() != N * Cc * HW or s.numel() != N * HW * Cp:
+                    raise ValueError(f"pack: raw {tuple(c.shape)} {c.dtype} / packed {tuple(s.shape)} {s.dtype} do not match {pack}")
+            elif c.dtype != s.dtype or c.numel() != s.numel():
                 raise ValueError(f"carry[{k}] {tuple(c.shape)} {c.dtype} does not match the step slice {tuple(s.shape)} {s.dtype}")
             carry_arr[k] = c.data_ptr()
-    rc = _call("b200rl_rollout_store_step_carry", 1, _lib.lib().b200rl_rollout_store_step_carry, src_arr, dst_arr, sb_arr,
-               carry_arr if carry is not None else None, n, step_dev.data_ptr(), T, _stream())
-    check(rc, "b200rl_rollout_store_step_carry")
+        elif packed:
+            raise ValueError("pack: the packed field needs the raw observation as its carry")
+        o = carry_or[k] if carry_or is not None else None
+        if o is not None:
+            _cuda(o, None, f"carry_or[{k}]")
+            if c is None or o.numel() != s.numel() or o.element_size() != 1 or s.element_size() != 1:
+                raise ValueError(f"carry_or[{k}]: needs carry[{k}] and one-byte elements of the step slice's size")
+            or_arr[k] = o.data_ptr()
+    L = _lib.lib()
+    if carry_or is None and pack is None and advance_ticket is None:
+        rc = _call("b200rl_rollout_store_step_carry", 1, L.b200rl_rollout_store_step_carry, src_arr, dst_arr, sb_arr,
+                   carry_arr if carry is not None else None, n, step_dev.data_ptr(), T, _stream())
+        check(rc, "b200rl_rollout_store_step_carry")
+        return
+    pk = None
+    if pack is not None:
+        pk = _lib.StorePack()
+        pk.field, pk.N, pk.C, pk.HW, pk.Cp = pack
+    if advance_ticket is not None:
+        _cuda(advance_ticket, torch.int32, "advance_ticket")
+    rc = _call("b200rl_rollout_store_step_fused", 1, L.b200rl_rollout_store_step_fused, src_arr, dst_arr, sb_arr,
+               carry_arr if carry is not None else None, or_arr if carry_or is not None else None, n,
+               C.byref(pk) if pk is not None else None, step_dev.data_ptr(), T, int(advance_ticket is not None),
+               _ptr(advance_ticket), _stream())
+    check(rc, "b200rl_rollout_store_step_fused")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -160,6 +160,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         # env steps taken so far, on the device: row index of the buffer write (mod n_steps) and RNG
         # offset of the sampling kernel, both read inside captured launches
         self.step_count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._k0_ticket = torch.zeros(1, dtype=torch.int32, device=self.device)  # K0's "last CTA advances the step" counter
         self._rollouts_done = 0
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_outputs = None
@@ -299,7 +300,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
 
         a, v, logp = self.policy.step_device(self.next_obs, self.next_action_masks, offset_dev=self.step_count)
         src, dst = self._fields(a, v, logp, with_starts=False)
-        ops.rollout_store_step(src, dst, self.step_count)
+        ops.rollout_store_step(src, dst, self.step_count, advance_ticket=self._k0_ticket)  # ... and step_count += 1
         if self._host_actions is None:
             pin = lambda t: torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
             self._host_actions = {k: pin(t) for k, t in a.items()} if isinstance(a, dict) else pin(a)
@@ -318,24 +319,40 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         a, v, logp = self.policy.step_device(self.next_obs, self.next_action_masks, offset_dev=self.step_count)
         next_obs, rewards, terminations, truncations, _ = self.vec_env.step(a)
         src, dst = self._fields(a, v, logp, rewards.reshape(self.rewards.shape[1:]))
-        # the env's outputs for the next step replace next_obs / next masks inside the same K0 launch
-        fits = lambda new, cur: (isinstance(new, torch.Tensor) and new.dtype == cur.dtype and new.shape == cur.shape
-                                 and new.is_contiguous() and new.data_ptr() != cur.data_ptr())
-        carry = {id(self.next_obs): next_obs} if fits(next_obs, self.next_obs) else {}
+        # Everything the reference does after env.step (sync_step_rollout.py:202-212) rides on the same K0 launch: the
+        # env's outputs for the next step replace next_obs / next masks (a raw float32 [N, C, H, W] observation is
+        # transposed into the packed layout on the way), next_episode_starts becomes terminations | truncations, and
+        # the step counter advances -- no launch of its own for any of them.
+        same = lambda new, cur: (isinstance(new, torch.Tensor) and new.is_cuda and new.is_contiguous()
+                                 and new.data_ptr() != cur.data_ptr())
+        fits = lambda new, cur: same(new, cur) and new.dtype == cur.dtype and new.shape == cur.shape
+        carry, carry_or, pack = {}, {}, None
+        if fits(next_obs, self.next_obs):
+            carry[id(self.next_obs)] = next_obs
+        elif (self._packed and same(next_obs, self.next_obs) and next_obs.dtype == torch.float32 and next_obs.dim() == 4
+              and self.next_obs.shape[-1] <= 128
+              and tuple(self.next_obs.shape) == (next_obs.shape[0], next_obs.shape[2], next_obs.shape[3], self.next_obs.shape[-1])):
+            N, Cc, H, W = next_obs.shape
+            carry[id(self.next_obs)] = next_obs
+            pack = (0, N, Cc, H * W, self.next_obs.shape[-1])  # _fields puts the observation first
         masks = self.get_action_mask() if self.next_action_masks is not None else None
+        pairs = []
         if masks is not None:
             pairs = ([(self.next_action_masks[k], masks[k]) for k in self.next_action_masks]
                      if isinstance(self.next_action_masks, dict) else [(self.next_action_masks, masks)])
             carry.update({id(cur): new for cur, new in pairs if fits(new, cur)})
-        ops.rollout_store_step(src, dst, self.step_count, carry=[carry.get(id(t)) for t in src])
+        starts = self.next_episode_starts
+        if fits(terminations, starts) and fits(truncations, starts):
+            carry[id(starts)], carry_or[id(starts)] = terminations, truncations
+        ops.rollout_store_step(src, dst, self.step_count, carry=[carry.get(id(t)) for t in src],
+                               carry_or=[carry_or.get(id(t)) for t in src], pack=pack, advance_ticket=self._k0_ticket)
         if id(self.next_obs) not in carry:
             self._set_next_obs(next_obs)
-        torch.logical_or(terminations, truncations, out=self.next_episode_starts)
-        if masks is not None:
-            for cur, new in pairs:
-                if id(cur) not in carry:
-                    cur.copy_(new)
-        self.step_count.add_(1)
+        if id(starts) not in carry:
+            torch.logical_or(terminations, truncations, out=starts)
+        for cur, new in pairs:
+            if id(cur) not in carry:
+                cur.copy_(new)
 
     def _capture(self, fn):
         """Warm up on a side stream, then capture `fn` once (torch.cuda.graph)."""
@@ -366,11 +383,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
                 if device_env:
                     self._graph, _ = self._capture(self._device_env_step)
                 else:
-                    def policy_part():
-                        a = self._policy_step()
-                        self.step_count.add_(1)
-                        return a
-                    self._graph, self._graph_outputs = self._capture(policy_part)
+                    self._graph, self._graph_outputs = self._capture(self._policy_step)
         self.step_count.fill_(self._rollouts_done * T)  # row 0 of the buffer, fresh RNG offsets
         self._rollouts_done += 1
         if not device_env:
@@ -400,7 +413,6 @@ class SyncStepRolloutGenerator(RolloutGenerator):
             else:
                 with torch.no_grad():
                     a = self._policy_step()
-                    self.step_count.add_(1)
             next_obs, rewards, terminations, truncations, _ = self.vec_env.step(self._env_actions(a, landed=True))
             self._set_next_obs(next_obs)
             if self.get_action_mask is not None and self.next_action_masks is not None:

@@ -50,9 +50,10 @@ def test_workspace_queries_are_host_only():
 
 
 def test_structs_match_the_header_layout():
-    # field order of the two structs that cross the ABI (a reordering would silently corrupt calls)
+    # field order of the structs that cross the ABI (a reordering would silently corrupt calls)
     text = open(HEADER).read()
-    for struct, cls in (("b200rl_ppo_args", _lib.PpoArgs), ("b200rl_gridnet_desc", _lib.GridnetDesc)):
+    for struct, cls in (("b200rl_ppo_args", _lib.PpoArgs), ("b200rl_gridnet_desc", _lib.GridnetDesc),
+                        ("b200rl_store_pack", _lib.StorePack)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), text, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = [re.search(r"(\w+)\s*$", decl.strip()).group(1) for decl in body.split(";") if decl.strip()]

@@ -123,6 +123,77 @@ def test_rollout_store_step_with_carry_over(cuda):
         ops.rollout_store_step(dev_cur, bufs, counter, carry=[None, None, None, torch.zeros(N + 1, device=cuda)])
 
 
+@pytest.mark.parametrize("N,C,H,W,Cp", [(24, 74, 16, 16, 80), (3, 75, 64, 64, 80), (5, 3, 5, 7, 8), (2, 8, 4, 4, 8)])
+def test_rollout_store_step_fused_bookkeeping(cuda, N, C, H, W, Cp):
+    """K0, fused form: the packed observation goes to its buffer row and is replaced by the env's raw [N, C, H, W]
+    observation transposed into the packed layout; next_episode_starts <- terminations | truncations; a plain carry and a
+    field without; the step counter advances by one per launch (several launches in a row, and inside a captured graph:
+    the ticket returns to zero every time)."""
+    from rl_algo_impls_b200 import ops
+
+    T = 4
+    g = torch.Generator(device=cuda).manual_seed(N + C)
+    packed = torch.zeros((N, H, W, Cp), device=cuda)
+    packed[..., :C] = torch.randn((N, H, W, C), device=cuda, generator=g)
+    starts = torch.rand(N, device=cuda, generator=g) < 0.5
+    mask = torch.rand((N, H * W, 5), device=cuda, generator=g) < 0.3
+    values = torch.randn(N, device=cuda, generator=g)
+    bufs = [torch.zeros((T,) + tuple(t.shape), dtype=t.dtype, device=cuda) for t in (packed, starts, mask, values)]
+    counter = torch.tensor([T + 1], dtype=torch.int64, device=cuda)
+    ticket = torch.zeros(1, dtype=torch.int32, device=cuda)
+    cur = [packed, starts, mask, values]
+    raw, term, trunc, nmask = (torch.empty((N, C, H, W), device=cuda), torch.empty(N, dtype=torch.bool, device=cuda),
+                               torch.empty(N, dtype=torch.bool, device=cuda), torch.empty_like(mask))
+
+    def launch():
+        ops.rollout_store_step(cur, bufs, counter, carry=[raw, term, nmask, None], carry_or=[None, trunc, None, None],
+                               pack=(0, N, C, H * W, Cp), advance_ticket=ticket)
+
+    graph = None
+    for it in range(5):
+        before = [t.clone() for t in cur]
+        raw.copy_(torch.randn((N, C, H, W), device=cuda, generator=g))
+        term.copy_(torch.rand(N, device=cuda, generator=g) < 0.3), trunc.copy_(torch.rand(N, device=cuda, generator=g) < 0.3)
+        nmask.copy_(torch.rand(mask.shape, device=cuda, generator=g) < 0.3)
+        row = int(counter.item()) % T
+        if it < 2:
+            launch()
+        else:  # replays of one captured launch
+            if graph is None:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                keep = [t.clone() for t in cur] + [b.clone() for b in bufs] + [counter.clone()]
+                with torch.cuda.stream(side):
+                    launch()
+                torch.cuda.current_stream().wait_stream(side)
+                for t, k in zip(cur + bufs + [counter], keep):  # undo the warm-up launch
+                    t.copy_(k)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    launch()
+                for t, k in zip(cur + bufs + [counter], keep):  # capture does not run the launch; be explicit anyway
+                    t.copy_(k)
+            graph.replay()
+        torch.cuda.synchronize()
+        for k in range(4):
+            assert torch.equal(bufs[k][row], before[k]), (it, k)
+        want = torch.zeros_like(packed)
+        want[..., :C] = raw.permute(0, 2, 3, 1)
+        assert torch.equal(packed, want), it
+        assert torch.equal(starts, term | trunc) and torch.equal(mask, nmask) and torch.equal(values, before[3])
+        assert int(counter.item()) == T + 1 + it + 1 and int(ticket.item()) == 0
+
+
+def test_rollout_store_step_advance_only(cuda):
+    """No field at all: the launch still advances the counter."""
+    from rl_algo_impls_b200 import ops
+
+    counter = torch.tensor([41], dtype=torch.int64, device=cuda)
+    ticket = torch.zeros(1, dtype=torch.int32, device=cuda)
+    ops.rollout_store_step([], [], counter, advance_ticket=ticket)
+    assert int(counter.item()) == 42 and int(ticket.item()) == 0
+
+
 @pytest.mark.parametrize("cfg", ["C1", "C3", "C4", "C5"])
 def test_graph_replayed_rollout_equals_eager(cuda, cfg):
     """The CUDA-graph path (one replay per env step) fills the rollout buffer with exactly what the
