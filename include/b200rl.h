@@ -402,8 +402,9 @@ int b200rl_reward_assemble_f32(const float* base, int64_t V0, const float* const
  *   the ReLU zeroed the output.  relu == 0: plain bias + max-pool.
  *   _bwd: dx [N, H, W, C] is written everywhere (zero where no window routes a gradient); dbias [C] nullable;
  *   workspace: b200rl_nhwc_bias_grad_workspace_bytes(N * Ho * Wo, C) bytes (only read / written when dbias != NULL).
- *   b200rl_nhwc_bias_relu_*: out = relu(x + bias) over [rows, C]; out may alias x, dx may alias dout;
- *   workspace: b200rl_nhwc_bias_grad_workspace_bytes(rows, C). */
+ *   b200rl_nhwc_bias_relu_*: out = relu(x + bias) over [rows, C] (relu == 0: out = x + bias, the logit head's bias);
+ *   out may alias x, dx may alias dout; workspace: b200rl_nhwc_bias_grad_workspace_bytes(rows, C).
+ *   _bwd with out == NULL is the relu == 0 case: d x is dout itself (dx is not written), dbias its column sums. */
 size_t b200rl_nhwc_bias_grad_workspace_bytes(int64_t rows, int64_t C);
 int b200rl_nhwc_bias_pool_relu_fwd(const float* x, const float* bias /*nullable*/, float* out, uint8_t* argmax /*nullable*/,
                                    int64_t N, int64_t H, int64_t W, int64_t C, int kernel, int stride, int padding,
@@ -411,9 +412,9 @@ int b200rl_nhwc_bias_pool_relu_fwd(const float* x, const float* bias /*nullable*
 int b200rl_nhwc_bias_pool_relu_bwd(const float* dout, const uint8_t* argmax, float* dx, float* dbias /*nullable*/,
                                    void* workspace, size_t workspace_bytes, int64_t N, int64_t H, int64_t W, int64_t C,
                                    int kernel, int stride, int padding, b200rl_stream_t stream);
-int b200rl_nhwc_bias_relu_fwd(const float* x, const float* bias, float* out, int64_t rows, int64_t C,
+int b200rl_nhwc_bias_relu_fwd(const float* x, const float* bias, float* out, int64_t rows, int64_t C, int relu,
                               b200rl_stream_t stream);
-int b200rl_nhwc_bias_relu_bwd(const float* dout, const float* out, float* dx, float* dbias /*nullable*/, void* workspace,
+int b200rl_nhwc_bias_relu_bwd(const float* dout, const float* out /*nullable*/, float* dx, float* dbias /*nullable*/, void* workspace,
                               size_t workspace_bytes, int64_t rows, int64_t C, b200rl_stream_t stream);
 
 #ifdef __cplusplus

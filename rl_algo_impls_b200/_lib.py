@@ -150,7 +150,7 @@ PROTOTYPES = {
     "b200rl_nhwc_bias_grad_workspace_bytes": (_sz, [_i64, _i64]),
     "b200rl_nhwc_bias_pool_relu_fwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),
     "b200rl_nhwc_bias_pool_relu_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _i64, _i64, _i64, _i64, _int, _int, _int, _vp]),
-    "b200rl_nhwc_bias_relu_fwd": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "b200rl_nhwc_bias_relu_fwd": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp]),
     "b200rl_nhwc_bias_relu_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _i64, _i64, _vp]),
 }
 

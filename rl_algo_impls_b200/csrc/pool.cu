@@ -91,22 +91,43 @@ __global__ void __launch_bounds__(kPoolBlock) pool_fwd_kernel(const PoolDev G) {
 #pragma unroll
   for (int j = 0; j < VEC; ++j) m[j] = -INFINITY, am[j] = (uint8_t)(kh_first * k + kw_first);
   const float* xn = G.x + n * G.H * G.W * G.C + c;
+  if constexpr (K > 0) {
+    // compile-time window: every load of the window is issued before the first compare (out-of-range taps re-read a
+    // clamped position and are skipped by the scan), instead of one round trip per tap
+    float v[K * K][VEC];
+    bool ok[K * K];
 #pragma unroll
-  for (int kh = 0; kh < (K > 0 ? K : 15); ++kh) {
-    if (kh >= k) break;
-    const int h = h0 + kh;
-    if (h < 0 || h >= G.H) continue;
+    for (int kh = 0; kh < K; ++kh)
 #pragma unroll
-    for (int kw = 0; kw < (K > 0 ? K : 15); ++kw) {
-      if (kw >= k) break;
-      const int w = w0 + kw;
-      if (w < 0 || w >= G.W) continue;
-      float v[VEC];
-      load_vec<VEC>(xn + ((long long)h * G.W + w) * G.C, v);
+      for (int kw = 0; kw < K; ++kw) {
+        const int h = h0 + kh, w = w0 + kw;
+        ok[kh * K + kw] = h >= 0 && h < G.H && w >= 0 && w < G.W;
+        const int hc = h < 0 ? 0 : (h >= G.H ? G.H - 1 : h), wc = w < 0 ? 0 : (w >= G.W ? G.W - 1 : w);
+        load_vec<VEC>(xn + ((long long)hc * G.W + wc) * G.C, v[kh * K + kw]);
+      }
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) {
+      if (!ok[t]) continue;
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        const float vb = v[j] + b[j];
-        if (vb > m[j] || vb != vb) m[j] = vb, am[j] = (uint8_t)(kh * k + kw);
+        const float vb = v[t][j] + b[j];
+        if (vb > m[j] || vb != vb) m[j] = vb, am[j] = (uint8_t)t;
+      }
+    }
+  } else {
+    for (int kh = 0; kh < k; ++kh) {
+      const int h = h0 + kh;
+      if (h < 0 || h >= G.H) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int w = w0 + kw;
+        if (w < 0 || w >= G.W) continue;
+        float v[VEC];
+        load_vec<VEC>(xn + ((long long)h * G.W + w) * G.C, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float vb = v[j] + b[j];
+          if (vb > m[j] || vb != vb) m[j] = vb, am[j] = (uint8_t)(kh * k + kw);
+        }
       }
     }
   }
@@ -146,6 +167,36 @@ __global__ void __launch_bounds__(kPoolBlock) pool_bwd_kernel(const PoolDev G) {
   float acc[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  const int nh = ho_hi - ho_lo + 1, nw = wo_hi - wo_lo + 1;
+  if (nh <= 2 && nw <= 2) {
+    // at most 2 x 2 covering windows (kernel <= 2 * stride: the encoder's 3 / 2): their codes and gradients are all
+    // loaded before the first compare (absent windows re-read a clamped one and are skipped), same order of the sum
+    uint8_t am[4][VEC];
+    float g[4][VEC];
+    bool ok[4];
+    uint8_t code[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        ok[a * 2 + b] = a < nh && b < nw;
+        int ho = ho_lo + a, wo = wo_lo + b;
+        ho = ho > G.Ho - 1 ? G.Ho - 1 : ho, wo = wo > G.Wo - 1 ? G.Wo - 1 : wo;
+        code[a * 2 + b] = (uint8_t)((hp - ho * G.s) * G.k + (wp - wo * G.s));
+        const long long o = ((n * G.Ho + ho) * G.Wo + wo) * G.C + c;
+        load_codes<VEC>(G.argmax + o, am[a * 2 + b]);
+        load_vec<VEC>(G.dout + o, g[a * 2 + b]);
+      }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (!ok[t]) continue;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        if (am[t][j] == code[t]) acc[j] += g[t][j];
+    }
+    store_vec<VEC>(G.dx + ((n * G.H + h) * G.W + w) * G.C + c, acc);
+    return;
+  }
   for (int ho = ho_lo; ho <= ho_hi; ++ho)
     for (int wo = wo_lo; wo <= wo_hi; ++wo) {
       const uint8_t code = (uint8_t)((hp - ho * G.s) * G.k + (wp - wo * G.s));
@@ -166,7 +217,7 @@ __global__ void __launch_bounds__(kPoolBlock) pool_bwd_kernel(const PoolDev G) {
 }
 
 // ---- bias + ReLU (decoder): elementwise over [rows, C] -------------------------------------------------
-template <int VEC>
+template <int VEC, bool RELU>
 __global__ void __launch_bounds__(kPoolBlock) bias_relu_fwd_kernel(const float* x, const float* bias, float* out,
                                                                    long long n_vec, int Cv) {
   const long long i = (long long)blockIdx.x * kPoolBlock + threadIdx.x;
@@ -177,7 +228,7 @@ __global__ void __launch_bounds__(kPoolBlock) bias_relu_fwd_kernel(const float* 
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     const float vb = v[j] + b[j];
-    v[j] = (vb > 0.f || vb != vb) ? vb : 0.f;
+    v[j] = (!RELU || vb > 0.f || vb != vb) ? vb : 0.f;
   }
   store_vec<VEC>(out + i * VEC, v);
 }
@@ -197,7 +248,8 @@ __global__ void __launch_bounds__(kPoolBlock) relu_bwd_kernel(const float* dout,
 }
 
 // ---- d bias: masked column sums of dout [rows, C] --------------------------------------------------------
-// MASK 0: argmax code != kDead (pooled outputs), 1: out > 0 (bias + ReLU outputs; `out <= 0` drops, NaN passes).
+// MASK 0: argmax code != kDead (pooled outputs), 1: out > 0 (bias + ReLU outputs; `out <= 0` drops, NaN passes),
+// 2: every entry (plain bias).
 // Grid (channel tiles, slabs): a CTA of TX x TY threads owns TX channel vectors and the rows of one slab; thread
 // (cx, ry) sums rows ry, ry + TY, ...; the TY partials fold in shared memory in ry order; stage 2 adds the slabs in
 // slab order.
@@ -233,12 +285,15 @@ __global__ void __launch_bounds__(kPoolBlock) colsum_partial_kernel(const ColSum
 #pragma unroll
         for (int j = 0; j < VEC; ++j)
           if (am[j] != kDead) acc[j] += g[j];
-      } else {
+      } else if constexpr (MASK == 1) {
         float ov[VEC];
         load_vec<VEC>(G.out + o, ov);
 #pragma unroll
         for (int j = 0; j < VEC; ++j)
           if (!(ov[j] <= 0.f)) acc[j] += g[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] += g[j];
       }
     }
   }
@@ -253,12 +308,21 @@ __global__ void __launch_bounds__(kPoolBlock) colsum_partial_kernel(const ColSum
   }
 }
 
+// stage 2: a CTA owns 32 channels; thread (cx, sy) adds slabs sy, sy + 8, ... (independent loads), the 8 partials fold in
+// sy order -- a fixed order, whatever the slab count
 __global__ void __launch_bounds__(kPoolBlock) colsum_final_kernel(const float* partial, float* dbias, int slabs, int C) {
-  const int c = blockIdx.x * kPoolBlock + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float s_part[kPoolBlock];
+  const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float acc = 0.f;
-  for (int s = 0; s < slabs; ++s) acc += partial[(long long)s * C + c];
-  dbias[c] = acc;
+  if (c < C)
+    for (int s = sy; s < slabs; s += kPoolBlock / 32) acc += partial[(long long)s * C + c];
+  s_part[threadIdx.x] = acc;
+  __syncthreads();
+  if (sy == 0 && c < C) {
+    for (int q = 1; q < kPoolBlock / 32; ++q) acc += s_part[q * 32 + cx];
+    dbias[c] = acc;
+  }
 }
 
 // lanes over channel vectors (the smallest power of two >= min(Cv, 32)) and the number of row slabs
@@ -297,13 +361,16 @@ static int launch_colsum(const float* dout, const uint8_t* argmax, const float* 
   if (argmax) {
     if (v4) colsum_partial_kernel<4, 0><<<grid, kPoolBlock, 0, stream>>>(G);
     else colsum_partial_kernel<1, 0><<<grid, kPoolBlock, 0, stream>>>(G);
-  } else {
+  } else if (out) {
     if (v4) colsum_partial_kernel<4, 1><<<grid, kPoolBlock, 0, stream>>>(G);
     else colsum_partial_kernel<1, 1><<<grid, kPoolBlock, 0, stream>>>(G);
+  } else {
+    if (v4) colsum_partial_kernel<4, 2><<<grid, kPoolBlock, 0, stream>>>(G);
+    else colsum_partial_kernel<1, 2><<<grid, kPoolBlock, 0, stream>>>(G);
   }
   int rc = check_launch(who);
   if (rc) return rc;
-  colsum_final_kernel<<<(C + kPoolBlock - 1) / kPoolBlock, kPoolBlock, 0, stream>>>(partial, dbias, slabs, C);
+  colsum_final_kernel<<<(C + 31) / 32, kPoolBlock, 0, stream>>>(partial, dbias, slabs, C);
   return check_launch(who);
 }
 
@@ -380,7 +447,7 @@ extern "C" int b200rl_nhwc_bias_pool_relu_bwd(const float* dout, const uint8_t* 
                        "nhwc_bias_pool_relu_bwd (bias gradient)");
 }
 
-extern "C" int b200rl_nhwc_bias_relu_fwd(const float* x, const float* bias, float* out, int64_t rows, int64_t C,
+extern "C" int b200rl_nhwc_bias_relu_fwd(const float* x, const float* bias, float* out, int64_t rows, int64_t C, int relu,
                                          b200rl_stream_t stream) {
   using namespace b200rl;
   B200RL_REQUIRE(rows >= 0 && C >= 1 && C <= (1 << 20), "nhwc_bias_relu_fwd: bad shape");
@@ -391,8 +458,11 @@ extern "C" int b200rl_nhwc_bias_relu_fwd(const float* x, const float* bias, floa
   const long long n_vec = rows * C / vec;
   B200RL_UNSUPPORTED((n_vec + kPoolBlock - 1) / kPoolBlock > 0x7fffffffLL, "nhwc_bias_relu_fwd: tensor too large");
   const unsigned grid = (unsigned)((n_vec + kPoolBlock - 1) / kPoolBlock);
-  if (v4) bias_relu_fwd_kernel<4><<<grid, kPoolBlock, 0, (cudaStream_t)stream>>>(x, bias, out, n_vec, (int)(C / 4));
-  else bias_relu_fwd_kernel<1><<<grid, kPoolBlock, 0, (cudaStream_t)stream>>>(x, bias, out, n_vec, (int)C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (v4 && relu) bias_relu_fwd_kernel<4, true><<<grid, kPoolBlock, 0, st>>>(x, bias, out, n_vec, (int)(C / 4));
+  else if (v4) bias_relu_fwd_kernel<4, false><<<grid, kPoolBlock, 0, st>>>(x, bias, out, n_vec, (int)(C / 4));
+  else if (relu) bias_relu_fwd_kernel<1, true><<<grid, kPoolBlock, 0, st>>>(x, bias, out, n_vec, (int)C);
+  else bias_relu_fwd_kernel<1, false><<<grid, kPoolBlock, 0, st>>>(x, bias, out, n_vec, (int)C);
   return check_launch("nhwc_bias_relu_fwd");
 }
 
@@ -400,7 +470,7 @@ extern "C" int b200rl_nhwc_bias_relu_bwd(const float* dout, const float* out, fl
                                          size_t workspace_bytes, int64_t rows, int64_t C, b200rl_stream_t stream) {
   using namespace b200rl;
   B200RL_REQUIRE(rows >= 0 && C >= 1 && C <= (1 << 20), "nhwc_bias_relu_bwd: bad shape");
-  B200RL_REQUIRE(rows == 0 || (dout && out && dx), "nhwc_bias_relu_bwd: null pointer");
+  B200RL_REQUIRE(rows == 0 || (dout && (out == nullptr || dx)), "nhwc_bias_relu_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) {
     if (dbias) cudaMemsetAsync(dbias, 0, (size_t)C * sizeof(float), st);
@@ -411,6 +481,7 @@ extern "C" int b200rl_nhwc_bias_relu_bwd(const float* dout, const float* out, fl
     int rc = launch_colsum(dout, nullptr, out, dbias, workspace, workspace_bytes, rows, (int)C, st, "nhwc_bias_relu_bwd (bias gradient)");
     if (rc) return rc;
   }
+  if (out == nullptr) return B200RL_OK;  // plain bias: dx IS dout, nothing to mask
   const bool v4 = C % 4 == 0 && aligned16(dout) && aligned16(out) && aligned16(dx);
   const int vec = v4 ? 4 : 1;
   const long long n_vec = rows * C / vec;

@@ -1005,34 +1005,38 @@ class _BiasPoolReluFn(torch.autograd.Function):
 
 
 class _BiasReluFn(torch.autograd.Function):
-    """relu(y + bias) on a channels-last map in one launch; backward = ReLU mask + two-stage bias-gradient sum."""
+    """relu(y + bias) -- or y + bias alone -- on a channels-last map in one launch, written over y (a convolution's
+    output, which its own backward never reads); backward = ReLU mask + two-stage bias-gradient sum."""
 
     @staticmethod
-    def forward(ctx, y, bias):
-        y = _nhwc(y)
-        N, Cc, H, W = y.shape
-        out = torch.empty_like(y, memory_format=torch.channels_last)
-        rc = _call("b200rl_nhwc_bias_relu_fwd", 1, _lib.lib().b200rl_nhwc_bias_relu_fwd, y.data_ptr(), bias.data_ptr(),
-                   out.data_ptr(), N * H * W, Cc, _stream())
+    def forward(ctx, y, bias, relu):
+        yc = _nhwc(y)
+        N, Cc, H, W = yc.shape
+        # in place when y itself is the dense channels-last buffer nobody else needs (no-grad passes included)
+        out = yc if (yc is y and not (y.requires_grad and y.is_leaf)) else torch.empty_like(yc, memory_format=torch.channels_last)
+        rc = _call("b200rl_nhwc_bias_relu_fwd", 1, _lib.lib().b200rl_nhwc_bias_relu_fwd, yc.data_ptr(), bias.data_ptr(),
+                   out.data_ptr(), N * H * W, Cc, int(relu), _stream())
         check(rc, "b200rl_nhwc_bias_relu_fwd")
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+        if out is y:
+            ctx.mark_dirty(y)
+        ctx.relu, ctx.want_bias = relu, ctx.needs_input_grad[1]
+        if relu and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
             ctx.save_for_backward(out)
-            ctx.want_bias = ctx.needs_input_grad[1]
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (out,) = ctx.saved_tensors
-        N, Cc, H, W = out.shape
         dout = _nhwc(dout)
-        dx = torch.empty_like(out, memory_format=torch.channels_last)
+        N, Cc, H, W = dout.shape
+        out = ctx.saved_tensors[0] if ctx.relu else None
+        dx = torch.empty_like(dout, memory_format=torch.channels_last) if ctx.relu else dout
         dbias = torch.empty(Cc, dtype=torch.float32, device=dout.device) if ctx.want_bias else None
         L = _lib.lib()
         ws = _workspace(L.b200rl_nhwc_bias_grad_workspace_bytes(N * H * W, Cc), dout.device)
-        rc = _call("b200rl_nhwc_bias_relu_bwd", 3 if ctx.want_bias else 1, L.b200rl_nhwc_bias_relu_bwd, dout.data_ptr(),
-                   out.data_ptr(), dx.data_ptr(), _ptr(dbias), ws.data_ptr(), ws.numel(), N * H * W, Cc, _stream())
+        rc = _call("b200rl_nhwc_bias_relu_bwd", (2 if ctx.want_bias else 0) + int(ctx.relu), L.b200rl_nhwc_bias_relu_bwd,
+                   dout.data_ptr(), _ptr(out), dx.data_ptr(), _ptr(dbias), ws.data_ptr(), ws.numel(), N * H * W, Cc, _stream())
         check(rc, "b200rl_nhwc_bias_relu_bwd")
-        return dx, dbias
+        return dx, dbias, None
 
 
 def bias_pool_relu(y: torch.Tensor, bias: Optional[torch.Tensor], kernel: int = 3, stride: int = 2, padding: int = 1,
@@ -1045,8 +1049,9 @@ def bias_pool_relu(y: torch.Tensor, bias: Optional[torch.Tensor], kernel: int = 
     return _BiasPoolReluFn.apply(y, bias, int(kernel), int(stride), int(padding), bool(relu))
 
 
-def bias_relu(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-    """``relu(y + bias[None, :, None, None])`` for a float32 CUDA map, channels-last in memory (gridnet_decoder.py:36-53)."""
+def bias_relu(y: torch.Tensor, bias: torch.Tensor, relu: bool = True) -> torch.Tensor:
+    """``relu(y + bias[None, :, None, None])`` (``relu=False``: the sum alone) for a float32 CUDA map, channels-last in
+    memory (gridnet_decoder.py:36-53).  ``y`` -- a convolution's output -- is overwritten when it can be."""
     _check_map(y)
     _cuda(bias.detach(), torch.float32, "bias")
-    return _BiasReluFn.apply(y, bias)
+    return _BiasReluFn.apply(y, bias, bool(relu))

@@ -84,22 +84,31 @@ def test_bias_pool_relu_accepts_nchw_strides(cuda):
     assert torch.equal(ops.bias_pool_relu(y, bias), F.relu(F.max_pool2d(y + bias[None, :, None, None], 3, 2, 1)))
 
 
-@pytest.mark.parametrize("N,C,H,W", [(24, 128, 2, 2), (24, 32, 8, 8), (5, 6, 3, 7), (3072, 32, 8, 8), (0, 8, 2, 2)])
-def test_bias_relu_matches_torch(cuda, N, C, H, W):
+@pytest.mark.parametrize("N,C,H,W", [(24, 128, 2, 2), (24, 32, 8, 8), (5, 6, 3, 7), (3072, 32, 8, 8), (256, 80, 16, 16),
+                                     (0, 8, 2, 2)])
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_bias_relu_matches_torch(cuda, N, C, H, W, relu, inplace):
+    """relu=False is the logit head's plain bias; inplace: the input is a non-leaf (as a convolution's output is) and
+    is overwritten."""
     from rl_algo_impls_b200 import ops
 
     y = _map((N, C, H, W), cuda, 5).requires_grad_(True)
     bias = (torch.randn(C, device=cuda) * 0.5).requires_grad_(True)
     y2, b2 = y.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
-    got = ops.bias_relu(y, bias)
-    want = F.relu(y2 + b2[None, :, None, None])
+    src = (y * 1.0).contiguous(memory_format=torch.channels_last) if inplace else y
+    got = ops.bias_relu(src, bias, relu=relu)
+    assert (got.data_ptr() == src.data_ptr()) == (inplace or N == 0)
+    want = y2 + b2[None, :, None, None]
+    if relu:
+        want = F.relu(want)
     assert torch.equal(got, want) and got.is_contiguous(memory_format=torch.channels_last)
     if N == 0:
         return
     dout = _map(tuple(want.shape), cuda, 6, sparse=False)
     got.backward(dout)
     want.backward(dout)
-    assert torch.equal(y.grad, y2.grad)  # a mask: exact
+    assert torch.equal(y.grad, y2.grad)  # a mask (or the identity): exact
     close(bias.grad, b2.grad, rtol=1e-5, what="dbias")
 
 
