@@ -59,6 +59,11 @@ const char* b200rl_last_error(void);
  * no pending CUDA error behind. */
 int b200rl_host_register(void* ptr, size_t bytes);
 int b200rl_host_unregister(void* ptr);
+/* One env step's uploads in one call: dst[i] (device) <- src[i] (page-locked host), bytes[i] each, asynchronous on
+ * `stream`, in order.  Replaces the per-field obs / mask transfers of rollout/sync_step_rollout.py:181-216 through
+ * policy.step (shared/policy/actor_critic.py:306-318). */
+int b200rl_h2d_batch(int n, void* const* dst_host, const void* const* src_host, const int64_t* bytes_host,
+                     b200rl_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K1  GAE(lambda) reverse-time scan + returns.
@@ -307,7 +312,10 @@ int b200rl_gridnet_num_actions(const b200rl_gridnet_desc* d, const uint8_t* mask
  */
 int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
                           const uint8_t* pick_mask, uint64_t seed, uint64_t offset, const int64_t* offset_dev,
-                          void* actions_out, void* pick_actions_out, float* logp, b200rl_stream_t stream);
+                          void* actions_out, void* pick_actions_out, float* logp,
+                          int64_t* actions_wide_out /*nullable: the per-cell actions once more as int64 [B, HW, A], what a
+                          host env is handed (actor_critic.py:315-318) -- no cast on the host*/,
+                          b200rl_stream_t stream);
 int b200rl_categorical_sample_f32(const float* logits, const uint8_t* mask, int64_t R, int64_t n, uint64_t seed,
                                   uint64_t offset, const int64_t* offset_dev, int64_t* actions_out, float* logp,
                                   b200rl_stream_t stream);

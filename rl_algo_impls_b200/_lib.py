@@ -121,7 +121,7 @@ PROTOTYPES = {
         [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, C.POINTER(PpoArgs), _vp, _vp, _vp, _vp, _sz, _vp, _sz, _int, _vp],
     ),
     "b200rl_gridnet_num_actions": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
-    "b200rl_gridnet_sample": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "b200rl_gridnet_sample": (_int, [C.POINTER(GridnetDesc), _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200rl_categorical_sample_f32": (_int, [_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
     "b200rl_running_norm_obs_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _int, C.c_double, C.c_double, _vp, _vp]),
     "b200rl_running_norm_reward_f32": (
@@ -147,6 +147,7 @@ PROTOTYPES = {
         _int,
         [_vp, _i64, C.POINTER(_vp), _int, _vp, _vp, C.POINTER(C.c_uint8), c_f32p, _vp, _i64, _vp],
     ),
+    "b200rl_h2d_batch": (_int, [_int, C.POINTER(_vp), C.POINTER(_vp), c_i64p, _vp]),
     "b200rl_nhwc_bias_grad_workspace_bytes": (_sz, [_i64, _i64]),
     "b200rl_nhwc_bias_pool_relu_fwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),
     "b200rl_nhwc_bias_pool_relu_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _i64, _i64, _i64, _i64, _int, _int, _int, _vp]),

@@ -71,3 +71,24 @@ extern "C" int b200rl_host_unregister(void* ptr) {
   }
   return B200RL_OK;
 }
+
+// One env step's host -> device copies in one call: dst[i] <- src[i] (bytes[i] each), cudaMemcpyAsync on `stream`, in
+// order.  The sources are page-locked (b200rl_host_register, or pinned allocations): plain DMAs, nothing staged.
+// Replaces the per-field obs / mask uploads of sync_step_rollout.py:181-216 (there: torch.as_tensor(...).to(device)
+// inside policy.step, actor_critic.py:306-318).
+extern "C" int b200rl_h2d_batch(int n, void* const* dst_host, const void* const* src_host, const int64_t* bytes_host,
+                                b200rl_stream_t stream) {
+  using namespace b200rl;
+  B200RL_REQUIRE(n >= 0 && (n == 0 || (dst_host && src_host && bytes_host)), "h2d_batch: null pointer");
+  for (int i = 0; i < n; ++i) {
+    B200RL_REQUIRE(bytes_host[i] >= 0 && (bytes_host[i] == 0 || (dst_host[i] && src_host[i])), "h2d_batch: copy %d is null", i);
+    if (bytes_host[i] == 0) continue;
+    cudaError_t e = cudaMemcpyAsync(dst_host[i], src_host[i], (size_t)bytes_host[i], cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+      set_error("h2d_batch: copy %d (%lld bytes): %s", i, (long long)bytes_host[i], cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return B200RL_ECUDA;
+    }
+  }
+  return B200RL_OK;
+}

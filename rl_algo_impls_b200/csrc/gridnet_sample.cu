@@ -34,6 +34,7 @@ struct SampleDev {
   const long long* offset_dev;
   void* actions_out;
   int act_dtype;
+  long long* actions_wide;  // nullable: the same actions once more as int64 (what a host env is handed)
   void* pick_out;
   int pick_dtype;
   float* logp;
@@ -53,12 +54,19 @@ __device__ __forceinline__ float logit_at(const SampleDev& G, long long i) {
   return G.logits_dtype == B200RL_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(G.logits)[i])
                                        : static_cast<const float*>(G.logits)[i];
 }
+__device__ __forceinline__ void put_index(void* base, int dtype, long long i, long long v);
+// a per-cell action: into the compact rollout-buffer dtype and, when asked for, the int64 copy for the host
+__device__ __forceinline__ void put_action(const struct SampleDev& G, long long i, long long v);
 __device__ __forceinline__ void put_index(void* base, int dtype, long long i, long long v) {
   switch (dtype) {
     case B200RL_U8: static_cast<uint8_t*>(base)[i] = (uint8_t)v; break;
     case B200RL_I32: static_cast<int32_t*>(base)[i] = (int32_t)v; break;
     default: static_cast<long long*>(base)[i] = v; break;
   }
+}
+__device__ __forceinline__ void put_action(const SampleDev& G, long long i, long long v) {
+  put_index(G.actions_out, G.act_dtype, i, v);
+  if (G.actions_wide) G.actions_wide[i] = v;
 }
 // -log(-log u): sampling noise only (never enters a reported log-prob), so the fast logarithms do
 __device__ __forceinline__ float gumbel(uint32_t bits) { return -__logf(-__logf(u01(bits))); }
@@ -86,6 +94,8 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
   const int words = (int)((G.HW + 31) >> 5);
   for (int w = tid; w < words; w += kSampleBlock) s_bitmap[w] = 0u;
   zero_fill<kSampleBlock>(static_cast<uint8_t*>(G.actions_out) + b * act_bytes, (uint32_t)act_bytes);
+  if (G.actions_wide)
+    zero_fill<kSampleBlock>(reinterpret_cast<uint8_t*>(G.actions_wide + b * G.HW * G.A), (uint32_t)(G.HW * G.A * 8));
   __syncthreads();
   scan_mask<kSampleBlock>(G.mask + b * G.HW * G.S, (uint32_t)G.HW * (uint32_t)G.S, (uint32_t)G.S, s_bitmap,
                           RowPrefetch{nullptr, 0u, 0u});
@@ -196,7 +206,7 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
       float lp = 0.f;
       if (my_parts > 0) {
         a = finish(d, &lp);
-        put_index(G.actions_out, G.act_dtype, cell * G.A + h, a);
+        put_action(G, cell * G.A + h, a);
       }
       const int a_ref = __shfl_sync(0xffffffffu, a, ref_lane);
       if (my_parts > 0 && (gr < 0 || a_ref == gate_val)) logp_acc += lp;
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
       const long long cell = b * G.HW + s_list[u];
       float lp;
       const int a = sample_head(cell, h, &lp);
-      put_index(G.actions_out, G.act_dtype, cell * G.A + h, a);
+      put_action(G, cell * G.A + h, a);
       s_lp[item] = lp;
     }
     __syncthreads();  // actions of the reference heads are written
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
       float lp[B200RL_MAX_HEADS];
       for (int h = 0; h < G.A; ++h) {
         chosen[h] = sample_head(cell, h, &lp[h]);
-        put_index(G.actions_out, G.act_dtype, cell * G.A + h, chosen[h]);
+        put_action(G, cell * G.A + h, chosen[h]);
       }
       for (int h = 0; h < G.A; ++h) {
         const int gr = G.gate_ref[h];
@@ -309,7 +319,7 @@ __global__ void __launch_bounds__(kSampleBlock) gridnet_sample_kernel(const Samp
 extern "C" int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* logits, const uint8_t* mask,
                                      const uint8_t* pick_mask, uint64_t seed, uint64_t offset,
                                      const int64_t* offset_dev, void* actions_out, void* pick_actions_out,
-                                     float* logp, b200rl_stream_t stream) {
+                                     float* logp, int64_t* actions_wide_out, b200rl_stream_t stream) {
   using namespace b200rl;
   B200RL_REQUIRE(d && logits && mask && actions_out && logp, "gridnet_sample: null pointer");
   B200RL_REQUIRE(d->B >= 0 && d->HW >= 1 && d->A >= 1 && d->A <= B200RL_MAX_HEADS && d->n_pick >= 0,
@@ -356,6 +366,7 @@ extern "C" int b200rl_gridnet_sample(const b200rl_gridnet_desc* d, const void* l
     G.max_part_count = max_count;
   }
   G.seed = seed, G.offset = offset, G.offset_dev = reinterpret_cast<const long long*>(offset_dev);
+  G.actions_wide = reinterpret_cast<long long*>(actions_wide_out);
   G.actions_out = actions_out, G.act_dtype = d->act_dtype, G.pick_out = pick_actions_out, G.pick_dtype = d->pick_dtype;
   G.logp = logp;
   B200RL_UNSUPPORTED(d->HW > 16384, "gridnet_sample: HW=%lld cells exceeds 16384", (long long)d->HW);

@@ -933,9 +933,15 @@ def gridnet_num_actions(spec: GridnetSpec, mask: torch.Tensor, pick_mask: Option
 
 
 def gridnet_sample(spec: GridnetSpec, logits, mask, pick_mask, seed: int, offset: int, act_dtype=torch.uint8,
-                   offset_dev: Optional[torch.Tensor] = None):
-    """Sample per-cell actions (+ pick) and their joint log-prob in one launch (gridnet.py:195-207)."""
+                   offset_dev: Optional[torch.Tensor] = None, wide_out: Optional[torch.Tensor] = None):
+    """Sample per-cell actions (+ pick) and their joint log-prob in one launch (gridnet.py:195-207).
+    ``wide_out`` ([B, HW, A] int64, optional) receives the per-cell actions a second time as int64: what a host env
+    is handed, without a cast on the host."""
     g = _GridCall(spec, logits, mask, pick_mask, None, None)
+    if wide_out is not None:
+        _cuda(wide_out, torch.int64, "wide_out")
+        if wide_out.numel() != g.B * g.HW * g.A:
+            raise ValueError(f"wide_out {tuple(wide_out.shape)} does not hold [{g.B}, {g.HW}, {g.A}] actions")
     actions = torch.empty((g.B, g.HW, g.A), dtype=act_dtype, device=logits.device)
     pick = torch.empty((g.B, spec.n_pick), dtype=torch.int64, device=logits.device) if spec.n_pick else None
     logp = torch.empty(g.B, dtype=torch.float32, device=logits.device)
@@ -943,7 +949,7 @@ def gridnet_sample(spec: GridnetSpec, logits, mask, pick_mask, seed: int, offset
     g.desc.pick_dtype = _lib.I64
     rc = _call("b200rl_gridnet_sample", 1, _lib.lib().b200rl_gridnet_sample,
         C.byref(g.desc), logits.data_ptr(), g.mask.data_ptr(), _ptr(g.pick_mask), seed, offset, _ptr(offset_dev),
-        actions.data_ptr(), _ptr(pick), logp.data_ptr(), _stream(),
+        actions.data_ptr(), _ptr(pick), logp.data_ptr(), _ptr(wide_out), _stream(),
     )  # fmt: skip
     check(rc, "b200rl_gridnet_sample")
     return actions, pick, logp

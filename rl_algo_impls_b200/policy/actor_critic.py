@@ -52,6 +52,8 @@ def clamp_actions(actions: NumpyOrDict, action_space, squash_output: bool) -> Nu
 
 
 class ActorCritic(nn.Module):
+    supports_wide_actions = True  # step_device(wide_out=...): GridNet per-cell actions also as int64 (host envs)
+
     def __init__(self, env, network: Optional[nn.Module] = None, subaction_mask=None, squash_output: bool = False,
                  **hyperparams) -> None:
         super().__init__()
@@ -169,7 +171,7 @@ class ActorCritic(nn.Module):
 
     @torch.no_grad()
     def step_device(self, obs: torch.Tensor, action_masks: Optional[TensorOrDict] = None,
-                    offset_dev: Optional[torch.Tensor] = None):
+                    offset_dev: Optional[torch.Tensor] = None, wide_out: Optional[torch.Tensor] = None):
         """(actions, values, logp) on the device; per-cell actions are uint8, pick / discrete int64.
         ``offset_dev`` (int64 device scalar) is added to the RNG offset on the device, so a launch
         captured in a CUDA graph draws fresh numbers on every replay."""
@@ -182,8 +184,9 @@ class ActorCritic(nn.Module):
             cells_mask = action_masks["per_position"] if isinstance(action_masks, dict) else action_masks
             pick_mask = action_masks.get("pick_position") if isinstance(action_masks, dict) else None
             logits = self._grid_logits(out).contiguous()
+            # wide_out ([N, HW, A] int64, GridNet only): the per-cell actions once more in the dtype a host env takes
             cells, pick, logp = ops.gridnet_sample(self.spec, logits, cells_mask, pick_mask, seed, offset, torch.uint8,
-                                                   offset_dev)
+                                                   offset_dev, wide_out)
             a: TensorOrDict = {"per_position": cells, "pick_position": pick} if self.n_pick else cells
             return a, out.values, logp
         if self.kind == "categorical":

@@ -25,6 +25,9 @@ class ReferenceAIRolloutGenerator(SyncStepRolloutGenerator):
     def __init__(self, policy, vec_env, **kwargs) -> None:
         kwargs.setdefault("cuda_graph", False)  # the env (a host AI) sits between the policy and the buffer write
         super().__init__(policy, vec_env, **kwargs)
+        if self._pack_in_step:  # this loop writes next_obs itself: no deferred packing
+            self._pack_raw()
+            self._pack_in_step = False
         self._row = torch.zeros(1, dtype=torch.int64, device=self.device)
         if not self.include_logp:
             self.zero_action = _map(lambda buf: torch.zeros(tuple(buf.shape[1:]), dtype=buf.dtype, device=self.device),

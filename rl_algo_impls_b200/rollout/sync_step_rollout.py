@@ -45,6 +45,8 @@ class _Uploader:
         self._registered_bytes = 0
         self._roots: list = []  # the page-locked arrays, kept alive while they are registered
         self.bytes = 0  # host -> device bytes moved so far
+        self._fast: Dict[tuple, tuple] = {}     # (field, host pointer) -> (nbytes, device pointer, shape, dtype): a plain DMA
+        self._batches: Dict[tuple, tuple] = {}  # host pointers of one step's DMAs -> prebuilt argument arrays
 
     def _page_locked(self, a: np.ndarray) -> bool:
         """True when `a` lives in a host buffer this uploader has page-locked (registering it on its second sighting)."""
@@ -77,12 +79,58 @@ class _Uploader:
                 _lib.lib().b200rl_host_unregister(ptr)
         self._registered.clear()
         self._roots = []
+        self._fast.clear(), self._batches.clear()
 
     def __del__(self):
         try:
             self.close()
         except Exception:  # interpreter shutdown: the library / driver may already be gone
             pass
+
+    def upload_step(self, items) -> None:
+        """One env step's uploads, ``items = [(field, host array or tensor, device tensor)]``.  Fields that arrive in a
+        page-locked buffer seen before (an env that reuses its output arrays, or cycles through a pool) are enqueued by
+        ONE C call (b200rl_h2d_batch) with cached arguments: ~4 us of host time for the step instead of ~15 us per
+        field through tensor wrappers; the rest takes the per-field path."""
+        import ctypes as C
+
+        ptrs = []
+        for name, src, dst in items:
+            entry = None
+            if type(src) is np.ndarray and src.flags.c_contiguous:
+                ptr = src.__array_interface__["data"][0]
+                entry = self._fast.get((name, ptr))
+                if entry is not None and (entry[1] != dst.data_ptr() or entry[2] != src.shape or entry[3] != src.dtype):
+                    entry = None  # the buffer at this address is another array now
+                if entry is None and src.nbytes >= self.REGISTER_MIN_BYTES and src.shape == tuple(dst.shape) \
+                        and torch.from_numpy(src).dtype == dst.dtype and dst.is_contiguous() and self._registered.get(self._root_key(src)):
+                    entry = self._fast[(name, ptr)] = (src.nbytes, dst.data_ptr(), src.shape, src.dtype)
+                    if len(self._fast) > 4096:
+                        self._fast.clear(), self._batches.clear()
+            if entry is None:
+                self(name, src, dst)
+            else:
+                ptrs.append((ptr, entry))
+        if not ptrs:
+            return
+        key = tuple((p, e[1]) for p, e in ptrs)
+        batch = self._batches.get(key)
+        if batch is None:
+            n = len(ptrs)
+            dst_arr, src_arr, nb_arr = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_int64 * n)()
+            for i, (p, e) in enumerate(ptrs):
+                dst_arr[i], src_arr[i], nb_arr[i] = e[1], p, e[0]
+            batch = self._batches[key] = (n, dst_arr, src_arr, nb_arr, sum(e[0] for _, e in ptrs))
+        rc = _lib.lib().b200rl_h2d_batch(batch[0], batch[1], batch[2], batch[3], torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "b200rl_h2d_batch")
+        self.bytes += batch[4]
+
+    @staticmethod
+    def _root_key(a: np.ndarray) -> tuple:
+        root = a
+        while isinstance(root.base, np.ndarray):
+            root = root.base
+        return (root.ctypes.data, root.nbytes)
 
     def __call__(self, name: str, src, dst: torch.Tensor) -> None:
         if isinstance(src, torch.Tensor):
@@ -167,6 +215,9 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         self._kernels_per_replay = 0
         self.d2h_bytes = 0  # device -> host bytes (sampled actions handed to a host env)
         self._host_actions = None  # pinned landing zone of the sampled actions (host env)
+        self._wide_actions: Optional[torch.Tensor] = None  # GridNet + host env: int64 per-cell actions, written by K5
+        self._host_wide = None   # ... and their two pinned landing zones (alternating)
+        self._host_parity = 0
         self._host_rewards: Optional[torch.Tensor] = None  # pinned [T, N(, V)]: a host env's rewards, uploaded per rollout
         self._host_starts: Optional[torch.Tensor] = None   # pinned [T + 1, N]: episode-start flags, row T carries over
         self.get_action_mask = getattr(vec_env, "get_action_mask", None)
@@ -184,6 +235,9 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         obs_dtype = torch.float32 if self._packed else _torch_dtype(obs_space.dtype)
         self._raw_obs = (torch.zeros((N,) + tuple(obs_space.shape), dtype=_torch_dtype(obs_space.dtype), device=dev)
                          if self._packed else None)  # landing zone of a host env's upload, packed from there
+        # host env: _raw_obs is the source of truth and every policy step starts by packing it (inside the captured
+        # step: no launch of its own between the upload and the replay)
+        self._pack_in_step = bool(self._packed) and getattr(vec_env, "device", None) is None
         self.obs = torch.zeros((T, N) + obs_shape, dtype=obs_dtype, device=dev)
         self.rewards = torch.zeros((T, N) + value_shape, dtype=torch.float32, device=dev)
         self.episode_starts = torch.zeros((T, N), dtype=torch.bool, device=dev)
@@ -204,6 +258,11 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         else:
             adt = torch.uint8 if kind == "gridnet" else (torch.float32 if kind == "gaussian" else torch.int64)
             self.actions = torch.zeros((T, N) + tuple(act_shape), dtype=adt, device=dev)
+
+        if (kind == "gridnet" and getattr(vec_env, "device", None) is None
+                and getattr(policy, "supports_wide_actions", False)):
+            cells = act_shape["per_position"] if isinstance(act_shape, dict) else act_shape
+            self._wide_actions = torch.zeros((N,) + tuple(cells), dtype=torch.int64, device=dev)
 
         first_obs, _ = vec_env.reset()
         self._set_next_obs(first_obs)
@@ -230,7 +289,33 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         if not isinstance(obs, torch.Tensor):
             self._upload("obs", obs, self._raw_obs)
             obs = self._raw_obs
+            if self._pack_in_step:  # the captured policy step packs _raw_obs itself (its first launch)
+                return
+        elif self._pack_in_step:
+            self._raw_obs.copy_(obs)
+            return
         self.policy.pack_observations(obs, out=self.next_obs)
+
+    def _pack_raw(self) -> None:
+        """Host env, packed observations: self.next_obs <- pack(self._raw_obs), the landing zone of the env's upload.
+        Idempotent; the first launch of every policy step, and called before anything else reads next_obs."""
+        if self._pack_in_step:
+            self.policy.pack_observations(self._raw_obs, out=self.next_obs)
+
+    def _upload_env_outputs(self, next_obs, masks) -> None:
+        """A host env's observation and masks for the next step, enqueued together (one C call when they come out of
+        page-locked buffers)."""
+        if isinstance(next_obs, torch.Tensor) or (self._packed and not self._pack_in_step):
+            self._set_next_obs(next_obs)
+            items = []
+        else:
+            items = [("obs", next_obs, self._raw_obs if self._packed else self.next_obs)]
+        if masks is not None:
+            if isinstance(masks, dict):
+                items += [("mask_" + k, v, self.next_action_masks[k]) for k, v in masks.items()]
+            else:
+                items.append(("mask", masks, self.next_action_masks))
+        self._upload.upload_step(items)
 
     def _upload_masks(self, m) -> None:
         if isinstance(m, dict):
@@ -239,12 +324,34 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         else:
             self._upload("mask", m, self.next_action_masks)
 
+    def _download_wide(self, a) -> None:
+        """Start the int64 per-cell actions (and the pick actions) towards the pinned buffer of this step's parity.  The
+        arrays handed to the env are views of it: valid until the policy step after the next one."""
+        self._host_parity ^= 1
+        if self._host_wide is None:
+            pin = lambda t: torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+            self._host_wide = [{"per_position": pin(self._wide_actions),
+                                **({"pick_position": pin(a["pick_position"])} if isinstance(a, dict) else {})}
+                               for _ in range(2)]
+        buf = self._host_wide[self._host_parity]
+        buf["per_position"].copy_(self._wide_actions, non_blocking=True)
+        if isinstance(a, dict):
+            buf["pick_position"].copy_(a["pick_position"], non_blocking=True)
+
     def _env_actions(self, a, landed: bool = False):
         """What vec_env.step receives: CUDA tensors for a device env, numpy (int64 / f32) for a host env.
         ``landed``: the step already copied `a` into the pinned ``_host_actions`` (wait for it, read it there)."""
         if getattr(self.vec_env, "device", None) is not None:
             return a
         from ..policy.actor_critic import clamp_actions
+
+        if landed and self._wide_actions is not None:
+            torch.cuda.current_stream().synchronize()
+            buf = self._host_wide[self._host_parity]
+            self.d2h_bytes += sum(t.numel() * t.element_size() for t in buf.values())
+            if isinstance(a, dict):
+                return {k: t.numpy().reshape(tuple(a[k].shape)) for k, t in buf.items()}
+            return buf["per_position"].numpy().reshape(tuple(a.shape))
 
         if landed:
             torch.cuda.current_stream().synchronize()
@@ -298,6 +405,15 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         in pinned [T, N] arrays and uploaded once per rollout."""
         from .. import ops
 
+        self._pack_raw()
+        if self._wide_actions is not None:
+            # GridNet: the sampling kernel also writes the per-cell actions as int64, the dtype the env is handed; they are
+            # downloaded after the replay into alternating pinned buffers (_download_wide): no cast and no copy on the host
+            a, v, logp = self.policy.step_device(self.next_obs, self.next_action_masks, offset_dev=self.step_count,
+                                                 wide_out=self._wide_actions)
+            src, dst = self._fields(a, v, logp, with_starts=False)
+            ops.rollout_store_step(src, dst, self.step_count, advance_ticket=self._k0_ticket)  # ... and step_count += 1
+            return a
         a, v, logp = self.policy.step_device(self.next_obs, self.next_action_masks, offset_dev=self.step_count)
         src, dst = self._fields(a, v, logp, with_starts=False)
         ops.rollout_store_step(src, dst, self.step_count, advance_ticket=self._k0_ticket)  # ... and step_count += 1
@@ -413,10 +529,12 @@ class SyncStepRolloutGenerator(RolloutGenerator):
             else:
                 with torch.no_grad():
                     a = self._policy_step()
+            if self._wide_actions is not None:
+                self._download_wide(a)
             next_obs, rewards, terminations, truncations, _ = self.vec_env.step(self._env_actions(a, landed=True))
-            self._set_next_obs(next_obs)
-            if self.get_action_mask is not None and self.next_action_masks is not None:
-                self._upload_masks(self.get_action_mask())
+            masks = (self.get_action_mask() if self.get_action_mask is not None and self.next_action_masks is not None
+                     else None)
+            self._upload_env_outputs(next_obs, masks)
             host_rewards[s] = np.asarray(rewards, dtype=np.float32).reshape(host_rewards.shape[1:])
             np.logical_or(terminations, truncations, out=host_starts[s + 1])
         if not device_env:  # one upload per rollout for the scalars the env produced on the host
@@ -424,6 +542,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
             self.rewards.copy_(self._host_rewards, non_blocking=True)
             self.episode_starts.copy_(self._host_starts[:T], non_blocking=True)
             self.next_episode_starts.copy_(self._host_starts[T], non_blocking=True)
+        self._pack_raw()
         next_values = self.policy.value_device(self.next_obs) if output_next_values else None
         self.policy.train()
         return next_values
@@ -486,7 +605,11 @@ class SyncStepRolloutGenerator(RolloutGenerator):
         next_obs, action_mask, _ = self.vec_env.masked_reset(reset)
         rows = torch.from_numpy(np.nonzero(reset)[0]).to(self.device)
         fresh = torch.as_tensor(next_obs).to(self.device)
-        self.next_obs[rows] = self.policy.pack_observations(fresh) if self._packed else fresh.to(self.next_obs.dtype)
+        if self._pack_in_step:
+            self._raw_obs[rows] = fresh.to(self._raw_obs.dtype)
+            self._pack_raw()
+        else:
+            self.next_obs[rows] = self.policy.pack_observations(fresh) if self._packed else fresh.to(self.next_obs.dtype)
         if self.next_action_masks is not None and action_mask is not None:
             if isinstance(self.next_action_masks, dict):
                 for k, dst in self.next_action_masks.items():

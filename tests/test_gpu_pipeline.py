@@ -234,6 +234,56 @@ def test_graph_replayed_rollout_equals_eager(cuda, cfg):
         assert torch.equal(eager[k], graphed[k]), k
 
 
+@pytest.mark.parametrize("cfg", ["C4", "C5"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_host_env_is_handed_the_sampled_actions_as_int64(cuda, cfg, graph):
+    """Host env + GridNet: env.step receives int64 arrays (the reference's contract, actor_critic.py:315-318) that equal
+    the uint8 actions stored in the rollout buffer, step for step; the array of step s is still intact while step s + 1
+    runs (two pinned landing zones); observations the env hands back reach the buffer in the packed layout."""
+    from rl_algo_impls_b200.envs import make_synthetic_env
+    from rl_algo_impls_b200.policy import ActorCritic
+    from rl_algo_impls_b200.rollout import SyncStepRolloutGenerator
+
+    name, n_envs, n_steps, _, pkw, _ = CONFIGS[cfg]
+    torch.manual_seed(0)
+    env = make_synthetic_env(name, n_envs, seed=1, device=None, pool=3)
+    seen, held, returned = [], [], []
+    inner = env.step
+
+    def step(actions):
+        acts = actions if isinstance(actions, dict) else {"per_position": actions}
+        for v in acts.values():
+            assert isinstance(v, np.ndarray) and v.dtype == np.int64
+        if held:  # the previous step's arrays were not overwritten by this step's download
+            for k, v in held[-1][0].items():
+                assert np.array_equal(v, held[-1][1][k]), k
+        held.append((acts, {k: v.copy() for k, v in acts.items()}))
+        seen.append({k: v.copy() for k, v in acts.items()})
+        out = inner(actions)
+        returned.append(np.array(out[0], copy=True))
+        return out
+
+    env.step = step
+    policy = ActorCritic(env, subaction_mask=env.spec.subaction_mask, **pkw).to(cuda)
+    gen = SyncStepRolloutGenerator(policy, env, n_steps=n_steps, subaction_mask=env.spec.subaction_mask, cuda_graph=graph)
+    assert gen._wide_actions is not None
+    for _ in range(2):  # the second rollout runs on replays when `graph`
+        seen.clear(), returned.clear()
+        r = gen.rollout(gamma=0.99 if policy.value_shape == () else [0.99] * 13,
+                        gae_lambda=0.95 if policy.value_shape == () else [0.95] * 13)
+        torch.cuda.synchronize()
+        stored = r.actions if isinstance(r.actions, dict) else {"per_position": r.actions}
+        assert len(seen) == n_steps
+        for s in range(n_steps):
+            for k, v in seen[s].items():
+                assert np.array_equal(stored[k][s].cpu().numpy().astype(np.int64).reshape(v.shape), v), (s, k)
+        # packed observations: row s + 1 of the buffer is what the env returned at step s
+        for s in (0, n_steps - 2):
+            packed, raw = gen.obs[s + 1].cpu(), torch.from_numpy(returned[s])
+            C = raw.shape[1]
+            assert torch.equal(packed[..., :C], raw.permute(0, 2, 3, 1).float()) and packed[..., C:].abs().sum() == 0
+
+
 def test_gridnet_sampler_draws_from_the_masked_softmax(cuda):
     """K5: Gumbel-max over Philox noise is an exact draw from softmax(logits | mask); the returned
     log-prob is the oracle's log-prob of the drawn action.  20,000 i.i.d. draws of one 2-head cell."""
