@@ -204,6 +204,38 @@ def bench_gather(M, B, row_shapes):
                 frac=nbytes / med / 1e6 / peak_gbs())
 
 
+def bench_glue(N, C, H, W):
+    """K8: bias + max-pool(3, 2, 1) + ReLU forward / backward and bias + ReLU forward / backward on a channels-last map."""
+    dev = "cuda"
+    y = torch.randn((N, C, H, W), device=dev).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(C, device=dev)
+    rows = []
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    yy, bb = y.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    out = ops.bias_pool_relu(yy, bb)
+    dout = torch.randn_like(out)
+    n_in, n_out = N * C * H * W, N * C * Ho * Wo
+    for name, fn, call, nbytes in (
+        ("bias_pool_relu_fwd", lambda: ops.bias_pool_relu(yy, bb), "b200rl_nhwc_bias_pool_relu_fwd", 4 * n_in + 5 * n_out),
+        ("bias_pool_relu_bwd", lambda: out.backward(dout, retain_graph=True), "b200rl_nhwc_bias_pool_relu_bwd",
+         4 * n_in + 5 * n_out + 5 * n_out),  # dx written; dout + codes read by the gather and again by the bias sum
+    ):
+        med, best = time_kernel(fn, call)
+        rows.append(dict(kernel=name, N=N, C=C, H=H, W=W, ms_median=med, ms_best=best, bytes=nbytes, gbs=nbytes / med / 1e6,
+                         frac=nbytes / med / 1e6 / peak_gbs()))
+    y2 = (y * 1.0).requires_grad_(True)
+    out2 = ops.bias_relu(y2 * 1.0, bb)
+    d2 = torch.randn_like(out2)
+    for name, fn, call, nbytes in (
+        ("bias_relu_fwd", lambda: ops.bias_relu(y2 * 1.0, bb), "b200rl_nhwc_bias_relu_fwd", 8 * n_in),
+        ("bias_relu_bwd", lambda: out2.backward(d2, retain_graph=True), "b200rl_nhwc_bias_relu_bwd", 12 * n_in + 8 * n_in),
+    ):
+        med, best = time_kernel(fn, call)
+        rows.append(dict(kernel=name, N=N, C=C, H=H, W=W, ms_median=med, ms_best=best, bytes=nbytes, gbs=nbytes / med / 1e6,
+                         frac=nbytes / med / 1e6 / peak_gbs()))
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="?", default="all")
@@ -280,6 +312,11 @@ def main():
         print(json.dumps(rows[-1]), flush=True)
         rows.append(bench_gae(32, 131072, 13))
         print(json.dumps(rows[-1]), flush=True)
+    if a.what in ("glue", "all"):  # K8 at the C4 minibatch's encoder levels 1 and 2, and the rollout step's level 1
+        for shape in ((3072, 32, 16, 16), (3072, 64, 8, 8), (24, 32, 16, 16)):
+            for r in bench_glue(*shape):
+                rows.append(r)
+                print(json.dumps(r), flush=True)
     if a.what in ("gather", "all"):
         rows.append(bench_gather(12288, 3072, [((74, 16, 16), torch.float32), ((256, 78), torch.uint8),
                                                ((256, 7), torch.uint8), ((), torch.float32), ((), torch.float32),

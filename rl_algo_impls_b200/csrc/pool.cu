@@ -66,18 +66,20 @@ __device__ __forceinline__ void store_codes(uint8_t* p, const uint8_t (&v)[VEC])
 }
 
 // ---- forward: one thread per (n, ho, wo, VEC channels) --------------------------------------------
-template <int VEC, int K>  // K > 0: compile-time window (3: the encoder's), 0: runtime G.k
+// IDX: unsigned when every element index fits 31 bits (64-bit divisions and address arithmetic were a third of the
+// instructions), long long otherwise
+template <int VEC, int K, typename IDX>  // K > 0: compile-time window (3: the encoder's), 0: runtime G.k
 __global__ void __launch_bounds__(kPoolBlock) pool_fwd_kernel(const PoolDev G) {
-  const int Cv = G.C / VEC;
-  const long long total = G.N * G.Ho * G.Wo * Cv;
-  const long long i = (long long)blockIdx.x * kPoolBlock + threadIdx.x;
+  const IDX Cv = (IDX)(G.C / VEC);
+  const IDX total = (IDX)G.N * (IDX)G.Ho * (IDX)G.Wo * Cv;
+  const IDX i = (IDX)blockIdx.x * kPoolBlock + threadIdx.x;
   if (i >= total) return;
   const int cv = (int)(i % Cv);
-  long long t = i / Cv;
-  const int wo = (int)(t % G.Wo);
-  t /= G.Wo;
-  const int ho = (int)(t % G.Ho);
-  const long long n = t / G.Ho;
+  IDX t = i / Cv;
+  const int wo = (int)(t % (IDX)G.Wo);
+  t /= (IDX)G.Wo;
+  const int ho = (int)(t % (IDX)G.Ho);
+  const IDX n = t / (IDX)G.Ho;
   const int k = K > 0 ? K : G.k;
   const int h0 = ho * G.s - G.p, w0 = wo * G.s - G.p;
   const int c = cv * VEC;
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(kPoolBlock) pool_fwd_kernel(const PoolDev G) {
   const int kh_first = h0 < 0 ? -h0 : 0, kw_first = w0 < 0 ? -w0 : 0;  // torch starts the arg-max at the first in-bounds entry
 #pragma unroll
   for (int j = 0; j < VEC; ++j) m[j] = -INFINITY, am[j] = (uint8_t)(kh_first * k + kw_first);
-  const float* xn = G.x + n * G.H * G.W * G.C + c;
+  const float* xn = G.x + n * (IDX)G.H * (IDX)G.W * (IDX)G.C + c;
   if constexpr (K > 0) {
     // compile-time window: every load of the window is issued before the first compare (out-of-range taps re-read a
     // clamped position and are skipped by the scan), instead of one round trip per tap
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(kPoolBlock) pool_fwd_kernel(const PoolDev G) {
         const int h = h0 + kh, w = w0 + kw;
         ok[kh * K + kw] = h >= 0 && h < G.H && w >= 0 && w < G.W;
         const int hc = h < 0 ? 0 : (h >= G.H ? G.H - 1 : h), wc = w < 0 ? 0 : (w >= G.W ? G.W - 1 : w);
-        load_vec<VEC>(xn + ((long long)hc * G.W + wc) * G.C, v[kh * K + kw]);
+        load_vec<VEC>(xn + ((IDX)hc * (IDX)G.W + (IDX)wc) * (IDX)G.C, v[kh * K + kw]);
       }
 #pragma unroll
     for (int t = 0; t < K * K; ++t) {
@@ -138,9 +140,63 @@ __global__ void __launch_bounds__(kPoolBlock) pool_fwd_kernel(const PoolDev G) {
       if (!live) m[j] = 0.f, am[j] = kDead;
     }
   }
-  const long long o = ((n * G.Ho + ho) * G.Wo + wo) * G.C + c;
+  const IDX o = ((n * (IDX)G.Ho + (IDX)ho) * (IDX)G.Wo + (IDX)wo) * (IDX)G.C + (IDX)c;
   store_vec<VEC>(G.out + o, m);
   if (G.argmax) store_codes<VEC>(G.argmax + o, am);
+}
+
+// ---- backward, kernel 3 / stride 2 / padding 1 (the encoder's): one thread per 2 x 2 input patch x VEC channels ------
+// Rows 2m, 2m+1 and columns 2q, 2q+1 are covered by windows ho in {m, m+1}, wo in {q, q+1} only (an even row by window
+// m alone), so the patch's four pixels share four (code, gradient) loads -- the gather form below reads four per pixel.
+// Same terms in the same (ho, wo) order per pixel: bit-identical to the gather form.
+template <int VEC, typename IDX>
+__global__ void __launch_bounds__(kPoolBlock) pool_bwd_k3s2_kernel(const PoolDev G) {
+  const IDX Cv = (IDX)(G.C / VEC);
+  const IDX Hm = (IDX)((G.H + 1) / 2), Wm = (IDX)((G.W + 1) / 2);
+  const IDX total = (IDX)G.N * Hm * Wm * Cv;
+  const IDX i = (IDX)blockIdx.x * kPoolBlock + threadIdx.x;
+  if (i >= total) return;
+  const int cv = (int)(i % Cv);
+  IDX t = i / Cv;
+  const int q = (int)(t % Wm);
+  t /= Wm;
+  const int m = (int)(t % Hm);
+  const IDX n = t / Hm;
+  const int c = cv * VEC;
+  uint8_t am[4][VEC];
+  float g[4][VEC];
+  bool ok[4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      ok[a * 2 + b] = m + a < G.Ho && q + b < G.Wo;
+      const int ho = m + a < G.Ho ? m + a : G.Ho - 1, wo = q + b < G.Wo ? q + b : G.Wo - 1;
+      const IDX o = ((n * (IDX)G.Ho + (IDX)ho) * (IDX)G.Wo + (IDX)wo) * (IDX)G.C + (IDX)c;
+      load_codes<VEC>(G.argmax + o, am[a * 2 + b]);
+      load_vec<VEC>(G.dout + o, g[a * 2 + b]);
+    }
+#pragma unroll
+  for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+    for (int dw = 0; dw < 2; ++dw) {
+      const int h = 2 * m + dh, w = 2 * q + dw;
+      if (h >= G.H || w >= G.W) continue;
+      float acc[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int a = 0; a <= dh; ++a)
+#pragma unroll
+        for (int b = 0; b <= dw; ++b) {
+          if (!ok[a * 2 + b]) continue;
+          const uint8_t code = (uint8_t)((dh + 1 - 2 * a) * 3 + (dw + 1 - 2 * b));
+#pragma unroll
+          for (int j = 0; j < VEC; ++j)
+            if (am[a * 2 + b][j] == code) acc[j] += g[a * 2 + b][j];
+        }
+      store_vec<VEC>(G.dx + ((n * (IDX)G.H + (IDX)h) * (IDX)G.W + (IDX)w) * (IDX)G.C + (IDX)c, acc);
+    }
 }
 
 // ---- backward: one thread per (n, h, w, VEC channels) gathers the windows that cover it ------------------
@@ -332,8 +388,8 @@ static void colsum_plan(long long rows, int C, int vec, int* tx_out, int* slabs_
   while (tx < Cv && tx < 32) tx *= 2;
   const int tiles = (Cv + tx - 1) / tx;
   const int ty = kPoolBlock / tx;
-  long long want = (long long)device_info().sm_count * 4 / tiles;  // ~4 CTAs per SM
-  const long long cap = (rows + ty * 4 - 1) / (ty * 4);           // >= 4 rows per thread
+  long long want = (long long)device_info().sm_count * 2 / tiles;  // ~2 CTAs per SM (stage 2 walks the slabs)
+  const long long cap = (rows + ty * 8 - 1) / (ty * 8);           // >= 8 rows per thread
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   if (want > 4096) want = 4096;
@@ -411,12 +467,14 @@ extern "C" int b200rl_nhwc_bias_pool_relu_fwd(const float* x, const float* bias,
   B200RL_UNSUPPORTED((total + kPoolBlock - 1) / kPoolBlock > 0x7fffffffLL, "nhwc_bias_pool_relu_fwd: tensor too large");
   const unsigned grid = (unsigned)((total + kPoolBlock - 1) / kPoolBlock);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool small = N * H * W * C < 0x7fffffffLL;  // every element index fits 31 bits
   if (v4) {
-    if (kernel == 3) pool_fwd_kernel<4, 3><<<grid, kPoolBlock, 0, st>>>(G);
-    else pool_fwd_kernel<4, 0><<<grid, kPoolBlock, 0, st>>>(G);
+    if (kernel == 3 && small) pool_fwd_kernel<4, 3, unsigned><<<grid, kPoolBlock, 0, st>>>(G);
+    else if (kernel == 3) pool_fwd_kernel<4, 3, long long><<<grid, kPoolBlock, 0, st>>>(G);
+    else pool_fwd_kernel<4, 0, long long><<<grid, kPoolBlock, 0, st>>>(G);
   } else {
-    if (kernel == 3) pool_fwd_kernel<1, 3><<<grid, kPoolBlock, 0, st>>>(G);
-    else pool_fwd_kernel<1, 0><<<grid, kPoolBlock, 0, st>>>(G);
+    if (kernel == 3) pool_fwd_kernel<1, 3, long long><<<grid, kPoolBlock, 0, st>>>(G);
+    else pool_fwd_kernel<1, 0, long long><<<grid, kPoolBlock, 0, st>>>(G);
   }
   return check_launch("nhwc_bias_pool_relu_fwd");
 }
@@ -439,8 +497,18 @@ extern "C" int b200rl_nhwc_bias_pool_relu_bwd(const float* dout, const uint8_t* 
   B200RL_UNSUPPORTED((total + kPoolBlock - 1) / kPoolBlock > 0x7fffffffLL, "nhwc_bias_pool_relu_bwd: tensor too large");
   const unsigned grid = (unsigned)((total + kPoolBlock - 1) / kPoolBlock);
   cudaStream_t st = (cudaStream_t)stream;
-  if (v4) pool_bwd_kernel<4><<<grid, kPoolBlock, 0, st>>>(G);
-  else pool_bwd_kernel<1><<<grid, kPoolBlock, 0, st>>>(G);
+  if (kernel == 3 && stride == 2 && padding == 1) {  // a thread per 2 x 2 input patch
+    const long long patches = N * ((H + 1) / 2) * ((W + 1) / 2) * (C / (v4 ? 4 : 1));
+    const unsigned pgrid = (unsigned)((patches + kPoolBlock - 1) / kPoolBlock);
+    const bool small = N * H * W * C < 0x7fffffffLL;
+    if (v4 && small) pool_bwd_k3s2_kernel<4, unsigned><<<pgrid, kPoolBlock, 0, st>>>(G);
+    else if (v4) pool_bwd_k3s2_kernel<4, long long><<<pgrid, kPoolBlock, 0, st>>>(G);
+    else pool_bwd_k3s2_kernel<1, long long><<<pgrid, kPoolBlock, 0, st>>>(G);
+  } else if (v4) {
+    pool_bwd_kernel<4><<<grid, kPoolBlock, 0, st>>>(G);
+  } else {
+    pool_bwd_kernel<1><<<grid, kPoolBlock, 0, st>>>(G);
+  }
   rc = check_launch("nhwc_bias_pool_relu_bwd");
   if (rc || !dbias) return rc;
   return launch_colsum(dout, argmax, nullptr, dbias, workspace, workspace_bytes, N * G.Ho * G.Wo, (int)C, st,
