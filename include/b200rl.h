@@ -425,6 +425,40 @@ int b200rl_nhwc_bias_relu_fwd(const float* x, const float* bias, float* out, int
 int b200rl_nhwc_bias_relu_bwd(const float* dout, const float* out /*nullable*/, float* dx, float* dbias /*nullable*/, void* workspace,
                               size_t workspace_bytes, int64_t rows, int64_t C, b200rl_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K9  channels-last glue of the squeeze U-net (shared/policy/actor_critic_network/squeeze_unet.py:20-196 over the
+ * SE-residual blocks of double_cone.py:18-86), float32 or bfloat16 maps (dtype = B200RL_F32 / B200RL_BF16), float32
+ * biases and reductions.  With bfloat16 maps every value PyTorch materialises as a bfloat16 tensor under autocast is
+ * rounded at the same point (forward bit-identical to the PyTorch chain).
+ *
+ *   b200rl_nhwc_bias_act_*: out = act(x + bias) over [rows, C], act 0 none / 1 ReLU / 2 GELU (torch's exact erf form);
+ *     _bwd: dx = dout * act'(x + bias) from the convolution's bias-free output x (no pre-activation tensor is kept),
+ *     dbias (nullable) = column sums of dx; workspace b200rl_nhwc_bias_act_workspace_bytes(rows, C).
+ *   SE tail of a residual block, out = gelu(x + (y2 + b2) * gate[n, c]) over [N, HW, C]:
+ *     b200rl_se_mean_sums       sums[n, c] = sum over hw of y2 (the caller adds b2 and divides: the squeeze mean);
+ *     b200rl_se_tail_fwd        the gated residual sum + output activation in one pass;
+ *     b200rl_se_tail_gate_grad  dgate[n, c] = sum over hw of dz * (y2 + b2), dz = dout * gelu'(z);
+ *     b200rl_se_tail_bwd        dx = dz, dy2 = dz * gate + dmean[n, c] (dmean: the mean path's gradient, already / HW),
+ *                               db2 (nullable) = column sums of dy2.
+ *   The two linears of the gate ([N, C] x [C, C/16]) stay library GEMMs on the host side of the ABI. */
+size_t b200rl_nhwc_bias_act_workspace_bytes(int64_t rows, int64_t C);
+int b200rl_nhwc_bias_act_fwd(const void* x, const float* bias, void* out, int64_t rows, int64_t C, int act, int dtype,
+                             b200rl_stream_t stream);
+int b200rl_nhwc_bias_act_bwd(const void* dout, const void* x, const float* bias, void* dx, float* dbias /*nullable*/,
+                             void* workspace, size_t workspace_bytes, int64_t rows, int64_t C, int act, int dtype,
+                             b200rl_stream_t stream);
+size_t b200rl_se_workspace_bytes(int64_t N, int64_t HW, int64_t C);  /* per-slab partials of the two reductions */
+int b200rl_se_mean_sums(const void* y2, float* sums, void* workspace, size_t workspace_bytes, int64_t N, int64_t HW,
+                        int64_t C, int dtype, b200rl_stream_t stream);
+int b200rl_se_tail_fwd(const void* x, const void* y2, const float* b2, const void* gate, void* out, int64_t N, int64_t HW,
+                       int64_t C, int dtype, b200rl_stream_t stream);
+int b200rl_se_tail_gate_grad(const void* dout, const void* x, const void* y2, const float* b2, const void* gate,
+                             float* dgate, void* workspace, size_t workspace_bytes, int64_t N, int64_t HW, int64_t C,
+                             int dtype, b200rl_stream_t stream);
+int b200rl_se_tail_bwd(const void* dout, const void* x, const void* y2, const float* b2, const void* gate,
+                       const float* dmean, void* dx, void* dy2, float* db2 /*nullable*/, void* workspace,
+                       size_t workspace_bytes, int64_t N, int64_t HW, int64_t C, int dtype, b200rl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1061,3 +1061,118 @@ def bias_relu(y: torch.Tensor, bias: torch.Tensor, relu: bool = True) -> torch.T
     _check_map(y)
     _cuda(bias.detach(), torch.float32, "bias")
     return _BiasReluFn.apply(y, bias, bool(relu))
+
+
+# ------------------------------------------------------------------------------------------------
+# K9: channels-last glue of the squeeze U-net (float32 / bfloat16 maps)
+_ACTS = {"none": 0, "relu": 1, "gelu": 2}
+_MAP_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def act_glue_supported(y: torch.Tensor) -> bool:
+    return y.is_cuda and y.dtype in _MAP_DTYPES and y.dim() == 4
+
+
+class _BiasActFn(torch.autograd.Function):
+    """act(y + bias) on a channels-last map in one launch.  y -- a convolution's bias-free output -- is what the
+    backward keeps: the pre-activation is recomputed from it, no second map is saved."""
+
+    @staticmethod
+    def forward(ctx, y, bias, act):
+        y = _nhwc(y)
+        N, Cc, H, W = y.shape
+        out = torch.empty_like(y, memory_format=torch.channels_last)
+        rc = _call("b200rl_nhwc_bias_act_fwd", 1, _lib.lib().b200rl_nhwc_bias_act_fwd, y.data_ptr(), bias.data_ptr(),
+                   out.data_ptr(), N * H * W, Cc, act, _MAP_DTYPES[y.dtype], _stream())
+        check(rc, "b200rl_nhwc_bias_act_fwd")
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            ctx.save_for_backward(y, bias)
+            ctx.act, ctx.want_bias = act, ctx.needs_input_grad[1]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, bias = ctx.saved_tensors
+        N, Cc, H, W = y.shape
+        dout = _nhwc(dout if dout.dtype == y.dtype else dout.to(y.dtype))
+        dx = torch.empty_like(y, memory_format=torch.channels_last)
+        dbias = torch.empty(Cc, dtype=torch.float32, device=y.device) if ctx.want_bias else None
+        L = _lib.lib()
+        ws = _workspace(L.b200rl_nhwc_bias_act_workspace_bytes(N * H * W, Cc), y.device)
+        rc = _call("b200rl_nhwc_bias_act_bwd", 3 if ctx.want_bias else 1, L.b200rl_nhwc_bias_act_bwd, dout.data_ptr(),
+                   y.data_ptr(), bias.data_ptr(), dx.data_ptr(), _ptr(dbias), ws.data_ptr(), ws.numel(), N * H * W, Cc,
+                   ctx.act, _MAP_DTYPES[y.dtype], _stream())
+        check(rc, "b200rl_nhwc_bias_act_bwd")
+        return dx, dbias, None
+
+
+def bias_act(y: torch.Tensor, bias: torch.Tensor, act: str = "gelu") -> torch.Tensor:
+    """``act(y + bias[None, :, None, None])`` for a float32 / bfloat16 CUDA map, channels-last in memory; ``bias`` float32
+    (rounded to the map's dtype as autocast would).  squeeze_unet.py's convolution -> GELU pairs."""
+    if not act_glue_supported(y):
+        raise TypeError(f"feature map: expected a float32 / bfloat16 CUDA [N, C, H, W] tensor, got {y.dtype} {tuple(y.shape)}")
+    _cuda(bias.detach(), torch.float32, "bias")
+    return _BiasActFn.apply(y, bias, _ACTS[act])
+
+
+class _SeTailFn(torch.autograd.Function):
+    """gelu(x + (y2 + b2) * sigmoid(W2 gelu(W1 mean_hw(y2 + b2)))): the tail of an SE-residual block (double_cone.py:18-86)
+    after its second convolution.  Forward: a per-(sample, channel) sum pass, the two small linears (library GEMMs on
+    [N, C]), one elementwise pass.  Backward: one reduction pass (the gate's gradient), the linears' backward on [N, C],
+    one elementwise pass (+ the bias column sums)."""
+
+    @staticmethod
+    def forward(ctx, x, y2, b2, w1, w2):
+        x, y2 = _nhwc(x), _nhwc(y2)
+        N, Cc, H, W = y2.shape
+        T, dt, L = y2.dtype, _MAP_DTYPES[y2.dtype], _lib.lib()
+        sums = torch.empty((N, Cc), dtype=torch.float32, device=y2.device)
+        ws = _workspace(L.b200rl_se_workspace_bytes(N, H * W, Cc), y2.device)
+        check(_call("b200rl_se_mean_sums", 2, L.b200rl_se_mean_sums, y2.data_ptr(), sums.data_ptr(), ws.data_ptr(), ws.numel(),
+                    N, H * W, Cc, dt, _stream()), "b200rl_se_mean_sums")
+        m = (sums / (H * W) + b2.to(T).float()).to(T)                 # what autocast hands the first linear
+        h1 = torch.nn.functional.linear(m, w1.to(T))
+        g1 = torch.nn.functional.gelu(h1)
+        gate = torch.sigmoid(torch.nn.functional.linear(g1, w2.to(T))).contiguous()
+        out = torch.empty_like(y2, memory_format=torch.channels_last)
+        check(_call("b200rl_se_tail_fwd", 1, L.b200rl_se_tail_fwd, x.data_ptr(), y2.data_ptr(), b2.data_ptr(), gate.data_ptr(),
+                    out.data_ptr(), N, H * W, Cc, dt, _stream()), "b200rl_se_tail_fwd")
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x, y2, b2, w1, w2, m, h1, g1, gate)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y2, b2, w1, w2, m, h1, g1, gate = ctx.saved_tensors
+        N, Cc, H, W = y2.shape
+        dt, L = _MAP_DTYPES[y2.dtype], _lib.lib()
+        dout = _nhwc(dout if dout.dtype == y2.dtype else dout.to(y2.dtype))
+        dgate = torch.empty((N, Cc), dtype=torch.float32, device=y2.device)
+        ws = _workspace(L.b200rl_se_workspace_bytes(N, H * W, Cc), y2.device)
+        check(_call("b200rl_se_tail_gate_grad", 2, L.b200rl_se_tail_gate_grad, dout.data_ptr(), x.data_ptr(), y2.data_ptr(),
+                    b2.data_ptr(), gate.data_ptr(), dgate.data_ptr(), ws.data_ptr(), ws.numel(), N, H * W, Cc, dt, _stream()),
+              "b200rl_se_tail_gate_grad")
+        # the gate's two linears backward, float32 on [N, C] / [N, C / 16]
+        sf, g1f, h1f, mf = gate.float(), g1.float(), h1.float(), m.float()
+        dh2 = dgate * sf * (1.0 - sf)
+        dw2 = dh2.t() @ g1f
+        dh1 = torch.ops.aten.gelu_backward(dh2 @ w2.float(), h1f)
+        dw1 = dh1.t() @ mf
+        dmean = ((dh1 @ w1.float()) / (H * W)).contiguous()
+        dx = torch.empty_like(y2, memory_format=torch.channels_last)
+        dy2 = torch.empty_like(y2, memory_format=torch.channels_last)
+        db2 = torch.empty(Cc, dtype=torch.float32, device=y2.device) if ctx.needs_input_grad[2] else None
+        ws = _workspace(L.b200rl_nhwc_bias_act_workspace_bytes(N * H * W, Cc), y2.device)
+        check(_call("b200rl_se_tail_bwd", 3 if db2 is not None else 1, L.b200rl_se_tail_bwd, dout.data_ptr(), x.data_ptr(),
+                    y2.data_ptr(), b2.data_ptr(), gate.data_ptr(), dmean.data_ptr(), dx.data_ptr(), dy2.data_ptr(), _ptr(db2),
+                    ws.data_ptr(), ws.numel(), N, H * W, Cc, dt, _stream()), "b200rl_se_tail_bwd")
+        return dx, dy2, db2, dw1.to(w1.dtype), dw2.to(w2.dtype)
+
+
+def se_tail(x: torch.Tensor, y2: torch.Tensor, b2: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor) -> torch.Tensor:
+    """The tail of an SE-residual block: ``gelu(x + SE(y2 + b2))`` with ``SE(u) = u * sigmoid(w2 gelu(w1 mean_hw(u)))``
+    (double_cone.py:18-86).  x: the block's input; y2: its second convolution's bias-free output (same dtype / shape)."""
+    if not act_glue_supported(y2) or x.dtype != y2.dtype or x.shape != y2.shape:
+        raise TypeError(f"se_tail: maps {x.dtype} {tuple(x.shape)} / {y2.dtype} {tuple(y2.shape)}")
+    _cuda(b2.detach(), torch.float32, "b2")
+    return _SeTailFn.apply(x, y2, b2, w1, w2)

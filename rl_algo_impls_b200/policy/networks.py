@@ -18,6 +18,11 @@ import torch.nn.functional as F
 
 from .. import ops
 
+# The launches between the trunks' convolutions run as fused kernels (ops.bias_pool_relu / bias_relu for the MicroRTS
+# encoder-decoder, ops.bias_act / se_tail for the squeeze U-net) when the maps are float32 / bfloat16 CUDA tensors.
+# False (or B200RL_FUSED_GLUE=0 in the environment): the PyTorch modules themselves -- parity tests compare the two.
+FUSED_GLUE = os.environ.get("B200RL_FUSED_GLUE", "1") != "0"
+
 _ACTIVATIONS = {"tanh": nn.Tanh, "relu": nn.ReLU, "gelu": nn.GELU, "identity": nn.Identity}
 
 
@@ -213,8 +218,7 @@ class GridEncoderDecoderActorCritic(_PaddedEnds):
         # reads and writes -- so permute(0, 2, 3, 1) is a free view instead of a 245 MB copy per minibatch.
         self.to(memory_format=torch.channels_last)
         self._init_padding(in_channels, n_logits, map_hw, self.encoder[0], self.decoder[-1])
-        # False (or B200RL_FUSED_GLUE=0): the PyTorch modules between the convolutions (parity tests compare the two)
-        self.fused_glue = os.environ.get("B200RL_FUSED_GLUE", "1") != "0"
+        self.fused_glue = FUSED_GLUE  # False: the PyTorch modules between the convolutions
 
     def forward(self, obs: torch.Tensor) -> HeadOutputs:
         w0, wh, bh = self._padded_weights()
@@ -265,7 +269,39 @@ class _SEResBlock(nn.Module):
         self.act = nn.GELU()
 
     def forward(self, x):
+        if FUSED_GLUE and ops.act_glue_supported(x):
+            # the two convolutions run without their bias; bias + GELU after the first and everything after the
+            # second -- bias, squeeze mean, gate, residual sum, output GELU -- are ops.bias_act / ops.se_tail
+            conv1, _, conv2, se = self.residual
+            y1 = F.conv2d(x, conv1.weight, None, padding=1)
+            if y1.dtype == x.dtype:  # (an autocast region fed a float32 map: PyTorch's own promotion rules apply)
+                y2 = F.conv2d(ops.bias_act(y1, conv1.bias, "gelu"), conv2.weight, None, padding=1)
+                return ops.se_tail(x, y2, conv2.bias, se.fc[0].weight, se.fc[2].weight)
         return self.act(x + self.residual(x))
+
+
+def _run_glued(seq, x: torch.Tensor) -> torch.Tensor:
+    """``seq(x)`` for a Sequential of the squeeze U-net, with every (transposed) convolution -> GELU pair as a bias-free
+    convolution + ops.bias_act (one launch for the bias add and the activation, forward and backward)."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if (FUSED_GLUE and i + 1 < len(mods) and isinstance(mods[i + 1], nn.GELU) and getattr(m, "bias", None) is not None
+                and isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)) and x.is_cuda):
+            if isinstance(m, nn.Conv2d):
+                y = F.conv2d(x, m.weight, None, m.stride, m.padding, m.dilation, m.groups)
+            else:
+                y = F.conv_transpose2d(x, m.weight, None, m.stride, m.padding, m.output_padding, m.groups, m.dilation)
+            if ops.act_glue_supported(y):
+                x = ops.bias_act(y, m.bias, "gelu")
+            else:
+                x = mods[i + 1](y + m.bias.to(y.dtype)[None, :, None, None])
+            i += 2
+            continue
+        x = m(x)
+        i += 1
+    return x
 
 
 def _stride_list(s) -> List[int]:
@@ -346,7 +382,8 @@ class SqueezeUnetActorCritic(_PaddedEnds):
         self._init_padding(in_channels, n_logits, obs_hw, self.encoders[0][0], self.actor)
 
     def _values(self, x: torch.Tensor) -> torch.Tensor:
-        v = self.critics[0](x) if self.shared_critic_head else torch.cat([c(x) for c in self.critics], dim=1)
+        v = (_run_glued(self.critics[0], x) if self.shared_critic_head
+             else torch.cat([_run_glued(c, x) for c in self.critics], dim=1))
         if any(a != "identity" for a in self.critic_activations):  # ChannelwiseActivation: one activation per head
             v = torch.stack([_apply_activation(a, v[:, i]) for i, a in enumerate(self.critic_activations)], dim=1)
         return v.squeeze(-1) if self.n_values == 1 else v
@@ -357,14 +394,18 @@ class SqueezeUnetActorCritic(_PaddedEnds):
         if self.obs_range != 1.0:
             x = x / self.obs_range  # backbone_actor_critic.py:189-192
         stem = self.encoders[0]
-        x = stem[1:](F.conv2d(x, w0, stem[0].bias, padding=1))
+        y = F.conv2d(x, w0, None, padding=1) if FUSED_GLUE and x.is_cuda else None
+        if y is not None and ops.act_glue_supported(y):
+            x = _run_glued(stem[2:], ops.bias_act(y, stem[0].bias, "gelu"))
+        else:
+            x = stem[1:](F.conv2d(x, w0, stem[0].bias, padding=1))
         skips = [x]
         for enc in list(self.encoders)[1:]:
-            x = enc(x)
+            x = _run_glued(enc, x)
             skips.append(x)
-        x = self.decoders[0](skips[-1])
+        x = _run_glued(self.decoders[0], skips[-1])
         for skip, dec in zip(reversed(skips[:-1]), list(self.decoders)[1:]):
-            x = dec(skip + x)
+            x = _run_glued(dec, skip + x)
         logits = F.conv2d(x, wh, bh, padding=1).permute(0, 2, 3, 1)  # [B, H, W, Lp]
         return HeadOutputs(logits, self._values(x))
 

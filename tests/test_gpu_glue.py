@@ -183,3 +183,118 @@ def test_gridnet_trunk_fused_glue_equals_torch_modules(cuda, monkeypatch, tf32):
     else:
         close(captured.pi, want.pi, rtol=1e-6, what="captured logits")
         close(captured.values, want.values, rtol=1e-6, what="captured values")
+
+
+# ---- K9: squeeze U-net glue (float32 / bfloat16) --------------------------------------------------------------------
+def _bias_act_ref(y, bias, act):
+    v = y + bias.to(y.dtype)[None, :, None, None]
+    return F.gelu(v) if act == "gelu" else (F.relu(v) if act == "relu" else v)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(4, 128, 16, 16), (3, 24, 5, 7), (2, 6, 3, 3), (0, 8, 2, 2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("act", ["gelu", "relu", "none"])
+def test_bias_act_matches_torch(cuda, N, C, H, W, dtype, act):
+    """Forward bit-exact against the PyTorch chain in the map's dtype (bias rounded as autocast rounds it, the sum rounded
+    before the activation); backward to the dtype's precision, bias gradient against the float32 column sums."""
+    from rl_algo_impls_b200 import ops
+
+    y = _map((N, C, H, W), cuda, 11, sparse=False).to(dtype).requires_grad_(True)
+    bias = (torch.randn(C, device=cuda) * 0.5).requires_grad_(True)
+    y2, b2 = y.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
+    got = ops.bias_act(y, bias, act)
+    want = _bias_act_ref(y2, b2, act)
+    assert got.dtype == dtype and torch.equal(got, want)
+    if N == 0:
+        return
+    dout = _map(tuple(want.shape), cuda, 12, sparse=False).to(dtype)
+    got.backward(dout)
+    want.backward(dout)
+    tol = 1e-6 if dtype == torch.float32 else 2 ** -7
+    close(y.grad, y2.grad, rtol=tol, what="dx")
+    close(bias.grad, b2.grad, rtol=1e-5 if dtype == torch.float32 else 2e-2, what="dbias")
+    # the bias gradient is the float32 column sum of the input gradient
+    close(bias.grad, y.grad.float().sum((0, 2, 3)), rtol=1e-5, what="dbias vs column sums")
+
+
+class _TorchSEBlock(torch.nn.Module):
+    """The PyTorch modules the fused tail replaces (networks._SEResBlock with FUSED_GLUE off)."""
+
+    def __init__(self, c):
+        super().__init__()
+        from rl_algo_impls_b200.policy import networks
+
+        self.block = networks._SEResBlock(c)
+
+    def forward(self, x):
+        from rl_algo_impls_b200.policy import networks
+
+        keep, networks.FUSED_GLUE = networks.FUSED_GLUE, False
+        try:
+            return self.block(x)
+        finally:
+            networks.FUSED_GLUE = keep
+
+
+@pytest.mark.parametrize("N,C,H,W", [(6, 128, 16, 16), (3, 32, 8, 8), (2, 48, 5, 3)])
+@pytest.mark.parametrize("autocast", [False, True])
+def test_se_residual_block_fused_equals_torch_modules(cuda, monkeypatch, N, C, H, W, autocast):
+    """One SE-residual block, fused (bias_act + se_tail) against its PyTorch modules on the same weights: outputs and every
+    gradient.  float32: full-precision convolutions, outputs 1e-6 (the squeeze mean is summed in another order), gradients
+    1e-5.  bfloat16 autocast: bf16 bars (the fused path rounds at the same points, sums in float32)."""
+    from rl_algo_impls_b200.policy import networks
+
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(networks, "FUSED_GLUE", True)
+    torch.manual_seed(3)
+    ref = _TorchSEBlock(C).to(cuda).to(memory_format=torch.channels_last)
+    for p in ref.parameters():  # non-trivial biases and gates
+        if p.dim() == 1:
+            torch.nn.init.normal_(p, std=0.3)
+    x0 = _map((N, C, H, W), cuda, 21, sparse=False)
+    dout = _map((N, C, H, W), cuda, 22, sparse=False)
+    res = []
+    for fused in (True, False):
+        x = x0.clone().requires_grad_(True)
+        ref.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            xin = F.gelu(x * 1.0) if not autocast else F.gelu((x * 1.0).to(torch.bfloat16))  # a map of the block's dtype
+            out = ref.block(xin) if fused else ref(xin)
+        out.backward(dout.to(out.dtype))
+        res.append((out.detach().float(), x.grad.clone(), {n: p.grad.clone() for n, p in ref.named_parameters()}))
+    (o1, gx1, gp1), (o0, gx0, gp0) = res
+    if autocast:
+        close(o1, o0, rtol=2 ** -7, what="out (bf16)")
+        close(gx1, gx0, rtol=3e-2, what="dx (bf16)")
+        for n in gp0:
+            close(gp1[n], gp0[n], rtol=5e-2, what=n + " (bf16)")
+    else:
+        close(o1, o0, rtol=1e-6, what="out")
+        close(gx1, gx0, rtol=1e-5, what="dx")
+        for n in gp0:
+            close(gp1[n], gp0[n], rtol=2e-5, what=n)
+
+
+def test_squeeze_unet_fused_glue_equals_torch_modules(cuda, monkeypatch):
+    """The whole squeeze U-net (a small Lux-shaped one), fused against PyTorch modules: float32, full-precision
+    convolutions; logits / values 1e-5, parameter gradients 1e-4 of their scale."""
+    from rl_algo_impls_b200.policy import networks
+
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    torch.manual_seed(0)
+    net = networks.SqueezeUnetActorCritic(75, 29, channels_per_level=[32, 32, 32], strides_per_level=[4, 4],
+                                          deconv_strides_per_level=[[2, 2], [2, 2]], encoder_residual_blocks_per_level=[2, 1, 1],
+                                          decoder_residual_blocks_per_level=[1, 2], critic_channels=32,
+                                          critic_activations=["identity"] * 3, shared_critic_head=True, obs_hw=(32, 32)).to(cuda)
+    obs = (torch.rand((5, 75, 32, 32), device=cuda) < 0.1).float()
+    res = []
+    for fused in (True, False):
+        monkeypatch.setattr(networks, "FUSED_GLUE", fused)
+        net.zero_grad(set_to_none=True)
+        out = net(obs)
+        (out.pi.square().mean() + out.values.square().mean()).backward()
+        res.append((out.pi.detach().clone(), out.values.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters()}))
+    close(res[0][0], res[1][0], rtol=1e-5, what="logits")
+    close(res[0][1], res[1][1], rtol=1e-5, what="values")
+    for n in res[0][2]:
+        close(res[0][2][n], res[1][2][n], rtol=1e-4, what=n)
