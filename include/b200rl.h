@@ -437,8 +437,9 @@ int b200rl_nhwc_bias_relu_bwd(const float* dout, const float* out /*nullable*/, 
  *   SE tail of a residual block, out = gelu(x + (y2 + b2) * gate[n, c]) over [N, HW, C]:
  *     b200rl_se_mean_sums       sums[n, c] = sum over hw of y2 (the caller adds b2 and divides: the squeeze mean);
  *     b200rl_se_tail_fwd        the gated residual sum + output activation in one pass;
- *     b200rl_se_tail_gate_grad  dgate[n, c] = sum over hw of dz * (y2 + b2), dz = dout * gelu'(z);
- *     b200rl_se_tail_bwd        dx = dz, dy2 = dz * gate + dmean[n, c] (dmean: the mean path's gradient, already / HW),
+ *     b200rl_se_tail_gate_grad  dgate[n, c] = sum over hw of dz * (y2 + b2), dz = dout * gelu'(z); dz is left in dx (it IS
+ *                               the block input's gradient through the residual sum);
+ *     b200rl_se_tail_bwd        dy2 = dz * gate + dmean[n, c] (dmean: the mean path's gradient, already / HW),
  *                               db2 (nullable) = column sums of dy2.
  *   The two linears of the gate ([N, C] x [C, C/16]) stay library GEMMs on the host side of the ABI. */
 size_t b200rl_nhwc_bias_act_workspace_bytes(int64_t rows, int64_t C);
@@ -453,11 +454,11 @@ int b200rl_se_mean_sums(const void* y2, float* sums, void* workspace, size_t wor
 int b200rl_se_tail_fwd(const void* x, const void* y2, const float* b2, const void* gate, void* out, int64_t N, int64_t HW,
                        int64_t C, int dtype, b200rl_stream_t stream);
 int b200rl_se_tail_gate_grad(const void* dout, const void* x, const void* y2, const float* b2, const void* gate,
-                             float* dgate, void* workspace, size_t workspace_bytes, int64_t N, int64_t HW, int64_t C,
-                             int dtype, b200rl_stream_t stream);
-int b200rl_se_tail_bwd(const void* dout, const void* x, const void* y2, const float* b2, const void* gate,
-                       const float* dmean, void* dx, void* dy2, float* db2 /*nullable*/, void* workspace,
-                       size_t workspace_bytes, int64_t N, int64_t HW, int64_t C, int dtype, b200rl_stream_t stream);
+                             float* dgate, void* dx /*out: dz*/, void* workspace, size_t workspace_bytes, int64_t N,
+                             int64_t HW, int64_t C, int dtype, b200rl_stream_t stream);
+int b200rl_se_tail_bwd(const void* dz, const void* gate, const float* dmean, void* dy2, float* db2 /*nullable*/,
+                       void* workspace, size_t workspace_bytes, int64_t N, int64_t HW, int64_t C, int dtype,
+                       b200rl_stream_t stream);
 
 #ifdef __cplusplus
 }

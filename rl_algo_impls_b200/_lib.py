@@ -153,8 +153,8 @@ PROTOTYPES = {
     "b200rl_se_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "b200rl_se_mean_sums": (_int, [_vp, _vp, _vp, _sz, _i64, _i64, _i64, _int, _vp]),
     "b200rl_se_tail_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _vp]),
-    "b200rl_se_tail_gate_grad": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i64, _i64, _i64, _int, _vp]),
-    "b200rl_se_tail_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i64, _i64, _i64, _int, _vp]),
+    "b200rl_se_tail_gate_grad": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i64, _i64, _i64, _int, _vp]),
+    "b200rl_se_tail_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i64, _i64, _i64, _int, _vp]),
     "b200rl_h2d_batch": (_int, [_int, C.POINTER(_vp), C.POINTER(_vp), c_i64p, _vp]),
     "b200rl_nhwc_bias_grad_workspace_bytes": (_sz, [_i64, _i64]),
     "b200rl_nhwc_bias_pool_relu_fwd": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _int, _int, _vp]),

@@ -91,22 +91,43 @@ __global__ void __launch_bounds__(kActBlock) bias_act_fwd_kernel(const T* x, con
   store_elems<T, VEC>(out + i * VEC, v);
 }
 
-template <typename T, int VEC, int ACT>
+// Grid-stride; with SUMS (kActBlock % Cv == 0, so a thread keeps its channel vector across iterations) the CTA also
+// leaves the column sums of the (rounded) gradients it wrote in partial[blockIdx.x][C]: the bias gradient needs no pass
+// of its own over dx.
+template <typename T, int VEC, int ACT, bool SUMS>
 __global__ void __launch_bounds__(kActBlock) bias_act_bwd_kernel(const T* dout, const T* x, const float* bias, T* dx,
-                                                                 long long n_vec, int Cv) {
-  const long long i = (long long)blockIdx.x * kActBlock + threadIdx.x;
-  if (i >= n_vec) return;
-  float g[VEC], v[VEC];
-  load_elems<T, VEC>(dout + i * VEC, g);
-  load_elems<T, VEC>(x + i * VEC, v);
-  const int c = (int)(i % Cv) * VEC;
+                                                                 long long n_vec, int Cv, float* partial) {
+  __shared__ float s_acc[SUMS ? kActBlock * 8 : 1];
+  float acc[VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    const float pre = round_to<T>(v[j] + round_to<T>(bias[c + j]));
-    if constexpr (ACT == kActGelu) g[j] = g[j] * gelu_grad_f(pre);
-    if constexpr (ACT == kActRelu) g[j] = pre <= 0.f ? 0.f : g[j];
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  const long long stride = (long long)gridDim.x * kActBlock;
+  for (long long i = (long long)blockIdx.x * kActBlock + threadIdx.x; i < n_vec; i += stride) {
+    float g[VEC], v[VEC];
+    load_elems<T, VEC>(dout + i * VEC, g);
+    load_elems<T, VEC>(x + i * VEC, v);
+    const int c = (int)(i % Cv) * VEC;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float pre = round_to<T>(v[j] + round_to<T>(bias[c + j]));
+      if constexpr (ACT == kActGelu) g[j] = g[j] * gelu_grad_f(pre);
+      if constexpr (ACT == kActRelu) g[j] = pre <= 0.f ? 0.f : g[j];
+      if constexpr (SUMS) acc[j] += round_to<T>(g[j]);
+    }
+    store_elems<T, VEC>(dx + i * VEC, g);
   }
-  store_elems<T, VEC>(dx + i * VEC, g);
+  if constexpr (SUMS) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s_acc[threadIdx.x * 8 + j] = acc[j];
+    __syncthreads();
+    if ((int)threadIdx.x < Cv) {
+      for (int q = 1; q < kActBlock / Cv; ++q)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] += s_acc[(q * Cv + threadIdx.x) * 8 + j];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) partial[(long long)blockIdx.x * Cv * VEC + threadIdx.x * VEC + j] = acc[j];
+    }
+  }
 }
 
 // ---- column sums of a [rows, C] map of T (bias gradients), float32, two stages, fixed order -------------------------
@@ -262,8 +283,10 @@ __global__ void __launch_bounds__(kActBlock) se_rowsum_kernel(const SeDev G) {
         for (int j = 0; j < VEC; ++j) {
           const float u = round_to<T>(v[j] + b[j]);
           const float z = round_to<T>(xv[j] + round_to<T>(u * sg[j]));
-          acc[j] += g[j] * gelu_grad_f(z) * u;
+          g[j] = g[j] * gelu_grad_f(z);  // dz: the gradient of the block's input through the residual sum, as it is
+          acc[j] += g[j] * u;
         }
+        store_elems<T, VEC>(static_cast<T*>(G.out) + o, g);
       }
     }
   }
@@ -290,7 +313,8 @@ __global__ void __launch_bounds__(kActBlock) se_fold_kernel(const float* partial
   out[i] = acc;
 }
 
-// forward: out = rT(gelu(rT(x + rT(rT(y2 + b2) * s))));  backward: dx = dz, dy2 = rT(dz * s + dmean)
+// forward: out = rT(gelu(rT(x + rT(rT(y2 + b2) * s))));  backward (second pass): dy2 = rT(dz * s + dmean) from the dz the
+// gate-gradient pass left in dx
 template <typename T, int VEC, bool BWD>
 __global__ void __launch_bounds__(kActBlock) se_apply_kernel(const SeDev G) {
   const int Cv = G.C / VEC;
@@ -299,30 +323,24 @@ __global__ void __launch_bounds__(kActBlock) se_apply_kernel(const SeDev G) {
   if (i >= n_vec) return;
   const int c = (int)(i % Cv) * VEC;
   const long long n = (i / Cv) / G.HW;
-  float xv[VEC], v[VEC], sg[VEC];
-  load_elems<T, VEC>(static_cast<const T*>(G.x) + i * VEC, xv);
-  load_elems<T, VEC>(static_cast<const T*>(G.y2) + i * VEC, v);
+  float sg[VEC];
   load_elems<T, VEC>(static_cast<const T*>(G.s) + n * G.C + c, sg);
-  float z[VEC];
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    const float u = round_to<T>(v[j] + round_to<T>(G.b2[c + j]));
-    z[j] = round_to<T>(xv[j] + round_to<T>(u * sg[j]));
-  }
   if constexpr (!BWD) {
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) z[j] = gelu_f(z[j]);
-    store_elems<T, VEC>(static_cast<T*>(G.out) + i * VEC, z);
-  } else {
-    float g[VEC], dy[VEC];
-    load_elems<T, VEC>(static_cast<const T*>(G.dout) + i * VEC, g);
+    float xv[VEC], v[VEC], z[VEC];
+    load_elems<T, VEC>(static_cast<const T*>(G.x) + i * VEC, xv);
+    load_elems<T, VEC>(static_cast<const T*>(G.y2) + i * VEC, v);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      g[j] = g[j] * gelu_grad_f(z[j]);  // dz: the residual input's gradient as it is
-      dy[j] = g[j] * sg[j] + G.dmean[n * G.C + c + j];
+      const float u = round_to<T>(v[j] + round_to<T>(G.b2[c + j]));
+      z[j] = gelu_f(round_to<T>(xv[j] + round_to<T>(u * sg[j])));
     }
-    store_elems<T, VEC>(static_cast<T*>(G.out) + i * VEC, g);
-    store_elems<T, VEC>(static_cast<T*>(G.dy2) + i * VEC, dy);
+    store_elems<T, VEC>(static_cast<T*>(G.out) + i * VEC, z);
+  } else {
+    float g[VEC];
+    load_elems<T, VEC>(static_cast<const T*>(G.dout) + i * VEC, g);  // dz
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) g[j] = g[j] * sg[j] + G.dmean[n * G.C + c + j];
+    store_elems<T, VEC>(static_cast<T*>(G.dy2) + i * VEC, g);
   }
 }
 
@@ -347,6 +365,7 @@ static int bias_act_fwd_t(const T* x, const float* bias, T* out, long long rows,
     }                                                                                                      \
   } while (0)
   B200RL_LAUNCH_ACT(bias_act_fwd_kernel, x, bias, out, n_vec, Cv);
+#undef B200RL_LAUNCH_ACT
   return check_launch("nhwc_bias_act_fwd");
 }
 
@@ -355,14 +374,40 @@ static int bias_act_bwd_t(const T* dout, const T* x, const float* bias, T* dx, f
                           long long rows, int C, int act, cudaStream_t st) {
   constexpr int V = Elems<T>::kVec;
   const bool vec = C % V == 0 && al16(dout) && al16(x) && al16(dx);
-  const long long n_vec = rows * C / (vec ? V : 1);
-  B200RL_UNSUPPORTED((n_vec + kActBlock - 1) / kActBlock > 0x7fffffffLL, "nhwc_bias_act_bwd: tensor too large");
-  const unsigned grid = (unsigned)((n_vec + kActBlock - 1) / kActBlock);
   const int Cv = C / (vec ? V : 1);
-  B200RL_LAUNCH_ACT(bias_act_bwd_kernel, dout, x, bias, dx, n_vec, Cv);
-#undef B200RL_LAUNCH_ACT
+  const long long n_vec = rows * Cv;
+  const long long full = (n_vec + kActBlock - 1) / kActBlock;
+  B200RL_UNSUPPORTED(full > 0x7fffffffLL, "nhwc_bias_act_bwd: tensor too large");
+  // the bias gradient rides on the same pass when a thread's channel vector is fixed across its iterations
+  const bool sums = dbias != nullptr && vec && Cv <= kActBlock && kActBlock % Cv == 0;
+  float* partial = nullptr;
+  unsigned grid = (unsigned)full;
+  if (sums) {
+    const long long cap = (long long)device_info().sm_count * 4;
+    grid = (unsigned)(full < cap ? full : cap);
+    B200RL_REQUIRE(ws != nullptr, "nhwc_bias_act_bwd: workspace is null");
+    partial = static_cast<float*>(ws);
+    partial += ((16 - (reinterpret_cast<uintptr_t>(partial) & 15)) & 15) / sizeof(float);
+    const size_t usable = ws_bytes - (size_t)(reinterpret_cast<uint8_t*>(partial) - static_cast<uint8_t*>(ws));
+    B200RL_REQUIRE(usable >= (size_t)grid * C * sizeof(float), "nhwc_bias_act_bwd: workspace too small (%zu < %zu bytes)",
+                   usable, (size_t)grid * C * sizeof(float));
+  }
+#define B200RL_LAUNCH_BWD(VV, SS)                                                                                          \
+  do {                                                                                                                     \
+    if (act == kActGelu) bias_act_bwd_kernel<T, VV, kActGelu, SS><<<grid, kActBlock, 0, st>>>(dout, x, bias, dx, n_vec, Cv, partial); \
+    else if (act == kActRelu) bias_act_bwd_kernel<T, VV, kActRelu, SS><<<grid, kActBlock, 0, st>>>(dout, x, bias, dx, n_vec, Cv, partial); \
+    else bias_act_bwd_kernel<T, VV, kActNone, SS><<<grid, kActBlock, 0, st>>>(dout, x, bias, dx, n_vec, Cv, partial);     \
+  } while (0)
+  if (sums) B200RL_LAUNCH_BWD(V, true);
+  else if (vec) B200RL_LAUNCH_BWD(V, false);
+  else B200RL_LAUNCH_BWD(1, false);
+#undef B200RL_LAUNCH_BWD
   int rc = check_launch("nhwc_bias_act_bwd");
   if (rc || !dbias) return rc;
+  if (sums) {
+    colsum_t_final_kernel<<<(C + 31) / 32, kActBlock, 0, st>>>(partial, dbias, (int)grid, C, nullptr);
+    return check_launch("nhwc_bias_act_bwd (bias gradient)");
+  }
   return launch_colsum_t<T>(dx, dbias, ws, ws_bytes, rows, C, nullptr, st, "nhwc_bias_act_bwd (bias gradient)");
 }
 
@@ -434,6 +479,8 @@ extern "C" size_t b200rl_nhwc_bias_act_workspace_bytes(int64_t rows, int64_t C) 
     b200rl::col_plan(rows, (int)C, vec, &tx, &slabs);
     best = slabs > best ? slabs : best;
   }
+  const int fused = b200rl::device_info().sm_count * 4;  // the backward's own per-CTA partials
+  best = fused > best ? fused : best;
   return (size_t)best * (size_t)C * sizeof(float) + 32;
 }
 
@@ -502,22 +549,21 @@ extern "C" int b200rl_se_tail_fwd(const void* x, const void* y2, const float* b2
 }
 
 extern "C" int b200rl_se_tail_gate_grad(const void* dout, const void* x, const void* y2, const float* b2, const void* gate,
-                                        float* dgate, void* workspace, size_t workspace_bytes, int64_t N, int64_t HW,
+                                        float* dgate, void* dx, void* workspace, size_t workspace_bytes, int64_t N, int64_t HW,
                                         int64_t C, int dtype, b200rl_stream_t stream) {
   using namespace b200rl;
   B200RL_REQUIRE(N >= 0 && HW >= 1 && C >= 1 && C <= (1 << 20), "se_tail_gate_grad: bad shape");
   B200RL_UNSUPPORTED(dtype != B200RL_F32 && dtype != B200RL_BF16, "se_tail_gate_grad: dtype %d", dtype);
   if (N == 0) return B200RL_OK;
-  B200RL_REQUIRE(dout && x && y2 && b2 && gate && dgate, "se_tail_gate_grad: null pointer");
+  B200RL_REQUIRE(dout && x && y2 && b2 && gate && dgate && dx, "se_tail_gate_grad: null pointer");
   SeDev G{};
-  G.dout = dout, G.x = x, G.y2 = y2, G.b2 = b2, G.s = gate, G.sums = dgate, G.N = N, G.HW = HW, G.C = (int)C;
+  G.dout = dout, G.x = x, G.y2 = y2, G.b2 = b2, G.s = gate, G.sums = dgate, G.out = dx, G.N = N, G.HW = HW, G.C = (int)C;
   return dtype == B200RL_BF16 ? se_launch<__nv_bfloat16>(G, 1, (cudaStream_t)stream, workspace, workspace_bytes)
                               : se_launch<float>(G, 1, (cudaStream_t)stream, workspace, workspace_bytes);
 }
 
-extern "C" int b200rl_se_tail_bwd(const void* dout, const void* x, const void* y2, const float* b2, const void* gate,
-                                  const float* dmean, void* dx, void* dy2, float* db2, void* workspace, size_t workspace_bytes,
-                                  int64_t N, int64_t HW, int64_t C, int dtype, b200rl_stream_t stream) {
+extern "C" int b200rl_se_tail_bwd(const void* dz, const void* gate, const float* dmean, void* dy2, float* db2, void* workspace,
+                                  size_t workspace_bytes, int64_t N, int64_t HW, int64_t C, int dtype, b200rl_stream_t stream) {
   using namespace b200rl;
   B200RL_REQUIRE(N >= 0 && HW >= 1 && C >= 1 && C <= (1 << 20), "se_tail_bwd: bad shape");
   B200RL_UNSUPPORTED(dtype != B200RL_F32 && dtype != B200RL_BF16, "se_tail_bwd: dtype %d", dtype);
@@ -526,9 +572,9 @@ extern "C" int b200rl_se_tail_bwd(const void* dout, const void* x, const void* y
     if (db2) cudaMemsetAsync(db2, 0, (size_t)C * sizeof(float), st);
     return check_launch("se_tail_bwd");
   }
-  B200RL_REQUIRE(dout && x && y2 && b2 && gate && dmean && dx && dy2, "se_tail_bwd: null pointer");
+  B200RL_REQUIRE(dz && gate && dmean && dy2, "se_tail_bwd: null pointer");
   SeDev G{};
-  G.dout = dout, G.x = x, G.y2 = y2, G.b2 = b2, G.s = gate, G.dmean = dmean, G.out = dx, G.dy2 = dy2;
+  G.dout = dz, G.s = gate, G.dmean = dmean, G.dy2 = dy2, G.y2 = dy2;  // (y2 only feeds the alignment test of the launcher)
   G.N = N, G.HW = HW, G.C = (int)C;
   int rc = dtype == B200RL_BF16 ? se_launch<__nv_bfloat16>(G, 3, st) : se_launch<float>(G, 3, st);
   if (rc || !db2) return rc;

@@ -1148,10 +1148,11 @@ class _SeTailFn(torch.autograd.Function):
         dt, L = _MAP_DTYPES[y2.dtype], _lib.lib()
         dout = _nhwc(dout if dout.dtype == y2.dtype else dout.to(y2.dtype))
         dgate = torch.empty((N, Cc), dtype=torch.float32, device=y2.device)
+        dx = torch.empty_like(y2, memory_format=torch.channels_last)
         ws = _workspace(L.b200rl_se_workspace_bytes(N, H * W, Cc), y2.device)
         check(_call("b200rl_se_tail_gate_grad", 2, L.b200rl_se_tail_gate_grad, dout.data_ptr(), x.data_ptr(), y2.data_ptr(),
-                    b2.data_ptr(), gate.data_ptr(), dgate.data_ptr(), ws.data_ptr(), ws.numel(), N, H * W, Cc, dt, _stream()),
-              "b200rl_se_tail_gate_grad")
+                    b2.data_ptr(), gate.data_ptr(), dgate.data_ptr(), dx.data_ptr(), ws.data_ptr(), ws.numel(), N, H * W, Cc, dt,
+                    _stream()), "b200rl_se_tail_gate_grad")
         # the gate's two linears backward, float32 on [N, C] / [N, C / 16]
         sf, g1f, h1f, mf = gate.float(), g1.float(), h1.float(), m.float()
         dh2 = dgate * sf * (1.0 - sf)
@@ -1159,13 +1160,12 @@ class _SeTailFn(torch.autograd.Function):
         dh1 = torch.ops.aten.gelu_backward(dh2 @ w2.float(), h1f)
         dw1 = dh1.t() @ mf
         dmean = ((dh1 @ w1.float()) / (H * W)).contiguous()
-        dx = torch.empty_like(y2, memory_format=torch.channels_last)
         dy2 = torch.empty_like(y2, memory_format=torch.channels_last)
         db2 = torch.empty(Cc, dtype=torch.float32, device=y2.device) if ctx.needs_input_grad[2] else None
         ws = _workspace(L.b200rl_nhwc_bias_act_workspace_bytes(N * H * W, Cc), y2.device)
-        check(_call("b200rl_se_tail_bwd", 3 if db2 is not None else 1, L.b200rl_se_tail_bwd, dout.data_ptr(), x.data_ptr(),
-                    y2.data_ptr(), b2.data_ptr(), gate.data_ptr(), dmean.data_ptr(), dx.data_ptr(), dy2.data_ptr(), _ptr(db2),
-                    ws.data_ptr(), ws.numel(), N, H * W, Cc, dt, _stream()), "b200rl_se_tail_bwd")
+        check(_call("b200rl_se_tail_bwd", 3 if db2 is not None else 1, L.b200rl_se_tail_bwd, dx.data_ptr(), gate.data_ptr(),
+                    dmean.data_ptr(), dy2.data_ptr(), _ptr(db2), ws.data_ptr(), ws.numel(), N, H * W, Cc, dt, _stream()),
+              "b200rl_se_tail_bwd")
         return dx, dy2, db2, dw1.to(w1.dtype), dw2.to(w2.dtype)
 
 
