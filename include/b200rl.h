@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200RL_VERSION 101 /* major*100 + minor */
+#define B200RL_VERSION 102 /* major*100 + minor */
 
 #define B200RL_OK 0
 #define B200RL_EINVAL (-1)

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_channel():
     L = _lib.lib()
-    assert L.b200rl_version() == 101
+    assert L.b200rl_version() == 102
     # a null pointer is an argument error, reported through the code + last_error, never a crash
     rc = L.b200rl_gae_scan_f32(None, None, None, None, None, None, None, 1, None, None, 4, 4, 1, None)
     assert rc == -1
