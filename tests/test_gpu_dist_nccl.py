@@ -2,6 +2,7 @@
 single-process update on the concatenated minibatch -- eager path and the three-segment CUDA-graph path with the
 all-reduces between the graph replays.  The worker (tests/dist_worker_nccl.py) holds the assertions."""
 import os
+import re
 import subprocess
 import sys
 
@@ -18,7 +19,8 @@ def test_two_rank_update_equals_the_single_process_update_on_the_concatenated_mi
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dist_worker_nccl.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    reports = [line for line in res.stdout.splitlines() if line.startswith("DIST_REPORT ")]
+    # the two ranks share one stdout: their report lines can land on one line, so count the reports, not the lines
+    reports = ["DIST_REPORT " + body for body in re.findall(r"DIST_REPORT (\{.*?\})", res.stdout)]
     out_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out_dir):  # kept next to the other run artefacts
         with open(os.path.join(out_dir, "dist_nccl_reports.txt"), "w") as f:
