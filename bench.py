@@ -55,6 +55,9 @@ REF_BUDGET_S = 240.0  # the reference arm stops timing new learn_epochs after th
 CPU_SAMPLE = {"C1": (8, 32, 256), "C2": (8, 32, 64), "C3": (512, 16, 2048), "C4": (24, 64, 384), "C5": (2, 8, 16)}
 
 
+EAGER_EVERY = 10  # GridNet configs: every 10th timed step runs its update eagerly (event-timed fused-loss launches)
+
+
 def peak_hbm_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -143,20 +146,26 @@ def loss_kernel_bytes(policy, batch: int, V: int, logits_bytes: int) -> int:
     return batch * per_sample
 
 
-def timed_epochs(algo, gen, steps: int, world: int):
+def timed_epochs(algo, gen, steps: int, world: int, eager_every: int = 0):
     """K learn_epochs bracketed by barrier + synchronize, CUDA events on the launching stream;
-    returns the max-over-ranks elapsed ms."""
+    returns the max-over-ranks elapsed ms.  eager_every > 0: the minibatch updates replay from CUDA graphs (the learner's
+    default) except in every eager_every-th step (the first included), whose update runs eagerly so that the kernel
+    timer's CUDA events bracket its launches -- a replay has no host call to bracket."""
     total = gen.n_steps * gen.vec_env.num_envs
+    graphed = algo.cuda_graph_update
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     elapsed_steps = 0
-    for _ in range(steps):
+    for i in range(steps):
+        if eager_every:
+            algo.cuda_graph_update = graphed and i % eager_every != 0
         elapsed_steps, _ = algo.learn_epoch(elapsed_steps, steps * total, gen, None)
     end.record()
     torch.cuda.synchronize()
+    algo.cuda_graph_update = graphed
     if world > 1:
         dist.barrier()
     ms = torch.tensor([start.elapsed_time(end)], device="cuda", dtype=torch.float64)
@@ -219,13 +228,17 @@ def gpu_leg(cfg, dev, rank: int, world: int, envs_per_gpu: int, steps: int, warm
     from rl_algo_impls_b200.configs import build
 
     env, policy, gen, algo = build(cfg, dev, env_device=dev, seed=1234 + rank, n_envs=envs_per_gpu)
-    # The roofline leg brackets every fused-loss launch with CUDA events, which a graph replay would
-    # hide.  On the GridNet configs the update is GPU-bound on the trunk (measured: graphed 181.2 vs
-    # eager 181.9 ms per C4 step), so their update runs eagerly here; the rollout stays graph-replayed.
-    if policy.kind == "gridnet":
-        algo.cuda_graph_update = False
+    # The roofline leg brackets the fused-loss launches with CUDA events, which a graph replay would hide: on the
+    # GridNet configs one step in EAGER_EVERY runs its update eagerly (timed launches), the others replay the captured
+    # update like the learner does by default (measured on C4: 41.7 ms graphed vs 46.6 ms eager update stage).
+    eager_every = EAGER_EVERY if policy.kind == "gridnet" and algo.cuda_graph_update else 0
+    algo_graphed = bool(algo.cuda_graph_update)
     for _ in range(max(3, warmup)):
         algo.learn_epoch(0, 1 << 40, gen, None)
+    if eager_every:  # the eager path warm as well
+        algo.cuda_graph_update = False
+        algo.learn_epoch(0, 1 << 40, gen, None)
+        algo.cuda_graph_update = True
     algo.profile_stages = True
     algo.learn_epoch(0, 1 << 40, gen, None)
     algo.profile_stages = False
@@ -235,7 +248,7 @@ def gpu_leg(cfg, dev, rank: int, world: int, envs_per_gpu: int, steps: int, warm
     ops.set_kernel_timer(timer)
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ms = timed_epochs(algo, gen, steps, world)
+    ms = timed_epochs(algo, gen, steps, world, eager_every)
     clock_info = clocks.stop()
     ops.set_kernel_timer(None)
     launches = algo.launches_last_epoch * steps
@@ -289,8 +302,12 @@ def gpu_leg(cfg, dev, rank: int, world: int, envs_per_gpu: int, steps: int, warm
         del hgen, henv, halgo
     del algo, policy
     torch.cuda.empty_cache()
+    update_mode = ("minibatch updates replay from CUDA graphs (the learner's default); every %dth timed step (the first "
+                   "included) runs them eagerly so that CUDA events bracket its fused-loss launches: roofline / kernels "
+                   "are those launches" % eager_every) if eager_every else (
+                   "CUDA-graph replays" if algo_graphed else "eager")
     return dict(value=value, ms=ms, clocks=clock_info, launches=launches, roofline=roofline, kernels=kernels,
-                stages=stages, e2e=e2e)
+                stages=stages, e2e=e2e, update_mode=update_mode)
 
 
 def emit(line: dict) -> None:
@@ -370,6 +387,7 @@ def main():
             "config": workload_of(cfg, world, envs_per_gpu, cfg.n_steps, cfg.algo["batch_size"], cfg.algo["n_epochs"]),
             "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["launches"], "roofline": res["roofline"],
             "cpu_baseline": cpu, "kernels": res["kernels"], "stages_ms": res["stages"],
+            "update_mode": res["update_mode"],
         }
         if scale_base is not None:
             line["scale_base"] = scale_base
