@@ -1,6 +1,9 @@
-"""Policy / value trunks.  These stay on PyTorch's own CUDA ops (BASELINE.json north_star): the
-data path only needs modules that turn observations into head outputs (logits or a Gaussian mean,
-and values) so that the fused loss kernels have something real to differentiate through.
+"""Policy / value trunks.  Their convolutions and linears stay on PyTorch's own CUDA ops (cuDNN / cuBLAS; BASELINE.json
+north_star): the data path only needs modules that turn observations into head outputs (logits or a Gaussian mean,
+and values) so that the fused loss kernels have something real to differentiate through.  What runs BETWEEN the
+convolutions of the two grid trunks on the channels-last maps -- bias adds, max-pool, ReLU / GELU, the squeeze-excite
+mean / gate / residual sum -- goes through the fused K8 / K9 ops (``FUSED_GLUE``; bit-identical forward, same modules,
+parameters and state dict).
 
 Architectures follow the families the reference configs name:
 MLP actor-critic (CartPole / HalfCheetah, shared/policy/actor_critic_network/connected_trio.py),
