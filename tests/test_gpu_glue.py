@@ -298,3 +298,41 @@ def test_squeeze_unet_fused_glue_equals_torch_modules(cuda, monkeypatch):
     close(res[0][1], res[1][1], rtol=1e-5, what="values")
     for n in res[0][2]:
         close(res[0][2][n], res[1][2][n], rtol=1e-4, what=n)
+
+
+def test_k9_at_the_c5_minibatch_size(cuda, monkeypatch):
+    """One C5 per-GPU minibatch at encoder level 0 (128 x 128 x 64 x 64, bfloat16 autocast, 134 MB per map): bias + GELU
+    bit-exact against the PyTorch chain; the SE-residual block fused vs its PyTorch modules to bf16 precision; the
+    float32 reductions (bias / gate gradients) deterministic across runs."""
+    from rl_algo_impls_b200 import ops
+    from rl_algo_impls_b200.policy import networks
+
+    monkeypatch.setattr(networks, "FUSED_GLUE", True)
+    N, C, H, W = 128, 128, 64, 64
+    y = _map((N, C, H, W), cuda, 31, sparse=False).to(torch.bfloat16)
+    bias = torch.randn(C, device=cuda) * 0.5
+    assert torch.equal(ops.bias_act(y, bias, "gelu"), F.gelu(y + bias.to(torch.bfloat16)[None, :, None, None]))
+    torch.manual_seed(5)
+    ref = _TorchSEBlock(C).to(cuda).to(memory_format=torch.channels_last)
+    x0 = F.gelu(_map((N, C, H, W), cuda, 32, sparse=False)).to(torch.bfloat16)
+    dout = _map((N, C, H, W), cuda, 33, sparse=False).to(torch.bfloat16)
+    runs = []
+    for mode in ("fused", "fused", "torch"):
+        x = x0.clone().requires_grad_(True)
+        ref.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = ref.block(x) if mode == "fused" else ref(x)
+        out.backward(dout)
+        runs.append((out.detach(), x.grad.detach(), {n: p.grad.clone() for n, p in ref.named_parameters()}))
+        del out
+    (o1, g1, p1), (o2, g2, p2), (o0, g0, p0) = runs
+    # deterministic where only these kernels (and forward convolutions) are upstream: the output, the second
+    # convolution's bias gradient, the gate's linears (cuDNN's dgrad / wgrad make no such promise for the rest)
+    assert torch.equal(o1, o2)
+    for n in p1:
+        if n.endswith("residual.2.bias") or ".fc." in n:
+            assert torch.equal(p1[n], p2[n]), n
+    close(o1.float(), o0.float(), rtol=2 ** -7, what="out")
+    close(g1.float(), g0.float(), rtol=3e-2, what="dx")
+    for n in p0:
+        close(p1[n], p0[n], rtol=5e-2, what=n)
