@@ -55,6 +55,7 @@ REF_BUDGET_S = 240.0  # the reference arm stops timing new learn_epochs after th
 CPU_SAMPLE = {"C1": (8, 32, 256), "C2": (8, 32, 64), "C3": (512, 16, 2048), "C4": (24, 64, 384), "C5": (2, 8, 16)}
 
 
+CUDNN_AUTOTUNE = os.environ.get("B200RL_CUDNN_BENCHMARK", "1") != "0"
 EAGER_EVERY = 10  # GridNet configs: every 10th timed step runs its update eagerly (event-timed fused-loss launches)
 
 
@@ -227,6 +228,12 @@ def gpu_leg(cfg, dev, rank: int, world: int, envs_per_gpu: int, steps: int, warm
     from rl_algo_impls_b200 import ops
     from rl_algo_impls_b200.configs import build
 
+    # The trunk's convolutions stay cuDNN calls; with fixed shapes (one rollout batch, one minibatch size) the library's
+    # own autotuner picks their algorithms during the warm-up steps (measured on C4: 99.6 -> 91.2 ms per step; the
+    # reference's set_seeds() turns it off for run-to-run determinism, runner/running_utils.py:181 -- it changes which
+    # convolution kernel runs, not the arithmetic type).  B200RL_CUDNN_BENCHMARK=0 keeps cuDNN's heuristic choice.
+    torch.backends.cudnn.benchmark = CUDNN_AUTOTUNE
+
     env, policy, gen, algo = build(cfg, dev, env_device=dev, seed=1234 + rank, n_envs=envs_per_gpu)
     # The roofline leg brackets the fused-loss launches with CUDA events, which a graph replay would hide: on the
     # GridNet configs one step in EAGER_EVERY runs its update eagerly (timed launches), the others replay the captured
@@ -381,8 +388,9 @@ def main():
             "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": res["ms"] / args.steps, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-            "dtype": ("bf16 autocast trunk / f32 loss math on bf16 logits" if bf16 else
-                      "f32 (loss kernels, GAE f64 carry); trunk convolutions run cuDNN's default TF32 tensor-op kernels"),
+            "dtype": (("bf16 autocast trunk / f32 loss math on bf16 logits" if bf16 else
+                       "f32 (loss kernels, GAE f64 carry); trunk convolutions run cuDNN's default TF32 tensor-op kernels")
+                      + ("; convolution algorithms autotuned (torch.backends.cudnn.benchmark)" if CUDNN_AUTOTUNE else "")),
             "data": "synthetic",
             "config": workload_of(cfg, world, envs_per_gpu, cfg.n_steps, cfg.algo["batch_size"], cfg.algo["n_epochs"]),
             "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["launches"], "roofline": res["roofline"],
