@@ -4,7 +4,9 @@ Every function takes CUDA tensors, checks dtype / contiguity, and launches on to
 stream.  Nothing here computes on the host and nothing falls back to eager PyTorch: a missing
 library or a CPU tensor raises.
 """
+import contextlib
 import ctypes as C
+import gc
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -96,8 +98,28 @@ def _f32_array(values: Sequence[float]):
 _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
 
 
+@contextlib.contextmanager
+def no_gc_during_capture():
+    """Python's cyclic collector must not run finalizers in the middle of a stream capture: an object from an earlier
+    run (a rollout generator's page-locked host buffers, an old graph's tensors) released then can issue a CUDA call that
+    is illegal under global-mode capture and invalidates it.  Collect first, keep the collector off for the capture."""
+    was_enabled = gc.isenabled()
+    gc.collect()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
 def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    """Per (device, stream) scratch buffer.  Calls on one stream are ordered, so reuse is safe."""
+    """Per (device, stream) scratch buffer.  Calls on one stream are ordered, so reuse is safe.  While a CUDA graph is
+    being captured the scratch is a fresh allocation out of that graph's own pool instead: a cached buffer may belong
+    to the pool of an earlier graph captured on a recycled stream handle, and dropping / regrowing it mid-capture would
+    touch that other pool from inside this capture."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
     key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:

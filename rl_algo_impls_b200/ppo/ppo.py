@@ -195,14 +195,14 @@ class _GraphedUpdate:
         before = ops.LAUNCHES
         if not self.collectives:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self.pool):
+            with ops.no_gc_during_capture(), torch.cuda.graph(g, pool=self.pool):
                 for seg in self.segments:
                     seg()
             self.graphs = [g]
         else:
             for k, seg in enumerate(self.segments):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=self.pool):
+                with ops.no_gc_during_capture(), torch.cuda.graph(g, pool=self.pool):
                     seg()
                 self.graphs.append(g)
         self.kernels_per_replay = ops.LAUNCHES - before

@@ -482,7 +482,7 @@ class SyncStepRolloutGenerator(RolloutGenerator):
 
         graph = torch.cuda.CUDAGraph()
         before = ops.LAUNCHES
-        with torch.cuda.graph(graph):
+        with ops.no_gc_during_capture(), torch.cuda.graph(graph):
             out = fn()
         self._kernels_per_replay = ops.LAUNCHES - before  # libb200rl kernels inside one replay
         return graph, out
