@@ -12,8 +12,11 @@ JSON line (rank 0):
   value      env-steps/s, whole job, device-resident env (nothing crosses PCIe in the timed region)
   e2e        the same metric through the reference-facing contract: a HOST (numpy) VectorEnv, so
              every env step uploads obs / masks / rewards and downloads the sampled actions
-  roofline   the fused GridNet PPO-loss kernel (K4), CUDA events around every launch inside the
-             timed region, algorithmic bytes / mean duration against MEASURED_PEAKS.json
+  roofline   the fused GridNet PPO-loss kernel (K4), CUDA events around its launches inside the
+             timed region, algorithmic bytes / mean duration against MEASURED_PEAKS.json.  The minibatch
+             updates replay from CUDA graphs like the learner's default does; every 10th timed step (the
+             first included) runs them eagerly so that the events have host calls to bracket
+             (``update_mode``, ``roofline.launches_timed``)
   cpu_baseline  the unmodified reference learner (oracle/_ref) timed on the host cores (bounded sample)
 
 Workloads.  N = 1 runs **C4** (GridNet MicroRTS 16x16, 24 envs x 512 steps: the largest config the reference's own CPU
@@ -21,6 +24,10 @@ path can also run at full size) and adds ``scale_base``: the C5 single-GPU point
 (torchrun, one process per GPU) runs **C5** (Lux 64x64, 1024 envs x 32 steps -- the config BASELINE.json names for the
 8-GPU split) with the 1024 envs sharded 1024 / N per GPU: ``"scaling": "strong"``.  Gradients are all-reduced over
 NCCL once per epoch (gradient accumulation); nothing else crosses ranks.  ``--config`` overrides the workload.
+
+The trunk's convolutions stay cuDNN calls whose algorithms the library's autotuner picks during the warm-up steps
+(``torch.backends.cudnn.benchmark``; said in the line's ``dtype``; ``B200RL_CUDNN_BENCHMARK=0`` keeps the heuristic
+choice).
 
 ``--impl reference`` times the UNMODIFIED reference (``rl_algo_impls.ppo.ppo.PPO`` + ``SyncStepRolloutGenerator`` +
 ``ActorCritic`` from oracle/_ref, imported through oracle/ref_shim.py) on the host cores with all threads, on the same
