@@ -310,3 +310,29 @@ def test_reference_copy_matches_its_manifest():
     for digest, rel in entries:
         with open(os.path.join(root, rel.strip()), "rb") as f:
             assert hashlib.sha256(f.read()).hexdigest() == digest, rel
+
+
+def test_no_gc_during_capture_restores_the_collector():
+    """The capture guard collects first, keeps the cyclic collector off inside, and restores its previous state --
+    also when it was off to begin with, and when the body raises."""
+    import gc
+
+    from rl_algo_impls_b200 import ops
+
+    assert gc.isenabled()
+    with ops.no_gc_during_capture():
+        assert not gc.isenabled()
+    assert gc.isenabled()
+    gc.disable()
+    try:
+        with ops.no_gc_during_capture():
+            assert not gc.isenabled()
+        assert not gc.isenabled()
+    finally:
+        gc.enable()
+    try:
+        with ops.no_gc_during_capture():
+            raise RuntimeError("boom")
+    except RuntimeError:
+        pass
+    assert gc.isenabled()
